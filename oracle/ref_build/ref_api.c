@@ -1,0 +1,299 @@
+/* ref_api.c - thin driver over the UNMODIFIED tmLQCD reference objects.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Compiled by oracle/ref_build/Makefile together with
+ * reference sources read in place from /root/reference into oracle/_ref/*.so.
+ * Used (a) to pin the C restatement in oracle/tmoracle.c, (b) to generate the
+ * golden fixtures in tests/golden/, (c) as the "reference" CPU baseline of
+ * bench.py.  The product library (tmlqcd_b200/csrc) never links or loads it.
+ *
+ * It does what benchmark.c:85-262 and tmlqcd_mpi_init (mpi_init.c:321-357) do by
+ * hand for a single process: set T,LX,..,VOLUME, allocate, geometry(), boundary().
+ * Every ref_* entry point takes plain double* buffers in the reference's own AoS
+ * layouts (spinor = 24 doubles, su3 = 18 doubles) and forwards to the reference
+ * function of the same name.
+ */
+#define INIT_GLOBALS
+#include "config.h"
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include <complex.h>
+#ifdef TM_USE_OMP
+#include <omp.h>
+#endif
+#include "global.h"
+#include "su3.h"
+#include "geometry_eo.h"
+#include "boundary.h"
+extern double X0, X1, X2, X3; /* read_input.h:65, defined in boundary.c:37 */
+#include "start.h"
+#include "ranlxd.h"
+#include "gamma.h"
+#include "gettime.h"
+#include "update_backward_gauge.h"
+#include "init/init_gauge_field.h"
+#include "init/init_geometry_indices.h"
+#include "init/init_spinor_field.h"
+#include "init/init_dirac_halfspinor.h"
+#include "init/init_openmp.h"
+#include "operator/Hopping_Matrix.h"
+#include "operator/Hopping_Matrix_nocom.h"
+#include "operator/tm_times_Hopping_Matrix.h"
+#include "operator/tm_sub_Hopping_Matrix.h"
+#include "operator/tm_operators.h"
+#include "operator/tm_operators_nd.h"
+#include "operator/D_psi.h"
+#include "linalg_eo.h"
+#include "solver/matrix_mult_typedef.h"
+#include "solver/matrix_mult_typedef_nd.h"
+#include "solver/cg_her.h"
+#include "solver/cg_her_nd.h"
+
+/* phmc.c is not compiled (drags in the whole PHMC); tm_operators_nd.c only needs these
+ * scalars from it (phmc.h). */
+double phmc_invmaxev = 1.0;
+double phmc_cheb_evmin, phmc_cheb_evmax, phmc_Cpol;
+int phmc_dop_n_cheby;
+double *phmc_dop_cheby_coef;
+int phmc_ptilde_n_cheby;
+double *phmc_ptilde_cheby_coef;
+_Complex double *phmc_root;
+double phmc_stilde_low, phmc_stilde_max;
+int phmc_exact_poly;
+
+static int ref_initialised = 0;
+#define NSF 24 /* g_spinor_field slots: user 0..7, DUM_DERI 8..15, DUM_MATRIX 16..23 */
+
+int ref_init(int t, int lx, int ly, int lz, int nthreads) {
+  if (ref_initialised) {
+    if (t == T && lx == LX && ly == LY && lz == LZ) return 0;
+    fprintf(stderr, "ref_init: already initialised with another lattice\n");
+    return -1;
+  }
+  T = t; L = lx; LX = lx; LY = ly; LZ = lz; T_global = t;
+  N_PROC_T = N_PROC_X = N_PROC_Y = N_PROC_Z = 1;
+  g_nproc = g_nproc_t = g_nproc_x = g_nproc_y = g_nproc_z = 1;
+  g_proc_id = 0; g_cart_id = 0; g_stdio_proc = 0;
+  for (int i = 0; i < 4; i++) g_proc_coords[i] = 0;
+  VOLUME = T * LX * LY * LZ; RAND = 0; EDGES = 0; VOLUMEPLUSRAND = VOLUME;
+  SPACEVOLUME = LX * LY * LZ; SPACERAND = 0;
+  g_dbw2rand = 0; g_debug_level = 0; g_sloppy_precision_flag = 0; g_sloppy_precision = 0;
+  g_rgi_C1 = 0.; g_c_sw = 0.; g_use_clover_flag = 0; lowmem_flag = 0;
+  DUM_DERI = 8; DUM_MATRIX = 16; NO_OF_SPINORFIELDS = NSF;
+#ifdef TM_USE_OMP
+  omp_num_threads = nthreads > 0 ? nthreads : 1;
+  init_openmp();
+#else
+  (void)nthreads;
+#endif
+  if (init_gauge_field(VOLUMEPLUSRAND, 1) != 0) return -2;
+  if (init_geometry_indices(VOLUMEPLUSRAND) != 0) return -3;
+  /* full-volume sized slots so that D_psi (lexicographic, V sites) can use them too */
+  if (init_spinor_field(VOLUMEPLUSRAND, NSF) != 0) return -4;
+  geometry();
+  g_kappa = 0.16; g_mu = 0.0; X0 = X1 = X2 = X3 = 0.;
+  boundary(g_kappa);
+#ifdef _USE_HALFSPINOR
+  if (init_dirac_halfspinor() != 0) return -5;
+#endif
+  g_update_gauge_copy = 1;
+  ref_initialised = 1;
+  return 0;
+}
+
+int ref_num_threads(void) {
+#ifdef TM_USE_OMP
+  return omp_num_threads;
+#else
+  return 1;
+#endif
+}
+
+int ref_is_halfspinor(void) {
+#ifdef _USE_HALFSPINOR
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+/* g_mu is 2*kappa*mu (invert_eo.c:255, operator.c:337) */
+void ref_set_params(double kappa, double gmu, double x0, double x1, double x2, double x3) {
+  g_kappa = kappa; g_mu = gmu; X0 = x0; X1 = x1; X2 = x2; X3 = x3;
+  boundary(g_kappa);
+}
+void ref_set_nd_params(double mubar, double epsbar, double invmaxev) {
+  g_mubar = mubar; g_epsbar = epsbar; phmc_invmaxev = invmaxev;
+}
+void ref_set_debug_level(int l) { g_debug_level = l; }
+
+void ref_start_ranlux(int level, int seed) { start_ranlux(level, seed); }
+/* benchmark.c:247-248 */
+void ref_random_gauge(int seed) {
+  start_ranlux(1, seed);
+  random_gauge_field(1, g_gauge_field);
+  g_update_gauge_copy = 1;
+}
+void ref_get_gauge(double *out) { memcpy(out, g_gauge_field[0], (size_t)VOLUME * 4 * sizeof(su3)); }
+void ref_set_gauge(const double *in) {
+  memcpy(g_gauge_field[0], in, (size_t)VOLUME * 4 * sizeof(su3));
+  g_update_gauge_copy = 1;
+}
+/* benchmark.c:259 */
+void ref_random_spinor_eo(double *out) { random_spinor_field_eo((spinor *)out, 1, RN_GAUSS); }
+void ref_random_spinor_lexic(double *out) { random_spinor_field_lexic((spinor *)out, 1, RN_GAUSS); }
+
+void ref_get_eo2lexic(int *out) { memcpy(out, g_eo2lexic, (size_t)VOLUME * sizeof(int)); }
+void ref_get_lexic2eosub(int *out) { memcpy(out, g_lexic2eosub, (size_t)VOLUME * sizeof(int)); }
+void ref_get_hi(int *out) { memcpy(out, g_hi, (size_t)VOLUME * 16 * sizeof(int)); }
+void ref_get_iup(int *out) { for (int i = 0; i < VOLUME; i++) for (int m = 0; m < 4; m++) out[4 * i + m] = g_iup[i][m]; }
+void ref_get_idn(int *out) { for (int i = 0; i < VOLUME; i++) for (int m = 0; m < 4; m++) out[4 * i + m] = g_idn[i][m]; }
+void ref_get_ka(double *out) {
+  _Complex double k[4] = {ka0, ka1, ka2, ka3};
+  for (int i = 0; i < 4; i++) { out[2 * i] = creal(k[i]); out[2 * i + 1] = cimag(k[i]); }
+}
+
+/* ---- operators (a6..a19) ---- */
+void ref_Hopping_Matrix(int ieo, double *l, double *k) { Hopping_Matrix(ieo, (spinor *)l, (spinor *)k); }
+void ref_tm_times_Hopping_Matrix(int ieo, double *l, double *k, double cre, double cim) {
+  tm_times_Hopping_Matrix(ieo, (spinor *)l, (spinor *)k, cre + cim * I);
+}
+void ref_tm_sub_Hopping_Matrix(int ieo, double *l, double *p, double *k, double cre, double cim) {
+  tm_sub_Hopping_Matrix(ieo, (spinor *)l, (spinor *)p, (spinor *)k, cre + cim * I);
+}
+void ref_H_eo_tm_inv_psi(double *l, double *k, int ieo, double sign) { H_eo_tm_inv_psi((spinor *)l, (spinor *)k, ieo, sign); }
+void ref_Qtm_pm_psi(double *l, double *k) { Qtm_pm_psi((spinor *)l, (spinor *)k); }
+void ref_Qtm_plus_psi(double *l, double *k) { Qtm_plus_psi((spinor *)l, (spinor *)k); }
+void ref_Qtm_minus_psi(double *l, double *k) { Qtm_minus_psi((spinor *)l, (spinor *)k); }
+void ref_Mtm_plus_psi(double *l, double *k) { Mtm_plus_psi((spinor *)l, (spinor *)k); }
+void ref_Mtm_minus_psi(double *l, double *k) { Mtm_minus_psi((spinor *)l, (spinor *)k); }
+void ref_M_full(double *en, double *on, double *e, double *o) { M_full((spinor *)en, (spinor *)on, (spinor *)e, (spinor *)o); }
+void ref_Q_full(double *en, double *on, double *e, double *o) { Q_full((spinor *)en, (spinor *)on, (spinor *)e, (spinor *)o); }
+void ref_D_psi(double *p, double *q) { D_psi((spinor *)p, (spinor *)q); }
+void ref_Q_pm_psi(double *l, double *k) { Q_pm_psi((spinor *)l, (spinor *)k); }
+void ref_gamma5(double *l, double *k, int n) { gamma5((spinor *)l, (spinor *)k, n); }
+void ref_mul_one_pm_imu_inv(double *l, double sign, int n) { mul_one_pm_imu_inv((spinor *)l, sign, n); }
+void ref_assign_mul_one_pm_imu_inv(double *l, double *k, double sign, int n) { assign_mul_one_pm_imu_inv((spinor *)l, (spinor *)k, sign, n); }
+void ref_assign_mul_one_pm_imu(double *l, double *k, double sign, int n) { assign_mul_one_pm_imu((spinor *)l, (spinor *)k, sign, n); }
+void ref_mul_one_pm_imu_sub_mul_gamma5(double *l, double *k, double *j, double sign) {
+  mul_one_pm_imu_sub_mul_gamma5((spinor *)l, (spinor *)k, (spinor *)j, sign);
+}
+void ref_convert_eo_to_lexic(double *p, double *s, double *r) { convert_eo_to_lexic((spinor *)p, (spinor *)s, (spinor *)r); }
+void ref_convert_lexic_to_eo(double *s, double *r, double *p) { convert_lexic_to_eo((spinor *)s, (spinor *)r, (spinor *)p); }
+
+/* ---- BLAS-1 (a20..a25) ---- */
+double ref_square_norm(double *p, int n) { return square_norm((spinor *)p, n, 1); }
+double ref_scalar_prod_r(double *s, double *r, int n) { return scalar_prod_r((spinor *)s, (spinor *)r, n, 1); }
+void ref_assign_add_mul_r(double *p, double *q, double c, int n) { assign_add_mul_r((spinor *)p, (spinor *)q, c, n); }
+void ref_assign_mul_add_r(double *r, double c, double *s, int n) { assign_mul_add_r((spinor *)r, c, (spinor *)s, n); }
+double ref_assign_mul_add_r_and_square(double *r, double c, double *s, int n) {
+  return assign_mul_add_r_and_square((spinor *)r, c, (spinor *)s, n, 1);
+}
+void ref_diff(double *q, double *r, double *s, int n) { diff((spinor *)q, (spinor *)r, (spinor *)s, n); }
+void ref_assign(double *r, double *s, int n) { assign((spinor *)r, (spinor *)s, n); }
+void ref_mul_r(double *r, double c, double *s, int n) { mul_r((spinor *)r, c, (spinor *)s, n); }
+
+/* ---- solvers ---- */
+int ref_cg_her(double *p, double *q, int max_iter, double eps_sq, int rel_prec) {
+  return cg_her((spinor *)p, (spinor *)q, max_iter, eps_sq, rel_prec, VOLUME / 2, &Qtm_pm_psi);
+}
+
+/* The CG branch of invert_eo restated on top of the compiled reference functions:
+ * invert_eo.c:152-157, :252, :268-270, :306-310 (invert_eo.c itself needs c-lime headers
+ * and every other solver to link).  Returns the cg_her iteration count. */
+int ref_invert_eo_cg(double *even_new, double *odd_new, double *even, double *odd,
+                     double precision, int max_iter, int rel_prec) {
+  spinor *En = (spinor *)even_new, *On = (spinor *)odd_new, *E = (spinor *)even, *O = (spinor *)odd;
+  int iter;
+  assign_mul_one_pm_imu_inv(En, E, +1., VOLUME / 2);
+  Hopping_Matrix(OE, g_spinor_field[DUM_DERI], En);
+  assign_mul_add_r(g_spinor_field[DUM_DERI], +1., O, VOLUME / 2);
+  gamma5(g_spinor_field[DUM_DERI], g_spinor_field[DUM_DERI], VOLUME / 2);
+  iter = cg_her(On, g_spinor_field[DUM_DERI], max_iter, precision, rel_prec, VOLUME / 2, &Qtm_pm_psi);
+  Qtm_minus_psi(On, On);
+  Hopping_Matrix(EO, g_spinor_field[DUM_DERI], On);
+  mul_one_pm_imu_inv(g_spinor_field[DUM_DERI], +1., VOLUME / 2);
+  assign_add_mul_r(En, g_spinor_field[DUM_DERI], +1., VOLUME / 2);
+  return iter;
+}
+
+/* ---- ND doublet (a29, a30) ---- */
+void ref_Qtm_pm_ndpsi(double *ls, double *lc, double *ks, double *kc) {
+  Qtm_pm_ndpsi((spinor *)ls, (spinor *)lc, (spinor *)ks, (spinor *)kc);
+}
+void ref_Qtm_ndpsi(double *ls, double *lc, double *ks, double *kc) {
+  Qtm_ndpsi((spinor *)ls, (spinor *)lc, (spinor *)ks, (spinor *)kc);
+}
+void ref_Qtm_dagger_ndpsi(double *ls, double *lc, double *ks, double *kc) {
+  Qtm_dagger_ndpsi((spinor *)ls, (spinor *)lc, (spinor *)ks, (spinor *)kc);
+}
+void ref_M_ee_inv_ndpsi(double *ls, double *lc, double *ks, double *kc, double mu, double eps) {
+  M_ee_inv_ndpsi((spinor *)ls, (spinor *)lc, (spinor *)ks, (spinor *)kc, mu, eps);
+}
+int ref_cg_her_nd(double *ps, double *pc, double *qs, double *qc, int max_iter, double eps_sq, int rel_prec) {
+  return cg_her_nd((spinor *)ps, (spinor *)pc, (spinor *)qs, (spinor *)qc, max_iter, eps_sq, rel_prec,
+                   VOLUME / 2, &Qtm_pm_ndpsi);
+}
+/* invert_doublet_eo.c:102-178 restated on the compiled reference functions (NO_EXT_INV, CG). */
+int ref_invert_doublet_eo_cg(double *ens, double *ons, double *enc, double *onc,
+                             double *es, double *os, double *ec, double *oc,
+                             double precision, int max_iter, int rel_prec) {
+  spinor *Ens = (spinor *)ens, *Ons = (spinor *)ons, *Enc = (spinor *)enc, *Onc = (spinor *)onc;
+  spinor *Es = (spinor *)es, *Os = (spinor *)os, *Ec = (spinor *)ec, *Oc = (spinor *)oc;
+  int iter;
+  M_ee_inv_ndpsi(Ens, Enc, Es, Ec, g_mubar, g_epsbar);
+  Hopping_Matrix(OE, g_spinor_field[DUM_DERI], Ens);
+  Hopping_Matrix(OE, g_spinor_field[DUM_DERI + 1], Enc);
+  assign_mul_add_r(g_spinor_field[DUM_DERI], +1., Os, VOLUME / 2);
+  assign_mul_add_r(g_spinor_field[DUM_DERI + 1], +1., Oc, VOLUME / 2);
+  gamma5(g_spinor_field[DUM_DERI], g_spinor_field[DUM_DERI], VOLUME / 2);
+  gamma5(g_spinor_field[DUM_DERI + 1], g_spinor_field[DUM_DERI + 1], VOLUME / 2);
+  iter = cg_her_nd(Ons, Onc, g_spinor_field[DUM_DERI], g_spinor_field[DUM_DERI + 1], max_iter, precision,
+                   rel_prec, VOLUME / 2, &Qtm_pm_ndpsi);
+  Qtm_dagger_ndpsi(Ons, Onc, Ons, Onc);
+  Hopping_Matrix(EO, g_spinor_field[DUM_DERI], Ons);
+  Hopping_Matrix(EO, g_spinor_field[DUM_DERI + 1], Onc);
+  M_ee_inv_ndpsi(g_spinor_field[DUM_DERI + 2], g_spinor_field[DUM_DERI + 3], g_spinor_field[DUM_DERI],
+                 g_spinor_field[DUM_DERI + 1], g_mubar, g_epsbar);
+  assign_add_mul_r(Ens, g_spinor_field[DUM_DERI + 2], +1., VOLUME / 2);
+  assign_add_mul_r(Enc, g_spinor_field[DUM_DERI + 3], +1., VOLUME / 2);
+  return iter;
+}
+
+/* ---- timing, the benchmark.c:262-327 recipe: nreps x { H(0, sf1, sf0); H(1, sf2, sf1) } ---- */
+double ref_bench_hopping(int nreps) {
+  double t1, t2;
+  random_spinor_field_eo(g_spinor_field[0], 1, RN_GAUSS);
+  Hopping_Matrix(0, g_spinor_field[1], g_spinor_field[0]); /* warm-up, builds the gauge copy */
+  Hopping_Matrix(1, g_spinor_field[2], g_spinor_field[1]);
+  t1 = gettime();
+  for (int j = 0; j < nreps; j++) {
+    Hopping_Matrix(0, g_spinor_field[1], g_spinor_field[0]);
+    Hopping_Matrix(1, g_spinor_field[2], g_spinor_field[1]);
+  }
+  t2 = gettime();
+  return t2 - t1;
+}
+double ref_bench_D_psi(int nreps) {
+  double t1, t2;
+  random_spinor_field_lexic(g_spinor_field[0], 1, RN_GAUSS);
+  D_psi(g_spinor_field[1], g_spinor_field[0]);
+  t1 = gettime();
+  for (int j = 0; j < nreps; j++) {
+    D_psi(g_spinor_field[1], g_spinor_field[0]);
+    D_psi(g_spinor_field[0], g_spinor_field[1]);
+  }
+  t2 = gettime();
+  return t2 - t1;
+}
+/* nreps applications of Qtm_pm_psi (the CG matrix) */
+double ref_bench_Qtm_pm(int nreps) {
+  double t1, t2;
+  random_spinor_field_eo(g_spinor_field[0], 1, RN_GAUSS);
+  Qtm_pm_psi(g_spinor_field[1], g_spinor_field[0]);
+  t1 = gettime();
+  for (int j = 0; j < nreps; j++) Qtm_pm_psi(g_spinor_field[1], g_spinor_field[0]);
+  t2 = gettime();
+  return t2 - t1;
+}
+double ref_gettime(void) { return gettime(); }
