@@ -1,0 +1,138 @@
+/* tmlqcd_b200.h - C ABI of the B200-native even/odd twisted-mass Wilson-Dirac path.
+ *
+ * One process drives one GPU.  All entry points are extern "C", take plain pointers and
+ * sizes, and return 0 on success or a negative code (tmb_last_error() gives the text).
+ * Two levels:
+ *
+ *  (1) device level (this file): explicit lifecycle, device-resident eo spinor fields
+ *      (opaque device pointers from tmb_field_alloc) and operators on them.  This is what a
+ *      caller that wants the fields to stay in HBM binds, e.g. a solver or the HMC.
+ *  (2) reference level (tmlqcd_b200_dropin.h): the reference's own symbols
+ *      (Hopping_Matrix, Qtm_pm_psi, cg_her, invert_eo, ...) with the reference's signatures
+ *      and host pointers, implemented on top of (1).
+ *
+ * Host layouts are the reference's (su3.h:40-63): spinor = 24 doubles (s0..s3 x c0..c2,
+ * re/im), su3 = 18 doubles row-major; eo fields hold VOLUME/2 sites in g_lexic2eosub order;
+ * the gauge field is g_gauge_field[ix][mu], ix lexicographic (geometry_eo.c:290).
+ *
+ * Each function cites the reference interface it replaces (file:line in urbach/tmLQCD).
+ */
+#ifndef TMLQCD_B200_H
+#define TMLQCD_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- lifecycle: replaces tmlqcd_mpi_init (mpi_init.c:321-357), init_gauge_field,
+ *      init_spinor_field, geometry() (geometry_eo.c:743) for the device side ---- */
+int tmb_init(int T, int LX, int LY, int LZ, int device); /* local extents of this rank; LZ and T even */
+int tmb_finalize(void);
+int tmb_is_initialized(void);
+const char *tmb_last_error(void);
+int tmb_volume_half(void); /* VOLUME/2 of this rank */
+
+/* multi-GPU: T is split over `nranks` processes, rank r holds global t in [r*T,(r+1)*T).
+ * id128 is a 128-byte ncclUniqueId made by rank 0 and distributed by the caller
+ * (torch.distributed / MPI).  Replaces g_cart_grid + xchange/ (mpi_init.c:375, xchange_field.c:583). */
+int tmb_comm_unique_id(void *id128);
+int tmb_comm_init(const void *id128, int nranks, int rank);
+int tmb_comm_loopback(int on); /* single GPU: exercise the halo/boundary path against itself */
+int tmb_comm_nranks(void);
+
+/* ---- parameters: the globals the reference operators read at call time ---- */
+/* boundary(kappa) with X0..X3 (boundary.c:40-55): ka_mu = kappa*exp(i*theta_mu*pi/L_mu^global) */
+int tmb_set_boundary(double kappa, const double theta[4]);
+int tmb_set_hopping_phases(const double ka_re_im[8]);              /* ka0..ka3 as (re,im) pairs, boundary.c:47-50 */
+int tmb_set_mu(double g_mu);                                       /* g_mu = 2*kappa*mu (invert_eo.c:255) */
+int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_operators_nd.c */
+/* kernel configuration knobs (profiling / tuning; defaults are the measured best) */
+int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
+
+/* ---- memory ---- */
+void *tmb_field_alloc(void);         /* one eo spinor field, VOLUME/2 sites, device SoA layout */
+int tmb_field_free(void *field);
+int tmb_field_zero(void *field);
+void *tmb_host_alloc(size_t bytes);  /* pinned host memory */
+int tmb_host_free(void *p);
+int tmb_host_register(void *p, size_t bytes); /* pin caller-owned memory (e.g. the reference's calloc slabs) */
+int tmb_host_unregister(void *p);
+/* host AoS (reference layout) <-> device field; synchronous on return */
+int tmb_field_upload(void *field, const double *host_spinors);
+int tmb_field_download(double *host_spinors, const void *field);
+/* lexicographic full-volume field <-> (even, odd) pair: convert_lexic_to_eo / convert_eo_to_lexic
+ * (linalg/convert_eo_to_lexic.c:35-115) fused into the transfer */
+int tmb_field_upload_lexic(void *even, void *odd, const double *host_lexic);
+int tmb_field_download_lexic(double *host_lexic, const void *even, const void *odd);
+/* g_gauge_field upload; what update_backward_gauge (update_backward_gauge.c:185) + xchange_gauge
+ * do for the CPU code whenever g_update_gauge_copy is set */
+int tmb_gauge_upload(const double *host_gauge);
+int tmb_sync(void);
+int tmb_timer_start(void);           /* CUDA events on the library's compute stream */
+int tmb_timer_stop(float *ms);
+
+/* ---- operators on device fields ---- */
+/* Hopping_Matrix(ieo,l,k): operator/Hopping_Matrix.c:131 */
+int tmb_Hopping_Matrix(int ieo, void *l, const void *k);
+/* tm_times_Hopping_Matrix(ieo,l,k,cfactor): operator/tm_times_Hopping_Matrix.c:119 */
+int tmb_tm_times_Hopping_Matrix(int ieo, void *l, const void *k, double cf_re, double cf_im);
+/* tm_sub_Hopping_Matrix(ieo,l,p,k,cfactor): operator/tm_sub_Hopping_Matrix.c:122 */
+int tmb_tm_sub_Hopping_Matrix(int ieo, void *l, const void *p, const void *k, double cf_re, double cf_im);
+/* H_eo_tm_inv_psi / tm_sub_H_eo_gamma5: operator/tm_operators.c:508, :528 */
+int tmb_H_eo_tm_inv_psi(void *l, const void *k, int ieo, double sign);
+int tmb_tm_sub_H_eo_gamma5(void *l, const void *p, const void *k, int ieo, double sign);
+/* operator/tm_operators.c:338, :172, :216, :245, :289, :117, :130 */
+int tmb_Qtm_pm_psi(void *l, const void *k);
+int tmb_Qtm_plus_psi(void *l, const void *k);
+int tmb_Qtm_minus_psi(void *l, const void *k);
+int tmb_Mtm_plus_psi(void *l, const void *k);
+int tmb_Mtm_minus_psi(void *l, const void *k);
+int tmb_M_full(void *even_new, void *odd_new, const void *even, const void *odd);
+int tmb_Q_full(void *even_new, void *odd_new, const void *even, const void *odd);
+/* D_psi on an (even,odd) pair = one lexicographic field: operator/D_psi_body.c:266 */
+int tmb_D_psi_eo(void *even_new, void *odd_new, const void *even, const void *odd);
+/* twisted-mass diagonal: mul_one_pm_imu_inv_body.c:1/:44, tm_operators.c:669, :813; gamma.c:77 */
+int tmb_assign_mul_one_pm_imu_inv(void *l, const void *k, double sign);
+int tmb_assign_mul_one_pm_imu(void *l, const void *k, double sign);
+int tmb_mul_one_pm_imu_sub_mul_gamma5(void *l, const void *k, const void *j, double sign);
+int tmb_mul_one_pm_imu_sub_mul(void *l, const void *k, const void *j, double sign);
+int tmb_gamma5(void *l, const void *k);
+
+/* ---- BLAS-1 (linalg/): results of reductions are global sums over ranks ---- */
+int tmb_square_norm(const void *p, double *result);                       /* square_norm.c:253 */
+int tmb_scalar_prod_r(const void *s, const void *r, double *result);      /* scalar_prod_r.c:135 */
+int tmb_assign_add_mul_r(void *p, const void *q, double c);               /* assign_add_mul_r.c:346 */
+int tmb_assign_mul_add_r(void *r, double c, const void *s);               /* assign_mul_add_r.c:340 */
+int tmb_assign_mul_add_r_and_square(void *r, double c, const void *s, double *result); /* assign_mul_add_r_and_square.c:145 */
+int tmb_diff(void *q, const void *r, const void *s);                      /* diff.c:270 */
+int tmb_add(void *q, const void *r, const void *s);                       /* add.c */
+int tmb_assign(void *r, const void *s);                                   /* assign.c:42 */
+int tmb_mul_r(void *r, double c, const void *s);                          /* mul_r.c:40 */
+
+/* ---- solvers, fields stay resident, scalars stay on the device ---- */
+/* cg_her(P,Q,max_iter,eps_sq,rel_prec,VOLUME/2,&Qtm_pm_psi): solver/cg_her.c:62.
+ * Returns the iteration count, -1 if not converged (cg_her.c:141), < -1 on a CUDA error. */
+int tmb_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec);
+/* the CG branch of invert_eo: invert_eo.c:152-157, :252, :268-270, :306-310 */
+int tmb_invert_eo(void *even_new, void *odd_new, const void *even, const void *odd, double precision, int max_iter,
+                  int rel_prec);
+/* last solve: iterations, final |r|^2 as seen by the CG, seconds spent in the CG loop */
+int tmb_solver_stats(int *iterations, double *final_err, double *seconds);
+
+/* ---- non-degenerate doublet: operator/tm_operators_nd.c:68,:130,:195,:639; cg_her_nd.c:57;
+ *      invert_doublet_eo.c:68 ---- */
+int tmb_M_ee_inv_ndpsi(void *ls, void *lc, const void *ks, const void *kc, double mu, double eps);
+int tmb_Qtm_ndpsi(void *ls, void *lc, const void *ks, const void *kc);
+int tmb_Qtm_dagger_ndpsi(void *ls, void *lc, const void *ks, const void *kc);
+int tmb_Qtm_pm_ndpsi(void *ls, void *lc, const void *ks, const void *kc);
+int tmb_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq, int rel_prec);
+int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
+                          const void *ec, const void *oc, double precision, int max_iter, int rel_prec);
+
+/* number of kernels this library launched since tmb_init (bench.py's gpu_launches) */
+long long tmb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMLQCD_B200_H */

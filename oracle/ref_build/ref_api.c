@@ -62,7 +62,7 @@ double phmc_stilde_low, phmc_stilde_max;
 int phmc_exact_poly;
 
 static int ref_initialised = 0;
-#define NSF 24 /* g_spinor_field slots: user 0..7, DUM_DERI 8..15, DUM_MATRIX 16..23 */
+#define NSF 14 /* g_spinor_field slots: user 0..3, DUM_DERI 4..7, DUM_MATRIX 8..13 */
 
 int ref_init(int t, int lx, int ly, int lz, int nthreads) {
   if (ref_initialised) {
@@ -79,7 +79,7 @@ int ref_init(int t, int lx, int ly, int lz, int nthreads) {
   SPACEVOLUME = LX * LY * LZ; SPACERAND = 0;
   g_dbw2rand = 0; g_debug_level = 0; g_sloppy_precision_flag = 0; g_sloppy_precision = 0;
   g_rgi_C1 = 0.; g_c_sw = 0.; g_use_clover_flag = 0; lowmem_flag = 0;
-  DUM_DERI = 8; DUM_MATRIX = 16; NO_OF_SPINORFIELDS = NSF;
+  DUM_DERI = 4; DUM_MATRIX = 8; NO_OF_SPINORFIELDS = NSF;
 #ifdef TM_USE_OMP
   omp_num_threads = nthreads > 0 ? nthreads : 1;
   init_openmp();

@@ -1,0 +1,136 @@
+/* tmb_emul.cu - TEST-ONLY host emulation of the device site functions.
+ *
+ * This container has no GPU.  To check the device code's layout conversion, neighbour
+ * arithmetic, spin projection tables, epilogues and the T-slab halo logic on the CPU, this
+ * file includes the product kernel source and calls its __host__ __device__ site functions
+ * and functors from plain host loops.  It is built into tests/emul/libtmb_emul.so by
+ * tests/emul/build.sh and loaded only by tests/ (-m "not gpu").  It is NOT part of the
+ * product library and is not a CPU fallback: tmlqcd_b200/csrc never references it.
+ */
+#include "../../tmlqcd_b200/csrc/tmb_kernels.cu"
+
+template <int MODE, int DIST>
+static void hop_host(double2 *out, const tmb_hop_fields &f, const double2 *p, const tmb_geom &g, int par,
+                     const double2 ka[4], double2 cf, int site0, int nsites, int split, int gap) {
+  tmb_policies pol = {0, 0};
+  for (int w = 0; w < nsites; w++) {
+    const int i = site0 + w + (w >= split ? gap : 0);
+    double2 r[12];
+    tmb_hop_site<DIST, 0>(r, f, g, par, i, ka, pol);
+    for (int c = 0; c < 12; c++) {
+      double2 pc = make_double2(0., 0.);
+      if (MODE >= 2) pc = p[(size_t)c * g.Vh + i];
+      out[(size_t)c * g.Vh + i] = tmb_epilogue<MODE>(c, r[c], pc, cf);
+    }
+  }
+}
+
+extern "C" {
+
+void emul_pack_eo(double *soa, const double *aos, int Vh) {
+  EwPackEo f = {(double2 *)soa, (const double2 *)aos, Vh};
+  for (size_t k = 0; k < (size_t)12 * Vh; k++) f(k);
+}
+void emul_unpack_eo(double *aos, const double *soa, int Vh) {
+  EwUnpackEo f = {(double2 *)aos, (const double2 *)soa, Vh};
+  for (size_t k = 0; k < (size_t)12 * Vh; k++) f(k);
+}
+void emul_pack_lexic(double *even, double *odd, const double *lex, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  EwPackLex f = {(double2 *)even, (double2 *)odd, (const double2 *)lex, g};
+  for (size_t k = 0; k < (size_t)24 * g.Vh; k++) f(k);
+}
+void emul_unpack_lexic(double *lex, const double *even, const double *odd, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  EwUnpackLex f = {(double2 *)lex, (const double2 *)even, (const double2 *)odd, g};
+  for (size_t k = 0; k < (size_t)24 * g.Vh; k++) f(k);
+}
+void emul_pack_gauge(double *U, const double *lex, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  EwPackGauge f = {(double2 *)U, (const double2 *)lex, g};
+  for (size_t k = 0; k < (size_t)72 * g.Vh; k++) f(k);
+}
+void emul_pack_halo(double *up, double *dn, const double *in, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 1);
+  EwPackHalo f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g};
+  for (size_t k = 0; k < (size_t)6 * g.S; k++) f(k);
+}
+void emul_pack_gauge_halo(double *out, const double *U, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 1);
+  EwPackGaugeHalo f = {(double2 *)out, (const double2 *)U, g};
+  for (size_t k = 0; k < (size_t)18 * g.S; k++) f(k);
+}
+/* neighbour table by the closed forms of tmb_geom.h: nb[8*i+d], for comparison with g_hi */
+void emul_neighbours(int *nb, int par, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  for (int i = 0; i < g.Vh; i++) tmb_neighbours(g, par, i, nb + 8 * i);
+}
+void emul_eo2lexic(int *out, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  for (int par = 0; par < 2; par++)
+    for (int i = 0; i < g.Vh; i++) out[par * g.Vh + i] = tmb_eo_to_lexic(g, par, i);
+}
+
+/* the full hopping term as the product's hop() composes it: one launch when dist == 0,
+ * interior + boundary ranges when dist == 1 (same site0/nsites/split/gap arithmetic) */
+int emul_hop(int par, double *out, const double *in, const double *p, const double *U, const double *halo_up,
+             const double *halo_dn, const double *Uhalo, int T, int LX, int LY, int LZ, const double *ka8,
+             double cre, double cim, int mode, int dist) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, dist);
+  tmb_hop_fields f;
+  f.in = (const double2 *)in; f.U = (const double2 *)U;
+  f.halo_up = (const double2 *)halo_up; f.halo_dn = (const double2 *)halo_dn; f.Uhalo = (const double2 *)Uhalo;
+  double2 ka[4];
+  for (int m = 0; m < 4; m++) ka[m] = make_double2(ka8[2 * m], ka8[2 * m + 1]);
+  const double2 cf = make_double2(cre, cim);
+  double2 *o = (double2 *)out; const double2 *pp = (const double2 *)p;
+#define GO(M, D, s0, n, sp, gp) hop_host<M, D>(o, f, pp, g, par, ka, cf, s0, n, sp, gp)
+#define MODES(D, s0, n, sp, gp) \
+  switch (mode) { case 0: GO(0, D, s0, n, sp, gp); break; case 1: GO(1, D, s0, n, sp, gp); break; \
+                  case 2: GO(2, D, s0, n, sp, gp); break; case 3: GO(3, D, s0, n, sp, gp); break; default: return -1; }
+  if (!dist) { MODES(0, 0, g.Vh, g.Vh, 0); }
+  else {
+    if (g.Vh > 2 * g.S) { MODES(0, g.S, g.Vh - 2 * g.S, g.Vh - 2 * g.S, 0); }
+    MODES(1, 0, 2 * g.S, g.S, g.Vh - 2 * g.S);
+  }
+  return 0;
+}
+
+/* x-blocked traversal: the permutation of work indices used by hop_kernel must be a bijection */
+void emul_xblock_perm(int *out, int T, int LX, int LY, int LZ, int XB) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  const int P = g.LY * g.Lzh;
+  for (int ww = 0; ww < g.Vh; ww++) {
+    const int plane = ww / P, off = ww - plane * P;
+    const int per = g.T * XB;
+    const int xb = plane / per, rem = plane - xb * per;
+    const int t = rem / XB, xi = rem - t * XB;
+    out[ww] = (t * g.LX + xb * XB + xi) * P + off;
+  }
+}
+
+/* elementwise functors */
+void emul_diag(double *l, const double *k, double zre, double zim, int Vh) {
+  EwDiag f = {(double2 *)l, (const double2 *)k, make_double2(zre, zim), (size_t)6 * Vh};
+  for (size_t i = 0; i < (size_t)12 * Vh; i++) f(i);
+}
+void emul_diag_sub(double *l, const double *k, const double *j, double zre, double zim, int g5, int Vh) {
+  EwDiagSub f = {(double2 *)l, (const double2 *)k, (const double2 *)j, make_double2(zre, zim), g5, (size_t)6 * Vh};
+  for (size_t i = 0; i < (size_t)12 * Vh; i++) f(i);
+}
+void emul_gamma5(double *l, const double *k, int Vh) {
+  EwG5 f = {(double2 *)l, (const double2 *)k, (size_t)6 * Vh};
+  for (size_t i = 0; i < (size_t)12 * Vh; i++) f(i);
+}
+void emul_nd_mee_inv(double *ls, double *lc, const double *ks, const double *kc, double mu, double eps, int Vh) {
+  EwNdMeeInv f = {(double2 *)ls, (double2 *)lc, (const double2 *)ks, (const double2 *)kc, mu, eps,
+                  1. / (1. + mu * mu - eps * eps), (size_t)6 * Vh};
+  for (size_t i = 0; i < (size_t)12 * Vh; i++) f(i);
+}
+void emul_nd_moo_sub_g5(double *ls, double *lc, const double *ks, const double *kc, const double *js,
+                        const double *jc, double mu, double eps, int Vh) {
+  EwNdMooSubG5 f = {(double2 *)ls, (double2 *)lc, (const double2 *)ks, (const double2 *)kc,
+                    (const double2 *)js, (const double2 *)jc, mu, eps, (size_t)6 * Vh};
+  for (size_t i = 0; i < (size_t)12 * Vh; i++) f(i);
+}
+} /* extern "C" */

@@ -1,0 +1,349 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/tmlqcd_b200.h and the
+reference-named drop-in symbols of include/tmlqcd_b200_dropin.h), against the CPU oracle on the
+same seeded inputs.  Tolerance from BASELINE.json north_star: relative L2 <= 1e-13 in double,
+CG iteration count within +-1 of the reference recurrence.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import random_gauge, random_spinor, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-13
+KAPPA, GMU = 0.16, 0.0032
+ND = (0.139, 0.15, 0.9)
+
+
+def _setup(oracle_lib, dims, theta, seed=7):
+    import tmlqcd_b200 as tm
+    rng = np.random.default_rng(seed)
+    o = oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g)
+    o.set_params(KAPPA, GMU, theta)
+    o.set_nd_params(*ND)
+    d = tm.Device(*dims)
+    d.set_params(KAPPA, GMU, theta)
+    d.ck(d.lib.tmb_set_nd(*ND))
+    d.gauge_upload(g)
+    return rng, o, d, g
+
+
+CASES = [((4, 4, 4, 4), (0., 0., 0., 0.)), ((8, 4, 6, 8), (1., 0.3, 0., 0.7)), ((6, 10, 4, 6), (1., 0., 0., 0.)),
+         ((8, 8, 8, 8), (0., 0., 0., 0.))]
+
+
+@pytest.mark.parametrize("dims,theta", CASES)
+@pytest.mark.parametrize("loopback", [0, 1])
+def test_hopping_and_epilogues(oracle_lib, dims, theta, loopback):
+    rng, o, d, g = _setup(oracle_lib, dims, theta)
+    try:
+        if loopback:  # the T-split halo/boundary kernels, this rank being its own neighbour
+            d.ck(d.lib.tmb_comm_loopback(1))
+            d.gauge_upload(g)
+        k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        dk, dp, dl = d.field(k), d.field(p), d.field()
+        for ieo in (0, 1):
+            exp = o.spinor()
+            o.Hopping_Matrix(ieo, exp, k)
+            d.call("Hopping_Matrix", ieo, dl, dk)
+            assert rel_l2(d.download(dl), exp) <= TOL
+            o.tm_times_Hopping_Matrix(ieo, exp, k, 0.9, -0.2)
+            d.call("tm_times_Hopping_Matrix", ieo, dl, dk, 0.9, -0.2)
+            assert rel_l2(d.download(dl), exp) <= TOL
+            o.tm_sub_Hopping_Matrix(ieo, exp, p, k, 1.0, 0.3)
+            d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3)
+            assert rel_l2(d.download(dl), exp) <= TOL
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("variant", range(0, 10))
+@pytest.mark.parametrize("hints,xblock", [(1, 0), (0, 0), (1, 2)])
+def test_hopping_kernel_variants(oracle_lib, variant, hints, xblock):
+    """every tuning variant of the plain kernel computes the same thing"""
+    rng, o, d, g = _setup(oracle_lib, (4, 8, 6, 8), (1., 0., 0.5, 0.))
+    try:
+        d.ck(d.lib.tmb_set_tuning(variant, hints, xblock))
+        k = random_spinor(rng, o.Vh)
+        dk, dl = d.field(k), d.field()
+        exp = o.spinor()
+        o.Hopping_Matrix(1, exp, k)
+        d.call("Hopping_Matrix", 1, dl, dk)
+        assert rel_l2(d.download(dl), exp) <= TOL
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("dims,theta", CASES[:3])
+def test_composite_operators(oracle_lib, dims, theta):
+    rng, o, d, g = _setup(oracle_lib, dims, theta)
+    try:
+        k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        dk, dp, dl, dm = d.field(k), d.field(p), d.field(), d.field()
+        for name in ("Qtm_pm_psi", "Qtm_plus_psi", "Qtm_minus_psi", "Mtm_plus_psi", "Mtm_minus_psi"):
+            exp = o.spinor()
+            getattr(o, name)(exp, k)
+            d.call(name, dl, dk)
+            assert rel_l2(d.download(dl), exp) <= TOL, name
+        e1, e2 = o.spinor(), o.spinor()
+        o.M_full(e1, e2, k, p)
+        d.call("M_full", dl, dm, dk, dp)
+        assert rel_l2(d.download(dl), e1) <= TOL and rel_l2(d.download(dm), e2) <= TOL
+        o.Q_full(e1, e2, k, p)
+        d.call("Q_full", dl, dm, dk, dp)
+        assert rel_l2(d.download(dl), e1) <= TOL and rel_l2(d.download(dm), e2) <= TOL
+        # D_psi on a lexicographic field == M_full after the eo permutation (qphix_test_Dslash.c:233 recipe)
+        lex = random_spinor(rng, o.V)
+        explex = o.spinor(o.V)
+        o.D_psi(explex, lex)
+        d.upload_lexic(dk, dp, lex)
+        d.call("D_psi_eo", dl, dm, dk, dp)
+        assert rel_l2(d.download_lexic(dl, dm), explex) <= TOL
+        # in-place Qtm_minus_psi(l, l) as invert_eo.c:270 uses it
+        exp = o.spinor()
+        o.Qtm_minus_psi(exp, k)
+        d.upload(dk, k)
+        d.call("Qtm_minus_psi", dk, dk)
+        assert rel_l2(d.download(dk), exp) <= TOL
+    finally:
+        d.close()
+
+
+def test_blas1_and_diagonal(oracle_lib):
+    dims = (4, 6, 4, 8)
+    rng, o, d, g = _setup(oracle_lib, dims, (0., 0., 0., 0.))
+    try:
+        a, b, c = (random_spinor(rng, o.Vh) for _ in range(3))
+        da, db, dc = d.field(a), d.field(b), d.field(c)
+        n = o.Vh
+        assert abs(d.reduce("square_norm", da) / o.square_norm(a, n) - 1) < 1e-14
+        assert abs(d.reduce("scalar_prod_r", da, db) - o.scalar_prod_r(a, b, n)) < 1e-11
+        x = a.copy(); o.assign_add_mul_r(x, b, 0.37, n); d.call("assign_add_mul_r", da, db, 0.37)
+        assert rel_l2(d.download(da), x) <= TOL
+        y = x.copy(); o.assign_mul_add_r(y, -1.3, b, n); d.call("assign_mul_add_r", da, -1.3, db)
+        assert rel_l2(d.download(da), y) <= TOL
+        z = y.copy(); e = o.assign_mul_add_r_and_square(z, 0.6, c, n)
+        got = d.reduce("assign_mul_add_r_and_square", da, 0.6, dc)
+        assert rel_l2(d.download(da), z) <= TOL and abs(got / e - 1) < 1e-14
+        w = o.spinor(); o.diff(w, b, c, n); d.call("diff", da, db, dc); assert rel_l2(d.download(da), w) <= TOL
+        o.add(w, b, c, n); d.call("add", da, db, dc); assert rel_l2(d.download(da), w) <= TOL
+        o.mul_r(w, 2.5, b, n); d.call("mul_r", da, 2.5, db); assert rel_l2(d.download(da), w) <= TOL
+        o.gamma5(w, b, n); d.call("gamma5", da, db); assert np.array_equal(d.download(da), w)
+        d.call("assign", da, db); assert np.array_equal(d.download(da), b)
+        for sign in (+1., -1.):
+            o.assign_mul_one_pm_imu_inv(w, b, sign, n); d.call("assign_mul_one_pm_imu_inv", da, db, sign)
+            assert rel_l2(d.download(da), w) <= TOL
+            o.assign_mul_one_pm_imu(w, b, sign, n); d.call("assign_mul_one_pm_imu", da, db, sign)
+            assert rel_l2(d.download(da), w) <= TOL
+            o.mul_one_pm_imu_sub_mul_gamma5(w, b, c, sign); d.call("mul_one_pm_imu_sub_mul_gamma5", da, db, dc, sign)
+            assert rel_l2(d.download(da), w) <= TOL
+            o.mul_one_pm_imu_sub_mul(w, b, c, sign, n); d.call("mul_one_pm_imu_sub_mul", da, db, dc, sign)
+            assert rel_l2(d.download(da), w) <= TOL
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("dims,theta,loopback", [((8, 4, 4, 4), (0., 0., 0., 0.), 0), ((8, 8, 8, 8), (1., 0., 0., 0.), 0),
+                                                 ((8, 4, 6, 8), (1., 0.3, 0., 0.7), 1)])
+def test_cg_and_invert_eo(oracle_lib, dims, theta, loopback):
+    rng, o, d, g = _setup(oracle_lib, dims, theta)
+    try:
+        if loopback:
+            d.ck(d.lib.tmb_comm_loopback(1))
+            d.gauge_upload(g)
+        q = random_spinor(rng, o.Vh)
+        x_ref = o.spinor()
+        it_ref = o.cg_her(x_ref, q, 2000, 1e-22, 1)
+        dq, dx = d.field(q), d.field()
+        it = d.call("cg_her", dx, dq, 2000, 1e-22, 1)
+        assert it_ref > 0 and abs(it - it_ref) <= 1, (it, it_ref)
+        assert rel_l2(d.download(dx), x_ref) <= 1e-10  # both solved to 1e-11 relative residual
+        # absolute precision + non-convergence return value (cg_her.c:141)
+        assert d.call("cg_her", dx, dq, 3, 1e-30, 0) == -1
+        # invert_eo CG branch
+        E, O = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        en_r, on_r = o.spinor(), o.spinor()
+        it_ref = o.invert_eo_cg(en_r, on_r, E, O, 1e-22, 2000, 1)
+        dE, dO, dEn, dOn = d.field(E), d.field(O), d.field(), d.field()
+        it = d.call("invert_eo", dEn, dOn, dE, dO, 1e-22, 2000, 1)
+        assert abs(it - it_ref) <= 1
+        en, on = d.download(dEn), d.download(dOn)
+        assert rel_l2(en, en_r) <= 1e-10 and rel_l2(on, on_r) <= 1e-10
+        # the reference's own end-to-end check: |M_full x - b|^2 with the CPU operator (operator.c:358-384)
+        r1, r2 = o.spinor(), o.spinor()
+        o.M_full(r1, r2, en, on)
+        res = np.linalg.norm(r1 - E) ** 2 + np.linalg.norm(r2 - O) ** 2
+        assert res <= 1e-18 * (np.linalg.norm(E) ** 2 + np.linalg.norm(O) ** 2)
+    finally:
+        d.close()
+
+
+def test_nd_doublet(oracle_lib):
+    dims = (4, 4, 6, 8)
+    rng, o, d, g = _setup(oracle_lib, dims, (1., 0., 0., 0.))
+    try:
+        s, c, q, w = (random_spinor(rng, o.Vh) for _ in range(4))
+        ds, dc, dls, dlc = d.field(s), d.field(c), d.field(), d.field()
+        for name in ("Qtm_ndpsi", "Qtm_dagger_ndpsi", "Qtm_pm_ndpsi"):
+            e1, e2 = o.spinor(), o.spinor()
+            getattr(o, name)(e1, e2, s, c)
+            d.call(name, dls, dlc, ds, dc)
+            assert rel_l2(d.download(dls), e1) <= TOL and rel_l2(d.download(dlc), e2) <= TOL, name
+        e1, e2 = o.spinor(), o.spinor()
+        it_ref = o.cg_her_nd(e1, e2, s, c, 2000, 1e-20, 1)
+        d.call("field_zero", dls); d.call("field_zero", dlc)
+        it = d.call("cg_her_nd", dls, dlc, ds, dc, 2000, 1e-20, 1)
+        assert abs(it - it_ref) <= 1
+        assert rel_l2(d.download(dls), e1) <= 1e-9 and rel_l2(d.download(dlc), e2) <= 1e-9
+        A = [o.spinor() for _ in range(4)]
+        it_ref = o.invert_doublet_eo_cg(*A, s, c, q, w, 1e-20, 2000, 1)
+        dq, dw = d.field(q), d.field(w)
+        outs = [d.field() for _ in range(4)]
+        # argument order: Even_new_s, Odd_new_s, Even_new_c, Odd_new_c, Even_s, Odd_s, Even_c, Odd_c
+        it = d.call("invert_doublet_eo", *outs, ds, dc, dq, dw, 1e-20, 2000, 1)
+        assert abs(it - it_ref) <= 1
+        for f, a in zip(outs, A):
+            assert rel_l2(d.download(f), a) <= 1e-9
+    finally:
+        d.close()
+
+
+def test_dropin_reference_symbols(oracle_lib):
+    """the reference-named entry points with host buffers (what a tmLQCD executable links)"""
+    import tmlqcd_b200 as tm
+    dims, theta = (8, 4, 4, 6), (1., 0., 0.25, 0.)
+    rng = np.random.default_rng(3)
+    o = oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, theta); o.set_nd_params(*ND)
+    D = tm.DropIn(*dims)
+    try:
+        D.set_params(KAPPA, GMU, theta); D.set_nd_params(*ND); D.set_gauge(g)
+        k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        l, exp = D.spinor(), o.spinor()
+        for ieo in (0, 1):
+            D.Hopping_Matrix(ieo, l, k); o.Hopping_Matrix(ieo, exp, k); assert rel_l2(l, exp) <= TOL
+            D.tm_times_Hopping_Matrix(ieo, l, k, 0.9, -0.2); o.tm_times_Hopping_Matrix(ieo, exp, k, 0.9, -0.2)
+            assert rel_l2(l, exp) <= TOL
+            D.tm_sub_Hopping_Matrix(ieo, l, p, k, 1.0, 0.3); o.tm_sub_Hopping_Matrix(ieo, exp, p, k, 1.0, 0.3)
+            assert rel_l2(l, exp) <= TOL
+        for name in ("Qtm_pm_psi", "Qtm_plus_psi", "Qtm_minus_psi", "Mtm_plus_psi", "Mtm_minus_psi"):
+            getattr(D, name)(l, k); getattr(o, name)(exp, k); assert rel_l2(l, exp) <= TOL, name
+        # callers flip the global g_mu around calls (tm_operators.c:382-386): re-read at every call
+        D.glob("g_mu").value = -GMU; o.set_params(KAPPA, -GMU, theta)
+        D.Qtm_plus_psi(l, k); o.Qtm_plus_psi(exp, k); assert rel_l2(l, exp) <= TOL
+        D.glob("g_mu").value = GMU; o.set_params(KAPPA, GMU, theta)
+        # ... and call boundary() with another kappa per monomial (detratio_monomial.c:57-59)
+        D.boundary(0.12); o.set_params(0.12, GMU, theta)
+        D.Hopping_Matrix(0, l, k); o.Hopping_Matrix(0, exp, k); assert rel_l2(l, exp) <= TOL
+        D.boundary(KAPPA); o.set_params(KAPPA, GMU, theta)
+        # gauge dirty flag (g_update_gauge_copy)
+        g2 = random_gauge(rng, o.V); D.set_gauge(g2); o.set_gauge(g2)
+        D.Hopping_Matrix(1, l, k); o.Hopping_Matrix(1, exp, k); assert rel_l2(l, exp) <= TOL
+        assert D.glob("g_update_gauge_copy", C.c_int).value == 0
+        # lexicographic D_psi and BLAS-1
+        lex, outl, expl = random_spinor(rng, o.V), D.spinor(o.V), o.spinor(o.V)
+        D.D_psi(outl, lex); o.D_psi(expl, lex); assert rel_l2(outl, expl) <= TOL
+        D.Q_pm_psi(outl, lex); o.Q_pm_psi(expl, lex); assert rel_l2(outl, expl) <= TOL
+        assert abs(D.square_norm(k, o.Vh, 1) / o.square_norm(k, o.Vh) - 1) < 1e-14
+        assert abs(D.square_norm(lex, o.V, 1) / o.square_norm(lex, o.V) - 1) < 1e-14
+        assert abs(D.scalar_prod_r(k, p, o.Vh, 1) - o.scalar_prod_r(k, p, o.Vh)) < 1e-11
+        a1, a2 = k.copy(), k.copy()
+        D.assign_add_mul_r(a1, p, 0.4, o.Vh); o.assign_add_mul_r(a2, p, 0.4, o.Vh); assert rel_l2(a1, a2) <= TOL
+        e1 = D.assign_mul_add_r_and_square(a1, -0.7, p, o.Vh, 1); e2 = o.assign_mul_add_r_and_square(a2, -0.7, p, o.Vh)
+        assert rel_l2(a1, a2) <= TOL and abs(e1 / e2 - 1) < 1e-14
+        # solvers: cg_her dispatches on the identity of f exactly like monomial_solve.c:134
+        x, xr = D.spinor(), o.spinor()
+        it = D.cg_her(x, k, 2000, 1e-22, 1, o.Vh, D.fptr("Qtm_pm_psi")); itr = o.cg_her(xr, k, 2000, 1e-22, 1)
+        assert abs(it - itr) <= 1 and rel_l2(x, xr) <= 1e-10
+        # any other f takes the generic path: same recurrence, f applied through its host-pointer entry point
+        raw = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(("Qtm_pm_psi", D.lib))
+        cb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(lambda l_, k_: raw(l_, k_))
+        x[:] = 0; it2 = D.cg_her(x, k, 2000, 1e-22, 1, o.Vh, C.cast(cb, C.c_void_p))
+        assert abs(it2 - itr) <= 1 and rel_l2(x, xr) <= 1e-10
+        en, on, enr, onr = D.spinor(), D.spinor(), o.spinor(), o.spinor()
+        it = D.invert_eo(en, on, k, p, 1e-22, 2000, 1, 1, 0, 1, 0, None, tm.capi.SolverParams(), 0, 0, 0, 18)
+        itr = o.invert_eo_cg(enr, onr, k, p, 1e-22, 2000, 1)
+        assert abs(it - itr) <= 1 and rel_l2(en, enr) <= 1e-10 and rel_l2(on, onr) <= 1e-10
+        # ND
+        ls, lc, es, ec = D.spinor(), D.spinor(), o.spinor(), o.spinor()
+        D.Qtm_pm_ndpsi(ls, lc, k, p); o.Qtm_pm_ndpsi(es, ec, k, p)
+        assert rel_l2(ls, es) <= TOL and rel_l2(lc, ec) <= TOL
+        ls[:] = 0; lc[:] = 0; es[:] = 0; ec[:] = 0
+        it = D.cg_her_nd(ls, lc, k, p, 2000, 1e-20, 1, o.Vh, D.fptr("Qtm_pm_ndpsi")); itr = o.cg_her_nd(es, ec, k, p, 2000, 1e-20, 1)
+        assert abs(it - itr) <= 1 and rel_l2(ls, es) <= 1e-9
+    finally:
+        D.close()
+
+
+def test_tmLQCD_facade(oracle_lib):
+    """include/tmLQCD.h entry points: lexicographic source in, propagator out (lib_wrapper.c:242-279)"""
+    import tmlqcd_b200 as tm
+    lib = tm.load()
+    dims = (8, 4, 4, 4)
+    rng = np.random.default_rng(11)
+    o = oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, (1., 0., 0., 0.))
+    lib.tmLQCD_b200_set_lattice(*dims)
+    lib.tmLQCD_b200_set_theta(1., 0., 0., 0.)
+    op = lib.tmLQCD_b200_add_operator(KAPPA, GMU, 1e-22, 2000, 1)
+    assert lib.tmLQCD_invert_init(0, None, 0, 0) == 0
+    try:
+        gf = C.POINTER(C.c_double)()
+        assert lib.tmLQCD_get_gauge_field_pointer(C.byref(gf)) == 0
+        C.memmove(gf, g.ctypes.data, g.nbytes)
+        src = random_spinor(rng, o.V)
+        prop = np.zeros_like(src)
+        assert lib.tmLQCD_invert(prop, src, op, 0) == 0
+        it, rp = C.c_int(0), C.c_double(0.)
+        lib.tmLQCD_b200_get_solver_info(op, C.byref(it), C.byref(rp))
+        # oracle: same pipeline
+        E, O, En, On = o.spinor(), o.spinor(), o.spinor(), o.spinor()
+        o.convert_lexic_to_eo(E, O, src)
+        itr = o.invert_eo_cg(En, On, E, O, 1e-22, 2000, 1)
+        exp = o.spinor(o.V)
+        o.convert_eo_to_lexic(exp, En * (2 * KAPPA), On * (2 * KAPPA))
+        assert abs(it.value - itr) <= 1 and rel_l2(prop, exp) <= 1e-10
+        assert rp.value <= 1e-18 * np.linalg.norm(src) ** 2
+        assert lib.tmLQCD_read_gauge(0) == -1  # LIME I/O is out of scope and says so
+    finally:
+        assert lib.tmLQCD_finalise() == 0
+
+
+def test_full_size_properties(oracle_lib):
+    """BASELINE config 2 size (24^3 x 48): size-independent properties + a sampled oracle check."""
+    import tmlqcd_b200 as tm
+    dims = (48, 24, 24, 24)
+    rng = np.random.default_rng(5)
+    V = int(np.prod(dims)); Vh = V // 2
+    g = random_gauge(rng, V)
+    d = tm.Device(*dims)
+    try:
+        d.set_params(KAPPA, GMU, (0., 0., 0., 0.))
+        d.gauge_upload(g)
+        a, b = random_spinor(rng, Vh), random_spinor(rng, Vh)
+        da, db, dl, dm = d.field(a), d.field(b), d.field(), d.field()
+        # linearity: H(a + 0.5 b) == H a + 0.5 H b
+        d.call("Hopping_Matrix", 0, dl, da); Ha = d.download(dl)
+        d.call("Hopping_Matrix", 0, dl, db); Hb = d.download(dl)
+        d.upload(dm, a + 0.5 * b); d.call("Hopping_Matrix", 0, dl, dm)
+        assert rel_l2(d.download(dl), Ha + 0.5 * Hb) <= TOL
+        # g5-hermiticity of the hopping term: <b, g5 H_oe g5 a>_odd == <H_eo b, a>  (H_oe^dag = g5 H_eo g5)
+        d.call("Qtm_pm_psi", dl, da); d.call("Qtm_pm_psi", dm, db)
+        lhs = d.reduce("scalar_prod_r", db, dl); rhs = d.reduce("scalar_prod_r", dm, da)
+        assert abs(lhs - rhs) <= 1e-12 * abs(lhs)  # Qtm_pm_psi is hermitian
+        assert d.reduce("scalar_prod_r", da, dl) > 0  # ... and positive
+        # oracle on the full lattice (a few seconds on the host)
+        o = oracle_lib.Oracle(*dims)
+        o.set_gauge(g); o.set_params(KAPPA, GMU, (0., 0., 0., 0.))
+        exp = o.spinor(); o.Hopping_Matrix(0, exp, a)
+        assert rel_l2(Ha, exp) <= TOL
+        exp2 = o.spinor(); o.Qtm_pm_psi(exp2, a)
+        assert rel_l2(d.download(dl), exp2) <= TOL
+    finally:
+        d.close()

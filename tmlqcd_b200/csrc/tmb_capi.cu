@@ -1,0 +1,769 @@
+/* tmb_capi.cu - the C-ABI layer (include/tmlqcd_b200.h) over the kernels in tmb_kernels.cu.
+ *
+ * Holds the one-GPU context: streams, the device gauge field, halo buffers, the NCCL
+ * communicator for the T-split, the scratch fields that play the role of the reference's
+ * g_spinor_field[DUM_MATRIX..] and the device-resident CG.  No CPU compute path exists here:
+ * every operator launches CUDA kernels and fails loudly when CUDA is unavailable.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <chrono>
+#include <string>
+#include <vector>
+#include "../../include/tmlqcd_b200.h"
+#include "tmb_kernels.h"
+
+/* ------------------------------------------------------------------ NCCL, bound at run time
+ * (the process usually already has torch's libnccl.so.2 loaded; dlopen gives us that copy) */
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { NCCL_SUM = 0, NCCL_FLOAT64 = 8, NCCL_UINT8 = 1 };
+struct NcclApi {
+  void *handle;
+  int (*GetUniqueId)(ncclUniqueId *);
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  int (*CommDestroy)(ncclComm_t);
+  int (*GroupStart)(void);
+  int (*GroupEnd)(void);
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(int);
+};
+
+#define NSCRATCH 12
+
+struct Ctx {
+  bool init = false;
+  int device = 0;
+  tmb_geom g;
+  int nranks = 1, rank = 0;
+  bool dist = false, loopback = false;
+  cudaStream_t s_main = nullptr, s_comm = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
+  double2 *U = nullptr, *Uhalo = nullptr;
+  double2 *send_up = nullptr, *send_dn = nullptr, *halo_up = nullptr, *halo_dn = nullptr;
+  double2 *stage = nullptr; /* AoS staging, 24*Vh double2 (one lexicographic field) */
+  double *partial = nullptr; int npartial = 0;
+  tmb_cg_state *st = nullptr;      /* device */
+  tmb_cg_state *st_host = nullptr; /* pinned, 2 slots */
+  double2 ka[4];
+  double kappa = 0., mu = 0., mubar = 0., epsbar = 0., invmaxev = 1.;
+  double2 *scratch[NSCRATCH] = {nullptr};
+  int hop_variant = 0, hints = 1, xblock = 0;
+  NcclApi nccl = {};
+  ncclComm_t comm = nullptr;
+  std::vector<void *> fields;
+  long long launches = 0;
+  int last_iters = 0; double last_err = 0., last_seconds = 0.;
+  bool gauge_loaded = false;
+};
+static Ctx C;
+static std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(-100, "%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+#define KL(x) do { cudaError_t e_ = (x); C.launches++; if (e_ != cudaSuccess) return fail(-101, "%s:%d kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+#define NC(x) do { int e_ = (x); if (e_ != 0) return fail(-102, "%s:%d NCCL error: %s", __FILE__, __LINE__, C.nccl.GetErrorString ? C.nccl.GetErrorString(e_) : "?"); } while (0)
+#define NEED_INIT() do { if (!C.init) return fail(-1, "tmb_init has not been called"); } while (0)
+#define TRY(x) do { int r_ = (x); if (r_ < 0) return r_; } while (0)
+
+static inline size_t N2() { return (size_t)12 * C.g.Vh; }
+static inline size_t HALF() { return (size_t)6 * C.g.Vh; }
+static inline size_t FIELD_BYTES() { return N2() * sizeof(double2); }
+static inline double2 *F(void *p) { return (double2 *)p; }
+static inline const double2 *F(const void *p) { return (const double2 *)p; }
+
+extern "C" const char *tmb_last_error(void) { return g_err.c_str(); }
+extern "C" int tmb_is_initialized(void) { return C.init ? 1 : 0; }
+extern "C" int tmb_volume_half(void) { return C.init ? C.g.Vh : 0; }
+extern "C" long long tmb_launch_count(void) { return C.launches; }
+extern "C" int tmb_comm_nranks(void) { return C.nranks; }
+
+extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
+  if (C.init) {
+    if (C.g.T == T && C.g.LX == LX && C.g.LY == LY && C.g.LZ == LZ) return 0;
+    return fail(-2, "tmb_init: already initialised with %dx%dx%dx%d; call tmb_finalize first", C.g.T, C.g.LX, C.g.LY, C.g.LZ);
+  }
+  if (T < 2 || LX < 1 || LY < 1 || LZ < 2 || (LZ & 1) || (T & 1))
+    return fail(-3, "tmb_init: need T >= 2 even and LZ >= 2 even (got T=%d LX=%d LY=%d LZ=%d)", T, LX, LY, LZ);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(-4, "tmb_init: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+  CU(cudaSetDevice(device));
+  C.device = device;
+  C.g = tmb_make_geom(T, LX, LY, LZ, 0);
+  CU(cudaStreamCreateWithFlags(&C.s_main, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&C.s_comm, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&C.ev_in, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&C.ev_halo, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&C.ev_chk[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&C.ev_chk[1], cudaEventDisableTiming));
+  CU(cudaEventCreate(&C.ev_t0));
+  CU(cudaEventCreate(&C.ev_t1));
+  CU(cudaMalloc(&C.U, (size_t)72 * C.g.Vh * sizeof(double2)));
+  CU(cudaMalloc(&C.stage, (size_t)24 * C.g.Vh * sizeof(double2)));
+  C.npartial = C.g.Vh / 64 + 4096;
+  CU(cudaMalloc(&C.partial, (size_t)C.npartial * sizeof(double)));
+  CU(cudaMalloc(&C.st, sizeof(tmb_cg_state)));
+  CU(cudaMemset(C.st, 0, sizeof(tmb_cg_state)));
+  CU(cudaHostAlloc(&C.st_host, 2 * sizeof(tmb_cg_state), cudaHostAllocDefault));
+  const size_t hb = (size_t)6 * C.g.S * sizeof(double2);
+  CU(cudaMalloc(&C.send_up, hb)); CU(cudaMalloc(&C.send_dn, hb));
+  CU(cudaMalloc(&C.halo_up, hb)); CU(cudaMalloc(&C.halo_dn, hb));
+  CU(cudaMalloc(&C.Uhalo, (size_t)18 * C.g.S * sizeof(double2)));
+  C.kappa = 0.; C.mu = 0.;
+  for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
+  C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
+  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0;
+  C.init = true;
+  return 0;
+}
+
+extern "C" int tmb_finalize(void) {
+  if (!C.init) return 0;
+  cudaDeviceSynchronize();
+  if (C.comm && C.nccl.CommDestroy) { C.nccl.CommDestroy(C.comm); C.comm = nullptr; }
+  for (void *p : C.fields) cudaFree(p);
+  C.fields.clear();
+  for (int i = 0; i < NSCRATCH; i++) { if (C.scratch[i]) cudaFree(C.scratch[i]); C.scratch[i] = nullptr; }
+  cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
+  cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
+  cudaFreeHost(C.st_host);
+  cudaEventDestroy(C.ev_in); cudaEventDestroy(C.ev_halo); cudaEventDestroy(C.ev_t0); cudaEventDestroy(C.ev_t1);
+  cudaEventDestroy(C.ev_chk[0]); cudaEventDestroy(C.ev_chk[1]);
+  cudaStreamDestroy(C.s_main); cudaStreamDestroy(C.s_comm);
+  C = Ctx();
+  return 0;
+}
+
+/* ------------------------------------------------------------------ communicator */
+static int load_nccl() {
+  if (C.nccl.handle) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(-110, "cannot dlopen libnccl.so.2: %s", dlerror());
+  C.nccl.handle = h;
+#define SYM(field, name) *(void **)(&C.nccl.field) = dlsym(h, name); if (!C.nccl.field) return fail(-111, "NCCL symbol %s missing", name)
+  SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+  SYM(AllReduce, "ncclAllReduce"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return 0;
+}
+extern "C" int tmb_comm_unique_id(void *id128) {
+  TRY(load_nccl());
+  ncclUniqueId id;
+  NC(C.nccl.GetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return 0;
+}
+extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) {
+  NEED_INIT();
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(-5, "tmb_comm_init: bad rank %d of %d", rank, nranks);
+  if (nranks == 1) { C.nranks = 1; C.rank = 0; C.dist = C.loopback; C.g.dist_t = C.dist; return 0; }
+  TRY(load_nccl());
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NC(C.nccl.CommInitRank(&C.comm, nranks, id, rank));
+  C.nranks = nranks; C.rank = rank; C.dist = true; C.g.dist_t = 1;
+  return 0;
+}
+extern "C" int tmb_comm_loopback(int on) {
+  NEED_INIT();
+  if (C.nranks > 1) return fail(-6, "tmb_comm_loopback: only for a single rank");
+  C.loopback = on != 0; C.dist = C.loopback; C.g.dist_t = C.dist ? 1 : 0;
+  C.gauge_loaded = false; /* Uhalo must be rebuilt */
+  return 0;
+}
+static int allreduce_slot(int slot) {
+  if (C.nranks > 1) NC(C.nccl.AllReduce(&C.st->tmp[slot], &C.st->tmp[slot], 1, NCCL_FLOAT64, NCCL_SUM, C.comm, C.s_main));
+  return 0;
+}
+
+/* ------------------------------------------------------------------ parameters */
+extern "C" int tmb_set_boundary(double kappa, const double theta[4]) {
+  NEED_INIT();
+  /* boundary.c:40-55, incl. its PI_ literal; global extents: only T is distributed */
+  const double PI_ = 3.14159265358979;
+  const double ext[4] = {(double)C.g.T * C.nranks, (double)C.g.LX, (double)C.g.LY, (double)C.g.LZ};
+  C.kappa = kappa;
+  for (int m = 0; m < 4; m++) {
+    const double x = (theta ? theta[m] : 0.) * PI_ / ext[m];
+    C.ka[m] = make_double2(kappa * cos(x), kappa * sin(x));
+  }
+  return 0;
+}
+/* ka0..ka3 exactly as the caller's boundary() computed them (re,im pairs) */
+extern "C" int tmb_set_hopping_phases(const double ka_re_im[8]) {
+  NEED_INIT();
+  for (int m = 0; m < 4; m++) C.ka[m] = make_double2(ka_re_im[2 * m], ka_re_im[2 * m + 1]);
+  C.kappa = sqrt(C.ka[0].x * C.ka[0].x + C.ka[0].y * C.ka[0].y);
+  return 0;
+}
+extern "C" int tmb_set_mu(double g_mu) { NEED_INIT(); C.mu = g_mu; return 0; }
+extern "C" int tmb_set_nd(double mubar, double epsbar, double invmaxev) {
+  NEED_INIT(); C.mubar = mubar; C.epsbar = epsbar; C.invmaxev = invmaxev; return 0;
+}
+extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
+  NEED_INIT();
+  if (hop_variant < 0 || hop_variant > 9) return fail(-7, "hop_variant must be 0..9");
+  if (xblock > 0 && C.g.LX % xblock) return fail(-7, "xblock must divide LX");
+  C.hop_variant = hop_variant; C.hints = cache_hints ? 1 : 0; C.xblock = xblock;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ memory */
+extern "C" void *tmb_field_alloc(void) {
+  if (!C.init) { fail(-1, "tmb_init has not been called"); return nullptr; }
+  void *p = nullptr;
+  if (cudaMalloc(&p, FIELD_BYTES()) != cudaSuccess) { fail(-100, "cudaMalloc of a spinor field failed"); return nullptr; }
+  cudaMemsetAsync(p, 0, FIELD_BYTES(), C.s_main);
+  C.fields.push_back(p);
+  return p;
+}
+extern "C" int tmb_field_free(void *field) {
+  NEED_INIT();
+  for (size_t i = 0; i < C.fields.size(); i++)
+    if (C.fields[i] == field) { CU(cudaStreamSynchronize(C.s_main)); CU(cudaFree(field)); C.fields.erase(C.fields.begin() + i); return 0; }
+  return fail(-8, "tmb_field_free: unknown field");
+}
+extern "C" int tmb_field_zero(void *field) { NEED_INIT(); CU(cudaMemsetAsync(field, 0, FIELD_BYTES(), C.s_main)); return 0; }
+extern "C" void *tmb_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail(-100, "cudaHostAlloc failed"); return nullptr; }
+  return p;
+}
+extern "C" int tmb_host_free(void *p) { CU(cudaFreeHost(p)); return 0; }
+extern "C" int tmb_host_register(void *p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return 0; }
+extern "C" int tmb_host_unregister(void *p) { CU(cudaHostUnregister(p)); return 0; }
+extern "C" int tmb_sync(void) { NEED_INIT(); CU(cudaStreamSynchronize(C.s_comm)); CU(cudaStreamSynchronize(C.s_main)); return 0; }
+extern "C" int tmb_timer_start(void) { NEED_INIT(); CU(cudaEventRecord(C.ev_t0, C.s_main)); return 0; }
+extern "C" int tmb_timer_stop(float *ms) {
+  NEED_INIT();
+  CU(cudaEventRecord(C.ev_t1, C.s_main));
+  CU(cudaEventSynchronize(C.ev_t1));
+  CU(cudaEventElapsedTime(ms, C.ev_t0, C.ev_t1));
+  return 0;
+}
+
+extern "C" int tmb_field_upload(void *field, const double *host) {
+  NEED_INIT();
+  CU(cudaMemcpyAsync(C.stage, host, FIELD_BYTES(), cudaMemcpyHostToDevice, C.s_main));
+  KL(tmb_launch_pack_eo(F(field), C.stage, C.g.Vh, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  return 0;
+}
+extern "C" int tmb_field_download(double *host, const void *field) {
+  NEED_INIT();
+  KL(tmb_launch_unpack_eo(C.stage, F(field), C.g.Vh, C.s_main));
+  CU(cudaMemcpyAsync(host, C.stage, FIELD_BYTES(), cudaMemcpyDeviceToHost, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  return 0;
+}
+extern "C" int tmb_field_upload_lexic(void *even, void *odd, const double *host) {
+  NEED_INIT();
+  CU(cudaMemcpyAsync(C.stage, host, 2 * FIELD_BYTES(), cudaMemcpyHostToDevice, C.s_main));
+  KL(tmb_launch_pack_lexic(F(even), F(odd), C.stage, C.g, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  return 0;
+}
+extern "C" int tmb_field_download_lexic(double *host, const void *even, const void *odd) {
+  NEED_INIT();
+  KL(tmb_launch_unpack_lexic(C.stage, F(even), F(odd), C.g, C.s_main));
+  CU(cudaMemcpyAsync(host, C.stage, 2 * FIELD_BYTES(), cudaMemcpyDeviceToHost, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  return 0;
+}
+
+/* exchange of the two T-face buffers: send_up -> rank+1's halo_dn, send_dn -> rank-1's halo_up */
+static int exchange_faces(const double2 *sup, const double2 *sdn, double2 *hup, double2 *hdn, size_t count2, cudaStream_t s) {
+  const size_t bytes = count2 * sizeof(double2);
+  if (C.nranks == 1) { /* loopback: this rank is its own neighbour in T */
+    CU(cudaMemcpyAsync(hdn, sup, bytes, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(hup, sdn, bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
+  NC(C.nccl.GroupStart());
+  NC(C.nccl.Send(sup, 2 * count2, NCCL_FLOAT64, up, C.comm, s));
+  NC(C.nccl.Recv(hdn, 2 * count2, NCCL_FLOAT64, dn, C.comm, s));
+  NC(C.nccl.Send(sdn, 2 * count2, NCCL_FLOAT64, dn, C.comm, s));
+  NC(C.nccl.Recv(hup, 2 * count2, NCCL_FLOAT64, up, C.comm, s));
+  NC(C.nccl.GroupEnd());
+  return 0;
+}
+
+extern "C" int tmb_gauge_upload(const double *host_gauge) {
+  NEED_INIT();
+  const size_t bytes = (size_t)72 * C.g.Vh * sizeof(double2); /* V*4 links * 9 complex */
+  double2 *raw = nullptr;
+  CU(cudaMalloc(&raw, bytes));
+  CU(cudaMemcpyAsync(raw, host_gauge, bytes, cudaMemcpyHostToDevice, C.s_main));
+  KL(tmb_launch_pack_gauge(C.U, raw, C.g, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  CU(cudaFree(raw));
+  if (C.dist) { /* one-off gauge halo: U_0 of rank-1's last time-slice (xchange_gauge in the reference) */
+    double2 *tmp = nullptr;
+    const size_t n = (size_t)18 * C.g.S;
+    CU(cudaMalloc(&tmp, n * sizeof(double2)));
+    KL(tmb_launch_pack_gauge_halo(tmp, C.U, C.g, C.s_main));
+    if (C.nranks == 1) {
+      CU(cudaMemcpyAsync(C.Uhalo, tmp, n * sizeof(double2), cudaMemcpyDeviceToDevice, C.s_main));
+    } else {
+      const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
+      NC(C.nccl.GroupStart());
+      NC(C.nccl.Send(tmp, 2 * n, NCCL_FLOAT64, up, C.comm, C.s_main));
+      NC(C.nccl.Recv(C.Uhalo, 2 * n, NCCL_FLOAT64, dn, C.comm, C.s_main));
+      NC(C.nccl.GroupEnd());
+    }
+    CU(cudaStreamSynchronize(C.s_main));
+    CU(cudaFree(tmp));
+  }
+  C.gauge_loaded = true;
+  return 0;
+}
+
+static double2 *scratch(int k) {
+  if (!C.scratch[k]) {
+    if (cudaMalloc(&C.scratch[k], FIELD_BYTES()) != cudaSuccess) { fail(-100, "cudaMalloc of a scratch field failed"); return nullptr; }
+    cudaMemsetAsync(C.scratch[k], 0, FIELD_BYTES(), C.s_main);
+  }
+  return C.scratch[k];
+}
+#define SCR(var, k) double2 *var = scratch(k); if (!var) return -100
+
+/* ------------------------------------------------------------------ the hopping term */
+struct HopOpt {
+  int mode = 0; double2 cf = {1., 0.}; const double2 *p = nullptr;
+  const double2 *dotw = nullptr; const tmb_cg_state *st = nullptr;
+  int *npartial = nullptr;
+};
+static int hop(int ieo, double2 *out, const double2 *in, const HopOpt &o) {
+  if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
+  if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
+  tmb_hop_launch a;
+  memset(&a, 0, sizeof(a));
+  a.in = in; a.out = out; a.p = o.p; a.dotw = o.dotw; a.U = C.U;
+  a.halo_up = C.halo_up; a.halo_dn = C.halo_dn; a.Uhalo = C.Uhalo;
+  a.partial = C.partial; a.st = o.st; a.g = C.g; a.par = ieo ? 1 : 0;
+  for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
+  a.cf = o.cf; a.mode = o.mode; a.dot = o.dotw ? 1 : 0; a.hints = C.hints;
+  int np = 0;
+  if (!C.dist) {
+    a.dist = 0; a.site0 = 0; a.nsites = C.g.Vh; a.split = C.g.Vh; a.gap = 0;
+    /* tuning variants exist for the plain Hopping_Matrix kernel only */
+    a.variant = (o.mode == 0 && !a.dot) ? C.hop_variant : 0;
+    a.xblock = C.xblock;
+    KL(tmb_launch_hop(a, C.s_main));
+    np = tmb_hop_grid(a);
+  } else {
+    /* halo exchange on the comm stream, overlapped with the interior kernel:
+     * replaces xchange_field(k, ieo) at operator/Hopping_Matrix.c:141-143 */
+    const int S = C.g.S, Vh = C.g.Vh;
+    CU(cudaEventRecord(C.ev_in, C.s_main));
+    CU(cudaStreamWaitEvent(C.s_comm, C.ev_in, 0));
+    KL(tmb_launch_pack_halo(C.send_up, C.send_dn, in, C.g, C.s_comm));
+    TRY(exchange_faces(C.send_up, C.send_dn, C.halo_up, C.halo_dn, (size_t)6 * S, C.s_comm));
+    CU(cudaEventRecord(C.ev_halo, C.s_comm));
+    int nb_int = 0;
+    a.variant = 0; a.xblock = 0;
+    if (Vh > 2 * S) { /* interior time-slices t in [1, T-2]: no halo data needed */
+      a.dist = 0; a.site0 = S; a.nsites = Vh - 2 * S; a.split = a.nsites; a.gap = 0;
+      KL(tmb_launch_hop(a, C.s_main));
+      nb_int = tmb_hop_grid(a);
+    }
+    CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
+    /* boundary slices t = 0 and t = T-1 */
+    a.dist = 1; a.site0 = 0; a.nsites = 2 * S; a.split = S; a.gap = Vh - 2 * S;
+    a.partial = C.partial + nb_int;
+    KL(tmb_launch_hop(a, C.s_main));
+    np = nb_int + tmb_hop_grid(a);
+  }
+  if (np > C.npartial) return fail(-10, "partial buffer too small");
+  if (o.npartial) *o.npartial = np;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ operators on device fields */
+extern "C" int tmb_Hopping_Matrix(int ieo, void *l, const void *k) {
+  NEED_INIT(); HopOpt o; return hop(ieo, F(l), F(k), o);
+}
+extern "C" int tmb_tm_times_Hopping_Matrix(int ieo, void *l, const void *k, double cre, double cim) {
+  NEED_INIT(); HopOpt o; o.mode = 1; o.cf = make_double2(cre, cim); return hop(ieo, F(l), F(k), o);
+}
+extern "C" int tmb_tm_sub_Hopping_Matrix(int ieo, void *l, const void *p, const void *k, double cre, double cim) {
+  NEED_INIT(); HopOpt o; o.mode = 2; o.cf = make_double2(cre, cim); o.p = F(p); return hop(ieo, F(l), F(k), o);
+}
+/* z of H_eo_tm_inv_psi (tm_operators.c:514-521): (1 -+ i mu)/(1+mu^2) */
+static double2 z_inv(double sign) {
+  const double nrm = 1. / (1. + C.mu * C.mu), sg = sign < 0. ? 1. : -1.;
+  return make_double2(nrm, sg * nrm * C.mu);
+}
+/* z of tm_sub_H_eo_gamma5 / mul_one_pm_imu (tm_operators.c:533-541): 1 +- i mu */
+static double2 z_fwd(double sign) { return make_double2(1., (sign < 0. ? -1. : 1.) * C.mu); }
+
+extern "C" int tmb_H_eo_tm_inv_psi(void *l, const void *k, int ieo, double sign) {
+  NEED_INIT(); HopOpt o; o.mode = 1; o.cf = z_inv(sign); return hop(ieo, F(l), F(k), o);
+}
+extern "C" int tmb_tm_sub_H_eo_gamma5(void *l, const void *p, const void *k, int ieo, double sign) {
+  NEED_INIT(); HopOpt o; o.mode = 2; o.cf = z_fwd(sign); o.p = F(p); return hop(ieo, F(l), F(k), o);
+}
+
+/* Qtm_pm_psi (tm_operators.c:338-345): 4 hops, each with its diagonal fused in the epilogue.
+ * dotw/st: the CG asks for <dotw, l> and the early exit. */
+static int qtm_pm(double2 *l, const double2 *k, const double2 *dotw, const tmb_cg_state *st, int *np) {
+  SCR(w0, 0); SCR(w1, 1);
+  HopOpt a; a.mode = 1; a.cf = z_inv(-1.); a.st = st;
+  TRY(hop(0, w1, k, a));
+  HopOpt b; b.mode = 2; b.cf = z_fwd(-1.); b.p = k; b.st = st;
+  TRY(hop(1, w0, w1, b));
+  HopOpt c; c.mode = 1; c.cf = z_inv(+1.); c.st = st;
+  TRY(hop(0, w1, w0, c));
+  HopOpt d; d.mode = 2; d.cf = z_fwd(+1.); d.p = w0; d.st = st; d.dotw = dotw; d.npartial = np;
+  TRY(hop(1, l, w1, d));
+  return 0;
+}
+extern "C" int tmb_Qtm_pm_psi(void *l, const void *k) { NEED_INIT(); return qtm_pm(F(l), F(k), nullptr, nullptr, nullptr); }
+
+/* Q_+- = g5[(1 +- i mu g5) k - H_oe (1 +- i mu g5)^-1 H_eo k]  (tm_operators.c:172-177, :216-221);
+ * l may alias k: k is only read site-locally by the last kernel */
+static int qtm_pm_single(double2 *l, const double2 *k, double sign, int g5) {
+  SCR(w1, 1);
+  HopOpt a; a.mode = 1; a.cf = z_inv(sign);
+  TRY(hop(0, w1, k, a));
+  HopOpt b; b.mode = g5 ? 2 : 3; b.cf = z_fwd(sign); b.p = k;
+  TRY(hop(1, l, w1, b));
+  return 0;
+}
+extern "C" int tmb_Qtm_plus_psi(void *l, const void *k) { NEED_INIT(); return qtm_pm_single(F(l), F(k), +1., 1); }
+extern "C" int tmb_Qtm_minus_psi(void *l, const void *k) { NEED_INIT(); return qtm_pm_single(F(l), F(k), -1., 1); }
+extern "C" int tmb_Mtm_plus_psi(void *l, const void *k) { NEED_INIT(); return qtm_pm_single(F(l), F(k), +1., 0); }
+extern "C" int tmb_Mtm_minus_psi(void *l, const void *k) { NEED_INIT(); return qtm_pm_single(F(l), F(k), -1., 0); }
+
+/* M_full (tm_operators.c:117-128): En = (1+i mu g5)E - H_eo O ; On = (1+i mu g5)O - H_oe E */
+static int m_full(double2 *en, double2 *on, const double2 *e, const double2 *o, int g5) {
+  HopOpt a; a.mode = g5 ? 2 : 3; a.cf = z_fwd(+1.); a.p = e;
+  TRY(hop(0, en, o, a));
+  HopOpt b; b.mode = g5 ? 2 : 3; b.cf = z_fwd(+1.); b.p = o;
+  TRY(hop(1, on, e, b));
+  return 0;
+}
+extern "C" int tmb_M_full(void *en, void *on, const void *e, const void *o) {
+  NEED_INIT();
+  if (en == e || en == o || on == e || on == o) return fail(-11, "tmb_M_full: output must not alias input");
+  return m_full(F(en), F(on), F(e), F(o), 0);
+}
+extern "C" int tmb_Q_full(void *en, void *on, const void *e, const void *o) {
+  NEED_INIT();
+  if (en == e || en == o || on == e || on == o) return fail(-11, "tmb_Q_full: output must not alias input");
+  return m_full(F(en), F(on), F(e), F(o), 1);
+}
+/* D_psi (D_psi_body.c:266-375) = M_full on the eo-split field: phase_mu = -ka_mu gives the minus sign */
+extern "C" int tmb_D_psi_eo(void *en, void *on, const void *e, const void *o) { return tmb_M_full(en, on, e, o); }
+
+extern "C" int tmb_assign_mul_one_pm_imu_inv(void *l, const void *k, double sign) {
+  NEED_INIT(); KL(tmb_launch_diag(F(l), F(k), z_inv(sign), N2(), HALF(), C.s_main)); return 0;
+}
+extern "C" int tmb_assign_mul_one_pm_imu(void *l, const void *k, double sign) {
+  NEED_INIT(); KL(tmb_launch_diag(F(l), F(k), z_fwd(sign), N2(), HALF(), C.s_main)); return 0;
+}
+extern "C" int tmb_mul_one_pm_imu_sub_mul_gamma5(void *l, const void *k, const void *j, double sign) {
+  NEED_INIT(); KL(tmb_launch_diag_sub(F(l), F(k), F(j), z_fwd(sign), 1, N2(), HALF(), C.s_main)); return 0;
+}
+extern "C" int tmb_mul_one_pm_imu_sub_mul(void *l, const void *k, const void *j, double sign) {
+  NEED_INIT(); KL(tmb_launch_diag_sub(F(l), F(k), F(j), z_fwd(sign), 0, N2(), HALF(), C.s_main)); return 0;
+}
+extern "C" int tmb_gamma5(void *l, const void *k) { NEED_INIT(); KL(tmb_launch_gamma5(F(l), F(k), N2(), HALF(), C.s_main)); return 0; }
+
+/* ------------------------------------------------------------------ BLAS-1 */
+static int finish_reduction(int npart, double *result) {
+  KL(tmb_launch_final(C.partial, npart, C.st, 0, TMB_FIN_STORE, 0, C.s_main));
+  TRY(allreduce_slot(0));
+  CU(cudaMemcpyAsync(result, &C.st->tmp[0], sizeof(double), cudaMemcpyDeviceToHost, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  return 0;
+}
+extern "C" int tmb_square_norm(const void *p, double *result) {
+  NEED_INIT(); KL(tmb_launch_norm2(F(p), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
+}
+extern "C" int tmb_scalar_prod_r(const void *s, const void *r, double *result) {
+  NEED_INIT(); KL(tmb_launch_dot(F(s), F(r), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
+}
+extern "C" int tmb_assign_mul_add_r_and_square(void *r, double c, const void *s, double *result) {
+  NEED_INIT(); KL(tmb_launch_xpay_norm(F(r), c, F(s), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
+}
+extern "C" int tmb_assign_add_mul_r(void *p, const void *q, double c) { NEED_INIT(); KL(tmb_launch_axpy(F(p), F(q), c, N2(), C.s_main)); return 0; }
+extern "C" int tmb_assign_mul_add_r(void *r, double c, const void *s) { NEED_INIT(); KL(tmb_launch_xpay(F(r), c, F(s), N2(), C.s_main)); return 0; }
+extern "C" int tmb_diff(void *q, const void *r, const void *s) { NEED_INIT(); KL(tmb_launch_lincomb(F(q), 1., F(r), -1., F(s), N2(), C.s_main)); return 0; }
+extern "C" int tmb_add(void *q, const void *r, const void *s) { NEED_INIT(); KL(tmb_launch_lincomb(F(q), 1., F(r), 1., F(s), N2(), C.s_main)); return 0; }
+extern "C" int tmb_assign(void *r, const void *s) {
+  NEED_INIT();
+  if (r != s) CU(cudaMemcpyAsync(r, s, FIELD_BYTES(), cudaMemcpyDeviceToDevice, C.s_main));
+  return 0;
+}
+extern "C" int tmb_mul_r(void *r, double c, const void *s) { NEED_INIT(); KL(tmb_launch_scale(F(r), c, F(s), N2(), C.s_main)); return 0; }
+
+/* ------------------------------------------------------------------ CG, solver/cg_her.c:62-143
+ * Same recurrence and stopping rule as the reference.  What changes is where things live:
+ * p, r, Ap, x and the scalars normsq/pro/alpha/err/beta stay in HBM; <p,Ap> is accumulated in the
+ * epilogue of the 4th hop of Qtm_pm_psi; x += alpha p, r -= alpha Ap and |r|^2 are one sweep;
+ * the stop test runs on the device and turns every later kernel into a no-op, so the host
+ * enqueues iterations in chunks without a synchronisation per iteration. */
+#define CG_CHUNK 8
+static int reduce_to(int npart, int slot, int op) {
+  if (C.nranks > 1) {
+    KL(tmb_launch_final(C.partial, npart, C.st, slot, op, 0, C.s_main));
+    TRY(allreduce_slot(slot));
+    KL(tmb_launch_apply(C.st, slot, op, C.s_main));
+  } else {
+    KL(tmb_launch_final(C.partial, npart, C.st, slot, op, 1, C.s_main));
+  }
+  return 0;
+}
+
+extern "C" int tmb_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec) {
+  NEED_INIT();
+  SCR(ap, 2); SCR(r, 3); SCR(p, 4);
+  double2 *x = F(P); const double2 *q = F(Q);
+  const size_t n2 = N2();
+  auto t0 = std::chrono::steady_clock::now();
+  /* squarenorm = |Q|^2 (cg_her.c:82) */
+  double sqn = 0.;
+  TRY(tmb_square_norm(Q, &sqn));
+  tmb_cg_state h;
+  memset(&h, 0, sizeof(h));
+  h.sqnorm_q = sqn; h.eps_sq = eps_sq; h.rel_prec = rel_prec;
+  CU(cudaMemcpyAsync(C.st, &h, sizeof(h), cudaMemcpyHostToDevice, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main)); /* h is on the stack */
+  /* r = Q - A x ; p = r ; normsq = |r|^2 (cg_her.c:84-88) */
+  TRY(qtm_pm(ap, x, nullptr, nullptr, nullptr));
+  KL(tmb_launch_lincomb(r, 1., q, -1., ap, n2, C.s_main));
+  CU(cudaMemcpyAsync(p, r, FIELD_BYTES(), cudaMemcpyDeviceToDevice, C.s_main));
+  KL(tmb_launch_norm2(r, n2, C.partial, C.s_main));
+  TRY(reduce_to(tmb_red_grid(n2), 0, TMB_FIN_CG_INIT));
+
+  int enq = 0, chunk = 0, done = 0;
+  bool pending[2] = {false, false};
+  while (!done) {
+    const int todo = (max_iter - enq) < CG_CHUNK ? (max_iter - enq) : CG_CHUNK;
+    for (int k = 0; k < todo; k++) {
+      int np = 0;
+      TRY(qtm_pm(ap, p, p, C.st, &np));                                     /* cg_her.c:92 + :93 fused */
+      TRY(reduce_to(np, 1, TMB_FIN_CG_PRO));                                /* alpha = normsq/pro */
+      KL(tmb_launch_cg_update_xr(x, r, p, ap, n2, C.st, C.partial, C.s_main)); /* cg_her.c:95-101 */
+      TRY(reduce_to(tmb_red_grid(n2), 2, TMB_FIN_CG_ERR));                  /* stop test, beta */
+      KL(tmb_launch_cg_update_p(p, r, n2, C.st, C.s_main));                 /* cg_her.c:122 */
+    }
+    enq += todo;
+    const int slot = chunk & 1;
+    CU(cudaMemcpyAsync(&C.st_host[slot], C.st, sizeof(tmb_cg_state), cudaMemcpyDeviceToHost, C.s_main));
+    CU(cudaEventRecord(C.ev_chk[slot], C.s_main));
+    pending[slot] = true;
+    /* look at the PREVIOUS chunk's state while this one runs */
+    const int prev = slot ^ 1;
+    if (pending[prev]) {
+      CU(cudaEventSynchronize(C.ev_chk[prev]));
+      pending[prev] = false;
+      if (C.st_host[prev].converged) done = 1;
+    }
+    if (enq >= max_iter) done = 1;
+    chunk++;
+  }
+  CU(cudaStreamSynchronize(C.s_main));
+  CU(cudaMemcpy(&h, C.st, sizeof(h), cudaMemcpyDeviceToHost));
+  auto t1 = std::chrono::steady_clock::now();
+  C.last_iters = h.iter; C.last_err = h.err;
+  C.last_seconds = std::chrono::duration<double>(t1 - t0).count();
+  if (!h.converged) return -1; /* cg_her.c:141 */
+  return h.iter;
+}
+
+extern "C" int tmb_solver_stats(int *iterations, double *final_err, double *seconds) {
+  if (iterations) *iterations = C.last_iters;
+  if (final_err) *final_err = C.last_err;
+  if (seconds) *seconds = C.last_seconds;
+  return 0;
+}
+
+/* invert_eo, CG branch (invert_eo.c:152-157, :252, :268-270, :306-310) */
+extern "C" int tmb_invert_eo(void *even_new, void *odd_new, const void *even, const void *odd, double precision,
+                             int max_iter, int rel_prec) {
+  NEED_INIT();
+  SCR(d, 5);
+  double2 *En = F(even_new), *On = F(odd_new);
+  const size_t n2 = N2();
+  /* Even_new = Mee^-1 Even */
+  KL(tmb_launch_diag(En, F(even), z_inv(+1.), n2, HALF(), C.s_main));
+  /* DUM_DERI = g5 (Odd + H_oe Even_new): MODE 2 with cf = -1 gives g5(-Odd - H En); so do it in two steps */
+  HopOpt a; TRY(hop(1, d, En, a));
+  KL(tmb_launch_xpay(d, 1., F(odd), n2, C.s_main));
+  KL(tmb_launch_gamma5(d, d, n2, HALF(), C.s_main));
+  const int iter = tmb_cg_her(odd_new, d, max_iter, precision, rel_prec);
+  if (iter < -1) return iter;
+  TRY(qtm_pm_single(On, On, -1., 1));            /* Qtm_minus_psi(Odd_new, Odd_new) */
+  /* Even_new += Mee^-1 H_eo Odd_new */
+  HopOpt b; b.mode = 1; b.cf = z_inv(+1.);
+  TRY(hop(0, d, On, b));
+  KL(tmb_launch_axpy(En, d, 1., n2, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  return iter;
+}
+
+/* ------------------------------------------------------------------ ND doublet, tm_operators_nd.c */
+extern "C" int tmb_M_ee_inv_ndpsi(void *ls, void *lc, const void *ks, const void *kc, double mu, double eps) {
+  NEED_INIT(); KL(tmb_launch_nd_mee_inv(F(ls), F(lc), F(ks), F(kc), mu, eps, N2(), HALF(), C.s_main)); return 0;
+}
+static int nd_moo(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc, const double2 *js, const double2 *jc,
+                  double mu, double eps) {
+  KL(tmb_launch_nd_moo_sub_g5(ls, lc, ks, kc, js, jc, mu, eps, N2(), HALF(), C.s_main)); return 0;
+}
+static int hop0(int ieo, double2 *l, const double2 *k) { HopOpt o; return hop(ieo, l, k, o); }
+
+/* tm_operators_nd.c:68-89 */
+extern "C" int tmb_Qtm_ndpsi(void *ls_, void *lc_, const void *ks_, const void *kc_) {
+  NEED_INIT();
+  double2 *ls = F(ls_), *lc = F(lc_); const double2 *ks = F(ks_), *kc = F(kc_);
+  SCR(s0, 6); SCR(s1, 7); SCR(s2, 8); SCR(s3, 9);
+  TRY(hop0(0, s0, ks)); TRY(hop0(0, s1, kc));
+  KL(tmb_launch_nd_mee_inv(s3, s2, s0, s1, C.mubar, C.epsbar, N2(), HALF(), C.s_main));
+  TRY(hop0(1, ls, s3)); TRY(hop0(1, lc, s2));
+  TRY(nd_moo(s0, s1, ks, kc, ls, lc, -C.mubar, -C.epsbar));
+  KL(tmb_launch_scale(ls, C.invmaxev, s0, N2(), C.s_main));
+  KL(tmb_launch_scale(lc, C.invmaxev, s1, N2(), C.s_main));
+  return 0;
+}
+/* tm_operators_nd.c:130-152; l may alias k */
+extern "C" int tmb_Qtm_dagger_ndpsi(void *ls_, void *lc_, const void *ks_, const void *kc_) {
+  NEED_INIT();
+  double2 *ls = F(ls_), *lc = F(lc_); const double2 *ks = F(ks_), *kc = F(kc_);
+  SCR(s0, 6); SCR(s1, 7); SCR(s2, 8); SCR(s3, 9);
+  TRY(hop0(0, s0, kc)); TRY(hop0(0, s1, ks));
+  KL(tmb_launch_nd_mee_inv(s2, s3, s0, s1, C.mubar, C.epsbar, N2(), HALF(), C.s_main));
+  TRY(hop0(1, s0, s2)); TRY(hop0(1, s1, s3));
+  TRY(nd_moo(ls, lc, ks, kc, s1, s0, C.mubar, -C.epsbar));
+  KL(tmb_launch_scale(lc, C.invmaxev, lc, N2(), C.s_main));
+  KL(tmb_launch_scale(ls, C.invmaxev, ls, N2(), C.s_main));
+  return 0;
+}
+/* tm_operators_nd.c:195-238 */
+static int qtm_pm_nd(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc) {
+  SCR(s0, 6); SCR(s1, 7); SCR(s2, 8); SCR(s3, 9); SCR(s4, 10); SCR(s5, 11);
+  TRY(hop0(0, s0, kc)); TRY(hop0(0, s1, ks));
+  KL(tmb_launch_nd_mee_inv(s2, s3, s0, s1, C.mubar, C.epsbar, N2(), HALF(), C.s_main));
+  TRY(hop0(1, s0, s2)); TRY(hop0(1, s1, s3));
+  TRY(nd_moo(s2, s3, kc, ks, s0, s1, -C.mubar, -C.epsbar));
+  TRY(hop0(0, s0, s3)); TRY(hop0(0, s1, s2));
+  KL(tmb_launch_nd_mee_inv(s5, s4, s1, s0, -C.mubar, C.epsbar, N2(), HALF(), C.s_main));
+  TRY(hop0(1, ls, s4)); TRY(hop0(1, lc, s5));
+  TRY(nd_moo(ls, lc, s3, s2, ls, lc, -C.mubar, -C.epsbar));
+  const double f = C.invmaxev * C.invmaxev;
+  if (f != 1.) {
+    KL(tmb_launch_scale(lc, f, lc, N2(), C.s_main));
+    KL(tmb_launch_scale(ls, f, ls, N2(), C.s_main));
+  }
+  return 0;
+}
+extern "C" int tmb_Qtm_pm_ndpsi(void *ls, void *lc, const void *ks, const void *kc) {
+  NEED_INIT(); return qtm_pm_nd(F(ls), F(lc), F(ks), F(kc));
+}
+
+/* solver/cg_her_nd.c:57-170: same recurrence over the two-flavour field; host-side scalars
+ * (two reductions read back per iteration) - the doublet solve is the config-4 row, the
+ * device-scalar treatment of tmb_cg_her is applied to it in a later round. */
+static int two_norm(const double2 *a, const double2 *b, double *out) {
+  double x = 0., y = 0.;
+  TRY(tmb_square_norm(a, &x)); TRY(tmb_square_norm(b, &y));
+  *out = x + y; return 0;
+}
+extern "C" int tmb_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq,
+                             int rel_prec) {
+  NEED_INIT();
+  const size_t n2 = N2();
+  double2 *u[5], *d[5];
+  std::vector<void *> tmp;
+  for (int i = 0; i < 5; i++) {
+    u[i] = F(tmb_field_alloc()); d[i] = F(tmb_field_alloc());
+    if (!u[i] || !d[i]) return -100;
+    tmp.push_back(u[i]); tmp.push_back(d[i]);
+  }
+  auto cleanup = [&]() { for (void *p : tmp) tmb_field_free(p); };
+  auto t0 = std::chrono::steady_clock::now();
+  double squarenorm, normsp, normsq, pro, err = 0., a, b;
+  int ret = -1, rc = 0;
+#define ND(x) do { rc = (x); if (rc < 0) { cleanup(); return rc < -1 ? rc : -100; } } while (0)
+  ND(two_norm(F(Qup), F(Qdn), &squarenorm));
+  ND(tmb_assign(u[0], Pup)); ND(tmb_assign(d[0], Pdn));
+  ND(two_norm(F(Pup), F(Pdn), &normsp));
+  if (normsp == 0.) {
+    ND(tmb_assign(u[1], Qup)); ND(tmb_assign(d[1], Qdn)); ND(tmb_assign(u[2], Qup)); ND(tmb_assign(d[2], Qdn));
+    ND(two_norm(F(Qup), F(Qdn), &normsq));
+  } else {
+    ND(qtm_pm_nd(u[3], d[3], u[0], d[0]));
+    ND(tmb_diff(u[1], Qup, u[3])); ND(tmb_diff(d[1], Qdn, d[3]));
+    ND(tmb_assign(u[2], u[1])); ND(tmb_assign(d[2], d[1]));
+    ND(two_norm(u[2], d[2], &normsq));
+  }
+  int it;
+  for (it = 0; it < max_iter; it++) {
+    ND(qtm_pm_nd(u[4], d[4], u[2], d[2]));
+    ND(tmb_scalar_prod_r(u[2], u[4], &a)); ND(tmb_scalar_prod_r(d[2], d[4], &b));
+    pro = a + b;
+    const double alpha = normsq / pro;
+    KL(tmb_launch_axpy(u[0], u[2], alpha, n2, C.s_main)); KL(tmb_launch_axpy(d[0], d[2], alpha, n2, C.s_main));
+    KL(tmb_launch_axpy(u[1], u[4], -alpha, n2, C.s_main)); KL(tmb_launch_axpy(d[1], d[4], -alpha, n2, C.s_main));
+    ND(two_norm(u[1], d[1], &err));
+    if ((err <= eps_sq && rel_prec == 0) || (err <= eps_sq * squarenorm && rel_prec == 1)) { ret = it + 1; break; }
+    const double beta = err / normsq;
+    KL(tmb_launch_xpay(u[2], beta, u[1], n2, C.s_main)); KL(tmb_launch_xpay(d[2], beta, d[1], n2, C.s_main));
+    normsq = err;
+  }
+  ND(tmb_assign(Pup, u[0])); ND(tmb_assign(Pdn, d[0]));
+  CU(cudaStreamSynchronize(C.s_main));
+#undef ND
+  cleanup();
+  auto t1 = std::chrono::steady_clock::now();
+  C.last_iters = ret; C.last_err = err; C.last_seconds = std::chrono::duration<double>(t1 - t0).count();
+  return ret;
+}
+
+/* invert_doublet_eo.c:102-178 (NO_EXT_INV, CG) */
+extern "C" int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
+                                     const void *ec, const void *oc, double precision, int max_iter, int rel_prec) {
+  NEED_INIT();
+  const size_t n2 = N2();
+  double2 *d[4];
+  for (int i = 0; i < 4; i++) { d[i] = F(tmb_field_alloc()); if (!d[i]) return -100; }
+  int rc = 0, iter = -1;
+  do {
+    if ((rc = tmb_M_ee_inv_ndpsi(ens, enc, es, ec, C.mubar, C.epsbar)) < 0) break;
+    if ((rc = hop0(1, d[0], F(ens))) < 0) break;
+    if ((rc = hop0(1, d[1], F(enc))) < 0) break;
+    if ((rc = tmb_assign_mul_add_r(d[0], 1., os)) < 0) break;
+    if ((rc = tmb_assign_mul_add_r(d[1], 1., oc)) < 0) break;
+    if ((rc = tmb_gamma5(d[0], d[0])) < 0) break;
+    if ((rc = tmb_gamma5(d[1], d[1])) < 0) break;
+    iter = tmb_cg_her_nd(ons, onc, d[0], d[1], max_iter, precision, rel_prec);
+    if (iter < -1) { rc = iter; break; }
+    if ((rc = tmb_Qtm_dagger_ndpsi(ons, onc, ons, onc)) < 0) break;
+    if ((rc = hop0(0, d[0], F(ons))) < 0) break;
+    if ((rc = hop0(0, d[1], F(onc))) < 0) break;
+    if ((rc = tmb_M_ee_inv_ndpsi(d[2], d[3], d[0], d[1], C.mubar, C.epsbar)) < 0) break;
+    if ((rc = tmb_assign_add_mul_r(ens, d[2], 1.)) < 0) break;
+    if ((rc = tmb_assign_add_mul_r(enc, d[3], 1.)) < 0) break;
+    cudaStreamSynchronize(C.s_main);
+  } while (0);
+  (void)n2;
+  for (int i = 0; i < 4; i++) tmb_field_free(d[i]);
+  return rc < 0 ? rc : iter;
+}

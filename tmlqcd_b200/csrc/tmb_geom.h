@@ -1,0 +1,75 @@
+/* tmb_geom.h - even/odd lattice geometry of one GPU's slab, shared by host and device code.
+ *
+ * Rebuilt from the rules of the reference's geometry_eo.c (not from its tables):
+ *   lexicographic index  ix = ((t*LX + x)*LY + y)*LZ + z          geometry_eo.c:290
+ *   parity               even iff (t+x+y+z) % 2 == 0              geometry_eo.c:807-814
+ *   eo-sub index         rank of ix among the sites of its own parity in increasing ix
+ *                                                                 geometry_eo.c:869-884
+ * With LZ even every (t,x,y) row holds LZ/2 sites of each parity in increasing z, hence
+ *   i = ((t*LX + x)*LY + y)*Lzh + zh,   z = 2*zh + ((t+x+y+parity) & 1).
+ * tests/test_geometry.py checks these closed forms against the reference's
+ * g_eo2lexic / g_lexic2eosub / g_hi tables.
+ */
+#ifndef TMB_GEOM_H
+#define TMB_GEOM_H
+
+#if defined(__CUDACC__)
+#define TMB_HD __host__ __device__ __forceinline__
+#else
+#define TMB_HD static inline
+#endif
+
+typedef struct {
+  int T, LX, LY, LZ; /* local extents of this rank's slab */
+  int Lzh;           /* LZ/2 */
+  int S;             /* LX*LY*Lzh: sites of one parity in one time-slice (a T-face) */
+  int Vh;            /* T*S: sites of one parity */
+  int dist_t;        /* 1: T is split over ranks, +-t neighbours of the boundary slices come from halo buffers */
+} tmb_geom;
+
+TMB_HD tmb_geom tmb_make_geom(int T, int LX, int LY, int LZ, int dist_t) {
+  tmb_geom g;
+  g.T = T; g.LX = LX; g.LY = LY; g.LZ = LZ; g.Lzh = LZ / 2;
+  g.S = LX * LY * g.Lzh; g.Vh = T * g.S; g.dist_t = dist_t;
+  return g;
+}
+
+/* eo-sub index -> coordinates; `par` is the parity of the site (0 even, 1 odd) */
+TMB_HD void tmb_eo_coords(const tmb_geom g, int par, int i, int *t, int *x, int *y, int *z) {
+  unsigned u = (unsigned)i;
+  unsigned zh = u % (unsigned)g.Lzh; u /= (unsigned)g.Lzh;
+  unsigned yy = u % (unsigned)g.LY;  u /= (unsigned)g.LY;
+  unsigned xx = u % (unsigned)g.LX;  unsigned tt = u / (unsigned)g.LX;
+  *t = (int)tt; *x = (int)xx; *y = (int)yy;
+  *z = (int)(2u * zh + ((tt + xx + yy + (unsigned)par) & 1u));
+}
+
+TMB_HD int tmb_eo_to_lexic(const tmb_geom g, int par, int i) {
+  int t, x, y, z;
+  tmb_eo_coords(g, par, i, &t, &x, &y, &z);
+  return ((t * g.LX + x) * g.LY + y) * g.LZ + z;
+}
+
+/* Neighbour eo-sub indices (in the field of the OPPOSITE parity) of site i of parity `par`,
+ * order +t,-t,+x,-x,+y,-y,+z,-z as g_hi[16*icx + 2d+1] (geometry_eo.c:1470-1536).
+ * Periodic wrap inside the slab; with dist_t the caller replaces nb[0] for t==T-1 and nb[1]
+ * for t==0 by halo reads.  Returns t. */
+TMB_HD int tmb_neighbours(const tmb_geom g, int par, int i, int nb[8]) {
+  unsigned u = (unsigned)i;
+  unsigned zh = u % (unsigned)g.Lzh; u /= (unsigned)g.Lzh;
+  unsigned y = u % (unsigned)g.LY;   u /= (unsigned)g.LY;
+  unsigned x = u % (unsigned)g.LX;   unsigned t = u / (unsigned)g.LX;
+  const int r = (int)((t + x + y + (unsigned)par) & 1u); /* z = 2*zh + r */
+  const int sx = g.LY * g.Lzh;
+  nb[0] = ((int)t + 1 < g.T) ? i + g.S : i - (g.T - 1) * g.S;
+  nb[1] = (t > 0) ? i - g.S : i + (g.T - 1) * g.S;
+  nb[2] = ((int)x + 1 < g.LX) ? i + sx : i - (g.LX - 1) * sx;
+  nb[3] = (x > 0) ? i - sx : i + (g.LX - 1) * sx;
+  nb[4] = ((int)y + 1 < g.LY) ? i + g.Lzh : i - (g.LY - 1) * g.Lzh;
+  nb[5] = (y > 0) ? i - g.Lzh : i + (g.LY - 1) * g.Lzh;
+  nb[6] = r ? (((int)zh + 1 < g.Lzh) ? i + 1 : i - (g.Lzh - 1)) : i;
+  nb[7] = r ? i : ((zh > 0) ? i - 1 : i + (g.Lzh - 1));
+  return (int)t;
+}
+
+#endif /* TMB_GEOM_H */

@@ -1,0 +1,376 @@
+/* tmb_kernels.cu - hand-written CUDA kernels (sm_100a) for tmLQCD's even/odd twisted-mass path.
+ *
+ * K1  hop_kernel        Hopping_Matrix / tm_times_ / tm_sub_ (operator/Hopping_Matrix.c:131,
+ *                       tm_times_Hopping_Matrix.c:119, tm_sub_Hopping_Matrix.c:122) with the
+ *                       epilogue and, for the CG, the <p,Ap> reduction fused in.
+ * K3  elementwise       linalg/ BLAS-1 + twisted-mass diagonal (tm_operators.c, tm_operators_nd.c)
+ * K4  reductions        square_norm / scalar_prod_r / assign_mul_add_r_and_square, two-stage:
+ *                       warp shuffle + block partial, then one CTA finishing and doing the CG
+ *                       scalar bookkeeping on the device.
+ * Bandwidth-bound stencil: no tensor cores.  One thread per output site, 128-bit loads that are
+ * contiguous across the warp (SoA), gauge streamed with L1::no_allocate + L2 evict-first.
+ */
+#include "tmb_kernels.h"
+#include "tmb_site.cuh"
+
+#define TMB_SMS 148
+
+/* ------------------------------------------------------------------ block reduction */
+template <int BLOCK>
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  v = 0.;
+  if (wid == 0) {
+    v = (lane < BLOCK / 32) ? sh[lane] : 0.;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v; /* valid in thread 0 */
+}
+
+/* ------------------------------------------------------------------ K1: hopping */
+template <int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a) {
+  if (a.st != nullptr && a.st->converged) return; /* CG already stopped: uniform early exit */
+  const int w = blockIdx.x * BLOCK + threadIdx.x;
+  double dsum = 0.;
+  if (w < a.nsites) {
+    int ww = w;
+    if (a.xblock > 0) { /* x-blocked traversal of the (t,x) planes, memory layout unchanged */
+      const int P = a.g.LY * a.g.Lzh, XB = a.xblock;
+      const int plane = ww / P, off = ww - plane * P;
+      const int per = a.g.T * XB;
+      const int xb = plane / per, rem = plane - xb * per;
+      const int t = rem / XB, xi = rem - t * XB;
+      ww = (t * a.g.LX + xb * XB + xi) * P + off;
+    }
+    const int i = a.site0 + ww + (ww >= a.split ? a.gap : 0);
+    tmb_policies pol;
+    pol.stream = tmb_policy_evict_first();
+    pol.reuse = tmb_policy_evict_last();
+    tmb_hop_fields f;
+    f.in = a.in; f.U = a.U; f.halo_up = a.halo_up; f.halo_dn = a.halo_dn; f.Uhalo = a.Uhalo;
+    double2 r[12];
+    tmb_hop_site<DIST, HINTS>(r, f, a.g, a.par, i, a.ka, pol);
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      double2 pc = make_double2(0., 0.);
+      if (MODE >= 2) pc = a.p[(size_t)c * a.g.Vh + i];
+      const double2 o = tmb_epilogue<MODE>(c, r[c], pc, a.cf);
+      if (DOT) {
+        const double2 dw = a.dotw[(size_t)c * a.g.Vh + i];
+        dsum += dw.x * o.x;
+        dsum += dw.y * o.y;
+      }
+      tmb_store_out<HINTS>(a.out + (size_t)c * a.g.Vh + i, o, pol);
+    }
+  }
+  if (DOT) {
+    const double s = block_sum<BLOCK>(dsum);
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = s;
+  }
+}
+
+static int hop_variant_block(int variant);
+int tmb_hop_grid(const tmb_hop_launch &a) { const int b = hop_variant_block(a.variant); return (a.nsites + b - 1) / b; }
+
+template <int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
+static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
+  const int grid = tmb_hop_grid(a);
+  if (grid <= 0) return cudaSuccess;
+  hop_kernel<MODE, DIST, DOT, HINTS, BLOCK, MINB><<<grid, BLOCK, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+/* production configuration: chosen from the sweep in profiles/  */
+#ifndef TMB_HOP_BLOCK
+#define TMB_HOP_BLOCK 128
+#endif
+#ifndef TMB_HOP_MINB
+#define TMB_HOP_MINB 3
+#endif
+
+template <int DIST, int HINTS>
+static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
+  if (a.dot) {
+    if (a.mode != 2) return cudaErrorInvalidValue;
+    return hop_go<2, DIST, 1, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+  }
+  switch (a.mode) {
+    case 0: return hop_go<0, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    case 1: return hop_go<1, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    case 2: return hop_go<2, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    case 3: return hop_go<3, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+/* tuning variants of the plain Hopping_Matrix kernel (MODE 0, no halo): block x min-blocks/SM */
+template <int HINTS>
+static cudaError_t hop_tune(const tmb_hop_launch &a, int variant, cudaStream_t s) {
+  switch (variant) {
+    case 1: return hop_go<0, 0, 0, HINTS, 64, 4>(a, s);
+    case 2: return hop_go<0, 0, 0, HINTS, 64, 6>(a, s);
+    case 3: return hop_go<0, 0, 0, HINTS, 128, 2>(a, s);
+    case 4: return hop_go<0, 0, 0, HINTS, 128, 3>(a, s);
+    case 5: return hop_go<0, 0, 0, HINTS, 128, 4>(a, s);
+    case 6: return hop_go<0, 0, 0, HINTS, 256, 1>(a, s);
+    case 7: return hop_go<0, 0, 0, HINTS, 256, 2>(a, s);
+    case 8: return hop_go<0, 0, 0, HINTS, 96, 4>(a, s);
+    case 9: return hop_go<0, 0, 0, HINTS, 192, 2>(a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+static int hop_variant_block(int variant) {
+  static const int b[10] = {TMB_HOP_BLOCK, 64, 64, 128, 128, 128, 256, 256, 96, 192};
+  return (variant >= 0 && variant < 10) ? b[variant] : TMB_HOP_BLOCK;
+}
+
+cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s) {
+  const int variant = a.variant;
+  if (variant > 0) {
+    if (a.mode != 0 || a.dist || a.dot) return cudaErrorInvalidValue;
+    return a.hints ? hop_tune<1>(a, variant, s) : hop_tune<0>(a, variant, s);
+  }
+  if (a.dist) return a.hints ? hop_mode<1, 1>(a, s) : hop_mode<1, 0>(a, s);
+  return a.hints ? hop_mode<0, 1>(a, s) : hop_mode<0, 0>(a, s);
+}
+
+/* ------------------------------------------------------------------ K4: reductions */
+#define RED_BLOCK 256
+int tmb_red_grid(size_t n2) {
+  size_t need = (n2 + RED_BLOCK - 1) / RED_BLOCK;
+  size_t cap = (size_t)TMB_SMS * 8;
+  return (int)(need < cap ? (need ? need : 1) : cap);
+}
+
+struct RedNorm2 {
+  const double2 *a;
+  __device__ double operator()(size_t k) const { const double2 v = a[k]; return v.x * v.x + v.y * v.y; }
+};
+struct RedDot { /* Re <a,b> = sum a.re*b.re + a.im*b.im   (linalg/scalar_prod_r.c:159-163) */
+  const double2 *a, *b;
+  __device__ double operator()(size_t k) const { const double2 v = a[k], w = b[k]; return v.x * w.x + v.y * w.y; }
+};
+struct RedXpayNorm { /* R = c R + S, |R|^2   (linalg/assign_mul_add_r_and_square.c:145) */
+  double2 *r; const double2 *sv; double c;
+  __device__ double operator()(size_t k) const {
+    double2 v = r[k]; const double2 w = sv[k];
+    v.x = c * v.x + w.x; v.y = c * v.y + w.y; r[k] = v;
+    return v.x * v.x + v.y * v.y;
+  }
+};
+struct RedCgXR { /* x += alpha p ; r -= alpha Ap ; |r|^2      (cg_her.c:95-101) */
+  double2 *x, *r; const double2 *p, *ap; const tmb_cg_state *st;
+  __device__ double operator()(size_t k) const {
+    const double al = st->alpha;
+    double2 xv = x[k]; const double2 pv = p[k];
+    xv.x += al * pv.x; xv.y += al * pv.y; x[k] = xv;
+    double2 rv = r[k]; const double2 av = ap[k];
+    rv.x = rv.x - al * av.x; rv.y = rv.y - al * av.y; r[k] = rv;
+    return rv.x * rv.x + rv.y * rv.y;
+  }
+};
+
+template <class F>
+__global__ void __launch_bounds__(RED_BLOCK) red_kernel(F f, size_t n2, double *partial, const tmb_cg_state *st) {
+  if (st != nullptr && st->converged) return;
+  double acc = 0.;
+  for (size_t k = (size_t)blockIdx.x * RED_BLOCK + threadIdx.x; k < n2; k += (size_t)gridDim.x * RED_BLOCK)
+    acc += f(k);
+  const double s = block_sum<RED_BLOCK>(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__device__ void cg_apply(tmb_cg_state *st, int slot, int op) {
+  const double sum = st->tmp[slot];
+  if (op == TMB_FIN_CG_PRO) {
+    st->pro = sum;
+    st->alpha = st->normsq / sum;
+  } else if (op == TMB_FIN_CG_ERR) {
+    st->err = sum;
+    st->iter += 1;
+    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
+    if (sum <= thr) {
+      st->converged = 1;
+    } else {
+      st->beta = sum / st->normsq;
+      st->normsq = sum;
+    }
+  } else if (op == TMB_FIN_CG_INIT) {
+    st->normsq = sum;
+  }
+}
+
+/* one CTA: sums the block partials in a fixed order (deterministic), then the CG bookkeeping */
+__global__ void __launch_bounds__(RED_BLOCK) final_kernel(const double *partial, int n, tmb_cg_state *st, int slot,
+                                                           int op, int apply) {
+  if (op != TMB_FIN_STORE && st->converged) return;
+  double acc = 0.;
+  for (int k = threadIdx.x; k < n; k += RED_BLOCK) acc += partial[k];
+  const double s = block_sum<RED_BLOCK>(acc);
+  if (threadIdx.x == 0) {
+    st->tmp[slot] = s;
+    if (apply) cg_apply(st, slot, op);
+  }
+}
+__global__ void apply_kernel(tmb_cg_state *st, int slot, int op) {
+  if (st->converged) return;
+  cg_apply(st, slot, op);
+}
+
+cudaError_t tmb_launch_final(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
+                             cudaStream_t s) {
+  final_kernel<<<1, RED_BLOCK, 0, s>>>(partial, n, st, slot, op, apply);
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s) {
+  apply_kernel<<<1, 1, 0, s>>>(st, slot, op);
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_norm2(const double2 *a, size_t n2, double *partial, cudaStream_t s) {
+  RedNorm2 f = {a};
+  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, nullptr);
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_dot(const double2 *a, const double2 *b, size_t n2, double *partial, cudaStream_t s) {
+  RedDot f = {a, b};
+  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, nullptr);
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s) {
+  RedXpayNorm f = {r, sv, c};
+  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, nullptr);
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_cg_update_xr(double2 *x, double2 *r, const double2 *p, const double2 *ap, size_t n2,
+                                    const tmb_cg_state *st, double *partial, cudaStream_t s) {
+  RedCgXR f = {x, r, p, ap, st};
+  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ K3: elementwise */
+template <class F>
+__global__ void __launch_bounds__(256) ew_kernel(F f, size_t n2, const tmb_cg_state *st) {
+  if (st != nullptr && st->converged) return;
+  for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < n2; k += (size_t)gridDim.x * 256) f(k);
+}
+static int ew_grid(size_t n2) {
+  size_t need = (n2 + 255) / 256, cap = (size_t)TMB_SMS * 16;
+  return (int)(need < cap ? (need ? need : 1) : cap);
+}
+#define EW_LAUNCH(f, n2, st, s) \
+  do { ew_kernel<<<ew_grid(n2), 256, 0, s>>>(f, n2, st); return cudaGetLastError(); } while (0)
+
+struct EwAxpy { double2 *p; const double2 *q; double c; /* P += c Q  (linalg/assign_add_mul_r.c:346) */
+  __host__ __device__ void operator()(size_t k) const { double2 v = p[k]; const double2 w = q[k]; v.x += c * w.x; v.y += c * w.y; p[k] = v; } };
+struct EwXpay { double2 *r; const double2 *sv; double c; /* R = c R + S  (linalg/assign_mul_add_r.c:340) */
+  __host__ __device__ void operator()(size_t k) const { double2 v = r[k]; const double2 w = sv[k]; v.x = c * v.x + w.x; v.y = c * v.y + w.y; r[k] = v; } };
+struct EwLin { double2 *q; const double2 *r, *sv; double a, b; /* Q = a R + b S  (diff.c:270, add.c) */
+  __host__ __device__ void operator()(size_t k) const { const double2 v = r[k], w = sv[k]; q[k] = make_double2(a * v.x + b * w.x, a * v.y + b * w.y); } };
+struct EwScale { double2 *r; const double2 *sv; double c; /* R = c S  (linalg/mul_r.c:40) */
+  __host__ __device__ void operator()(size_t k) const { const double2 w = sv[k]; r[k] = make_double2(c * w.x, c * w.y); } };
+struct EwG5 { double2 *l; const double2 *kk; size_t half; /* gamma.c:77-98 */
+  __host__ __device__ void operator()(size_t k) const { const double2 w = kk[k]; l[k] = (k < half) ? w : make_double2(-w.x, -w.y); } };
+struct EwDiag { double2 *l; const double2 *kk; double2 z; size_t half; /* (z | conj z) k : tm_operators.c:669, mul_one_pm_imu_inv_body.c */
+  __host__ __device__ void operator()(size_t k) const { l[k] = c_mul((k < half) ? z : c_conj(z), kk[k]); } };
+struct EwDiagSub { double2 *l; const double2 *kk, *jj; double2 z; int g5; size_t half; /* tm_operators.c:813-857 */
+  __host__ __device__ void operator()(size_t k) const {
+    const bool up = k < half;
+    const double2 zk = c_mul(up ? z : c_conj(z), kk[k]); const double2 j = jj[k];
+    l[k] = (up || !g5) ? c_sub(zk, j) : c_sub(j, zk);
+  } };
+struct EwCgP { double2 *p; const double2 *r; const tmb_cg_state *st; /* p = beta p + r  (cg_her.c:122) */
+  __host__ __device__ void operator()(size_t k) const { const double b = st->beta; double2 v = p[k]; const double2 w = r[k]; v.x = b * v.x + w.x; v.y = b * v.y + w.y; p[k] = v; } };
+/* tm_operators_nd.c:639-695 */
+struct EwNdMeeInv { double2 *ls, *lc; const double2 *ks, *kc; double mu, eps, nrm; size_t half;
+  __host__ __device__ void operator()(size_t k) const {
+    const double2 zs = make_double2(1., (k < half) ? -mu : mu), zc = c_conj(zs);
+    const double2 s = ks[k], c = kc[k];
+    double2 a = c_mul(zs, s); a.x += eps * c.x; a.y += eps * c.y;
+    double2 b = c_mul(zc, c); b.x += eps * s.x; b.y += eps * s.y;
+    ls[k] = make_double2(nrm * a.x, nrm * a.y); lc[k] = make_double2(nrm * b.x, nrm * b.y);
+  } };
+/* tm_operators_nd.c:698-756 */
+struct EwNdMooSubG5 { double2 *ls, *lc; const double2 *ks, *kc, *js, *jc; double mu, eps; size_t half;
+  __host__ __device__ void operator()(size_t k) const {
+    const bool up = k < half;
+    const double2 zs = make_double2(1., up ? -mu : mu), zc = c_conj(zs);
+    const double2 s = ks[k], c = kc[k], ts = js[k], tc = jc[k];
+    double2 a = c_mul(zs, s); a.x += eps * c.x; a.y += eps * c.y;
+    double2 b = c_mul(zc, c); b.x += eps * s.x; b.y += eps * s.y;
+    ls[k] = up ? c_sub(a, ts) : c_sub(ts, a); lc[k] = up ? c_sub(b, tc) : c_sub(tc, b);
+  } };
+
+cudaError_t tmb_launch_axpy(double2 *p, const double2 *q, double c, size_t n2, cudaStream_t s) { EwAxpy f = {p, q, c}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_xpay(double2 *r, double c, const double2 *sv, size_t n2, cudaStream_t s) { EwXpay f = {r, sv, c}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_lincomb(double2 *q, double a, const double2 *r, double b, const double2 *sv, size_t n2, cudaStream_t s) { EwLin f = {q, r, sv, a, b}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_scale(double2 *r, double c, const double2 *sv, size_t n2, cudaStream_t s) { EwScale f = {r, sv, c}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_gamma5(double2 *l, const double2 *k, size_t n2, size_t half, cudaStream_t s) { EwG5 f = {l, k, half}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_diag(double2 *l, const double2 *k, double2 z, size_t n2, size_t half, cudaStream_t s) { EwDiag f = {l, k, z, half}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_diag_sub(double2 *l, const double2 *k, const double2 *j, double2 z, int g5, size_t n2, size_t half, cudaStream_t s) { EwDiagSub f = {l, k, j, z, g5, half}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_cg_update_p(double2 *p, const double2 *r, size_t n2, const tmb_cg_state *st, cudaStream_t s) { EwCgP f = {p, r, st}; EW_LAUNCH(f, n2, st, s); }
+cudaError_t tmb_launch_nd_mee_inv(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc, double mu, double eps, size_t n2, size_t half, cudaStream_t s) {
+  EwNdMeeInv f = {ls, lc, ks, kc, mu, eps, 1. / (1. + mu * mu - eps * eps), half}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_nd_moo_sub_g5(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc, const double2 *js, const double2 *jc, double mu, double eps, size_t n2, size_t half, cudaStream_t s) {
+  EwNdMooSubG5 f = {ls, lc, ks, kc, js, jc, mu, eps, half}; EW_LAUNCH(f, n2, nullptr, s); }
+
+/* ------------------------------------------------------------------ layout conversion */
+/* host AoS spinor (su3.h:60-63: 12 complex per site, site-major)  <->  device SoA [12][Vh] */
+struct EwPackEo { double2 *soa; const double2 *aos; int Vh;
+  __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / Vh), i = (int)(k - (size_t)c * Vh); soa[k] = aos[(size_t)i * 12 + c]; } };
+struct EwUnpackEo { double2 *aos; const double2 *soa; int Vh;
+  __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / Vh), i = (int)(k - (size_t)c * Vh); aos[(size_t)i * 12 + c] = soa[k]; } };
+/* lexicographic host field of V sites <-> (even, odd) device fields (linalg/convert_eo_to_lexic.c:35-115) */
+struct EwPackLex { double2 *even, *odd; const double2 *lex; tmb_geom g;
+  __host__ __device__ void operator()(size_t k) const {
+    const size_t per = (size_t)12 * g.Vh; const int par = (int)(k / per); const size_t kk = k - par * per;
+    const int c = (int)(kk / g.Vh), i = (int)(kk - (size_t)c * g.Vh);
+    const int ix = tmb_eo_to_lexic(g, par, i);
+    (par ? odd : even)[kk] = lex[(size_t)ix * 12 + c];
+  } };
+struct EwUnpackLex { double2 *lex; const double2 *even, *odd; tmb_geom g;
+  __host__ __device__ void operator()(size_t k) const {
+    const size_t per = (size_t)12 * g.Vh; const int par = (int)(k / per); const size_t kk = k - par * per;
+    const int c = (int)(kk / g.Vh), i = (int)(kk - (size_t)c * g.Vh);
+    const int ix = tmb_eo_to_lexic(g, par, i);
+    lex[(size_t)ix * 12 + c] = (par ? odd : even)[kk];
+  } };
+/* host gauge g_gauge_field[ix][mu] (init/init_gauge_field.c:51-68, su3 = 9 complex row-major)
+ * -> U[((q*4+mu)*9+e)*Vh + i] */
+struct EwPackGauge { double2 *U; const double2 *lex; tmb_geom g;
+  __host__ __device__ void operator()(size_t k) const {
+    const int i = (int)(k % g.Vh); const int row = (int)(k / g.Vh); /* row = (q*4+mu)*9+e */
+    const int e = row % 9, qm = row / 9, mu = qm & 3, q = qm >> 2;
+    const int ix = tmb_eo_to_lexic(g, q, i);
+    U[k] = lex[((size_t)ix * 4 + mu) * 9 + e];
+  } };
+struct EwPackHalo { double2 *up, *dn; const double2 *in; tmb_geom g;
+  __host__ __device__ void operator()(size_t k) const { /* k in [0, 6*S) */
+    const int c = (int)(k / g.S), j = (int)(k - (size_t)c * g.S);
+    const size_t last = (size_t)(g.T - 1) * g.S + j;
+    const double2 a = in[(size_t)c * g.Vh + last], b = in[(size_t)(c + 6) * g.Vh + last];
+    up[k] = c_sub(a, b);                 /* (1-g0): s0-s2, s1-s3 of the last slice -> rank+1 */
+    const double2 a0 = in[(size_t)c * g.Vh + j], b0 = in[(size_t)(c + 6) * g.Vh + j];
+    dn[k] = c_add(a0, b0);               /* (1+g0): s0+s2, s1+s3 of the first slice -> rank-1 */
+  } };
+struct EwPackGaugeHalo { double2 *out; const double2 *U; tmb_geom g;
+  __host__ __device__ void operator()(size_t k) const { /* k in [0, 2*9*S) : out[(q*9+e)*S + j] */
+    const int j = (int)(k % g.S); const int qe = (int)(k / g.S); const int e = qe % 9, q = qe / 9;
+    out[k] = U[(size_t)((q * 4 + 0) * 9 + e) * g.Vh + (size_t)(g.T - 1) * g.S + j];
+  } };
+
+cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStream_t s) { EwPackEo f = {soa, aos, Vh}; EW_LAUNCH(f, (size_t)12 * Vh, nullptr, s); }
+cudaError_t tmb_launch_unpack_eo(double2 *aos, const double2 *soa, int Vh, cudaStream_t s) { EwUnpackEo f = {aos, soa, Vh}; EW_LAUNCH(f, (size_t)12 * Vh, nullptr, s); }
+cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackLex f = {even, odd, lex, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
+cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s) { EwUnpackLex f = {lex, even, odd, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
+cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackGauge f = {U, lex, g}; EW_LAUNCH(f, (size_t)72 * g.Vh, nullptr, s); }
+cudaError_t tmb_launch_pack_halo(double2 *up, double2 *dn, const double2 *in, tmb_geom g, cudaStream_t s) { EwPackHalo f = {up, dn, in, g}; EW_LAUNCH(f, (size_t)6 * g.S, nullptr, s); }
+cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s) { EwPackGaugeHalo f = {out, U, g}; EW_LAUNCH(f, (size_t)18 * g.S, nullptr, s); }

@@ -1,0 +1,89 @@
+/* tmb_kernels.h - internal C++ interface between the C-ABI layer (tmb_capi.cu) and the
+ * CUDA kernels (tmb_kernels.cu).  Not installed; the public interface is include/tmlqcd_b200.h. */
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "tmb_geom.h"
+
+/* Device-resident scalar block of the CG (solver/cg_her.c:62-143 keeps these on the host;
+ * here they never leave HBM during the iteration, kernels read them directly). */
+struct tmb_cg_state {
+  double normsq;   /* (r,r) of the previous iteration */
+  double pro;      /* (p, A p) */
+  double err;      /* (r,r) new */
+  double alpha, beta;
+  double sqnorm_q; /* |Q|^2, for rel_prec */
+  double eps_sq;
+  double tmp[4];   /* landing slots of reductions (all-reduced in place when nranks > 1) */
+  int rel_prec;
+  int converged;   /* set on device when err <= eps_sq (* sqnorm_q); later kernels become no-ops */
+  int iter;        /* iterations completed */
+  int pad;
+};
+
+enum tmb_fin_op {
+  TMB_FIN_STORE = 0,   /* tmp[slot] = sum */
+  TMB_FIN_CG_PRO = 1,  /* pro = sum; alpha = normsq/pro              cg_her.c:93-94 */
+  TMB_FIN_CG_ERR = 2,  /* err = sum; iter++; stop test; beta; normsq cg_her.c:101-126 */
+  TMB_FIN_CG_INIT = 3  /* normsq = sum                               cg_her.c:88 */
+};
+
+struct tmb_hop_launch {
+  const double2 *in; double2 *out; const double2 *p; const double2 *dotw;
+  const double2 *U; const double2 *halo_up, *halo_dn, *Uhalo;
+  double *partial;          /* fused-dot block partials (DOT) */
+  const tmb_cg_state *st;   /* if non-null: kernel exits immediately when st->converged */
+  tmb_geom g;
+  int par;                  /* parity of the OUTPUT sites = ieo of Hopping_Matrix(ieo,l,k) */
+  double2 ka[4]; double2 cf;
+  int mode;                 /* epilogue 0..3, see tmb_site.cuh */
+  int dist;                 /* 1: +-t of the boundary slices from halo buffers */
+  int dot;                  /* 1: accumulate Re<dotw, out> into partial[] */
+  int hints;                /* 1: L1/L2 cache-policy loads */
+  int variant;              /* 0: production kernel; 1..9: tuning variants of the plain kernel */
+  int site0, nsites;        /* contiguous work range ... */
+  int split, gap;           /* ... with a hole: i = site0 + w + (w >= split ? gap : 0) */
+  int xblock;               /* >0: traverse (t,x) planes x-blocked for L2 locality */
+};
+
+int tmb_hop_grid(const tmb_hop_launch &a);
+cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s);
+
+/* reductions: block partials -> one scalar in st->tmp[slot] (+ optional CG bookkeeping) */
+cudaError_t tmb_launch_final(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
+                             cudaStream_t s);
+cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s);
+int tmb_red_grid(size_t n2);
+cudaError_t tmb_launch_norm2(const double2 *a, size_t n2, double *partial, cudaStream_t s);
+cudaError_t tmb_launch_dot(const double2 *a, const double2 *b, size_t n2, double *partial, cudaStream_t s);
+cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s);
+cudaError_t tmb_launch_cg_update_xr(double2 *x, double2 *r, const double2 *p, const double2 *ap, size_t n2,
+                                    const tmb_cg_state *st, double *partial, cudaStream_t s);
+cudaError_t tmb_launch_cg_update_p(double2 *p, const double2 *r, size_t n2, const tmb_cg_state *st, cudaStream_t s);
+
+/* elementwise, n2 = 12*Vh double2 elements; `half` = 6*Vh separates spin 0,1 from spin 2,3 */
+cudaError_t tmb_launch_axpy(double2 *p, const double2 *q, double c, size_t n2, cudaStream_t s);
+cudaError_t tmb_launch_xpay(double2 *r, double c, const double2 *sv, size_t n2, cudaStream_t s);
+cudaError_t tmb_launch_lincomb(double2 *q, double a, const double2 *r, double b, const double2 *sv, size_t n2, cudaStream_t s);
+cudaError_t tmb_launch_scale(double2 *r, double c, const double2 *sv, size_t n2, cudaStream_t s);
+cudaError_t tmb_launch_gamma5(double2 *l, const double2 *k, size_t n2, size_t half, cudaStream_t s);
+cudaError_t tmb_launch_diag(double2 *l, const double2 *k, double2 z, size_t n2, size_t half, cudaStream_t s);
+/* l = (g5?) ( (z|conj z) k - j ) */
+cudaError_t tmb_launch_diag_sub(double2 *l, const double2 *k, const double2 *j, double2 z, int g5, size_t n2,
+                                size_t half, cudaStream_t s);
+cudaError_t tmb_launch_nd_mee_inv(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc, double mu,
+                                  double eps, size_t n2, size_t half, cudaStream_t s);
+cudaError_t tmb_launch_nd_moo_sub_g5(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc,
+                                     const double2 *js, const double2 *jc, double mu, double eps, size_t n2,
+                                     size_t half, cudaStream_t s);
+
+/* layout conversion between the reference's host AoS layouts and the device SoA layout */
+cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStream_t s);
+cudaError_t tmb_launch_unpack_eo(double2 *aos, const double2 *soa, int Vh, cudaStream_t s);
+cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s);
+cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s);
+cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s);
+/* T-face half-spinors: send_up = (1-g0) proj of the last slice, send_dn = (1+g0) proj of the first */
+cudaError_t tmb_launch_pack_halo(double2 *send_up, double2 *send_dn, const double2 *in, tmb_geom g, cudaStream_t s);
+/* Uhalo[q][e][j] = U[q][0][e][(T-1)S + j] : what rank+1 needs from this rank */
+cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s);

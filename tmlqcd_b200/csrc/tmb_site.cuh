@@ -1,0 +1,239 @@
+/* tmb_site.cuh - per-site arithmetic of the even/odd Wilson hopping term, written once as
+ * __host__ __device__ code: the CUDA kernels in tmb_kernels.cu call it on the device; the
+ * CPU-only logic tests compile the very same functions for the host (tests/emul/) to check
+ * layout, neighbour arithmetic and spin algebra without a GPU.  The shipped library has no
+ * host compute path: nothing in tmlqcd_b200/csrc calls these functions from host code.
+ *
+ * What is computed (reference: operator/hopping.h:574-694 generic-C macros, index walk
+ * operator/hopping_body_dbl.c:64-181):
+ *   r(x) = sum_mu [ ka_mu U_mu(x) (1+g_mu)-proj k(x+mu) + conj(ka_mu) U_mu(x-mu)^+ (1-g_mu)-proj k(x-mu) ]
+ *
+ * Device layout (B200-first, not the reference's AoS):
+ *   spinor field  f[c*Vh + i]                 c = 3*spin+colour (12), i = eo-sub site, double2 = (re,im)
+ *   gauge field   U[((q*4+mu)*9 + e)*Vh + i]  q = parity of the site that owns the forward link,
+ *                                             e = 3*row+col; each link stored ONCE (4V links);
+ *                                             the backward hop gathers U[1-p][mu][.][nb] at the
+ *                                             same neighbour index as the neighbour spinor.
+ * Every load of a warp is 32 consecutive double2 = 512 contiguous bytes (128-bit per thread).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include "tmb_geom.h"
+
+/* ---------------- loads with cache policy ---------------- */
+#if defined(__CUDACC__)
+/* gauge links: read exactly once per hop -> do not allocate in L1, evict-first in L2 so the
+ * 126 MB L2 keeps the input spinor (8-fold reuse) resident across time-slices */
+__device__ __forceinline__ double2 tmb_ld_stream(const double2 *p, unsigned long long pol) {
+  double2 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+      : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+/* neighbour spinors: reused by 8 output sites -> keep in L1/L2 */
+__device__ __forceinline__ double2 tmb_ld_reuse(const double2 *p, unsigned long long pol) {
+  double2 v;
+  asm("ld.global.nc.L1::evict_last.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+      : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void tmb_st_stream(double2 *p, double2 v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;"
+               :: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned long long tmb_policy_evict_first() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long tmb_policy_evict_last() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+#endif
+
+struct tmb_policies { unsigned long long stream, reuse; };
+
+template <int HINTS>
+TMB_HD double2 tmb_load_gauge(const double2 *p, const tmb_policies &pol) {
+#if defined(__CUDA_ARCH__)
+  if (HINTS) return tmb_ld_stream(p, pol.stream);
+  return __ldg(p);
+#else
+  (void)pol; return *p;
+#endif
+}
+template <int HINTS>
+TMB_HD double2 tmb_load_spinor(const double2 *p, const tmb_policies &pol) {
+#if defined(__CUDA_ARCH__)
+  if (HINTS) return tmb_ld_reuse(p, pol.reuse);
+  return __ldg(p);
+#else
+  (void)pol; return *p;
+#endif
+}
+template <int HINTS>
+TMB_HD void tmb_store_out(double2 *p, double2 v, const tmb_policies &pol) {
+#if defined(__CUDA_ARCH__)
+  if (HINTS) { tmb_st_stream(p, v, pol.stream); return; }
+  *p = v;
+#else
+  (void)pol; *p = v;
+#endif
+}
+
+/* ---------------- complex helpers on double2 ---------------- */
+TMB_HD double2 c_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+TMB_HD double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+TMB_HD double2 c_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+TMB_HD double2 c_mulc(double2 a, double2 b) { /* conj(a)*b */
+  return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+TMB_HD double2 c_conj(double2 a) { return make_double2(a.x, -a.y); }
+TMB_HD void c_mad(double2 &acc, double2 a, double2 b) { /* acc += a*b */
+  acc.x += a.x * b.x; acc.x -= a.y * b.y; acc.y += a.x * b.y; acc.y += a.y * b.x;
+}
+TMB_HD void c_madc(double2 &acc, double2 a, double2 b) { /* acc += conj(a)*b */
+  acc.x += a.x * b.x; acc.x += a.y * b.y; acc.y += a.x * b.y; acc.y -= a.y * b.x;
+}
+/* x + coef*y, coef code: 0:+1  1:-1  2:+i  3:-i */
+template <int C> TMB_HD double2 c_comb(double2 x, double2 y) {
+  if (C == 0) return make_double2(x.x + y.x, x.y + y.y);
+  if (C == 1) return make_double2(x.x - y.x, x.y - y.y);
+  if (C == 2) return make_double2(x.x - y.y, x.y + y.x);
+  return make_double2(x.x + y.y, x.y - y.x);
+}
+/* the conjugate coefficient: 0->0, 1->1, 2->3, 3->2 */
+template <int C> struct conj_code { static const int v = (C < 2) ? C : (5 - C); };
+
+/* ---------------- projector table, hopping.h:578-672 ----------------
+ * direction D = 2*mu + (0 forward | 1 backward):  a = s0 + CA*s[PA],  b = s1 + CB*s[PB]
+ * reconstruction:  r0 += phi_a, r[PA] += conj(CA) phi_a, r1 += phi_b, r[PB] += conj(CB) phi_b */
+template <int D> struct hop_tab;
+template <> struct hop_tab<0> { static const int PA = 2, CA = 0, PB = 3, CB = 0; };
+template <> struct hop_tab<1> { static const int PA = 2, CA = 1, PB = 3, CB = 1; };
+template <> struct hop_tab<2> { static const int PA = 3, CA = 2, PB = 2, CB = 2; };
+template <> struct hop_tab<3> { static const int PA = 3, CA = 3, PB = 2, CB = 3; };
+template <> struct hop_tab<4> { static const int PA = 3, CA = 0, PB = 2, CB = 1; };
+template <> struct hop_tab<5> { static const int PA = 3, CA = 1, PB = 2, CB = 0; };
+template <> struct hop_tab<6> { static const int PA = 2, CA = 2, PB = 3, CB = 3; };
+template <> struct hop_tab<7> { static const int PA = 2, CA = 3, PB = 3, CB = 2; };
+
+/* half-spinor of direction D from a full neighbour spinor at SoA index n */
+template <int D, int HINTS>
+TMB_HD void tmb_project(double2 a[3], double2 b[3], const double2 *__restrict__ in, int Vh, int n,
+                        const tmb_policies &pol) {
+  typedef hop_tab<D> Tb;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double2 s0 = tmb_load_spinor<HINTS>(in + (size_t)(0 + c) * Vh + n, pol);
+    double2 s1 = tmb_load_spinor<HINTS>(in + (size_t)(3 + c) * Vh + n, pol);
+    double2 sa = tmb_load_spinor<HINTS>(in + (size_t)(3 * Tb::PA + c) * Vh + n, pol);
+    double2 sb = tmb_load_spinor<HINTS>(in + (size_t)(3 * Tb::PB + c) * Vh + n, pol);
+    a[c] = c_comb<Tb::CA>(s0, sa);
+    b[c] = c_comb<Tb::CB>(s1, sb);
+  }
+}
+
+/* phi = c * (U a) for forward, c * (U^dagger a) for backward (su3.h:308-316), then scatter */
+template <int D>
+TMB_HD void tmb_link_accumulate(double2 r[12], const double2 u[9], const double2 a[3], const double2 b[3],
+                                double2 ka) {
+  typedef hop_tab<D> Tb;
+  const int BWD = D & 1;
+  const double2 c = BWD ? c_conj(ka) : ka;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double2 xa = make_double2(0., 0.), xb = make_double2(0., 0.);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (BWD) { c_madc(xa, u[3 * j + i], a[j]); c_madc(xb, u[3 * j + i], b[j]); }
+      else     { c_mad(xa, u[3 * i + j], a[j]);  c_mad(xb, u[3 * i + j], b[j]); }
+    }
+    xa = c_mul(c, xa); xb = c_mul(c, xb);
+    r[0 + i] = c_add(r[0 + i], xa);
+    r[3 + i] = c_add(r[3 + i], xb);
+    r[3 * Tb::PA + i] = c_comb<conj_code<Tb::CA>::v>(r[3 * Tb::PA + i], xa);
+    r[3 * Tb::PB + i] = c_comb<conj_code<Tb::CB>::v>(r[3 * Tb::PB + i], xb);
+  }
+}
+
+struct tmb_hop_fields {
+  const double2 *in;      /* k : field of the opposite parity, 12*Vh double2 */
+  const double2 *U;       /* gauge, [2][4][9][Vh] */
+  const double2 *halo_up; /* dist_t: [6][S] (1+g0)-projected first slice of rank+1 */
+  const double2 *halo_dn; /* dist_t: [6][S] (1-g0)-projected last slice of rank-1 */
+  const double2 *Uhalo;   /* dist_t: [2][9][S] U_0 of rank-1's last slice, by owner parity */
+};
+
+template <int D, int HINTS>
+TMB_HD void tmb_hop_dir(double2 r[12], const tmb_hop_fields &f, const tmb_geom &g, int par, int i, int n,
+                        double2 ka, const tmb_policies &pol) {
+  const int mu = D >> 1, BWD = D & 1;
+  double2 a[3], b[3], u[9];
+  /* forward link lives at the output site (parity par), backward link at the neighbour (parity 1-par) */
+  const double2 *ub = f.U + (size_t)(((BWD ? 1 - par : par) * 4 + mu) * 9) * g.Vh + (BWD ? n : i);
+#pragma unroll
+  for (int e = 0; e < 9; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
+  tmb_project<D, HINTS>(a, b, f.in, g.Vh, n, pol);
+  tmb_link_accumulate<D>(r, u, a, b, ka);
+}
+
+/* halo variants for the distributed T direction: the half-spinor arrives already projected */
+template <int D, int HINTS>
+TMB_HD void tmb_hop_dir_halo(double2 r[12], const tmb_hop_fields &f, const tmb_geom &g, int par, int i, int j,
+                             double2 ka, const tmb_policies &pol) {
+  double2 a[3], b[3], u[9];
+  if (D == 0) { /* +t at t == T-1: local forward link, half-spinor from rank+1 */
+    const double2 *ub = f.U + (size_t)((par * 4 + 0) * 9) * g.Vh + i;
+#pragma unroll
+    for (int e = 0; e < 9; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { a[c] = f.halo_up[(size_t)c * g.S + j]; b[c] = f.halo_up[(size_t)(3 + c) * g.S + j]; }
+  } else {      /* -t at t == 0: link and half-spinor from rank-1 */
+    const double2 *ub = f.Uhalo + (size_t)((1 - par) * 9) * g.S + j;
+#pragma unroll
+    for (int e = 0; e < 9; e++) u[e] = ub[(size_t)e * g.S];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { a[c] = f.halo_dn[(size_t)c * g.S + j]; b[c] = f.halo_dn[(size_t)(3 + c) * g.S + j]; }
+  }
+  tmb_link_accumulate<D>(r, u, a, b, ka);
+}
+
+/* The full 8-direction sum for output site i of parity par.  ka[mu] = kappa*exp(i theta_mu pi/L_mu)
+ * exactly as boundary.c:40-55 computes them on the host. */
+template <int DIST, int HINTS>
+TMB_HD void tmb_hop_site(double2 r[12], const tmb_hop_fields &f, const tmb_geom &g, int par, int i,
+                         const double2 ka[4], const tmb_policies &pol) {
+  int nb[8];
+  const int t = tmb_neighbours(g, par, i, nb);
+#pragma unroll
+  for (int c = 0; c < 12; c++) r[c] = make_double2(0., 0.);
+  if (DIST && t == g.T - 1) tmb_hop_dir_halo<0, HINTS>(r, f, g, par, i, i - t * g.S, ka[0], pol);
+  else                      tmb_hop_dir<0, HINTS>(r, f, g, par, i, nb[0], ka[0], pol);
+  if (DIST && t == 0)       tmb_hop_dir_halo<1, HINTS>(r, f, g, par, i, i, ka[0], pol);
+  else                      tmb_hop_dir<1, HINTS>(r, f, g, par, i, nb[1], ka[0], pol);
+  tmb_hop_dir<2, HINTS>(r, f, g, par, i, nb[2], ka[1], pol);
+  tmb_hop_dir<3, HINTS>(r, f, g, par, i, nb[3], ka[1], pol);
+  tmb_hop_dir<4, HINTS>(r, f, g, par, i, nb[4], ka[2], pol);
+  tmb_hop_dir<5, HINTS>(r, f, g, par, i, nb[5], ka[2], pol);
+  tmb_hop_dir<6, HINTS>(r, f, g, par, i, nb[6], ka[3], pol);
+  tmb_hop_dir<7, HINTS>(r, f, g, par, i, nb[7], ka[3], pol);
+}
+
+/* Epilogues (hopping.h:674-694):
+ *   MODE 0  l = r                                   _store_res                 Hopping_Matrix
+ *   MODE 1  l = (cf on s0,s1 | conj(cf) on s2,s3) r _hop_mul_g5_cmplx_and_store tm_times_Hopping_Matrix
+ *   MODE 2  l = g5( (cf|conj cf) p - r )            _g5_cmplx_sub_hop_and_g5store tm_sub_Hopping_Matrix
+ *   MODE 3  l = (cf|conj cf) p - r                  (M_full / D_psi rows: tm_operators.c:117-128)
+ */
+template <int MODE>
+TMB_HD double2 tmb_epilogue(int c, double2 r, double2 p, double2 cf) {
+  if (MODE == 0) return r;
+  const double2 f = (c < 6) ? cf : c_conj(cf);
+  if (MODE == 1) return c_mul(f, r);
+  const double2 zp = c_mul(f, p);
+  if (MODE == 2) return (c < 6) ? c_sub(zp, r) : c_sub(r, zp);
+  return c_sub(zp, r);
+}
