@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Multi-GPU parity: torchrun --nproc-per-node N scripts/mgpu_parity.py
+The GLOBAL lattice (T = N*T_loc) is generated identically on every rank; rank r takes its T-slab
+(the reference's PARALLELT decomposition, mpi_init.c:321), runs the distributed operators / CG with
+NCCL half-spinor halos, and rank 0 compares the gathered result with the CPU oracle on the global
+lattice (the decomposition-independence recipe of SURVEY 4: reproducible global fields)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import tmlqcd_b200 as tm  # noqa: E402
+from conftest import random_gauge, random_spinor, rel_l2  # noqa: E402
+from oracle.oracleclient import Oracle  # noqa: E402
+
+KAPPA, GMU, THETA = 0.16, 0.0032, (1., 0., 0.3, 0.)
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    Tl, LX, LY, LZ = (int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "8x8x8x8").split("x"))
+    T = Tl * world
+    rng = np.random.default_rng(2024)
+    V, Vh = T * LX * LY * LZ, T * LX * LY * LZ // 2
+    g = random_gauge(rng, V)
+    k, p = random_spinor(rng, Vh), random_spinor(rng, Vh)
+    Vl, Vhl = V // world, Vh // world
+    sl, slh = slice(rank * Vl, (rank + 1) * Vl), slice(rank * Vhl, (rank + 1) * Vhl)
+
+    d = tm.Device(Tl, LX, LY, LZ, device=lr)
+    idbuf = (C.c_ubyte * 128)()
+    if rank == 0:
+        d.ck(d.lib.tmb_comm_unique_id(C.cast(idbuf, C.c_void_p)))
+    t_id = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t_id, 0)
+    idbuf = (C.c_ubyte * 128)(*t_id.cpu().tolist())
+    d.ck(d.lib.tmb_comm_init(C.cast(idbuf, C.c_void_p), world, rank))
+    d.set_params(KAPPA, GMU, THETA)
+    d.gauge_upload(g[sl])
+
+    def gather(field):
+        loc = torch.from_numpy(d.download(field)).cuda()
+        out = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(out, loc)
+        return torch.cat(out).cpu().numpy()
+
+    dk, dp, dl, dx = d.field(k[slh]), d.field(p[slh]), d.field(), d.field()
+    res = {}
+    for ieo in (0, 1):
+        d.call("Hopping_Matrix", ieo, dl, dk); res[f"hop{ieo}"] = gather(dl)
+        d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3); res[f"tm_sub{ieo}"] = gather(dl)
+    d.call("Qtm_pm_psi", dl, dk); res["Qtm_pm"] = gather(dl)
+    sq = d.reduce("square_norm", dk)
+    it = d.call("cg_her", dx, dk, 2000, 1e-22, 1); res["cg_x"] = gather(dx)
+    dE, dO, dEn, dOn = d.field(k[slh]), d.field(p[slh]), d.field(), d.field()
+    it2 = d.call("invert_eo", dEn, dOn, dE, dO, 1e-22, 2000, 1)
+    res["inv_e"], res["inv_o"] = gather(dEn), gather(dOn)
+    ok = True
+    if rank == 0:
+        o = Oracle(T, LX, LY, LZ)
+        o.set_gauge(g); o.set_params(KAPPA, GMU, THETA)
+        e = o.spinor()
+        for ieo in (0, 1):
+            o.Hopping_Matrix(ieo, e, k); r1 = rel_l2(res[f"hop{ieo}"], e)
+            o.tm_sub_Hopping_Matrix(ieo, e, p, k, 1.0, 0.3); r2 = rel_l2(res[f"tm_sub{ieo}"], e)
+            print(f"hop{ieo} rel {r1:.2e}  tm_sub{ieo} rel {r2:.2e}"); ok &= r1 <= 1e-13 and r2 <= 1e-13
+        o.Qtm_pm_psi(e, k); r = rel_l2(res["Qtm_pm"], e); print(f"Qtm_pm rel {r:.2e}"); ok &= r <= 1e-13
+        r = abs(sq / o.square_norm(k, Vh) - 1); print(f"global square_norm rel {r:.2e}"); ok &= r < 1e-14
+        x = o.spinor(); itr = o.cg_her(x, k, 2000, 1e-22, 1); r = rel_l2(res["cg_x"], x)
+        print(f"cg_her iters {it} (oracle {itr}) x rel {r:.2e}"); ok &= abs(it - itr) <= 1 and r <= 1e-10
+        en, on = o.spinor(), o.spinor(); itr = o.invert_eo_cg(en, on, k, p, 1e-22, 2000, 1)
+        r1, r2 = rel_l2(res["inv_e"], en), rel_l2(res["inv_o"], on)
+        print(f"invert_eo iters {it2} (oracle {itr}) rel {r1:.2e} {r2:.2e}"); ok &= abs(it2 - itr) <= 1 and max(r1, r2) <= 1e-10
+        print("MGPU PARITY", "OK" if ok else "FAILED", f"world={world} global={T}x{LX}x{LY}x{LZ}")
+    d.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

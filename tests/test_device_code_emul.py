@@ -1,0 +1,114 @@
+"""CPU-only logic tests of the PRODUCT's device code: tmb_site.cuh / tmb_geom.h / the layout functors
+of tmb_kernels.cu are __host__ __device__ and are compiled here for the host (tests/emul/), then
+compared with the oracle.  Covers what cannot be checked on this GPU-less box otherwise: SoA layout
+conversion, closed-form neighbour arithmetic vs the reference's g_hi table, the spin projector
+tables and epilogues, the T-slab halo (loopback) path and the x-blocked traversal."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_gauge, random_spinor, rel_l2
+from emul_client import Emul
+
+KAPPA, GMU = 0.16, 0.0032
+
+
+def ka_of(kappa, theta, ext):
+    x = np.array(theta) * 3.14159265358979 / np.array(ext, dtype=float)
+    return np.stack([kappa * np.cos(x), kappa * np.sin(x)], axis=1).reshape(-1)
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (4, 6, 4, 8), (2, 2, 2, 2), (6, 2, 10, 4)])
+def test_closed_form_geometry_matches_reference_tables(oracle_lib, dims):
+    e = Emul(*dims)
+    o = oracle_lib.Oracle(*dims)
+    e2l = np.zeros(e.V, dtype=np.int32)
+    e.E.emul_eo2lexic(e2l, *dims)
+    assert np.array_equal(e2l, o.eo2lexic())
+    if dims == (4, 4, 4, 4):  # the reference's own g_hi table (golden fixture, geometry_eo.c:1470-1536)
+        hi = np.load(os.path.join(ROOT, "tests", "golden", "ref_4x4x4x4.npz"))["hi"]
+        for par in (0, 1):
+            nb = np.zeros(e.Vh * 8, dtype=np.int32)
+            e.E.emul_neighbours(nb, par, *dims)
+            assert np.array_equal(nb.reshape(e.Vh, 8), hi[par * e.Vh:(par + 1) * e.Vh, 1::2])
+
+
+@pytest.mark.parametrize("dims,theta", [((4, 4, 4, 4), (0., 0., 0., 0.)), ((4, 6, 4, 8), (1., 0.3, 0., 0.7)),
+                                        ((2, 4, 2, 6), (1., 0., 0., 0.)), ((6, 2, 10, 4), (0., 0.5, 0.5, 1.))])
+def test_hop_all_modes_and_halo_loopback(oracle_lib, dims, theta):
+    rng = np.random.default_rng(5)
+    e, o = Emul(*dims), oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, theta)
+    ka = ka_of(KAPPA, theta, dims)
+    U = e.pack_gauge(g)
+    k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+    sk, sp = e.pack(k), e.pack(p)
+    assert np.array_equal(e.unpack(sk), k)
+    up, dn = e.pack_halo(sk)
+    halo = (dn, up, e.pack_gauge_halo(U))  # loopback: halo_up <- own send_dn, halo_dn <- own send_up
+    for par in (0, 1):
+        exp = o.spinor()
+        for h in (None, halo):
+            o.Hopping_Matrix(par, exp, k)
+            assert rel_l2(e.unpack(e.hop(par, sk, U, ka, 0, halo=h)), exp) < 1e-14
+            o.tm_times_Hopping_Matrix(par, exp, k, 0.9, -0.2)
+            assert rel_l2(e.unpack(e.hop(par, sk, U, ka, 1, (0.9, -0.2), halo=h)), exp) < 1e-14
+            o.tm_sub_Hopping_Matrix(par, exp, p, k, 1.0, 0.3)
+            assert rel_l2(e.unpack(e.hop(par, sk, U, ka, 2, (1.0, 0.3), sp, halo=h)), exp) < 1e-14
+            hk = o.spinor(); o.Hopping_Matrix(par, hk, k)
+            zp = o.spinor(); o.assign_mul_one_pm_imu(zp, p, +1., o.Vh)  # (1 + i mu g5) p
+            got = e.unpack(e.hop(par, sk, U, ka, 3, (1.0, GMU), sp, halo=h))
+            assert rel_l2(got, zp - hk) < 1e-14  # MODE 3: the M_full / D_psi row
+
+
+def test_golden_hopping_through_device_code():
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_4x4x4x4.npz"))
+    dims = tuple(int(x) for x in gold["dims"])
+    e = Emul(*dims)
+    U, sk, sp = e.pack_gauge(gold["gauge"]), e.pack(gold["k"]), e.pack(gold["p"])
+    for par in (0, 1):
+        assert rel_l2(e.unpack(e.hop(par, sk, U, gold["ka"], 0)), gold[f"hop{par}"]) < 1e-14
+        assert rel_l2(e.unpack(e.hop(par, sk, U, gold["ka"], 1, (0.9, -0.2))), gold[f"tm_times{par}"]) < 1e-14
+        assert rel_l2(e.unpack(e.hop(par, sk, U, gold["ka"], 2, (1.0, 0.3), sp)), gold[f"tm_sub{par}"]) < 1e-14
+
+
+def test_lexic_permutation_and_elementwise_functors(oracle_lib):
+    dims = (4, 6, 4, 8)
+    rng = np.random.default_rng(8)
+    e, o = Emul(*dims), oracle_lib.Oracle(*dims)
+    o.set_params(KAPPA, 0.37)
+    lex = random_spinor(rng, o.V)
+    ev, od = np.zeros(24 * e.Vh), np.zeros(24 * e.Vh)
+    e.E.emul_pack_lexic(ev, od, lex.reshape(-1), *dims)
+    E_, O_ = o.spinor(), o.spinor()
+    o.convert_lexic_to_eo(E_, O_, lex)
+    assert np.array_equal(e.unpack(ev), E_) and np.array_equal(e.unpack(od), O_)
+    back = np.zeros(24 * e.V)
+    e.E.emul_unpack_lexic(back, ev, od, *dims)
+    assert np.array_equal(back.reshape(o.V, 24), lex)
+    a, b, c, f = (random_spinor(rng, o.Vh) for _ in range(4))
+    out, exp = np.zeros(24 * e.Vh), o.spinor()
+    e.E.emul_gamma5(out, e.pack(a), e.Vh); o.gamma5(exp, a, o.Vh); assert np.array_equal(e.unpack(out), exp)
+    nrm = 1. / (1. + 0.37 ** 2)
+    e.E.emul_diag(out, e.pack(a), nrm, -nrm * 0.37, e.Vh); o.assign_mul_one_pm_imu_inv(exp, a, +1., o.Vh)
+    assert rel_l2(e.unpack(out), exp) < 1e-15
+    e.E.emul_diag_sub(out, e.pack(a), e.pack(b), 1., -0.37, 1, e.Vh); o.mul_one_pm_imu_sub_mul_gamma5(exp, a, b, -1.)
+    assert rel_l2(e.unpack(out), exp) < 1e-15
+    e.E.emul_diag_sub(out, e.pack(a), e.pack(b), 1., 0.37, 0, e.Vh); o.mul_one_pm_imu_sub_mul(exp, a, b, +1., o.Vh)
+    assert rel_l2(e.unpack(out), exp) < 1e-15
+    o1, o2, e1, e2 = np.zeros(24 * e.Vh), np.zeros(24 * e.Vh), o.spinor(), o.spinor()
+    e.E.emul_nd_mee_inv(o1, o2, e.pack(a), e.pack(b), 0.139, 0.15, e.Vh); o.M_ee_inv_ndpsi(e1, e2, a, b, 0.139, 0.15)
+    assert rel_l2(e.unpack(o1), e1) < 1e-15 and rel_l2(e.unpack(o2), e2) < 1e-15
+    e.E.emul_nd_moo_sub_g5(o1, o2, e.pack(a), e.pack(b), e.pack(c), e.pack(f), -0.139, -0.15, e.Vh)
+    o.M_oo_sub_g5_ndpsi(e1, e2, a, b, c, f, -0.139, -0.15)
+    assert rel_l2(e.unpack(o1), e1) < 1e-15 and rel_l2(e.unpack(o2), e2) < 1e-15
+
+
+@pytest.mark.parametrize("dims,xb", [((4, 8, 4, 6), 2), ((4, 8, 4, 6), 4), ((6, 6, 2, 4), 3)])
+def test_xblock_traversal_is_a_permutation(dims, xb):
+    e = Emul(*dims)
+    perm = np.zeros(e.Vh, dtype=np.int32)
+    e.E.emul_xblock_perm(perm, *dims, xb)
+    assert np.array_equal(np.sort(perm), np.arange(e.Vh))

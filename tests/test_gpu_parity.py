@@ -32,7 +32,7 @@ def _setup(oracle_lib, dims, theta, seed=7):
     return rng, o, d, g
 
 
-CASES = [((4, 4, 4, 4), (0., 0., 0., 0.)), ((8, 4, 6, 8), (1., 0.3, 0., 0.7)), ((6, 10, 4, 6), (1., 0., 0., 0.)),
+CASES = [((4, 4, 4, 4), (0., 0., 0., 0.)), ((8, 4, 6, 8), (1., 0.3, 0., 0.7)), ((6, 10, 2, 6), (1., 0., 0., 0.)),
          ((8, 8, 8, 8), (0., 0., 0., 0.))]
 
 
@@ -347,3 +347,17 @@ def test_full_size_properties(oracle_lib):
         assert rel_l2(d.download(dl), exp2) <= TOL
     finally:
         d.close()
+
+
+def test_two_gpu_T_split_nccl():
+    """real NCCL halos: 2 ranks, global 16x8x8x8, vs the oracle on the global lattice (scripts/mgpu_parity.py)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (the gloo test in test_multirank_gloo.py covers the logic on CPU)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "mgpu_parity.py"),
+                        "8x8x8x8"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MGPU PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

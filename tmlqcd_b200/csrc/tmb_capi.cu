@@ -94,8 +94,10 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
     if (C.g.T == T && C.g.LX == LX && C.g.LY == LY && C.g.LZ == LZ) return 0;
     return fail(-2, "tmb_init: already initialised with %dx%dx%dx%d; call tmb_finalize first", C.g.T, C.g.LX, C.g.LY, C.g.LZ);
   }
-  if (T < 2 || LX < 1 || LY < 1 || LZ < 2 || (LZ & 1) || (T & 1))
-    return fail(-3, "tmb_init: need T >= 2 even and LZ >= 2 even (got T=%d LX=%d LY=%d LZ=%d)", T, LX, LY, LZ);
+  /* even/odd preconditioning on a periodic lattice needs every extent even (a wrap-around
+   * neighbour of an odd extent would have the SAME parity) */
+  if (T < 2 || LX < 2 || LY < 2 || LZ < 2 || ((T | LX | LY | LZ) & 1))
+    return fail(-3, "tmb_init: all local extents must be even and >= 2 (got T=%d LX=%d LY=%d LZ=%d)", T, LX, LY, LZ);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
