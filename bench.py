@@ -199,7 +199,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--loopback", action="store_true", help="1 GPU: run the T-split halo/boundary path against itself")
     ap.add_argument("--sweep", action="store_true", help="time every kernel variant (tuning aid, prints to stderr)")
+    ap.add_argument("--sweep-overlap", action="store_true", help="time PDL / L2-prefetch combinations (stderr)")
+    ap.add_argument("--overlap", type=int, default=0, help="tmb_set_overlap flags: 1 PDL, 2 L2 gauge prefetch")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--hints", type=int, default=None)
     ap.add_argument("--xblock", type=int, default=None)
@@ -244,6 +247,9 @@ def main():
     dev.set_params(KAPPA, GMU)
     if args.variant is not None or args.hints is not None or args.xblock is not None:
         dev.ck(lib.tmb_set_tuning(args.variant or 0, 1 if args.hints is None else args.hints, args.xblock or 0))
+    dev.ck(lib.tmb_set_overlap(args.overlap))
+    if args.loopback and world == 1:
+        dev.ck(lib.tmb_comm_loopback(1))
     dev.gauge_upload(g)
     rng = np.random.default_rng(99 + rank)
     src = rng.normal(scale=np.sqrt(0.5), size=(Vh, 24))
@@ -289,6 +295,17 @@ def main():
         log("best:", results[:5])
         dev.ck(lib.tmb_set_tuning(args.variant or 0, 1 if args.hints is None else args.hints, args.xblock or 0))
 
+    if args.sweep_overlap and rank == 0:
+        for flags in (0, 1, 2, 3):
+            for variant in (0, 2):
+                dev.ck(lib.tmb_set_tuning(variant, 1, 0)); dev.ck(lib.tmb_set_overlap(flags))
+                time_pairs(10)
+                ms, _ = time_pairs(200)
+                per = ms / 400.0
+                log(f"overlap flags={flags} (pdl={flags & 1} prefetch={flags >> 1}) variant={variant}: {per * 1e3:8.2f} us/hop "
+                    f"{Vh * BYTES_SITE / per / 1e6:8.1f} GB/s")
+        dev.ck(lib.tmb_set_tuning(args.variant or 0, 1 if args.hints is None else args.hints, args.xblock or 0))
+        dev.ck(lib.tmb_set_overlap(args.overlap))
     # ---- timed region: K pairs, device resident, inputs larger than L2 (gauge alone is 1152 B/site) ----
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -48,6 +48,7 @@ int tmb_set_mu(double g_mu);                                       /* g_mu = 2*k
 int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_operators_nd.c */
 /* kernel configuration knobs (profiling / tuning; defaults are the measured best) */
 int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
+int tmb_set_overlap(int flags); /* bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows */
 
 /* ---- memory ---- */
 void *tmb_field_alloc(void);         /* one eo spinor field, VOLUME/2 sites, device SoA layout */
@@ -74,6 +75,9 @@ int tmb_timer_stop(float *ms);
 /* ---- operators on device fields ---- */
 /* Hopping_Matrix(ieo,l,k): operator/Hopping_Matrix.c:131 */
 int tmb_Hopping_Matrix(int ieo, void *l, const void *k);
+/* the same on caller-owned HOST buffers (reference AoS layout), transfers pipelined with the kernel
+ * in chunks of time-slices; mode 0: Hopping_Matrix, mode 1: tm_times_Hopping_Matrix with cfactor */
+int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_host, int mode, double cf_re, double cf_im);
 /* tm_times_Hopping_Matrix(ieo,l,k,cfactor): operator/tm_times_Hopping_Matrix.c:119 */
 int tmb_tm_times_Hopping_Matrix(int ieo, void *l, const void *k, double cf_re, double cf_im);
 /* tm_sub_Hopping_Matrix(ieo,l,p,k,cfactor): operator/tm_sub_Hopping_Matrix.c:122 */

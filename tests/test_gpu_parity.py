@@ -78,6 +78,54 @@ def test_hopping_kernel_variants(oracle_lib, variant, hints, xblock):
         d.close()
 
 
+@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("loopback", [0, 1])
+def test_overlap_flags(oracle_lib, flags, loopback):
+    """programmatic dependent launch (bit 0) and L2 gauge prefetch (bit 1) change scheduling, not results"""
+    rng, o, d, g = _setup(oracle_lib, (8, 4, 6, 8), (1., 0.3, 0., 0.7))
+    try:
+        if loopback:
+            d.ck(d.lib.tmb_comm_loopback(1))
+            d.gauge_upload(g)
+        d.ck(d.lib.tmb_set_overlap(flags))
+        k = random_spinor(rng, o.Vh)
+        dk, dl, dx = d.field(k), d.field(), d.field()
+        exp = o.spinor()
+        for ieo in (0, 1):
+            o.Hopping_Matrix(ieo, exp, k); d.call("Hopping_Matrix", ieo, dl, dk)
+            assert rel_l2(d.download(dl), exp) <= TOL
+        # back-to-back dependent launches: each hop consumes the previous one's output
+        d.call("Hopping_Matrix", 0, dl, dk); d.call("Hopping_Matrix", 1, dx, dl); d.call("Hopping_Matrix", 0, dl, dx)
+        e1, e2 = o.spinor(), o.spinor()
+        o.Hopping_Matrix(0, e1, k); o.Hopping_Matrix(1, e2, e1); o.Hopping_Matrix(0, e1, e2)
+        assert rel_l2(d.download(dl), e1) <= TOL
+        o.Qtm_pm_psi(exp, k); d.call("Qtm_pm_psi", dl, dk)
+        assert rel_l2(d.download(dl), exp) <= TOL
+        xr = o.spinor(); itr = o.cg_her(xr, k, 2000, 1e-22, 1)
+        it = d.call("cg_her", dx, dk, 2000, 1e-22, 1)
+        assert abs(it - itr) <= 1 and rel_l2(d.download(dx), xr) <= 1e-10
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (16, 4, 4, 4), (34, 2, 4, 4), (6, 10, 2, 6)])
+def test_pipelined_host_hopping(oracle_lib, dims):
+    """tmb_Hopping_Matrix_host: chunked upload / compute / download gives the same field"""
+    rng, o, d, g = _setup(oracle_lib, dims, (1., 0., 0.5, 0.))
+    try:
+        k = random_spinor(rng, o.Vh)
+        out, exp = np.zeros_like(k), o.spinor()
+        for ieo in (0, 1):
+            d.call("Hopping_Matrix_host", ieo, out, k, 0, 1., 0.)
+            o.Hopping_Matrix(ieo, exp, k)
+            assert rel_l2(out, exp) <= TOL
+            d.call("Hopping_Matrix_host", ieo, out, k, 1, 0.9, -0.2)
+            o.tm_times_Hopping_Matrix(ieo, exp, k, 0.9, -0.2)
+            assert rel_l2(out, exp) <= TOL
+    finally:
+        d.close()
+
+
 @pytest.mark.parametrize("dims,theta", CASES[:3])
 def test_composite_operators(oracle_lib, dims, theta):
     rng, o, d, g = _setup(oracle_lib, dims, theta)

@@ -35,7 +35,8 @@ struct NcclApi {
   const char *(*GetErrorString)(int);
 };
 
-#define NSCRATCH 12
+#define NSCRATCH 14
+#define MAXCHUNK 64
 
 struct Ctx {
   bool init = false;
@@ -43,7 +44,8 @@ struct Ctx {
   tmb_geom g;
   int nranks = 1, rank = 0;
   bool dist = false, loopback = false;
-  cudaStream_t s_main = nullptr, s_comm = nullptr;
+  cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_up[MAXCHUNK] = {nullptr}, ev_done[MAXCHUNK] = {nullptr};
   cudaEvent_t ev_in = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
   double2 *U = nullptr, *Uhalo = nullptr;
   double2 *send_up = nullptr, *send_dn = nullptr, *halo_up = nullptr, *halo_dn = nullptr;
@@ -54,7 +56,7 @@ struct Ctx {
   double2 ka[4];
   double kappa = 0., mu = 0., mubar = 0., epsbar = 0., invmaxev = 1.;
   double2 *scratch[NSCRATCH] = {nullptr};
-  int hop_variant = 0, hints = 1, xblock = 0;
+  int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields;
@@ -105,8 +107,19 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   CU(cudaSetDevice(device));
   C.device = device;
   C.g = tmb_make_geom(T, LX, LY, LZ, 0);
-  CU(cudaStreamCreateWithFlags(&C.s_main, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&C.s_comm, cudaStreamNonBlocking));
+  /* the comm stream (halo pack + NCCL send/recv) gets the highest priority: its few CTAs must be
+   * scheduled ahead of the thousands of pending CTAs of the interior kernel, otherwise the exchange
+   * only starts when the interior kernel has drained and nothing overlaps */
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CU(cudaStreamCreateWithPriority(&C.s_main, cudaStreamNonBlocking, prio_lo));
+  CU(cudaStreamCreateWithPriority(&C.s_comm, cudaStreamNonBlocking, prio_hi));
+  CU(cudaStreamCreateWithFlags(&C.s_h2d, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&C.s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < MAXCHUNK; i++) {
+    CU(cudaEventCreateWithFlags(&C.ev_up[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&C.ev_done[i], cudaEventDisableTiming));
+  }
   CU(cudaEventCreateWithFlags(&C.ev_in, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_halo, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_chk[0], cudaEventDisableTiming));
@@ -127,7 +140,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0;
+  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0;
   C.init = true;
   return 0;
 }
@@ -144,7 +157,8 @@ extern "C" int tmb_finalize(void) {
   cudaFreeHost(C.st_host);
   cudaEventDestroy(C.ev_in); cudaEventDestroy(C.ev_halo); cudaEventDestroy(C.ev_t0); cudaEventDestroy(C.ev_t1);
   cudaEventDestroy(C.ev_chk[0]); cudaEventDestroy(C.ev_chk[1]);
-  cudaStreamDestroy(C.s_main); cudaStreamDestroy(C.s_comm);
+  for (int i = 0; i < MAXCHUNK; i++) { cudaEventDestroy(C.ev_up[i]); cudaEventDestroy(C.ev_done[i]); }
+  cudaStreamDestroy(C.s_main); cudaStreamDestroy(C.s_comm); cudaStreamDestroy(C.s_h2d); cudaStreamDestroy(C.s_d2h);
   C = Ctx();
   return 0;
 }
@@ -224,6 +238,8 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   C.hop_variant = hop_variant; C.hints = cache_hints ? 1 : 0; C.xblock = xblock;
   return 0;
 }
+/* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
+extern "C" int tmb_set_overlap(int flags) { NEED_INIT(); C.pdl = flags & 1; C.prefetch = (flags >> 1) & 1; return 0; }
 
 /* ------------------------------------------------------------------ memory */
 extern "C" void *tmb_field_alloc(void) {
@@ -350,6 +366,7 @@ struct HopOpt {
   int mode = 0; double2 cf = {1., 0.}; const double2 *p = nullptr;
   const double2 *dotw = nullptr; const tmb_cg_state *st = nullptr;
   int *npartial = nullptr;
+  int site0 = 0, nsites = -1; /* sub-range of output sites (single rank only); -1: all */
 };
 static int hop(int ieo, double2 *out, const double2 *in, const HopOpt &o) {
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
@@ -361,15 +378,17 @@ static int hop(int ieo, double2 *out, const double2 *in, const HopOpt &o) {
   a.partial = C.partial; a.st = o.st; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.dotw ? 1 : 0; a.hints = C.hints;
+  a.pdl = C.pdl; a.prefetch = C.prefetch;
   int np = 0;
   if (!C.dist) {
-    a.dist = 0; a.site0 = 0; a.nsites = C.g.Vh; a.split = C.g.Vh; a.gap = 0;
+    a.dist = 0; a.site0 = o.site0; a.nsites = o.nsites < 0 ? C.g.Vh : o.nsites; a.split = a.nsites; a.gap = 0;
     /* tuning variants exist for the plain Hopping_Matrix kernel only */
     a.variant = (o.mode == 0 && !a.dot) ? C.hop_variant : 0;
-    a.xblock = C.xblock;
+    a.xblock = o.nsites < 0 ? C.xblock : 0;
     KL(tmb_launch_hop(a, C.s_main));
     np = tmb_hop_grid(a);
   } else {
+    if (o.nsites >= 0) return fail(-12, "site sub-ranges are not supported with a distributed T direction");
     /* halo exchange on the comm stream, overlapped with the interior kernel:
      * replaces xchange_field(k, ieo) at operator/Hopping_Matrix.c:141-143 */
     const int S = C.g.S, Vh = C.g.Vh;
@@ -394,6 +413,66 @@ static int hop(int ieo, double2 *out, const double2 *in, const HopOpt &o) {
   }
   if (np > C.npartial) return fail(-10, "partial buffer too small");
   if (o.npartial) *o.npartial = np;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ host-pointer hopping, pipelined
+ * Hopping_Matrix(ieo, l, k) with caller-owned HOST buffers is PCIe-bound (192 B/site each way for
+ * 1536 B/site of HBM traffic).  Instead of upload -> kernel -> download, the field is cut into
+ * chunks of time-slices: chunk c is computed as soon as chunks c-1, c, c+1 have arrived, and its
+ * result goes back while later chunks are still coming in, so the H2D and D2H copy engines run
+ * concurrently (full duplex) and the kernel time disappears behind them. */
+extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_host, int mode, double cre, double cim) {
+  NEED_INIT();
+  if (mode != 0 && mode != 1) return fail(-13, "tmb_Hopping_Matrix_host: mode must be 0 or 1");
+  SCR(din, 12); SCR(dout, 13);
+  const int T = C.g.T, S = C.g.S, Vh = C.g.Vh;
+  if (C.dist) { /* distributed T: plain upload / compute / download */
+    TRY(tmb_field_upload(din, k_host));
+    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim);
+    TRY(hop(ieo, dout, din, o));
+    return tmb_field_download(l_host, dout);
+  }
+  int spc = (T + 15) / 16; if (spc < 1) spc = 1;
+  const int nchunk = (T + spc - 1) / spc;
+  if (nchunk > MAXCHUNK) return fail(-13, "too many chunks");
+  double2 *in_aos = C.stage, *out_aos = C.stage + (size_t)12 * Vh;
+  const double2 *hk = (const double2 *)k_host; double2 *hl = (double2 *)l_host;
+  CU(cudaStreamSynchronize(C.s_main));
+  auto first = [&](int c) { return c * spc * S; };
+  auto count = [&](int c) { int t1 = (c + 1) * spc; if (t1 > T) t1 = T; return (t1 - c * spc) * S; };
+  /* upload order: the three chunks the first output chunk needs, then the rest */
+  int order[MAXCHUNK], no = 0;
+  order[no++] = 0;
+  if (nchunk > 1) order[no++] = 1;
+  if (nchunk > 2) order[no++] = nchunk - 1;
+  for (int c = 2; c < nchunk - 1; c++) order[no++] = c;
+  for (int q = 0; q < no; q++) {
+    const int c = order[q];
+    CU(cudaMemcpyAsync(in_aos + (size_t)first(c) * 12, hk + (size_t)first(c) * 12, (size_t)count(c) * 192,
+                       cudaMemcpyHostToDevice, C.s_h2d));
+    CU(cudaEventRecord(C.ev_up[c], C.s_h2d));
+  }
+  bool packed[MAXCHUNK] = {false};
+  for (int c = 0; c < nchunk; c++) {
+    const int need[3] = {(c + nchunk - 1) % nchunk, c, (c + 1) % nchunk};
+    for (int q = 0; q < 3; q++) {
+      const int n = need[q];
+      if (packed[n]) continue;
+      CU(cudaStreamWaitEvent(C.s_main, C.ev_up[n], 0));
+      KL(tmb_launch_pack_eo_range(din, in_aos, Vh, first(n), count(n), C.s_main));
+      packed[n] = true;
+    }
+    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.site0 = first(c); o.nsites = count(c);
+    TRY(hop(ieo, dout, din, o));
+    KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, first(c), count(c), C.s_main));
+    CU(cudaEventRecord(C.ev_done[c], C.s_main));
+    CU(cudaStreamWaitEvent(C.s_d2h, C.ev_done[c], 0));
+    CU(cudaMemcpyAsync(hl + (size_t)first(c) * 12, out_aos + (size_t)first(c) * 12, (size_t)count(c) * 192,
+                       cudaMemcpyDeviceToHost, C.s_d2h));
+  }
+  CU(cudaStreamSynchronize(C.s_d2h));
+  CU(cudaStreamSynchronize(C.s_main));
   return 0;
 }
 

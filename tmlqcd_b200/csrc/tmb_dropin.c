@@ -96,18 +96,20 @@ static void down(spinor *h, int k) { CHK(tmb_field_download((double *)h, dev(k))
 
 /* ---------------- operators: one upload per input, one download per output ---------------- */
 void Hopping_Matrix(const int ieo, spinor *const l, spinor *const k) {
-  sync_globals(); up(0, k); CHK(tmb_Hopping_Matrix(ieo, dev(1), dev(0))); down(l, 1);
+  sync_globals(); CHK(tmb_Hopping_Matrix_host(ieo, (double *)l, (const double *)k, 0, 1., 0.));
 }
 void Hopping_Matrix_nocom(const int ieo, spinor *const l, spinor *const k) { Hopping_Matrix(ieo, l, k); }
 void tm_times_Hopping_Matrix(const int ieo, spinor *const l, spinor *const k, _Complex double const cf) {
-  sync_globals(); up(0, k); CHK(tmb_tm_times_Hopping_Matrix(ieo, dev(1), dev(0), creal(cf), cimag(cf))); down(l, 1);
+  sync_globals(); CHK(tmb_Hopping_Matrix_host(ieo, (double *)l, (const double *)k, 1, creal(cf), cimag(cf)));
 }
 void tm_sub_Hopping_Matrix(const int ieo, spinor *const l, spinor *const p, spinor *const k, _Complex double const cf) {
   sync_globals(); up(0, k); up(2, p);
   CHK(tmb_tm_sub_Hopping_Matrix(ieo, dev(1), dev(2), dev(0), creal(cf), cimag(cf))); down(l, 1);
 }
 void H_eo_tm_inv_psi(spinor *const l, spinor *const k, const int ieo, const double sign) {
-  sync_globals(); up(0, k); CHK(tmb_H_eo_tm_inv_psi(dev(1), dev(0), ieo, sign)); down(l, 1);
+  /* tm_operators.c:514-521: z = (1 -+ i mu)/(1+mu^2) */
+  const double nrm = 1. / (1. + g_mu * g_mu), sg = sign < 0. ? 1. : -1.;
+  sync_globals(); CHK(tmb_Hopping_Matrix_host(ieo, (double *)l, (const double *)k, 1, nrm, sg * nrm * g_mu));
 }
 void tm_sub_H_eo_gamma5(spinor *const l, spinor *const p, spinor *const k, const int ieo, const double sign) {
   sync_globals(); up(0, k); up(2, p); CHK(tmb_tm_sub_H_eo_gamma5(dev(1), dev(2), dev(0), ieo, sign)); down(l, 1);

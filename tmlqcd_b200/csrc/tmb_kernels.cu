@@ -36,6 +36,28 @@ __device__ __forceinline__ double block_sum(double v) {
 /* ------------------------------------------------------------------ K1: hopping */
 template <int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a) {
+  /* Programmatic dependent launch: let the next kernel of the stream start filling SMs while this
+   * grid drains, and do everything that does not depend on the previous kernel before the wait -
+   * here an L2 bulk prefetch of this CTA's gauge rows (75 % of its traffic, read-only for the
+   * whole solve).  Both instructions are no-ops when the launch carries no PDL attribute. */
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (a.prefetch && threadIdx.x < 72) {
+    const int first = blockIdx.x * BLOCK;
+    int n = a.nsites - first; n = n > BLOCK ? BLOCK : n;
+    if (n > 0) {
+      const int i0 = a.site0 + first + (first >= a.split ? a.gap : 0);
+      const int d = threadIdx.x / 9, e = threadIdx.x - 9 * d, mu = d >> 1, bwd = d & 1;
+      int j0 = i0;
+      if (bwd) {
+        const int shift = mu == 0 ? a.g.S : (mu == 1 ? a.g.LY * a.g.Lzh : (mu == 2 ? a.g.Lzh : 0));
+        j0 = i0 - shift; if (j0 < 0) j0 += a.g.Vh;
+      }
+      if (j0 > a.g.Vh - n) j0 = a.g.Vh - n;
+      const double2 *src = a.U + (size_t)(((bwd ? 1 - a.par : a.par) * 4 + mu) * 9 + e) * a.g.Vh + j0;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n * 16));
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (a.st != nullptr && a.st->converged) return; /* CG already stopped: uniform early exit */
   const int w = blockIdx.x * BLOCK + threadIdx.x;
   double dsum = 0.;
@@ -83,6 +105,15 @@ template <int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
 static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
   const int grid = tmb_hop_grid(a);
   if (grid <= 0) return cudaSuccess;
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, hop_kernel<MODE, DIST, DOT, HINTS, BLOCK, MINB>, a);
+  }
   hop_kernel<MODE, DIST, DOT, HINTS, BLOCK, MINB><<<grid, BLOCK, 0, s>>>(a);
   return cudaGetLastError();
 }
@@ -328,6 +359,11 @@ struct EwPackEo { double2 *soa; const double2 *aos; int Vh;
   __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / Vh), i = (int)(k - (size_t)c * Vh); soa[k] = aos[(size_t)i * 12 + c]; } };
 struct EwUnpackEo { double2 *aos; const double2 *soa; int Vh;
   __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / Vh), i = (int)(k - (size_t)c * Vh); aos[(size_t)i * 12 + c] = soa[k]; } };
+/* the same for a contiguous site range [i0, i0+n): used by the pipelined host-pointer operators */
+struct EwPackEoRange { double2 *soa; const double2 *aos; int Vh, i0, n;
+  __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / n), i = i0 + (int)(k - (size_t)c * n); soa[(size_t)c * Vh + i] = aos[(size_t)i * 12 + c]; } };
+struct EwUnpackEoRange { double2 *aos; const double2 *soa; int Vh, i0, n;
+  __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / n), i = i0 + (int)(k - (size_t)c * n); aos[(size_t)i * 12 + c] = soa[(size_t)c * Vh + i]; } };
 /* lexicographic host field of V sites <-> (even, odd) device fields (linalg/convert_eo_to_lexic.c:35-115) */
 struct EwPackLex { double2 *even, *odd; const double2 *lex; tmb_geom g;
   __host__ __device__ void operator()(size_t k) const {
@@ -369,6 +405,8 @@ struct EwPackGaugeHalo { double2 *out; const double2 *U; tmb_geom g;
 
 cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStream_t s) { EwPackEo f = {soa, aos, Vh}; EW_LAUNCH(f, (size_t)12 * Vh, nullptr, s); }
 cudaError_t tmb_launch_unpack_eo(double2 *aos, const double2 *soa, int Vh, cudaStream_t s) { EwUnpackEo f = {aos, soa, Vh}; EW_LAUNCH(f, (size_t)12 * Vh, nullptr, s); }
+cudaError_t tmb_launch_pack_eo_range(double2 *soa, const double2 *aos, int Vh, int i0, int n, cudaStream_t s) { EwPackEoRange f = {soa, aos, Vh, i0, n}; EW_LAUNCH(f, (size_t)12 * n, nullptr, s); }
+cudaError_t tmb_launch_unpack_eo_range(double2 *aos, const double2 *soa, int Vh, int i0, int n, cudaStream_t s) { EwUnpackEoRange f = {aos, soa, Vh, i0, n}; EW_LAUNCH(f, (size_t)12 * n, nullptr, s); }
 cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackLex f = {even, odd, lex, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
 cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s) { EwUnpackLex f = {lex, even, odd, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
 cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackGauge f = {U, lex, g}; EW_LAUNCH(f, (size_t)72 * g.Vh, nullptr, s); }

@@ -44,6 +44,8 @@ struct tmb_hop_launch {
   int site0, nsites;        /* contiguous work range ... */
   int split, gap;           /* ... with a hole: i = site0 + w + (w >= split ? gap : 0) */
   int xblock;               /* >0: traverse (t,x) planes x-blocked for L2 locality */
+  int pdl;                  /* launch with programmatic stream serialization (PDL) */
+  int prefetch;             /* bulk-prefetch the CTA's gauge rows into L2 before the dependency wait */
 };
 
 int tmb_hop_grid(const tmb_hop_launch &a);
@@ -80,6 +82,8 @@ cudaError_t tmb_launch_nd_moo_sub_g5(double2 *ls, double2 *lc, const double2 *ks
 /* layout conversion between the reference's host AoS layouts and the device SoA layout */
 cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStream_t s);
 cudaError_t tmb_launch_unpack_eo(double2 *aos, const double2 *soa, int Vh, cudaStream_t s);
+cudaError_t tmb_launch_pack_eo_range(double2 *soa, const double2 *aos, int Vh, int i0, int n, cudaStream_t s);
+cudaError_t tmb_launch_unpack_eo_range(double2 *aos, const double2 *soa, int Vh, int i0, int n, cudaStream_t s);
 cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s);
