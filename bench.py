@@ -388,6 +388,16 @@ def main():
         cg = {"iterations": it, "time_to_solution_s": t_dev, "cg_loop_s": t_cg, "final_rr": err, "eps_sq": CG_EPS_SQ,
               "rel_prec": 1, "gflops_cg_1608_convention": ((2 * (2 * 1608.0 + 24) + 24 + max(it, 0) * (2 * (2 * 1608.0 + 24) + 120))
                                                              * Vh * world / max(t_cg, 1e-9) / 1e9)}
+        # mixed-precision CG (float inner solve, double defect correction; solver/mixed_cg_her.c:65)
+        dev.call("field_zero", dOn)
+        dev.call("invert_eo_mixed", dEn, dOn, dE, dO, CG_EPS_SQ, CG_MAXITER, 1)
+        barrier()
+        t0 = time.perf_counter()
+        itm = dev.call("invert_eo_mixed", dEn, dOn, dE, dO, CG_EPS_SQ, CG_MAXITER, 1)
+        barrier()
+        cg["mixed_time_to_solution_s"] = time.perf_counter() - t0
+        cg["mixed_count"] = itm
+        cg["mixed_true_rr"] = dev.solver_stats()[1]
         if world == 1 and not args.skip_e2e:
             hE, _ = pinned(dev, (Vh, 24)); hO, _ = pinned(dev, (Vh, 24)); hEn, _ = pinned(dev, (Vh, 24)); hOn, _ = pinned(dev, (Vh, 24))
             hE[:] = E; hO[:] = O; hOn[:] = 0

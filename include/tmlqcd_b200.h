@@ -123,6 +123,22 @@ int tmb_invert_eo(void *even_new, void *odd_new, const void *even, const void *o
 /* last solve: iterations, final |r|^2 as seen by the CG, seconds spent in the CG loop */
 int tmb_solver_stats(int *iterations, double *final_err, double *seconds);
 
+/* ---- single precision operator + mixed-precision CG ----
+ * float fields hold VOLUME/2 spinor32 (su3.h:75-78) in the same SoA layout with float2 elements */
+void *tmb_field32_alloc(void);                                   /* free with tmb_field_free */
+int tmb_field32_upload(void *field32, const float *host_spinor32);
+int tmb_field32_download(float *host_spinor32, const void *field32);
+int tmb_assign_to_32(void *field32, const void *field64);        /* linalg/assign_to_32.c */
+int tmb_assign_to_64(void *field64, const void *field32);
+int tmb_Hopping_Matrix_32(int ieo, void *l32, const void *k32);  /* operator/Hopping_Matrix_32.c:119 */
+int tmb_Qtm_pm_psi_32(void *l32, const void *k32);               /* operator/tm_operators_32.c:94 */
+int tmb_set_mixcg(double innereps, int maxinnersolverit);        /* mixcg_innereps / mixcg_maxinnersolverit, default_input_values.h:193 */
+/* mixed_cg_her(P,Q,params,max_iter,eps_sq,rel_prec,VOLUME/2,&Qtm_pm_psi,&Qtm_pm_psi_32): solver/mixed_cg_her.c:65 */
+int tmb_mixed_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec);
+/* invert_eo with solver_flag == MIXEDCG: invert_eo.c:225-232 */
+int tmb_invert_eo_mixed(void *even_new, void *odd_new, const void *even, const void *odd, double precision,
+                        int max_iter, int rel_prec);
+
 /* ---- non-degenerate doublet: operator/tm_operators_nd.c:68,:130,:195,:639; cg_her_nd.c:57;
  *      invert_doublet_eo.c:68 ---- */
 int tmb_M_ee_inv_ndpsi(void *ls, void *lc, const void *ks, const void *kc, double mu, double eps);

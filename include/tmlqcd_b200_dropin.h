@@ -25,6 +25,8 @@
 typedef struct { _Complex double c00, c01, c02, c10, c11, c12, c20, c21, c22; } su3;
 typedef struct { _Complex double c0, c1, c2; } su3_vector;
 typedef struct { su3_vector s0, s1, s2, s3; } spinor;
+typedef struct { _Complex float c0, c1, c2; } su3_vector32;
+typedef struct { su3_vector32 s0, s1, s2, s3; } spinor32; /* su3.h:55-78 */
 /* solver/matrix_mult_typedef.h:30, matrix_mult_typedef_nd.h */
 typedef void (*matrix_mult)(spinor *const, spinor *const);
 typedef void (*matrix_mult_nd)(spinor *const, spinor *const, spinor *const, spinor *const);
@@ -55,6 +57,7 @@ typedef struct {
 } solver_params_t;
 /* solver/solver_types.h:23-49 (only CG is on the scoped path) */
 #define TMB_SOLVER_CG 1
+#define TMB_SOLVER_MIXEDCG 13
 #define EO 0 /* global.h / operator headers: ieo = 0 -> output on even sites */
 #define OE 1
 
@@ -65,6 +68,8 @@ extern double g_kappa, g_mu, g_mubar, g_epsbar, phmc_invmaxev;
 extern double X0, X1, X2, X3;
 extern _Complex double ka0, ka1, ka2, ka3, phase_0, phase_1, phase_2, phase_3;
 extern su3 **g_gauge_field;
+extern double mixcg_innereps;      /* read_input.h: MixCGInnerEps */
+extern int mixcg_maxinnersolverit; /* read_input.h: MixCGMaxIter */
 
 /* ---- lifecycle added by the drop-in (the reference allocates in its mains) ----
  * sets T,L,LX,LY,LZ,VOLUME,..., allocates g_gauge_field (init/init_gauge_field.c:41) and
@@ -124,6 +129,11 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
               double *const extra_masses, solver_params_t solver_params, const int id,
               const ExternalInverter external_inverter, const SloppyPrecision sloppy,
               const CompressionType compression);
+/* operator/Hopping_Matrix_32.c:119; operator/tm_operators_32.c:94; solver/mixed_cg_her.c:65 */
+void Hopping_Matrix_32(const int ieo, spinor32 *const l, spinor32 *const k);
+void Qtm_pm_psi_32(spinor32 *const l, spinor32 *const k);
+int mixed_cg_her(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
+                 const int rel_prec, const int N, matrix_mult f, matrix_mult32 f32);
 /* operator/tm_operators_nd.c:68,:130,:195,:639; solver/cg_her_nd.c:57; invert_doublet_eo.c:68 */
 void M_ee_inv_ndpsi(spinor *const l_s, spinor *const l_c, spinor *const k_s, spinor *const k_c, const double mu, const double eps);
 void Qtm_ndpsi(spinor *const l_strange, spinor *const l_charm, spinor *const k_strange, spinor *const k_charm);

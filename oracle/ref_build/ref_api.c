@@ -48,6 +48,10 @@ extern double X0, X1, X2, X3; /* read_input.h:65, defined in boundary.c:37 */
 #include "solver/matrix_mult_typedef_nd.h"
 #include "solver/cg_her.h"
 #include "solver/cg_her_nd.h"
+#include "solver/solver_params.h"
+#include "solver/mixed_cg_her.h"
+#include "operator/Hopping_Matrix_32.h"
+#include "operator/tm_operators_32.h"
 
 /* phmc.c is not compiled (drags in the whole PHMC); tm_operators_nd.c only needs these
  * scalars from it (phmc.h). */
@@ -297,3 +301,35 @@ double ref_bench_Qtm_pm(int nreps) {
   return t2 - t1;
 }
 double ref_gettime(void) { return gettime(); }
+
+/* ---- single precision operator + mixed CG; half-spinor build only:
+ *      Hopping_Matrix_32 exits with "only implemented with HALFSPINOR" otherwise
+ *      (operator/Hopping_Matrix_32.c:112-114) ---- */
+double mixcg_innereps = 5.0e-5;      /* default_input_values.h:193, normally set by read_input.l:2912 */
+int mixcg_maxinnersolverit = 5000;   /* default_input_values.h:194 */
+static int ref32_up = 0;
+int ref_init32(void) {
+#ifdef _USE_HALFSPINOR
+  if (ref32_up) return 0;
+  if (init_gauge_field_32(VOLUMEPLUSRAND, 1) != 0) return -1;
+  if (init_spinor_field_32(VOLUMEPLUSRAND / 2, 6) != 0) return -2;
+  if (init_dirac_halfspinor32() != 0) return -3;
+  ref32_up = 1;
+  return 0;
+#else
+  return -9;
+#endif
+}
+/* lib_wrapper.c:232: convert_32_gauge_field after every gauge change */
+void ref_update_gauge32(void) {
+  convert_32_gauge_field(g_gauge_field_32, g_gauge_field, VOLUMEPLUSRAND);
+  g_update_gauge_copy_32 = 1;
+}
+void ref_set_mixcg(double innereps, int maxinner) { mixcg_innereps = innereps; mixcg_maxinnersolverit = maxinner; }
+void ref_Hopping_Matrix_32(int ieo, float *l, float *k) { Hopping_Matrix_32(ieo, (spinor32 *)l, (spinor32 *)k); }
+void ref_Qtm_pm_psi_32(float *l, float *k) { Qtm_pm_psi_32((spinor32 *)l, (spinor32 *)k); }
+int ref_mixed_cg_her(double *p, double *q, int max_iter, double eps_sq, int rel_prec) {
+  solver_params_t sp;
+  memset(&sp, 0, sizeof(sp));
+  return mixed_cg_her((spinor *)p, (spinor *)q, sp, max_iter, eps_sq, rel_prec, VOLUME / 2, &Qtm_pm_psi, &Qtm_pm_psi_32);
+}

@@ -14,6 +14,7 @@ _REFDIR = os.path.join(_HERE, "_ref")
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
 
 def lib_path(halfspinor=False):
@@ -91,6 +92,9 @@ class Reference:
             "ref_M_ee_inv_ndpsi": (None, [_dp] * 4 + [d, d]),
             "ref_cg_her_nd": (i, [_dp] * 4 + [i, d, i]),
             "ref_invert_doublet_eo_cg": (i, [_dp] * 8 + [d, i, i]),
+            "ref_init32": (i, []), "ref_update_gauge32": (None, []), "ref_set_mixcg": (None, [d, i]),
+            "ref_Hopping_Matrix_32": (None, [i, _fp, _fp]), "ref_Qtm_pm_psi_32": (None, [_fp, _fp]),
+            "ref_mixed_cg_her": (i, [_dp, _dp, i, d, i]),
             "ref_bench_hopping": (d, [i]),
             "ref_bench_D_psi": (d, [i]),
             "ref_bench_Qtm_pm": (d, [i]),

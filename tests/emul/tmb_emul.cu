@@ -10,7 +10,7 @@
 #include "../../tmlqcd_b200/csrc/tmb_kernels.cu"
 
 template <int MODE, int DIST>
-static void hop_host(double2 *out, const tmb_hop_fields &f, const double2 *p, const tmb_geom &g, int par,
+static void hop_host(double2 *out, const tmb_hop_fields<double2> &f, const double2 *p, const tmb_geom &g, int par,
                      const double2 ka[4], double2 cf, int site0, int nsites, int split, int gap) {
   tmb_policies pol = {0, 0};
   for (int w = 0; w < nsites; w++) {
@@ -52,7 +52,7 @@ void emul_pack_gauge(double *U, const double *lex, int T, int LX, int LY, int LZ
 }
 void emul_pack_halo(double *up, double *dn, const double *in, int T, int LX, int LY, int LZ) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 1);
-  EwPackHalo f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g};
+  EwPackHalo<double2> f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g};
   for (size_t k = 0; k < (size_t)6 * g.S; k++) f(k);
 }
 void emul_pack_gauge_halo(double *out, const double *U, int T, int LX, int LY, int LZ) {
@@ -77,7 +77,7 @@ int emul_hop(int par, double *out, const double *in, const double *p, const doub
              const double *halo_dn, const double *Uhalo, int T, int LX, int LY, int LZ, const double *ka8,
              double cre, double cim, int mode, int dist) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, dist);
-  tmb_hop_fields f;
+  tmb_hop_fields<double2> f;
   f.in = (const double2 *)in; f.U = (const double2 *)U;
   f.halo_up = (const double2 *)halo_up; f.halo_dn = (const double2 *)halo_dn; f.Uhalo = (const double2 *)Uhalo;
   double2 ka[4];

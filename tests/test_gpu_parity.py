@@ -409,3 +409,66 @@ def test_two_gpu_T_split_nccl():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "mgpu_parity.py"),
                         "8x8x8x8"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MGPU PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_single_precision_operator_and_mixed_cg(oracle_lib):
+    """row a31: Hopping_Matrix_32 / Qtm_pm_psi_32 (<= 1e-5 of the double operator, north_star) and
+    mixed_cg_her (float inner CG, double defect correction) reaching the double residual"""
+    import tmlqcd_b200 as tm
+    for dims, theta, loopback in (((8, 4, 6, 8), (1., 0.3, 0., 0.7), 0), ((8, 8, 8, 8), (1., 0., 0., 0.), 1)):
+        rng, o, d, g = _setup(oracle_lib, dims, theta)
+        try:
+            if loopback:
+                d.ck(d.lib.tmb_comm_loopback(1))
+                d.gauge_upload(g)
+            k = random_spinor(rng, o.Vh)
+            k32 = k.astype(np.float32)
+            dk32, dl32 = d.field32(k32), d.field32()
+            exp = o.spinor()
+            for ieo in (0, 1):
+                o.Hopping_Matrix(ieo, exp, k); d.call("Hopping_Matrix_32", ieo, dl32, dk32)
+                assert rel_l2(d.download32(dl32).astype(np.float64), exp) <= 1e-5
+            o.Qtm_pm_psi(exp, k); d.call("Qtm_pm_psi_32", dl32, dk32)
+            assert rel_l2(d.download32(dl32).astype(np.float64), exp) <= 1e-5
+            # precision conversion round trip
+            dk, dt = d.field(k), d.field()
+            d.call("assign_to_32", dl32, dk); d.call("assign_to_64", dt, dl32)
+            assert rel_l2(d.download(dt), k32.astype(np.float64)) == 0.0
+            # mixed CG vs the double CG of the oracle
+            xr = o.spinor(); itr = o.cg_her(xr, k, 2000, 1e-22, 1)
+            dx = d.field()
+            it = d.call("mixed_cg_her", dx, dk, 2000, 1e-22, 1)
+            x = d.download(dx)
+            assert it > 0 and it <= 1.3 * itr + 10, (it, itr)
+            assert rel_l2(x, xr) <= 1e-9
+            r = o.spinor(); o.Qtm_pm_psi(r, x)
+            assert np.linalg.norm(r - k) ** 2 <= 1e-22 * np.linalg.norm(k) ** 2 * 1.01
+            # invert_eo with solver_flag == MIXEDCG through the reference-named symbol
+            E, O = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+            enr, onr = o.spinor(), o.spinor(); o.invert_eo_cg(enr, onr, E, O, 1e-22, 2000, 1)
+            dE, dO, dEn, dOn = d.field(E), d.field(O), d.field(), d.field()
+            it = d.call("invert_eo_mixed", dEn, dOn, dE, dO, 1e-22, 2000, 1)
+            assert it > 0 and rel_l2(d.download(dEn), enr) <= 1e-9 and rel_l2(d.download(dOn), onr) <= 1e-9
+        finally:
+            d.close()
+    # reference-named symbols with host buffers
+    D = tm.DropIn(8, 4, 4, 4)
+    try:
+        rng = np.random.default_rng(21)
+        o = oracle_lib.Oracle(8, 4, 4, 4)
+        g = random_gauge(rng, o.V)
+        o.set_gauge(g); o.set_params(KAPPA, GMU, (1., 0., 0., 0.))
+        D.set_params(KAPPA, GMU, (1., 0., 0., 0.)); D.set_gauge(g)
+        k = random_spinor(rng, o.Vh); k32 = k.astype(np.float32); l32 = np.zeros_like(k32); exp = o.spinor()
+        D.Hopping_Matrix_32(1, l32, k32); o.Hopping_Matrix(1, exp, k); assert rel_l2(l32.astype(np.float64), exp) <= 1e-5
+        D.Qtm_pm_psi_32(l32, k32); o.Qtm_pm_psi(exp, k); assert rel_l2(l32.astype(np.float64), exp) <= 1e-5
+        x, xr = D.spinor(), o.spinor()
+        itr = o.cg_her(xr, k, 2000, 1e-22, 1)
+        it = D.mixed_cg_her(x, k, tm.capi.SolverParams(), 2000, 1e-22, 1, o.Vh, D.fptr("Qtm_pm_psi"), D.fptr("Qtm_pm_psi_32"))
+        assert it > 0 and rel_l2(x, xr) <= 1e-9
+        en, on, enr, onr = D.spinor(), D.spinor(), o.spinor(), o.spinor()
+        o.invert_eo_cg(enr, onr, k, xr, 1e-22, 2000, 1)
+        it = D.invert_eo(en, on, k, xr, 1e-22, 2000, 13, 1, 0, 1, 0, None, tm.capi.SolverParams(), 0, 0, 0, 18)  # MIXEDCG
+        assert it > 0 and rel_l2(en, enr) <= 1e-9 and rel_l2(on, onr) <= 1e-9
+    finally:
+        D.close()

@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "lib", "libtmlqcd_b200.so")
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _vp, _d, _i = C.c_void_p, C.c_double, C.c_int
 
 
@@ -64,6 +65,11 @@ DEVICE_API = {
     "tmb_M_ee_inv_ndpsi": (_i, [_vp] * 4 + [_d, _d]), "tmb_Qtm_ndpsi": (_i, [_vp] * 4),
     "tmb_Qtm_dagger_ndpsi": (_i, [_vp] * 4), "tmb_Qtm_pm_ndpsi": (_i, [_vp] * 4),
     "tmb_cg_her_nd": (_i, [_vp] * 4 + [_i, _d, _i]), "tmb_invert_doublet_eo": (_i, [_vp] * 8 + [_d, _i, _i]),
+    "tmb_field32_alloc": (_vp, []), "tmb_field32_upload": (_i, [_vp, _vp]), "tmb_field32_download": (_i, [_vp, _vp]),
+    "tmb_assign_to_32": (_i, [_vp, _vp]), "tmb_assign_to_64": (_i, [_vp, _vp]),
+    "tmb_Hopping_Matrix_32": (_i, [_i, _vp, _vp]), "tmb_Qtm_pm_psi_32": (_i, [_vp, _vp]),
+    "tmb_set_mixcg": (_i, [_d, _i]), "tmb_mixed_cg_her": (_i, [_vp, _vp, _i, _d, _i]),
+    "tmb_invert_eo_mixed": (_i, [_vp] * 4 + [_d, _i, _i]),
     "tmb_launch_count": (C.c_longlong, []),
 }
 
@@ -105,6 +111,8 @@ DROPIN_API = {
     "convert_eo_to_lexic": (None, [_sp, _sp, _sp]), "convert_lexic_to_eo": (None, [_sp, _sp, _sp]),
     "cg_her": (_i, [_sp, _sp, _i, _d, _i, _i, _vp]),
     "invert_eo": (_i, [_sp] * 4 + [_d, _i, _i, _i, _i, _i, _i, _vp, SolverParams, _i, _i, _i, _i]),
+    "Hopping_Matrix_32": (None, [_i, _fp, _fp]), "Qtm_pm_psi_32": (None, [_fp, _fp]),
+    "mixed_cg_her": (_i, [_sp, _sp, SolverParams, _i, _d, _i, _i, _vp, _vp]),
     "M_ee_inv_ndpsi": (None, [_sp] * 4 + [_d, _d]), "Qtm_ndpsi": (None, [_sp] * 4),
     "Qtm_dagger_ndpsi": (None, [_sp] * 4), "Qtm_pm_ndpsi": (None, [_sp] * 4),
     "cg_her_nd": (_i, [_sp] * 4 + [_i, _d, _i, _i, _vp]),
@@ -119,9 +127,9 @@ DROPIN_API = {
 DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND", "g_update_gauge_copy", "g_proc_id",
                   "g_debug_level", "g_nproc", "g_nproc_t", "g_kappa", "g_mu", "g_mubar", "g_epsbar", "phmc_invmaxev",
                   "X0", "X1", "X2", "X3", "ka0", "ka1", "ka2", "ka3", "phase_0", "phase_1", "phase_2", "phase_3",
-                  "g_gauge_field"]
+                  "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit"]
 
-_SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo"}
+_SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed"}
 _lib = None
 
 
@@ -150,7 +158,7 @@ class TmbError(RuntimeError):
 def _addr(a):
     """device pointer (int) or host numpy array -> void*"""
     if isinstance(a, np.ndarray):
-        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        assert a.dtype in (np.float64, np.float32) and a.flags["C_CONTIGUOUS"]
         return a.ctypes.data_as(_vp)
     return _vp(a)
 
@@ -203,6 +211,21 @@ class Device:
     def download(self, field):
         out = np.zeros((self.Vh, 24), dtype=np.float64)
         self.ck(self.lib.tmb_field_download(out.ctypes.data_as(_vp), field))
+        return out
+
+    def field32(self, host=None):
+        p = self.lib.tmb_field32_alloc()
+        if not p:
+            raise TmbError(self.lib.tmb_last_error().decode())
+        if host is not None:
+            host = np.ascontiguousarray(host, dtype=np.float32)
+            assert host.size == self.Vh * 24
+            self.ck(self.lib.tmb_field32_upload(p, host.ctypes.data_as(_vp)))
+        return p
+
+    def download32(self, field):
+        out = np.zeros((self.Vh, 24), dtype=np.float32)
+        self.ck(self.lib.tmb_field32_download(out.ctypes.data_as(_vp), field))
         return out
 
     def upload_lexic(self, even, odd, host):

@@ -56,6 +56,9 @@ struct Ctx {
   double2 ka[4];
   double kappa = 0., mu = 0., mubar = 0., epsbar = 0., invmaxev = 1.;
   double2 *scratch[NSCRATCH] = {nullptr};
+  float2 *scratch32[NSCRATCH] = {nullptr};
+  float2 *U32 = nullptr, *Uhalo32 = nullptr; bool gauge32_valid = false;
+  double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
   int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
@@ -152,6 +155,8 @@ extern "C" int tmb_finalize(void) {
   for (void *p : C.fields) cudaFree(p);
   C.fields.clear();
   for (int i = 0; i < NSCRATCH; i++) { if (C.scratch[i]) cudaFree(C.scratch[i]); C.scratch[i] = nullptr; }
+  for (int i = 0; i < NSCRATCH; i++) { if (C.scratch32[i]) cudaFree(C.scratch32[i]); C.scratch32[i] = nullptr; }
+  if (C.U32) cudaFree(C.U32); if (C.Uhalo32) cudaFree(C.Uhalo32);
   cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
@@ -305,8 +310,7 @@ extern "C" int tmb_field_download_lexic(double *host, const void *even, const vo
 }
 
 /* exchange of the two T-face buffers: send_up -> rank+1's halo_dn, send_dn -> rank-1's halo_up */
-static int exchange_faces(const double2 *sup, const double2 *sdn, double2 *hup, double2 *hdn, size_t count2, cudaStream_t s) {
-  const size_t bytes = count2 * sizeof(double2);
+static int exchange_faces(const void *sup, const void *sdn, void *hup, void *hdn, size_t bytes, cudaStream_t s) {
   if (C.nranks == 1) { /* loopback: this rank is its own neighbour in T */
     CU(cudaMemcpyAsync(hdn, sup, bytes, cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(hup, sdn, bytes, cudaMemcpyDeviceToDevice, s));
@@ -314,10 +318,10 @@ static int exchange_faces(const double2 *sup, const double2 *sdn, double2 *hup, 
   }
   const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
   NC(C.nccl.GroupStart());
-  NC(C.nccl.Send(sup, 2 * count2, NCCL_FLOAT64, up, C.comm, s));
-  NC(C.nccl.Recv(hdn, 2 * count2, NCCL_FLOAT64, dn, C.comm, s));
-  NC(C.nccl.Send(sdn, 2 * count2, NCCL_FLOAT64, dn, C.comm, s));
-  NC(C.nccl.Recv(hup, 2 * count2, NCCL_FLOAT64, up, C.comm, s));
+  NC(C.nccl.Send(sup, bytes, NCCL_UINT8, up, C.comm, s));
+  NC(C.nccl.Recv(hdn, bytes, NCCL_UINT8, dn, C.comm, s));
+  NC(C.nccl.Send(sdn, bytes, NCCL_UINT8, dn, C.comm, s));
+  NC(C.nccl.Recv(hup, bytes, NCCL_UINT8, up, C.comm, s));
   NC(C.nccl.GroupEnd());
   return 0;
 }
@@ -349,6 +353,7 @@ extern "C" int tmb_gauge_upload(const double *host_gauge) {
     CU(cudaFree(tmp));
   }
   C.gauge_loaded = true;
+  C.gauge32_valid = false;
   return 0;
 }
 
@@ -363,18 +368,22 @@ static double2 *scratch(int k) {
 
 /* ------------------------------------------------------------------ the hopping term */
 struct HopOpt {
-  int mode = 0; double2 cf = {1., 0.}; const double2 *p = nullptr;
-  const double2 *dotw = nullptr; const tmb_cg_state *st = nullptr;
+  int mode = 0; double2 cf = {1., 0.}; const void *p = nullptr;
+  const void *dotw = nullptr; const tmb_cg_state *st = nullptr;
   int *npartial = nullptr;
   int site0 = 0, nsites = -1; /* sub-range of output sites (single rank only); -1: all */
+  int prec = 0;               /* 0: double fields, 1: float fields + float gauge copy */
 };
-static int hop(int ieo, double2 *out, const double2 *in, const HopOpt &o) {
+static int ensure_gauge32();
+static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
   if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
   tmb_hop_launch a;
   memset(&a, 0, sizeof(a));
-  a.in = in; a.out = out; a.p = o.p; a.dotw = o.dotw; a.U = C.U;
-  a.halo_up = C.halo_up; a.halo_dn = C.halo_dn; a.Uhalo = C.Uhalo;
+  if (o.prec) TRY(ensure_gauge32());
+  a.prec = o.prec;
+  a.in = in; a.out = out; a.p = o.p; a.dotw = o.dotw; a.U = o.prec ? (const void *)C.U32 : (const void *)C.U;
+  a.halo_up = C.halo_up; a.halo_dn = C.halo_dn; a.Uhalo = o.prec ? (const void *)C.Uhalo32 : (const void *)C.Uhalo;
   a.partial = C.partial; a.st = o.st; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.dotw ? 1 : 0; a.hints = C.hints;
@@ -394,21 +403,25 @@ static int hop(int ieo, double2 *out, const double2 *in, const HopOpt &o) {
     const int S = C.g.S, Vh = C.g.Vh;
     CU(cudaEventRecord(C.ev_in, C.s_main));
     CU(cudaStreamWaitEvent(C.s_comm, C.ev_in, 0));
-    KL(tmb_launch_pack_halo(C.send_up, C.send_dn, in, C.g, C.s_comm));
-    TRY(exchange_faces(C.send_up, C.send_dn, C.halo_up, C.halo_dn, (size_t)6 * S, C.s_comm));
-    CU(cudaEventRecord(C.ev_halo, C.s_comm));
-    int nb_int = 0;
+    KL(tmb_launch_pack_halo(o.prec, C.send_up, C.send_dn, in, C.g, C.s_comm));
+    TRY(exchange_faces(C.send_up, C.send_dn, C.halo_up, C.halo_dn, (size_t)6 * S * (o.prec ? sizeof(float2) : sizeof(double2)), C.s_comm));
     a.variant = 0; a.xblock = 0;
+    /* the interior grid size fixes where the boundary launch puts its fused-dot partials */
+    int nb_int = 0;
+    tmb_hop_launch ai = a;
     if (Vh > 2 * S) { /* interior time-slices t in [1, T-2]: no halo data needed */
-      a.dist = 0; a.site0 = S; a.nsites = Vh - 2 * S; a.split = a.nsites; a.gap = 0;
-      KL(tmb_launch_hop(a, C.s_main));
-      nb_int = tmb_hop_grid(a);
+      ai.dist = 0; ai.site0 = S; ai.nsites = Vh - 2 * S; ai.split = ai.nsites; ai.gap = 0;
+      nb_int = tmb_hop_grid(ai);
     }
-    CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
-    /* boundary slices t = 0 and t = T-1 */
+    /* boundary slices t = 0 and t = T-1: launched on the HIGH-PRIORITY comm stream right behind the
+     * exchange, so their CTAs interleave with the interior kernel's instead of forming a second,
+     * poorly filled launch after it (outputs are disjoint sites) */
     a.dist = 1; a.site0 = 0; a.nsites = 2 * S; a.split = S; a.gap = Vh - 2 * S;
     a.partial = C.partial + nb_int;
-    KL(tmb_launch_hop(a, C.s_main));
+    KL(tmb_launch_hop(a, C.s_comm));
+    CU(cudaEventRecord(C.ev_halo, C.s_comm));
+    if (nb_int > 0) KL(tmb_launch_hop(ai, C.s_main));
+    CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
     np = nb_int + tmb_hop_grid(a);
   }
   if (np > C.npartial) return fail(-10, "partial buffer too small");
@@ -576,10 +589,10 @@ static int finish_reduction(int npart, double *result) {
   return 0;
 }
 extern "C" int tmb_square_norm(const void *p, double *result) {
-  NEED_INIT(); KL(tmb_launch_norm2(F(p), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
+  NEED_INIT(); KL(tmb_launch_norm2(0, F(p), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
 }
 extern "C" int tmb_scalar_prod_r(const void *s, const void *r, double *result) {
-  NEED_INIT(); KL(tmb_launch_dot(F(s), F(r), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
+  NEED_INIT(); KL(tmb_launch_dot(0, F(s), F(r), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
 }
 extern "C" int tmb_assign_mul_add_r_and_square(void *r, double c, const void *s, double *result) {
   NEED_INIT(); KL(tmb_launch_xpay_norm(F(r), c, F(s), N2(), C.partial, C.s_main)); return finish_reduction(tmb_red_grid(N2()), result);
@@ -631,7 +644,7 @@ extern "C" int tmb_cg_her(void *P, const void *Q, int max_iter, double eps_sq, i
   TRY(qtm_pm(ap, x, nullptr, nullptr, nullptr));
   KL(tmb_launch_lincomb(r, 1., q, -1., ap, n2, C.s_main));
   CU(cudaMemcpyAsync(p, r, FIELD_BYTES(), cudaMemcpyDeviceToDevice, C.s_main));
-  KL(tmb_launch_norm2(r, n2, C.partial, C.s_main));
+  KL(tmb_launch_norm2(0, r, n2, C.partial, C.s_main));
   TRY(reduce_to(tmb_red_grid(n2), 0, TMB_FIN_CG_INIT));
 
   int enq = 0, chunk = 0, done = 0;
@@ -642,9 +655,9 @@ extern "C" int tmb_cg_her(void *P, const void *Q, int max_iter, double eps_sq, i
       int np = 0;
       TRY(qtm_pm(ap, p, p, C.st, &np));                                     /* cg_her.c:92 + :93 fused */
       TRY(reduce_to(np, 1, TMB_FIN_CG_PRO));                                /* alpha = normsq/pro */
-      KL(tmb_launch_cg_update_xr(x, r, p, ap, n2, C.st, C.partial, C.s_main)); /* cg_her.c:95-101 */
+      KL(tmb_launch_cg_update_xr(0, x, r, p, ap, n2, C.st, C.partial, C.s_main)); /* cg_her.c:95-101 */
       TRY(reduce_to(tmb_red_grid(n2), 2, TMB_FIN_CG_ERR));                  /* stop test, beta */
-      KL(tmb_launch_cg_update_p(p, r, n2, C.st, C.s_main));                 /* cg_her.c:122 */
+      KL(tmb_launch_cg_update_p(0, p, r, n2, C.st, C.s_main));                 /* cg_her.c:122 */
     }
     enq += todo;
     const int slot = chunk & 1;
@@ -848,3 +861,5 @@ extern "C" int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc,
   for (int i = 0; i < 4; i++) tmb_field_free(d[i]);
   return rc < 0 ? rc : iter;
 }
+
+#include "tmb_capi_mixed.inc"

@@ -28,11 +28,14 @@ double g_kappa = 0., g_mu = 0., g_mubar = 0., g_epsbar = 0., phmc_invmaxev = 1.;
 double X0 = 0., X1 = 0., X2 = 0., X3 = 0.;
 _Complex double ka0, ka1, ka2, ka3, phase_0, phase_1, phase_2, phase_3;
 su3 **g_gauge_field = NULL;
+double mixcg_innereps = 5.0e-5;    /* read_input.h / default_input_values.h:193 */
+int mixcg_maxinnersolverit = 5000; /* default_input_values.h:194 */
 
 static su3 *gauge_slab = NULL;
 static int dropin_up = 0;
 #define NDEV 12
 static void *D[NDEV];
+static void *D32[4];
 
 static void die(const char *where) {
   /* like fatal_error() (fatal_error.c): message, then abort the program */
@@ -64,6 +67,7 @@ int tmb_dropin_init(int t, int lx, int ly, int lz, int device) {
 }
 int tmb_dropin_finalize(void) {
   for (int k = 0; k < NDEV; k++) D[k] = NULL; /* freed by tmb_finalize */
+  for (int k = 0; k < 4; k++) D32[k] = NULL;
   tmb_finalize();
   free(gauge_slab); free(g_gauge_field); gauge_slab = NULL; g_gauge_field = NULL;
   dropin_up = 0;
@@ -285,6 +289,41 @@ int cg_her(spinor *const P, spinor *const Q, const int max_iter, double eps_sq, 
   return it > max_iter ? -1 : it;
 }
 
+/* solver/mixed_cg_her.c:65: the (f, f32) = (Qtm_pm_psi, Qtm_pm_psi_32) pair runs on the device */
+int mixed_cg_her(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
+                 const int rel_prec, const int N, matrix_mult f, matrix_mult32 f32) {
+  (void)solver_params;
+  if (f != &Qtm_pm_psi || f32 != (matrix_mult32)&Qtm_pm_psi_32 || N != VOLUME / 2) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in mixed_cg_her: only (Qtm_pm_psi, Qtm_pm_psi_32) on VOLUME/2 sites is implemented\n");
+    exit(1);
+  }
+  sync_globals();
+  CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
+  up(6, Q);
+  int iter = tmb_mixed_cg_her(dev(7), dev(6), max_iter, eps_sq, rel_prec);
+  if (iter < -1) die(__func__);
+  down(P, 7);
+  if (g_debug_level > 0 && g_proc_id == 0) {
+    int it; double err, sec; tmb_solver_stats(&it, &err, &sec);
+    printf("# mixed CG: iter: %d eps_sq: %1.4e t/s: %1.4e\n", it, eps_sq, sec); /* mixed_cg_her.c:181 */
+  }
+  return iter;
+}
+
+/* operator/Hopping_Matrix_32.c:119, operator/tm_operators_32.c:94 on host spinor32 buffers */
+static void *dev32(int k) {
+  if (!D32[k]) { D32[k] = tmb_field32_alloc(); if (!D32[k]) die("tmb_field32_alloc"); }
+  return D32[k];
+}
+void Hopping_Matrix_32(const int ieo, spinor32 *const l, spinor32 *const k) {
+  sync_globals(); CHK(tmb_field32_upload(dev32(0), (const float *)k));
+  CHK(tmb_Hopping_Matrix_32(ieo, dev32(1), dev32(0))); CHK(tmb_field32_download((float *)l, dev32(1)));
+}
+void Qtm_pm_psi_32(spinor32 *const l, spinor32 *const k) {
+  sync_globals(); CHK(tmb_field32_upload(dev32(0), (const float *)k));
+  CHK(tmb_Qtm_pm_psi_32(dev32(1), dev32(0))); CHK(tmb_field32_download((float *)l, dev32(1)));
+}
+
 /* invert_eo.c:83-561: the even/odd CG branch (:152-157, :252, :268-270, :306-310) */
 int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
               const double precision, const int max_iter, const int solver_flag, const int rel_prec,
@@ -294,9 +333,9 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
               const CompressionType compression) {
   (void)sub_evs_flag; (void)no_extra_masses; (void)extra_masses; (void)solver_params; (void)id;
   (void)external_inverter; (void)sloppy; (void)compression;
-  if (!even_odd_flag || solver_flag != TMB_SOLVER_CG) {
-    fprintf(stderr, "tmLQCD-B200 FATAL in invert_eo: only the even/odd CG branch (solver_flag == CG, even_odd_flag != 0) "
-                    "is implemented on the GPU; got solver_flag=%d even_odd_flag=%d\n", solver_flag, even_odd_flag);
+  if (!even_odd_flag || (solver_flag != TMB_SOLVER_CG && solver_flag != TMB_SOLVER_MIXEDCG)) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in invert_eo: only the even/odd CG and MIXEDCG branches (even_odd_flag != 0) "
+                    "are implemented on the GPU; got solver_flag=%d even_odd_flag=%d\n", solver_flag, even_odd_flag);
     exit(1);
   }
   if (g_proc_id == 0 && g_debug_level > 0) {
@@ -305,7 +344,12 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
   }
   sync_globals();
   up(6, Even); up(7, Odd); up(9, Odd_new); /* Odd_new is the CG's initial guess (cg_her.c:84) */
-  int iter = tmb_invert_eo(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
+  int iter;
+  if (solver_flag == TMB_SOLVER_MIXEDCG) { /* invert_eo.c:225-232; mixed_cg_her zeroes the guess (:108) */
+    CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
+    iter = tmb_invert_eo_mixed(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
+  } else
+    iter = tmb_invert_eo(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
   if (iter < -1) die(__func__);
   down(Even_new, 8); down(Odd_new, 9);
   return iter;

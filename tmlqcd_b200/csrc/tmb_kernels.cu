@@ -2,12 +2,13 @@
  *
  * K1  hop_kernel        Hopping_Matrix / tm_times_ / tm_sub_ (operator/Hopping_Matrix.c:131,
  *                       tm_times_Hopping_Matrix.c:119, tm_sub_Hopping_Matrix.c:122) with the
- *                       epilogue and, for the CG, the <p,Ap> reduction fused in.
+ *                       epilogue and, for the CG, the <p,Ap> reduction fused in; double and,
+ *                       for the mixed CG, single precision (operator/Hopping_Matrix_32.c:99)
  * K3  elementwise       linalg/ BLAS-1 + twisted-mass diagonal (tm_operators.c, tm_operators_nd.c)
  * K4  reductions        square_norm / scalar_prod_r / assign_mul_add_r_and_square, two-stage:
  *                       warp shuffle + block partial, then one CTA finishing and doing the CG
  *                       scalar bookkeeping on the device.
- * Bandwidth-bound stencil: no tensor cores.  One thread per output site, 128-bit loads that are
+ * Bandwidth-bound stencil: no tensor cores.  One thread per output site, vector loads that are
  * contiguous across the warp (SoA), gauge streamed with L1::no_allocate + L2 evict-first.
  */
 #include "tmb_kernels.h"
@@ -34,12 +35,12 @@ __device__ __forceinline__ double block_sum(double v) {
 }
 
 /* ------------------------------------------------------------------ K1: hopping */
-template <int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
+template <class V2, int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a) {
   /* Programmatic dependent launch: let the next kernel of the stream start filling SMs while this
    * grid drains, and do everything that does not depend on the previous kernel before the wait -
-   * here an L2 bulk prefetch of this CTA's gauge rows (75 % of its traffic, read-only for the
-   * whole solve).  Both instructions are no-ops when the launch carries no PDL attribute. */
+   * optionally an L2 bulk prefetch of this CTA's gauge rows.  Both instructions are no-ops when
+   * the launch carries no PDL attribute.  (Measured: neither helps this kernel, see DESIGN.md.) */
   asm volatile("griddepcontrol.launch_dependents;");
   if (a.prefetch && threadIdx.x < 72) {
     const int first = blockIdx.x * BLOCK;
@@ -53,8 +54,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
         j0 = i0 - shift; if (j0 < 0) j0 += a.g.Vh;
       }
       if (j0 > a.g.Vh - n) j0 = a.g.Vh - n;
-      const double2 *src = a.U + (size_t)(((bwd ? 1 - a.par : a.par) * 4 + mu) * 9 + e) * a.g.Vh + j0;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n * 16));
+      const V2 *src = (const V2 *)a.U + (size_t)(((bwd ? 1 - a.par : a.par) * 4 + mu) * 9 + e) * a.g.Vh + j0;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((int)(n * sizeof(V2))));
     }
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -75,47 +76,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
     tmb_policies pol;
     pol.stream = tmb_policy_evict_first();
     pol.reuse = tmb_policy_evict_last();
-    tmb_hop_fields f;
-    f.in = a.in; f.U = a.U; f.halo_up = a.halo_up; f.halo_dn = a.halo_dn; f.Uhalo = a.Uhalo;
-    double2 r[12];
-    tmb_hop_site<DIST, HINTS>(r, f, a.g, a.par, i, a.ka, pol);
+    tmb_hop_fields<V2> f;
+    f.in = (const V2 *)a.in; f.U = (const V2 *)a.U;
+    f.halo_up = (const V2 *)a.halo_up; f.halo_dn = (const V2 *)a.halo_dn; f.Uhalo = (const V2 *)a.Uhalo;
+    V2 ka[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) ka[m] = cvt2<V2>(a.ka[m]);
+    const V2 cf = cvt2<V2>(a.cf);
+    V2 r[12];
+    tmb_hop_site<DIST, HINTS>(r, f, a.g, a.par, i, ka, pol);
+    const V2 *pp = (const V2 *)a.p, *dw_ = (const V2 *)a.dotw;
+    V2 *out = (V2 *)a.out;
 #pragma unroll
     for (int c = 0; c < 12; c++) {
-      double2 pc = make_double2(0., 0.);
-      if (MODE >= 2) pc = a.p[(size_t)c * a.g.Vh + i];
-      const double2 o = tmb_epilogue<MODE>(c, r[c], pc, a.cf);
+      V2 pc = mk2<V2>(0, 0);
+      if (MODE >= 2) pc = pp[(size_t)c * a.g.Vh + i];
+      const V2 o = tmb_epilogue<MODE>(c, r[c], pc, cf);
       if (DOT) {
-        const double2 dw = a.dotw[(size_t)c * a.g.Vh + i];
-        dsum += dw.x * o.x;
-        dsum += dw.y * o.y;
+        const V2 dw = dw_[(size_t)c * a.g.Vh + i];
+        dsum += (double)dw.x * (double)o.x;
+        dsum += (double)dw.y * (double)o.y;
       }
-      tmb_store_out<HINTS>(a.out + (size_t)c * a.g.Vh + i, o, pol);
+      tmb_store_out<HINTS>(out + (size_t)c * a.g.Vh + i, o, pol);
     }
   }
   if (DOT) {
     const double s = block_sum<BLOCK>(dsum);
     if (threadIdx.x == 0) a.partial[blockIdx.x] = s;
   }
-}
-
-static int hop_variant_block(int variant);
-int tmb_hop_grid(const tmb_hop_launch &a) { const int b = hop_variant_block(a.variant); return (a.nsites + b - 1) / b; }
-
-template <int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
-static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
-  const int grid = tmb_hop_grid(a);
-  if (grid <= 0) return cudaSuccess;
-  if (a.pdl) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, hop_kernel<MODE, DIST, DOT, HINTS, BLOCK, MINB>, a);
-  }
-  hop_kernel<MODE, DIST, DOT, HINTS, BLOCK, MINB><<<grid, BLOCK, 0, s>>>(a);
-  return cudaGetLastError();
 }
 
 /* production configuration: chosen from the sweep in profiles/  */
@@ -125,18 +113,61 @@ static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
 #ifndef TMB_HOP_MINB
 #define TMB_HOP_MINB 3
 #endif
+/* single precision: half the registers per value -> more CTAs per SM */
+#define TMB_HOP_BLOCK_F 128
+#define TMB_HOP_MINB_F 4
+
+static int hop_variant_block(int variant) {
+  static const int b[10] = {TMB_HOP_BLOCK, 64, 64, 128, 128, 128, 256, 256, 96, 192};
+  return (variant >= 0 && variant < 10) ? b[variant] : TMB_HOP_BLOCK;
+}
+int tmb_hop_grid(const tmb_hop_launch &a) {
+  const int b = a.prec ? TMB_HOP_BLOCK_F : hop_variant_block(a.variant);
+  return (a.nsites + b - 1) / b;
+}
+
+template <class V2, int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
+static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
+  const int grid = (a.nsites + BLOCK - 1) / BLOCK;
+  if (grid <= 0) return cudaSuccess;
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, hop_kernel<V2, MODE, DIST, DOT, HINTS, BLOCK, MINB>, a);
+  }
+  hop_kernel<V2, MODE, DIST, DOT, HINTS, BLOCK, MINB><<<grid, BLOCK, 0, s>>>(a);
+  return cudaGetLastError();
+}
 
 template <int DIST, int HINTS>
 static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
     if (a.mode != 2) return cudaErrorInvalidValue;
-    return hop_go<2, DIST, 1, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    return hop_go<double2, 2, DIST, 1, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
   }
   switch (a.mode) {
-    case 0: return hop_go<0, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
-    case 1: return hop_go<1, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
-    case 2: return hop_go<2, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
-    case 3: return hop_go<3, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    case 0: return hop_go<double2, 0, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    case 1: return hop_go<double2, 1, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    case 2: return hop_go<double2, 2, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+    case 3: return hop_go<double2, 3, DIST, 0, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+/* single precision: cache-policy loads always on */
+template <int DIST>
+static cudaError_t hop_mode_f(const tmb_hop_launch &a, cudaStream_t s) {
+  if (a.dot) {
+    if (a.mode != 2) return cudaErrorInvalidValue;
+    return hop_go<float2, 2, DIST, 1, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+  }
+  switch (a.mode) {
+    case 0: return hop_go<float2, 0, DIST, 0, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+    case 1: return hop_go<float2, 1, DIST, 0, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+    case 2: return hop_go<float2, 2, DIST, 0, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -145,25 +176,21 @@ static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
 template <int HINTS>
 static cudaError_t hop_tune(const tmb_hop_launch &a, int variant, cudaStream_t s) {
   switch (variant) {
-    case 1: return hop_go<0, 0, 0, HINTS, 64, 4>(a, s);
-    case 2: return hop_go<0, 0, 0, HINTS, 64, 6>(a, s);
-    case 3: return hop_go<0, 0, 0, HINTS, 128, 2>(a, s);
-    case 4: return hop_go<0, 0, 0, HINTS, 128, 3>(a, s);
-    case 5: return hop_go<0, 0, 0, HINTS, 128, 4>(a, s);
-    case 6: return hop_go<0, 0, 0, HINTS, 256, 1>(a, s);
-    case 7: return hop_go<0, 0, 0, HINTS, 256, 2>(a, s);
-    case 8: return hop_go<0, 0, 0, HINTS, 96, 4>(a, s);
-    case 9: return hop_go<0, 0, 0, HINTS, 192, 2>(a, s);
+    case 1: return hop_go<double2, 0, 0, 0, HINTS, 64, 4>(a, s);
+    case 2: return hop_go<double2, 0, 0, 0, HINTS, 64, 6>(a, s);
+    case 3: return hop_go<double2, 0, 0, 0, HINTS, 128, 2>(a, s);
+    case 4: return hop_go<double2, 0, 0, 0, HINTS, 128, 3>(a, s);
+    case 5: return hop_go<double2, 0, 0, 0, HINTS, 128, 4>(a, s);
+    case 6: return hop_go<double2, 0, 0, 0, HINTS, 256, 1>(a, s);
+    case 7: return hop_go<double2, 0, 0, 0, HINTS, 256, 2>(a, s);
+    case 8: return hop_go<double2, 0, 0, 0, HINTS, 96, 4>(a, s);
+    case 9: return hop_go<double2, 0, 0, 0, HINTS, 192, 2>(a, s);
   }
   return cudaErrorInvalidValue;
 }
 
-static int hop_variant_block(int variant) {
-  static const int b[10] = {TMB_HOP_BLOCK, 64, 64, 128, 128, 128, 256, 256, 96, 192};
-  return (variant >= 0 && variant < 10) ? b[variant] : TMB_HOP_BLOCK;
-}
-
 cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s) {
+  if (a.prec) return a.dist ? hop_mode_f<1>(a, s) : hop_mode_f<0>(a, s);
   const int variant = a.variant;
   if (variant > 0) {
     if (a.mode != 0 || a.dist || a.dot) return cudaErrorInvalidValue;
@@ -181,13 +208,13 @@ int tmb_red_grid(size_t n2) {
   return (int)(need < cap ? (need ? need : 1) : cap);
 }
 
-struct RedNorm2 {
-  const double2 *a;
-  __device__ double operator()(size_t k) const { const double2 v = a[k]; return v.x * v.x + v.y * v.y; }
+template <class V2> struct RedNorm2 {
+  const V2 *a;
+  __device__ double operator()(size_t k) const { const V2 v = a[k]; return (double)v.x * v.x + (double)v.y * v.y; }
 };
-struct RedDot { /* Re <a,b> = sum a.re*b.re + a.im*b.im   (linalg/scalar_prod_r.c:159-163) */
-  const double2 *a, *b;
-  __device__ double operator()(size_t k) const { const double2 v = a[k], w = b[k]; return v.x * w.x + v.y * w.y; }
+template <class V2> struct RedDot { /* Re <a,b> = sum a.re*b.re + a.im*b.im   (linalg/scalar_prod_r.c:159-163) */
+  const V2 *a, *b;
+  __device__ double operator()(size_t k) const { const V2 v = a[k], w = b[k]; return (double)v.x * w.x + (double)v.y * w.y; }
 };
 struct RedXpayNorm { /* R = c R + S, |R|^2   (linalg/assign_mul_add_r_and_square.c:145) */
   double2 *r; const double2 *sv; double c;
@@ -197,15 +224,16 @@ struct RedXpayNorm { /* R = c R + S, |R|^2   (linalg/assign_mul_add_r_and_square
     return v.x * v.x + v.y * v.y;
   }
 };
-struct RedCgXR { /* x += alpha p ; r -= alpha Ap ; |r|^2      (cg_her.c:95-101) */
-  double2 *x, *r; const double2 *p, *ap; const tmb_cg_state *st;
+template <class V2> struct RedCgXR { /* x += alpha p ; r -= alpha Ap ; |r|^2      (cg_her.c:95-101) */
+  V2 *x, *r; const V2 *p, *ap; const tmb_cg_state *st;
   __device__ double operator()(size_t k) const {
-    const double al = st->alpha;
-    double2 xv = x[k]; const double2 pv = p[k];
+    typedef typename tmb_real<V2>::type R;
+    const R al = (R)st->alpha;
+    V2 xv = x[k]; const V2 pv = p[k];
     xv.x += al * pv.x; xv.y += al * pv.y; x[k] = xv;
-    double2 rv = r[k]; const double2 av = ap[k];
+    V2 rv = r[k]; const V2 av = ap[k];
     rv.x = rv.x - al * av.x; rv.y = rv.y - al * av.y; r[k] = rv;
-    return rv.x * rv.x + rv.y * rv.y;
+    return (double)rv.x * rv.x + (double)rv.y * rv.y;
   }
 };
 
@@ -236,6 +264,17 @@ __device__ void cg_apply(tmb_cg_state *st, int slot, int op) {
     }
   } else if (op == TMB_FIN_CG_INIT) {
     st->normsq = sum;
+  } else if (op == TMB_FIN_MCG_ERR) {
+    /* solver/mixed_cg_her.c:139-150: j counts the iterations that did NOT break */
+    st->err = sum;
+    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
+    if (sum <= st->inner_eps * st->sqnrm0 || st->iter == st->max_iter || 1.3 * sum <= thr) {
+      st->converged = 1;
+    } else {
+      st->beta = sum / st->normsq;
+      st->normsq = sum;
+      st->iter += 1;
+    }
   }
 }
 
@@ -265,26 +304,24 @@ cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s)
   apply_kernel<<<1, 1, 0, s>>>(st, slot, op);
   return cudaGetLastError();
 }
-cudaError_t tmb_launch_norm2(const double2 *a, size_t n2, double *partial, cudaStream_t s) {
-  RedNorm2 f = {a};
-  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, nullptr);
-  return cudaGetLastError();
+#define RED_LAUNCH(f, n2, partial, st, s) \
+  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st); return cudaGetLastError(); } while (0)
+
+cudaError_t tmb_launch_norm2(int prec, const void *a, size_t n2, double *partial, cudaStream_t s) {
+  if (prec) { RedNorm2<float2> f = {(const float2 *)a}; RED_LAUNCH(f, n2, partial, nullptr, s); }
+  RedNorm2<double2> f = {(const double2 *)a}; RED_LAUNCH(f, n2, partial, nullptr, s);
 }
-cudaError_t tmb_launch_dot(const double2 *a, const double2 *b, size_t n2, double *partial, cudaStream_t s) {
-  RedDot f = {a, b};
-  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, nullptr);
-  return cudaGetLastError();
+cudaError_t tmb_launch_dot(int prec, const void *a, const void *b, size_t n2, double *partial, cudaStream_t s) {
+  if (prec) { RedDot<float2> f = {(const float2 *)a, (const float2 *)b}; RED_LAUNCH(f, n2, partial, nullptr, s); }
+  RedDot<double2> f = {(const double2 *)a, (const double2 *)b}; RED_LAUNCH(f, n2, partial, nullptr, s);
 }
 cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s) {
-  RedXpayNorm f = {r, sv, c};
-  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, nullptr);
-  return cudaGetLastError();
+  RedXpayNorm f = {r, sv, c}; RED_LAUNCH(f, n2, partial, nullptr, s);
 }
-cudaError_t tmb_launch_cg_update_xr(double2 *x, double2 *r, const double2 *p, const double2 *ap, size_t n2,
+cudaError_t tmb_launch_cg_update_xr(int prec, void *x, void *r, const void *p, const void *ap, size_t n2,
                                     const tmb_cg_state *st, double *partial, cudaStream_t s) {
-  RedCgXR f = {x, r, p, ap, st};
-  red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st);
-  return cudaGetLastError();
+  if (prec) { RedCgXR<float2> f = {(float2 *)x, (float2 *)r, (const float2 *)p, (const float2 *)ap, st}; RED_LAUNCH(f, n2, partial, st, s); }
+  RedCgXR<double2> f = {(double2 *)x, (double2 *)r, (const double2 *)p, (const double2 *)ap, st}; RED_LAUNCH(f, n2, partial, st, s);
 }
 
 /* ------------------------------------------------------------------ K3: elementwise */
@@ -318,8 +355,10 @@ struct EwDiagSub { double2 *l; const double2 *kk, *jj; double2 z; int g5; size_t
     const double2 zk = c_mul(up ? z : c_conj(z), kk[k]); const double2 j = jj[k];
     l[k] = (up || !g5) ? c_sub(zk, j) : c_sub(j, zk);
   } };
-struct EwCgP { double2 *p; const double2 *r; const tmb_cg_state *st; /* p = beta p + r  (cg_her.c:122) */
-  __host__ __device__ void operator()(size_t k) const { const double b = st->beta; double2 v = p[k]; const double2 w = r[k]; v.x = b * v.x + w.x; v.y = b * v.y + w.y; p[k] = v; } };
+template <class V2> struct EwCgP { V2 *p; const V2 *r; const tmb_cg_state *st; /* p = beta p + r  (cg_her.c:122) */
+  __host__ __device__ void operator()(size_t k) const {
+    typedef typename tmb_real<V2>::type R;
+    const R b = (R)st->beta; V2 v = p[k]; const V2 w = r[k]; v.x = b * v.x + w.x; v.y = b * v.y + w.y; p[k] = v; } };
 /* tm_operators_nd.c:639-695 */
 struct EwNdMeeInv { double2 *ls, *lc; const double2 *ks, *kc; double mu, eps, nrm; size_t half;
   __host__ __device__ void operator()(size_t k) const {
@@ -339,6 +378,11 @@ struct EwNdMooSubG5 { double2 *ls, *lc; const double2 *ks, *kc, *js, *jc; double
     double2 b = c_mul(zc, c); b.x += eps * s.x; b.y += eps * s.y;
     ls[k] = up ? c_sub(a, ts) : c_sub(ts, a); lc[k] = up ? c_sub(b, tc) : c_sub(tc, b);
   } };
+/* linalg/assign_to_32.c, linalg/addto_32.c */
+struct EwToFloat { float2 *d; const double2 *sv;
+  __host__ __device__ void operator()(size_t k) const { const double2 v = sv[k]; d[k] = make_float2((float)v.x, (float)v.y); } };
+struct EwAddFromFloat { double2 *d; const float2 *sv;
+  __host__ __device__ void operator()(size_t k) const { double2 v = d[k]; const float2 w = sv[k]; v.x += (double)w.x; v.y += (double)w.y; d[k] = v; } };
 
 cudaError_t tmb_launch_axpy(double2 *p, const double2 *q, double c, size_t n2, cudaStream_t s) { EwAxpy f = {p, q, c}; EW_LAUNCH(f, n2, nullptr, s); }
 cudaError_t tmb_launch_xpay(double2 *r, double c, const double2 *sv, size_t n2, cudaStream_t s) { EwXpay f = {r, sv, c}; EW_LAUNCH(f, n2, nullptr, s); }
@@ -347,11 +391,16 @@ cudaError_t tmb_launch_scale(double2 *r, double c, const double2 *sv, size_t n2,
 cudaError_t tmb_launch_gamma5(double2 *l, const double2 *k, size_t n2, size_t half, cudaStream_t s) { EwG5 f = {l, k, half}; EW_LAUNCH(f, n2, nullptr, s); }
 cudaError_t tmb_launch_diag(double2 *l, const double2 *k, double2 z, size_t n2, size_t half, cudaStream_t s) { EwDiag f = {l, k, z, half}; EW_LAUNCH(f, n2, nullptr, s); }
 cudaError_t tmb_launch_diag_sub(double2 *l, const double2 *k, const double2 *j, double2 z, int g5, size_t n2, size_t half, cudaStream_t s) { EwDiagSub f = {l, k, j, z, g5, half}; EW_LAUNCH(f, n2, nullptr, s); }
-cudaError_t tmb_launch_cg_update_p(double2 *p, const double2 *r, size_t n2, const tmb_cg_state *st, cudaStream_t s) { EwCgP f = {p, r, st}; EW_LAUNCH(f, n2, st, s); }
+cudaError_t tmb_launch_cg_update_p(int prec, void *p, const void *r, size_t n2, const tmb_cg_state *st, cudaStream_t s) {
+  if (prec) { EwCgP<float2> f = {(float2 *)p, (const float2 *)r, st}; EW_LAUNCH(f, n2, st, s); }
+  EwCgP<double2> f = {(double2 *)p, (const double2 *)r, st}; EW_LAUNCH(f, n2, st, s);
+}
 cudaError_t tmb_launch_nd_mee_inv(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc, double mu, double eps, size_t n2, size_t half, cudaStream_t s) {
   EwNdMeeInv f = {ls, lc, ks, kc, mu, eps, 1. / (1. + mu * mu - eps * eps), half}; EW_LAUNCH(f, n2, nullptr, s); }
 cudaError_t tmb_launch_nd_moo_sub_g5(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc, const double2 *js, const double2 *jc, double mu, double eps, size_t n2, size_t half, cudaStream_t s) {
   EwNdMooSubG5 f = {ls, lc, ks, kc, js, jc, mu, eps, half}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_to_float(float2 *dst, const double2 *src, size_t n, cudaStream_t s) { EwToFloat f = {dst, src}; EW_LAUNCH(f, n, nullptr, s); }
+cudaError_t tmb_launch_add_from_float(double2 *dst, const float2 *src, size_t n, cudaStream_t s) { EwAddFromFloat f = {dst, src}; EW_LAUNCH(f, n, nullptr, s); }
 
 /* ------------------------------------------------------------------ layout conversion */
 /* host AoS spinor (su3.h:60-63: 12 complex per site, site-major)  <->  device SoA [12][Vh] */
@@ -388,13 +437,13 @@ struct EwPackGauge { double2 *U; const double2 *lex; tmb_geom g;
     const int ix = tmb_eo_to_lexic(g, q, i);
     U[k] = lex[((size_t)ix * 4 + mu) * 9 + e];
   } };
-struct EwPackHalo { double2 *up, *dn; const double2 *in; tmb_geom g;
+template <class V2> struct EwPackHalo { V2 *up, *dn; const V2 *in; tmb_geom g;
   __host__ __device__ void operator()(size_t k) const { /* k in [0, 6*S) */
     const int c = (int)(k / g.S), j = (int)(k - (size_t)c * g.S);
     const size_t last = (size_t)(g.T - 1) * g.S + j;
-    const double2 a = in[(size_t)c * g.Vh + last], b = in[(size_t)(c + 6) * g.Vh + last];
+    const V2 a = in[(size_t)c * g.Vh + last], b = in[(size_t)(c + 6) * g.Vh + last];
     up[k] = c_sub(a, b);                 /* (1-g0): s0-s2, s1-s3 of the last slice -> rank+1 */
-    const double2 a0 = in[(size_t)c * g.Vh + j], b0 = in[(size_t)(c + 6) * g.Vh + j];
+    const V2 a0 = in[(size_t)c * g.Vh + j], b0 = in[(size_t)(c + 6) * g.Vh + j];
     dn[k] = c_add(a0, b0);               /* (1+g0): s0+s2, s1+s3 of the first slice -> rank-1 */
   } };
 struct EwPackGaugeHalo { double2 *out; const double2 *U; tmb_geom g;
@@ -410,5 +459,8 @@ cudaError_t tmb_launch_unpack_eo_range(double2 *aos, const double2 *soa, int Vh,
 cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackLex f = {even, odd, lex, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
 cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s) { EwUnpackLex f = {lex, even, odd, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
 cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackGauge f = {U, lex, g}; EW_LAUNCH(f, (size_t)72 * g.Vh, nullptr, s); }
-cudaError_t tmb_launch_pack_halo(double2 *up, double2 *dn, const double2 *in, tmb_geom g, cudaStream_t s) { EwPackHalo f = {up, dn, in, g}; EW_LAUNCH(f, (size_t)6 * g.S, nullptr, s); }
+cudaError_t tmb_launch_pack_halo(int prec, void *up, void *dn, const void *in, tmb_geom g, cudaStream_t s) {
+  if (prec) { EwPackHalo<float2> f = {(float2 *)up, (float2 *)dn, (const float2 *)in, g}; EW_LAUNCH(f, (size_t)6 * g.S, nullptr, s); }
+  EwPackHalo<double2> f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g}; EW_LAUNCH(f, (size_t)6 * g.S, nullptr, s);
+}
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s) { EwPackGaugeHalo f = {out, U, g}; EW_LAUNCH(f, (size_t)18 * g.S, nullptr, s); }

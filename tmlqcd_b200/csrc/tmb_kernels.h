@@ -1,5 +1,7 @@
 /* tmb_kernels.h - internal C++ interface between the C-ABI layer (tmb_capi.cu) and the
- * CUDA kernels (tmb_kernels.cu).  Not installed; the public interface is include/tmlqcd_b200.h. */
+ * CUDA kernels (tmb_kernels.cu).  Not installed; the public interface is include/tmlqcd_b200.h.
+ * Field pointers are void*: `prec` (0 = double2 elements, 1 = float2 elements) selects the
+ * instantiation, reductions always accumulate and land in double. */
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -14,28 +16,32 @@ struct tmb_cg_state {
   double alpha, beta;
   double sqnorm_q; /* |Q|^2, for rel_prec */
   double eps_sq;
+  double inner_eps; /* mixed CG: inner stop err <= inner_eps * sqnrm0 (mixed_cg_her.c:141) */
+  double sqnrm0;    /* mixed CG: |delta|^2 at the start of the inner solve */
   double tmp[4];   /* landing slots of reductions (all-reduced in place when nranks > 1) */
   int rel_prec;
-  int converged;   /* set on device when err <= eps_sq (* sqnorm_q); later kernels become no-ops */
+  int converged;   /* set on device when the stop test fires; later kernels become no-ops */
   int iter;        /* iterations completed */
-  int pad;
+  int max_iter;    /* mixed CG inner loop: also stop after this many iterations */
 };
 
 enum tmb_fin_op {
-  TMB_FIN_STORE = 0,   /* tmp[slot] = sum */
-  TMB_FIN_CG_PRO = 1,  /* pro = sum; alpha = normsq/pro              cg_her.c:93-94 */
-  TMB_FIN_CG_ERR = 2,  /* err = sum; iter++; stop test; beta; normsq cg_her.c:101-126 */
-  TMB_FIN_CG_INIT = 3  /* normsq = sum                               cg_her.c:88 */
+  TMB_FIN_STORE = 0,    /* tmp[slot] = sum */
+  TMB_FIN_CG_PRO = 1,   /* pro = sum; alpha = normsq/pro              cg_her.c:93-94 */
+  TMB_FIN_CG_ERR = 2,   /* err = sum; iter++; stop test; beta; normsq cg_her.c:101-126 */
+  TMB_FIN_CG_INIT = 3,  /* normsq = sum                               cg_her.c:88 */
+  TMB_FIN_MCG_ERR = 4   /* inner loop of mixed_cg_her.c:139-150: its four-way stop test */
 };
 
 struct tmb_hop_launch {
-  const double2 *in; double2 *out; const double2 *p; const double2 *dotw;
-  const double2 *U; const double2 *halo_up, *halo_dn, *Uhalo;
+  const void *in; void *out; const void *p; const void *dotw;
+  const void *U; const void *halo_up, *halo_dn, *Uhalo;
   double *partial;          /* fused-dot block partials (DOT) */
   const tmb_cg_state *st;   /* if non-null: kernel exits immediately when st->converged */
   tmb_geom g;
   int par;                  /* parity of the OUTPUT sites = ieo of Hopping_Matrix(ieo,l,k) */
   double2 ka[4]; double2 cf;
+  int prec;                 /* 0: double, 1: float */
   int mode;                 /* epilogue 0..3, see tmb_site.cuh */
   int dist;                 /* 1: +-t of the boundary slices from halo buffers */
   int dot;                  /* 1: accumulate Re<dotw, out> into partial[] */
@@ -56,14 +62,14 @@ cudaError_t tmb_launch_final(const double *partial, int n, tmb_cg_state *st, int
                              cudaStream_t s);
 cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s);
 int tmb_red_grid(size_t n2);
-cudaError_t tmb_launch_norm2(const double2 *a, size_t n2, double *partial, cudaStream_t s);
-cudaError_t tmb_launch_dot(const double2 *a, const double2 *b, size_t n2, double *partial, cudaStream_t s);
+cudaError_t tmb_launch_norm2(int prec, const void *a, size_t n2, double *partial, cudaStream_t s);
+cudaError_t tmb_launch_dot(int prec, const void *a, const void *b, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s);
-cudaError_t tmb_launch_cg_update_xr(double2 *x, double2 *r, const double2 *p, const double2 *ap, size_t n2,
+cudaError_t tmb_launch_cg_update_xr(int prec, void *x, void *r, const void *p, const void *ap, size_t n2,
                                     const tmb_cg_state *st, double *partial, cudaStream_t s);
-cudaError_t tmb_launch_cg_update_p(double2 *p, const double2 *r, size_t n2, const tmb_cg_state *st, cudaStream_t s);
+cudaError_t tmb_launch_cg_update_p(int prec, void *p, const void *r, size_t n2, const tmb_cg_state *st, cudaStream_t s);
 
-/* elementwise, n2 = 12*Vh double2 elements; `half` = 6*Vh separates spin 0,1 from spin 2,3 */
+/* elementwise, n2 = 12*Vh complex elements; `half` = 6*Vh separates spin 0,1 from spin 2,3 */
 cudaError_t tmb_launch_axpy(double2 *p, const double2 *q, double c, size_t n2, cudaStream_t s);
 cudaError_t tmb_launch_xpay(double2 *r, double c, const double2 *sv, size_t n2, cudaStream_t s);
 cudaError_t tmb_launch_lincomb(double2 *q, double a, const double2 *r, double b, const double2 *sv, size_t n2, cudaStream_t s);
@@ -78,6 +84,9 @@ cudaError_t tmb_launch_nd_mee_inv(double2 *ls, double2 *lc, const double2 *ks, c
 cudaError_t tmb_launch_nd_moo_sub_g5(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc,
                                      const double2 *js, const double2 *jc, double mu, double eps, size_t n2,
                                      size_t half, cudaStream_t s);
+/* precision conversion (linalg/assign_to_32.c, addto_32.c): n complex elements */
+cudaError_t tmb_launch_to_float(float2 *dst, const double2 *src, size_t n, cudaStream_t s);
+cudaError_t tmb_launch_add_from_float(double2 *dst, const float2 *src, size_t n, cudaStream_t s); /* dst += src */
 
 /* layout conversion between the reference's host AoS layouts and the device SoA layout */
 cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStream_t s);
@@ -88,6 +97,6 @@ cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *le
 cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s);
 /* T-face half-spinors: send_up = (1-g0) proj of the last slice, send_dn = (1+g0) proj of the first */
-cudaError_t tmb_launch_pack_halo(double2 *send_up, double2 *send_dn, const double2 *in, tmb_geom g, cudaStream_t s);
+cudaError_t tmb_launch_pack_halo(int prec, void *send_up, void *send_dn, const void *in, tmb_geom g, cudaStream_t s);
 /* Uhalo[q][e][j] = U[q][0][e][(T-1)S + j] : what rank+1 needs from this rank */
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s);

@@ -8,17 +8,31 @@
  * operator/hopping_body_dbl.c:64-181):
  *   r(x) = sum_mu [ ka_mu U_mu(x) (1+g_mu)-proj k(x+mu) + conj(ka_mu) U_mu(x-mu)^+ (1-g_mu)-proj k(x-mu) ]
  *
+ * Everything is templated on the complex element type V2: double2 for the double-precision
+ * path, float2 for the single-precision operator of the mixed CG (operator/Hopping_Matrix_32.c,
+ * operator/tm_operators_32.c).
+ *
  * Device layout (B200-first, not the reference's AoS):
- *   spinor field  f[c*Vh + i]                 c = 3*spin+colour (12), i = eo-sub site, double2 = (re,im)
+ *   spinor field  f[c*Vh + i]                 c = 3*spin+colour (12), i = eo-sub site, V2 = (re,im)
  *   gauge field   U[((q*4+mu)*9 + e)*Vh + i]  q = parity of the site that owns the forward link,
  *                                             e = 3*row+col; each link stored ONCE (4V links);
  *                                             the backward hop gathers U[1-p][mu][.][nb] at the
  *                                             same neighbour index as the neighbour spinor.
- * Every load of a warp is 32 consecutive double2 = 512 contiguous bytes (128-bit per thread).
+ * Every load of a warp is 32 consecutive V2: 512 (double) or 256 (float) contiguous bytes.
  */
 #pragma once
 #include <cuda_runtime.h>
 #include "tmb_geom.h"
+
+template <class V2> struct tmb_real;
+template <> struct tmb_real<double2> { typedef double type; };
+template <> struct tmb_real<float2> { typedef float type; };
+template <class V2> TMB_HD V2 mk2(typename tmb_real<V2>::type x, typename tmb_real<V2>::type y) {
+  V2 v; v.x = x; v.y = y; return v;
+}
+template <class V2> TMB_HD V2 cvt2(double2 a) {
+  return mk2<V2>((typename tmb_real<V2>::type)a.x, (typename tmb_real<V2>::type)a.y);
+}
 
 /* ---------------- loads with cache policy ---------------- */
 #if defined(__CUDACC__)
@@ -30,6 +44,12 @@ __device__ __forceinline__ double2 tmb_ld_stream(const double2 *p, unsigned long
       : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ float2 tmb_ld_stream(const float2 *p, unsigned long long pol) {
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+      : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
 /* neighbour spinors: reused by 8 output sites -> keep in L1/L2 */
 __device__ __forceinline__ double2 tmb_ld_reuse(const double2 *p, unsigned long long pol) {
   double2 v;
@@ -37,9 +57,19 @@ __device__ __forceinline__ double2 tmb_ld_reuse(const double2 *p, unsigned long 
       : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ float2 tmb_ld_reuse(const float2 *p, unsigned long long pol) {
+  float2 v;
+  asm("ld.global.nc.L1::evict_last.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+      : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void tmb_st_stream(double2 *p, double2 v, unsigned long long pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;"
                :: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tmb_st_stream(float2 *p, float2 v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
 __device__ __forceinline__ unsigned long long tmb_policy_evict_first() {
   unsigned long long pol;
@@ -55,8 +85,8 @@ __device__ __forceinline__ unsigned long long tmb_policy_evict_last() {
 
 struct tmb_policies { unsigned long long stream, reuse; };
 
-template <int HINTS>
-TMB_HD double2 tmb_load_gauge(const double2 *p, const tmb_policies &pol) {
+template <int HINTS, class V2>
+TMB_HD V2 tmb_load_gauge(const V2 *p, const tmb_policies &pol) {
 #if defined(__CUDA_ARCH__)
   if (HINTS) return tmb_ld_stream(p, pol.stream);
   return __ldg(p);
@@ -64,8 +94,8 @@ TMB_HD double2 tmb_load_gauge(const double2 *p, const tmb_policies &pol) {
   (void)pol; return *p;
 #endif
 }
-template <int HINTS>
-TMB_HD double2 tmb_load_spinor(const double2 *p, const tmb_policies &pol) {
+template <int HINTS, class V2>
+TMB_HD V2 tmb_load_spinor(const V2 *p, const tmb_policies &pol) {
 #if defined(__CUDA_ARCH__)
   if (HINTS) return tmb_ld_reuse(p, pol.reuse);
   return __ldg(p);
@@ -73,8 +103,8 @@ TMB_HD double2 tmb_load_spinor(const double2 *p, const tmb_policies &pol) {
   (void)pol; return *p;
 #endif
 }
-template <int HINTS>
-TMB_HD void tmb_store_out(double2 *p, double2 v, const tmb_policies &pol) {
+template <int HINTS, class V2>
+TMB_HD void tmb_store_out(V2 *p, V2 v, const tmb_policies &pol) {
 #if defined(__CUDA_ARCH__)
   if (HINTS) { tmb_st_stream(p, v, pol.stream); return; }
   *p = v;
@@ -83,26 +113,23 @@ TMB_HD void tmb_store_out(double2 *p, double2 v, const tmb_policies &pol) {
 #endif
 }
 
-/* ---------------- complex helpers on double2 ---------------- */
-TMB_HD double2 c_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-TMB_HD double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-TMB_HD double2 c_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-TMB_HD double2 c_mulc(double2 a, double2 b) { /* conj(a)*b */
-  return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
-}
-TMB_HD double2 c_conj(double2 a) { return make_double2(a.x, -a.y); }
-TMB_HD void c_mad(double2 &acc, double2 a, double2 b) { /* acc += a*b */
+/* ---------------- complex helpers on V2 ---------------- */
+template <class V2> TMB_HD V2 c_add(V2 a, V2 b) { return mk2<V2>(a.x + b.x, a.y + b.y); }
+template <class V2> TMB_HD V2 c_sub(V2 a, V2 b) { return mk2<V2>(a.x - b.x, a.y - b.y); }
+template <class V2> TMB_HD V2 c_mul(V2 a, V2 b) { return mk2<V2>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <class V2> TMB_HD V2 c_conj(V2 a) { return mk2<V2>(a.x, -a.y); }
+template <class V2> TMB_HD void c_mad(V2 &acc, V2 a, V2 b) { /* acc += a*b */
   acc.x += a.x * b.x; acc.x -= a.y * b.y; acc.y += a.x * b.y; acc.y += a.y * b.x;
 }
-TMB_HD void c_madc(double2 &acc, double2 a, double2 b) { /* acc += conj(a)*b */
+template <class V2> TMB_HD void c_madc(V2 &acc, V2 a, V2 b) { /* acc += conj(a)*b */
   acc.x += a.x * b.x; acc.x += a.y * b.y; acc.y += a.x * b.y; acc.y -= a.y * b.x;
 }
 /* x + coef*y, coef code: 0:+1  1:-1  2:+i  3:-i */
-template <int C> TMB_HD double2 c_comb(double2 x, double2 y) {
-  if (C == 0) return make_double2(x.x + y.x, x.y + y.y);
-  if (C == 1) return make_double2(x.x - y.x, x.y - y.y);
-  if (C == 2) return make_double2(x.x - y.y, x.y + y.x);
-  return make_double2(x.x + y.y, x.y - y.x);
+template <int C, class V2> TMB_HD V2 c_comb(V2 x, V2 y) {
+  if (C == 0) return mk2<V2>(x.x + y.x, x.y + y.y);
+  if (C == 1) return mk2<V2>(x.x - y.x, x.y - y.y);
+  if (C == 2) return mk2<V2>(x.x - y.y, x.y + y.x);
+  return mk2<V2>(x.x + y.y, x.y - y.x);
 }
 /* the conjugate coefficient: 0->0, 1->1, 2->3, 3->2 */
 template <int C> struct conj_code { static const int v = (C < 2) ? C : (5 - C); };
@@ -121,31 +148,29 @@ template <> struct hop_tab<6> { static const int PA = 2, CA = 2, PB = 3, CB = 3;
 template <> struct hop_tab<7> { static const int PA = 2, CA = 3, PB = 3, CB = 2; };
 
 /* half-spinor of direction D from a full neighbour spinor at SoA index n */
-template <int D, int HINTS>
-TMB_HD void tmb_project(double2 a[3], double2 b[3], const double2 *__restrict__ in, int Vh, int n,
-                        const tmb_policies &pol) {
+template <int D, int HINTS, class V2>
+TMB_HD void tmb_project(V2 a[3], V2 b[3], const V2 *__restrict__ in, int Vh, int n, const tmb_policies &pol) {
   typedef hop_tab<D> Tb;
 #pragma unroll
   for (int c = 0; c < 3; c++) {
-    double2 s0 = tmb_load_spinor<HINTS>(in + (size_t)(0 + c) * Vh + n, pol);
-    double2 s1 = tmb_load_spinor<HINTS>(in + (size_t)(3 + c) * Vh + n, pol);
-    double2 sa = tmb_load_spinor<HINTS>(in + (size_t)(3 * Tb::PA + c) * Vh + n, pol);
-    double2 sb = tmb_load_spinor<HINTS>(in + (size_t)(3 * Tb::PB + c) * Vh + n, pol);
+    V2 s0 = tmb_load_spinor<HINTS>(in + (size_t)(0 + c) * Vh + n, pol);
+    V2 s1 = tmb_load_spinor<HINTS>(in + (size_t)(3 + c) * Vh + n, pol);
+    V2 sa = tmb_load_spinor<HINTS>(in + (size_t)(3 * Tb::PA + c) * Vh + n, pol);
+    V2 sb = tmb_load_spinor<HINTS>(in + (size_t)(3 * Tb::PB + c) * Vh + n, pol);
     a[c] = c_comb<Tb::CA>(s0, sa);
     b[c] = c_comb<Tb::CB>(s1, sb);
   }
 }
 
 /* phi = c * (U a) for forward, c * (U^dagger a) for backward (su3.h:308-316), then scatter */
-template <int D>
-TMB_HD void tmb_link_accumulate(double2 r[12], const double2 u[9], const double2 a[3], const double2 b[3],
-                                double2 ka) {
+template <int D, class V2>
+TMB_HD void tmb_link_accumulate(V2 r[12], const V2 u[9], const V2 a[3], const V2 b[3], V2 ka) {
   typedef hop_tab<D> Tb;
   const int BWD = D & 1;
-  const double2 c = BWD ? c_conj(ka) : ka;
+  const V2 c = BWD ? c_conj(ka) : ka;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    double2 xa = make_double2(0., 0.), xb = make_double2(0., 0.);
+    V2 xa = mk2<V2>(0, 0), xb = mk2<V2>(0, 0);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       if (BWD) { c_madc(xa, u[3 * j + i], a[j]); c_madc(xb, u[3 * j + i], b[j]); }
@@ -159,21 +184,21 @@ TMB_HD void tmb_link_accumulate(double2 r[12], const double2 u[9], const double2
   }
 }
 
-struct tmb_hop_fields {
-  const double2 *in;      /* k : field of the opposite parity, 12*Vh double2 */
-  const double2 *U;       /* gauge, [2][4][9][Vh] */
-  const double2 *halo_up; /* dist_t: [6][S] (1+g0)-projected first slice of rank+1 */
-  const double2 *halo_dn; /* dist_t: [6][S] (1-g0)-projected last slice of rank-1 */
-  const double2 *Uhalo;   /* dist_t: [2][9][S] U_0 of rank-1's last slice, by owner parity */
+template <class V2> struct tmb_hop_fields {
+  const V2 *in;      /* k : field of the opposite parity, 12*Vh elements */
+  const V2 *U;       /* gauge, [2][4][9][Vh] */
+  const V2 *halo_up; /* dist_t: [6][S] (1+g0)-projected first slice of rank+1 */
+  const V2 *halo_dn; /* dist_t: [6][S] (1-g0)-projected last slice of rank-1 */
+  const V2 *Uhalo;   /* dist_t: [2][9][S] U_0 of rank-1's last slice, by owner parity */
 };
 
-template <int D, int HINTS>
-TMB_HD void tmb_hop_dir(double2 r[12], const tmb_hop_fields &f, const tmb_geom &g, int par, int i, int n,
-                        double2 ka, const tmb_policies &pol) {
+template <int D, int HINTS, class V2>
+TMB_HD void tmb_hop_dir(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_geom &g, int par, int i, int n, V2 ka,
+                        const tmb_policies &pol) {
   const int mu = D >> 1, BWD = D & 1;
-  double2 a[3], b[3], u[9];
+  V2 a[3], b[3], u[9];
   /* forward link lives at the output site (parity par), backward link at the neighbour (parity 1-par) */
-  const double2 *ub = f.U + (size_t)(((BWD ? 1 - par : par) * 4 + mu) * 9) * g.Vh + (BWD ? n : i);
+  const V2 *ub = f.U + (size_t)(((BWD ? 1 - par : par) * 4 + mu) * 9) * g.Vh + (BWD ? n : i);
 #pragma unroll
   for (int e = 0; e < 9; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
   tmb_project<D, HINTS>(a, b, f.in, g.Vh, n, pol);
@@ -181,18 +206,18 @@ TMB_HD void tmb_hop_dir(double2 r[12], const tmb_hop_fields &f, const tmb_geom &
 }
 
 /* halo variants for the distributed T direction: the half-spinor arrives already projected */
-template <int D, int HINTS>
-TMB_HD void tmb_hop_dir_halo(double2 r[12], const tmb_hop_fields &f, const tmb_geom &g, int par, int i, int j,
-                             double2 ka, const tmb_policies &pol) {
-  double2 a[3], b[3], u[9];
+template <int D, int HINTS, class V2>
+TMB_HD void tmb_hop_dir_halo(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_geom &g, int par, int i, int j, V2 ka,
+                             const tmb_policies &pol) {
+  V2 a[3], b[3], u[9];
   if (D == 0) { /* +t at t == T-1: local forward link, half-spinor from rank+1 */
-    const double2 *ub = f.U + (size_t)((par * 4 + 0) * 9) * g.Vh + i;
+    const V2 *ub = f.U + (size_t)((par * 4 + 0) * 9) * g.Vh + i;
 #pragma unroll
     for (int e = 0; e < 9; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
 #pragma unroll
     for (int c = 0; c < 3; c++) { a[c] = f.halo_up[(size_t)c * g.S + j]; b[c] = f.halo_up[(size_t)(3 + c) * g.S + j]; }
   } else {      /* -t at t == 0: link and half-spinor from rank-1 */
-    const double2 *ub = f.Uhalo + (size_t)((1 - par) * 9) * g.S + j;
+    const V2 *ub = f.Uhalo + (size_t)((1 - par) * 9) * g.S + j;
 #pragma unroll
     for (int e = 0; e < 9; e++) u[e] = ub[(size_t)e * g.S];
 #pragma unroll
@@ -203,13 +228,13 @@ TMB_HD void tmb_hop_dir_halo(double2 r[12], const tmb_hop_fields &f, const tmb_g
 
 /* The full 8-direction sum for output site i of parity par.  ka[mu] = kappa*exp(i theta_mu pi/L_mu)
  * exactly as boundary.c:40-55 computes them on the host. */
-template <int DIST, int HINTS>
-TMB_HD void tmb_hop_site(double2 r[12], const tmb_hop_fields &f, const tmb_geom &g, int par, int i,
-                         const double2 ka[4], const tmb_policies &pol) {
+template <int DIST, int HINTS, class V2>
+TMB_HD void tmb_hop_site(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_geom &g, int par, int i, const V2 ka[4],
+                         const tmb_policies &pol) {
   int nb[8];
   const int t = tmb_neighbours(g, par, i, nb);
 #pragma unroll
-  for (int c = 0; c < 12; c++) r[c] = make_double2(0., 0.);
+  for (int c = 0; c < 12; c++) r[c] = mk2<V2>(0, 0);
   if (DIST && t == g.T - 1) tmb_hop_dir_halo<0, HINTS>(r, f, g, par, i, i - t * g.S, ka[0], pol);
   else                      tmb_hop_dir<0, HINTS>(r, f, g, par, i, nb[0], ka[0], pol);
   if (DIST && t == 0)       tmb_hop_dir_halo<1, HINTS>(r, f, g, par, i, i, ka[0], pol);
@@ -228,12 +253,12 @@ TMB_HD void tmb_hop_site(double2 r[12], const tmb_hop_fields &f, const tmb_geom 
  *   MODE 2  l = g5( (cf|conj cf) p - r )            _g5_cmplx_sub_hop_and_g5store tm_sub_Hopping_Matrix
  *   MODE 3  l = (cf|conj cf) p - r                  (M_full / D_psi rows: tm_operators.c:117-128)
  */
-template <int MODE>
-TMB_HD double2 tmb_epilogue(int c, double2 r, double2 p, double2 cf) {
+template <int MODE, class V2>
+TMB_HD V2 tmb_epilogue(int c, V2 r, V2 p, V2 cf) {
   if (MODE == 0) return r;
-  const double2 f = (c < 6) ? cf : c_conj(cf);
+  const V2 f = (c < 6) ? cf : c_conj(cf);
   if (MODE == 1) return c_mul(f, r);
-  const double2 zp = c_mul(f, p);
+  const V2 zp = c_mul(f, p);
   if (MODE == 2) return (c < 6) ? c_sub(zp, r) : c_sub(r, zp);
   return c_sub(zp, r);
 }
