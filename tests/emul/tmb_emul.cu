@@ -96,6 +96,45 @@ int emul_hop(int par, double *out, const double *in, const double *p, const doub
   return 0;
 }
 
+/* 12-real compressed links: same composition with CFG bit 1 set */
+int emul_hop12(int par, double *out, const double *in, const double *U12, const double *halo_up, const double *halo_dn,
+               const double *Uhalo12, int T, int LX, int LY, int LZ, const double *ka8, int dist) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, dist);
+  tmb_hop_fields<double2> f;
+  f.in = (const double2 *)in; f.U = (const double2 *)U12;
+  f.halo_up = (const double2 *)halo_up; f.halo_dn = (const double2 *)halo_dn; f.Uhalo = (const double2 *)Uhalo12;
+  double2 ka[4];
+  for (int m = 0; m < 4; m++) ka[m] = make_double2(ka8[2 * m], ka8[2 * m + 1]);
+  tmb_policies pol = {0, 0};
+  double2 *o = (double2 *)out;
+  for (int i = 0; i < g.Vh; i++) {
+    double2 r[12];
+    if (dist) tmb_hop_site<1, 2>(r, f, g, par, i, ka, pol); else tmb_hop_site<0, 2>(r, f, g, par, i, ka, pol);
+    for (int c = 0; c < 12; c++) o[(size_t)c * g.Vh + i] = r[c];
+  }
+  return 0;
+}
+void emul_compress12(double *dst, const double *src, long n, int nlinks) {
+  EwCompress12 f = {(double2 *)dst, (const double2 *)src, (size_t)n};
+  for (size_t k = 0; k < (size_t)nlinks * 6 * n; k++) f(k);
+}
+/* single precision instantiation of the same site code */
+int emul_hop_f(int par, float *out, const float *in, const float *U, int T, int LX, int LY, int LZ, const double *ka8) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  tmb_hop_fields<float2> f;
+  f.in = (const float2 *)in; f.U = (const float2 *)U; f.halo_up = f.halo_dn = f.Uhalo = nullptr;
+  float2 ka[4];
+  for (int m = 0; m < 4; m++) ka[m] = make_float2((float)ka8[2 * m], (float)ka8[2 * m + 1]);
+  tmb_policies pol = {0, 0};
+  float2 *o = (float2 *)out;
+  for (int i = 0; i < g.Vh; i++) {
+    float2 r[12];
+    tmb_hop_site<0, 0>(r, f, g, par, i, ka, pol);
+    for (int c = 0; c < 12; c++) o[(size_t)c * g.Vh + i] = r[c];
+  }
+  return 0;
+}
+
 /* x-blocked traversal: the permutation of work indices used by hop_kernel must be a bijection */
 void emul_xblock_perm(int *out, int T, int LX, int LY, int LZ, int XB) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "emul", "libtmb_emul.so")
 dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 i, d = C.c_int, C.c_double
 
 
@@ -28,12 +29,14 @@ def load():
         "emul_pack_gauge_halo": [dp, dp, i, i, i, i], "emul_neighbours": [ip, i, i, i, i, i],
         "emul_eo2lexic": [ip, i, i, i, i], "emul_xblock_perm": [ip, i, i, i, i, i],
         "emul_hop": [i, dp, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, d, d, i, i],
+        "emul_hop12": [i, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, i], "emul_compress12": [dp, dp, C.c_long, i],
+        "emul_hop_f": [i, fp, fp, fp, i, i, i, i, dp],
         "emul_diag": [dp, dp, d, d, i], "emul_diag_sub": [dp, dp, dp, d, d, i, i], "emul_gamma5": [dp, dp, i],
         "emul_nd_mee_inv": [dp, dp, dp, dp, d, d, i], "emul_nd_moo_sub_g5": [dp, dp, dp, dp, dp, dp, d, d, i],
     }
     for n, a in sig.items():
         getattr(E, n).argtypes = a
-        getattr(E, n).restype = i if n == "emul_hop" else None
+        getattr(E, n).restype = i if n in ("emul_hop", "emul_hop12", "emul_hop_f") else None
     return E
 
 

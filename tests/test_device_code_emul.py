@@ -112,3 +112,29 @@ def test_xblock_traversal_is_a_permutation(dims, xb):
     perm = np.zeros(e.Vh, dtype=np.int32)
     e.E.emul_xblock_perm(perm, *dims, xb)
     assert np.array_equal(np.sort(perm), np.arange(e.Vh))
+
+
+def test_compressed_links_and_single_precision_instantiations(oracle_lib):
+    """12-real link reconstruction (CFG bit 1) and the float2 instantiation of the same site code"""
+    dims, theta = (4, 6, 4, 8), (1., 0.3, 0., 0.7)
+    rng = np.random.default_rng(12)
+    e, o = Emul(*dims), oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, theta)
+    ka = ka_of(KAPPA, theta, dims)
+    U = e.pack_gauge(g)
+    U12 = np.zeros(8 * 6 * 2 * e.Vh); e.E.emul_compress12(U12, U, e.Vh, 8)
+    k = random_spinor(rng, o.Vh); sk = e.pack(k)
+    up, dn = e.pack_halo(sk)
+    Uh = e.pack_gauge_halo(U); Uh12 = np.zeros(2 * 6 * 2 * e.S); e.E.emul_compress12(Uh12, Uh, e.S, 2)
+    z = np.zeros(2)
+    for par in (0, 1):
+        exp = o.spinor(); o.Hopping_Matrix(par, exp, k)
+        out = np.zeros(24 * e.Vh)
+        assert e.E.emul_hop12(par, out, sk, U12, z, z, z, *dims, ka, 0) == 0
+        assert rel_l2(e.unpack(out), exp) < 1e-14
+        assert e.E.emul_hop12(par, out, sk, U12, dn, up, Uh12, *dims, ka, 1) == 0
+        assert rel_l2(e.unpack(out), exp) < 1e-14
+        outf = np.zeros(24 * e.Vh, dtype=np.float32)
+        assert e.E.emul_hop_f(par, outf, sk.astype(np.float32), U.astype(np.float32), *dims, ka) == 0
+        assert rel_l2(e.unpack(outf.astype(np.float64)), exp) < 1e-6

@@ -472,3 +472,39 @@ def test_single_precision_operator_and_mixed_cg(oracle_lib):
         assert it > 0 and rel_l2(en, enr) <= 1e-9 and rel_l2(on, onr) <= 1e-9
     finally:
         D.close()
+
+
+@pytest.mark.parametrize("loopback", [0, 1])
+def test_gauge_compression_12(oracle_lib, loopback):
+    """CompressionType 12 (two rows streamed, third rebuilt): same results to 1e-13, refused for non-SU(3) links"""
+    import tmlqcd_b200 as tm
+    rng, o, d, g = _setup(oracle_lib, (8, 4, 6, 8), (1., 0.3, 0., 0.7))
+    try:
+        if loopback:
+            d.ck(d.lib.tmb_comm_loopback(1))
+            d.gauge_upload(g)
+        d.ck(d.lib.tmb_set_compression(12))
+        k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        dk, dp, dl, dx = d.field(k), d.field(p), d.field(), d.field()
+        exp = o.spinor()
+        for ieo in (0, 1):
+            o.Hopping_Matrix(ieo, exp, k); d.call("Hopping_Matrix", ieo, dl, dk); assert rel_l2(d.download(dl), exp) <= TOL
+            o.tm_sub_Hopping_Matrix(ieo, exp, p, k, 1.0, 0.3); d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3)
+            assert rel_l2(d.download(dl), exp) <= TOL
+        o.Qtm_pm_psi(exp, k); d.call("Qtm_pm_psi", dl, dk); assert rel_l2(d.download(dl), exp) <= TOL
+        xr = o.spinor(); itr = o.cg_her(xr, k, 2000, 1e-22, 1)
+        it = d.call("cg_her", dx, dk, 2000, 1e-22, 1)
+        assert abs(it - itr) <= 1 and rel_l2(d.download(dx), xr) <= 1e-10
+        it = d.call("mixed_cg_her", dx, dk, 2000, 1e-22, 1)  # float inner solve on compressed float links
+        assert it > 0 and rel_l2(d.download(dx), xr) <= 1e-9
+        # a new gauge field keeps the mode; a non-unitary field is refused loudly
+        g2 = random_gauge(rng, o.V); d.gauge_upload(g2); o.set_gauge(g2)
+        o.Hopping_Matrix(0, exp, k); d.call("Hopping_Matrix", 0, dl, dk); assert rel_l2(d.download(dl), exp) <= TOL
+        bad = g2.copy(); bad[5, 2, 13] += 1e-9
+        with pytest.raises(tm.capi.TmbError, match="compression refused"):
+            d.gauge_upload(bad)
+        d.ck(d.lib.tmb_set_compression(18))
+        d.gauge_upload(bad); o.set_gauge(bad)
+        o.Hopping_Matrix(0, exp, k); d.call("Hopping_Matrix", 0, dl, dk); assert rel_l2(d.download(dl), exp) <= TOL
+    finally:
+        d.close()

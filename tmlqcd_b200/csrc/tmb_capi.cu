@@ -58,6 +58,8 @@ struct Ctx {
   double2 *scratch[NSCRATCH] = {nullptr};
   float2 *scratch32[NSCRATCH] = {nullptr};
   float2 *U32 = nullptr, *Uhalo32 = nullptr; bool gauge32_valid = false;
+  int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
+  double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
   int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0;
   NcclApi nccl = {};
@@ -68,6 +70,7 @@ struct Ctx {
   bool gauge_loaded = false;
 };
 static Ctx C;
+static int ensure_gauge12(int prec);
 static std::string g_err;
 
 static int fail(int code, const char *fmt, ...) {
@@ -143,7 +146,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0;
+  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18;
   C.init = true;
   return 0;
 }
@@ -157,6 +160,7 @@ extern "C" int tmb_finalize(void) {
   for (int i = 0; i < NSCRATCH; i++) { if (C.scratch[i]) cudaFree(C.scratch[i]); C.scratch[i] = nullptr; }
   for (int i = 0; i < NSCRATCH; i++) { if (C.scratch32[i]) cudaFree(C.scratch32[i]); C.scratch32[i] = nullptr; }
   if (C.U32) cudaFree(C.U32); if (C.Uhalo32) cudaFree(C.Uhalo32);
+  if (C.U12) cudaFree(C.U12); if (C.Uhalo12) cudaFree(C.Uhalo12); if (C.U12f) cudaFree(C.U12f); if (C.Uhalo12f) cudaFree(C.Uhalo12f);
   cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
@@ -353,7 +357,8 @@ extern "C" int tmb_gauge_upload(const double *host_gauge) {
     CU(cudaFree(tmp));
   }
   C.gauge_loaded = true;
-  C.gauge32_valid = false;
+  C.gauge32_valid = false; C.c12_valid = false; C.c12f_valid = false;
+  if (C.compression == 12) TRY(ensure_gauge12(0));
   return 0;
 }
 
@@ -375,15 +380,25 @@ struct HopOpt {
   int prec = 0;               /* 0: double fields, 1: float fields + float gauge copy */
 };
 static int ensure_gauge32();
+static int ensure_gauge12(int prec);
 static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
   if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
   tmb_hop_launch a;
   memset(&a, 0, sizeof(a));
-  if (o.prec) TRY(ensure_gauge32());
   a.prec = o.prec;
-  a.in = in; a.out = out; a.p = o.p; a.dotw = o.dotw; a.U = o.prec ? (const void *)C.U32 : (const void *)C.U;
-  a.halo_up = C.halo_up; a.halo_dn = C.halo_dn; a.Uhalo = o.prec ? (const void *)C.Uhalo32 : (const void *)C.Uhalo;
+  a.recon12 = C.compression == 12;
+  a.in = in; a.out = out; a.p = o.p; a.dotw = o.dotw;
+  a.halo_up = C.halo_up; a.halo_dn = C.halo_dn;
+  if (a.recon12) {
+    TRY(ensure_gauge12(o.prec));
+    a.U = o.prec ? (const void *)C.U12f : (const void *)C.U12;
+    a.Uhalo = o.prec ? (const void *)C.Uhalo12f : (const void *)C.Uhalo12;
+  } else {
+    if (o.prec) TRY(ensure_gauge32());
+    a.U = o.prec ? (const void *)C.U32 : (const void *)C.U;
+    a.Uhalo = o.prec ? (const void *)C.Uhalo32 : (const void *)C.Uhalo;
+  }
   a.partial = C.partial; a.st = o.st; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.dotw ? 1 : 0; a.hints = C.hints;
@@ -392,7 +407,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   if (!C.dist) {
     a.dist = 0; a.site0 = o.site0; a.nsites = o.nsites < 0 ? C.g.Vh : o.nsites; a.split = a.nsites; a.gap = 0;
     /* tuning variants exist for the plain Hopping_Matrix kernel only */
-    a.variant = (o.mode == 0 && !a.dot) ? C.hop_variant : 0;
+    a.variant = (o.mode == 0 && !a.dot && !a.recon12 && !o.prec) ? C.hop_variant : 0;
     a.xblock = o.nsites < 0 ? C.xblock : 0;
     KL(tmb_launch_hop(a, C.s_main));
     np = tmb_hop_grid(a);

@@ -332,7 +332,7 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
               const ExternalInverter external_inverter, const SloppyPrecision sloppy,
               const CompressionType compression) {
   (void)sub_evs_flag; (void)no_extra_masses; (void)extra_masses; (void)solver_params; (void)id;
-  (void)external_inverter; (void)sloppy; (void)compression;
+  (void)external_inverter; (void)sloppy;
   if (!even_odd_flag || (solver_flag != TMB_SOLVER_CG && solver_flag != TMB_SOLVER_MIXEDCG)) {
     fprintf(stderr, "tmLQCD-B200 FATAL in invert_eo: only the even/odd CG and MIXEDCG branches (even_odd_flag != 0) "
                     "are implemented on the GPU; got solver_flag=%d even_odd_flag=%d\n", solver_flag, even_odd_flag);
@@ -343,6 +343,9 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
     fflush(stdout);
   }
   sync_globals();
+  /* CompressionType as the reference hands it to its external inverters (invert_eo.c:93-101);
+   * COMPRESSION_8 has no double-precision-exact reconstruction and is served as COMPRESSION_12 */
+  CHK(tmb_set_compression(compression == NO_COMPRESSION ? 18 : 12));
   up(6, Even); up(7, Odd); up(9, Odd_new); /* Odd_new is the CG's initial guess (cg_her.c:84) */
   int iter;
   if (solver_flag == TMB_SOLVER_MIXEDCG) { /* invert_eo.c:225-232; mixed_cg_her zeroes the guess (:108) */
@@ -351,6 +354,7 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
   } else
     iter = tmb_invert_eo(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
   if (iter < -1) die(__func__);
+  CHK(tmb_set_compression(18));
   down(Even_new, 8); down(Odd_new, 9);
   return iter;
 }

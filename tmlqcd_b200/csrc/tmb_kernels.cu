@@ -42,19 +42,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
    * optionally an L2 bulk prefetch of this CTA's gauge rows.  Both instructions are no-ops when
    * the launch carries no PDL attribute.  (Measured: neither helps this kernel, see DESIGN.md.) */
   asm volatile("griddepcontrol.launch_dependents;");
-  if (a.prefetch && threadIdx.x < 72) {
+  const int NE = (HINTS & 2) ? 6 : 9; /* stored complex numbers per link (12-real compression: 6) */
+  if (a.prefetch && threadIdx.x < 8 * NE) {
     const int first = blockIdx.x * BLOCK;
     int n = a.nsites - first; n = n > BLOCK ? BLOCK : n;
     if (n > 0) {
       const int i0 = a.site0 + first + (first >= a.split ? a.gap : 0);
-      const int d = threadIdx.x / 9, e = threadIdx.x - 9 * d, mu = d >> 1, bwd = d & 1;
+      const int d = threadIdx.x / NE, e = threadIdx.x - NE * d, mu = d >> 1, bwd = d & 1;
       int j0 = i0;
       if (bwd) {
         const int shift = mu == 0 ? a.g.S : (mu == 1 ? a.g.LY * a.g.Lzh : (mu == 2 ? a.g.Lzh : 0));
         j0 = i0 - shift; if (j0 < 0) j0 += a.g.Vh;
       }
       if (j0 > a.g.Vh - n) j0 = a.g.Vh - n;
-      const V2 *src = (const V2 *)a.U + (size_t)(((bwd ? 1 - a.par : a.par) * 4 + mu) * 9 + e) * a.g.Vh + j0;
+      const V2 *src = (const V2 *)a.U + (size_t)(((bwd ? 1 - a.par : a.par) * 4 + mu) * NE + e) * a.g.Vh + j0;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((int)(n * sizeof(V2))));
     }
   }
@@ -143,6 +144,7 @@ static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+/* HINTS is a configuration mask: bit 0 cache-policy loads, bit 1 12-real links (see tmb_site.cuh) */
 template <int DIST, int HINTS>
 static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
@@ -158,16 +160,16 @@ static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
   return cudaErrorInvalidValue;
 }
 /* single precision: cache-policy loads always on */
-template <int DIST>
+template <int DIST, int CFG>
 static cudaError_t hop_mode_f(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
     if (a.mode != 2) return cudaErrorInvalidValue;
-    return hop_go<float2, 2, DIST, 1, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+    return hop_go<float2, 2, DIST, 1, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
   }
   switch (a.mode) {
-    case 0: return hop_go<float2, 0, DIST, 0, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
-    case 1: return hop_go<float2, 1, DIST, 0, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
-    case 2: return hop_go<float2, 2, DIST, 0, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+    case 0: return hop_go<float2, 0, DIST, 0, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+    case 1: return hop_go<float2, 1, DIST, 0, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+    case 2: return hop_go<float2, 2, DIST, 0, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -190,7 +192,11 @@ static cudaError_t hop_tune(const tmb_hop_launch &a, int variant, cudaStream_t s
 }
 
 cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s) {
-  if (a.prec) return a.dist ? hop_mode_f<1>(a, s) : hop_mode_f<0>(a, s);
+  if (a.prec) {
+    if (a.recon12) return a.dist ? hop_mode_f<1, 3>(a, s) : hop_mode_f<0, 3>(a, s);
+    return a.dist ? hop_mode_f<1, 1>(a, s) : hop_mode_f<0, 1>(a, s);
+  }
+  if (a.recon12) return a.dist ? hop_mode<1, 3>(a, s) : hop_mode<0, 3>(a, s);
   const int variant = a.variant;
   if (variant > 0) {
     if (a.mode != 0 || a.dist || a.dot) return cudaErrorInvalidValue;
@@ -462,5 +468,48 @@ cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cu
 cudaError_t tmb_launch_pack_halo(int prec, void *up, void *dn, const void *in, tmb_geom g, cudaStream_t s) {
   if (prec) { EwPackHalo<float2> f = {(float2 *)up, (float2 *)dn, (const float2 *)in, g}; EW_LAUNCH(f, (size_t)6 * g.S, nullptr, s); }
   EwPackHalo<double2> f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g}; EW_LAUNCH(f, (size_t)6 * g.S, nullptr, s);
+}
+/* 12-real copies: rows 0,1 of every link; n = sites per link row (Vh for the bulk, S for the halo), nl links rows */
+struct EwCompress12 { double2 *dst; const double2 *src; size_t n;
+  __host__ __device__ void operator()(size_t k) const { /* k in [0, nl*6*n) */
+    const size_t i = k % n, row = k / n, e = row % 6, l = row / 6;
+    dst[k] = src[(l * 9 + e) * n + i];
+  } };
+cudaError_t tmb_launch_compress12(double2 *dst, const double2 *src, size_t n, int nlinks, cudaStream_t s) {
+  EwCompress12 f = {dst, src, n}; EW_LAUNCH(f, (size_t)nlinks * 6 * n, nullptr, s);
+}
+/* max over links of |row2 - conj(row0 x row1)|^2: how far the field is from what compression assumes */
+struct RedSu3Defect { const double2 *U; size_t n;
+  __device__ double operator()(size_t k) const { /* k in [0, nl*n) */
+    const size_t i = k % n, l = k / n;
+    double2 u[9];
+    for (int e = 0; e < 9; e++) u[e] = U[(l * 9 + e) * n + i];
+    double2 w[9];
+    for (int e = 0; e < 6; e++) w[e] = u[e];
+    tmb_reconstruct_row2(w);
+    double d = 0.;
+    for (int e = 6; e < 9; e++) { const double dx = w[e].x - u[e].x, dy = w[e].y - u[e].y; d += dx * dx + dy * dy; }
+    return d;
+  } };
+template <class F>
+__global__ void __launch_bounds__(RED_BLOCK) max_kernel(F f, size_t n2, double *partial) {
+  double acc = 0.;
+  for (size_t k = (size_t)blockIdx.x * RED_BLOCK + threadIdx.x; k < n2; k += (size_t)gridDim.x * RED_BLOCK) {
+    const double v = f(k); acc = v > acc ? v : acc;
+  }
+  __shared__ double sh[RED_BLOCK];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = RED_BLOCK / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] = sh[threadIdx.x + o] > sh[threadIdx.x] ? sh[threadIdx.x + o] : sh[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+/* partial[b] = max defect seen by block b; the caller takes the max over tmb_red_grid(nl*n) entries */
+cudaError_t tmb_launch_su3_defect(const double2 *U, size_t n, int nlinks, double *partial, cudaStream_t s) {
+  RedSu3Defect f = {U, n};
+  max_kernel<<<tmb_red_grid((size_t)nlinks * n), RED_BLOCK, 0, s>>>(f, (size_t)nlinks * n, partial);
+  return cudaGetLastError();
 }
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s) { EwPackGaugeHalo f = {out, U, g}; EW_LAUNCH(f, (size_t)18 * g.S, nullptr, s); }

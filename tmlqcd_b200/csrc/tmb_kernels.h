@@ -52,6 +52,7 @@ struct tmb_hop_launch {
   int xblock;               /* >0: traverse (t,x) planes x-blocked for L2 locality */
   int pdl;                  /* launch with programmatic stream serialization (PDL) */
   int prefetch;             /* bulk-prefetch the CTA's gauge rows into L2 before the dependency wait */
+  int recon12;              /* U / Uhalo hold 12-real compressed links (6 complex per link) */
 };
 
 int tmb_hop_grid(const tmb_hop_launch &a);
@@ -98,5 +99,8 @@ cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const dou
 cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s);
 /* T-face half-spinors: send_up = (1-g0) proj of the last slice, send_dn = (1+g0) proj of the first */
 cudaError_t tmb_launch_pack_halo(int prec, void *send_up, void *send_dn, const void *in, tmb_geom g, cudaStream_t s);
+/* 12-real compression: dst[l][6][n] = rows 0,1 of src[l][9][n]; su3_defect: max |row2 - conj(row0 x row1)|^2 */
+cudaError_t tmb_launch_compress12(double2 *dst, const double2 *src, size_t n, int nlinks, cudaStream_t s);
+cudaError_t tmb_launch_su3_defect(const double2 *U, size_t n, int nlinks, double *partial, cudaStream_t s);
 /* Uhalo[q][e][j] = U[q][0][e][(T-1)S + j] : what rank+1 needs from this rank */
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s);

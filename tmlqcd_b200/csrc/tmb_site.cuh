@@ -186,43 +186,56 @@ TMB_HD void tmb_link_accumulate(V2 r[12], const V2 u[9], const V2 a[3], const V2
 
 template <class V2> struct tmb_hop_fields {
   const V2 *in;      /* k : field of the opposite parity, 12*Vh elements */
-  const V2 *U;       /* gauge, [2][4][9][Vh] */
+  const V2 *U;       /* gauge, [2][4][9][Vh]  (12-real compression: [2][4][6][Vh]) */
   const V2 *halo_up; /* dist_t: [6][S] (1+g0)-projected first slice of rank+1 */
   const V2 *halo_dn; /* dist_t: [6][S] (1-g0)-projected last slice of rank-1 */
-  const V2 *Uhalo;   /* dist_t: [2][9][S] U_0 of rank-1's last slice, by owner parity */
+  const V2 *Uhalo;   /* dist_t: [2][9|6][S] U_0 of rank-1's last slice, by owner parity */
 };
 
-template <int D, int HINTS, class V2>
+/* 12-real gauge compression (the reference's CompressionType, misc_types.h:33-37, offered to its
+ * external inverters): only the first two rows of an SU(3) link are stored and streamed, the third
+ * is conj(row0 x row1).  Exact to rounding for unitary links; refused at upload otherwise. */
+template <class V2> TMB_HD void tmb_reconstruct_row2(V2 u[9]) {
+  u[6] = c_conj(c_sub(c_mul(u[1], u[5]), c_mul(u[2], u[4])));
+  u[7] = c_conj(c_sub(c_mul(u[2], u[3]), c_mul(u[0], u[5])));
+  u[8] = c_conj(c_sub(c_mul(u[0], u[4]), c_mul(u[1], u[3])));
+}
+
+/* CFG bit 0: cache-policy loads; bit 1: 12-real links (6 stored complex numbers instead of 9) */
+template <int D, int CFG, class V2>
 TMB_HD void tmb_hop_dir(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_geom &g, int par, int i, int n, V2 ka,
                         const tmb_policies &pol) {
-  const int mu = D >> 1, BWD = D & 1;
+  const int mu = D >> 1, BWD = D & 1, HINTS = CFG & 1, NE = (CFG & 2) ? 6 : 9;
   V2 a[3], b[3], u[9];
   /* forward link lives at the output site (parity par), backward link at the neighbour (parity 1-par) */
-  const V2 *ub = f.U + (size_t)(((BWD ? 1 - par : par) * 4 + mu) * 9) * g.Vh + (BWD ? n : i);
+  const V2 *ub = f.U + (size_t)(((BWD ? 1 - par : par) * 4 + mu) * NE) * g.Vh + (BWD ? n : i);
 #pragma unroll
-  for (int e = 0; e < 9; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
+  for (int e = 0; e < NE; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
   tmb_project<D, HINTS>(a, b, f.in, g.Vh, n, pol);
+  if (NE == 6) tmb_reconstruct_row2(u);
   tmb_link_accumulate<D>(r, u, a, b, ka);
 }
 
 /* halo variants for the distributed T direction: the half-spinor arrives already projected */
-template <int D, int HINTS, class V2>
+template <int D, int CFG, class V2>
 TMB_HD void tmb_hop_dir_halo(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_geom &g, int par, int i, int j, V2 ka,
                              const tmb_policies &pol) {
+  const int HINTS = CFG & 1, NE = (CFG & 2) ? 6 : 9;
   V2 a[3], b[3], u[9];
   if (D == 0) { /* +t at t == T-1: local forward link, half-spinor from rank+1 */
-    const V2 *ub = f.U + (size_t)((par * 4 + 0) * 9) * g.Vh + i;
+    const V2 *ub = f.U + (size_t)((par * 4 + 0) * NE) * g.Vh + i;
 #pragma unroll
-    for (int e = 0; e < 9; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
+    for (int e = 0; e < NE; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
 #pragma unroll
     for (int c = 0; c < 3; c++) { a[c] = f.halo_up[(size_t)c * g.S + j]; b[c] = f.halo_up[(size_t)(3 + c) * g.S + j]; }
   } else {      /* -t at t == 0: link and half-spinor from rank-1 */
-    const V2 *ub = f.Uhalo + (size_t)((1 - par) * 9) * g.S + j;
+    const V2 *ub = f.Uhalo + (size_t)((1 - par) * NE) * g.S + j;
 #pragma unroll
-    for (int e = 0; e < 9; e++) u[e] = ub[(size_t)e * g.S];
+    for (int e = 0; e < NE; e++) u[e] = ub[(size_t)e * g.S];
 #pragma unroll
     for (int c = 0; c < 3; c++) { a[c] = f.halo_dn[(size_t)c * g.S + j]; b[c] = f.halo_dn[(size_t)(3 + c) * g.S + j]; }
   }
+  if (NE == 6) tmb_reconstruct_row2(u);
   tmb_link_accumulate<D>(r, u, a, b, ka);
 }
 
