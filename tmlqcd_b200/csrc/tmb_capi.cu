@@ -378,6 +378,7 @@ struct HopOpt {
   int *npartial = nullptr;
   int site0 = 0, nsites = -1; /* sub-range of output sites (single rank only); -1: all */
   int prec = 0;               /* 0: double fields, 1: float fields + float gauge copy */
+  int fin_op = -1, fin_slot = 0; /* fused finish of the dot reduction (single rank) */
 };
 static int ensure_gauge32();
 static int ensure_gauge12(int prec);
@@ -403,14 +404,16 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.dotw ? 1 : 0; a.hints = C.hints;
   a.pdl = C.pdl; a.prefetch = C.prefetch;
+  a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && C.nranks == 1) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
   int np = 0;
   if (!C.dist) {
     a.dist = 0; a.site0 = o.site0; a.nsites = o.nsites < 0 ? C.g.Vh : o.nsites; a.split = a.nsites; a.gap = 0;
     /* tuning variants exist for the plain Hopping_Matrix kernel only */
     a.variant = (o.mode == 0 && !a.dot && !a.recon12 && !o.prec) ? C.hop_variant : 0;
     a.xblock = o.nsites < 0 ? C.xblock : 0;
-    KL(tmb_launch_hop(a, C.s_main));
     np = tmb_hop_grid(a);
+    a.fin_total = np;
+    KL(tmb_launch_hop(a, C.s_main));
   } else {
     if (o.nsites >= 0) return fail(-12, "site sub-ranges are not supported with a distributed T direction");
     /* halo exchange on the comm stream, overlapped with the interior kernel:
@@ -433,6 +436,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
      * poorly filled launch after it (outputs are disjoint sites) */
     a.dist = 1; a.site0 = 0; a.nsites = 2 * S; a.split = S; a.gap = Vh - 2 * S;
     a.partial = C.partial + nb_int;
+    a.fin_total = ai.fin_total = nb_int + tmb_hop_grid(a);
     KL(tmb_launch_hop(a, C.s_comm));
     CU(cudaEventRecord(C.ev_halo, C.s_comm));
     if (nb_int > 0) KL(tmb_launch_hop(ai, C.s_main));
@@ -531,7 +535,8 @@ extern "C" int tmb_tm_sub_H_eo_gamma5(void *l, const void *p, const void *k, int
 
 /* Qtm_pm_psi (tm_operators.c:338-345): 4 hops, each with its diagonal fused in the epilogue.
  * dotw/st: the CG asks for <dotw, l> and the early exit. */
-static int qtm_pm(double2 *l, const double2 *k, const double2 *dotw, const tmb_cg_state *st, int *np) {
+static int qtm_pm(double2 *l, const double2 *k, const double2 *dotw, const tmb_cg_state *st, int *np,
+                  int fin_op = -1, int fin_slot = 0) {
   SCR(w0, 0); SCR(w1, 1);
   HopOpt a; a.mode = 1; a.cf = z_inv(-1.); a.st = st;
   TRY(hop(0, w1, k, a));
@@ -540,6 +545,7 @@ static int qtm_pm(double2 *l, const double2 *k, const double2 *dotw, const tmb_c
   HopOpt c; c.mode = 1; c.cf = z_inv(+1.); c.st = st;
   TRY(hop(0, w1, w0, c));
   HopOpt d; d.mode = 2; d.cf = z_fwd(+1.); d.p = w0; d.st = st; d.dotw = dotw; d.npartial = np;
+  d.fin_op = fin_op; d.fin_slot = fin_slot;
   TRY(hop(1, l, w1, d));
   return 0;
 }
@@ -668,10 +674,11 @@ extern "C" int tmb_cg_her(void *P, const void *Q, int max_iter, double eps_sq, i
     const int todo = (max_iter - enq) < CG_CHUNK ? (max_iter - enq) : CG_CHUNK;
     for (int k = 0; k < todo; k++) {
       int np = 0;
-      TRY(qtm_pm(ap, p, p, C.st, &np));                                     /* cg_her.c:92 + :93 fused */
-      TRY(reduce_to(np, 1, TMB_FIN_CG_PRO));                                /* alpha = normsq/pro */
-      KL(tmb_launch_cg_update_xr(0, x, r, p, ap, n2, C.st, C.partial, C.s_main)); /* cg_her.c:95-101 */
-      TRY(reduce_to(tmb_red_grid(n2), 2, TMB_FIN_CG_ERR));                  /* stop test, beta */
+      const bool fuse = C.nranks == 1; /* no all-reduce between the partial sums and the bookkeeping */
+      TRY(qtm_pm(ap, p, p, C.st, &np, fuse ? TMB_FIN_CG_PRO : -1, 1));      /* cg_her.c:92 + :93 fused */
+      if (!fuse) TRY(reduce_to(np, 1, TMB_FIN_CG_PRO));                     /* alpha = normsq/pro */
+      KL(tmb_launch_cg_update_xr(0, x, r, p, ap, n2, C.st, C.partial, 2, fuse ? TMB_FIN_CG_ERR : -1, C.s_main)); /* cg_her.c:95-101 */
+      if (!fuse) TRY(reduce_to(tmb_red_grid(n2), 2, TMB_FIN_CG_ERR));       /* stop test, beta */
       KL(tmb_launch_cg_update_p(0, p, r, n2, C.st, C.s_main));                 /* cg_her.c:122 */
     }
     enq += todo;

@@ -34,6 +34,62 @@ __device__ __forceinline__ double block_sum(double v) {
   return v; /* valid in thread 0 */
 }
 
+__device__ void cg_apply(tmb_cg_state *st, int slot, int op) {
+  const double sum = st->tmp[slot];
+  if (op == TMB_FIN_CG_PRO) {
+    st->pro = sum;
+    st->alpha = st->normsq / sum;
+  } else if (op == TMB_FIN_CG_ERR) {
+    st->err = sum;
+    st->iter += 1;
+    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
+    if (sum <= thr) {
+      st->converged = 1;
+    } else {
+      st->beta = sum / st->normsq;
+      st->normsq = sum;
+    }
+  } else if (op == TMB_FIN_CG_INIT) {
+    st->normsq = sum;
+  } else if (op == TMB_FIN_MCG_ERR) {
+    /* solver/mixed_cg_her.c:139-150: j counts the iterations that did NOT break */
+    st->err = sum;
+    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
+    if (sum <= st->inner_eps * st->sqnrm0 || st->iter == st->max_iter || 1.3 * sum <= thr) {
+      st->converged = 1;
+    } else {
+      st->beta = sum / st->normsq;
+      st->normsq = sum;
+      st->iter += 1;
+    }
+  }
+}
+
+/* Fused finish of a two-stage reduction: the CTA that takes the last ticket sums all block partials
+ * in index order (same order whichever CTA is last -> deterministic) and does the CG bookkeeping,
+ * which saves the separate one-CTA launch per reduction.  Used when no all-reduce sits in between. */
+template <int BLOCK>
+__device__ __forceinline__ void finish_last_block(const double *partial, int total, tmb_cg_state *st, int slot, int op) {
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __threadfence(); /* this CTA's partial is visible before the ticket is taken */
+    const unsigned t = atomicAdd(&st->ticket[slot], 1u);
+    is_last = (t == (unsigned)(total - 1));
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double acc = 0.;
+    for (int k = threadIdx.x; k < total; k += BLOCK) acc += __ldcg(partial + k);
+    const double s = block_sum<BLOCK>(acc);
+    if (threadIdx.x == 0) {
+      st->tmp[slot] = s;
+      cg_apply(st, slot, op);
+      st->ticket[slot] = 0;
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ K1: hopping */
 template <class V2, int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a) {
@@ -88,22 +144,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
     tmb_hop_site<DIST, HINTS>(r, f, a.g, a.par, i, ka, pol);
     const V2 *pp = (const V2 *)a.p, *dw_ = (const V2 *)a.dotw;
     V2 *out = (V2 *)a.out;
+    /* All epilogue operands are loaded as one batch BEFORE the first store: `out` may alias `p`
+     * (Qtm_minus_psi(l, l), invert_eo.c:270), so the compiler must not move a load across a store,
+     * and interleaving them serialises 12 DRAM round trips per thread (measured: 138 us instead of
+     * 80 us per launch at 24^3x48, profiles/r01_cg_launches_before_epilogue_fix.csv). */
+    V2 pc[12], dw[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) {
-      V2 pc = mk2<V2>(0, 0);
-      if (MODE >= 2) pc = pp[(size_t)c * a.g.Vh + i];
-      const V2 o = tmb_epilogue<MODE>(c, r[c], pc, cf);
-      if (DOT) {
-        const V2 dw = dw_[(size_t)c * a.g.Vh + i];
-        dsum += (double)dw.x * (double)o.x;
-        dsum += (double)dw.y * (double)o.y;
-      }
-      tmb_store_out<HINTS>(out + (size_t)c * a.g.Vh + i, o, pol);
+      if (MODE >= 2) pc[c] = pp[(size_t)c * a.g.Vh + i];
+      if (DOT) dw[c] = dw_[(size_t)c * a.g.Vh + i];
     }
+    V2 o[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      o[c] = tmb_epilogue<MODE>(c, r[c], MODE >= 2 ? pc[c] : mk2<V2>(0, 0), cf);
+      if (DOT) {
+        dsum += (double)dw[c].x * (double)o[c].x;
+        dsum += (double)dw[c].y * (double)o[c].y;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 12; c++) tmb_store_out<HINTS & 1>(out + (size_t)c * a.g.Vh + i, o[c], pol);
   }
   if (DOT) {
     const double s = block_sum<BLOCK>(dsum);
     if (threadIdx.x == 0) a.partial[blockIdx.x] = s;
+    if (a.fin_op >= 0) finish_last_block<BLOCK>(a.partial_base, a.fin_total, a.st_fin, a.fin_slot, a.fin_op);
   }
 }
 
@@ -244,44 +310,15 @@ template <class V2> struct RedCgXR { /* x += alpha p ; r -= alpha Ap ; |r|^2    
 };
 
 template <class F>
-__global__ void __launch_bounds__(RED_BLOCK) red_kernel(F f, size_t n2, double *partial, const tmb_cg_state *st) {
+__global__ void __launch_bounds__(RED_BLOCK) red_kernel(F f, size_t n2, double *partial, const tmb_cg_state *st,
+                                                         tmb_cg_state *st_fin, int fin_slot, int fin_op) {
   if (st != nullptr && st->converged) return;
   double acc = 0.;
   for (size_t k = (size_t)blockIdx.x * RED_BLOCK + threadIdx.x; k < n2; k += (size_t)gridDim.x * RED_BLOCK)
     acc += f(k);
   const double s = block_sum<RED_BLOCK>(acc);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-
-__device__ void cg_apply(tmb_cg_state *st, int slot, int op) {
-  const double sum = st->tmp[slot];
-  if (op == TMB_FIN_CG_PRO) {
-    st->pro = sum;
-    st->alpha = st->normsq / sum;
-  } else if (op == TMB_FIN_CG_ERR) {
-    st->err = sum;
-    st->iter += 1;
-    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
-    if (sum <= thr) {
-      st->converged = 1;
-    } else {
-      st->beta = sum / st->normsq;
-      st->normsq = sum;
-    }
-  } else if (op == TMB_FIN_CG_INIT) {
-    st->normsq = sum;
-  } else if (op == TMB_FIN_MCG_ERR) {
-    /* solver/mixed_cg_her.c:139-150: j counts the iterations that did NOT break */
-    st->err = sum;
-    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
-    if (sum <= st->inner_eps * st->sqnrm0 || st->iter == st->max_iter || 1.3 * sum <= thr) {
-      st->converged = 1;
-    } else {
-      st->beta = sum / st->normsq;
-      st->normsq = sum;
-      st->iter += 1;
-    }
-  }
+  if (fin_op >= 0) finish_last_block<RED_BLOCK>(partial, (int)gridDim.x, st_fin, fin_slot, fin_op);
 }
 
 /* one CTA: sums the block partials in a fixed order (deterministic), then the CG bookkeeping */
@@ -311,7 +348,9 @@ cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s)
   return cudaGetLastError();
 }
 #define RED_LAUNCH(f, n2, partial, st, s) \
-  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st); return cudaGetLastError(); } while (0)
+  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st, nullptr, 0, -1); return cudaGetLastError(); } while (0)
+#define RED_LAUNCH_FIN(f, n2, partial, st, stf, slot, op, s) \
+  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st, stf, slot, op); return cudaGetLastError(); } while (0)
 
 cudaError_t tmb_launch_norm2(int prec, const void *a, size_t n2, double *partial, cudaStream_t s) {
   if (prec) { RedNorm2<float2> f = {(const float2 *)a}; RED_LAUNCH(f, n2, partial, nullptr, s); }
@@ -325,9 +364,9 @@ cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t
   RedXpayNorm f = {r, sv, c}; RED_LAUNCH(f, n2, partial, nullptr, s);
 }
 cudaError_t tmb_launch_cg_update_xr(int prec, void *x, void *r, const void *p, const void *ap, size_t n2,
-                                    const tmb_cg_state *st, double *partial, cudaStream_t s) {
-  if (prec) { RedCgXR<float2> f = {(float2 *)x, (float2 *)r, (const float2 *)p, (const float2 *)ap, st}; RED_LAUNCH(f, n2, partial, st, s); }
-  RedCgXR<double2> f = {(double2 *)x, (double2 *)r, (const double2 *)p, (const double2 *)ap, st}; RED_LAUNCH(f, n2, partial, st, s);
+                                    tmb_cg_state *st, double *partial, int fin_slot, int fin_op, cudaStream_t s) {
+  if (prec) { RedCgXR<float2> f = {(float2 *)x, (float2 *)r, (const float2 *)p, (const float2 *)ap, st}; RED_LAUNCH_FIN(f, n2, partial, st, st, fin_slot, fin_op, s); }
+  RedCgXR<double2> f = {(double2 *)x, (double2 *)r, (const double2 *)p, (const double2 *)ap, st}; RED_LAUNCH_FIN(f, n2, partial, st, st, fin_slot, fin_op, s);
 }
 
 /* ------------------------------------------------------------------ K3: elementwise */

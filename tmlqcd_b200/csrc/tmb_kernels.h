@@ -23,6 +23,7 @@ struct tmb_cg_state {
   int converged;   /* set on device when the stop test fires; later kernels become no-ops */
   int iter;        /* iterations completed */
   int max_iter;    /* mixed CG inner loop: also stop after this many iterations */
+  unsigned int ticket[4]; /* last-CTA election of the fused reduction finish, one per slot */
 };
 
 enum tmb_fin_op {
@@ -53,6 +54,8 @@ struct tmb_hop_launch {
   int pdl;                  /* launch with programmatic stream serialization (PDL) */
   int prefetch;             /* bulk-prefetch the CTA's gauge rows into L2 before the dependency wait */
   int recon12;              /* U / Uhalo hold 12-real compressed links (6 complex per link) */
+  /* fused finish of the DOT reduction (fin_op >= 0): the last of fin_total CTAs sums partial_base[0..fin_total) */
+  tmb_cg_state *st_fin; const double *partial_base; int fin_op, fin_slot, fin_total;
 };
 
 int tmb_hop_grid(const tmb_hop_launch &a);
@@ -67,7 +70,7 @@ cudaError_t tmb_launch_norm2(int prec, const void *a, size_t n2, double *partial
 cudaError_t tmb_launch_dot(int prec, const void *a, const void *b, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_cg_update_xr(int prec, void *x, void *r, const void *p, const void *ap, size_t n2,
-                                    const tmb_cg_state *st, double *partial, cudaStream_t s);
+                                    tmb_cg_state *st, double *partial, int fin_slot, int fin_op, cudaStream_t s);
 cudaError_t tmb_launch_cg_update_p(int prec, void *p, const void *r, size_t n2, const tmb_cg_state *st, cudaStream_t s);
 
 /* elementwise, n2 = 12*Vh complex elements; `half` = 6*Vh separates spin 0,1 from spin 2,3 */
