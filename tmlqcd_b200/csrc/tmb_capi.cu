@@ -61,7 +61,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0;
+  int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields;
@@ -146,7 +146,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18;
+  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1;
   C.init = true;
   return 0;
 }
@@ -248,7 +248,7 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   return 0;
 }
 /* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
-extern "C" int tmb_set_overlap(int flags) { NEED_INIT(); C.pdl = flags & 1; C.prefetch = (flags >> 1) & 1; return 0; }
+extern "C" int tmb_set_overlap(int flags) { NEED_INIT(); C.pdl = flags & 1; C.prefetch = (flags >> 1) & 1; C.cg_graph = (flags & 4) ? 0 : 1; return 0; }
 
 /* ------------------------------------------------------------------ memory */
 extern "C" void *tmb_field_alloc(void) {
@@ -647,6 +647,7 @@ static int reduce_to(int npart, int slot, int op) {
   return 0;
 }
 
+static int cg_drive(int prec, void *x, void *r, void *p, void *ap, int err_op, int trips, tmb_cg_state *hout);
 extern "C" int tmb_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec) {
   NEED_INIT();
   SCR(ap, 2); SCR(r, 3); SCR(p, 4);
@@ -668,36 +669,8 @@ extern "C" int tmb_cg_her(void *P, const void *Q, int max_iter, double eps_sq, i
   KL(tmb_launch_norm2(0, r, n2, C.partial, C.s_main));
   TRY(reduce_to(tmb_red_grid(n2), 0, TMB_FIN_CG_INIT));
 
-  int enq = 0, chunk = 0, done = 0;
-  bool pending[2] = {false, false};
-  while (!done) {
-    const int todo = (max_iter - enq) < CG_CHUNK ? (max_iter - enq) : CG_CHUNK;
-    for (int k = 0; k < todo; k++) {
-      int np = 0;
-      const bool fuse = C.nranks == 1; /* no all-reduce between the partial sums and the bookkeeping */
-      TRY(qtm_pm(ap, p, p, C.st, &np, fuse ? TMB_FIN_CG_PRO : -1, 1));      /* cg_her.c:92 + :93 fused */
-      if (!fuse) TRY(reduce_to(np, 1, TMB_FIN_CG_PRO));                     /* alpha = normsq/pro */
-      KL(tmb_launch_cg_update_xr(0, x, r, p, ap, n2, C.st, C.partial, 2, fuse ? TMB_FIN_CG_ERR : -1, C.s_main)); /* cg_her.c:95-101 */
-      if (!fuse) TRY(reduce_to(tmb_red_grid(n2), 2, TMB_FIN_CG_ERR));       /* stop test, beta */
-      KL(tmb_launch_cg_update_p(0, p, r, n2, C.st, C.s_main));                 /* cg_her.c:122 */
-    }
-    enq += todo;
-    const int slot = chunk & 1;
-    CU(cudaMemcpyAsync(&C.st_host[slot], C.st, sizeof(tmb_cg_state), cudaMemcpyDeviceToHost, C.s_main));
-    CU(cudaEventRecord(C.ev_chk[slot], C.s_main));
-    pending[slot] = true;
-    /* look at the PREVIOUS chunk's state while this one runs */
-    const int prev = slot ^ 1;
-    if (pending[prev]) {
-      CU(cudaEventSynchronize(C.ev_chk[prev]));
-      pending[prev] = false;
-      if (C.st_host[prev].converged) done = 1;
-    }
-    if (enq >= max_iter) done = 1;
-    chunk++;
-  }
-  CU(cudaStreamSynchronize(C.s_main));
-  CU(cudaMemcpy(&h, C.st, sizeof(h), cudaMemcpyDeviceToHost));
+  /* main loop (cg_her.c:91-127), enqueued in chunks / as a replayed CUDA graph: see cg_drive() */
+  TRY(cg_drive(0, x, r, p, ap, TMB_FIN_CG_ERR, max_iter, &h));
   auto t1 = std::chrono::steady_clock::now();
   C.last_iters = h.iter; C.last_err = h.err;
   C.last_seconds = std::chrono::duration<double>(t1 - t0).count();
