@@ -152,6 +152,53 @@ int tmb_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int ma
 int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
                           const void *ec, const void *oc, double precision, int max_iter, int rel_prec);
 
+/* rg_mixed_cg_her (solver/rg_mixed_cg_her.c:180), the default mixed solver of solve_degenerate; delta = solver_params.mcg_delta */
+int tmb_set_mcg_delta(double delta);
+int tmb_rg_mixed_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec);
+
+/* ---- HMC side: fermion force, chronological guess, DET / DETRATIO monomials ---- */
+/* hf->derivative (hamiltonian_field.h:30): host layout [ix][mu][8] doubles = su3adj d1..d8 (su3adj.h:25-27),
+ * ix lexicographic; it lives on the device between the calls below */
+int tmb_derivative_zero(void);
+int tmb_derivative_upload(const double *host_df);
+int tmb_derivative_download(double *host_df);
+/* deriv_Sb(ieo, l, k, hf, factor): deriv_Sb.c:402; l has parity ieo, k the other; accumulates into the device
+ * derivative field; with a T split the halo exchange of xchange_2fields (deriv_Sb.c:413) is done inside */
+int tmb_deriv_Sb(int ieo, const void *l, const void *k, double factor);
+/* complex BLAS-1 used by the chronological guess: linalg/scalar_prod_body.c, assign_add_mul.c, assign_diff_mul.c:31, mul.c */
+int tmb_scalar_prod(const void *s, const void *r, double *re, double *im);
+int tmb_assign_add_mul(void *r, const void *s, double c_re, double c_im);
+int tmb_assign_diff_mul(void *r, const void *s, double c_re, double c_im);
+int tmb_mul(void *r, double c_re, double c_im, const void *s);
+/* solver/solver_types.h:23-49: the solver ids on the scoped path */
+#define TMB_SOLVER_CG 1
+#define TMB_SOLVER_MIXEDCG 13
+#define TMB_SOLVER_RGMIXEDCG 14
+/* matrix_mult selector for device-level callers (the reference passes a function pointer) */
+enum { TMB_OP_QTM_PM = 0, TMB_OP_QTM_PLUS = 1, TMB_OP_QTM_MINUS = 2 };
+/* chrono_add_solution / chrono_guess: solver/chrono_guess.c:43, :82; v = array of N device fields */
+int tmb_chrono_add_solution(const void *trial, void *const *v, int *index_array, int N, int *n);
+int tmb_chrono_guess(void *trial, const void *phi, void *const *v, const int *index_array, int N, int n, int op);
+/* solve_degenerate(P, Q, params, max_iter, eps_sq, rel_prec, VOLUME/2, &Qtm_pm_psi, solver): solver/monomial_solve.c:86;
+ * solver_type as solver/solver_types.h:23-49: CG = 1, MIXEDCG = 13, RGMIXEDCG = 14 */
+int tmb_solve_degenerate(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec, int solver_type);
+/* monomials: type DET = 0, DETRATIO = 1 (monomial.h:27-28); parameters as the BeginMonomial block sets them */
+enum { TMB_MNL_DET = 0, TMB_MNL_DETRATIO = 1 };
+int tmb_monomial_add(int type, double kappa, double mu, double kappa2, double mu2, int solver, int maxiter,
+                     double forceprec, double accprec, int csg_N); /* returns the monomial id */
+int tmb_monomial_clear(void);
+int tmb_set_relative_precision_flag(int flag);                      /* g_relative_precision_flag */
+/* det_heatbath / detratio_heatbath (det_monomial.c:150, detratio_monomial.c:199); `gauss` = device field holding what
+ * random_spinor_field_eo(w_fields[0], rngrepro, RN_GAUSS) drew (the RNG stays with the caller) */
+int tmb_monomial_heatbath(int id, const void *gauss, double *energy0);
+/* det_derivative / detratio_derivative (det_monomial.c:47, detratio_monomial.c:49): adds to the device derivative field */
+int tmb_monomial_derivative(int id);
+/* det_acc / detratio_acc (det_monomial.c:202, detratio_monomial.c:266): *dH = energy1 - energy0 */
+int tmb_monomial_acc(int id, double *dH);
+int tmb_monomial_info(int id, double *energy0, double *energy1, int *iter0, int *iter1, int *csg_n);
+void *tmb_monomial_pf(int id);     /* the pseudo-fermion field (device) */
+void *tmb_monomial_wfield(int k);  /* w_fields[k], k < 6 (device) */
+
 /* number of kernels this library launched since tmb_init (bench.py's gpu_launches) */
 long long tmb_launch_count(void);
 

@@ -55,9 +55,7 @@ typedef struct {
   SloppyPrecision sloppy_precision;
   ExternalInverter external_inverter;
 } solver_params_t;
-/* solver/solver_types.h:23-49 (only CG is on the scoped path) */
-#define TMB_SOLVER_CG 1
-#define TMB_SOLVER_MIXEDCG 13
+/* solver/solver_types.h:23-49: TMB_SOLVER_CG / _MIXEDCG / _RGMIXEDCG come from tmlqcd_b200.h */
 #define EO 0 /* global.h / operator headers: ieo = 0 -> output on even sites */
 #define OE 1
 

@@ -69,6 +69,16 @@ class Oracle:
             "orc_Qtm_pm_ndpsi": (None, [_dp] * 4),
             "orc_cg_her_nd": (i, [_dp] * 4 + [i, d, i]),
             "orc_invert_doublet_eo_cg": (i, [_dp] * 8 + [d, i, i]),
+            "orc_deriv_Sb": (None, [i, _dp, _dp, _dp, d]),
+            "orc_set_relative_precision_flag": (None, [i]),
+            "orc_mnl_add": (i, [i, d, d, d, d, i, i, d, d, i]),
+            "orc_mnl_clear": (None, []),
+            "orc_mnl_heatbath": (d, [i, _dp]),
+            "orc_mnl_derivative": (None, [i, _dp]),
+            "orc_mnl_acc": (d, [i]),
+            "orc_mnl_get_pf": (None, [i, _dp]),
+            "orc_mnl_set_pf": (None, [i, _dp]),
+            "orc_mnl_info": (None, [i, C.POINTER(d), C.POINTER(d), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -90,6 +100,15 @@ class Oracle:
 
     def set_params(self, kappa, gmu, theta=(0., 0., 0., 0.)):
         self.lib.orc_set_params(kappa, gmu, *[float(t) for t in theta])
+
+    def derivative(self):
+        """hf->derivative as [V][4][8] doubles"""
+        return np.zeros((self.V, 4, 8), dtype=np.float64)
+
+    def mnl_info(self, id):
+        e0, e1, i0, i1, n = C.c_double(), C.c_double(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.orc_mnl_info(id, C.byref(e0), C.byref(e1), C.byref(i0), C.byref(i1), C.byref(n))
+        return {"energy0": e0.value, "energy1": e1.value, "iter0": i0.value, "iter1": i1.value, "csg_n": n.value}
 
     def eo2lexic(self):
         out = np.zeros(self.V, dtype=np.int32)

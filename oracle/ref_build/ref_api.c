@@ -333,3 +333,75 @@ int ref_mixed_cg_her(double *p, double *q, int max_iter, double eps_sq, int rel_
   memset(&sp, 0, sizeof(sp));
   return mixed_cg_her((spinor *)p, (spinor *)q, sp, max_iter, eps_sq, rel_prec, VOLUME / 2, &Qtm_pm_psi, &Qtm_pm_psi_32);
 }
+
+/* ---- HMC pieces: deriv_Sb, chronological guess, solve_degenerate and the
+ *      DET / DETRATIO monomials, all the unmodified reference (deriv_Sb.c, solver/chrono_guess.c,
+ *      solver/monomial_solve.c, monomial/{monomial,det_monomial,detratio_monomial}.c) ---- */
+#include "hamiltonian_field.h"
+#include "deriv_Sb.h"
+#include "init/init_moment_field.h"
+#include "monomial/monomial.h"
+#include "solver/chrono_guess.h"
+#include "solver/monomial_solve.h"
+
+extern int even_odd_flag; /* read_input.h, defined in ref_shim.c */
+static hamiltonian_field_t ref_hf;
+static int ref_hmc_up = 0;
+int ref_hmc_init(void) {
+  if (ref_hmc_up) return 0;
+  if (init_moment_field(VOLUME, VOLUMEPLUSRAND) != 0) return -1;
+  ref_hf.gaugefield = g_gauge_field; ref_hf.momenta = moment; ref_hf.derivative = df0;
+  ref_hf.update_gauge_copy = g_update_gauge_copy; ref_hf.traj_counter = 0;
+  g_relative_precision_flag = 0;
+  ref_hmc_up = 1;
+  return 0;
+}
+void ref_set_relative_precision_flag(int f) { g_relative_precision_flag = f; }
+/* df: [VOLUME][4][8] doubles = hf->derivative (su3adj.h:25-27), accumulated in place */
+void ref_deriv_Sb(int ieo, double *l, double *k, double *df, double factor) {
+  memcpy(df0[0], df, (size_t)VOLUME * 4 * sizeof(su3adj));
+  deriv_Sb(ieo, (spinor *)l, (spinor *)k, &ref_hf, factor);
+  memcpy(df, df0[0], (size_t)VOLUME * 4 * sizeof(su3adj));
+}
+/* what read_input.l does for a BeginMonomial DET / DETRATIO block, then init_monomials (hmc_tm.c:300) */
+int ref_mnl_add(int type, double kappa, double mu, double kappa2, double mu2, int solver, int maxiter,
+                double forceprec, double accprec, int csg_N) {
+  int id = add_monomial(type) - 1;
+  monomial *m = &monomial_list[id];
+  m->type = type; /* read_input.l sets it after add_monomial() */
+  m->kappa = kappa; m->mu = mu; m->kappa2 = kappa2; m->mu2 = mu2; m->solver = solver; m->maxiter = maxiter;
+  m->forceprec = forceprec; m->accprec = accprec; m->csg_N = csg_N; m->csg_N2 = 0; m->even_odd_flag = 1;
+  m->solver_params.mcg_delta = (float)mixcg_innereps;
+  return id;
+}
+int ref_mnl_init(void) {
+  if (init_monomials(VOLUMEPLUSRAND / 2, even_odd_flag) != 0) return -1;
+  if (init_csg_field(VOLUMEPLUSRAND / 2) != 0) return -2;
+  return 0;
+}
+void ref_mnl_heatbath(int id) { monomial_list[id].hbfunction(id, &ref_hf); }
+double ref_mnl_acc(int id) { return monomial_list[id].accfunction(id, &ref_hf); }
+void ref_mnl_derivative(int id, double *df) {
+  memcpy(df0[0], df, (size_t)VOLUME * 4 * sizeof(su3adj));
+  monomial_list[id].derivativefunction(id, &ref_hf);
+  memcpy(df, df0[0], (size_t)VOLUME * 4 * sizeof(su3adj));
+}
+void ref_mnl_get_pf(int id, double *out) { memcpy(out, monomial_list[id].pf, (size_t)(VOLUME / 2) * sizeof(spinor)); }
+void ref_mnl_set_pf(int id, const double *in) { memcpy(monomial_list[id].pf, in, (size_t)(VOLUME / 2) * sizeof(spinor)); }
+void ref_mnl_info(int id, double *energy0, double *energy1, int *iter0, int *iter1, int *csg_n) {
+  monomial *m = &monomial_list[id];
+  *energy0 = m->energy0; *energy1 = m->energy1; *iter0 = m->iter0; *iter1 = m->iter1; *csg_n = m->csg_n;
+}
+/* direct access to the chronological guess for unit parity: history of `n` fields, newest last */
+int ref_solve_degenerate(double *p, double *q, int max_iter, double eps_sq, int rel_prec, int solver) {
+  solver_params_t sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.mcg_delta = (float)mixcg_innereps;
+  return solve_degenerate((spinor *)p, (spinor *)q, sp, max_iter, eps_sq, rel_prec, VOLUME / 2, &Qtm_pm_psi, solver);
+}
+/* timing of one derivative call of monomial id (bench.py hmc leg) */
+double ref_bench_mnl_derivative(int id, int nreps) {
+  double t1 = gettime();
+  for (int j = 0; j < nreps; j++) monomial_list[id].derivativefunction(id, &ref_hf);
+  return gettime() - t1;
+}

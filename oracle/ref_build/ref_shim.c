@@ -13,7 +13,6 @@ int even_odd_flag = 1;
 int bc_flag = 0;
 int usegpu_flag = 0;
 int use_preconditioning = 0;
-int no_monomials = 0;
 #ifndef TM_USE_OMP
 int omp_num_threads = 1;
 #endif
@@ -39,5 +38,23 @@ OFF_PATH(init_blocks_gaugefield)
 OFF_PATH(init_blocks_gaugefield_32)
 OFF_PATH(spinorPrecondition)
 double g_prec_sequence_d_dagger_d[3] = {0., 0., 0.};
-/* monomial_list is only touched by init_csg_field (init/init_spinor_field.c:183), never called here */
-char monomial_list[1 << 20];
+/* monomial/monomial.c (compiled unmodified for add_monomial / init_monomials /
+ * mnl_backup_restore_globals and the DET / DETRATIO wiring) references every other monomial type
+ * and solver/monomial_solve.c every other solver; none of them is on the scoped path. */
+OFF_PATH(Qsw_full_minus_psi) OFF_PATH(Qsw_full_plus_psi) OFF_PATH(Qsw_full_pm_psi)
+OFF_PATH(Qsw_minus_psi) OFF_PATH(Qsw_plus_psi) OFF_PATH(Qsw_pm_psi) OFF_PATH(Qsw_pm_psi_32)
+OFF_PATH(copy_32_sw_fields) OFF_PATH(init_swpm)
+OFF_PATH(clover_trlog_acc) OFF_PATH(clover_trlog_heatbath)
+OFF_PATH(cloverdet_acc) OFF_PATH(cloverdet_derivative) OFF_PATH(cloverdet_heatbath)
+OFF_PATH(cloverdetratio_acc) OFF_PATH(cloverdetratio_derivative) OFF_PATH(cloverdetratio_heatbath)
+OFF_PATH(cloverdetratio_rwacc) OFF_PATH(clovernd_trlog_acc) OFF_PATH(clovernd_trlog_heatbath)
+OFF_PATH(cloverndpoly_acc) OFF_PATH(cloverndpoly_derivative) OFF_PATH(cloverndpoly_heatbath)
+OFF_PATH(gauge_EMderivative) OFF_PATH(gauge_acc) OFF_PATH(gauge_derivative) OFF_PATH(gauge_heatbath)
+OFF_PATH(init_ndpoly_monomial) OFF_PATH(init_ndrat_monomial) OFF_PATH(nddetratio_acc)
+OFF_PATH(ndpoly_acc) OFF_PATH(ndpoly_derivative) OFF_PATH(ndpoly_heatbath)
+OFF_PATH(ndrat_acc) OFF_PATH(ndrat_derivative) OFF_PATH(ndrat_heatbath)
+OFF_PATH(ndratcor_acc) OFF_PATH(ndratcor_heatbath)
+OFF_PATH(poly_acc) OFF_PATH(poly_derivative) OFF_PATH(poly_heatbath)
+OFF_PATH(rat_acc) OFF_PATH(rat_derivative) OFF_PATH(rat_heatbath) OFF_PATH(ratcor_acc) OFF_PATH(ratcor_heatbath)
+OFF_PATH(bicgstab_complex) OFF_PATH(cg_mms_tm) OFF_PATH(cg_mms_tm_nd) OFF_PATH(mixed_cg_mms_tm_nd)
+OFF_PATH(sw_term) OFF_PATH(sw_invert) OFF_PATH(sw_deriv) OFF_PATH(sw_all)

@@ -95,6 +95,14 @@ class Reference:
             "ref_init32": (i, []), "ref_update_gauge32": (None, []), "ref_set_mixcg": (None, [d, i]),
             "ref_Hopping_Matrix_32": (None, [i, _fp, _fp]), "ref_Qtm_pm_psi_32": (None, [_fp, _fp]),
             "ref_mixed_cg_her": (i, [_dp, _dp, i, d, i]),
+            "ref_hmc_init": (i, []), "ref_set_relative_precision_flag": (None, [i]),
+            "ref_deriv_Sb": (None, [i, _dp, _dp, _dp, d]),
+            "ref_mnl_add": (i, [i, d, d, d, d, i, i, d, d, i]), "ref_mnl_init": (i, []),
+            "ref_mnl_heatbath": (None, [i]), "ref_mnl_acc": (d, [i]), "ref_mnl_derivative": (None, [i, _dp]),
+            "ref_mnl_get_pf": (None, [i, _dp]), "ref_mnl_set_pf": (None, [i, _dp]),
+            "ref_mnl_info": (None, [i, C.POINTER(d), C.POINTER(d), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+            "ref_solve_degenerate": (i, [_dp, _dp, i, d, i, i]),
+            "ref_bench_mnl_derivative": (d, [i, i]),
             "ref_bench_hopping": (d, [i]),
             "ref_bench_D_psi": (d, [i]),
             "ref_bench_Qtm_pm": (d, [i]),
@@ -136,6 +144,15 @@ class Reference:
 
     def set_params(self, kappa, gmu, theta=(0., 0., 0., 0.)):
         self.lib.ref_set_params(kappa, gmu, *[float(t) for t in theta])
+
+    def derivative(self):
+        """hf->derivative as [V][4][8] doubles"""
+        return np.zeros((self.V, 4, 8), dtype=np.float64)
+
+    def mnl_info(self, id):
+        e0, e1, i0, i1, n = C.c_double(), C.c_double(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.ref_mnl_info(id, C.byref(e0), C.byref(e1), C.byref(i0), C.byref(i1), C.byref(n))
+        return {"energy0": e0.value, "energy1": e1.value, "iter0": i0.value, "iter1": i1.value, "csg_n": n.value}
 
     def table(self, name):
         n = {"eo2lexic": 1, "lexic2eosub": 1, "hi": 16, "iup": 4, "idn": 4}[name]

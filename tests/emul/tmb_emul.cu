@@ -8,6 +8,7 @@
  * product library and is not a CPU fallback: tmlqcd_b200/csrc never references it.
  */
 #include "../../tmlqcd_b200/csrc/tmb_kernels.cu"
+#include "../../tmlqcd_b200/csrc/tmb_force.cu"
 
 template <int MODE, int DIST>
 static void hop_host(double2 *out, const tmb_hop_fields<double2> &f, const double2 *p, const tmb_geom &g, int par,
@@ -171,5 +172,46 @@ void emul_nd_moo_sub_g5(double *ls, double *lc, const double *ks, const double *
   EwNdMooSubG5 f = {(double2 *)ls, (double2 *)lc, (const double2 *)ks, (const double2 *)kc,
                     (const double2 *)js, (const double2 *)jc, mu, eps, (size_t)6 * Vh};
   for (size_t i = 0; i < (size_t)12 * Vh; i++) f(i);
+}
+/* fermion force: the gather over link owners exactly as deriv_kernel composes it (interior slices with
+ * DIST = 0, last slice with DIST = 1 reading the (1+g0)-projected halo of the upper neighbour) */
+void emul_pack_deriv(double *dev, const double *lex, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  for (size_t x = 0; x < (size_t)64 * g.Vh; x++) {
+    const int i = (int)(x % g.Vh), row = (int)(x / g.Vh), a = row & 7, mu = (row >> 3) & 3, q = row >> 5;
+    dev[x] = lex[((size_t)tmb_eo_to_lexic(g, q, i) * 4 + mu) * 8 + a];
+  }
+}
+void emul_unpack_deriv(double *lex, const double *dev, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  for (size_t x = 0; x < (size_t)64 * g.Vh; x++) {
+    const int i = (int)(x % g.Vh), row = (int)(x / g.Vh), a = row & 7, mu = (row >> 3) & 3, q = row >> 5;
+    lex[((size_t)tmb_eo_to_lexic(g, q, i) * 4 + mu) * 8 + a] = dev[x];
+  }
+}
+void emul_pack_deriv_halo(double *out, const double *k, const double *l, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 1);
+  const double2 *K = (const double2 *)k, *L = (const double2 *)l; double2 *o = (double2 *)out;
+  for (size_t x = 0; x < (size_t)12 * g.S; x++) {
+    const int which = (int)(x / ((size_t)6 * g.S)); const size_t y = x - (size_t)which * 6 * g.S;
+    const int c = (int)(y / g.S), j = (int)(y - (size_t)c * g.S);
+    const double2 *f = which ? L : K;
+    o[x] = c_add(f[(size_t)c * g.Vh + j], f[(size_t)(c + 6) * g.Vh + j]);
+  }
+}
+void emul_deriv(int ieo, const double *l, const double *k, const double *U, double *df, const double *halo, int T, int LX,
+                int LY, int LZ, const double *ka8, double factor, int dist) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, dist);
+  tmb_deriv_fields f;
+  f.l = (const double2 *)l; f.k = (const double2 *)k; f.U = (const double2 *)U; f.df = df;
+  f.halo_k = (const double2 *)halo; f.halo_l = (const double2 *)halo + (size_t)6 * g.S;
+  double2 ka[4];
+  for (int m = 0; m < 4; m++) ka[m] = make_double2(ka8[2 * m], ka8[2 * m + 1]);
+  for (int q = 0; q < 2; q++)
+    for (int i = 0; i < g.Vh; i++) {
+      const bool last = dist && i >= (g.T - 1) * g.S;
+      if (q == ieo) { if (last) tmb_deriv_site<1, 1>(f, g, q, i, ka, 2. * factor); else tmb_deriv_site<1, 0>(f, g, q, i, ka, 2. * factor); }
+      else          { if (last) tmb_deriv_site<0, 1>(f, g, q, i, ka, 2. * factor); else tmb_deriv_site<0, 0>(f, g, q, i, ka, 2. * factor); }
+    }
 }
 } /* extern "C" */

@@ -17,7 +17,7 @@ i, d = C.c_int, C.c_double
 def load():
     src = os.path.join(HERE, "emul", "tmb_emul.cu")
     csrc = os.path.join(os.path.dirname(HERE), "tmlqcd_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("tmb_kernels.cu", "tmb_site.cuh", "tmb_geom.h", "tmb_kernels.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("tmb_kernels.cu", "tmb_force.cu", "tmb_site.cuh", "tmb_geom.h", "tmb_kernels.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(p) > os.path.getmtime(LIB) for p in deps):
         r = subprocess.run(["bash", os.path.join(HERE, "emul", "build.sh")], capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
@@ -32,6 +32,9 @@ def load():
         "emul_hop12": [i, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, i], "emul_compress12": [dp, dp, C.c_long, i],
         "emul_hop_f": [i, fp, fp, fp, i, i, i, i, dp],
         "emul_diag": [dp, dp, d, d, i], "emul_diag_sub": [dp, dp, dp, d, d, i, i], "emul_gamma5": [dp, dp, i],
+        "emul_pack_deriv": [dp, dp, i, i, i, i], "emul_unpack_deriv": [dp, dp, i, i, i, i],
+        "emul_pack_deriv_halo": [dp, dp, dp, i, i, i, i],
+        "emul_deriv": [i, dp, dp, dp, dp, dp, i, i, i, i, dp, d, i],
         "emul_nd_mee_inv": [dp, dp, dp, dp, d, d, i], "emul_nd_moo_sub_g5": [dp, dp, dp, dp, dp, dp, d, d, i],
     }
     for n, a in sig.items():
@@ -65,6 +68,18 @@ class Emul:
 
     def pack_gauge_halo(self, U):
         out = np.zeros(36 * self.S); self.E.emul_pack_gauge_halo(out, U, *self.dims); return out
+
+    def deriv(self, ieo, soa_l, soa_k, U, ka, df_lex, factor, halo=None):
+        """deriv_Sb on device-layout fields; df_lex in the reference's [V][4][8] layout, returned likewise"""
+        dev = np.zeros(64 * self.Vh); self.E.emul_pack_deriv(dev, np.ascontiguousarray(df_lex).reshape(-1), *self.dims)
+        h = halo if halo is not None else np.zeros(2)
+        self.E.emul_deriv(ieo, soa_l, soa_k, U, dev, h, *self.dims, np.asarray(ka, dtype=np.float64), factor,
+                          0 if halo is None else 1)
+        out = np.zeros(32 * self.V); self.E.emul_unpack_deriv(out, dev, *self.dims)
+        return out.reshape(self.V, 4, 8)
+
+    def pack_deriv_halo(self, soa_k, soa_l):
+        out = np.zeros(24 * self.S); self.E.emul_pack_deriv_halo(out, soa_k, soa_l, *self.dims); return out
 
     def hop(self, par, soa_in, U, ka, mode=0, cf=(1., 0.), soa_p=None, halo=None):
         out = np.zeros(24 * self.Vh)

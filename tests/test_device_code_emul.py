@@ -138,3 +138,34 @@ def test_compressed_links_and_single_precision_instantiations(oracle_lib):
         outf = np.zeros(24 * e.Vh, dtype=np.float32)
         assert e.E.emul_hop_f(par, outf, sk.astype(np.float32), U.astype(np.float32), *dims, ka) == 0
         assert rel_l2(e.unpack(outf.astype(np.float64)), exp) < 1e-6
+
+
+@pytest.mark.parametrize("dims,theta", [((4, 4, 4, 4), (0., 0., 0., 0.)), ((4, 6, 4, 8), (1., 0.3, 0., 0.7)), ((2, 4, 2, 6), (1., 0., 0., 0.))])
+def test_fermion_force_gather_and_halo_loopback(oracle_lib, dims, theta):
+    """deriv_Sb as the device computes it (gather over link owners, tmb_deriv_site) vs the oracle's scatter
+    restatement of deriv_Sb.c:402-649, with and without the T-halo path (loopback)"""
+    rng = np.random.default_rng(21)
+    e, o = Emul(*dims), oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, theta)
+    ka = ka_of(KAPPA, theta, dims)
+    U = e.pack_gauge(g)
+    l, k = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+    sl, sk = e.pack(l), e.pack(k)
+    df0 = rng.normal(size=(o.V, 4, 8))
+    for ieo in (0, 1):
+        exp = df0.copy(); o.deriv_Sb(ieo, l, k, exp, 0.7)
+        assert rel_l2(e.deriv(ieo, sl, sk, U, ka, df0, 0.7) - df0, exp - df0) < 1e-14
+        halo = e.pack_deriv_halo(sk, sl)  # loopback: this rank is its own upper neighbour
+        assert rel_l2(e.deriv(ieo, sl, sk, U, ka, df0, 0.7, halo=halo) - df0, exp - df0) < 1e-14
+
+
+def test_golden_fermion_force_through_device_code():
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_hmc_4x4x4x4.npz"))
+    dims = tuple(int(x) for x in gold["dims"])
+    e = Emul(*dims)
+    ka = ka_of(float(gold["kappa"]), gold["theta"], dims)
+    U, sl, sk = e.pack_gauge(gold["gauge"]), e.pack(gold["l"]), e.pack(gold["k"])
+    for ieo in (0, 1):
+        got = e.deriv(ieo, sl, sk, U, ka, np.zeros((e.V, 4, 8)), 0.7)
+        assert rel_l2(got, gold[f"deriv_Sb{ieo}"]) < 1e-14

@@ -70,6 +70,21 @@ DEVICE_API = {
     "tmb_Hopping_Matrix_32": (_i, [_i, _vp, _vp]), "tmb_Qtm_pm_psi_32": (_i, [_vp, _vp]),
     "tmb_set_mixcg": (_i, [_d, _i]), "tmb_mixed_cg_her": (_i, [_vp, _vp, _i, _d, _i]),
     "tmb_invert_eo_mixed": (_i, [_vp] * 4 + [_d, _i, _i]),
+    "tmb_set_mcg_delta": (_i, [_d]), "tmb_rg_mixed_cg_her": (_i, [_vp, _vp, _i, _d, _i]),
+    "tmb_derivative_zero": (_i, []), "tmb_derivative_upload": (_i, [_vp]), "tmb_derivative_download": (_i, [_vp]),
+    "tmb_deriv_Sb": (_i, [_i, _vp, _vp, _d]),
+    "tmb_scalar_prod": (_i, [_vp, _vp, C.POINTER(_d), C.POINTER(_d)]),
+    "tmb_assign_add_mul": (_i, [_vp, _vp, _d, _d]), "tmb_assign_diff_mul": (_i, [_vp, _vp, _d, _d]),
+    "tmb_mul": (_i, [_vp, _d, _d, _vp]),
+    "tmb_chrono_add_solution": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i), _i, C.POINTER(_i)]),
+    "tmb_chrono_guess": (_i, [_vp, _vp, C.POINTER(_vp), C.POINTER(_i), _i, _i, _i]),
+    "tmb_solve_degenerate": (_i, [_vp, _vp, _i, _d, _i, _i]),
+    "tmb_monomial_add": (_i, [_i, _d, _d, _d, _d, _i, _i, _d, _d, _i]), "tmb_monomial_clear": (_i, []),
+    "tmb_set_relative_precision_flag": (_i, [_i]),
+    "tmb_monomial_heatbath": (_i, [_i, _vp, C.POINTER(_d)]), "tmb_monomial_derivative": (_i, [_i]),
+    "tmb_monomial_acc": (_i, [_i, C.POINTER(_d)]),
+    "tmb_monomial_info": (_i, [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "tmb_monomial_pf": (_vp, [_i]), "tmb_monomial_wfield": (_vp, [_i]),
     "tmb_launch_count": (C.c_longlong, []),
 }
 
@@ -129,7 +144,8 @@ DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND"
                   "X0", "X1", "X2", "X3", "ka0", "ka1", "ka2", "ka3", "phase_0", "phase_1", "phase_2", "phase_3",
                   "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit"]
 
-_SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed"}
+_SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed",
+            "rg_mixed_cg_her", "solve_degenerate"}
 _lib = None
 
 
@@ -259,6 +275,22 @@ class Device:
         ms = C.c_float(0.)
         self.ck(self.lib.tmb_timer_stop(C.byref(ms)))
         return ms.value
+
+    # ---- HMC side ----
+    def derivative_upload(self, df):
+        df = np.ascontiguousarray(df, dtype=np.float64)
+        assert df.size == self.V * 32
+        self.ck(self.lib.tmb_derivative_upload(df.ctypes.data_as(_vp)))
+
+    def derivative_download(self):
+        out = np.zeros((self.V, 4, 8), dtype=np.float64)
+        self.ck(self.lib.tmb_derivative_download(out.ctypes.data_as(_vp)))
+        return out
+
+    def monomial_info(self, id):
+        e0, e1, i0, i1, n = _d(0.), _d(0.), _i(0), _i(0), _i(0)
+        self.ck(self.lib.tmb_monomial_info(id, C.byref(e0), C.byref(e1), C.byref(i0), C.byref(i1), C.byref(n)))
+        return {"energy0": e0.value, "energy1": e1.value, "iter0": i0.value, "iter1": i1.value, "csg_n": n.value}
 
     def solver_stats(self):
         it, err, sec = _i(0), _d(0.), _d(0.)

@@ -37,6 +37,18 @@ struct NcclApi {
 
 #define NSCRATCH 14
 #define MAXCHUNK 64
+#define TMB_MAXCSG 20 /* chrono_guess.c:91: max_N = 20 */
+#define TMB_MAXMNL 30 /* monomial.h:51: max_no_monomials */
+
+/* one DET / DETRATIO monomial (the fields of the reference's `monomial` struct this path uses, monomial.h:53-131) */
+struct Monomial {
+  int type = 0, solver = 1, maxiter = 5000, csg_N = 0, csg_n = 0, iter0 = 0, iter1 = 0;
+  double kappa = 0., mu = 0., kappa2 = 0., mu2 = 0., forceprec = 1e-7, accprec = 1e-16, forcefactor = 1.;
+  double energy0 = 0., energy1 = 0.;
+  double2 *pf = nullptr;
+  double2 *csg[TMB_MAXCSG] = {nullptr};
+  int idx[TMB_MAXCSG] = {0};
+};
 
 struct Ctx {
   bool init = false;
@@ -49,7 +61,7 @@ struct Ctx {
   cudaEvent_t ev_in = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
   double2 *U = nullptr, *Uhalo = nullptr;
   double2 *send_up = nullptr, *send_dn = nullptr, *halo_up = nullptr, *halo_dn = nullptr;
-  double2 *stage = nullptr; /* AoS staging, 24*Vh double2 (one lexicographic field) */
+  double2 *stage = nullptr; /* AoS staging, 32*Vh double2 (one lexicographic spinor field or one derivative field) */
   double *partial = nullptr; int npartial = 0;
   tmb_cg_state *st = nullptr;      /* device */
   tmb_cg_state *st_host = nullptr; /* pinned, 2 slots */
@@ -67,10 +79,20 @@ struct Ctx {
   std::vector<void *> fields;
   long long launches = 0;
   int last_iters = 0; double last_err = 0., last_seconds = 0.;
+  int last_inner_sp = 0, last_inner_dp = 0, last_outer = 0;
   bool gauge_loaded = false;
+  /* HMC side (tmb_capi_hmc.inc) */
+  double2 phase[4] = {{1., 0.}, {1., 0.}, {1., 0.}, {1., 0.}}; /* exp(i theta_mu pi / L_mu): ka_mu / kappa */
+  double *df = nullptr;                       /* hf->derivative on the device, [2][4][8][Vh] */
+  double2 *dhalo_send = nullptr, *dhalo_recv = nullptr;
+  Monomial mnl[TMB_MAXMNL]; int nmnl = 0;
+  double2 *w[6] = {nullptr};                  /* w_fields (monomial.c:57) */
+  int rel_prec_flag = 0;                      /* g_relative_precision_flag */
+  double mcg_delta = 5.0e-5;                  /* solver_params.mcg_delta = _default_mixcg_innereps (monomial.c:106) */
 };
 static Ctx C;
 static int ensure_gauge12(int prec);
+extern "C" int tmb_rg_mixed_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec);
 static std::string g_err;
 
 static int fail(int code, const char *fmt, ...) {
@@ -133,7 +155,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   CU(cudaEventCreate(&C.ev_t0));
   CU(cudaEventCreate(&C.ev_t1));
   CU(cudaMalloc(&C.U, (size_t)72 * C.g.Vh * sizeof(double2)));
-  CU(cudaMalloc(&C.stage, (size_t)24 * C.g.Vh * sizeof(double2)));
+  CU(cudaMalloc(&C.stage, (size_t)32 * C.g.Vh * sizeof(double2))); /* one lexicographic spinor field (24 Vh) or one derivative field (32 Vh) */
   C.npartial = C.g.Vh / 64 + 4096;
   CU(cudaMalloc(&C.partial, (size_t)C.npartial * sizeof(double)));
   CU(cudaMalloc(&C.st, sizeof(tmb_cg_state)));
@@ -161,6 +183,9 @@ extern "C" int tmb_finalize(void) {
   for (int i = 0; i < NSCRATCH; i++) { if (C.scratch32[i]) cudaFree(C.scratch32[i]); C.scratch32[i] = nullptr; }
   if (C.U32) cudaFree(C.U32); if (C.Uhalo32) cudaFree(C.Uhalo32);
   if (C.U12) cudaFree(C.U12); if (C.Uhalo12) cudaFree(C.Uhalo12); if (C.U12f) cudaFree(C.U12f); if (C.Uhalo12f) cudaFree(C.Uhalo12f);
+  if (C.df) cudaFree(C.df); if (C.dhalo_send) cudaFree(C.dhalo_send); if (C.dhalo_recv) cudaFree(C.dhalo_recv);
+  for (int k = 0; k < C.nmnl; k++) { if (C.mnl[k].pf) cudaFree(C.mnl[k].pf); for (int i = 0; i < TMB_MAXCSG; i++) if (C.mnl[k].csg[i]) cudaFree(C.mnl[k].csg[i]); }
+  for (int i = 0; i < 6; i++) if (C.w[i]) cudaFree(C.w[i]);
   cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
@@ -226,6 +251,7 @@ extern "C" int tmb_set_boundary(double kappa, const double theta[4]) {
   for (int m = 0; m < 4; m++) {
     const double x = (theta ? theta[m] : 0.) * PI_ / ext[m];
     C.ka[m] = make_double2(kappa * cos(x), kappa * sin(x));
+    C.phase[m] = make_double2(cos(x), sin(x));
   }
   return 0;
 }
@@ -234,6 +260,10 @@ extern "C" int tmb_set_hopping_phases(const double ka_re_im[8]) {
   NEED_INIT();
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(ka_re_im[2 * m], ka_re_im[2 * m + 1]);
   C.kappa = sqrt(C.ka[0].x * C.ka[0].x + C.ka[0].y * C.ka[0].y);
+  for (int m = 0; m < 4; m++) {
+    const double a = sqrt(C.ka[m].x * C.ka[m].x + C.ka[m].y * C.ka[m].y);
+    C.phase[m] = a > 0. ? make_double2(C.ka[m].x / a, C.ka[m].y / a) : make_double2(1., 0.);
+  }
   return 0;
 }
 extern "C" int tmb_set_mu(double g_mu) { NEED_INIT(); C.mu = g_mu; return 0; }
@@ -858,3 +888,4 @@ extern "C" int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc,
 }
 
 #include "tmb_capi_mixed.inc"
+#include "tmb_capi_hmc.inc"

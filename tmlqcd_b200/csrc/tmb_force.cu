@@ -1,0 +1,78 @@
+/* tmb_force.cu - fermion force kernel (sm_100a): deriv_Sb(ieo, l, k, hf, factor), deriv_Sb.c:402-649.
+ *
+ * The reference scatters into hf->derivative with omp atomics (su3adj.h:140-156); here every link
+ * owner site gathers its one contribution per call (see tmb_site.cuh), so there are no atomics and
+ * the result is deterministic.  One thread per (parity, site): 12 local + 4 x 12 remote spinor
+ * components, 4 x 9 link elements, 4 x 8 derivative components read-modify-written, all loads
+ * contiguous across the warp.  Bandwidth-bound like the hopping kernel (1.25 flop/B): algorithmic
+ * bytes per link-owner site 192 (spinor, perfect reuse) + 4*144 (links) + 2*4*64 (df r/w) = 1280.
+ */
+#include "tmb_kernels.h"
+#include "tmb_site.cuh"
+
+template <int DIST>
+__global__ void __launch_bounds__(128, 3) deriv_kernel(const tmb_deriv_launch a) {
+  const int q = blockIdx.y;                       /* parity of the link owner */
+  const int w = blockIdx.x * 128 + threadIdx.x;
+  if (w >= a.nt * a.g.S) return;
+  const int i = a.t0 * a.g.S + w;
+  tmb_deriv_fields f;
+  f.l = (const double2 *)a.l; f.k = (const double2 *)a.k; f.U = (const double2 *)a.U; f.df = a.df;
+  f.halo_k = (const double2 *)a.halo_k; f.halo_l = (const double2 *)a.halo_l;
+  if (q == a.ieo) tmb_deriv_site<1, DIST>(f, a.g, q, i, a.ka, a.c); /* block-uniform branch */
+  else            tmb_deriv_site<0, DIST>(f, a.g, q, i, a.ka, a.c);
+}
+
+cudaError_t tmb_launch_deriv(const tmb_deriv_launch &a, cudaStream_t s) {
+  const int n = a.nt * a.g.S;
+  if (n <= 0) return cudaSuccess;
+  dim3 grid((n + 127) / 128, 2);
+  if (a.dist) deriv_kernel<1><<<grid, 128, 0, s>>>(a);
+  else deriv_kernel<0><<<grid, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) pack_deriv_halo_kernel(double2 *out, const double2 *k, const double2 *l, tmb_geom g) {
+  const size_t n = (size_t)12 * g.S;
+  for (size_t x = (size_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (size_t)gridDim.x * 256) {
+    const int which = (int)(x / ((size_t)6 * g.S)); const size_t y = x - (size_t)which * 6 * g.S;
+    const int c = (int)(y / g.S), j = (int)(y - (size_t)c * g.S);
+    const double2 *f = which ? l : k;
+    out[x] = c_add(f[(size_t)c * g.Vh + j], f[(size_t)(c + 6) * g.Vh + j]);
+  }
+}
+cudaError_t tmb_launch_pack_deriv_halo(double2 *out, const double2 *k, const double2 *l, tmb_geom g, cudaStream_t s) {
+  const size_t n = (size_t)12 * g.S;
+  pack_deriv_halo_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(out, k, l, g);
+  return cudaGetLastError();
+}
+
+/* host [ix][mu][8] <-> device [q][mu][8][Vh] */
+__global__ void __launch_bounds__(256) pack_deriv_kernel(double *dev, const double *lex, tmb_geom g) {
+  const size_t n = (size_t)64 * g.Vh;
+  for (size_t x = (size_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (size_t)gridDim.x * 256) {
+    const int i = (int)(x % g.Vh); const int row = (int)(x / g.Vh);
+    const int a = row & 7, mu = (row >> 3) & 3, q = row >> 5;
+    const int ix = tmb_eo_to_lexic(g, q, i);
+    dev[x] = lex[((size_t)ix * 4 + mu) * 8 + a];
+  }
+}
+__global__ void __launch_bounds__(256) unpack_deriv_kernel(double *lex, const double *dev, tmb_geom g, int add) {
+  const size_t n = (size_t)64 * g.Vh;
+  for (size_t x = (size_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (size_t)gridDim.x * 256) {
+    const int i = (int)(x % g.Vh); const int row = (int)(x / g.Vh);
+    const int a = row & 7, mu = (row >> 3) & 3, q = row >> 5;
+    const int ix = tmb_eo_to_lexic(g, q, i);
+    double *o = lex + ((size_t)ix * 4 + mu) * 8 + a;
+    *o = add ? *o + dev[x] : dev[x];
+  }
+}
+static int lin_grid(size_t n) { size_t need = (n + 255) / 256, cap = 148 * 16; return (int)(need < cap ? (need ? need : 1) : cap); }
+cudaError_t tmb_launch_pack_deriv(double *dev, const double *lex, tmb_geom g, cudaStream_t s) {
+  pack_deriv_kernel<<<lin_grid((size_t)64 * g.Vh), 256, 0, s>>>(dev, lex, g);
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_unpack_deriv(double *lex, const double *dev, tmb_geom g, int add, cudaStream_t s) {
+  unpack_deriv_kernel<<<lin_grid((size_t)64 * g.Vh), 256, 0, s>>>(lex, dev, g, add);
+  return cudaGetLastError();
+}

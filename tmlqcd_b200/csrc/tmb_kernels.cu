@@ -38,7 +38,7 @@ __device__ void cg_apply(tmb_cg_state *st, int slot, int op) {
   const double sum = st->tmp[slot];
   if (op == TMB_FIN_CG_PRO) {
     st->pro = sum;
-    st->alpha = st->normsq / sum;
+    st->alpha = st->fprec ? (double)((float)st->normsq / (float)sum) : st->normsq / sum;
   } else if (op == TMB_FIN_CG_ERR) {
     st->err = sum;
     st->iter += 1;
@@ -61,6 +61,22 @@ __device__ void cg_apply(tmb_cg_state *st, int slot, int op) {
       st->beta = sum / st->normsq;
       st->normsq = sum;
       st->iter += 1;
+    }
+  } else if (op == TMB_FIN_RG_ERR) {
+    /* rg_mixed_cg_her.c:118-145 (float) / :75-104 (double): ++j; ...; rho = |r|^2; beta = rho / *rho1; *rho1 = rho;
+     * if (1.3 rho < eps_sq) break; if (rho > rhomax) rhomax = rho; while (rho > delta*rhomax && j+iter <= max_iter) */
+    const double rho = st->fprec ? (double)(float)sum : sum;
+    st->err = rho;
+    st->iter += 1;
+    st->beta = st->fprec ? (double)((float)rho / (float)st->normsq) : rho / st->normsq;
+    st->normsq = rho;
+    const double eps = st->fprec ? (double)(float)st->eps_sq : st->eps_sq;
+    if (1.3 * rho < eps) {
+      st->converged = 1;
+    } else {
+      if (rho > st->sqnrm0) st->sqnrm0 = rho;
+      const double lim = st->fprec ? (double)((float)st->inner_eps * (float)st->sqnrm0) : st->inner_eps * st->sqnrm0;
+      if (!(rho > lim && st->iter <= st->max_iter)) st->converged = 1;
     }
   }
 }
@@ -446,6 +462,33 @@ cudaError_t tmb_launch_nd_moo_sub_g5(double2 *ls, double2 *lc, const double2 *ks
   EwNdMooSubG5 f = {ls, lc, ks, kc, js, jc, mu, eps, half}; EW_LAUNCH(f, n2, nullptr, s); }
 cudaError_t tmb_launch_to_float(float2 *dst, const double2 *src, size_t n, cudaStream_t s) { EwToFloat f = {dst, src}; EW_LAUNCH(f, n, nullptr, s); }
 cudaError_t tmb_launch_add_from_float(double2 *dst, const float2 *src, size_t n, cudaStream_t s) { EwAddFromFloat f = {dst, src}; EW_LAUNCH(f, n, nullptr, s); }
+
+/* complex BLAS-1 of the chronological guess (solver/chrono_guess.c): linalg/assign_diff_mul.c:31,
+ * linalg/mul.c, linalg/assign_add_mul.c */
+struct EwCAxpy { double2 *r; const double2 *sv; double2 c; /* R += c S */
+  __host__ __device__ void operator()(size_t k) const { double2 v = r[k]; c_mad(v, c, sv[k]); r[k] = v; } };
+struct EwCScale { double2 *r; const double2 *sv; double2 c; /* R = c S */
+  __host__ __device__ void operator()(size_t k) const { r[k] = c_mul(c, sv[k]); } };
+cudaError_t tmb_launch_caxpy(double2 *r, double2 c, const double2 *sv, size_t n2, cudaStream_t s) { EwCAxpy f = {r, sv, c}; EW_LAUNCH(f, n2, nullptr, s); }
+cudaError_t tmb_launch_cscale(double2 *r, double2 c, const double2 *sv, size_t n2, cudaStream_t s) { EwCScale f = {r, sv, c}; EW_LAUNCH(f, n2, nullptr, s); }
+
+/* <S,R> = sum conj(S) R (linalg/scalar_prod_body.c): real parts to partial[b], imaginary to partial[grid + b] */
+__global__ void __launch_bounds__(RED_BLOCK) cdot_kernel(const double2 *a, const double2 *b, size_t n2, double *partial) {
+  double re = 0., im = 0.;
+  for (size_t k = (size_t)blockIdx.x * RED_BLOCK + threadIdx.x; k < n2; k += (size_t)gridDim.x * RED_BLOCK) {
+    const double2 v = a[k], w = b[k];
+    re += v.x * w.x + v.y * w.y;
+    im += v.x * w.y - v.y * w.x;
+  }
+  const double sr = block_sum<RED_BLOCK>(re);
+  __syncthreads();
+  const double si = block_sum<RED_BLOCK>(im);
+  if (threadIdx.x == 0) { partial[blockIdx.x] = sr; partial[gridDim.x + blockIdx.x] = si; }
+}
+cudaError_t tmb_launch_cdot(const double2 *a, const double2 *b, size_t n2, double *partial, cudaStream_t s) {
+  cdot_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(a, b, n2, partial);
+  return cudaGetLastError();
+}
 
 /* ------------------------------------------------------------------ layout conversion */
 /* host AoS spinor (su3.h:60-63: 12 complex per site, site-major)  <->  device SoA [12][Vh] */

@@ -24,6 +24,7 @@ struct tmb_cg_state {
   int iter;        /* iterations completed */
   int max_iter;    /* mixed CG inner loop: also stop after this many iterations */
   unsigned int ticket[4]; /* last-CTA election of the fused reduction finish, one per slot */
+  int fprec;       /* 1: scalars rounded to float like the reference's float inner loops (rg_mixed_cg_her.c:107-111) */
 };
 
 enum tmb_fin_op {
@@ -31,7 +32,8 @@ enum tmb_fin_op {
   TMB_FIN_CG_PRO = 1,   /* pro = sum; alpha = normsq/pro              cg_her.c:93-94 */
   TMB_FIN_CG_ERR = 2,   /* err = sum; iter++; stop test; beta; normsq cg_her.c:101-126 */
   TMB_FIN_CG_INIT = 3,  /* normsq = sum                               cg_her.c:88 */
-  TMB_FIN_MCG_ERR = 4   /* inner loop of mixed_cg_her.c:139-150: its four-way stop test */
+  TMB_FIN_MCG_ERR = 4,  /* inner loop of mixed_cg_her.c:139-150: its four-way stop test */
+  TMB_FIN_RG_ERR = 5    /* inner loops of rg_mixed_cg_her.c:75-104 / :107-145: inner_eps = delta, sqnrm0 = rhomax */
 };
 
 struct tmb_hop_launch {
@@ -88,6 +90,10 @@ cudaError_t tmb_launch_nd_mee_inv(double2 *ls, double2 *lc, const double2 *ks, c
 cudaError_t tmb_launch_nd_moo_sub_g5(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc,
                                      const double2 *js, const double2 *jc, double mu, double eps, size_t n2,
                                      size_t half, cudaStream_t s);
+/* complex BLAS-1 (chronological guess): R += c S, R = c S, <S,R> -> partial[0..grid) re, partial[grid..2grid) im */
+cudaError_t tmb_launch_caxpy(double2 *r, double2 c, const double2 *sv, size_t n2, cudaStream_t s);
+cudaError_t tmb_launch_cscale(double2 *r, double2 c, const double2 *sv, size_t n2, cudaStream_t s);
+cudaError_t tmb_launch_cdot(const double2 *a, const double2 *b, size_t n2, double *partial, cudaStream_t s);
 /* precision conversion (linalg/assign_to_32.c, addto_32.c): n complex elements */
 cudaError_t tmb_launch_to_float(float2 *dst, const double2 *src, size_t n, cudaStream_t s);
 cudaError_t tmb_launch_add_from_float(double2 *dst, const float2 *src, size_t n, cudaStream_t s); /* dst += src */
@@ -107,3 +113,20 @@ cudaError_t tmb_launch_compress12(double2 *dst, const double2 *src, size_t n, in
 cudaError_t tmb_launch_su3_defect(const double2 *U, size_t n, int nlinks, double *partial, cudaStream_t s);
 /* Uhalo[q][e][j] = U[q][0][e][(T-1)S + j] : what rank+1 needs from this rank */
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s);
+
+/* ---- fermion force (tmb_force.cu): deriv_Sb.c:402-649 as a gather over link owners ---- */
+struct tmb_deriv_launch {
+  const void *l, *k, *U; double *df;
+  const void *halo_k, *halo_l;
+  tmb_geom g;
+  int ieo;                 /* parity of l (the field that gets the gamma5) */
+  int dist;                /* 1: +t remote of slice T-1 from the halo buffers */
+  int t0, nt;              /* time-slices [t0, t0+nt) of both parities */
+  double2 ka[4]; double c; /* c = 2*factor */
+};
+cudaError_t tmb_launch_deriv(const tmb_deriv_launch &a, cudaStream_t s);
+/* first time-slice of k and of l, (1+g0)-projected: out[0][6][S] from k, out[1][6][S] from l */
+cudaError_t tmb_launch_pack_deriv_halo(double2 *out, const double2 *k, const double2 *l, tmb_geom g, cudaStream_t s);
+/* hf->derivative host layout [ix][mu][8] (init/init_moment_field.c:62-80) <-> device [2][4][8][Vh]; mode 0: set, 1: add */
+cudaError_t tmb_launch_pack_deriv(double *dev, const double *lex, tmb_geom g, cudaStream_t s);
+cudaError_t tmb_launch_unpack_deriv(double *lex, const double *dev, tmb_geom g, int add, cudaStream_t s);

@@ -275,3 +275,129 @@ TMB_HD V2 tmb_epilogue(int c, V2 r, V2 p, V2 cf) {
   if (MODE == 2) return (c < 6) ? c_sub(zp, r) : c_sub(r, zp);
   return c_sub(zp, r);
 }
+
+/* ====================================================================================
+ * Fermion force: deriv_Sb(ieo, l, k, hf, factor), deriv_Sb.c:402-649 (generic C branch).
+ *
+ * The reference loops over the sites x of parity ieo and SCATTERS two terms per direction:
+ *   forward   hf->derivative[x][mu]    += 2 factor tr_lambda( ka_mu U_mu(x)    v^+ ),  v = phi(x) psi(x+mu)^+
+ *   backward  hf->derivative[x-mu][mu] += 2 factor tr_lambda( ka_mu U_mu(x-mu) v^+ ),  v = psi(x-mu) phi(x)^+
+ * with phi = P_d(g5 l), psi = P_d(k), P_d the hopping projector of direction d (deriv_Sb.c:470-640).
+ * Every link (z, mu) of the lattice receives exactly ONE of the two terms per call: the forward one
+ * if z has parity ieo, the backward one (seen from x = z+mu) otherwise.  So the device version is a
+ * GATHER over link owners z of either parity, with no atomics:
+ *   v = P_d(local(z)) P_d(remote(z+mu))^+,   d = 2mu (forward type) or 2mu+1 (backward type),
+ *   forward type : local = g5 l(z), remote = k(z+mu);   backward type: local = k(z), remote = g5 l(z+mu)
+ *   df[z][mu] += 2 factor tr_lambda( ka_mu U_mu(z) v^+ )      (su3.h:605-614, :706-715; su3adj.h:164-172)
+ * Momentum-derivative field on the device: df[((q*4 + mu)*8 + a)*Vh + i], same (q, mu, i) indexing
+ * as the gauge field, a = 0..7 the su3adj components d1..d8 (su3adj.h:25-27).
+ * ==================================================================================== */
+template <int D, class V2>
+TMB_HD void tmb_project_regs(V2 a[3], V2 b[3], const V2 s[12]) {
+  typedef hop_tab<D> Tb;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    a[c] = c_comb<Tb::CA>(s[c], s[3 * Tb::PA + c]);
+    b[c] = c_comb<Tb::CB>(s[3 + c], s[3 * Tb::PB + c]);
+  }
+}
+
+/* r_a += c * Re tr( w lambda_a )-style projection, exactly _trace_lambda_mul_add_assign (su3adj.h:164-172) */
+TMB_HD void tmb_trace_lambda_add(double r[8], double c, const double2 w[9]) {
+  r[0] += c * (-w[3].y - w[1].y);
+  r[1] += c * (+w[3].x - w[1].x);
+  r[2] += c * (-w[0].y + w[4].y);
+  r[3] += c * (-w[6].y - w[2].y);
+  r[4] += c * (+w[6].x - w[2].x);
+  r[5] += c * (-w[7].y - w[5].y);
+  r[6] += c * (+w[7].x - w[5].x);
+  r[7] += c * ((-w[0].y - w[4].y + 2.0 * w[8].y) * 0.577350269189625);
+}
+
+/* one link: la/lb = projected local half-spinor, ra/rb = projected remote half-spinor */
+TMB_HD void tmb_deriv_link(double r[8], const double2 la[3], const double2 lb[3], const double2 ra[3],
+                           const double2 rb[3], const double2 u[9], double2 ka, double c) {
+  double2 v[9], w[9];
+  /* _vector_tensor_vector_add: v_ij = la_i conj(ra_j) + lb_i conj(rb_j) */
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double2 t = make_double2(0., 0.);
+      c_madc(t, ra[j], la[i]);
+      c_madc(t, rb[j], lb[i]);
+      v[3 * i + j] = t;
+    }
+  /* _su3_times_su3d: w_ij = sum_k u_ik conj(v_jk);  then _complex_times_su3 with ka */
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double2 t = make_double2(0., 0.);
+#pragma unroll
+      for (int k = 0; k < 3; k++) c_madc(t, v[3 * j + k], u[3 * i + k]);
+      w[3 * i + j] = c_mul(ka, t);
+    }
+  tmb_trace_lambda_add(r, c, w);
+}
+
+struct tmb_deriv_fields {
+  const double2 *l, *k;   /* l: field of parity ieo (gets the g5), k: field of parity 1-ieo */
+  const double2 *U;       /* [2][4][9][Vh] */
+  double *df;             /* [2][4][8][Vh] */
+  const double2 *halo_k;  /* dist_t: [6][S] (1+g0)-projected first slice of rank+1's k */
+  const double2 *halo_l;  /* dist_t: [6][S] (1+g0)-projected first slice of rank+1's l (= P_1(g5 l)) */
+};
+
+template <int MU, int FWD, int DIST>
+TMB_HD void tmb_deriv_dir(const tmb_deriv_fields &f, const tmb_geom &g, int q, int i, int n, int t,
+                          const double2 loc[12], double2 ka, double c) {
+  const int D = 2 * MU + (FWD ? 0 : 1);
+  double2 la[3], lb[3], ra[3], rb[3], u[9];
+  tmb_project_regs<D>(la, lb, loc);
+  if (DIST && MU == 0 && t == g.T - 1) {
+    const double2 *h = FWD ? f.halo_k : f.halo_l;
+    const int j = i - t * g.S;
+#pragma unroll
+    for (int cidx = 0; cidx < 3; cidx++) { ra[cidx] = h[(size_t)cidx * g.S + j]; rb[cidx] = h[(size_t)(3 + cidx) * g.S + j]; }
+  } else {
+    const double2 *rf = FWD ? f.k : f.l;
+    double2 rem[12];
+#pragma unroll
+    for (int cidx = 0; cidx < 12; cidx++) {
+      double2 s = rf[(size_t)cidx * g.Vh + n];
+      if (!FWD && cidx >= 6) s = make_double2(-s.x, -s.y); /* g5 on the l-derived spinor */
+      rem[cidx] = s;
+    }
+    tmb_project_regs<D>(ra, rb, rem);
+  }
+  const double2 *ub = f.U + (size_t)((q * 4 + MU) * 9) * g.Vh + i;
+#pragma unroll
+  for (int e = 0; e < 9; e++) u[e] = ub[(size_t)e * g.Vh];
+  double *d = f.df + (size_t)((q * 4 + MU) * 8) * g.Vh + i;
+  double r[8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) r[a] = d[(size_t)a * g.Vh];
+  tmb_deriv_link(r, la, lb, ra, rb, u, ka, c);
+#pragma unroll
+  for (int a = 0; a < 8; a++) d[(size_t)a * g.Vh] = r[a];
+}
+
+/* all four links owned by site i of parity q; FWD = (q == ieo) */
+template <int FWD, int DIST>
+TMB_HD void tmb_deriv_site(const tmb_deriv_fields &f, const tmb_geom &g, int q, int i, const double2 ka[4], double c) {
+  int nb[8];
+  const int t = tmb_neighbours(g, q, i, nb);
+  const double2 *lf = FWD ? f.l : f.k;
+  double2 loc[12];
+#pragma unroll
+  for (int cidx = 0; cidx < 12; cidx++) {
+    double2 s = lf[(size_t)cidx * g.Vh + i];
+    if (FWD && cidx >= 6) s = make_double2(-s.x, -s.y);
+    loc[cidx] = s;
+  }
+  tmb_deriv_dir<0, FWD, DIST>(f, g, q, i, nb[0], t, loc, ka[0], c);
+  tmb_deriv_dir<1, FWD, DIST>(f, g, q, i, nb[2], t, loc, ka[1], c);
+  tmb_deriv_dir<2, FWD, DIST>(f, g, q, i, nb[4], t, loc, ka[2], c);
+  tmb_deriv_dir<3, FWD, DIST>(f, g, q, i, nb[6], t, loc, ka[3], c);
+}
