@@ -104,6 +104,10 @@ int tmb_assign_mul_one_pm_imu(void *l, const void *k, double sign);
 int tmb_mul_one_pm_imu_sub_mul_gamma5(void *l, const void *k, const void *j, double sign);
 int tmb_mul_one_pm_imu_sub_mul(void *l, const void *k, const void *j, double sign);
 int tmb_gamma5(void *l, const void *k);
+/* the generic forms behind the family above (Mee_psi / Mee_inv_psi take mu as an argument, tm_operators.c:587, :723;
+ * mul_one_sub_mul_gamma5, :781): l = (z on s0,s1 | conj z on s2,s3) k  and  l = [g5]((z | conj z) k - j) */
+int tmb_diag(void *l, const void *k, double z_re, double z_im);
+int tmb_diag_sub(void *l, const void *k, const void *j, double z_re, double z_im, int g5);
 
 /* ---- BLAS-1 (linalg/): results of reductions are global sums over ranks ---- */
 int tmb_square_norm(const void *p, double *result);                       /* square_norm.c:253 */
@@ -145,6 +149,8 @@ int tmb_invert_eo_mixed(void *even_new, void *odd_new, const void *even, const v
 /* ---- non-degenerate doublet: operator/tm_operators_nd.c:68,:130,:195,:639; cg_her_nd.c:57;
  *      invert_doublet_eo.c:68 ---- */
 int tmb_M_ee_inv_ndpsi(void *ls, void *lc, const void *ks, const void *kc, double mu, double eps);
+int tmb_M_oo_sub_g5_ndpsi(void *ls, void *lc, const void *ks, const void *kc, const void *js, const void *jc,
+                          double mu, double eps); /* tm_operators_nd.c:698 */
 int tmb_Qtm_ndpsi(void *ls, void *lc, const void *ks, const void *kc);
 int tmb_Qtm_dagger_ndpsi(void *ls, void *lc, const void *ks, const void *kc);
 int tmb_Qtm_pm_ndpsi(void *ls, void *lc, const void *ks, const void *kc);

@@ -145,6 +145,80 @@ int invert_doublet_eo(spinor *const Even_new_s, spinor *const Odd_new_s, spinor 
                       solver_params_t solver_params, const ExternalInverter external_inverter,
                       const SloppyPrecision sloppy, const CompressionType compression);
 
+/* ---- remaining members of the operator families ---- */
+/* operator/tm_operators.c:587,:723 (mass as an argument), :813, :781, :145 */
+void Mee_inv_psi(spinor *const l, spinor *const k, const double mu);
+void Mee_psi(spinor *const l, spinor *const k, const double mu);
+void mul_one_pm_imu_sub_mul(spinor *const l, spinor *const k, spinor *const j, const double sign, const int N);
+void mul_one_sub_mul_gamma5(spinor *const l, spinor *const k, spinor *const j);
+void M_minus_1_timesC(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd);
+/* operator/tm_operators.c:186,:223,:259,:296,:312,:347 and the _nocom forms :179,:194,:252,:267,:304,:366 */
+void Qtm_plus_sym_psi(spinor *const l, spinor *const k);
+void Qtm_minus_sym_psi(spinor *const l, spinor *const k);
+void Mtm_plus_sym_psi(spinor *const l, spinor *const k);
+void Mtm_minus_sym_psi(spinor *const l, spinor *const k);
+void Mtm_plus_sym_dagg_psi(spinor *const l, spinor *const k);
+void Qtm_pm_sym_psi(spinor *const l, spinor *const k);
+void Qtm_plus_sym_psi_nocom(spinor *const l, spinor *const k);
+void Mtm_plus_sym_psi_nocom(spinor *const l, spinor *const k);
+void Mtm_minus_sym_psi_nocom(spinor *const l, spinor *const k);
+void Qtm_plus_psi_nocom(spinor *const l, spinor *const k);
+void Mtm_plus_psi_nocom(spinor *const l, spinor *const k);
+void Qtm_pm_psi_nocom(spinor *const l, spinor *const k);
+/* operator/tm_operators.c:471, :390 */
+void M_minus_psi(spinor *const l, spinor *const k);
+void D_dagg_psi(spinor *const l, spinor *const k);
+/* start.c:354; linalg/assign_to_32.c:37,:84; linalg/addto_32.c:16; solver/solver_field.c:31,:67 */
+void zero_spinor_field(spinor *const k, const int N);
+void assign_to_32(spinor32 *const R, spinor *const S, const int N);
+void assign_to_64(spinor *const R, spinor32 *const S, const int N);
+void addto_32(spinor *const Q, const spinor32 *const R, const int N);
+int init_solver_field(spinor ***const solver_field, const int V, const int nr);
+void finalize_solver(spinor **solver_field, const int nr);
+/* operator/tm_operators_nd.c:508, :698, :599 */
+void H_eo_tm_ndpsi(spinor *const l_strange, spinor *const l_charm, spinor *const k_strange, spinor *const k_charm, const int ieo);
+void M_oo_sub_g5_ndpsi(spinor *const l_s, spinor *const l_c, spinor *const k_s, spinor *const k_c, spinor *const j_s,
+                       spinor *const j_c, const double mu, const double eps);
+void mul_one_pm_iconst(spinor *const l, spinor *const k, const double mu_, const int sign_);
+/* solver/rg_mixed_cg_her.c:180 */
+int rg_mixed_cg_her(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
+                    const int rel_prec, const int N, matrix_mult f, matrix_mult32 f32);
+
+/* ---- HMC side: su3adj.h:25-27, hamiltonian_field.h:28-34 ---- */
+typedef struct { double d1, d2, d3, d4, d5, d6, d7, d8; } su3adj;
+typedef struct {
+  su3 **gaugefield;
+  su3adj **momenta;
+  su3adj **derivative;
+  int update_gauge_copy;
+  int traj_counter;
+} hamiltonian_field_t;
+extern int g_relative_precision_flag;
+/* deriv_Sb.c:402 */
+void deriv_Sb(const int ieo, spinor *const l, spinor *const k, hamiltonian_field_t *const hf, const double factor);
+/* solver/chrono_guess.c:43, :82 */
+void chrono_add_solution(spinor *const trial, spinor **const v, int index_array[], const int N, int *_n, const int V);
+int chrono_guess(spinor *const trial, spinor *const phi, spinor **const v, int index_array[], const int N, const int n,
+                 const int V, matrix_mult f);
+/* solver/monomial_solve.c:86 */
+int solve_degenerate(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
+                     const int rel_prec, const int N, matrix_mult f, int solver_type);
+/* monomial/det_monomial.c:47,:150,:202 and monomial/detratio_monomial.c:49,:199,:266 with the signatures of the
+ * function pointers in `monomial` (monomial.h:125-127).  Parameters come from a one-time registration (the
+ * reference side copies them out of monomial_list[id]); the heatbath noise comes from the caller's
+ * random_spinor_field_eo (start.c:284), registered as a callback so that the RNG stream stays the reference's */
+typedef void (*tmb_random_spinor_fn)(spinor *const k, const int repro, const int rn_type);
+int tmb_dropin_register_monomial(int id, int type, double kappa, double mu, double kappa2, double mu2, int solver,
+                                 int maxiter, double forceprec, double accprec, int csg_N);
+void tmb_dropin_set_random_spinor_field_eo(tmb_random_spinor_fn fn);
+int tmb_dropin_monomial_info(int id, double *energy0, double *energy1, int *iter0, int *iter1);
+void det_heatbath(const int id, hamiltonian_field_t *const hf);
+double det_acc(const int id, hamiltonian_field_t *const hf);
+void det_derivative(const int id, hamiltonian_field_t *const hf);
+void detratio_heatbath(const int id, hamiltonian_field_t *const hf);
+double detratio_acc(const int id, hamiltonian_field_t *const hf);
+void detratio_derivative(const int id, hamiltonian_field_t *const hf);
+
 /* ---- include/tmLQCD.h:37-59, wrapper/lib_wrapper.c:77-370 ---- */
 typedef struct { unsigned int LX, LY, LZ, T, nstore, nsave, no_operators; } tmLQCD_lat_params;
 typedef struct {

@@ -405,3 +405,34 @@ double ref_bench_mnl_derivative(int id, int nreps) {
   for (int j = 0; j < nreps; j++) monomial_list[id].derivativefunction(id, &ref_hf);
   return gettime() - t1;
 }
+
+/* ---- remaining members of the operator families ---- */
+#define REF_UNARY(name) void ref_##name(double *l, double *k) { name((spinor *)l, (spinor *)k); }
+REF_UNARY(Qtm_plus_sym_psi) REF_UNARY(Qtm_minus_sym_psi) REF_UNARY(Mtm_plus_sym_psi) REF_UNARY(Mtm_minus_sym_psi)
+REF_UNARY(Mtm_plus_sym_dagg_psi) REF_UNARY(Qtm_pm_sym_psi) REF_UNARY(M_minus_psi) REF_UNARY(D_dagg_psi)
+REF_UNARY(Q_plus_psi) REF_UNARY(Q_minus_psi)
+void ref_Mee_psi(double *l, double *k, double mu) { Mee_psi((spinor *)l, (spinor *)k, mu); }
+void ref_Mee_inv_psi(double *l, double *k, double mu) { Mee_inv_psi((spinor *)l, (spinor *)k, mu); }
+void ref_mul_one_sub_mul_gamma5(double *l, double *k, double *j) { mul_one_sub_mul_gamma5((spinor *)l, (spinor *)k, (spinor *)j); }
+void ref_mul_one_pm_imu_sub_mul(double *l, double *k, double *j, double sign, int n) {
+  mul_one_pm_imu_sub_mul((spinor *)l, (spinor *)k, (spinor *)j, sign, n);
+}
+void ref_M_minus_1_timesC(double *en, double *on, double *e, double *o) {
+  M_minus_1_timesC((spinor *)en, (spinor *)on, (spinor *)e, (spinor *)o);
+}
+void ref_H_eo_tm_ndpsi(double *ls, double *lc, double *ks, double *kc, int ieo) {
+  H_eo_tm_ndpsi((spinor *)ls, (spinor *)lc, (spinor *)ks, (spinor *)kc, ieo);
+}
+void M_oo_sub_g5_ndpsi(spinor *const, spinor *const, spinor *const, spinor *const, spinor *const, spinor *const, const double, const double);
+void mul_one_pm_iconst(spinor *const, spinor *const, const double, const int);
+void ref_M_oo_sub_g5_ndpsi(double *ls, double *lc, double *ks, double *kc, double *js, double *jc, double mu, double eps) {
+  M_oo_sub_g5_ndpsi((spinor *)ls, (spinor *)lc, (spinor *)ks, (spinor *)kc, (spinor *)js, (spinor *)jc, mu, eps);
+}
+void ref_mul_one_pm_iconst(double *l, double *k, double mu, int sign) { mul_one_pm_iconst((spinor *)l, (spinor *)k, mu, sign); }
+#include "solver/rg_mixed_cg_her.h"
+int ref_rg_mixed_cg_her(double *p, double *q, int max_iter, double eps_sq, int rel_prec, double delta) {
+  solver_params_t sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.mcg_delta = (float)delta;
+  return rg_mixed_cg_her((spinor *)p, (spinor *)q, sp, max_iter, eps_sq, rel_prec, VOLUME / 2, &Qtm_pm_psi, &Qtm_pm_psi_32);
+}

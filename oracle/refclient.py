@@ -103,6 +103,13 @@ class Reference:
             "ref_mnl_info": (None, [i, C.POINTER(d), C.POINTER(d), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
             "ref_solve_degenerate": (i, [_dp, _dp, i, d, i, i]),
             "ref_bench_mnl_derivative": (d, [i, i]),
+            **{"ref_" + n: (None, [_dp, _dp]) for n in ("Qtm_plus_sym_psi", "Qtm_minus_sym_psi", "Mtm_plus_sym_psi",
+               "Mtm_minus_sym_psi", "Mtm_plus_sym_dagg_psi", "Qtm_pm_sym_psi", "M_minus_psi", "D_dagg_psi", "Q_plus_psi", "Q_minus_psi")},
+            "ref_Mee_psi": (None, [_dp, _dp, d]), "ref_Mee_inv_psi": (None, [_dp, _dp, d]),
+            "ref_mul_one_sub_mul_gamma5": (None, [_dp] * 3), "ref_mul_one_pm_imu_sub_mul": (None, [_dp] * 3 + [d, i]),
+            "ref_M_minus_1_timesC": (None, [_dp] * 4), "ref_H_eo_tm_ndpsi": (None, [_dp] * 4 + [i]),
+            "ref_M_oo_sub_g5_ndpsi": (None, [_dp] * 6 + [d, d]), "ref_mul_one_pm_iconst": (None, [_dp, _dp, d, i]),
+            "ref_rg_mixed_cg_her": (i, [_dp, _dp, i, d, i, d]),
             "ref_bench_hopping": (d, [i]),
             "ref_bench_D_psi": (d, [i]),
             "ref_bench_Qtm_pm": (d, [i]),

@@ -1,0 +1,152 @@
+"""GPU parity of the remaining reference-named entry points (SURVEY 8a rows a13, a15, a16, a18, a25, a27, a29,
+a31 and the HMC symbols of 8f) through the drop-in layer with host buffers, against results of the UNMODIFIED
+reference (tests/golden/ref_ops_4x4x4x4.npz, ref_hmc_4x4x4x4.npz; generators committed beside them)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-13
+CG, MIXEDCG, RGMIXEDCG = 1, 13, 14
+
+
+def _gold(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name))
+
+
+@pytest.fixture()
+def dropin():
+    import tmlqcd_b200 as tm
+    base = _gold("ref_4x4x4x4.npz")
+    D = tm.DropIn(*[int(x) for x in base["dims"]])
+    D.set_params(float(base["kappa"]), float(base["gmu"]), base["theta"])
+    D.set_nd_params(*base["nd"])
+    D.set_gauge(base["gauge"])
+    yield D, base
+    D.close()
+
+
+def test_operator_family_members_vs_reference(dropin):
+    D, base = dropin
+    ops = _gold("ref_ops_4x4x4x4.npz")
+    k, p, q, w, lex = (np.array(base[n]) for n in ("k", "p", "q", "w", "lex"))
+    out = D.spinor()
+    for name in ("Qtm_plus_sym_psi", "Qtm_minus_sym_psi", "Mtm_plus_sym_psi", "Mtm_minus_sym_psi", "Mtm_plus_sym_dagg_psi",
+                 "Qtm_pm_sym_psi"):
+        getattr(D, name)(out, k); assert rel_l2(out, ops[name]) <= TOL, name
+    for name, ref in (("Qtm_plus_sym_psi_nocom", "Qtm_plus_sym_psi"), ("Mtm_plus_sym_psi_nocom", "Mtm_plus_sym_psi"),
+                      ("Mtm_minus_sym_psi_nocom", "Mtm_minus_sym_psi")):
+        getattr(D, name)(out, k); assert rel_l2(out, ops[ref]) <= TOL, name
+    for name, ref in (("Qtm_plus_psi_nocom", "Qtm_plus_psi"), ("Mtm_plus_psi_nocom", "Mtm_plus_psi"), ("Qtm_pm_psi_nocom", "Qtm_pm_psi")):
+        getattr(D, name)(out, k); assert rel_l2(out, base[ref]) <= TOL, name
+    outl = D.spinor(D.V)
+    for name in ("M_minus_psi", "D_dagg_psi", "Q_plus_psi", "Q_minus_psi"):
+        getattr(D, name)(outl, lex); assert rel_l2(outl, ops[name]) <= TOL, name
+    D.Mee_psi(out, k, 0.37); assert rel_l2(out, ops["Mee_psi"]) <= TOL
+    D.Mee_inv_psi(out, k, 0.37); assert rel_l2(out, ops["Mee_inv_psi"]) <= TOL
+    D.mul_one_sub_mul_gamma5(out, k, p); assert rel_l2(out, ops["mul_one_sub_mul_gamma5"]) <= TOL
+    D.mul_one_pm_imu_sub_mul(out, k, p, -1., D.Vh); assert rel_l2(out, ops["mul_one_pm_imu_sub_mul"]) <= TOL
+    a, b = D.spinor(), D.spinor()
+    D.M_minus_1_timesC(a, b, k, p)
+    assert rel_l2(a, ops["M_minus_1_timesC_e"]) <= TOL and rel_l2(b, ops["M_minus_1_timesC_o"]) <= TOL
+    D.H_eo_tm_ndpsi(a, b, k, p, 1)
+    assert rel_l2(a, ops["H_eo_tm_ndpsi_s"]) <= TOL and rel_l2(b, ops["H_eo_tm_ndpsi_c"]) <= TOL
+    D.M_oo_sub_g5_ndpsi(a, b, k, p, q, w, -0.139, -0.15)
+    assert rel_l2(a, ops["M_oo_sub_g5_ndpsi_s"]) <= TOL and rel_l2(b, ops["M_oo_sub_g5_ndpsi_c"]) <= TOL
+    D.mul_one_pm_iconst(out, k, 0.21, -1); assert rel_l2(out, ops["mul_one_pm_iconst"]) <= TOL
+
+
+def test_host_memory_helpers_and_precision_conversion(dropin):
+    D, base = dropin
+    k, p = np.array(base["k"]), np.array(base["p"])
+    z = k.copy(); D.zero_spinor_field(z, D.Vh); assert not z.any()
+    f = np.zeros((D.Vh, 24), dtype=np.float32)
+    D.assign_to_32(f, k, D.Vh); assert np.array_equal(f, k.astype(np.float32))
+    back = D.spinor(); D.assign_to_64(back, f, D.Vh); assert np.array_equal(back, f.astype(np.float64))
+    acc = p.copy(); D.addto_32(acc, f, D.Vh); assert rel_l2(acc, p + f.astype(np.float64)) <= 1e-15
+    sf = C.POINTER(C.c_void_p)()
+    assert D.init_solver_field(C.byref(sf), D.Vh, 3) == 0
+    assert sf[1] - sf[0] == D.Vh * 192 and sf[2] - sf[1] == D.Vh * 192 and sf[3] == sf[0]  # solver_field.c:63-66
+    D.finalize_solver(sf, 3)
+
+
+def test_solvers_with_reference_signatures(dropin):
+    import tmlqcd_b200 as tm
+    D, base = dropin
+    k = np.array(base["k"])
+    sp = tm.capi.SolverParams(); sp.mcg_delta = 5e-5
+    xr = base["cg_x"]  # reference cg_her(k, 1e-20 relative)
+    for solver in (CG, MIXEDCG, RGMIXEDCG):
+        x = D.spinor()
+        it = D.solve_degenerate(x, k, sp, 2000, 1e-20, 1, D.Vh, D.fptr("Qtm_pm_psi"), solver)
+        assert it > 0 and rel_l2(x, xr) <= 1e-8, solver
+        if solver == CG:
+            assert abs(it - int(base["cg_iters"])) <= 1
+    x = D.spinor()
+    it = D.rg_mixed_cg_her(x, k, sp, 2000, 1e-20, 1, D.Vh, D.fptr("Qtm_pm_psi"), D.fptr("Qtm_pm_psi_32"))
+    assert it > 0 and rel_l2(x, xr) <= 1e-8
+
+
+def test_hmc_symbols_with_reference_signatures():
+    """deriv_Sb / chrono_* / det_* / detratio_* with the reference's own signatures and host buffers"""
+    import tmlqcd_b200 as tm
+    gold = _gold("ref_hmc_4x4x4x4.npz")
+    D = tm.DropIn(*[int(x) for x in gold["dims"]])
+    try:
+        D.set_params(float(gold["kappa"]), float(gold["gmu"]), gold["theta"])
+        D.set_gauge(gold["gauge"])
+        l, k = np.array(gold["l"]), np.array(gold["k"])
+        for ieo in (0, 1):
+            df = np.zeros((D.V, 4, 8))
+            hf = D.hamiltonian_field(df)
+            D.deriv_Sb(ieo, l, k, C.byref(hf), 0.7)
+            assert rel_l2(df, gold[f"deriv_Sb{ieo}"]) <= TOL
+            D.deriv_Sb(ieo, l, k, C.byref(hf), -0.7)  # accumulates into the caller's array
+            assert np.abs(df).max() <= 1e-12
+        # chronological guess on host fields: the exact solution in the history reproduces itself
+        N = 2
+        hist = [D.spinor() for _ in range(N)]
+        v = (C.c_void_p * N)(*[h.ctypes.data for h in hist])
+        idx, n = (C.c_int * N)(), C.c_int(0)
+        x = D.spinor()
+        sp = tm.capi.SolverParams()
+        assert D.solve_degenerate(x, k, sp, 2000, 1e-24, 0, D.Vh, D.fptr("Qtm_pm_psi"), CG) > 0
+        D.chrono_add_solution(x, v, idx, N, C.byref(n), D.Vh)
+        assert n.value == 1 and abs(np.linalg.norm(hist[0]) - 1) < 1e-14
+        trial = D.spinor()
+        assert D.chrono_guess(trial, k, v, idx, N, n.value, D.Vh, D.fptr("Qtm_pm_psi")) == 0
+        assert rel_l2(trial, x) <= 1e-9
+        # monomials through the hbfunction / derivativefunction / accfunction signatures
+        etas = {}
+
+        def rng(ptr, repro, rn_type):
+            assert repro == 1 and rn_type == 0
+            np.ctypeslib.as_array(ptr, shape=(D.Vh * 24,))[:] = etas["cur"].reshape(-1)
+        cb = tm.capi.RANDOM_SPINOR_FN(rng)
+        D.tmb_dropin_set_random_spinor_field_eo(cb)
+        names = {0: ("det_heatbath", "det_derivative", "det_acc"), 1: ("detratio_heatbath", "detratio_derivative", "detratio_acc")}
+        for id, (typ, csg_N) in enumerate(gold["monomials"]):
+            assert D.tmb_dropin_register_monomial(id, int(typ), float(gold["kappa"]), float(gold["gmu"]), float(gold["kappa2"]),
+                                                  float(gold["gmu2"]), CG, 2000, float(gold["forceprec"]), float(gold["accprec"]),
+                                                  int(csg_N)) == 0
+            hb, der, acc = names[int(typ)]
+            etas["cur"] = np.array(gold[f"m{id}_eta"])
+            df = np.zeros((D.V, 4, 8)); hf = D.hamiltonian_field(df)
+            getattr(D, hb)(id, C.byref(hf))
+            for call in range(3):
+                getattr(D, der)(id, C.byref(hf))
+                assert rel_l2(df, gold[f"m{id}_df{call}"]) <= 1e-9, (id, call)
+            dH = getattr(D, acc)(id, C.byref(hf))
+            assert abs(dH - float(gold[f"m{id}_dH"])) <= 1e-7
+            e0, e1, i0, i1 = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+            assert D.tmb_dropin_monomial_info(id, C.byref(e0), C.byref(e1), C.byref(i0), C.byref(i1)) == 0
+            assert abs(e0.value / float(gold[f"m{id}_energy0"]) - 1) <= 1e-13
+            assert abs(i1.value - int(gold[f"m{id}_iter1_2"])) <= 3
+        # the caller's globals are untouched by the monomials (mnl_backup_restore_globals)
+        assert D.glob("g_mu").value == float(gold["gmu"]) and D.glob("g_kappa").value == float(gold["kappa"])
+    finally:
+        D.close()

@@ -55,7 +55,8 @@ DEVICE_API = {
     "tmb_M_full": (_i, [_vp] * 4), "tmb_Q_full": (_i, [_vp] * 4), "tmb_D_psi_eo": (_i, [_vp] * 4),
     "tmb_assign_mul_one_pm_imu_inv": (_i, [_vp, _vp, _d]), "tmb_assign_mul_one_pm_imu": (_i, [_vp, _vp, _d]),
     "tmb_mul_one_pm_imu_sub_mul_gamma5": (_i, [_vp, _vp, _vp, _d]), "tmb_mul_one_pm_imu_sub_mul": (_i, [_vp, _vp, _vp, _d]),
-    "tmb_gamma5": (_i, [_vp, _vp]),
+    "tmb_gamma5": (_i, [_vp, _vp]), "tmb_diag": (_i, [_vp, _vp, _d, _d]), "tmb_diag_sub": (_i, [_vp, _vp, _vp, _d, _d, _i]),
+    "tmb_M_oo_sub_g5_ndpsi": (_i, [_vp] * 6 + [_d, _d]),
     "tmb_square_norm": (_i, [_vp, C.POINTER(_d)]), "tmb_scalar_prod_r": (_i, [_vp, _vp, C.POINTER(_d)]),
     "tmb_assign_add_mul_r": (_i, [_vp, _vp, _d]), "tmb_assign_mul_add_r": (_i, [_vp, _d, _vp]),
     "tmb_assign_mul_add_r_and_square": (_i, [_vp, _d, _vp, C.POINTER(_d)]),
@@ -101,6 +102,14 @@ class SolverParams(C.Structure):
                 ("sloppy_precision", _i), ("external_inverter", _i)]
 
 
+class HamiltonianField(C.Structure):
+    """hamiltonian_field_t (hamiltonian_field.h:28-34)"""
+    _fields_ = [("gaugefield", _vp), ("momenta", _vp), ("derivative", C.POINTER(C.POINTER(_d))),
+                ("update_gauge_copy", _i), ("traj_counter", _i)]
+
+
+RANDOM_SPINOR_FN = C.CFUNCTYPE(None, C.POINTER(_d), _i, _i)
+
 # reference-named entry points (include/tmlqcd_b200_dropin.h).  `_Complex double` by value is
 # two doubles in SSE registers under the x86-64 SysV ABI, hence the (_d, _d) pairs.
 DROPIN_API = {
@@ -132,6 +141,32 @@ DROPIN_API = {
     "Qtm_dagger_ndpsi": (None, [_sp] * 4), "Qtm_pm_ndpsi": (None, [_sp] * 4),
     "cg_her_nd": (_i, [_sp] * 4 + [_i, _d, _i, _i, _vp]),
     "invert_doublet_eo": (_i, [_sp] * 8 + [_d, _i, _i, _i, SolverParams, _i, _i, _i]),
+    "Mee_inv_psi": (None, [_sp, _sp, _d]), "Mee_psi": (None, [_sp, _sp, _d]),
+    "mul_one_pm_imu_sub_mul": (None, [_sp, _sp, _sp, _d, _i]), "mul_one_sub_mul_gamma5": (None, [_sp, _sp, _sp]),
+    "M_minus_1_timesC": (None, [_sp] * 4),
+    "Qtm_plus_sym_psi": (None, [_sp, _sp]), "Qtm_minus_sym_psi": (None, [_sp, _sp]), "Mtm_plus_sym_psi": (None, [_sp, _sp]),
+    "Mtm_minus_sym_psi": (None, [_sp, _sp]), "Mtm_plus_sym_dagg_psi": (None, [_sp, _sp]), "Qtm_pm_sym_psi": (None, [_sp, _sp]),
+    "Qtm_plus_sym_psi_nocom": (None, [_sp, _sp]), "Mtm_plus_sym_psi_nocom": (None, [_sp, _sp]),
+    "Mtm_minus_sym_psi_nocom": (None, [_sp, _sp]), "Qtm_plus_psi_nocom": (None, [_sp, _sp]),
+    "Mtm_plus_psi_nocom": (None, [_sp, _sp]), "Qtm_pm_psi_nocom": (None, [_sp, _sp]),
+    "M_minus_psi": (None, [_sp, _sp]), "D_dagg_psi": (None, [_sp, _sp]),
+    "zero_spinor_field": (None, [_sp, _i]), "assign_to_32": (None, [_fp, _sp, _i]), "assign_to_64": (None, [_sp, _fp, _i]),
+    "addto_32": (None, [_sp, _fp, _i]),
+    "init_solver_field": (_i, [C.POINTER(C.POINTER(_vp)), _i, _i]), "finalize_solver": (None, [C.POINTER(_vp), _i]),
+    "H_eo_tm_ndpsi": (None, [_sp] * 4 + [_i]), "M_oo_sub_g5_ndpsi": (None, [_sp] * 6 + [_d, _d]),
+    "mul_one_pm_iconst": (None, [_sp, _sp, _d, _i]),
+    "rg_mixed_cg_her": (_i, [_sp, _sp, SolverParams, _i, _d, _i, _i, _vp, _vp]),
+    "deriv_Sb": (None, [_i, _sp, _sp, C.POINTER(HamiltonianField), _d]),
+    "chrono_add_solution": (None, [_sp, C.POINTER(_vp), C.POINTER(_i), _i, C.POINTER(_i), _i]),
+    "chrono_guess": (_i, [_sp, _sp, C.POINTER(_vp), C.POINTER(_i), _i, _i, _i, _vp]),
+    "solve_degenerate": (_i, [_sp, _sp, SolverParams, _i, _d, _i, _i, _vp, _i]),
+    "tmb_dropin_register_monomial": (_i, [_i, _i, _d, _d, _d, _d, _i, _i, _d, _d, _i]),
+    "tmb_dropin_set_random_spinor_field_eo": (None, [RANDOM_SPINOR_FN]),
+    "tmb_dropin_monomial_info": (_i, [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), C.POINTER(_i)]),
+    "det_heatbath": (None, [_i, C.POINTER(HamiltonianField)]), "det_acc": (_d, [_i, C.POINTER(HamiltonianField)]),
+    "det_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
+    "detratio_heatbath": (None, [_i, C.POINTER(HamiltonianField)]), "detratio_acc": (_d, [_i, C.POINTER(HamiltonianField)]),
+    "detratio_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
     "tmLQCD_invert_init": (_i, [_i, _vp, _i, _i]), "tmLQCD_read_gauge": (_i, [_i]),
     "tmLQCD_invert": (_i, [_sp, _sp, _i, _i]), "tmLQCD_finalise": (_i, []),
     "tmLQCD_get_gauge_field_pointer": (_i, [C.POINTER(C.POINTER(_d))]),
@@ -142,7 +177,7 @@ DROPIN_API = {
 DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND", "g_update_gauge_copy", "g_proc_id",
                   "g_debug_level", "g_nproc", "g_nproc_t", "g_kappa", "g_mu", "g_mubar", "g_epsbar", "phmc_invmaxev",
                   "X0", "X1", "X2", "X3", "ka0", "ka1", "ka2", "ka3", "phase_0", "phase_1", "phase_2", "phase_3",
-                  "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit"]
+                  "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit", "g_relative_precision_flag"]
 
 _SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed",
             "rg_mixed_cg_her", "solve_degenerate"}
@@ -336,6 +371,19 @@ class DropIn:
 
     def spinor(self, n=None):
         return np.zeros((self.Vh if n is None else n, 24), dtype=np.float64)
+
+    def hamiltonian_field(self, df):
+        """hamiltonian_field_t over g_gauge_field and a caller-owned derivative array df[V][4][8]"""
+        assert df.dtype == np.float64 and df.flags["C_CONTIGUOUS"] and df.size == self.V * 32
+        rows = (C.POINTER(_d) * self.V)()
+        base = df.ctypes.data
+        for ix in range(self.V):
+            rows[ix] = C.cast(base + ix * 4 * 8 * 8, C.POINTER(_d))
+        hf = HamiltonianField()
+        hf.gaugefield = C.cast(C.POINTER(C.POINTER(_d)).in_dll(self.lib, "g_gauge_field"), _vp)
+        hf.derivative = C.cast(rows, C.POINTER(C.POINTER(_d)))
+        hf._keep = (rows, df)
+        return hf
 
     def fptr(self, name):
         return C.cast(getattr(self.lib, name), _vp)

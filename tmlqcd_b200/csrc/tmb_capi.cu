@@ -629,6 +629,13 @@ extern "C" int tmb_mul_one_pm_imu_sub_mul_gamma5(void *l, const void *k, const v
 extern "C" int tmb_mul_one_pm_imu_sub_mul(void *l, const void *k, const void *j, double sign) {
   NEED_INIT(); KL(tmb_launch_diag_sub(F(l), F(k), F(j), z_fwd(sign), 0, N2(), HALF(), C.s_main)); return 0;
 }
+/* generic forms: l = (z on s0,s1 | conj z on s2,s3) k   and   l = [g5]( (z | conj z) k - j ) */
+extern "C" int tmb_diag(void *l, const void *k, double zre, double zim) {
+  NEED_INIT(); KL(tmb_launch_diag(F(l), F(k), make_double2(zre, zim), N2(), HALF(), C.s_main)); return 0;
+}
+extern "C" int tmb_diag_sub(void *l, const void *k, const void *j, double zre, double zim, int g5) {
+  NEED_INIT(); KL(tmb_launch_diag_sub(F(l), F(k), F(j), make_double2(zre, zim), g5 ? 1 : 0, N2(), HALF(), C.s_main)); return 0;
+}
 extern "C" int tmb_gamma5(void *l, const void *k) { NEED_INIT(); KL(tmb_launch_gamma5(F(l), F(k), N2(), HALF(), C.s_main)); return 0; }
 
 /* ------------------------------------------------------------------ BLAS-1 */
@@ -746,6 +753,10 @@ extern "C" int tmb_M_ee_inv_ndpsi(void *ls, void *lc, const void *ks, const void
 static int nd_moo(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc, const double2 *js, const double2 *jc,
                   double mu, double eps) {
   KL(tmb_launch_nd_moo_sub_g5(ls, lc, ks, kc, js, jc, mu, eps, N2(), HALF(), C.s_main)); return 0;
+}
+extern "C" int tmb_M_oo_sub_g5_ndpsi(void *ls, void *lc, const void *ks, const void *kc, const void *js, const void *jc,
+                                     double mu, double eps) {
+  NEED_INIT(); return nd_moo(F(ls), F(lc), F(ks), F(kc), F(js), F(jc), mu, eps);
 }
 static int hop0(int ieo, double2 *l, const double2 *k) { HopOpt o; return hop(ieo, l, k, o); }
 

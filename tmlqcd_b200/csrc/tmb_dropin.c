@@ -65,9 +65,11 @@ int tmb_dropin_init(int t, int lx, int ly, int lz, int device) {
   dropin_up = 1;
   return 0;
 }
+static void hmc_forget(void);
 int tmb_dropin_finalize(void) {
   for (int k = 0; k < NDEV; k++) D[k] = NULL; /* freed by tmb_finalize */
   for (int k = 0; k < 4; k++) D32[k] = NULL;
+  hmc_forget();
   tmb_finalize();
   free(gauge_slab); free(g_gauge_field); gauge_slab = NULL; g_gauge_field = NULL;
   dropin_up = 0;
@@ -523,3 +525,309 @@ int tmLQCD_finalise(void) {
   facade_up = 0; no_operators = 0; lat[0] = 0;
   return 0;
 }
+
+/* ==================================================================================================
+ * Remaining members of the operator families
+ * ================================================================================================== */
+/* tm_operators.c:587 / :723: the mass is an ARGUMENT here, not g_mu */
+void Mee_inv_psi(spinor *const l, spinor *const k, const double mu) {
+  const double nrm = 1. / (1. + mu * mu);
+  sync_globals(); up(0, k); CHK(tmb_diag(dev(1), dev(0), nrm, -nrm * mu)); down(l, 1);
+}
+void Mee_psi(spinor *const l, spinor *const k, const double mu) {
+  sync_globals(); up(0, k); CHK(tmb_diag(dev(1), dev(0), 1., mu)); down(l, 1);
+}
+/* tm_operators.c:813 (mul_one_pm_imu_sub_mul_body.c), :781 */
+void mul_one_pm_imu_sub_mul(spinor *const l, spinor *const k, spinor *const j, const double sign, const int N) {
+  sync_globals();
+  for (int q = 0, n = nparts(N, __func__); q < n; q++) {
+    up(0, PART(k, q)); up(1, PART(j, q)); CHK(tmb_mul_one_pm_imu_sub_mul(dev(2), dev(0), dev(1), sign)); down(PART(l, q), 2);
+  }
+}
+void mul_one_sub_mul_gamma5(spinor *const l, spinor *const k, spinor *const j) {
+  sync_globals(); up(0, k); up(1, j); CHK(tmb_diag_sub(dev(2), dev(0), dev(1), 1., 0., 1)); down(l, 2);
+}
+/* tm_operators.c:145 */
+void M_minus_1_timesC(spinor *const En, spinor *const On, spinor *const E, spinor *const O) {
+  sync_globals(); up(0, E); up(1, O);
+  CHK(tmb_H_eo_tm_inv_psi(dev(2), dev(1), EO, +1.)); CHK(tmb_H_eo_tm_inv_psi(dev(3), dev(0), OE, +1.));
+  down(En, 2); down(On, 3);
+}
+/* the "symmetric" even/odd operators, tm_operators.c:186-310: 1 - (M_oo)^-1 H_oe (M_ee)^-1 H_eo.
+ * which: 0 -> l = k - w ; 1 -> l = g5 (k - w), with w = (1 +- i mu g5)^-1 H_oe (1 +- i mu g5)^-1 H_eo k */
+static void sym_op(spinor *const l, spinor *const k, double sign, int g5) {
+  sync_globals(); up(0, k);
+  CHK(tmb_H_eo_tm_inv_psi(dev(1), dev(0), EO, sign));
+  CHK(tmb_H_eo_tm_inv_psi(dev(2), dev(1), OE, sign));
+  CHK(tmb_diag_sub(dev(3), dev(0), dev(2), 1., 0., g5));
+  down(l, 3);
+}
+void Qtm_plus_sym_psi(spinor *const l, spinor *const k) { sym_op(l, k, +1., 1); }
+void Qtm_minus_sym_psi(spinor *const l, spinor *const k) { sym_op(l, k, -1., 1); }
+void Mtm_plus_sym_psi(spinor *const l, spinor *const k) { sym_op(l, k, +1., 0); }
+void Mtm_minus_sym_psi(spinor *const l, spinor *const k) { sym_op(l, k, -1., 0); }
+void Qtm_plus_sym_psi_nocom(spinor *const l, spinor *const k) { sym_op(l, k, +1., 1); }
+void Mtm_plus_sym_psi_nocom(spinor *const l, spinor *const k) { sym_op(l, k, +1., 0); }
+void Mtm_minus_sym_psi_nocom(spinor *const l, spinor *const k) { sym_op(l, k, -1., 0); }
+/* tm_operators.c:312-322 */
+void Mtm_plus_sym_dagg_psi(spinor *const l, spinor *const k) {
+  sync_globals(); up(0, k);
+  CHK(tmb_gamma5(dev(1), dev(0)));
+  CHK(tmb_assign_mul_one_pm_imu_inv(dev(1), dev(1), -1.));
+  CHK(tmb_H_eo_tm_inv_psi(dev(2), dev(1), EO, -1.));
+  CHK(tmb_Hopping_Matrix(OE, dev(3), dev(2)));
+  CHK(tmb_gamma5(dev(2), dev(3)));
+  CHK(tmb_diff(dev(1), dev(0), dev(2)));
+  down(l, 1);
+}
+/* tm_operators.c:347-364, mirrored LITERALLY: its second half multiplies the scratch field DUM_MATRIX (not
+ * the freshly hopped DUM_MATRIX+1) by the inverse, so the function is not Q_+^sym Q_-^sym; the reference's
+ * behaviour is kept, not silently fixed ("odd corner cases") */
+void Qtm_pm_sym_psi(spinor *const l, spinor *const k) {
+  sync_globals(); up(0, k);
+  void *L = dev(3), *M0 = dev(1), *M1 = dev(2);
+  CHK(tmb_H_eo_tm_inv_psi(M1, dev(0), EO, -1.));
+  CHK(tmb_H_eo_tm_inv_psi(M0, M1, OE, -1.));
+  CHK(tmb_diag_sub(L, dev(0), M0, 1., 0., 1));          /* l = g5 (k - M0) */
+  CHK(tmb_H_eo_tm_inv_psi(L, M0, EO, +1.));             /* Hopping_Matrix(EO, l, M0); mul_one_pm_imu_inv(l, +1) */
+  CHK(tmb_Hopping_Matrix(OE, M1, L));
+  CHK(tmb_assign_mul_one_pm_imu_inv(M0, M0, +1.));      /* applied to M0, as in the reference */
+  CHK(tmb_diag_sub(L, dev(0), M0, 1., 0., 1));
+  down(l, 3);
+}
+/* no halo exchange exists at the host-pointer level of a single rank: the *_nocom forms coincide */
+void Qtm_plus_psi_nocom(spinor *const l, spinor *const k) { Qtm_plus_psi(l, k); }
+void Mtm_plus_psi_nocom(spinor *const l, spinor *const k) { Mtm_plus_psi(l, k); }
+void Qtm_pm_psi_nocom(spinor *const l, spinor *const k) { Qtm_pm_psi(l, k); }
+/* tm_operators.c:471, :390: full-lattice; the reference flips the global g_mu around D_psi */
+void M_minus_psi(spinor *const l, spinor *const k) {
+  sync_globals();
+  CHK(tmb_field_upload_lexic(dev(0), dev(1), (const double *)k));
+  CHK(tmb_set_mu(-g_mu)); CHK(tmb_M_full(dev(2), dev(3), dev(0), dev(1))); CHK(tmb_set_mu(g_mu));
+  CHK(tmb_field_download_lexic((double *)l, dev(2), dev(3)));
+}
+void D_dagg_psi(spinor *const l, spinor *const k) { /* g5 D(-mu) g5 */
+  sync_globals();
+  CHK(tmb_field_upload_lexic(dev(0), dev(1), (const double *)k));
+  CHK(tmb_gamma5(dev(0), dev(0))); CHK(tmb_gamma5(dev(1), dev(1)));
+  CHK(tmb_set_mu(-g_mu)); CHK(tmb_Q_full(dev(2), dev(3), dev(0), dev(1))); CHK(tmb_set_mu(g_mu));
+  CHK(tmb_field_download_lexic((double *)l, dev(2), dev(3)));
+}
+/* start.c:354; linalg/assign_to_32.c:37,:84; linalg/addto_32.c:16: host-to-host, conversion on the device */
+void zero_spinor_field(spinor *const k, const int N) { memset(k, 0, sizeof(spinor) * (size_t)N); }
+void assign_to_32(spinor32 *const R, spinor *const S, const int N) {
+  (void)nparts(N, __func__);
+  sync_globals();
+  for (int q = 0, n = nparts(N, __func__); q < n; q++) {
+    up(0, PART(S, q)); CHK(tmb_assign_to_32(dev32(0), dev(0)));
+    CHK(tmb_field32_download((float *)((spinor32 *)R + (size_t)q * (VOLUME / 2)), dev32(0)));
+  }
+}
+void assign_to_64(spinor *const R, spinor32 *const S, const int N) {
+  sync_globals();
+  for (int q = 0, n = nparts(N, __func__); q < n; q++) {
+    CHK(tmb_field32_upload(dev32(0), (const float *)((spinor32 *)S + (size_t)q * (VOLUME / 2))));
+    CHK(tmb_assign_to_64(dev(0), dev32(0))); down(PART(R, q), 0);
+  }
+}
+void addto_32(spinor *const Q, const spinor32 *const R, const int N) {
+  sync_globals();
+  for (int q = 0, n = nparts(N, __func__); q < n; q++) {
+    CHK(tmb_field32_upload(dev32(0), (const float *)((const spinor32 *)R + (size_t)q * (VOLUME / 2))));
+    CHK(tmb_assign_to_64(dev(1), dev32(0))); up(0, PART(Q, q)); CHK(tmb_add(dev(0), dev(0), dev(1))); down(PART(Q, q), 0);
+  }
+}
+/* solver/solver_field.c:31-71: host scratch for callers that drive their own recurrences */
+int init_solver_field(spinor ***const solver_field, const int V, const int nr) {
+  if ((*solver_field = (spinor **)malloc((size_t)(nr + 1) * sizeof(spinor *))) == NULL) return 2;
+  if (((*solver_field)[nr] = (spinor *)calloc((size_t)nr * V + 1, sizeof(spinor))) == NULL) return 1;
+  (*solver_field)[0] = (*solver_field)[nr];
+  for (int i = 1; i < nr; i++) (*solver_field)[i] = (*solver_field)[i - 1] + V;
+  return 0;
+}
+void finalize_solver(spinor **solver_field, const int nr) { free(solver_field[nr]); free(solver_field); }
+/* tm_operators_nd.c:508, :698, :599 */
+void H_eo_tm_ndpsi(spinor *const ls, spinor *const lc, spinor *const ks, spinor *const kc, const int ieo) {
+  sync_globals(); up(0, ks); up(1, kc);
+  CHK(tmb_Hopping_Matrix(ieo, dev(2), dev(0))); CHK(tmb_Hopping_Matrix(ieo, dev(3), dev(1)));
+  CHK(tmb_M_ee_inv_ndpsi(dev(1), dev(0), dev(2), dev(3), -g_mubar, g_epsbar)); /* (l_charm, l_strange, ...) as :515 */
+  down(ls, 0); down(lc, 1);
+}
+void M_oo_sub_g5_ndpsi(spinor *const ls, spinor *const lc, spinor *const ks, spinor *const kc, spinor *const js,
+                       spinor *const jc, const double mu, const double eps) {
+  sync_globals(); up(0, ks); up(1, kc); up(2, js); up(3, jc);
+  CHK(tmb_M_oo_sub_g5_ndpsi(dev(4), dev(5), dev(0), dev(1), dev(2), dev(3), mu, eps)); down(ls, 4); down(lc, 5);
+}
+void mul_one_pm_iconst(spinor *const l, spinor *const k, const double mu_, const int sign_) {
+  sync_globals(); up(0, k); CHK(tmb_diag(dev(1), dev(0), 1., sign_ < 0 ? -mu_ : mu_)); down(l, 1);
+}
+/* solver/rg_mixed_cg_her.c:180 */
+int rg_mixed_cg_her(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
+                    const int rel_prec, const int N, matrix_mult f, matrix_mult32 f32) {
+  if (f != &Qtm_pm_psi || f32 != (matrix_mult32)&Qtm_pm_psi_32 || N != VOLUME / 2) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in rg_mixed_cg_her: only (Qtm_pm_psi, Qtm_pm_psi_32) on VOLUME/2 sites is implemented\n");
+    exit(1);
+  }
+  sync_globals();
+  CHK(tmb_set_mcg_delta((double)solver_params.mcg_delta));
+  up(6, Q);
+  int iter = tmb_rg_mixed_cg_her(dev(7), dev(6), max_iter, eps_sq, rel_prec);
+  if (iter < -1) die(__func__);
+  down(P, 7);
+  return iter;
+}
+
+/* ==================================================================================================
+ * HMC side with the reference's names and host pointers
+ * ================================================================================================== */
+int g_relative_precision_flag = 0; /* global.h:75 */
+
+/* deriv_Sb.c:402: accumulates into hf->derivative (host).  hf->gaugefield must be g_gauge_field. */
+void deriv_Sb(const int ieo, spinor *const l, spinor *const k, hamiltonian_field_t *const hf, const double factor) {
+  if (hf->gaugefield != g_gauge_field) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in deriv_Sb: hf->gaugefield is not g_gauge_field\n"); exit(1);
+  }
+  sync_globals();
+  up(0, l); up(1, k);
+  CHK(tmb_derivative_upload((const double *)hf->derivative[0]));
+  CHK(tmb_deriv_Sb(ieo, dev(0), dev(1), factor));
+  CHK(tmb_derivative_download((double *)hf->derivative[0]));
+}
+
+static int op_id(matrix_mult f, const char *who) {
+  if (f == &Qtm_pm_psi) return TMB_OP_QTM_PM;
+  if (f == &Qtm_plus_psi) return TMB_OP_QTM_PLUS;
+  if (f == &Qtm_minus_psi) return TMB_OP_QTM_MINUS;
+  fprintf(stderr, "tmLQCD-B200 FATAL in %s: matrix_mult must be Qtm_pm_psi, Qtm_plus_psi or Qtm_minus_psi\n", who);
+  exit(1);
+}
+/* solver/chrono_guess.c:43, :82 on host fields: the history is moved to the device for the call and the
+ * (orthogonalised / appended) vectors are written back, as the reference modifies v[] in place.  The
+ * monomial entry points below keep the history resident instead. */
+#define CSG_MAX 20
+static void *csg_dev[CSG_MAX];
+static void *csg_slot(int i) {
+  if (!csg_dev[i]) { csg_dev[i] = tmb_field_alloc(); if (!csg_dev[i]) die("tmb_field_alloc"); }
+  return csg_dev[i];
+}
+void chrono_add_solution(spinor *const trial, spinor **const v, int index_array[], const int N, int *_n, const int V) {
+  if (N <= 0) return;
+  if (V != VOLUME / 2 || N > CSG_MAX) { fprintf(stderr, "tmLQCD-B200 FATAL in chrono_add_solution: V != VOLUME/2 or N > %d\n", CSG_MAX); exit(1); }
+  sync_globals();
+  void *hist[CSG_MAX];
+  for (int i = 0; i < N; i++) hist[i] = csg_slot(i);
+  up(0, trial);
+  CHK(tmb_chrono_add_solution(dev(0), hist, index_array, N, _n));
+  const int slot = index_array[(*_n) - 1 < N ? (*_n) - 1 : N - 1];
+  CHK(tmb_field_download((double *)v[slot], hist[slot]));
+}
+int chrono_guess(spinor *const trial, spinor *const phi, spinor **const v, int index_array[], const int N, const int n,
+                 const int V, matrix_mult f) {
+  if (N <= 0) { zero_spinor_field(trial, V); return 0; }
+  if (V != VOLUME / 2 || N > CSG_MAX) { fprintf(stderr, "tmLQCD-B200 FATAL in chrono_guess: V != VOLUME/2 or N > %d\n", CSG_MAX); exit(1); }
+  sync_globals();
+  void *hist[CSG_MAX];
+  for (int i = 0; i < N; i++) hist[i] = csg_slot(i);
+  for (int j = 0; j < n; j++) CHK(tmb_field_upload(hist[index_array[j]], (const double *)v[index_array[j]]));
+  up(0, phi);
+  CHK(tmb_chrono_guess(dev(1), dev(0), hist, index_array, N, n, op_id(f, __func__)));
+  for (int j = 0; j < n - 1; j++) CHK(tmb_field_download((double *)v[index_array[j]], hist[index_array[j]])); /* orthogonalised */
+  down(trial, 1);
+  return 0;
+}
+/* solver/monomial_solve.c:86 */
+int solve_degenerate(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
+                     const int rel_prec, const int N, matrix_mult f, int solver_type) {
+  if (f != &Qtm_pm_psi || N != VOLUME / 2) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in solve_degenerate: only f == Qtm_pm_psi on VOLUME/2 sites is implemented\n");
+    exit(1);
+  }
+  if (solver_type != TMB_SOLVER_CG && solver_type != TMB_SOLVER_MIXEDCG && solver_type != TMB_SOLVER_RGMIXEDCG) {
+    if (g_proc_id == 0) printf("Error: solver not allowed for degenerate solve. Aborting...\n"); /* monomial_solve.c:164 */
+    exit(2);
+  }
+  sync_globals();
+  CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
+  CHK(tmb_set_mcg_delta((double)solver_params.mcg_delta));
+  up(6, Q); up(7, P); /* P is the initial guess of the CG branch */
+  int iter = tmb_solve_degenerate(dev(7), dev(6), max_iter, eps_sq, rel_prec, solver_type);
+  if (iter < -1) die(__func__);
+  down(P, 7);
+  if (g_debug_level > 0) { /* monomial_solve.c:167-174 */
+    double r = 0.;
+    CHK(tmb_Qtm_pm_psi(dev(8), dev(7))); CHK(tmb_diff(dev(8), dev(8), dev(6))); CHK(tmb_square_norm(dev(8), &r));
+    if (g_proc_id == 0) printf("# solve_degenerate residual check: %e\n", r);
+  }
+  return iter;
+}
+
+/* ---- DET / DETRATIO monomials: the reference's hbfunction / accfunction / derivativefunction signatures
+ *      (monomial.h:125-127).  The reference keeps the parameters in monomial_list[id] (monomial.h:53-131), a
+ *      struct this library does not bind; the glue on the reference side registers them once
+ *      (INTEGRATION.md), after which pf, w_fields and the chronological history stay in HBM. ---- */
+#define MAX_MNL 30
+static int mnl_map[MAX_MNL];
+static int mnl_registered[MAX_MNL];
+static tmb_random_spinor_fn rng_fn = NULL;
+int tmb_dropin_register_monomial(int id, int type, double kappa, double mu, double kappa2, double mu2, int solver,
+                                 int maxiter, double forceprec, double accprec, int csg_N) {
+  if (id < 0 || id >= MAX_MNL) return -1;
+  int did = tmb_monomial_add(type, kappa, mu, kappa2, mu2, solver, maxiter, forceprec, accprec, csg_N);
+  if (did < 0) return -1;
+  mnl_map[id] = did; mnl_registered[id] = 1;
+  return 0;
+}
+void tmb_dropin_set_random_spinor_field_eo(tmb_random_spinor_fn fn) { rng_fn = fn; }
+int tmb_dropin_monomial_info(int id, double *energy0, double *energy1, int *iter0, int *iter1) {
+  if (id < 0 || id >= MAX_MNL || !mnl_registered[id]) return -1;
+  return tmb_monomial_info(mnl_map[id], energy0, energy1, iter0, iter1, NULL);
+}
+static void hmc_forget(void) { /* device objects are gone after tmb_finalize */
+  for (int i = 0; i < CSG_MAX; i++) csg_dev[i] = NULL;
+  for (int i = 0; i < MAX_MNL; i++) mnl_registered[i] = 0;
+}
+static int mnl_dev(int id, const char *who) {
+  if (id < 0 || id >= MAX_MNL || !mnl_registered[id]) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in %s: monomial %d was not registered (tmb_dropin_register_monomial)\n", who, id);
+    exit(1);
+  }
+  return mnl_map[id];
+}
+static void mnl_heatbath(const int id, hamiltonian_field_t *const hf, const char *who) {
+  (void)hf;
+  const int did = mnl_dev(id, who);
+  if (!rng_fn) { fprintf(stderr, "tmLQCD-B200 FATAL in %s: no random_spinor_field_eo registered (tmb_dropin_set_random_spinor_field_eo)\n", who); exit(1); }
+  sync_globals();
+  CHK(tmb_set_relative_precision_flag(g_relative_precision_flag));
+  spinor *eta = (spinor *)calloc((size_t)VOLUME / 2 + 1, sizeof(spinor));
+  if (!eta) { fprintf(stderr, "%s: out of memory\n", who); exit(1); }
+  rng_fn(eta, 1 /* rngrepro: reproduce_randomnumber_flag */, 0 /* RN_GAUSS */); /* det_monomial.c:165 */
+  up(0, eta);
+  free(eta);
+  double e0;
+  CHK(tmb_monomial_heatbath(did, dev(0), &e0));
+}
+static double mnl_acc(const int id, hamiltonian_field_t *const hf, const char *who) {
+  (void)hf;
+  const int did = mnl_dev(id, who);
+  double dH = 0.;
+  sync_globals();
+  CHK(tmb_set_relative_precision_flag(g_relative_precision_flag));
+  CHK(tmb_monomial_acc(did, &dH));
+  return dH;
+}
+static void mnl_derivative(const int id, hamiltonian_field_t *const hf, const char *who) {
+  const int did = mnl_dev(id, who);
+  if (hf->gaugefield != g_gauge_field) { fprintf(stderr, "tmLQCD-B200 FATAL in %s: hf->gaugefield is not g_gauge_field\n", who); exit(1); }
+  sync_globals();
+  CHK(tmb_set_relative_precision_flag(g_relative_precision_flag));
+  CHK(tmb_derivative_upload((const double *)hf->derivative[0]));
+  CHK(tmb_monomial_derivative(did));
+  CHK(tmb_derivative_download((double *)hf->derivative[0]));
+}
+void det_heatbath(const int id, hamiltonian_field_t *const hf) { mnl_heatbath(id, hf, __func__); }          /* det_monomial.c:150 */
+double det_acc(const int id, hamiltonian_field_t *const hf) { return mnl_acc(id, hf, __func__); }           /* det_monomial.c:202 */
+void det_derivative(const int id, hamiltonian_field_t *const hf) { mnl_derivative(id, hf, __func__); }      /* det_monomial.c:47 */
+void detratio_heatbath(const int id, hamiltonian_field_t *const hf) { mnl_heatbath(id, hf, __func__); }     /* detratio_monomial.c:199 */
+double detratio_acc(const int id, hamiltonian_field_t *const hf) { return mnl_acc(id, hf, __func__); }      /* detratio_monomial.c:266 */
+void detratio_derivative(const int id, hamiltonian_field_t *const hf) { mnl_derivative(id, hf, __func__); } /* detratio_monomial.c:49 */
