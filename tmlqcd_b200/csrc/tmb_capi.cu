@@ -87,6 +87,7 @@ struct Ctx {
   double2 *dhalo_send = nullptr, *dhalo_recv = nullptr;
   Monomial mnl[TMB_MAXMNL]; int nmnl = 0;
   double2 *w[6] = {nullptr};                  /* w_fields (monomial.c:57) */
+  double2 *nd[5] = {nullptr};                 /* two-flavour CG vectors of tmb_cg_her_nd, [2][12][Vh] each */
   int rel_prec_flag = 0;                      /* g_relative_precision_flag */
   double mcg_delta = 5.0e-5;                  /* solver_params.mcg_delta = _default_mixcg_innereps (monomial.c:106) */
 };
@@ -186,6 +187,7 @@ extern "C" int tmb_finalize(void) {
   if (C.df) cudaFree(C.df); if (C.dhalo_send) cudaFree(C.dhalo_send); if (C.dhalo_recv) cudaFree(C.dhalo_recv);
   for (int k = 0; k < C.nmnl; k++) { if (C.mnl[k].pf) cudaFree(C.mnl[k].pf); for (int i = 0; i < TMB_MAXCSG; i++) if (C.mnl[k].csg[i]) cudaFree(C.mnl[k].csg[i]); }
   for (int i = 0; i < 6; i++) if (C.w[i]) cudaFree(C.w[i]);
+  for (int i = 0; i < 5; i++) if (C.nd[i]) cudaFree(C.nd[i]);
   cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
@@ -808,64 +810,8 @@ extern "C" int tmb_Qtm_pm_ndpsi(void *ls, void *lc, const void *ks, const void *
   NEED_INIT(); return qtm_pm_nd(F(ls), F(lc), F(ks), F(kc));
 }
 
-/* solver/cg_her_nd.c:57-170: same recurrence over the two-flavour field; host-side scalars
- * (two reductions read back per iteration) - the doublet solve is the config-4 row, the
- * device-scalar treatment of tmb_cg_her is applied to it in a later round. */
-static int two_norm(const double2 *a, const double2 *b, double *out) {
-  double x = 0., y = 0.;
-  TRY(tmb_square_norm(a, &x)); TRY(tmb_square_norm(b, &y));
-  *out = x + y; return 0;
-}
-extern "C" int tmb_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq,
-                             int rel_prec) {
-  NEED_INIT();
-  const size_t n2 = N2();
-  double2 *u[5], *d[5];
-  std::vector<void *> tmp;
-  for (int i = 0; i < 5; i++) {
-    u[i] = F(tmb_field_alloc()); d[i] = F(tmb_field_alloc());
-    if (!u[i] || !d[i]) return -100;
-    tmp.push_back(u[i]); tmp.push_back(d[i]);
-  }
-  auto cleanup = [&]() { for (void *p : tmp) tmb_field_free(p); };
-  auto t0 = std::chrono::steady_clock::now();
-  double squarenorm, normsp, normsq, pro, err = 0., a, b;
-  int ret = -1, rc = 0;
-#define ND(x) do { rc = (x); if (rc < 0) { cleanup(); return rc < -1 ? rc : -100; } } while (0)
-  ND(two_norm(F(Qup), F(Qdn), &squarenorm));
-  ND(tmb_assign(u[0], Pup)); ND(tmb_assign(d[0], Pdn));
-  ND(two_norm(F(Pup), F(Pdn), &normsp));
-  if (normsp == 0.) {
-    ND(tmb_assign(u[1], Qup)); ND(tmb_assign(d[1], Qdn)); ND(tmb_assign(u[2], Qup)); ND(tmb_assign(d[2], Qdn));
-    ND(two_norm(F(Qup), F(Qdn), &normsq));
-  } else {
-    ND(qtm_pm_nd(u[3], d[3], u[0], d[0]));
-    ND(tmb_diff(u[1], Qup, u[3])); ND(tmb_diff(d[1], Qdn, d[3]));
-    ND(tmb_assign(u[2], u[1])); ND(tmb_assign(d[2], d[1]));
-    ND(two_norm(u[2], d[2], &normsq));
-  }
-  int it;
-  for (it = 0; it < max_iter; it++) {
-    ND(qtm_pm_nd(u[4], d[4], u[2], d[2]));
-    ND(tmb_scalar_prod_r(u[2], u[4], &a)); ND(tmb_scalar_prod_r(d[2], d[4], &b));
-    pro = a + b;
-    const double alpha = normsq / pro;
-    KL(tmb_launch_axpy(u[0], u[2], alpha, n2, C.s_main)); KL(tmb_launch_axpy(d[0], d[2], alpha, n2, C.s_main));
-    KL(tmb_launch_axpy(u[1], u[4], -alpha, n2, C.s_main)); KL(tmb_launch_axpy(d[1], d[4], -alpha, n2, C.s_main));
-    ND(two_norm(u[1], d[1], &err));
-    if ((err <= eps_sq && rel_prec == 0) || (err <= eps_sq * squarenorm && rel_prec == 1)) { ret = it + 1; break; }
-    const double beta = err / normsq;
-    KL(tmb_launch_xpay(u[2], beta, u[1], n2, C.s_main)); KL(tmb_launch_xpay(d[2], beta, d[1], n2, C.s_main));
-    normsq = err;
-  }
-  ND(tmb_assign(Pup, u[0])); ND(tmb_assign(Pdn, d[0]));
-  CU(cudaStreamSynchronize(C.s_main));
-#undef ND
-  cleanup();
-  auto t1 = std::chrono::steady_clock::now();
-  C.last_iters = ret; C.last_err = err; C.last_seconds = std::chrono::duration<double>(t1 - t0).count();
-  return ret;
-}
+/* tmb_cg_her_nd (solver/cg_her_nd.c:57-170): device-resident, see tmb_capi_mixed.inc */
+extern "C" int tmb_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq, int rel_prec);
 
 /* invert_doublet_eo.c:102-178 (NO_EXT_INV, CG) */
 extern "C" int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
