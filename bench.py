@@ -157,7 +157,7 @@ def workload_name(ngpus, dims):
     if ngpus == 1:
         return f"BASELINE configs[1] lattice {LX}^3x{T} (eo Hopping_Matrix pairs + invert_eo CG), kappa=0.16 mu=0.01, random SU(3)"
     return (f"BASELINE configs[2]: {LX}^3x{T * ngpus} split along T over {ngpus} GPUs, {LX}^3x{T} per GPU (weak), "
-            "NCCL half-spinor halos")
+            "T-neighbour fields read in place over NVLink (peer mode; NCCL half-spinor halos as fallback)")
 
 
 def cpu_baseline(dims, gauge_ref, target_s=12.0):
@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--skip-cg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--loopback", action="store_true", help="1 GPU: run the T-split halo/boundary path against itself")
+    ap.add_argument("--loopback2", action="store_true", help="1 GPU: run the T-split peer-mode path against itself")
     ap.add_argument("--sweep", action="store_true", help="time every kernel variant (tuning aid, prints to stderr)")
     ap.add_argument("--sweep-overlap", action="store_true", help="time PDL / L2-prefetch combinations (stderr)")
     ap.add_argument("--overlap", type=int, default=0, help="tmb_set_overlap flags: 1 PDL, 2 L2 gauge prefetch")
@@ -254,8 +255,8 @@ def main():
     if args.variant is not None or args.hints is not None or args.xblock is not None:
         dev.ck(lib.tmb_set_tuning(args.variant or 0, 1 if args.hints is None else args.hints, args.xblock or 0))
     dev.ck(lib.tmb_set_overlap(args.overlap))
-    if args.loopback and world == 1:
-        dev.ck(lib.tmb_comm_loopback(1))
+    if (args.loopback or args.loopback2) and world == 1:
+        dev.ck(lib.tmb_comm_loopback(2 if args.loopback2 else 1))
     dev.gauge_upload(g)
     rng = np.random.default_rng(99 + rank)
     src = rng.normal(scale=np.sqrt(0.5), size=(Vh, 24))
@@ -342,6 +343,7 @@ def main():
                    "step": "one EO+OE Hopping_Matrix pair (benchmark.c:293-299)"},
         "gflops_1608": sites * FLOP_SITE_REF * args.steps / (ms * 1e-3) / 1e9,
         "hbm_gbs_effective_per_gpu": achieved,
+        "peer_mode": bool(lib.tmb_comm_peer_mode()),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

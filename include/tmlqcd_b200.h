@@ -37,7 +37,8 @@ int tmb_volume_half(void); /* VOLUME/2 of this rank */
  * (torch.distributed / MPI).  Replaces g_cart_grid + xchange/ (mpi_init.c:375, xchange_field.c:583). */
 int tmb_comm_unique_id(void *id128);
 int tmb_comm_init(const void *id128, int nranks, int rank);
-int tmb_comm_loopback(int on); /* single GPU: exercise the halo/boundary path against itself */
+int tmb_comm_loopback(int on); /* single GPU: exercise the T-split path against itself; 1: halo buffers, 2: peer mode */
+int tmb_comm_peer_mode(void);  /* 1 if the hops read the neighbours' fields directly over NVLink (CUDA IPC), 0: NCCL halos */
 int tmb_comm_nranks(void);
 
 /* ---- parameters: the globals the reference operators read at call time ---- */

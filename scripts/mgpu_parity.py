@@ -45,6 +45,8 @@ def main():
     d.ck(d.lib.tmb_comm_init(C.cast(idbuf, C.c_void_p), world, rank))
     d.set_params(KAPPA, GMU, THETA)
     d.gauge_upload(g[sl])
+    if rank == 0:
+        print("peer mode:", bool(d.lib.tmb_comm_peer_mode()), flush=True)
 
     def gather(field):
         loc = torch.from_numpy(d.download(field)).cuda()

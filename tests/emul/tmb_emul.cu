@@ -149,6 +149,13 @@ void emul_xblock_perm(int *out, int T, int LX, int LY, int LZ, int XB) {
   }
 }
 
+/* peer mode: the halo buffers as the copy CTAs of hop_kernel pull them out of the neighbours' fields */
+void emul_pull_halo(double *halo_up, double *halo_dn, const double *in_up, const double *in_dn, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 1);
+  for (size_t k = 0; k < (size_t)12 * g.S; k++)
+    tmb_pull_halo_element((double2 *)halo_up, (double2 *)halo_dn, (const double2 *)in_up, (const double2 *)in_dn, g, k);
+}
+
 /* elementwise functors */
 void emul_diag(double *l, const double *k, double zre, double zim, int Vh) {
   EwDiag f = {(double2 *)l, (const double2 *)k, make_double2(zre, zim), (size_t)6 * Vh};

@@ -27,7 +27,7 @@ def load():
         "emul_pack_lexic": [dp, dp, dp, i, i, i, i], "emul_unpack_lexic": [dp, dp, dp, i, i, i, i],
         "emul_pack_gauge": [dp, dp, i, i, i, i], "emul_pack_halo": [dp, dp, dp, i, i, i, i],
         "emul_pack_gauge_halo": [dp, dp, i, i, i, i], "emul_neighbours": [ip, i, i, i, i, i],
-        "emul_eo2lexic": [ip, i, i, i, i], "emul_xblock_perm": [ip, i, i, i, i, i],
+        "emul_eo2lexic": [ip, i, i, i, i], "emul_pull_halo": [dp, dp, dp, dp, i, i, i, i], "emul_xblock_perm": [ip, i, i, i, i, i],
         "emul_hop": [i, dp, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, d, d, i, i],
         "emul_hop12": [i, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, i], "emul_compress12": [dp, dp, C.c_long, i],
         "emul_hop_f": [i, fp, fp, fp, i, i, i, i, dp],
@@ -80,6 +80,10 @@ class Emul:
 
     def pack_deriv_halo(self, soa_k, soa_l):
         out = np.zeros(24 * self.S); self.E.emul_pack_deriv_halo(out, soa_k, soa_l, *self.dims); return out
+
+    def pull_halo(self, soa_up, soa_dn):
+        hu, hd = np.zeros(12 * self.S), np.zeros(12 * self.S)
+        self.E.emul_pull_halo(hu, hd, soa_up, soa_dn, *self.dims); return hu, hd
 
     def hop(self, par, soa_in, U, ka, mode=0, cf=(1., 0.), soa_p=None, halo=None):
         out = np.zeros(24 * self.Vh)

@@ -61,6 +61,9 @@ def test_hop_all_modes_and_halo_loopback(oracle_lib, dims, theta):
             zp = o.spinor(); o.assign_mul_one_pm_imu(zp, p, +1., o.Vh)  # (1 + i mu g5) p
             got = e.unpack(e.hop(par, sk, U, ka, 3, (1.0, GMU), sp, halo=h))
             assert rel_l2(got, zp - hk) < 1e-14  # MODE 3: the M_full / D_psi row
+        # peer mode: the halo the copy CTAs PULL out of the neighbours' fields equals what pack + send/recv deliver
+        hu, hd = e.pull_halo(sk, sk)
+        assert np.array_equal(hu, dn) and np.array_equal(hd, up)
 
 
 def test_golden_hopping_through_device_code():

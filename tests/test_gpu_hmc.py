@@ -34,12 +34,12 @@ CASES = [((4, 4, 4, 4), (0., 0., 0., 0.)), ((8, 4, 6, 8), (1., 0.3, 0., 0.7)), (
 
 
 @pytest.mark.parametrize("dims,theta", CASES)
-@pytest.mark.parametrize("loopback", [0, 1])
+@pytest.mark.parametrize("loopback", [0, 1, 2])
 def test_deriv_Sb(oracle_lib, dims, theta, loopback):
     rng, o, d, g = _setup(oracle_lib, dims, theta)
     try:
         if loopback:
-            d.ck(d.lib.tmb_comm_loopback(1))
+            d.ck(d.lib.tmb_comm_loopback(loopback))
             d.gauge_upload(g)
         l, k = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
         dl, dk = d.field(l), d.field(k)

@@ -37,12 +37,12 @@ CASES = [((4, 4, 4, 4), (0., 0., 0., 0.)), ((8, 4, 6, 8), (1., 0.3, 0., 0.7)), (
 
 
 @pytest.mark.parametrize("dims,theta", CASES)
-@pytest.mark.parametrize("loopback", [0, 1])
+@pytest.mark.parametrize("loopback", [0, 1, 2])
 def test_hopping_and_epilogues(oracle_lib, dims, theta, loopback):
     rng, o, d, g = _setup(oracle_lib, dims, theta)
     try:
         if loopback:  # the T-split halo/boundary kernels, this rank being its own neighbour
-            d.ck(d.lib.tmb_comm_loopback(1))
+            d.ck(d.lib.tmb_comm_loopback(loopback))
             d.gauge_upload(g)
         k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
         dk, dp, dl = d.field(k), d.field(p), d.field()
@@ -79,13 +79,13 @@ def test_hopping_kernel_variants(oracle_lib, variant, hints, xblock):
 
 
 @pytest.mark.parametrize("flags", [1, 2, 3])
-@pytest.mark.parametrize("loopback", [0, 1])
+@pytest.mark.parametrize("loopback", [0, 1, 2])
 def test_overlap_flags(oracle_lib, flags, loopback):
     """programmatic dependent launch (bit 0) and L2 gauge prefetch (bit 1) change scheduling, not results"""
     rng, o, d, g = _setup(oracle_lib, (8, 4, 6, 8), (1., 0.3, 0., 0.7))
     try:
         if loopback:
-            d.ck(d.lib.tmb_comm_loopback(1))
+            d.ck(d.lib.tmb_comm_loopback(loopback))
             d.gauge_upload(g)
         d.ck(d.lib.tmb_set_overlap(flags))
         k = random_spinor(rng, o.Vh)
@@ -201,7 +201,7 @@ def test_cg_and_invert_eo(oracle_lib, dims, theta, loopback):
     rng, o, d, g = _setup(oracle_lib, dims, theta)
     try:
         if loopback:
-            d.ck(d.lib.tmb_comm_loopback(1))
+            d.ck(d.lib.tmb_comm_loopback(loopback))
             d.gauge_upload(g)
         q = random_spinor(rng, o.Vh)
         x_ref = o.spinor()
@@ -474,14 +474,14 @@ def test_single_precision_operator_and_mixed_cg(oracle_lib):
         D.close()
 
 
-@pytest.mark.parametrize("loopback", [0, 1])
+@pytest.mark.parametrize("loopback", [0, 1, 2])
 def test_gauge_compression_12(oracle_lib, loopback):
     """CompressionType 12 (two rows streamed, third rebuilt): same results to 1e-13, refused for non-SU(3) links"""
     import tmlqcd_b200 as tm
     rng, o, d, g = _setup(oracle_lib, (8, 4, 6, 8), (1., 0.3, 0., 0.7))
     try:
         if loopback:
-            d.ck(d.lib.tmb_comm_loopback(1))
+            d.ck(d.lib.tmb_comm_loopback(loopback))
             d.gauge_upload(g)
         d.ck(d.lib.tmb_set_compression(12))
         k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)

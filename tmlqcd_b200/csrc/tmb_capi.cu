@@ -32,6 +32,7 @@ struct NcclApi {
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
   const char *(*GetErrorString)(int);
 };
 
@@ -76,11 +77,18 @@ struct Ctx {
   int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
-  std::vector<void *> fields;
+  std::vector<void *> fields; std::vector<size_t> field_bytes;
   long long launches = 0;
   int last_iters = 0; double last_err = 0., last_seconds = 0.;
   int last_inner_sp = 0, last_inner_dp = 0, last_outer = 0;
   bool gauge_loaded = false;
+  /* peer mode: symmetric arena for spinor fields + flags, neighbours' arenas mapped through CUDA IPC */
+  bool p2p = false; int loopback_mode = 0;
+  char *arena = nullptr; size_t arena_bytes = 0, arena_used = 0;
+  std::vector<std::pair<size_t, size_t>> arena_free; /* (offset, bytes) */
+  char *up_base = nullptr, *dn_base = nullptr;
+  unsigned int *flags = nullptr, *up_flags = nullptr, *dn_flags = nullptr, *p2p_ticket = nullptr;
+  int *p2p_err = nullptr; unsigned int hop_seq = 0; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
   /* HMC side (tmb_capi_hmc.inc) */
   double2 phase[4] = {{1., 0.}, {1., 0.}, {1., 0.}, {1., 0.}}; /* exp(i theta_mu pi / L_mu): ka_mu / kappa */
   double *df = nullptr;                       /* hf->derivative on the device, [2][4][8][Vh] */
@@ -113,6 +121,38 @@ static inline size_t HALF() { return (size_t)6 * C.g.Vh; }
 static inline size_t FIELD_BYTES() { return N2() * sizeof(double2); }
 static inline double2 *F(void *p) { return (double2 *)p; }
 static inline const double2 *F(const void *p) { return (const double2 *)p; }
+
+/* ------------------------------------------------------------------ symmetric field memory
+ * With more than one rank every spinor field comes out of ONE arena per rank, allocated in the same order
+ * on all ranks (SPMD), so that "the same field on the neighbouring rank" is the neighbour's arena base plus
+ * this rank's offset - what the peer-mode hopping kernel dereferences over NVLink. */
+#define ARENA_RESERVED 256 /* flags live at the start of the arena */
+static inline bool in_arena(const void *p) {
+  return C.arena && (const char *)p >= C.arena && (const char *)p < C.arena + C.arena_bytes;
+}
+static void *sym_malloc(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (C.arena) {
+    for (size_t i = 0; i < C.arena_free.size(); i++)
+      if (C.arena_free[i].second == bytes) { void *p = C.arena + C.arena_free[i].first; C.arena_free.erase(C.arena_free.begin() + i); return p; }
+    if (C.arena_used + bytes <= C.arena_bytes) { void *p = C.arena + C.arena_used; C.arena_used += bytes; return p; }
+    if (!C.arena_warned) {
+      fprintf(stderr, "tmlqcd_b200: field arena of %zu MB exhausted (set TMB_ARENA_MB); further fields use NCCL halos\n", C.arena_bytes >> 20);
+      C.arena_warned = true;
+    }
+  }
+  void *p = nullptr;
+  return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+static void sym_free(void *p) {
+  if (!p) return;
+  if (in_arena(p)) return; /* arena blocks are recycled by size through arena_release() or die with the arena */
+  cudaFree(p);
+}
+static void arena_release(void *p, size_t bytes) {
+  if (in_arena(p)) C.arena_free.push_back(std::make_pair((size_t)((char *)p - C.arena), (bytes + 255) & ~(size_t)255));
+  else cudaFree(p);
+}
 
 extern "C" const char *tmb_last_error(void) { return g_err.c_str(); }
 extern "C" int tmb_is_initialized(void) { return C.init ? 1 : 0; }
@@ -178,16 +218,20 @@ extern "C" int tmb_finalize(void) {
   if (!C.init) return 0;
   cudaDeviceSynchronize();
   if (C.comm && C.nccl.CommDestroy) { C.nccl.CommDestroy(C.comm); C.comm = nullptr; }
-  for (void *p : C.fields) cudaFree(p);
-  C.fields.clear();
-  for (int i = 0; i < NSCRATCH; i++) { if (C.scratch[i]) cudaFree(C.scratch[i]); C.scratch[i] = nullptr; }
-  for (int i = 0; i < NSCRATCH; i++) { if (C.scratch32[i]) cudaFree(C.scratch32[i]); C.scratch32[i] = nullptr; }
+  for (void *p : C.fields) sym_free(p);
+  C.fields.clear(); C.field_bytes.clear();
+  for (int i = 0; i < NSCRATCH; i++) { sym_free(C.scratch[i]); C.scratch[i] = nullptr; }
+  for (int i = 0; i < NSCRATCH; i++) { sym_free(C.scratch32[i]); C.scratch32[i] = nullptr; }
   if (C.U32) cudaFree(C.U32); if (C.Uhalo32) cudaFree(C.Uhalo32);
   if (C.U12) cudaFree(C.U12); if (C.Uhalo12) cudaFree(C.Uhalo12); if (C.U12f) cudaFree(C.U12f); if (C.Uhalo12f) cudaFree(C.Uhalo12f);
   if (C.df) cudaFree(C.df); if (C.dhalo_send) cudaFree(C.dhalo_send); if (C.dhalo_recv) cudaFree(C.dhalo_recv);
-  for (int k = 0; k < C.nmnl; k++) { if (C.mnl[k].pf) cudaFree(C.mnl[k].pf); for (int i = 0; i < TMB_MAXCSG; i++) if (C.mnl[k].csg[i]) cudaFree(C.mnl[k].csg[i]); }
-  for (int i = 0; i < 6; i++) if (C.w[i]) cudaFree(C.w[i]);
-  for (int i = 0; i < 5; i++) if (C.nd[i]) cudaFree(C.nd[i]);
+  for (int k = 0; k < C.nmnl; k++) { sym_free(C.mnl[k].pf); for (int i = 0; i < TMB_MAXCSG; i++) sym_free(C.mnl[k].csg[i]); }
+  for (int i = 0; i < 6; i++) sym_free(C.w[i]);
+  for (int i = 0; i < 5; i++) sym_free(C.nd[i]);
+  if (C.up_base && C.up_base != C.arena) cudaIpcCloseMemHandle(C.up_base);
+  if (C.dn_base && C.dn_base != C.arena && C.dn_base != C.up_base) cudaIpcCloseMemHandle(C.dn_base);
+  if (C.arena) cudaFree(C.arena); else if (C.flags) cudaFree(C.flags);
+  if (C.p2p_ticket) cudaFree(C.p2p_ticket); if (C.p2p_err) cudaFree(C.p2p_err);
   cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
@@ -209,7 +253,7 @@ static int load_nccl() {
 #define SYM(field, name) *(void **)(&C.nccl.field) = dlsym(h, name); if (!C.nccl.field) return fail(-111, "NCCL symbol %s missing", name)
   SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
   SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
-  SYM(AllReduce, "ncclAllReduce"); SYM(GetErrorString, "ncclGetErrorString");
+  SYM(AllReduce, "ncclAllReduce"); SYM(AllGather, "ncclAllGather"); SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   return 0;
 }
@@ -218,6 +262,67 @@ extern "C" int tmb_comm_unique_id(void *id128) {
   ncclUniqueId id;
   NC(C.nccl.GetUniqueId(&id));
   memcpy(id128, &id, 128);
+  return 0;
+}
+/* Peer mode set-up: one arena per rank for all spinor fields, its CUDA-IPC handle all-gathered over NCCL,
+ * the two T-neighbours' arenas mapped into this process.  Any failure leaves the NCCL halo path in place. */
+static int p2p_small_buffers() {
+  if (!C.p2p_ticket) { CU(cudaMalloc(&C.p2p_ticket, 2 * sizeof(unsigned int))); CU(cudaMemset(C.p2p_ticket, 0, 2 * sizeof(unsigned int))); }
+  const char *cc = getenv("TMB_P2P_COPY_CTAS");
+  C.p2p_copy_ctas = cc ? atoi(cc) : 64;
+  if (C.p2p_copy_ctas < 1) C.p2p_copy_ctas = 1;
+  if (!C.p2p_err) { CU(cudaMalloc(&C.p2p_err, sizeof(int))); CU(cudaMemset(C.p2p_err, 0, sizeof(int))); }
+  return 0;
+}
+static int setup_p2p() {
+  const char *env = getenv("TMB_P2P");
+  if (env && atoi(env) == 0) return 0;
+  if (!C.fields.empty()) { fprintf(stderr, "tmlqcd_b200: fields were allocated before tmb_comm_init; NCCL halos only\n"); return 0; }
+  size_t freeb = 0, totalb = 0;
+  CU(cudaMemGetInfo(&freeb, &totalb));
+  size_t want = (size_t)48 * FIELD_BYTES() + ((size_t)64 << 20);
+  const char *mb = getenv("TMB_ARENA_MB");
+  if (mb) want = (size_t)atoll(mb) << 20;
+  if (want > freeb / 10 * 7) want = freeb / 10 * 7;
+  want &= ~(size_t)((2 << 20) - 1);
+  if (cudaMalloc(&C.arena, want) != cudaSuccess) { cudaGetLastError(); C.arena = nullptr; fprintf(stderr, "tmlqcd_b200: arena allocation failed; NCCL halos only\n"); return 0; }
+  C.arena_bytes = want; C.arena_used = ARENA_RESERVED; C.arena_free.clear();
+  CU(cudaMemset(C.arena, 0, ARENA_RESERVED));
+  cudaIpcMemHandle_t mine;
+  std::vector<cudaIpcMemHandle_t> all(C.nranks);
+  bool ok = cudaIpcGetMemHandle(&mine, C.arena) == cudaSuccess;
+  char *dsend = nullptr, *drecv = nullptr;
+  CU(cudaMalloc(&dsend, sizeof(mine) + 8)); CU(cudaMalloc(&drecv, (sizeof(mine) + 8) * C.nranks));
+  struct Msg { cudaIpcMemHandle_t h; long long ok; } msg;
+  msg.h = mine; msg.ok = ok ? 1 : 0;
+  static_assert(sizeof(Msg) == sizeof(cudaIpcMemHandle_t) + 8, "packing");
+  CU(cudaMemcpy(dsend, &msg, sizeof(msg), cudaMemcpyHostToDevice));
+  NC(C.nccl.AllGather(dsend, drecv, sizeof(msg), NCCL_UINT8, C.comm, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  std::vector<Msg> msgs(C.nranks);
+  CU(cudaMemcpy(msgs.data(), drecv, sizeof(Msg) * C.nranks, cudaMemcpyDeviceToHost));
+  cudaFree(dsend); cudaFree(drecv);
+  for (int r = 0; r < C.nranks; r++) ok = ok && msgs[r].ok;
+  const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
+  void *pu = nullptr, *pd = nullptr;
+  if (ok && cudaIpcOpenMemHandle(&pu, msgs[up].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  if (ok) {
+    if (dn == up) pd = pu;
+    else if (cudaIpcOpenMemHandle(&pd, msgs[dn].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  }
+  /* everybody must agree, otherwise one rank would wait for flags nobody writes */
+  int *dflag = nullptr; CU(cudaMalloc(&dflag, sizeof(double)));
+  double mineok = ok ? 0. : 1., sum = 0.;
+  CU(cudaMemcpy(dflag, &mineok, sizeof(double), cudaMemcpyHostToDevice));
+  NC(C.nccl.AllReduce(dflag, dflag, 1, NCCL_FLOAT64, NCCL_SUM, C.comm, C.s_main));
+  CU(cudaStreamSynchronize(C.s_main));
+  CU(cudaMemcpy(&sum, dflag, sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dflag);
+  if (sum != 0.) { fprintf(stderr, "tmlqcd_b200: CUDA IPC peer mapping unavailable; NCCL halos only\n"); return 0; }
+  C.up_base = (char *)pu; C.dn_base = (char *)pd;
+  C.flags = (unsigned int *)C.arena; C.up_flags = (unsigned int *)C.up_base; C.dn_flags = (unsigned int *)C.dn_base;
+  TRY(p2p_small_buffers());
+  C.hop_seq = 0; C.p2p = true;
   return 0;
 }
 extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) {
@@ -229,13 +334,24 @@ extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) {
   memcpy(&id, id128, 128);
   NC(C.nccl.CommInitRank(&C.comm, nranks, id, rank));
   C.nranks = nranks; C.rank = rank; C.dist = true; C.g.dist_t = 1;
+  TRY(setup_p2p());
   return 0;
 }
+extern "C" int tmb_comm_peer_mode(void) { return C.p2p ? 1 : 0; }
+/* on = 1: halo buffers (pack / copy / boundary launch); on = 2: peer mode against itself (one launch, flags) */
 extern "C" int tmb_comm_loopback(int on) {
   NEED_INIT();
   if (C.nranks > 1) return fail(-6, "tmb_comm_loopback: only for a single rank");
-  C.loopback = on != 0; C.dist = C.loopback; C.g.dist_t = C.dist ? 1 : 0;
+  C.loopback = on != 0; C.loopback_mode = on; C.dist = C.loopback; C.g.dist_t = C.dist ? 1 : 0;
   C.gauge_loaded = false; /* Uhalo must be rebuilt */
+  C.p2p = false;
+  if (on == 2) {
+    if (!C.flags) { CU(cudaMalloc(&C.flags, ARENA_RESERVED)); }
+    CU(cudaMemset(C.flags, 0, ARENA_RESERVED));
+    C.up_flags = C.dn_flags = C.flags;
+    TRY(p2p_small_buffers());
+    C.hop_seq = 0; C.p2p = true;
+  }
   return 0;
 }
 static int allreduce_slot(int slot) {
@@ -280,21 +396,31 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   return 0;
 }
 /* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
-extern "C" int tmb_set_overlap(int flags) { NEED_INIT(); C.pdl = flags & 1; C.prefetch = (flags >> 1) & 1; C.cg_graph = (flags & 4) ? 0 : 1; return 0; }
+extern "C" int tmb_set_overlap(int flags) {
+  NEED_INIT(); C.pdl = flags & 1; C.prefetch = (flags >> 1) & 1; C.cg_graph = (flags & 4) ? 0 : 1;
+  C.p2p_diag = (flags >> 3) & 31; /* timing diagnostics only: 1 = boundary reads from the LOCAL field, 2 = no end-of-hop handshake */
+  return 0;
+}
 
 /* ------------------------------------------------------------------ memory */
 extern "C" void *tmb_field_alloc(void) {
   if (!C.init) { fail(-1, "tmb_init has not been called"); return nullptr; }
-  void *p = nullptr;
-  if (cudaMalloc(&p, FIELD_BYTES()) != cudaSuccess) { fail(-100, "cudaMalloc of a spinor field failed"); return nullptr; }
+  void *p = sym_malloc(FIELD_BYTES());
+  if (!p) { fail(-100, "cudaMalloc of a spinor field failed"); return nullptr; }
   cudaMemsetAsync(p, 0, FIELD_BYTES(), C.s_main);
   C.fields.push_back(p);
+  C.field_bytes.push_back(FIELD_BYTES());
   return p;
 }
 extern "C" int tmb_field_free(void *field) {
   NEED_INIT();
   for (size_t i = 0; i < C.fields.size(); i++)
-    if (C.fields[i] == field) { CU(cudaStreamSynchronize(C.s_main)); CU(cudaFree(field)); C.fields.erase(C.fields.begin() + i); return 0; }
+    if (C.fields[i] == field) {
+      CU(cudaStreamSynchronize(C.s_main));
+      arena_release(field, C.field_bytes[i]);
+      C.fields.erase(C.fields.begin() + i); C.field_bytes.erase(C.field_bytes.begin() + i);
+      return 0;
+    }
   return fail(-8, "tmb_field_free: unknown field");
 }
 extern "C" int tmb_field_zero(void *field) { NEED_INIT(); CU(cudaMemsetAsync(field, 0, FIELD_BYTES(), C.s_main)); return 0; }
@@ -306,7 +432,15 @@ extern "C" void *tmb_host_alloc(size_t bytes) {
 extern "C" int tmb_host_free(void *p) { CU(cudaFreeHost(p)); return 0; }
 extern "C" int tmb_host_register(void *p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return 0; }
 extern "C" int tmb_host_unregister(void *p) { CU(cudaHostUnregister(p)); return 0; }
-extern "C" int tmb_sync(void) { NEED_INIT(); CU(cudaStreamSynchronize(C.s_comm)); CU(cudaStreamSynchronize(C.s_main)); return 0; }
+extern "C" int tmb_sync(void) {
+  NEED_INIT(); CU(cudaStreamSynchronize(C.s_comm)); CU(cudaStreamSynchronize(C.s_main));
+  if (C.p2p_err) {
+    int e = 0;
+    CU(cudaMemcpy(&e, C.p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) { cudaMemset(C.p2p_err, 0, sizeof(int)); return fail(-120, "peer-mode hop: a neighbour's flag did not arrive within the time-out (ranks out of step?)"); }
+  }
+  return 0;
+}
 extern "C" int tmb_timer_start(void) { NEED_INIT(); CU(cudaEventRecord(C.ev_t0, C.s_main)); return 0; }
 extern "C" int tmb_timer_stop(float *ms) {
   NEED_INIT();
@@ -396,7 +530,7 @@ extern "C" int tmb_gauge_upload(const double *host_gauge) {
 
 static double2 *scratch(int k) {
   if (!C.scratch[k]) {
-    if (cudaMalloc(&C.scratch[k], FIELD_BYTES()) != cudaSuccess) { fail(-100, "cudaMalloc of a scratch field failed"); return nullptr; }
+    if (!(C.scratch[k] = (double2 *)sym_malloc(FIELD_BYTES()))) { fail(-100, "cudaMalloc of a scratch field failed"); return nullptr; }
     cudaMemsetAsync(C.scratch[k], 0, FIELD_BYTES(), C.s_main);
   }
   return C.scratch[k];
@@ -443,6 +577,21 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     /* tuning variants exist for the plain Hopping_Matrix kernel only */
     a.variant = (o.mode == 0 && !a.dot && !a.recon12 && !o.prec) ? C.hop_variant : 0;
     a.xblock = o.nsites < 0 ? C.xblock : 0;
+    np = tmb_hop_grid(a);
+    a.fin_total = np;
+    KL(tmb_launch_hop(a, C.s_main));
+  } else if (C.p2p && o.nsites < 0 && (C.nranks == 1 || in_arena(in))) {
+    /* peer mode: one launch; boundary slices read the neighbours' copies of `in` over NVLink */
+    const size_t off = C.nranks == 1 ? 0 : (size_t)((const char *)in - C.arena);
+    a.dist = 2; a.site0 = 0; a.nsites = C.g.Vh; a.split = a.nsites; a.gap = 0; a.variant = 0; a.xblock = 0;
+    const bool local = C.nranks == 1 || (C.p2p_diag & 1);
+    a.in_up = local ? in : (const void *)(C.up_base + off);
+    a.in_dn = local ? in : (const void *)(C.dn_base + off);
+    a.p2p_nohandshake = (C.p2p_diag & 2) ? 1 : 0; a.p2p_diag = C.p2p_diag;
+    a.seq = ++C.hop_seq; a.flags = C.flags; a.up_flags = C.up_flags; a.dn_flags = C.dn_flags;
+    a.p2p_err = C.p2p_err; a.p2p_copied = C.p2p_ticket;
+    a.halo_up_w = C.halo_up; a.halo_dn_w = C.halo_dn;
+    a.p2p_copy_ctas = C.p2p_copy_ctas;
     np = tmb_hop_grid(a);
     a.fin_total = np;
     KL(tmb_launch_hop(a, C.s_main));

@@ -106,6 +106,24 @@ __device__ __forceinline__ void finish_last_block(const double *partial, int tot
   }
 }
 
+/* ------------------------------------------------------------------ cross-GPU flags (peer mode) */
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+/* spin until *p has reached seq (wrap-safe); gives up after ~4 s and raises *err instead of hanging the GPU */
+__device__ __forceinline__ void wait_flag(const unsigned int *p, unsigned int seq, int *err) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - seq) < 0) {
+    if (clock64() - t0 > 8000000000LL) { *err = 1; break; }
+    __nanosleep(100);
+  }
+}
+
 /* ------------------------------------------------------------------ K1: hopping */
 template <class V2, int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a) {
@@ -132,11 +150,104 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
     }
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (a.st != nullptr && a.st->converged) return; /* CG already stopped: uniform early exit */
-  const int w = blockIdx.x * BLOCK + threadIdx.x;
+  if (a.st != nullptr && a.st->converged) return; /* CG already stopped: uniform early exit (same on every rank) */
+  int w = blockIdx.x * BLOCK + threadIdx.x;
+  bool worker = true, bcta = false;
+  if (DIST == 2) {
+    /* Peer mode: ONE launch does the whole hop and its halo exchange.
+     * (1) Block 0 tells both neighbours that this rank's input field is complete (everything before this
+     *     kernel in the stream has finished).
+     * (2) The first p2p_copy_ctas CTAs wait for the neighbours' ready flags and PULL the two boundary
+     *     time-slices of the neighbours' fields over NVLink, projecting them to half-spinors on the way
+     *     (192 B read remotely, 96 B written locally per site), with 12 loads in flight per thread.
+     * (3) Block 0 then acts as the closer: when all pulls have landed it publishes halo_ready = seq for the
+     *     boundary CTAs, tells the neighbours that this rank no longer reads their memory (only the pull CTAs
+     *     ever do) and waits for the same from them.  The kernel cannot complete before that, so whatever
+     *     follows in the stream may overwrite the input field.  No election, no per-CTA atomics.
+     * (4) All other CTAs do the stencil in the ROTATED slice order T/2, .., T-1, 0, .., T/2-1: consecutive slices
+     *     stay adjacent in time (the +-t neighbour slices are L2 hits, exactly one pair is cut), the two
+     *     boundary slices T-1 and 0 sit in the middle of the launch - half a hop after the pull started, and
+     *     not in the tail - and only their CTAs wait for halo_ready. */
+    const int Gc = a.p2p_copy_ctas;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(a.up_flags + 1, a.seq);
+      st_release_sys(a.dn_flags + 0, a.seq);
+    }
+    if ((int)blockIdx.x < Gc) {
+      worker = false;
+      if (threadIdx.x == 0) { wait_flag(a.flags + 0, a.seq, a.p2p_err); wait_flag(a.flags + 1, a.seq, a.p2p_err); }
+      __syncthreads();
+      const size_t n = (size_t)12 * a.g.S, stride = (size_t)Gc * BLOCK;
+      const size_t half = (size_t)6 * a.g.S;
+      const V2 *iu = (const V2 *)a.in_up, *id = (const V2 *)a.in_dn;
+      V2 *hu = (V2 *)a.halo_up_w, *hd = (V2 *)a.halo_dn_w;
+      const unsigned long long keep = tmb_policy_evict_last();
+      for (size_t k0 = (size_t)blockIdx.x * BLOCK + threadIdx.x; k0 < n && !(a.p2p_diag & 4); k0 += 6 * stride) {
+        V2 x[6], y[6]; /* 12 remote loads in flight before the first store */
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+          const size_t k = k0 + u * stride;
+          if (k < n) {
+            const bool up = k < half; const size_t kk = up ? k : k - half;
+            const int c = (int)(kk / a.g.S), j = (int)(kk - (size_t)c * a.g.S);
+            const V2 *src = up ? iu : id; const size_t site = up ? (size_t)j : (size_t)(a.g.T - 1) * a.g.S + j;
+            x[u] = src[(size_t)c * a.g.Vh + site]; y[u] = src[(size_t)(c + 6) * a.g.Vh + site];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 6; u++) { /* halo buffers: keep them in L2 until the boundary CTAs come */
+          const size_t k = k0 + u * stride;
+          if (k < n) { if (k < half) tmb_st_keep(hu + k, c_add(x[u], y[u]), keep); else tmb_st_keep(hd + (k - half), c_sub(x[u], y[u]), keep); }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(a.p2p_copied, 1u);
+        if (blockIdx.x == 0) { /* the closer */
+          const long long t0 = clock64();
+          while (*(volatile unsigned int *)a.p2p_copied < (unsigned int)Gc) {
+            if (clock64() - t0 > 8000000000LL) { *a.p2p_err = 1; break; }
+            __nanosleep(200);
+          }
+          *a.p2p_copied = 0;
+          __threadfence();
+          *(volatile unsigned int *)(a.p2p_copied + 1) = a.seq; /* halo_ready */
+          __threadfence_system();
+          st_release_sys(a.up_flags + 3, a.seq);
+          st_release_sys(a.dn_flags + 2, a.seq);
+          if (!a.p2p_nohandshake) { wait_flag(a.flags + 2, a.seq, a.p2p_err); wait_flag(a.flags + 3, a.seq, a.p2p_err); }
+        }
+      }
+    } else {
+      const int wb = (int)blockIdx.x - Gc;
+      w = wb * BLOCK + threadIdx.x;
+      const int S = a.g.S, Vh = a.g.Vh;
+      const int s0 = (a.g.T + 1) / 2;                               /* first slice of the rotated order */
+      const int b0 = (a.g.T - 1 - s0) * S, b1 = b0 + 2 * S;        /* work range of slices T-1 and 0 */
+      (void)Vh;
+      if (wb * BLOCK + BLOCK > b0 && wb * BLOCK < b1) { /* block-uniform: this CTA touches slice T-1 or slice 0 */
+        bcta = !(a.p2p_diag & 8);
+        if (threadIdx.x == 0) {
+          const long long t0 = clock64();
+          while ((int)(*(volatile unsigned int *)(a.p2p_copied + 1) - a.seq) < 0) {
+            if (clock64() - t0 > 8000000000LL) { *a.p2p_err = 1; break; }
+            __nanosleep(100);
+          }
+          __threadfence();
+        }
+        __syncthreads();
+      }
+    }
+  }
   double dsum = 0.;
-  if (w < a.nsites) {
+  if (worker && w < a.nsites) {
     int ww = w;
+    if (DIST == 2 && !(a.p2p_diag & 16)) { /* rotated slice order s0, .., T-1, 0, .., s0-1 */
+      ww = w + ((a.g.T + 1) / 2) * a.g.S;
+      if (ww >= a.g.Vh) ww -= a.g.Vh;
+    }
     if (a.xblock > 0) { /* x-blocked traversal of the (t,x) planes, memory layout unchanged */
       const int P = a.g.LY * a.g.Lzh, XB = a.xblock;
       const int plane = ww / P, off = ww - plane * P;
@@ -157,7 +268,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
     for (int m = 0; m < 4; m++) ka[m] = cvt2<V2>(a.ka[m]);
     const V2 cf = cvt2<V2>(a.cf);
     V2 r[12];
-    tmb_hop_site<DIST, HINTS>(r, f, a.g, a.par, i, ka, pol);
+    /* peer mode: interior CTAs run the branch-free site code (all 8 directions' loads can be batched), only
+     * the CTAs of the two boundary slices take the variant with the per-site halo branches */
+    if (DIST == 1 || (DIST == 2 && bcta)) tmb_hop_site<1, HINTS>(r, f, a.g, a.par, i, ka, pol);
+    else tmb_hop_site<0, HINTS>(r, f, a.g, a.par, i, ka, pol);
     const V2 *pp = (const V2 *)a.p, *dw_ = (const V2 *)a.dotw;
     V2 *out = (V2 *)a.out;
     /* All epilogue operands are loaded as one batch BEFORE the first store: `out` may alias `p`
@@ -206,12 +320,12 @@ static int hop_variant_block(int variant) {
 }
 int tmb_hop_grid(const tmb_hop_launch &a) {
   const int b = a.prec ? TMB_HOP_BLOCK_F : hop_variant_block(a.variant);
-  return (a.nsites + b - 1) / b;
+  return (a.nsites + b - 1) / b + (a.dist == 2 ? a.p2p_copy_ctas : 0);
 }
 
 template <class V2, int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
 static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
-  const int grid = (a.nsites + BLOCK - 1) / BLOCK;
+  const int grid = (a.nsites + BLOCK - 1) / BLOCK + (DIST == 2 ? a.p2p_copy_ctas : 0);
   if (grid <= 0) return cudaSuccess;
   if (a.pdl) {
     cudaLaunchConfig_t cfg = {};
@@ -227,6 +341,20 @@ static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
 }
 
 /* HINTS is a configuration mask: bit 0 cache-policy loads, bit 1 12-real links (see tmb_site.cuh) */
+template <int DIST, int HINTS>
+static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s);
+template <int DIST, int CFG>
+static cudaError_t hop_mode_f(const tmb_hop_launch &a, cudaStream_t s);
+template <int HINTS>
+static cudaError_t hop_dist(const tmb_hop_launch &a, cudaStream_t s) {
+  if (a.dist == 2) return hop_mode<2, HINTS>(a, s);
+  return a.dist ? hop_mode<1, HINTS>(a, s) : hop_mode<0, HINTS>(a, s);
+}
+template <int CFG>
+static cudaError_t hop_dist_f(const tmb_hop_launch &a, cudaStream_t s) {
+  if (a.dist == 2) return hop_mode_f<2, CFG>(a, s);
+  return a.dist ? hop_mode_f<1, CFG>(a, s) : hop_mode_f<0, CFG>(a, s);
+}
 template <int DIST, int HINTS>
 static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
@@ -275,17 +403,16 @@ static cudaError_t hop_tune(const tmb_hop_launch &a, int variant, cudaStream_t s
 
 cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.prec) {
-    if (a.recon12) return a.dist ? hop_mode_f<1, 3>(a, s) : hop_mode_f<0, 3>(a, s);
-    return a.dist ? hop_mode_f<1, 1>(a, s) : hop_mode_f<0, 1>(a, s);
+    if (a.recon12) return hop_dist_f<3>(a, s);
+    return hop_dist_f<1>(a, s);
   }
-  if (a.recon12) return a.dist ? hop_mode<1, 3>(a, s) : hop_mode<0, 3>(a, s);
+  if (a.recon12) return hop_dist<3>(a, s);
   const int variant = a.variant;
   if (variant > 0) {
     if (a.mode != 0 || a.dist || a.dot) return cudaErrorInvalidValue;
     return a.hints ? hop_tune<1>(a, variant, s) : hop_tune<0>(a, variant, s);
   }
-  if (a.dist) return a.hints ? hop_mode<1, 1>(a, s) : hop_mode<1, 0>(a, s);
-  return a.hints ? hop_mode<0, 1>(a, s) : hop_mode<0, 0>(a, s);
+  return a.hints ? hop_dist<1>(a, s) : hop_dist<0>(a, s);
 }
 
 /* ------------------------------------------------------------------ K4: reductions */

@@ -56,6 +56,20 @@ struct tmb_hop_launch {
   int pdl;                  /* launch with programmatic stream serialization (PDL) */
   int prefetch;             /* bulk-prefetch the CTA's gauge rows into L2 before the dependency wait */
   int recon12;              /* U / Uhalo hold 12-real compressed links (6 complex per link) */
+  /* peer mode (dist == 2): ONE launch per hop.  Its first p2p_copy_ctas CTAs pull the projected boundary
+   * time-slices out of the neighbours' copies of `in` (in_up / in_dn: peer memory over NVLink) into halo_up /
+   * halo_dn while the other CTAs work through the interior; the CTAs of the two boundary slices come last.
+   * flags (own memory, written by the peers): [0] ready from rank+1, [1] ready from rank-1, [2] done from
+   * rank+1, [3] done from rank-1; up_flags / dn_flags are the neighbours' arrays seen from here. */
+  const void *in_up, *in_dn;
+  void *halo_up_w, *halo_dn_w;
+  unsigned int seq;
+  int p2p_copy_ctas;
+  unsigned int *flags, *up_flags, *dn_flags;
+  unsigned int *p2p_copied; /* device-local: [0] pull CTAs finished (counter), [1] halo_ready (= seq) */
+  int *p2p_err;             /* set to 1 if a flag wait timed out (deadlock guard) */
+  int p2p_nohandshake;      /* timing diagnostic: skip the end-of-hop handshake (NOT safe) */
+  int p2p_diag;             /* timing diagnostics (results invalid): 4 no pull, 8 no halo path in boundary CTAs, 16 natural slice order */
   /* fused finish of the DOT reduction (fin_op >= 0): the last of fin_total CTAs sums partial_base[0..fin_total) */
   tmb_cg_state *st_fin; const double *partial_base; int fin_op, fin_slot, fin_total;
 };

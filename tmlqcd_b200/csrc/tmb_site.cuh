@@ -71,6 +71,13 @@ __device__ __forceinline__ void tmb_st_stream(float2 *p, float2 v, unsigned long
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;"
                :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
+/* halo buffers of the peer mode: written early, read late -> ask L2 to keep them */
+__device__ __forceinline__ void tmb_st_keep(double2 *p, double2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" :: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tmb_st_keep(float2 *p, float2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ unsigned long long tmb_policy_evict_first() {
   unsigned long long pol;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -191,6 +198,23 @@ template <class V2> struct tmb_hop_fields {
   const V2 *halo_dn; /* dist_t: [6][S] (1-g0)-projected last slice of rank-1 */
   const V2 *Uhalo;   /* dist_t: [2][9|6][S] U_0 of rank-1's last slice, by owner parity */
 };
+
+/* Peer mode: element k in [0, 12 S) of the two halo buffers, PULLED out of the neighbours' copies of the input
+ * field (peer memory over NVLink, same layout as the local field): halo_up <- (1+g0) projection of rank+1's
+ * first time-slice, halo_dn <- (1-g0) projection of rank-1's last one (what pack_halo + send/recv deliver in
+ * the NCCL path).  k < 6 S: halo_up, else halo_dn. */
+template <class V2>
+TMB_HD void tmb_pull_halo_element(V2 *halo_up, V2 *halo_dn, const V2 *in_up, const V2 *in_dn, const tmb_geom &g, size_t k) {
+  const size_t half = (size_t)6 * g.S;
+  const bool up = k < half;
+  const size_t kk = up ? k : k - half;
+  const int c = (int)(kk / g.S), j = (int)(kk - (size_t)c * g.S);
+  if (up) halo_up[kk] = c_add(in_up[(size_t)c * g.Vh + j], in_up[(size_t)(c + 6) * g.Vh + j]);
+  else {
+    const size_t last = (size_t)(g.T - 1) * g.S + j;
+    halo_dn[kk] = c_sub(in_dn[(size_t)c * g.Vh + last], in_dn[(size_t)(c + 6) * g.Vh + last]);
+  }
+}
 
 /* 12-real gauge compression (the reference's CompressionType, misc_types.h:33-37, offered to its
  * external inverters): only the first two rows of an SU(3) link are stored and streamed, the third
