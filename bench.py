@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-sections", action="store_true", help="skip the configs[3] (ND doublet) and configs[4] (HMC monomials) sections")
     ap.add_argument("--loopback", action="store_true", help="1 GPU: run the T-split halo/boundary path against itself")
     ap.add_argument("--loopback2", action="store_true", help="1 GPU: run the T-split peer-mode path against itself")
     ap.add_argument("--sweep", action="store_true", help="time every kernel variant (tuning aid, prints to stderr)")
@@ -457,9 +458,18 @@ def main():
                 out["cg"]["cpu_reference_time_to_solution_s_est"] = cb["qtm_pm_psi_s"] * (out["cg"]["iterations"] + 1)
                 out["cg"]["cpu_reference_est_how"] = ("reference Qtm_pm_psi time per application x (iterations+1); "
                                                       "lower bound, BLAS-1 of cg_her not included")
+    dev.close()
+    # ---- BASELINE configs[3] and configs[4] on their own lattices, each in its own process (scripts/bench_sections.py) ----
+    if rank == 0 and world == 1 and not args.skip_sections:
+        for name in ("nd", "hmc"):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_sections.py"), name],
+                                   capture_output=True, text=True, timeout=600)
+                out[name] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-400:]}
+            except Exception as e:  # pragma: no cover
+                out[name] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out), file=real_stdout, flush=True)
-    dev.close()
     if dist is not None:
         dist.destroy_process_group()
 

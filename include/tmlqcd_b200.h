@@ -52,6 +52,7 @@ int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
 /* CompressionType of the reference (misc_types.h:33-37): 18 = full links (default), 12 = two rows streamed,
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);
+int tmb_set_host_chunks(int n); /* chunks of the pipelined host-pointer Hopping_Matrix (default 8, the measured best at 24^3x48) */
 int tmb_set_overlap(int flags); /* bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows */
 
 /* ---- memory ---- */

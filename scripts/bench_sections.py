@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""Extra measurement sections of bench.py, each on its own lattice in its own process (the reference keeps its
+lattice in C globals: one lattice per process), printing ONE JSON object on stdout.
+
+    python scripts/bench_sections.py nd  [TxLXxLYxLZ]   BASELINE configs[3]: invert_doublet_eo (Qtm_pm_ndpsi CG), 32^3x64
+    python scripts/bench_sections.py hmc [TxLXxLYxLZ]   BASELINE configs[4]: det + detratio monomials, 16^3x32
+                                                        (heatbath, derivative = inversion + deriv_Sb force, acc)
+
+GPU numbers: device-resident through the C ABI, wall clock around the call (the calls synchronise).  CPU numbers:
+the unmodified reference (oracle/_ref, half-spinor OpenMP build where the operator allows it) on all host cores,
+bounded samples.  Parameters: kappa = 0.16, mu = 0.01 (g_mu = 2 kappa mu), random SU(3) hot start; ND: 2KappaMubar =
+0.139, 2KappaEpsbar = 0.15 (sample-input/sample-cg.input:32-33); HMC: det with 2KappaMu = 0.032 (heavier), detratio
+(0.0032 / 0.032), CG, forceprec 1e-14, accprec 1e-18, csg history 2.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+KAPPA, MU = 0.16, 0.01
+GMU = 2 * KAPPA * MU
+CG = 1
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def gauge_and_ref(dims, nthreads, halfspinor):
+    """reference ranlux hot start when oracle/_ref is there (also the CPU baseline object), else numpy QR"""
+    from oracle import refclient
+    if refclient.available(halfspinor=halfspinor):
+        ref = refclient.Reference(*dims, nthreads=nthreads, halfspinor=halfspinor)
+        return ref.random_gauge(123456), ref, "reference ranlux random_gauge_field(seed 123456)"
+    from conftest import random_gauge
+    V = int(np.prod(dims))
+    return random_gauge(np.random.default_rng(123456), V), None, "numpy QR random SU(3) (seed 123456)"
+
+
+def section_nd(dims):
+    import tmlqcd_b200 as tm
+    from conftest import random_spinor
+    ncores = os.cpu_count() or 1
+    g, ref, how = gauge_and_ref(dims, ncores, True)
+    mubar, epsbar = 0.139, 0.15
+    d = tm.Device(*dims)
+    d.set_params(KAPPA, GMU)
+    d.ck(d.lib.tmb_set_nd(mubar, epsbar, 1.0))
+    d.gauge_upload(g)
+    rng = np.random.default_rng(5)
+    src = [random_spinor(rng, d.Vh) for _ in range(4)]
+    f = [d.field(s) for s in src] + [d.field() for _ in range(4)]
+    eps_sq, maxit = 1e-14, 5000
+    # operator alone: Qtm_pm_ndpsi = 8 hops + flavour mixing
+    d.call("Qtm_pm_ndpsi", f[4], f[5], f[0], f[1]); d.ck(d.lib.tmb_sync())
+    n = 20
+    t0 = time.perf_counter()
+    for _ in range(n):
+        d.call("Qtm_pm_ndpsi", f[4], f[5], f[0], f[1])
+    d.ck(d.lib.tmb_sync())
+    t_op = (time.perf_counter() - t0) / n
+    it = d.call("invert_doublet_eo", f[4], f[5], f[6], f[7], f[0], f[1], f[2], f[3], eps_sq, maxit, 1)  # warm-up
+    d.call("field_zero", f[5]); d.call("field_zero", f[7])
+    d.ck(d.lib.tmb_sync())
+    t0 = time.perf_counter()
+    it = d.call("invert_doublet_eo", f[4], f[5], f[6], f[7], f[0], f[1], f[2], f[3], eps_sq, maxit, 1)
+    d.ck(d.lib.tmb_sync())
+    t_solve = time.perf_counter() - t0
+    its, err, t_cg = d.solver_stats()
+    out = {"workload": "BASELINE configs[3]: invert_doublet_eo, non-degenerate doublet CG on Qtm_pm_ndpsi, %dx%dx%dx%d (TxLXxLYxLZ)" % dims,
+           "gauge": how, "2KappaMubar": mubar, "2KappaEpsbar": epsbar, "eps_sq": eps_sq, "rel_prec": 1,
+           "iterations": it, "time_to_solution_s": t_solve, "cg_loop_s": t_cg, "final_rr": err,
+           "Qtm_pm_ndpsi_us": 1e6 * t_op,
+           "Qtm_pm_ndpsi_hbm_gbs_at_8x1536_B_per_site": 8 * 1536.0 * d.Vh / t_op / 1e9,
+           "gflops_1320_per_hop": 8 * 1320.0 * d.Vh / t_op / 1e9}
+    d.close()
+    if ref is not None:
+        ref.set_params(KAPPA, GMU); ref.set_nd_params(mubar, epsbar, 1.0)
+        a, b = ref.spinor(), ref.spinor()
+        ref.Qtm_pm_ndpsi(a, b, src[0], src[1])
+        nrep = 2
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            ref.Qtm_pm_ndpsi(a, b, src[0], src[1])
+        t_ref = (time.perf_counter() - t0) / nrep
+        out["cpu_reference"] = {"Qtm_pm_ndpsi_s": t_ref, "cores": ref.nthreads, "kind": "reference",
+                                "sample": f"{nrep} applications of Qtm_pm_ndpsi, half-spinor OpenMP build of the unmodified reference",
+                                "time_to_solution_s_est": t_ref * (max(it, 0) + 1),
+                                "est_how": "Qtm_pm_ndpsi time x (iterations + 1); lower bound, BLAS-1 of cg_her_nd not included"}
+    return out
+
+
+def section_hmc(dims):
+    import tmlqcd_b200 as tm
+    from conftest import random_spinor
+    ncores = os.cpu_count() or 1
+    # half-spinor OpenMP build: the fastest generic-C variant of the CG's Hopping_Matrix; its deriv_Sb is the same code
+    g, ref, how = gauge_and_ref(dims, ncores, True)
+    forceprec, accprec, csgN, maxit = 1e-14, 1e-18, 2, 5000
+    mons = [(0, KAPPA, 10 * GMU, KAPPA, 10 * GMU), (1, KAPPA, GMU, KAPPA, 10 * GMU)]  # det(heavy), detratio(light/heavy)
+    d = tm.Device(*dims)
+    d.set_params(KAPPA, GMU)
+    d.gauge_upload(g)
+    d.ck(d.lib.tmb_set_relative_precision_flag(0))
+    rng = np.random.default_rng(11)
+    etas = [random_spinor(rng, d.Vh) for _ in mons]
+    out = {"workload": "BASELINE configs[4]: det + detratio monomials (heatbath, derivative = CG inversion + deriv_Sb force, acc), "
+                       "%dx%dx%dx%d (TxLXxLYxLZ), fields resident in HBM" % dims,
+           "gauge": how, "forceprec": forceprec, "accprec": accprec, "csg_N": csgN, "solver": "CG", "monomials": []}
+    V = d.V
+    # force kernel alone
+    l, k = d.field(etas[0]), d.field(etas[1])
+    d.call("derivative_zero"); d.call("deriv_Sb", 0, l, k, 1.0); d.ck(d.lib.tmb_sync())
+    n = 200
+    d.timer_start()
+    for _ in range(n):
+        d.lib.tmb_deriv_Sb(0, l, k, 1.0); d.lib.tmb_deriv_Sb(1, k, l, 1.0)
+    ms = d.timer_stop()
+    t_force = ms * 1e-3 / (2 * n)
+    out["deriv_Sb"] = {"us_per_call": 1e6 * t_force, "algorithmic_bytes_per_link_owner_site": 1280,
+                       "hbm_gbs_effective": 1280.0 * V / t_force / 1e9, "sites_per_call": V}
+    tot_gpu = 0.
+    for id, (typ, k1, m1, k2, m2) in enumerate(mons):
+        assert d.lib.tmb_monomial_add(typ, k1, m1, k2, m2, CG, maxit, forceprec, accprec, csgN) == id
+        eta = d.field(etas[id])
+        e0, dH = C.c_double(), C.c_double()
+        rec = {"type": "DET" if typ == 0 else "DETRATIO"}
+        d.ck(d.lib.tmb_sync()); t0 = time.perf_counter()
+        d.ck(d.lib.tmb_monomial_heatbath(id, eta, C.byref(e0)))
+        rec["heatbath_s"] = time.perf_counter() - t0
+        d.call("derivative_zero")
+        ts = []
+        for call in range(3):
+            d.ck(d.lib.tmb_sync()); t0 = time.perf_counter()
+            d.ck(d.lib.tmb_monomial_derivative(id))
+            ts.append(time.perf_counter() - t0)
+        rec["derivative_s"] = ts
+        d.ck(d.lib.tmb_sync()); t0 = time.perf_counter()
+        d.ck(d.lib.tmb_monomial_acc(id, C.byref(dH)))
+        rec["acc_s"] = time.perf_counter() - t0
+        rec.update(d.monomial_info(id)); rec["dH"] = dH.value
+        tot_gpu += rec["heatbath_s"] + sum(ts) + rec["acc_s"]
+        out["monomials"].append(rec)
+    out["total_s"] = tot_gpu
+    df_gpu = d.derivative_download()
+    d.close()
+    if ref is not None:
+        assert ref.hmc_init() == 0
+        ref.set_params(KAPPA, GMU)
+        ids = [ref.mnl_add(typ, k1, m1, k2, m2, CG, maxit, forceprec, accprec, csgN) for typ, k1, m1, k2, m2 in mons]
+        assert ref.mnl_init() == 0
+        tot = 0.
+        recs = []
+        for id in ids:
+            # the reference draws its own noise; the timing does not depend on which Gaussian field it is
+            ref.start_ranlux(1, 1000 + id)
+            t0 = time.perf_counter(); ref.mnl_heatbath(id); th = time.perf_counter() - t0
+            df = ref.derivative()
+            ts = []
+            for call in range(3):
+                t0 = time.perf_counter(); ref.mnl_derivative(id, df); ts.append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); ref.mnl_acc(id); ta = time.perf_counter() - t0
+            recs.append({"heatbath_s": th, "derivative_s": ts, "acc_s": ta, **ref.mnl_info(id)})
+            tot += th + sum(ts) + ta
+        out["cpu_reference"] = {"total_s": tot, "monomials": recs, "cores": ref.nthreads, "kind": "reference",
+                                "sample": "the same sequence (heatbath, 3 derivatives, acc per monomial) by the unmodified reference "
+                                          "(half-spinor OpenMP build: det_monomial.c, detratio_monomial.c, deriv_Sb.c, chrono_guess.c, cg_her.c)"}
+        out["speedup_vs_cpu_reference"] = tot / tot_gpu
+    out["derivative_norm"] = float(np.linalg.norm(df_gpu))
+    return out
+
+
+if __name__ == "__main__":
+    which = sys.argv[1]
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    if which == "nd":
+        dims = tuple(int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "64x32x32x32").split("x"))
+        res = section_nd(dims)
+    elif which == "hmc":
+        dims = tuple(int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "32x16x16x16").split("x"))
+        res = section_hmc(dims)
+    else:
+        raise SystemExit("usage: bench_sections.py nd|hmc [TxLXxLYxLZ]")
+    print(json.dumps(res), file=real_stdout, flush=True)

@@ -44,6 +44,10 @@ pg = np.array(hk)
 t = T("field_upload (pageable)", lambda: d.upload(f0, pg)); print(f"   -> {mb / t / 1e3:.1f} GB/s")
 T("drop-in Hopping_Matrix (first: gauge upload)", lambda: D.Hopping_Matrix(0, h2, hk), reps=1)
 t = T("drop-in Hopping_Matrix (pinned)", lambda: D.Hopping_Matrix(0, h2, hk)); print(f"   -> {mb / t / 1e3:.1f} GB/s each way")
+for nch in (4, 8, 16, 24, 48):
+    d.ck(d.lib.tmb_set_host_chunks(nch))
+    t = T(f"drop-in Hopping_Matrix (pinned), {nch} chunks", lambda: D.Hopping_Matrix(0, h2, hk)); print(f"   -> {mb / t / 1e3:.1f} GB/s each way")
+d.ck(d.lib.tmb_set_host_chunks(16))
 t = T("device Hopping_Matrix", lambda: d.lib.tmb_Hopping_Matrix(0, f1, f0))
 hk2 = pinned((d.Vh, 24)); hk2[:] = hk
 sp = tm.capi.SolverParams()

@@ -88,7 +88,7 @@ struct Ctx {
   std::vector<std::pair<size_t, size_t>> arena_free; /* (offset, bytes) */
   char *up_base = nullptr, *dn_base = nullptr;
   unsigned int *flags = nullptr, *up_flags = nullptr, *dn_flags = nullptr, *p2p_ticket = nullptr;
-  int *p2p_err = nullptr; unsigned int hop_seq = 0; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
+  int host_chunks = 8; int *p2p_err = nullptr; unsigned int hop_seq = 0; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
   /* HMC side (tmb_capi_hmc.inc) */
   double2 phase[4] = {{1., 0.}, {1., 0.}, {1., 0.}, {1., 0.}}; /* exp(i theta_mu pi / L_mu): ka_mu / kappa */
   double *df = nullptr;                       /* hf->derivative on the device, [2][4][8][Vh] */
@@ -396,6 +396,8 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   return 0;
 }
 /* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
+/* number of time-slice chunks of the pipelined host-pointer Hopping_Matrix (1..64) */
+extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 1 || n > MAXCHUNK) return fail(-7, "host chunks must be in [1, %d]", MAXCHUNK); C.host_chunks = n; return 0; }
 extern "C" int tmb_set_overlap(int flags) {
   NEED_INIT(); C.pdl = flags & 1; C.prefetch = (flags >> 1) & 1; C.cg_graph = (flags & 4) ? 0 : 1;
   C.p2p_diag = (flags >> 3) & 31; /* timing diagnostics only: 1 = boundary reads from the LOCAL field, 2 = no end-of-hop handshake */
@@ -646,7 +648,7 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
     TRY(hop(ieo, dout, din, o));
     return tmb_field_download(l_host, dout);
   }
-  int spc = (T + 15) / 16; if (spc < 1) spc = 1;
+  int spc = (T + C.host_chunks - 1) / C.host_chunks; if (spc < 1) spc = 1; /* time-slices per chunk */
   const int nchunk = (T + spc - 1) / spc;
   if (nchunk > MAXCHUNK) return fail(-13, "too many chunks");
   double2 *in_aos = C.stage, *out_aos = C.stage + (size_t)12 * Vh;
