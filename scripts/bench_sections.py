@@ -77,6 +77,10 @@ def section_nd(dims):
            "gauge": how, "2KappaMubar": mubar, "2KappaEpsbar": epsbar, "eps_sq": eps_sq, "rel_prec": 1,
            "iterations": it, "time_to_solution_s": t_solve, "cg_loop_s": t_cg, "final_rr": err,
            "Qtm_pm_ndpsi_us": 1e6 * t_op,
+           "Qtm_pm_ndpsi_algorithmic_bytes_per_site": 8448,
+           "Qtm_pm_ndpsi_bytes_how": "4 two-flavour launches: 2 x (1152 links + 4 x 192 spinors) + 2 x (1152 + 6 x 192); "
+                                     "the reference's call sequence (8 hops + 5 sweeps) moves 17664",
+           "Qtm_pm_ndpsi_hbm_gbs_effective": 8448.0 * d.Vh / t_op / 1e9,
            "Qtm_pm_ndpsi_hbm_gbs_at_8x1536_B_per_site": 8 * 1536.0 * d.Vh / t_op / 1e9,
            "gflops_1320_per_hop": 8 * 1320.0 * d.Vh / t_op / 1e9}
     d.close()

@@ -913,11 +913,32 @@ extern "C" int tmb_M_oo_sub_g5_ndpsi(void *ls, void *lc, const void *ks, const v
 }
 static int hop0(int ieo, double2 *l, const double2 *k) { HopOpt o; return hop(ieo, l, k, o); }
 
+/* Two-flavour fused path (single rank, 18-real links): every Hopping_Matrix pair of tm_operators_nd.c is ONE
+ * launch that streams the links once for both flavours, with M_ee_inv_ndpsi / M_oo_sub_g5_ndpsi and the
+ * phmc_invmaxev scaling in its epilogue.  mode 1: out = M_ee_inv_nd(H in0, H in1); mode 2: out = scale g5(M_oo(p) - H in). */
+static bool nd_fused() { return !C.dist && C.compression == 18; }
+static int hop2(int ieo, double2 *o0, double2 *o1, const double2 *i0, const double2 *i1, int mode, const double2 *p0,
+                const double2 *p1, double mu, double eps, double scale) {
+  if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
+  if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
+  tmb_hop2_launch a;
+  memset(&a, 0, sizeof(a));
+  a.in0 = i0; a.in1 = i1; a.out0 = o0; a.out1 = o1; a.p0 = p0; a.p1 = p1; a.U = C.U; a.g = C.g; a.par = ieo ? 1 : 0;
+  for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
+  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = C.hints;
+  KL(tmb_launch_hop2(a, C.s_main));
+  return 0;
+}
+
 /* tm_operators_nd.c:68-89 */
 extern "C" int tmb_Qtm_ndpsi(void *ls_, void *lc_, const void *ks_, const void *kc_) {
   NEED_INIT();
   double2 *ls = F(ls_), *lc = F(lc_); const double2 *ks = F(ks_), *kc = F(kc_);
   SCR(s0, 6); SCR(s1, 7); SCR(s2, 8); SCR(s3, 9);
+  if (nd_fused()) {
+    TRY(hop2(0, s3, s2, ks, kc, 1, nullptr, nullptr, C.mubar, C.epsbar, 1.));
+    return hop2(1, ls, lc, s3, s2, 2, ks, kc, -C.mubar, -C.epsbar, C.invmaxev);
+  }
   TRY(hop0(0, s0, ks)); TRY(hop0(0, s1, kc));
   KL(tmb_launch_nd_mee_inv(s3, s2, s0, s1, C.mubar, C.epsbar, N2(), HALF(), C.s_main));
   TRY(hop0(1, ls, s3)); TRY(hop0(1, lc, s2));
@@ -931,6 +952,10 @@ extern "C" int tmb_Qtm_dagger_ndpsi(void *ls_, void *lc_, const void *ks_, const
   NEED_INIT();
   double2 *ls = F(ls_), *lc = F(lc_); const double2 *ks = F(ks_), *kc = F(kc_);
   SCR(s0, 6); SCR(s1, 7); SCR(s2, 8); SCR(s3, 9);
+  if (nd_fused()) {
+    TRY(hop2(0, s2, s3, kc, ks, 1, nullptr, nullptr, C.mubar, C.epsbar, 1.));
+    return hop2(1, ls, lc, s3, s2, 2, ks, kc, C.mubar, -C.epsbar, C.invmaxev);
+  }
   TRY(hop0(0, s0, kc)); TRY(hop0(0, s1, ks));
   KL(tmb_launch_nd_mee_inv(s2, s3, s0, s1, C.mubar, C.epsbar, N2(), HALF(), C.s_main));
   TRY(hop0(1, s0, s2)); TRY(hop0(1, s1, s3));
@@ -942,6 +967,13 @@ extern "C" int tmb_Qtm_dagger_ndpsi(void *ls_, void *lc_, const void *ks_, const
 /* tm_operators_nd.c:195-238 */
 static int qtm_pm_nd(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc) {
   SCR(s0, 6); SCR(s1, 7); SCR(s2, 8); SCR(s3, 9); SCR(s4, 10); SCR(s5, 11);
+  if (nd_fused()) { /* 4 launches, 8448 B/site instead of 8 hops + 5 sweeps, 17.7 kB/site */
+    double2 *a0 = s0, *a1 = s1, *b0 = s2, *b1 = s3;
+    TRY(hop2(0, a0, a1, kc, ks, 1, nullptr, nullptr, C.mubar, C.epsbar, 1.));            /* A = Mee^-1 H_eo (kc, ks) */
+    TRY(hop2(1, b0, b1, a0, a1, 2, kc, ks, -C.mubar, -C.epsbar, 1.));                   /* B = g5(Moo(kc,ks) - H_oe A): tau1 Qhat tau1 */
+    TRY(hop2(0, a0, a1, b0, b1, 1, nullptr, nullptr, -C.mubar, C.epsbar, 1.));          /* A = (s5, s4) */
+    return hop2(1, ls, lc, a1, a0, 2, b1, b0, -C.mubar, -C.epsbar, C.invmaxev * C.invmaxev);
+  }
   TRY(hop0(0, s0, kc)); TRY(hop0(0, s1, ks));
   KL(tmb_launch_nd_mee_inv(s2, s3, s0, s1, C.mubar, C.epsbar, N2(), HALF(), C.s_main));
   TRY(hop0(1, s0, s2)); TRY(hop0(1, s1, s3));

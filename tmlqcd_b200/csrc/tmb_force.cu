@@ -76,3 +76,58 @@ cudaError_t tmb_launch_unpack_deriv(double *lex, const double *dev, tmb_geom g, 
   unpack_deriv_kernel<<<lin_grid((size_t)64 * g.Vh), 256, 0, s>>>(lex, dev, g, add);
   return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------ two-flavour hopping kernel
+ * (lives in this translation unit to keep tmb_kernels.cu's compile time down) */
+template <int MODE, int HINTS>
+__global__ void __launch_bounds__(128, 2) hop2_kernel(const tmb_hop2_launch a) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= a.g.Vh) return;
+  tmb_policies pol;
+  pol.stream = tmb_policy_evict_first();
+  pol.reuse = tmb_policy_evict_last();
+  double2 r0[12], r1[12];
+  tmb_hop_site2<HINTS>(r0, r1, (const double2 *)a.in0, (const double2 *)a.in1, (const double2 *)a.U, a.g, a.par, i, a.ka, pol);
+  double2 *o0 = (double2 *)a.out0, *o1 = (double2 *)a.out1;
+  const size_t Vh = a.g.Vh;
+  if (MODE == 1) {
+    const double nrm = 1. / (1. + a.mu * a.mu - a.eps * a.eps);
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      double2 ls, lc;
+      tmb_nd_mee_inv_regs(ls, lc, r0[c], r1[c], c, a.mu, a.eps, nrm);
+      r0[c] = ls; r1[c] = lc;
+    }
+  } else if (MODE == 2) {
+    const double2 *p0 = (const double2 *)a.p0, *p1 = (const double2 *)a.p1;
+    double2 q0[12], q1[12]; /* all operand loads before the first store: out may alias p (see hop_kernel) */
+#pragma unroll
+    for (int c = 0; c < 12; c++) { q0[c] = p0[c * Vh + i]; q1[c] = p1[c * Vh + i]; }
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      const bool up = c < 6;
+      const double2 zs = make_double2(1., up ? -a.mu : a.mu), zc = c_conj(zs);
+      double2 x = c_mul(zs, q0[c]); x.x += a.eps * q1[c].x; x.y += a.eps * q1[c].y;
+      double2 y = c_mul(zc, q1[c]); y.x += a.eps * q0[c].x; y.y += a.eps * q0[c].y;
+      const double2 d0 = up ? c_sub(x, r0[c]) : c_sub(r0[c], x), d1 = up ? c_sub(y, r1[c]) : c_sub(r1[c], y);
+      r0[c] = make_double2(a.scale * d0.x, a.scale * d0.y); r1[c] = make_double2(a.scale * d1.x, a.scale * d1.y);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 12; c++) {
+    tmb_store_out<HINTS & 1>(o0 + c * Vh + i, r0[c], pol);
+    tmb_store_out<HINTS & 1>(o1 + c * Vh + i, r1[c], pol);
+  }
+}
+template <int HINTS>
+static cudaError_t hop2_go(const tmb_hop2_launch &a, cudaStream_t s) {
+  const int grid = (a.g.Vh + 127) / 128;
+  switch (a.mode) {
+    case 0: hop2_kernel<0, HINTS><<<grid, 128, 0, s>>>(a); break;
+    case 1: hop2_kernel<1, HINTS><<<grid, 128, 0, s>>>(a); break;
+    case 2: hop2_kernel<2, HINTS><<<grid, 128, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_hop2(const tmb_hop2_launch &a, cudaStream_t s) { return a.hints ? hop2_go<1>(a, s) : hop2_go<0>(a, s); }

@@ -146,3 +146,16 @@ cudaError_t tmb_launch_pack_deriv_halo(double2 *out, const double2 *k, const dou
 /* hf->derivative host layout [ix][mu][8] (init/init_moment_field.c:62-80) <-> device [2][4][8][Vh]; mode 0: set, 1: add */
 cudaError_t tmb_launch_pack_deriv(double *dev, const double *lex, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_unpack_deriv(double *lex, const double *dev, tmb_geom g, int add, cudaStream_t s);
+
+/* ---- two-flavour hopping (non-degenerate doublet): one gauge stream for both flavours ----
+ * mode 0: (out0, out1) = (H in0, H in1)
+ * mode 1: (out0, out1) = M_ee_inv_nd(H in0, H in1; mu, eps) with the flavour roles as tmb_launch_nd_mee_inv:
+ *         out0 = "ls" from (ks = H in0, kc = H in1)
+ * mode 2: (out0, out1) = g5( M_oo(p0, p1; mu, eps) - (H in0, H in1) ), the M_oo_sub_g5_ndpsi epilogue (:698-756),
+ *         then scaled by `scale` */
+struct tmb_hop2_launch {
+  const void *in0, *in1; void *out0, *out1; const void *p0, *p1; const void *U;
+  tmb_geom g; int par; double2 ka[4];
+  int mode; double mu, eps, scale; int hints;
+};
+cudaError_t tmb_launch_hop2(const tmb_hop2_launch &a, cudaStream_t s);

@@ -284,6 +284,51 @@ TMB_HD void tmb_hop_site(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_geom &
   tmb_hop_dir<7, HINTS>(r, f, g, par, i, nb[7], ka[3], pol);
 }
 
+/* Two right-hand sides at once (the two flavours of the non-degenerate doublet, operator/tm_operators_nd.c:
+ * every Hopping_Matrix there is applied to a strange and a charm field with the same links): each link is
+ * loaded ONCE and applied to both projected spinors, so the 1152 B/site gauge stream is shared:
+ * 1920 B per site-pair instead of 2 x 1536. */
+template <int D, int CFG, class V2>
+TMB_HD void tmb_hop_dir2(V2 r0[12], V2 r1[12], const V2 *in0, const V2 *in1, const V2 *U, const tmb_geom &g, int par, int i,
+                         int n, V2 ka, const tmb_policies &pol) {
+  const int mu = D >> 1, BWD = D & 1, HINTS = CFG & 1, NE = (CFG & 2) ? 6 : 9;
+  V2 a[3], b[3], u[9];
+  const V2 *ub = U + (size_t)(((BWD ? 1 - par : par) * 4 + mu) * NE) * g.Vh + (BWD ? n : i);
+#pragma unroll
+  for (int e = 0; e < NE; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
+  if (NE == 6) tmb_reconstruct_row2(u);
+  tmb_project<D, HINTS>(a, b, in0, g.Vh, n, pol);
+  tmb_link_accumulate<D>(r0, u, a, b, ka);
+  tmb_project<D, HINTS>(a, b, in1, g.Vh, n, pol);
+  tmb_link_accumulate<D>(r1, u, a, b, ka);
+}
+template <int CFG, class V2>
+TMB_HD void tmb_hop_site2(V2 r0[12], V2 r1[12], const V2 *in0, const V2 *in1, const V2 *U, const tmb_geom &g, int par, int i,
+                          const V2 ka[4], const tmb_policies &pol) {
+  int nb[8];
+  tmb_neighbours(g, par, i, nb);
+#pragma unroll
+  for (int c = 0; c < 12; c++) { r0[c] = mk2<V2>(0, 0); r1[c] = mk2<V2>(0, 0); }
+  tmb_hop_dir2<0, CFG>(r0, r1, in0, in1, U, g, par, i, nb[0], ka[0], pol);
+  tmb_hop_dir2<1, CFG>(r0, r1, in0, in1, U, g, par, i, nb[1], ka[0], pol);
+  tmb_hop_dir2<2, CFG>(r0, r1, in0, in1, U, g, par, i, nb[2], ka[1], pol);
+  tmb_hop_dir2<3, CFG>(r0, r1, in0, in1, U, g, par, i, nb[3], ka[1], pol);
+  tmb_hop_dir2<4, CFG>(r0, r1, in0, in1, U, g, par, i, nb[4], ka[2], pol);
+  tmb_hop_dir2<5, CFG>(r0, r1, in0, in1, U, g, par, i, nb[5], ka[2], pol);
+  tmb_hop_dir2<6, CFG>(r0, r1, in0, in1, U, g, par, i, nb[6], ka[3], pol);
+  tmb_hop_dir2<7, CFG>(r0, r1, in0, in1, U, g, par, i, nb[7], ka[3], pol);
+}
+/* M_ee_inv_ndpsi in registers (tm_operators_nd.c:639-695): (ls, lc) = nrm [ (1 -+ i mu) ks + eps kc , (1 +- i mu) kc + eps ks ],
+ * upper sign on s0,s1 (c < 6), lower on s2,s3 */
+template <class V2>
+TMB_HD void tmb_nd_mee_inv_regs(V2 &ls, V2 &lc, V2 ks, V2 kc, int c, double mu, double eps, double nrm) {
+  typedef typename tmb_real<V2>::type R;
+  const V2 zs = mk2<V2>((R)1, (R)((c < 6) ? -mu : mu)), zc = c_conj(zs);
+  V2 a = c_mul(zs, ks); a.x += (R)eps * kc.x; a.y += (R)eps * kc.y;
+  V2 b = c_mul(zc, kc); b.x += (R)eps * ks.x; b.y += (R)eps * ks.y;
+  ls = mk2<V2>((R)nrm * a.x, (R)nrm * a.y); lc = mk2<V2>((R)nrm * b.x, (R)nrm * b.y);
+}
+
 /* Epilogues (hopping.h:674-694):
  *   MODE 0  l = r                                   _store_res                 Hopping_Matrix
  *   MODE 1  l = (cf on s0,s1 | conj(cf) on s2,s3) r _hop_mul_g5_cmplx_and_store tm_times_Hopping_Matrix
