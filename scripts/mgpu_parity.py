@@ -65,6 +65,36 @@ def main():
     dE, dO, dEn, dOn = d.field(k[slh]), d.field(p[slh]), d.field(), d.field()
     it2 = d.call("invert_eo", dEn, dOn, dE, dO, 1e-22, 2000, 1)
     res["inv_e"], res["inv_o"] = gather(dEn), gather(dOn)
+    # mixed-precision solvers (float hops through the same halo machinery)
+    itm = d.call("mixed_cg_her", dx, dk, 2000, 1e-22, 1); res["mcg_x"] = gather(dx)
+    itg = d.call("rg_mixed_cg_her", dx, dk, 2000, 1e-22, 1); res["rg_x"] = gather(dx)
+    # non-degenerate doublet
+    d.ck(d.lib.tmb_set_nd(0.139, 0.15, 0.9))
+    dls, dlc = d.field(), d.field()
+    d.call("Qtm_pm_ndpsi", dls, dlc, dk, dp); res["nd_s"], res["nd_c"] = gather(dls), gather(dlc)
+    d.call("field_zero", dls); d.call("field_zero", dlc)
+    itn = d.call("cg_her_nd", dls, dlc, dk, dp, 2000, 1e-20, 1); res["cgnd_s"], res["cgnd_c"] = gather(dls), gather(dlc)
+    # fermion force and a det monomial with chronological guess (deriv_Sb exchanges the projected first slices)
+
+    def gather_df():
+        loc = torch.from_numpy(d.derivative_download()).cuda()
+        out = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(out, loc)
+        return torch.cat(out).cpu().numpy()
+    d.call("derivative_zero")
+    d.call("deriv_Sb", 0, dk, dp, 0.7); d.call("deriv_Sb", 1, dp, dk, -0.4)
+    res["df"] = gather_df()
+    margs = (0, 0.15, 0.01, 0.15, 0.05, 1, 3000, 1e-20, 1e-22, 2)
+    assert d.lib.tmb_monomial_add(*margs) == 0
+    e0 = C.c_double()
+    d.ck(d.lib.tmb_monomial_heatbath(0, dk, C.byref(e0)))
+    d.call("derivative_zero")
+    for _ in range(2):
+        d.ck(d.lib.tmb_monomial_derivative(0))
+    res["mnl_df"] = gather_df()
+    dH = C.c_double(); d.ck(d.lib.tmb_monomial_acc(0, C.byref(dH)))
+    minfo = d.monomial_info(0)
+    d.set_params(KAPPA, GMU, THETA)
     ok = True
     if rank == 0:
         o = Oracle(T, LX, LY, LZ)
@@ -81,6 +111,25 @@ def main():
         en, on = o.spinor(), o.spinor(); itr = o.invert_eo_cg(en, on, k, p, 1e-22, 2000, 1)
         r1, r2 = rel_l2(res["inv_e"], en), rel_l2(res["inv_o"], on)
         print(f"invert_eo iters {it2} (oracle {itr}) rel {r1:.2e} {r2:.2e}"); ok &= abs(it2 - itr) <= 1 and max(r1, r2) <= 1e-10
+        r1, r2 = rel_l2(res["mcg_x"], x), rel_l2(res["rg_x"], x)
+        print(f"mixed_cg_her count {itm}, rg_mixed_cg_her count {itg}: x rel {r1:.2e} {r2:.2e}"); ok &= itm > 0 and itg > 0 and max(r1, r2) <= 1e-8
+        o.set_nd_params(0.139, 0.15, 0.9)
+        es, ec = o.spinor(), o.spinor(); o.Qtm_pm_ndpsi(es, ec, k, p)
+        r1, r2 = rel_l2(res["nd_s"], es), rel_l2(res["nd_c"], ec); print(f"Qtm_pm_ndpsi rel {r1:.2e} {r2:.2e}"); ok &= max(r1, r2) <= 1e-13
+        es[:] = 0; ec[:] = 0; itr = o.cg_her_nd(es, ec, k, p, 2000, 1e-20, 1)
+        r1, r2 = rel_l2(res["cgnd_s"], es), rel_l2(res["cgnd_c"], ec)
+        print(f"cg_her_nd iters {itn} (oracle {itr}) rel {r1:.2e} {r2:.2e}"); ok &= abs(itn - itr) <= 1 and max(r1, r2) <= 1e-9
+        df = o.derivative(); o.deriv_Sb(0, k, p, df, 0.7); o.deriv_Sb(1, p, k, df, -0.4)
+        r = rel_l2(res["df"], df); print(f"deriv_Sb rel {r:.2e}"); ok &= r <= 1e-13
+        o.mnl_clear(); assert o.mnl_add(*margs) == 0
+        e0r = o.mnl_heatbath(0, k); dfo = o.derivative()
+        for _ in range(2):
+            o.mnl_derivative(0, dfo)
+        dHr = o.mnl_acc(0); oinfo = o.mnl_info(0)
+        r = rel_l2(res["mnl_df"], dfo)
+        print(f"det monomial: energy0 rel {abs(e0.value / e0r - 1):.2e}, derivative rel {r:.2e}, iter1 {minfo['iter1']} (oracle {oinfo['iter1']}), "
+              f"dH {dH.value:.2e} (oracle {dHr:.2e})")
+        ok &= abs(e0.value / e0r - 1) <= 1e-13 and r <= 1e-8 and abs(minfo["iter1"] - oinfo["iter1"]) <= 3 and abs(dH.value - dHr) <= 1e-7
         print("MGPU PARITY", "OK" if ok else "FAILED", f"world={world} global={T}x{LX}x{LY}x{LZ}")
     d.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
