@@ -205,3 +205,64 @@ def test_monomials_vs_oracle_loopback(oracle_lib):
         o.mnl_clear()
     finally:
         d.close()
+
+
+def test_full_size_force_and_doublet_properties(oracle_lib):
+    """BASELINE sizes: deriv_Sb at 24^3x48 (linearity, anti-symmetry of the accumulation, oracle on the full lattice),
+    the fused two-flavour Qtm_pm_ndpsi against the unfused composition (T-split loopback path) at 32^3x64,
+    hermiticity / positivity of Qtm_pm_ndpsi and a cg_her_nd solve checked by its true residual."""
+    import tmlqcd_b200 as tm
+    dims = (48, 24, 24, 24)
+    rng = np.random.default_rng(9)
+    V = int(np.prod(dims)); Vh = V // 2
+    g = random_gauge(rng, V)
+    d = tm.Device(*dims)
+    try:
+        d.set_params(KAPPA, GMU, (1., 0., 0., 0.))
+        d.gauge_upload(g)
+        l1, l2, k = (random_spinor(rng, Vh) for _ in range(3))
+        dl1, dl2, dk, ds = d.field(l1), d.field(l2), d.field(k), d.field(l1 + 0.5 * l2)
+
+        def force(ieo, fl, fk, factor):
+            d.call("derivative_zero"); d.call("deriv_Sb", ieo, fl, fk, factor); return d.derivative_download()
+        f1, f2, fs = force(0, dl1, dk, 1.0), force(0, dl2, dk, 1.0), force(0, ds, dk, 1.0)
+        assert rel_l2(fs, f1 + 0.5 * f2) <= TOL                      # anti-linear in l ... with real coefficients: linear
+        d.call("deriv_Sb", 0, ds, dk, -1.0)                           # accumulates: the same call with -factor cancels
+        assert np.abs(d.derivative_download()).max() <= 1e-12 * np.abs(fs).max()
+        o = oracle_lib.Oracle(*dims)
+        o.set_gauge(g); o.set_params(KAPPA, GMU, (1., 0., 0., 0.))
+        exp = o.derivative(); o.deriv_Sb(0, l1, k, exp, 1.0)
+        assert rel_l2(f1, exp) <= TOL
+    finally:
+        d.close()
+    dims = (64, 32, 32, 32)
+    V = int(np.prod(dims)); Vh = V // 2
+    g = random_gauge(rng, V)
+    d = tm.Device(*dims)
+    try:
+        d.set_params(KAPPA, GMU)
+        d.ck(d.lib.tmb_set_nd(0.139, 0.15, 0.9))
+        d.gauge_upload(g)
+        a, b = random_spinor(rng, Vh), random_spinor(rng, Vh)
+        da, db, ls, lc, ms, mc = d.field(a), d.field(b), d.field(), d.field(), d.field(), d.field()
+        d.call("Qtm_pm_ndpsi", ls, lc, da, db)
+        fused = d.download(ls), d.download(lc)
+        lhs = d.reduce("scalar_prod_r", da, ls) + d.reduce("scalar_prod_r", db, lc)
+        assert lhs > 0                                                # positive
+        d.call("Qtm_pm_ndpsi", ms, mc, db, da)                        # hermitian: <(b,a), Q (a,b)> == <Q (b,a), (a,b)>
+        x = d.reduce("scalar_prod_r", db, ls) + d.reduce("scalar_prod_r", da, lc)
+        y = d.reduce("scalar_prod_r", ms, da) + d.reduce("scalar_prod_r", mc, db)
+        assert abs(x - y) <= 1e-11 * abs(lhs)
+        # cg_her_nd: true residual by the operator itself
+        d.call("field_zero", ms); d.call("field_zero", mc)
+        it = d.call("cg_her_nd", ms, mc, da, db, 5000, 1e-16, 1)
+        assert it > 0
+        d.call("Qtm_pm_ndpsi", ls, lc, ms, mc)
+        rr = np.sum((d.download(ls) - a) ** 2) + np.sum((d.download(lc) - b) ** 2)
+        assert rr <= 4e-16 * (np.sum(a ** 2) + np.sum(b ** 2))
+        # the same operator through the unfused composition (8 hops + sweeps: what the T-split path runs)
+        d.ck(d.lib.tmb_comm_loopback(1)); d.gauge_upload(g)
+        d.call("Qtm_pm_ndpsi", ls, lc, da, db)
+        assert rel_l2(d.download(ls), fused[0]) <= TOL and rel_l2(d.download(lc), fused[1]) <= TOL
+    finally:
+        d.close()

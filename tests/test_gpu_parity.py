@@ -33,7 +33,7 @@ def _setup(oracle_lib, dims, theta, seed=7):
 
 
 CASES = [((4, 4, 4, 4), (0., 0., 0., 0.)), ((8, 4, 6, 8), (1., 0.3, 0., 0.7)), ((6, 10, 2, 6), (1., 0., 0., 0.)),
-         ((8, 8, 8, 8), (0., 0., 0., 0.))]
+         ((8, 8, 8, 8), (0., 0., 0., 0.)), ((2, 6, 4, 4), (1., 0., 0.5, 0.))]  # last: T = 2, every slice is a boundary slice
 
 
 @pytest.mark.parametrize("dims,theta", CASES)
