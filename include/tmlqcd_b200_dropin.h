@@ -219,6 +219,37 @@ void detratio_heatbath(const int id, hamiltonian_field_t *const hf);
 double detratio_acc(const int id, hamiltonian_field_t *const hf);
 void detratio_derivative(const int id, hamiltonian_field_t *const hf);
 
+/* ---- gauge configurations and propagator files: ILDG / SciDAC records in LIME containers.
+ *      Types: io/dml.h (DML_Checksum), io/params.h:78-104 (paramsXlfInfo, paramsGaugeInfo). ---- */
+typedef struct { unsigned int suma, sumb; } DML_Checksum;
+typedef struct {
+  char date[64];
+  char package_version[32];
+  double beta, c2_rec, epsilonbar, kappa, mu, mubar, plaq;
+  int counter;
+  long int time;
+} paramsXlfInfo;
+typedef struct {
+  double plaquetteEnergy;
+  int gaugeRead;
+  DML_Checksum checksum;
+  char *xlfInfo;
+  char *ildg_data_lfn;
+} tmb_gauge_info; /* = paramsGaugeInfo */
+extern tmb_gauge_info GaugeInfo;          /* io/gauge_read.c:28 */
+extern int gauge_precision_read_flag;     /* read_input.h:69: 64 or 32 */
+extern int g_disable_IO_checks;           /* global.h:77 */
+extern double g_beta, g_rgi_C1;           /* global.h: only printed into xlf-info */
+/* io/params_construct_xlfInfo.c; io/gauge.h:32,:35 */
+paramsXlfInfo *construct_paramsXlfInfo(double const plaq, int const counter);
+int read_gauge_field(char *filename, su3 **const gf);
+int write_gauge_field(char *filename, int prec, paramsXlfInfo const *xlfInfo);
+/* io/spinor.h:28 (even/odd pair, position-th scidac-binary-data record of the file) */
+int read_spinor(spinor *const s, spinor *const r, char *filename, const int position);
+/* the records op_write_prop (operator.c:532-605) writes for one flavour, PropInfo.format == 0 */
+int tmb_write_propagator(const char *filename, spinor *const s, spinor *const r, int prec, double epssq, int iter,
+                         const char *solver_name, int append);
+
 /* ---- include/tmLQCD.h:37-59, wrapper/lib_wrapper.c:77-370 ---- */
 typedef struct { unsigned int LX, LY, LZ, T, nstore, nsave, no_operators; } tmLQCD_lat_params;
 typedef struct {
@@ -239,5 +270,8 @@ int tmLQCD_b200_set_lattice(int t, int lx, int ly, int lz);
 int tmLQCD_b200_add_operator(double kappa, double two_kappa_mu, double eps_sq, int max_iter, int rel_prec);
 int tmLQCD_b200_set_theta(double x0, double x1, double x2, double x3);
 int tmLQCD_b200_get_solver_info(int op_id, int *iterations, double *reached_prec);
+/* GaugeConfigInputFile (default "conf", default_input_values.h:91) and the propagator output of
+ * tmLQCD_invert(..., write_prop != 0): basename (default "source", :93) and precision (default 32, :126) */
+int tmLQCD_b200_set_io(const char *gauge_input_filename, const char *prop_basename, int prop_precision);
 
 #endif /* TMLQCD_B200_DROPIN_H */

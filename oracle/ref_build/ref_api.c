@@ -436,3 +436,43 @@ int ref_rg_mixed_cg_her(double *p, double *q, int max_iter, double eps_sq, int r
   sp.mcg_delta = (float)delta;
   return rg_mixed_cg_her((spinor *)p, (spinor *)q, sp, max_iter, eps_sq, rel_prec, VOLUME / 2, &Qtm_pm_psi, &Qtm_pm_psi_32);
 }
+
+/* ---- gauge / propagator files: the reference's unmodified io/ code over the stand-in
+ *      LIME layer (stubs/lime.h) ---- */
+#include "io/gauge.h"
+#include "io/spinor.h"
+#include "io/params.h"
+#include "io/utils.h"
+#include "solver/solver_types.h"
+extern int gauge_precision_read_flag; /* read_input.h:69, defined in ref_shim.c */
+int ref_write_gauge(const char *filename, int prec, double plaq, int counter) {
+  paramsXlfInfo *xlf = construct_paramsXlfInfo(plaq, counter);
+  int st = write_gauge_field((char *)filename, prec, xlf);
+  free(xlf);
+  return st;
+}
+int ref_read_gauge(const char *filename, int prec) {
+  gauge_precision_read_flag = prec;
+  int st = read_gauge_field((char *)filename, g_gauge_field);
+  g_update_gauge_copy = 1;
+  return st;
+}
+/* what op_write_prop (operator.c:532-605) writes for one flavour with PropInfo.format == 0 */
+int ref_write_propagator(const char *filename, double *even, double *odd, int prec, double epssq, int iter) {
+  WRITER *writer = NULL;
+  spinor *s = (spinor *)even, *r = (spinor *)odd;
+  construct_writer(&writer, (char *)filename, 0);
+  write_propagator_type(writer, 0);
+  paramsInverterInfo *info = construct_paramsInverterInfo(epssq, iter, CG, 1);
+  write_spinor_info(writer, 0, info, 0);
+  free(info);
+  paramsPropagatorFormat *fmt = construct_paramsPropagatorFormat(prec, 1);
+  write_propagator_format(writer, fmt);
+  free(fmt);
+  int st = write_spinor(writer, &s, &r, 1, prec);
+  destruct_writer(writer);
+  return st;
+}
+int ref_read_spinor(double *even, double *odd, const char *filename, int position) {
+  return read_spinor((spinor *)even, (spinor *)odd, (char *)filename, position);
+}

@@ -13,6 +13,8 @@ int even_odd_flag = 1;
 int bc_flag = 0;
 int usegpu_flag = 0;
 int use_preconditioning = 0;
+int Nmeas = 1, Nsave = 1;          /* read_input.h: only printed into xlf-info style records */
+int gauge_precision_read_flag = 64; /* read_input.h:69, GaugeConfigReadPrecision */
 #ifndef TM_USE_OMP
 int omp_num_threads = 1;
 #endif

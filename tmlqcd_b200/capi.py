@@ -167,6 +167,10 @@ DROPIN_API = {
     "det_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
     "detratio_heatbath": (None, [_i, C.POINTER(HamiltonianField)]), "detratio_acc": (_d, [_i, C.POINTER(HamiltonianField)]),
     "detratio_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
+    "construct_paramsXlfInfo": (_vp, [_d, _i]), "read_gauge_field": (_i, [C.c_char_p, _vp]),
+    "write_gauge_field": (_i, [C.c_char_p, _i, _vp]), "read_spinor": (_i, [_sp, _sp, C.c_char_p, _i]),
+    "tmb_write_propagator": (_i, [C.c_char_p, _sp, _sp, _i, _d, _i, C.c_char_p, _i]),
+    "tmLQCD_b200_set_io": (_i, [C.c_char_p, C.c_char_p, _i]),
     "tmLQCD_invert_init": (_i, [_i, _vp, _i, _i]), "tmLQCD_read_gauge": (_i, [_i]),
     "tmLQCD_invert": (_i, [_sp, _sp, _i, _i]), "tmLQCD_finalise": (_i, []),
     "tmLQCD_get_gauge_field_pointer": (_i, [C.POINTER(C.POINTER(_d))]),
@@ -177,7 +181,8 @@ DROPIN_API = {
 DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND", "g_update_gauge_copy", "g_proc_id",
                   "g_debug_level", "g_nproc", "g_nproc_t", "g_kappa", "g_mu", "g_mubar", "g_epsbar", "phmc_invmaxev",
                   "X0", "X1", "X2", "X3", "ka0", "ka1", "ka2", "ka3", "phase_0", "phase_1", "phase_2", "phase_3",
-                  "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit", "g_relative_precision_flag"]
+                  "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit", "g_relative_precision_flag",
+                  "GaugeInfo", "gauge_precision_read_flag", "g_disable_IO_checks", "g_beta", "g_rgi_C1"]
 
 _SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed",
             "rg_mixed_cg_her", "solve_degenerate"}

@@ -465,13 +465,30 @@ int tmLQCD_invert_init(int argc, char *argv[], const int verbose, const int exte
   facade_up = 1;
   return 0;
 }
+static char gauge_input_filename[500] = "conf"; /* default_input_values.h:91 */
+static char prop_basename[400] = "source";      /* default_input_values.h:93 */
+static int prop_precision = 32, nstore = 0;     /* default_input_values.h:126, :89 */
+int tmLQCD_b200_set_io(const char *gauge_file, const char *prop_base, int prec) {
+  if (gauge_file) { strncpy(gauge_input_filename, gauge_file, sizeof(gauge_input_filename) - 1); }
+  if (prop_base) { strncpy(prop_basename, prop_base, sizeof(prop_basename) - 1); }
+  if (prec == 32 || prec == 64) prop_precision = prec;
+  return 0;
+}
+/* wrapper/lib_wrapper.c:203-239: "<GaugeConfigInputFile>.<nconfig, 4 digits>" through read_gauge_field */
 int tmLQCD_read_gauge(const int nconfig) {
-  (void)nconfig;
+  char conf_filename[600];
   if (!facade_up) { fprintf(stderr, "tmLQCD_read_gauge: tmLQCD_inver_init must be called first. Aborting...\n"); return -1; }
-  /* ILDG/LIME input (io/gauge_read.c, needs c-lime) is outside this path: the caller fills the
-   * array returned by tmLQCD_get_gauge_field_pointer and sets g_update_gauge_copy = 1. */
-  fprintf(stderr, "tmLQCD_read_gauge: LIME I/O is not part of the B200 path; fill tmLQCD_get_gauge_field_pointer() instead\n");
-  return -1;
+  nstore = nconfig;
+  sprintf(conf_filename, "%s.%.4d", gauge_input_filename, nconfig);
+  if (g_proc_id == 0 && g_debug_level > 0)
+    printf("#\n# Trying to read gauge field from file %s.\n", conf_filename);
+  int j = read_gauge_field(conf_filename, g_gauge_field);
+  if (j != 0) {
+    fprintf(stderr, "tmLQCD_read_gauge: Error %d while reading gauge field from %s\n ...\n", j, conf_filename);
+    return -1;
+  }
+  if (g_proc_id == 0 && g_debug_level > 0) printf("# Finished reading gauge field.\n");
+  return 0;
 }
 int tmLQCD_get_gauge_field_pointer(double **gf) {
   if (!facade_up) return -1;
@@ -496,7 +513,6 @@ int tmLQCD_get_mpi_params(tmLQCD_mpi_params *p) {
  * Schur complement, residual check with M_full, normalisation by 2 kappa, eo -> lexicographic.
  * Everything between the upload of `source` and the download of `propagator` stays in HBM. */
 int tmLQCD_invert(double *const propagator, double *const source, const int op_id, const int write_prop) {
-  (void)write_prop;
   if (!facade_up) { fprintf(stderr, "tmLQCD_invert: tmLQCD_inver_init must be called first. Aborting...\n"); return -1; }
   if (op_id < 0 || op_id >= no_operators) { fprintf(stderr, "tmLQCD_invert: op_id=%d not in valid range. Aborting...\n", op_id); return -1; }
   g_mu = ops[op_id].mu; g_kappa = ops[op_id].kappa; /* op_set_globals, operator.c:320 */
@@ -515,6 +531,16 @@ int tmLQCD_invert(double *const propagator, double *const source, const int op_i
   ops[op_id].reached_prec = n1 + n2;
   if (g_kappa != 0.) { CHK(tmb_mul_r(dev(8), 2. * g_kappa, dev(8))); CHK(tmb_mul_r(dev(9), 2. * g_kappa, dev(9))); }
   CHK(tmb_field_download_lexic(propagator, dev(8), dev(9)));
+  if (write_prop) { /* op_write_prop (operator.c:532-605): point-source naming, splitted files */
+    char fn[600];
+    spinor *pe = (spinor *)malloc((size_t)VOLUME / 2 * sizeof(spinor)), *po = (spinor *)malloc((size_t)VOLUME / 2 * sizeof(spinor));
+    if (!pe || !po) { fprintf(stderr, "tmLQCD_invert: out of memory\n"); return -1; }
+    down(pe, 8); down(po, 9);
+    sprintf(fn, "%s.%.4d.%.2d.%.2d.inverted", prop_basename, nstore, 0, 0);
+    const int st = tmb_write_propagator(fn, pe, po, prop_precision, ops[op_id].reached_prec, iter, "CG", 0);
+    free(pe); free(po);
+    if (st != 0) { fprintf(stderr, "tmLQCD_invert: writing %s failed\n", fn); return -1; }
+  }
   if (g_proc_id == 0 && g_debug_level > 0)
     printf("# Inversion done in %d iterations, squared residue = %e!\n", iter, ops[op_id].reached_prec);
   return 0;
