@@ -462,15 +462,16 @@ def main():
                 out["cg"]["cpu_reference_est_how"] = ("reference Qtm_pm_psi time per application x (iterations+1); "
                                                       "lower bound, BLAS-1 of cg_her not included")
     dev.close()
-    # ---- BASELINE configs[3] and configs[4] on their own lattices, each in its own process (scripts/bench_sections.py) ----
+    # ---- BASELINE configs[0], configs[3] and configs[4] on their own lattices, each in its own process (scripts/bench_sections.py) ----
     if rank == 0 and world == 1 and not args.skip_sections:
-        for name in ("nd", "hmc"):
+        for name in ("small", "nd", "hmc"):
             try:
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_sections.py"), name],
                                    capture_output=True, text=True, timeout=600)
-                out[name] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-400:]}
+                key = "benchmark_8x8x8x8" if name == "small" else name
+                out[key] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-400:]}
             except Exception as e:  # pragma: no cover
-                out[name] = {"error": repr(e)}
+                out[key] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out), file=real_stdout, flush=True)
     if dist is not None:

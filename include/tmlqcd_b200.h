@@ -49,6 +49,7 @@ int tmb_set_mu(double g_mu);                                       /* g_mu = 2*k
 int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_operators_nd.c */
 /* kernel configuration knobs (profiling / tuning; defaults are the measured best) */
 int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
+int tmb_set_hop2_variant(int v); /* two-flavour hop: 0 = both flavours in one thread (default, measured best), 1 = lane-paired flavours */
 /* CompressionType of the reference (misc_types.h:33-37): 18 = full links (default), 12 = two rows streamed,
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);

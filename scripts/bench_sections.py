@@ -3,6 +3,7 @@
 lattice in C globals: one lattice per process), printing ONE JSON object on stdout.
 
     python scripts/bench_sections.py nd  [TxLXxLYxLZ]   BASELINE configs[3]: invert_doublet_eo (Qtm_pm_ndpsi CG), 32^3x64
+    python scripts/bench_sections.py small [TxLXxLYxLZ] BASELINE configs[0]: benchmark (Hopping_Matrix + D_psi), 8^4
     python scripts/bench_sections.py hmc [TxLXxLYxLZ]   BASELINE configs[4]: det + detratio monomials, 16^3x32
                                                         (heatbath, derivative = inversion + deriv_Sb force, acc)
 
@@ -180,6 +181,64 @@ def section_hmc(dims):
     return out
 
 
+def section_small(dims):
+    """BASELINE configs[0]: the reference's `benchmark` program (benchmark.c:262-327: Hopping_Matrix EO+OE pairs with
+    even_odd_flag, D_psi without) on 8^4.  At 2048 sites per parity the GPU is launch-latency bound, not HBM bound."""
+    import tmlqcd_b200 as tm
+    from conftest import random_spinor
+    g, ref, how = gauge_and_ref(dims, 1, False)  # scalar full-spinor build, one thread: "scalar --disable-mpi CPU build"
+    d = tm.Device(*dims)
+    d.set_params(KAPPA, GMU)
+    d.gauge_upload(g)
+    rng = np.random.default_rng(3)
+    V, Vh = d.V, d.Vh
+    f = [d.field(random_spinor(rng, Vh)) for _ in range(2)] + [d.field() for _ in range(2)]
+    n = 2000
+    for _ in range(50):
+        d.lib.tmb_Hopping_Matrix(0, f[2], f[0]); d.lib.tmb_Hopping_Matrix(1, f[3], f[2])
+    d.timer_start()
+    for _ in range(n):
+        d.lib.tmb_Hopping_Matrix(0, f[2], f[0]); d.lib.tmb_Hopping_Matrix(1, f[3], f[2])
+    t_pair = d.timer_stop() * 1e-3 / n
+    for _ in range(50):
+        d.lib.tmb_D_psi_eo(f[2], f[3], f[0], f[1])
+    d.timer_start()
+    for _ in range(n):
+        d.lib.tmb_D_psi_eo(f[2], f[3], f[0], f[1])
+    t_dpsi = d.timer_stop() * 1e-3 / n
+    out = {"workload": "BASELINE configs[0]: benchmark (Hopping_Matrix + D_psi), %dx%dx%dx%d (TxLXxLYxLZ), device-resident fields" % dims,
+           "gauge": how, "Hopping_Matrix_pair_us": 1e6 * t_pair, "Hopping_Matrix_gflops_1320": V * 1320.0 / t_pair / 1e9,
+           "Hopping_Matrix_gflops_1608": V * 1608.0 / t_pair / 1e9,
+           "D_psi_us": 1e6 * t_dpsi, "D_psi_gflops_1680": V * 1680.0 / t_dpsi / 1e9,
+           "note": "2048 sites per parity = 16 CTAs: launch-latency bound (2 launches per pair and per D_psi), not an HBM measurement"}
+    # the same through the reference-named symbols with host buffers (PCIe copies inside the timing)
+    D = tm.DropIn(*dims)
+    D.set_params(KAPPA, GMU); D.set_gauge(g)
+    hk, h1, h2 = random_spinor(rng, Vh), np.zeros((Vh, 24)), np.zeros((Vh, 24))
+    P, Q = np.zeros((V, 24)), random_spinor(rng, V)
+    D.Hopping_Matrix(0, h1, hk); D.D_psi(P, Q)
+    m = 200
+    t0 = time.perf_counter()
+    for _ in range(m):
+        D.Hopping_Matrix(0, h1, hk); D.Hopping_Matrix(1, h2, h1)
+    out["dropin_Hopping_Matrix_pair_us"] = 1e6 * (time.perf_counter() - t0) / m
+    t0 = time.perf_counter()
+    for _ in range(m):
+        D.D_psi(P, Q)
+    out["dropin_D_psi_us"] = 1e6 * (time.perf_counter() - t0) / m
+    d.close()
+    if ref is not None:
+        ref.set_params(KAPPA, GMU)
+        nrep = 2000
+        th = ref.lib.ref_bench_hopping(nrep) / nrep
+        td = ref.lib.ref_bench_D_psi(nrep) / (2 * nrep)
+        out["cpu_reference"] = {"kind": "reference", "cores": 1,
+                                "sample": f"{nrep} EO+OE pairs and {2 * nrep} D_psi applications, scalar full-spinor build of the unmodified reference, 1 thread (benchmark.c recipe)",
+                                "Hopping_Matrix_pair_us": 1e6 * th, "Hopping_Matrix_gflops_1608": V * 1608.0 / th / 1e9,
+                                "D_psi_us": 1e6 * td, "D_psi_gflops_1680": V * 1680.0 / td / 1e9}
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -190,6 +249,9 @@ if __name__ == "__main__":
     elif which == "hmc":
         dims = tuple(int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "32x16x16x16").split("x"))
         res = section_hmc(dims)
+    elif which == "small":
+        dims = tuple(int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "8x8x8x8").split("x"))
+        res = section_small(dims)
     else:
-        raise SystemExit("usage: bench_sections.py nd|hmc [TxLXxLYxLZ]")
+        raise SystemExit("usage: bench_sections.py nd|hmc|small [TxLXxLYxLZ]")
     print(json.dumps(res), file=real_stdout, flush=True)

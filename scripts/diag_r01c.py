@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Round 1, third session diagnostics (one GPU):
+  nd    two-flavour hop kernel variants (0 both flavours per thread, 1 lane-paired): Qtm_pm_ndpsi time at 32^3x64
+  e2e   the host-pointer invert_eo of bench.py, phase by phase (g_debug_level = 2 prints upload / solve / download)
+  chunk host-pointer Hopping_Matrix against the number of pipeline chunks
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import tmlqcd_b200 as tm
+from conftest import random_gauge, random_spinor
+
+what = sys.argv[1]
+KAPPA, GMU = 0.16, 0.0032
+
+
+def timeit(d, fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    d.ck(d.lib.tmb_sync())
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    d.ck(d.lib.tmb_sync())
+    return (time.perf_counter() - t0) / n
+
+
+if what == "nd":
+    dims = (64, 32, 32, 32)
+    rng = np.random.default_rng(1)
+    d = tm.Device(*dims)
+    d.set_params(KAPPA, GMU); d.ck(d.lib.tmb_set_nd(0.139, 0.15, 1.0))
+    d.gauge_upload(random_gauge(rng, d.V))
+    f = [d.field(random_spinor(rng, d.Vh)) for _ in range(2)] + [d.field() for _ in range(4)]
+    res = {}
+    for v in (0, 1, 0, 1):
+        d.ck(d.lib.tmb_set_hop2_variant(v))
+        t = timeit(d, lambda: d.call("Qtm_pm_ndpsi", f[2], f[3], f[0], f[1]), n=50)
+        print(f"hop2 variant {v}: Qtm_pm_ndpsi {1e6 * t:8.1f} us  -> {8448.0 * d.Vh / t / 1e9:7.1f} GB/s effective (8448 B/site)", flush=True)
+        res[v] = d.download(f[2])
+    print("variants agree: rel", np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1]))
+    d.close()
+elif what in ("e2e", "chunk"):
+    dims = (48, 24, 24, 24)
+    rng = np.random.default_rng(1)
+    d = tm.Device(*dims)
+    d.set_params(KAPPA, GMU)
+    g = random_gauge(rng, d.V)
+    d.gauge_upload(g)
+    Vh = d.Vh
+
+    def pinned(shape):
+        n = int(np.prod(shape))
+        p = d.lib.tmb_host_alloc(n * 8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,)).reshape(shape)
+    D = tm.DropIn(*dims)
+    D.set_params(KAPPA, GMU)
+    D.set_gauge(g)
+    if what == "chunk":
+        hk, h1 = pinned((Vh, 24)), pinned((Vh, 24))
+        hk[:] = random_spinor(rng, Vh)
+        D.Hopping_Matrix(0, h1, hk)
+        for nch in (4, 6, 8, 12, 16, 24, 48, 8):
+            d.ck(d.lib.tmb_set_host_chunks(nch))
+            t = timeit(d, lambda: D.Hopping_Matrix(0, h1, hk), n=10)
+            print(f"host-pointer Hopping_Matrix, {nch:2d} chunks: {1e3 * t:7.3f} ms  ({Vh * 192 / t / 1e9:5.1f} GB/s each way)", flush=True)
+    else:
+        E, O = random_spinor(rng, Vh), random_spinor(rng, Vh)
+        dE, dO, dEn, dOn = d.field(E), d.field(O), d.field(), d.field()
+        for _ in range(2):
+            d.call("field_zero", dOn); d.ck(d.lib.tmb_sync())
+            t0 = time.perf_counter()
+            it = d.call("invert_eo", dEn, dOn, dE, dO, 1e-14, 5000, 1)
+            print("device invert_eo", it, "iterations", time.perf_counter() - t0, "s; stats", d.solver_stats(), flush=True)
+        hE, hO, hEn, hOn = (pinned((Vh, 24)) for _ in range(4))
+        hE[:] = E; hO[:] = O
+        C.c_int.in_dll(D.lib, "g_debug_level").value = 2
+        sp = tm.capi.SolverParams()
+        for _ in range(3):
+            hOn[:] = 0
+            t0 = time.perf_counter()
+            it = D.invert_eo(hEn, hOn, hE, hO, 1e-14, 5000, 1, 1, 0, 1, 0, None, sp, 0, 0, 0, 18)
+            print("drop-in invert_eo", it, "iterations", time.perf_counter() - t0, "s; stats", d.solver_stats(), flush=True)
+    d.close()

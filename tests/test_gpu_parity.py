@@ -230,10 +230,13 @@ def test_cg_and_invert_eo(oracle_lib, dims, theta, loopback):
         d.close()
 
 
-def test_nd_doublet(oracle_lib):
-    dims = (4, 4, 6, 8)
+@pytest.mark.parametrize("dims,variant", [((4, 4, 6, 8), 0), ((4, 4, 6, 8), 1), ((2, 6, 2, 6), 1)])
+def test_nd_doublet(oracle_lib, dims, variant):
+    """variant 0: both flavours in one thread (default), 1: lane-paired two-flavour kernel;
+    2x6x2x6: 2*Vh = 144 threads, the last warp of the paired kernel is half filled"""
     rng, o, d, g = _setup(oracle_lib, dims, (1., 0., 0., 0.))
     try:
+        d.ck(d.lib.tmb_set_hop2_variant(variant))
         s, c, q, w = (random_spinor(rng, o.Vh) for _ in range(4))
         ds, dc, dls, dlc = d.field(s), d.field(c), d.field(), d.field()
         for name in ("Qtm_ndpsi", "Qtm_dagger_ndpsi", "Qtm_pm_ndpsi"):

@@ -74,7 +74,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1;
+  int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 0;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -209,7 +209,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1;
+  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 0;
   C.init = true;
   return 0;
 }
@@ -388,6 +388,7 @@ extern "C" int tmb_set_mu(double g_mu) { NEED_INIT(); C.mu = g_mu; return 0; }
 extern "C" int tmb_set_nd(double mubar, double epsbar, double invmaxev) {
   NEED_INIT(); C.mubar = mubar; C.epsbar = epsbar; C.invmaxev = invmaxev; return 0;
 }
+extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < 0 || v > 1) return fail(-7, "hop2 variant must be 0 or 1"); C.hop2_variant = v; return 0; }
 extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   NEED_INIT();
   if (hop_variant < 0 || hop_variant > 9) return fail(-7, "hop_variant must be 0..9");
@@ -925,7 +926,7 @@ static int hop2(int ieo, double2 *o0, double2 *o1, const double2 *i0, const doub
   memset(&a, 0, sizeof(a));
   a.in0 = i0; a.in1 = i1; a.out0 = o0; a.out1 = o1; a.p0 = p0; a.p1 = p1; a.U = C.U; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
-  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = C.hints;
+  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = C.hints; a.variant = C.hop2_variant;
   KL(tmb_launch_hop2(a, C.s_main));
   return 0;
 }

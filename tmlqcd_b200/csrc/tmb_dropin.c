@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "../../include/tmlqcd_b200.h"
 #include "../../include/tmlqcd_b200_dropin.h"
 
@@ -97,6 +98,7 @@ static void sync_globals(void) {
     g_update_gauge_copy = 0;
   }
 }
+static double wall(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static void up(int k, const spinor *h) { CHK(tmb_field_upload(dev(k), (const double *)h)); }
 static void down(spinor *h, int k) { CHK(tmb_field_download((double *)h, dev(k))); }
 
@@ -344,11 +346,14 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
     printf("# Using even/odd preconditioning!\n# Using CG!\n# mu = %.12f, kappa = %.12f\n", g_mu / 2. / g_kappa, g_kappa);
     fflush(stdout);
   }
+  const double t0 = wall();
   sync_globals();
   /* CompressionType as the reference hands it to its external inverters (invert_eo.c:93-101);
    * COMPRESSION_8 has no double-precision-exact reconstruction and is served as COMPRESSION_12 */
   CHK(tmb_set_compression(compression == NO_COMPRESSION ? 18 : 12));
+  const double t1 = wall();
   up(6, Even); up(7, Odd); up(9, Odd_new); /* Odd_new is the CG's initial guess (cg_her.c:84) */
+  const double t2 = wall();
   int iter;
   if (solver_flag == TMB_SOLVER_MIXEDCG) { /* invert_eo.c:225-232; mixed_cg_her zeroes the guess (:108) */
     CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
@@ -356,8 +361,12 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
   } else
     iter = tmb_invert_eo(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
   if (iter < -1) die(__func__);
+  const double t3 = wall();
   CHK(tmb_set_compression(18));
   down(Even_new, 8); down(Odd_new, 9);
+  if (g_proc_id == 0 && g_debug_level > 1) /* where the time of a host-pointer solve goes */
+    printf("# invert_eo (B200): globals/gauge %.3f ms, upload %.3f ms, solve %.3f ms, download %.3f ms\n",
+           1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (wall() - t3));
   return iter;
 }
 

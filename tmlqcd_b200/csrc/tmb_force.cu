@@ -119,8 +119,73 @@ __global__ void __launch_bounds__(128, 2) hop2_kernel(const tmb_hop2_launch a) {
     tmb_store_out<HINTS & 1>(o1 + c * Vh + i, r1[c], pol);
   }
 }
+/* Lane-paired variant (tmb_set_hop2_variant(1); measured SLOWER than hop2_kernel at 32^3x64: 450 vs 413 us per
+ * launch, so it is not the default - kept selectable for re-tuning): lanes 2j and 2j+1 of a warp work on the SAME site, one flavour each.  Both lanes
+ * issue the gauge loads with the same address, so the coalescer fetches every link once per pair (a warp instruction
+ * covers 16 sites x 16 B = two full 128-B lines) - the gauge stream is still shared, 1920 B per site pair - but each
+ * thread carries ONE 12-component accumulator: 168 registers and 12 warps/SM like hop_kernel instead of 254 and 8.
+ * The 2x2 flavour mixing of the epilogues needs the partner's value: one __shfl_xor_sync per real number. */
+__device__ __forceinline__ double2 tmb_partner(double2 v) {
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1));
+}
+template <int MODE, int HINTS>
+__global__ void __launch_bounds__(128, 3) hop2p_kernel(const tmb_hop2_launch a) {
+  const int gid = blockIdx.x * 128 + threadIdx.x;
+  const int fl = gid & 1;
+  const bool live = (gid >> 1) < a.g.Vh;
+  const int i = live ? (gid >> 1) : a.g.Vh - 1; /* no early exit: the shuffles below want whole warps */
+  tmb_policies pol;
+  pol.stream = tmb_policy_evict_first();
+  pol.reuse = tmb_policy_evict_last();
+  tmb_hop_fields<double2> f;
+  f.in = (const double2 *)(fl ? a.in1 : a.in0); f.U = (const double2 *)a.U;
+  f.halo_up = nullptr; f.halo_dn = nullptr; f.Uhalo = nullptr;
+  double2 r[12];
+  tmb_hop_site<0, HINTS>(r, f, a.g, a.par, i, a.ka, pol);
+  const size_t Vh = a.g.Vh;
+  /* flavour 0 (strange) carries 1 -+ i mu, flavour 1 (charm) the conjugate (tm_operators_nd.c:639-756) */
+  const double smu = fl ? -a.mu : a.mu;
+  if (MODE == 1) {
+    const double nrm = 1. / (1. + a.mu * a.mu - a.eps * a.eps);
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      const double2 o = tmb_partner(r[c]);
+      const double2 z = make_double2(1., (c < 6) ? -smu : smu);
+      double2 x = c_mul(z, r[c]); x.x += a.eps * o.x; x.y += a.eps * o.y;
+      r[c] = make_double2(nrm * x.x, nrm * x.y);
+    }
+  } else if (MODE == 2) {
+    const double2 *p = (const double2 *)(fl ? a.p1 : a.p0);
+    double2 q[12]; /* all operand loads before the first store: out may alias p (see hop_kernel) */
+#pragma unroll
+    for (int c = 0; c < 12; c++) q[c] = p[c * Vh + i];
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      const bool up = c < 6;
+      const double2 o = tmb_partner(q[c]);
+      const double2 z = make_double2(1., up ? -smu : smu);
+      double2 x = c_mul(z, q[c]); x.x += a.eps * o.x; x.y += a.eps * o.y;
+      const double2 d = up ? c_sub(x, r[c]) : c_sub(r[c], x);
+      r[c] = make_double2(a.scale * d.x, a.scale * d.y);
+    }
+  }
+  if (!live) return;
+  double2 *out = (double2 *)(fl ? a.out1 : a.out0);
+#pragma unroll
+  for (int c = 0; c < 12; c++) tmb_store_out<HINTS & 1>(out + c * Vh + i, r[c], pol);
+}
 template <int HINTS>
 static cudaError_t hop2_go(const tmb_hop2_launch &a, cudaStream_t s) {
+  if (a.variant == 1) { /* lane-paired */
+    const int gridp = (int)(((size_t)2 * a.g.Vh + 127) / 128);
+    switch (a.mode) {
+      case 0: hop2p_kernel<0, HINTS><<<gridp, 128, 0, s>>>(a); break;
+      case 1: hop2p_kernel<1, HINTS><<<gridp, 128, 0, s>>>(a); break;
+      case 2: hop2p_kernel<2, HINTS><<<gridp, 128, 0, s>>>(a); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
   const int grid = (a.g.Vh + 127) / 128;
   switch (a.mode) {
     case 0: hop2_kernel<0, HINTS><<<grid, 128, 0, s>>>(a); break;

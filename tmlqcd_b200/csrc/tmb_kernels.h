@@ -157,5 +157,6 @@ struct tmb_hop2_launch {
   const void *in0, *in1; void *out0, *out1; const void *p0, *p1; const void *U;
   tmb_geom g; int par; double2 ka[4];
   int mode; double mu, eps, scale; int hints;
+  int variant; /* 0: one thread carries both flavours (hop2_kernel, default), 1: lane-paired flavours (hop2p_kernel) */
 };
 cudaError_t tmb_launch_hop2(const tmb_hop2_launch &a, cudaStream_t s);
