@@ -434,14 +434,16 @@ int tmLQCD_b200_get_solver_info(int op_id, int *iterations, double *reached_prec
  * grammar read_input.l is out of scope): T, L, LX, LY, LZ, ThetaT/X/Y/Z and, inside
  * BeginOperator TMWILSON ... EndOperator, kappa, 2KappaMu, SolverPrecision, MaxSolverIterations,
  * UseRelativePrecision.  Keys are case-insensitive, '#' starts a comment. */
+int tmLQCD_b200_set_io(const char *gauge_file, const char *prop_base, int prec);
 static int read_invert_input(const char *fn) {
   FILE *f = fopen(fn, "r");
   if (!f) return -1;
-  char line[512], key[128], val[128];
+  char line[512], orig[512], key[128], val[128];
   int in_op = 0;
   double kappa = 0., mu = 0., prec = 1e-14; int maxit = 1000, rel = 0;
   while (fgets(line, sizeof(line), f)) {
     char *h = strchr(line, '#'); if (h) *h = 0;
+    strcpy(orig, line); /* file names keep their case */
     for (char *c = line; *c; c++) *c = (char)tolower((unsigned char)*c);
     if (strstr(line, "beginoperator")) { in_op = 1; kappa = g_kappa; mu = 0.; prec = 1e-14; maxit = 1000; rel = 0; continue; }
     if (strstr(line, "endoperator")) { if (in_op) tmLQCD_b200_add_operator(kappa, mu, prec, maxit, rel); in_op = 0; continue; }
@@ -460,6 +462,15 @@ static int read_invert_input(const char *fn) {
     else if (!strcmp(key, "solverprecision")) prec = atof(val);
     else if (!strcmp(key, "maxsolveriterations")) maxit = atoi(val);
     else if (!strcmp(key, "userelativeprecision")) rel = !strcmp(val, "yes");
+    else if (!strcmp(key, "gaugeconfiginputfile") || !strcmp(key, "sourcefilename") || !strcmp(key, "propagatorprecision")) {
+      char raw[128] = ""; /* read_input.l:399 (GaugeConfigInputFile), :372 (SourceFilename), :808-816 (PropagatorPrecision) */
+      const char *eq = strchr(orig, '=');
+      if (eq && sscanf(eq + 1, " %127s", raw) == 1) {
+        if (key[0] == 'g') tmLQCD_b200_set_io(raw, NULL, 0);
+        else if (key[0] == 's') tmLQCD_b200_set_io(NULL, raw, 0);
+        else tmLQCD_b200_set_io(NULL, NULL, atoi(raw));
+      }
+    }
   }
   fclose(f);
   return 0;
