@@ -352,6 +352,16 @@ def main():
                      "kernel": "hop_kernel<MODE 0> (Hopping_Matrix)", "algorithmic_bytes_per_launch": Vh * BYTES_SITE,
                      "avg_launch_us": per_launch_ms * 1e3},
     }
+    # the same process, the same thermal state: device-to-device copy bandwidth sustained over ~0.5 s (read + write bytes),
+    # next to the burst figure of MEASURED_PEAKS.json that `peak` quotes
+    try:
+        gbs = C.c_double(0.)
+        dev.ck(lib.tmb_measure_copy_gbs(1 << 30, 1500, C.byref(gbs)))
+        out["roofline"]["copy_gbs_sustained_this_run"] = gbs.value
+        out["roofline"]["frac_of_sustained_copy"] = achieved / gbs.value
+    except Exception as e:  # pragma: no cover
+        out["roofline"]["copy_gbs_sustained_this_run"] = None
+        print("copy bandwidth measurement failed:", e, file=sys.stderr)
     tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tr):
         try:

@@ -54,7 +54,7 @@ int tmb_set_hop2_variant(int v); /* two-flavour hop: 0 = both flavours in one th
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);
 int tmb_set_host_chunks(int n); /* chunks of the pipelined host-pointer Hopping_Matrix (default 8, the measured best at 24^3x48) */
-int tmb_set_overlap(int flags); /* bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows */
+int tmb_set_overlap(int flags); /* bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows, bit2: no CUDA-graph replay in the CG, bit3: L2 prefetch of the epilogue operands (p, dotw) */
 
 /* ---- memory ---- */
 void *tmb_field_alloc(void);         /* one eo spinor field, VOLUME/2 sites, device SoA layout */
@@ -210,6 +210,8 @@ void *tmb_monomial_wfield(int k);  /* w_fields[k], k < 6 (device) */
 
 /* number of kernels this library launched since tmb_init (bench.py's gpu_launches) */
 long long tmb_launch_count(void);
+/* measurement aid: sustained device-to-device copy bandwidth (read + write), GB/s, `reps` copies of `bytes` */
+int tmb_measure_copy_gbs(size_t bytes, int reps, double *gbs);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,26 @@ if what == "nd":
         res[v] = d.download(f[2])
     print("variants agree: rel", np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1]))
     d.close()
+elif what == "cgpf":
+    # CG time-to-solution with / without the L2 prefetch of the epilogue operands (tmb_set_overlap bit 3)
+    dims = (48, 24, 24, 24)
+    rng = np.random.default_rng(1)
+    d = tm.Device(*dims)
+    d.set_params(KAPPA, GMU)
+    d.gauge_upload(random_gauge(rng, d.V))
+    E, O = d.field(random_spinor(rng, d.Vh)), d.field(random_spinor(rng, d.Vh))
+    En, On, W = d.field(), d.field(), d.field()
+    for flags in (0, 8, 0, 8):
+        d.ck(d.lib.tmb_set_overlap(flags))
+        best = 1e9
+        for rep in range(4):
+            d.call("field_zero", On); d.ck(d.lib.tmb_sync())
+            t0 = time.perf_counter()
+            it = d.call("invert_eo", En, On, E, O, 1e-22, 5000, 1)
+            best = min(best, time.perf_counter() - t0)
+        tq = timeit(d, lambda: d.call("Qtm_pm_psi", W, E), n=200)
+        print(f"overlap flags {flags}: invert_eo {it} iterations, best {1e3 * best:8.3f} ms ({1e6 * best / it:7.2f} us/iteration); Qtm_pm_psi {1e6 * tq:7.2f} us", flush=True)
+    d.close()
 elif what in ("e2e", "chunk"):
     dims = (48, 24, 24, 24)
     rng = np.random.default_rng(1)

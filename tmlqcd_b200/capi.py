@@ -86,7 +86,7 @@ DEVICE_API = {
     "tmb_monomial_acc": (_i, [_i, C.POINTER(_d)]),
     "tmb_monomial_info": (_i, [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tmb_monomial_pf": (_vp, [_i]), "tmb_monomial_wfield": (_vp, [_i]),
-    "tmb_launch_count": (C.c_longlong, []),
+    "tmb_launch_count": (C.c_longlong, []), "tmb_measure_copy_gbs": (_i, [C.c_size_t, _i, C.POINTER(_d)]),
 }
 
 _sp = _dp  # host spinor buffers (reference AoS layout) as float64 arrays

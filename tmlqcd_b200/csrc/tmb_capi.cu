@@ -62,6 +62,7 @@ struct Ctx {
   cudaEvent_t ev_in = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
   double2 *U = nullptr, *Uhalo = nullptr;
   double2 *send_up = nullptr, *send_dn = nullptr, *halo_up = nullptr, *halo_dn = nullptr;
+  double2 *gauge_raw = nullptr; int gauge_uploads = 0; /* AoS staging of tmb_gauge_upload, kept once the links change repeatedly */
   double2 *stage = nullptr; /* AoS staging, 32*Vh double2 (one lexicographic spinor field or one derivative field) */
   double *partial = nullptr; int npartial = 0;
   tmb_cg_state *st = nullptr;      /* device */
@@ -232,6 +233,7 @@ extern "C" int tmb_finalize(void) {
   if (C.dn_base && C.dn_base != C.arena && C.dn_base != C.up_base) cudaIpcCloseMemHandle(C.dn_base);
   if (C.arena) cudaFree(C.arena); else if (C.flags) cudaFree(C.flags);
   if (C.p2p_ticket) cudaFree(C.p2p_ticket); if (C.p2p_err) cudaFree(C.p2p_err);
+  if (C.gauge_raw) cudaFree(C.gauge_raw);
   cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
@@ -400,7 +402,7 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
 /* number of time-slice chunks of the pipelined host-pointer Hopping_Matrix (1..64) */
 extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 1 || n > MAXCHUNK) return fail(-7, "host chunks must be in [1, %d]", MAXCHUNK); C.host_chunks = n; return 0; }
 extern "C" int tmb_set_overlap(int flags) {
-  NEED_INIT(); C.pdl = flags & 1; C.prefetch = (flags >> 1) & 1; C.cg_graph = (flags & 4) ? 0 : 1;
+  NEED_INIT(); C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1;
   C.p2p_diag = (flags >> 3) & 31; /* timing diagnostics only: 1 = boundary reads from the LOCAL field, 2 = no end-of-hop handshake */
   return 0;
 }
@@ -453,6 +455,29 @@ extern "C" int tmb_timer_stop(float *ms) {
   return 0;
 }
 
+/* Measurement aid for bench.py's roofline: device-to-device copy bandwidth (read + write bytes) of `bytes` per copy,
+ * sustained over `reps` back-to-back copies on the compute stream - the same quantity MEASURED_PEAKS.json quotes as a
+ * burst figure, taken in the same process and thermal state as the kernels it is compared with. */
+extern "C" int tmb_measure_copy_gbs(size_t bytes, int reps, double *gbs) {
+  NEED_INIT();
+  if (bytes < 1024 || reps < 1 || !gbs) return fail(-7, "tmb_measure_copy_gbs: bad arguments");
+  void *a = nullptr, *b = nullptr;
+  CU(cudaMalloc(&a, bytes));
+  if (cudaMalloc(&b, bytes) != cudaSuccess) { cudaFree(a); return fail(-100, "tmb_measure_copy_gbs: out of memory"); }
+  cudaMemsetAsync(a, 1, bytes, C.s_main);
+  for (int i = 0; i < 3; i++) cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice, C.s_main);
+  cudaEventRecord(C.ev_t0, C.s_main);
+  for (int i = 0; i < reps; i++) cudaMemcpyAsync((i & 1) ? a : b, (i & 1) ? b : a, bytes, cudaMemcpyDeviceToDevice, C.s_main);
+  cudaEventRecord(C.ev_t1, C.s_main);
+  cudaError_t e = cudaEventSynchronize(C.ev_t1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, C.ev_t0, C.ev_t1);
+  cudaFree(a); cudaFree(b);
+  if (e != cudaSuccess) return fail(-100, "tmb_measure_copy_gbs: %s", cudaGetErrorString(e));
+  *gbs = 2. * (double)bytes * reps / (ms * 1e-3) / 1e9;
+  return 0;
+}
+
 extern "C" int tmb_field_upload(void *field, const double *host) {
   NEED_INIT();
   CU(cudaMemcpyAsync(C.stage, host, FIELD_BYTES(), cudaMemcpyHostToDevice, C.s_main));
@@ -502,12 +527,14 @@ static int exchange_faces(const void *sup, const void *sdn, void *hup, void *hdn
 extern "C" int tmb_gauge_upload(const double *host_gauge) {
   NEED_INIT();
   const size_t bytes = (size_t)72 * C.g.Vh * sizeof(double2); /* V*4 links * 9 complex */
-  double2 *raw = nullptr;
-  CU(cudaMalloc(&raw, bytes));
+  /* AoS staging copy: allocated per upload for a one-off configuration (inversions), kept from the second
+   * upload on (HMC: the links change every MD step, update_gauge.c:109 sets the dirty flag each time) */
+  double2 *raw = C.gauge_raw;
+  if (!raw) CU(cudaMalloc(&raw, bytes));
   CU(cudaMemcpyAsync(raw, host_gauge, bytes, cudaMemcpyHostToDevice, C.s_main));
   KL(tmb_launch_pack_gauge(C.U, raw, C.g, C.s_main));
   CU(cudaStreamSynchronize(C.s_main));
-  CU(cudaFree(raw));
+  if (++C.gauge_uploads >= 2) C.gauge_raw = raw; else CU(cudaFree(raw));
   if (C.dist) { /* one-off gauge halo: U_0 of rank-1's last time-slice (xchange_gauge in the reference) */
     double2 *tmp = nullptr;
     const size_t n = (size_t)18 * C.g.S;
@@ -649,7 +676,12 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
     TRY(hop(ieo, dout, din, o));
     return tmb_field_download(l_host, dout);
   }
-  int spc = (T + C.host_chunks - 1) / C.host_chunks; if (spc < 1) spc = 1; /* time-slices per chunk */
+  /* a chunk should carry at least ~2 MB: below that the per-chunk copies, events and launches cost more than the
+   * overlap saves (8^4: 0.39 MB per field -> one chunk, 350 -> ~40 us per call) */
+  int want = C.host_chunks;
+  const size_t min_chunk = (size_t)2 << 20;
+  if (FIELD_BYTES() / (size_t)want < min_chunk) { want = (int)(FIELD_BYTES() / min_chunk); if (want < 1) want = 1; }
+  int spc = (T + want - 1) / want; if (spc < 1) spc = 1; /* time-slices per chunk */
   const int nchunk = (T + spc - 1) / spc;
   if (nchunk > MAXCHUNK) return fail(-13, "too many chunks");
   double2 *in_aos = C.stage, *out_aos = C.stage + (size_t)12 * Vh;

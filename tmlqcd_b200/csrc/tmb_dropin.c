@@ -57,9 +57,11 @@ int tmb_dropin_init(int t, int lx, int ly, int lz, int device) {
   T = t; L = lx; LX = lx; LY = ly; LZ = lz;
   VOLUME = t * lx * ly * lz; RAND = 0; VOLUMEPLUSRAND = VOLUME;
   if (!g_gauge_field) { /* one contiguous slab, g_gauge_field[ix][mu] (init/init_gauge_field.c:51-68) */
-    gauge_slab = (su3 *)calloc((size_t)VOLUME * 4 + 1, sizeof(su3));
+    /* pinned: the links cross PCIe at every g_update_gauge_copy (each MD step in the HMC) */
+    gauge_slab = (su3 *)tmb_host_alloc(((size_t)VOLUME * 4 + 1) * sizeof(su3));
     g_gauge_field = (su3 **)calloc((size_t)VOLUME, sizeof(su3 *));
     if (!gauge_slab || !g_gauge_field) return -2;
+    memset(gauge_slab, 0, ((size_t)VOLUME * 4 + 1) * sizeof(su3));
     for (int ix = 0; ix < VOLUME; ix++) g_gauge_field[ix] = gauge_slab + 4 * (size_t)ix;
   }
   g_update_gauge_copy = 1;
@@ -71,8 +73,10 @@ int tmb_dropin_finalize(void) {
   for (int k = 0; k < NDEV; k++) D[k] = NULL; /* freed by tmb_finalize */
   for (int k = 0; k < 4; k++) D32[k] = NULL;
   hmc_forget();
+  if (gauge_slab) tmb_host_free(gauge_slab); /* before the context goes away; a caller-owned g_gauge_field is left alone */
   tmb_finalize();
-  free(gauge_slab); free(g_gauge_field); gauge_slab = NULL; g_gauge_field = NULL;
+  if (gauge_slab) free(g_gauge_field);
+  gauge_slab = NULL; g_gauge_field = NULL;
   dropin_up = 0;
   return 0;
 }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
    * the launch carries no PDL attribute.  (Measured: neither helps this kernel, see DESIGN.md.) */
   asm volatile("griddepcontrol.launch_dependents;");
   const int NE = (HINTS & 2) ? 6 : 9; /* stored complex numbers per link (12-real compression: 6) */
-  if (a.prefetch && threadIdx.x < 8 * NE) {
+  if ((a.prefetch & 1) && threadIdx.x < 8 * NE) {
     const int first = blockIdx.x * BLOCK;
     int n = a.nsites - first; n = n > BLOCK ? BLOCK : n;
     if (n > 0) {
@@ -267,6 +267,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
 #pragma unroll
     for (int m = 0; m < 4; m++) ka[m] = cvt2<V2>(a.ka[m]);
     const V2 cf = cvt2<V2>(a.cf);
+    /* optional (tmb_set_overlap bit 3): ask L2 for the epilogue operands of this site now, so that the batch of
+     * loads after the 8 directions finds them there instead of paying a DRAM round trip with all registers live */
+    if ((MODE >= 2 || DOT) && (a.prefetch & 2) && (threadIdx.x & 7) == 0) {
+#pragma unroll
+      for (int c = 0; c < 12; c++) {
+        if (MODE >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.p + (size_t)c * a.g.Vh + i));
+        if (DOT) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.dotw + (size_t)c * a.g.Vh + i));
+      }
+    }
     V2 r[12];
     /* peer mode: interior CTAs run the branch-free site code (all 8 directions' loads can be batched), only
      * the CTAs of the two boundary slices take the variant with the per-site halo branches */
