@@ -209,6 +209,9 @@ void *tmb_monomial_pf(int id);     /* the pseudo-fermion field (device) */
 void *tmb_monomial_wfield(int k);  /* w_fields[k], k < 6 (device) */
 
 /* number of kernels this library launched since tmb_init (bench.py's gpu_launches) */
+/* measure_plaquette (measure_gauge_action.c:46): sum over all sites of all ranks and the 6 planes of Re tr(P)/3;
+ * the average plaquette is result / (6 * VOLUME * nranks) */
+int tmb_measure_plaquette(double *result);
 long long tmb_launch_count(void);
 /* measurement aid: sustained device-to-device copy bandwidth (read + write), GB/s, `reps` copies of `bytes` */
 int tmb_measure_copy_gbs(size_t bytes, int reps, double *gbs);

@@ -219,6 +219,9 @@ void detratio_heatbath(const int id, hamiltonian_field_t *const hf);
 double detratio_acc(const int id, hamiltonian_field_t *const hf);
 void detratio_derivative(const int id, hamiltonian_field_t *const hf);
 
+/* measure_gauge_action.c:46: sum over sites and planes of Re tr(plaquette)/3, on the device copy of gf */
+double measure_plaquette(const su3 **const gf);
+
 /* ---- gauge configurations and propagator files: ILDG / SciDAC records in LIME containers.
  *      Types: io/dml.h (DML_Checksum), io/params.h:78-104 (paramsXlfInfo, paramsGaugeInfo). ---- */
 typedef struct { unsigned int suma, sumb; } DML_Checksum;

@@ -70,6 +70,7 @@ class Oracle:
             "orc_cg_her_nd": (i, [_dp] * 4 + [i, d, i]),
             "orc_invert_doublet_eo_cg": (i, [_dp] * 8 + [d, i, i]),
             "orc_deriv_Sb": (None, [i, _dp, _dp, _dp, d]),
+            "orc_measure_plaquette": (d, []),
             "orc_set_relative_precision_flag": (None, [i]),
             "orc_mnl_add": (i, [i, d, d, d, d, i, i, d, d, i]),
             "orc_mnl_clear": (None, []),

@@ -476,3 +476,8 @@ int ref_write_propagator(const char *filename, double *even, double *odd, int pr
 int ref_read_spinor(double *even, double *odd, const char *filename, int position) {
   return read_spinor((spinor *)even, (spinor *)odd, (char *)filename, position);
 }
+
+/* ---- plaquette (measure_gauge_action.c:46): what tmLQCD_read_gauge prints after reading a configuration
+ *      (wrapper/lib_wrapper.c:232-235) ---- */
+#include "measure_gauge_action.h"
+double ref_measure_plaquette(void) { return measure_plaquette((const su3 **)g_gauge_field); }

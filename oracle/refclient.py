@@ -110,6 +110,7 @@ class Reference:
             "ref_M_minus_1_timesC": (None, [_dp] * 4), "ref_H_eo_tm_ndpsi": (None, [_dp] * 4 + [i]),
             "ref_M_oo_sub_g5_ndpsi": (None, [_dp] * 6 + [d, d]), "ref_mul_one_pm_iconst": (None, [_dp, _dp, d, i]),
             "ref_rg_mixed_cg_her": (i, [_dp, _dp, i, d, i, d]),
+            "ref_measure_plaquette": (d, []),
             "ref_write_gauge": (i, [C.c_char_p, i, d, i]), "ref_read_gauge": (i, [C.c_char_p, i]),
             "ref_write_propagator": (i, [C.c_char_p, _dp, _dp, i, d, i]), "ref_read_spinor": (i, [_dp, _dp, C.c_char_p, i]),
             "ref_bench_hopping": (d, [i]),

@@ -221,4 +221,24 @@ void emul_deriv(int ieo, const double *l, const double *k, const double *U, doub
       else          { if (last) tmb_deriv_site<0, 1>(f, g, q, i, ka, 2. * factor); else tmb_deriv_site<0, 0>(f, g, q, i, ka, 2. * factor); }
     }
 }
+/* plaquette sum by the device site function; dist: the +t links of the last slice come from `up` = [2][3][9][S]
+ * (emul_pack_gauge_first_slice of the rank above; of the same field for a periodic single rank) */
+void emul_pack_gauge_first_slice(double *out, const double *U, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 1);
+  const double2 *u = (const double2 *)U; double2 *o = (double2 *)out;
+  for (size_t x = 0; x < (size_t)54 * g.S; x++) { /* the index arithmetic of pack_gauge_first_slice_kernel */
+    const int j = (int)(x % g.S); const int row = (int)(x / g.S);
+    const int e = row % 9, m = (row / 9) % 3, q = row / 27;
+    o[x] = u[(size_t)((q * 4 + (m + 1)) * 9 + e) * g.Vh + j];
+  }
+}
+double emul_plaquette(const double *U, const double *up, int T, int LX, int LY, int LZ, int dist) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, dist);
+  double s = 0.;
+  for (int q = 0; q < 2; q++)
+    for (int i = 0; i < g.Vh; i++)
+      s += dist ? tmb_plaq_site<1>((const double2 *)U, (const double2 *)up, g, q, i)
+                : tmb_plaq_site<0>((const double2 *)U, nullptr, g, q, i);
+  return s / 3.0;
+}
 } /* extern "C" */

@@ -35,11 +35,12 @@ def load():
         "emul_pack_deriv": [dp, dp, i, i, i, i], "emul_unpack_deriv": [dp, dp, i, i, i, i],
         "emul_pack_deriv_halo": [dp, dp, dp, i, i, i, i],
         "emul_deriv": [i, dp, dp, dp, dp, dp, i, i, i, i, dp, d, i],
+        "emul_pack_gauge_first_slice": [dp, dp, i, i, i, i], "emul_plaquette": [dp, dp, i, i, i, i, i],
         "emul_nd_mee_inv": [dp, dp, dp, dp, d, d, i], "emul_nd_moo_sub_g5": [dp, dp, dp, dp, dp, dp, d, d, i],
     }
     for n, a in sig.items():
         getattr(E, n).argtypes = a
-        getattr(E, n).restype = i if n in ("emul_hop", "emul_hop12", "emul_hop_f") else None
+        getattr(E, n).restype = i if n in ("emul_hop", "emul_hop12", "emul_hop_f") else (d if n == "emul_plaquette" else None)
     return E
 
 
@@ -77,6 +78,13 @@ class Emul:
                           0 if halo is None else 1)
         out = np.zeros(32 * self.V); self.E.emul_unpack_deriv(out, dev, *self.dims)
         return out.reshape(self.V, 4, 8)
+
+    def plaquette(self, U, up=None):
+        """measure_plaquette on the device-layout gauge field; up = first-slice spatial links of the rank above"""
+        return self.E.emul_plaquette(U, up if up is not None else np.zeros(2), *self.dims, 0 if up is None else 1)
+
+    def pack_gauge_first_slice(self, U):
+        out = np.zeros(108 * self.S); self.E.emul_pack_gauge_first_slice(out, U, *self.dims); return out
 
     def pack_deriv_halo(self, soa_k, soa_l):
         out = np.zeros(24 * self.S); self.E.emul_pack_deriv_halo(out, soa_k, soa_l, *self.dims); return out

@@ -50,6 +50,8 @@ def test_benchmark_program(built):
 def test_invert_program_with_files(built):
     r = subprocess.run([str(built / "invert_b200")], capture_output=True, text=True, cwd=str(built), timeout=600)
     assert r.returncode == 0 and "# all checks passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    m = re.search(r"# The computed plaquette value is ([0-9.e+-]+)\.", r.stdout)  # lib_wrapper.c:232-235
+    assert m and 0.0 < float(m.group(1)) < 0.5  # hot start: small average plaquette
     assert os.path.exists(built / "conf.0000") and os.path.exists(built / "prop_b200.0000.00.00.inverted")
     # the files are LIME containers with the reference's record sequence (io/gauge_write.c:34-47, operator.c:532-605)
     from test_io_formats import lime_records

@@ -86,7 +86,7 @@ DEVICE_API = {
     "tmb_monomial_acc": (_i, [_i, C.POINTER(_d)]),
     "tmb_monomial_info": (_i, [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tmb_monomial_pf": (_vp, [_i]), "tmb_monomial_wfield": (_vp, [_i]),
-    "tmb_launch_count": (C.c_longlong, []), "tmb_measure_copy_gbs": (_i, [C.c_size_t, _i, C.POINTER(_d)]),
+    "tmb_measure_plaquette": (_i, [C.POINTER(_d)]), "tmb_launch_count": (C.c_longlong, []), "tmb_measure_copy_gbs": (_i, [C.c_size_t, _i, C.POINTER(_d)]),
 }
 
 _sp = _dp  # host spinor buffers (reference AoS layout) as float64 arrays
@@ -167,6 +167,7 @@ DROPIN_API = {
     "det_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
     "detratio_heatbath": (None, [_i, C.POINTER(HamiltonianField)]), "detratio_acc": (_d, [_i, C.POINTER(HamiltonianField)]),
     "detratio_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
+    "measure_plaquette": (_d, [_vp]),
     "construct_paramsXlfInfo": (_vp, [_d, _i]), "read_gauge_field": (_i, [C.c_char_p, _vp]),
     "write_gauge_field": (_i, [C.c_char_p, _i, _vp]), "read_spinor": (_i, [_sp, _sp, C.c_char_p, _i]),
     "tmb_write_propagator": (_i, [C.c_char_p, _sp, _sp, _i, _d, _i, C.c_char_p, _i]),

@@ -253,6 +253,20 @@ void convert_lexic_to_eo(spinor *const s, spinor *const r, spinor *const P) {
   sync_globals(); CHK(tmb_field_upload_lexic(dev(0), dev(1), (const double *)P)); down(s, 0); down(r, 1);
 }
 
+/* measure_gauge_action.c:46-106.  gf is normally g_gauge_field (every caller in the reference passes it); another
+ * field is uploaded for the measurement and the device copy is marked dirty again afterwards. */
+double measure_plaquette(const su3 **const gf) {
+  double res = 0.;
+  if ((su3 **)gf != g_gauge_field) {
+    if (!dropin_up) { fprintf(stderr, "tmLQCD-B200 FATAL: tmb_dropin_init has not been called\n"); exit(1); }
+    CHK(tmb_gauge_upload((const double *)gf[0]));
+    g_update_gauge_copy = 1;
+  } else
+    sync_globals();
+  CHK(tmb_measure_plaquette(&res));
+  return res;
+}
+
 /* ---------------- solvers ---------------- */
 /* solver/cg_her.c:62-143.  f == Qtm_pm_psi on VOLUME/2 sites (the case invert_eo and
  * solve_degenerate use; monomial_solve.c:134 selects by function-pointer identity the same
@@ -512,6 +526,9 @@ int tmLQCD_read_gauge(const int nconfig) {
     return -1;
   }
   if (g_proc_id == 0 && g_debug_level > 0) printf("# Finished reading gauge field.\n");
+  /* lib_wrapper.c:232-235 */
+  const double plaquette = measure_plaquette((const su3 **)g_gauge_field) / (6. * VOLUME * g_nproc);
+  if (g_proc_id == 0) printf("# The computed plaquette value is %.16e.\n", plaquette);
   return 0;
 }
 int tmLQCD_get_gauge_field_pointer(double **gf) {

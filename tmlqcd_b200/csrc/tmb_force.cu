@@ -77,6 +77,39 @@ cudaError_t tmb_launch_unpack_deriv(double *lex, const double *dev, tmb_geom g, 
   return cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------ plaquette (measure_gauge_action.c:46-106)
+ * grid.y = parity; one partial sum per CTA, summed in index order by the caller's final kernel (deterministic). */
+template <int DIST>
+__global__ void __launch_bounds__(128) plaq_kernel(const double2 *U, const double2 *Uup, tmb_geom g, double *partial) {
+  const int q = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+  double v = (i < g.Vh) ? tmb_plaq_site<DIST>(U, Uup, g, q, i) : 0.;
+  __shared__ double sh[4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+int tmb_plaq_grid(const tmb_geom &g) { return 2 * ((g.Vh + 127) / 128); }
+cudaError_t tmb_launch_plaquette(const double2 *U, const double2 *Uup, tmb_geom g, int dist, double *partial, cudaStream_t s) {
+  dim3 grid((g.Vh + 127) / 128, 2);
+  if (dist) plaq_kernel<1><<<grid, 128, 0, s>>>(U, Uup, g, partial);
+  else plaq_kernel<0><<<grid, 128, 0, s>>>(U, Uup, g, partial);
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) pack_gauge_first_slice_kernel(double2 *out, const double2 *U, tmb_geom g) {
+  const size_t n = (size_t)54 * g.S; /* [2][3][9][S] */
+  for (size_t x = (size_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (size_t)gridDim.x * 256) {
+    const int j = (int)(x % g.S); const int row = (int)(x / g.S);
+    const int e = row % 9, m = (row / 9) % 3, q = row / 27;
+    out[x] = U[(size_t)((q * 4 + (m + 1)) * 9 + e) * g.Vh + j]; /* slice t = 0: eo index j */
+  }
+}
+cudaError_t tmb_launch_pack_gauge_first_slice(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s) {
+  pack_gauge_first_slice_kernel<<<lin_grid((size_t)54 * g.S), 256, 0, s>>>(out, U, g);
+  return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ two-flavour hopping kernel
  * (lives in this translation unit to keep tmb_kernels.cu's compile time down) */
 template <int MODE, int HINTS>

@@ -147,6 +147,12 @@ cudaError_t tmb_launch_pack_deriv_halo(double2 *out, const double2 *k, const dou
 cudaError_t tmb_launch_pack_deriv(double *dev, const double *lex, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_unpack_deriv(double *lex, const double *dev, tmb_geom g, int add, cudaStream_t s);
 
+/* ---- plaquette (tmb_force.cu): measure_gauge_action.c:46-106; partial[] gets one sum per CTA (grid from tmb_plaq_grid) ---- */
+int tmb_plaq_grid(const tmb_geom &g);
+cudaError_t tmb_launch_plaquette(const double2 *U, const double2 *Uup, tmb_geom g, int dist, double *partial, cudaStream_t s);
+/* spatial links of the first time-slice, [2][3][9][S]: what the rank below needs for its last slice's t-x, t-y, t-z plaquettes */
+cudaError_t tmb_launch_pack_gauge_first_slice(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s);
+
 /* ---- two-flavour hopping (non-degenerate doublet): one gauge stream for both flavours ----
  * mode 0: (out0, out1) = (H in0, H in1)
  * mode 1: (out0, out1) = M_ee_inv_nd(H in0, H in1; mu, eps) with the flavour roles as tmb_launch_nd_mee_inv:

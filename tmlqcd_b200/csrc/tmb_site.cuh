@@ -470,3 +470,54 @@ TMB_HD void tmb_deriv_site(const tmb_deriv_fields &f, const tmb_geom &g, int q, 
   tmb_deriv_dir<2, FWD, DIST>(f, g, q, i, nb[4], t, loc, ka[2], c);
   tmb_deriv_dir<3, FWD, DIST>(f, g, q, i, nb[6], t, loc, ka[3], c);
 }
+
+/* ====================================================================================
+ * Plaquette: measure_plaquette, measure_gauge_action.c:46-106 - what tmLQCD_read_gauge prints after reading a
+ * configuration (wrapper/lib_wrapper.c:232-235) and every main stores as plaquette_energy.
+ *   P(x) = sum_{mu1 < mu2} Re tr( U_mu1(x) U_mu2(x+mu1) [ U_mu2(x) U_mu1(x+mu2) ]^dagger )
+ * One thread per site of either parity: 4 own links + 12 links of the forward neighbours, read from the same
+ * [parity][mu][9][Vh] field the hopping kernel uses (compulsory traffic 576 B/site, neighbours through L2).
+ * Uup (T split only): the spatial links U_1..3 of rank+1's first time-slice, [2][3][9][S] by owner parity.
+ * ==================================================================================== */
+TMB_HD void tmb_load_link(double2 u[9], const double2 *U, const tmb_geom &g, int q, int mu, int i) {
+  const double2 *ub = U + (size_t)((q * 4 + mu) * 9) * g.Vh + i;
+#pragma unroll
+  for (int e = 0; e < 9; e++) u[e] = ub[(size_t)e * g.Vh];
+}
+TMB_HD void tmb_su3_times_su3(double2 r[9], const double2 a[9], const double2 b[9]) { /* su3.h:583-592 */
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double2 x = c_mul(a[3 * i], b[j]);
+      c_mad(x, a[3 * i + 1], b[3 + j]);
+      c_mad(x, a[3 * i + 2], b[6 + j]);
+      r[3 * i + j] = x;
+    }
+}
+template <int DIST>
+TMB_HD double tmb_plaq_site(const double2 *U, const double2 *Uup, const tmb_geom &g, int q, int i) {
+  int nb[8];
+  const int t = tmb_neighbours(g, q, i, nb);
+  double2 own[4][9];
+#pragma unroll
+  for (int mu = 0; mu < 4; mu++) tmb_load_link(own[mu], U, g, q, mu, i);
+  double sum = 0.;
+#pragma unroll
+  for (int mu1 = 0; mu1 < 3; mu1++)
+#pragma unroll
+    for (int mu2 = mu1 + 1; mu2 < 4; mu2++) {
+      double2 w[9], w2[9], pr1[9], pr2[9];
+      if (DIST && mu1 == 0 && t == g.T - 1) { /* U_mu2(x + t) lives on the rank above */
+        const double2 *ub = Uup + (size_t)(((1 - q) * 3 + (mu2 - 1)) * 9) * g.S + (i - t * g.S);
+#pragma unroll
+        for (int e = 0; e < 9; e++) w[e] = ub[(size_t)e * g.S];
+      } else tmb_load_link(w, U, g, 1 - q, mu2, nb[2 * mu1]);
+      tmb_load_link(w2, U, g, 1 - q, mu1, nb[2 * mu2]); /* mu2 >= 1: a spatial shift, always local */
+      tmb_su3_times_su3(pr1, own[mu1], w);
+      tmb_su3_times_su3(pr2, own[mu2], w2);
+#pragma unroll
+      for (int e = 0; e < 9; e++) { sum += pr1[e].x * pr2[e].x; sum += pr1[e].y * pr2[e].y; } /* su3.h:656-665 */
+    }
+  return sum;
+}
