@@ -48,6 +48,9 @@ int tmb_set_hopping_phases(const double ka_re_im[8]);              /* ka0..ka3 a
 int tmb_set_mu(double g_mu);                                       /* g_mu = 2*kappa*mu (invert_eo.c:255) */
 int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_operators_nd.c */
 /* kernel configuration knobs (profiling / tuning; defaults are the measured best) */
+/* hop_variant: -1 (default) picks the residency per launch (384 resident threads per SM, or 448 when that saves a
+ * nearly empty trailing wave on a short launch, e.g. 16^3x32); 0 forces 384; 1..9 are block/occupancy tuning variants
+ * of the plain kernel; 10 forces 448 */
 int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
 int tmb_set_hop2_variant(int v); /* two-flavour hop: 0 = both flavours in one thread (default, measured best), 1 = lane-paired flavours */
 /* CompressionType of the reference (misc_types.h:33-37): 18 = full links (default), 12 = two rows streamed,

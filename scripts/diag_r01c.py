@@ -46,6 +46,32 @@ if what == "nd":
         res[v] = d.download(f[2])
     print("variants agree: rel", np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1]))
     d.close()
+elif what == "quant":
+    # wave quantisation: 384 (variant 0) vs 448 (variant 10) resident threads per SM, hop pair and CG iteration
+    for dims in ((32, 16, 16, 16), (16, 16, 16, 16), (48, 24, 24, 24), (8, 8, 8, 8)):
+        rng = np.random.default_rng(1)
+        d = tm.Device(*dims)
+        d.set_params(KAPPA, GMU)
+        d.gauge_upload(random_gauge(rng, d.V))
+        E, O = d.field(random_spinor(rng, d.Vh)), d.field(random_spinor(rng, d.Vh))
+        En, On, W = d.field(), d.field(), d.field()
+        for v in (0, 10, -1, 0, 10):
+            d.ck(d.lib.tmb_set_tuning(v, 1, 0))
+            n = 500
+            for _ in range(20):
+                d.lib.tmb_Hopping_Matrix(0, W, E); d.lib.tmb_Hopping_Matrix(1, En, W)
+            d.timer_start()
+            for _ in range(n):
+                d.lib.tmb_Hopping_Matrix(0, W, E); d.lib.tmb_Hopping_Matrix(1, En, W)
+            us = d.timer_stop() * 1e3 / (2 * n)
+            best = 1e9
+            for rep in range(3):
+                d.call("field_zero", On); d.ck(d.lib.tmb_sync())
+                t0 = time.perf_counter()
+                it = d.call("invert_eo", En, On, E, O, 1e-22, 5000, 1)
+                best = min(best, time.perf_counter() - t0)
+            print(f"{dims} variant {v:2d}: {us:7.2f} us/hop ({1536.0 * d.Vh / us / 1e3:7.1f} GB/s), invert_eo {it} it. {1e6 * best / it:7.2f} us/iteration", flush=True)
+        d.close()
 elif what == "cgpf":
     # CG time-to-solution with / without the L2 prefetch of the epilogue operands (tmb_set_overlap bit 3)
     dims = (48, 24, 24, 24)

@@ -78,6 +78,45 @@ def test_hopping_kernel_variants(oracle_lib, variant, hints, xblock):
         d.close()
 
 
+@pytest.mark.parametrize("hints", [1, 0])
+def test_residency_448_every_epilogue(oracle_lib, hints):
+    """variant 10 (64 threads x 7 CTAs per SM) serves every epilogue of the double kernel, the fused dot included"""
+    rng, o, d, g = _setup(oracle_lib, (4, 8, 6, 8), (1., 0., 0.5, 0.))
+    try:
+        d.ck(d.lib.tmb_set_tuning(10, hints, 0))
+        k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        dk, dp, dl = d.field(k), d.field(p), d.field()
+        exp = o.spinor()
+        o.Hopping_Matrix(1, exp, k); d.call("Hopping_Matrix", 1, dl, dk)
+        assert rel_l2(d.download(dl), exp) <= TOL
+        o.tm_times_Hopping_Matrix(0, exp, k, 0.3, -0.7); d.call("tm_times_Hopping_Matrix", 0, dl, dk, 0.3, -0.7)
+        assert rel_l2(d.download(dl), exp) <= TOL
+        o.tm_sub_Hopping_Matrix(1, exp, p, k, 1.0, 0.2); d.call("tm_sub_Hopping_Matrix", 1, dl, dp, dk, 1.0, 0.2)
+        assert rel_l2(d.download(dl), exp) <= TOL
+        o.Qtm_pm_psi(exp, k); d.call("Qtm_pm_psi", dl, dk)
+        assert rel_l2(d.download(dl), exp) <= TOL
+        xr = o.spinor()
+        itr = o.cg_her(xr, k, 2000, 1e-20, 1)
+        d.call("field_zero", dl)
+        it = d.call("cg_her", dl, dk, 2000, 1e-20, 1)
+        assert abs(it - itr) <= 1 and rel_l2(d.download(dl), xr) <= 1e-9
+    finally:
+        d.close()
+
+
+def test_automatic_residency_at_16x16x16x32(oracle_lib):
+    """the default (-1) takes the 448-thread kernels at 65536 sites per parity: same numbers"""
+    rng, o, d, g = _setup(oracle_lib, (32, 16, 16, 16), (1., 0., 0., 0.))
+    try:
+        k = random_spinor(rng, o.Vh)
+        dk, dl = d.field(k), d.field()
+        exp = o.spinor()
+        o.Qtm_pm_psi(exp, k); d.call("Qtm_pm_psi", dl, dk)
+        assert rel_l2(d.download(dl), exp) <= TOL
+    finally:
+        d.close()
+
+
 @pytest.mark.parametrize("flags", [1, 2, 3])
 @pytest.mark.parametrize("loopback", [0, 1, 2])
 def test_overlap_flags(oracle_lib, flags, loopback):

@@ -75,7 +75,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = 0, hints = 1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 0;
+  int hop_variant = -1, hints = 1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 0;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -210,7 +210,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = 0; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 0;
+  C.launches = 0; C.hop_variant = -1; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 0;
   C.init = true;
   return 0;
 }
@@ -393,7 +393,7 @@ extern "C" int tmb_set_nd(double mubar, double epsbar, double invmaxev) {
 extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < 0 || v > 1) return fail(-7, "hop2 variant must be 0 or 1"); C.hop2_variant = v; return 0; }
 extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   NEED_INIT();
-  if (hop_variant < 0 || hop_variant > 9) return fail(-7, "hop_variant must be 0..9");
+  if (hop_variant < -1 || hop_variant > 10) return fail(-7, "hop_variant must be -1 (automatic) .. 10");
   if (xblock > 0 && C.g.LX % xblock) return fail(-7, "xblock must divide LX");
   C.hop_variant = hop_variant; C.hints = cache_hints ? 1 : 0; C.xblock = xblock;
   return 0;
@@ -578,6 +578,15 @@ struct HopOpt {
 };
 static int ensure_gauge32();
 static int ensure_gauge12(int prec);
+/* Wave quantisation: a launch of n sites occupies n / (148 x R) waves of resident threads, R = 384 (168 registers)
+ * or 448 (144 registers, variant 10).  The fuller residency wins when it saves a nearly empty trailing wave on a
+ * launch of only a few waves (16^3x32: 1.15 -> 0.99); on long launches the extra spill traffic costs more than the
+ * tail (24^3x48: 5.84 vs 5.004 waves - the 448 variant would ADD a wave there). */
+static bool hop_residency_448(int nsites) {
+  const double w384 = nsites / (148. * 384.), w448 = nsites / (148. * 448.);
+  if (w384 > 4.) return false;
+  return ceil(w448) < ceil(w384);
+}
 static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
   if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
@@ -606,6 +615,8 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     a.dist = 0; a.site0 = o.site0; a.nsites = o.nsites < 0 ? C.g.Vh : o.nsites; a.split = a.nsites; a.gap = 0;
     /* tuning variants exist for the plain Hopping_Matrix kernel only */
     a.variant = (o.mode == 0 && !a.dot && !a.recon12 && !o.prec) ? C.hop_variant : 0;
+    if (C.hop_variant == 10 || C.hop_variant == -1) /* 448-thread residency: every epilogue of the plain double kernel */
+      a.variant = (!a.recon12 && !o.prec && (C.hop_variant == 10 || hop_residency_448(a.nsites))) ? 10 : 0;
     a.xblock = o.nsites < 0 ? C.xblock : 0;
     np = tmb_hop_grid(a);
     a.fin_total = np;

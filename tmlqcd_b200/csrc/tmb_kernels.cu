@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
 #define TMB_HOP_MINB_F 4
 
 static int hop_variant_block(int variant) {
-  static const int b[10] = {TMB_HOP_BLOCK, 64, 64, 128, 128, 128, 256, 256, 96, 192};
-  return (variant >= 0 && variant < 10) ? b[variant] : TMB_HOP_BLOCK;
+  static const int b[11] = {TMB_HOP_BLOCK, 64, 64, 128, 128, 128, 256, 256, 96, 192, 64};
+  return (variant >= 0 && variant < 11) ? b[variant] : TMB_HOP_BLOCK;
 }
 int tmb_hop_grid(const tmb_hop_launch &a) {
   const int b = a.prec ? TMB_HOP_BLOCK_F : hop_variant_block(a.variant);
@@ -363,6 +363,24 @@ template <int CFG>
 static cudaError_t hop_dist_f(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dist == 2) return hop_mode_f<2, CFG>(a, s);
   return a.dist ? hop_mode_f<1, CFG>(a, s) : hop_mode_f<0, CFG>(a, s);
+}
+/* Variant 10: 64 threads x 7 CTAs per SM = 448 resident threads (144 registers) instead of 384 (168 registers), for
+ * ALL epilogues of the plain double-precision kernel.  Slightly more spill traffic per site, but a different wave
+ * count: 16^3x32 (65536 sites per parity) is 1.15 waves of 148 x 384 threads - a nearly empty second wave - and
+ * 0.99 waves of 148 x 448.  Chosen per lattice by tmb_capi.cu (see hop_residency()). */
+template <int HINTS>
+static cudaError_t hop_mode_448(const tmb_hop_launch &a, cudaStream_t s) {
+  if (a.dot) {
+    if (a.mode != 2) return cudaErrorInvalidValue;
+    return hop_go<double2, 2, 0, 1, HINTS, 64, 7>(a, s);
+  }
+  switch (a.mode) {
+    case 0: return hop_go<double2, 0, 0, 0, HINTS, 64, 7>(a, s);
+    case 1: return hop_go<double2, 1, 0, 0, HINTS, 64, 7>(a, s);
+    case 2: return hop_go<double2, 2, 0, 0, HINTS, 64, 7>(a, s);
+    case 3: return hop_go<double2, 3, 0, 0, HINTS, 64, 7>(a, s);
+  }
+  return cudaErrorInvalidValue;
 }
 template <int DIST, int HINTS>
 static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
@@ -417,6 +435,10 @@ cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s) {
   }
   if (a.recon12) return hop_dist<3>(a, s);
   const int variant = a.variant;
+  if (variant == 10) {
+    if (a.dist) return cudaErrorInvalidValue;
+    return a.hints ? hop_mode_448<1>(a, s) : hop_mode_448<0>(a, s);
+  }
   if (variant > 0) {
     if (a.mode != 0 || a.dist || a.dot) return cudaErrorInvalidValue;
     return a.hints ? hop_tune<1>(a, variant, s) : hop_tune<0>(a, variant, s);
