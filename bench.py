@@ -254,7 +254,7 @@ def main():
     g, ref, gauge_how = make_gauge(dims, 123456 if world == 1 else 1000 + rank)
     dev.set_params(KAPPA, GMU)
     if args.variant is not None or args.hints is not None or args.xblock is not None:
-        dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, 1 if args.hints is None else args.hints, args.xblock or 0))
+        dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, -1 if args.hints is None else args.hints, args.xblock or 0))
     dev.ck(lib.tmb_set_overlap(args.overlap))
     if (args.loopback or args.loopback2) and world == 1:
         dev.ck(lib.tmb_comm_loopback(2 if args.loopback2 else 1))
@@ -301,7 +301,7 @@ def main():
                         f"{Vh * BYTES_SITE / per / 1e6:8.1f} GB/s {Vh * FLOP_SITE / per / 1e6:8.1f} GFLOP/s")
         results.sort()
         log("best:", results[:5])
-        dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, 1 if args.hints is None else args.hints, args.xblock or 0))
+        dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, -1 if args.hints is None else args.hints, args.xblock or 0))
 
     if args.sweep_overlap and rank == 0:
         for flags in (0, 1, 2, 3):
@@ -312,7 +312,7 @@ def main():
                 per = ms / 400.0
                 log(f"overlap flags={flags} (pdl={flags & 1} prefetch={flags >> 1}) variant={variant}: {per * 1e3:8.2f} us/hop "
                     f"{Vh * BYTES_SITE / per / 1e6:8.1f} GB/s")
-        dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, 1 if args.hints is None else args.hints, args.xblock or 0))
+        dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, -1 if args.hints is None else args.hints, args.xblock or 0))
         dev.ck(lib.tmb_set_overlap(args.overlap))
     # ---- timed region: K pairs, device resident, inputs larger than L2 (gauge alone is 1152 B/site) ----
     sampler = ClockSampler(local_rank)

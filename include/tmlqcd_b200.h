@@ -50,14 +50,15 @@ int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_ope
 /* kernel configuration knobs (profiling / tuning; defaults are the measured best) */
 /* hop_variant: -1 (default) picks the residency per launch (384 resident threads per SM, or 448 when that saves a
  * nearly empty trailing wave on a short launch, e.g. 16^3x32); 0 forces 384; 1..9 are block/occupancy tuning variants
- * of the plain kernel; 10 forces 448 */
+ * of the plain kernel; 10 forces 448.  cache_hints: 1 = L2 eviction policies on the link / spinor loads, 0 = plain
+ * loads, -1 (default) = policies only when links + CG vectors exceed the L2 (see eff_hints() in tmb_capi.cu) */
 int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
 int tmb_set_hop2_variant(int v); /* two-flavour hop: 0 = both flavours in one thread (default, measured best), 1 = lane-paired flavours */
 /* CompressionType of the reference (misc_types.h:33-37): 18 = full links (default), 12 = two rows streamed,
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);
 int tmb_set_host_chunks(int n); /* chunks of the pipelined host-pointer Hopping_Matrix (default 8, the measured best at 24^3x48) */
-int tmb_set_overlap(int flags); /* bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows, bit2: no CUDA-graph replay in the CG, bit3: L2 prefetch of the epilogue operands (p, dotw) */
+int tmb_set_overlap(int flags); /* bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows, bit2: no CUDA-graph replay in the CG, bit3: L2 prefetch of the epilogue operands (p, dotw), bit4: the CG takes <p, A p> from the last hop (operand load) instead of |Q- p|^2 from the second */
 
 /* ---- memory ---- */
 void *tmb_field_alloc(void);         /* one eo spinor field, VOLUME/2 sites, device SoA layout */

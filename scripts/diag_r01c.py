@@ -72,6 +72,51 @@ elif what == "quant":
                 best = min(best, time.perf_counter() - t0)
             print(f"{dims} variant {v:2d}: {us:7.2f} us/hop ({1536.0 * d.Vh / us / 1e3:7.1f} GB/s), invert_eo {it} it. {1e6 * best / it:7.2f} us/iteration", flush=True)
         d.close()
+elif what == "hints":
+    # small lattices fit (partly) in the 126 MB L2: is the evict-first policy on the gauge stream still right there?
+    for dims in ((8, 8, 8, 8), (16, 8, 8, 8), (16, 16, 16, 16), (32, 16, 16, 16), (24, 24, 24, 24)):
+        rng = np.random.default_rng(1)
+        d = tm.Device(*dims)
+        d.set_params(KAPPA, GMU)
+        d.gauge_upload(random_gauge(rng, d.V))
+        E, O = d.field(random_spinor(rng, d.Vh)), d.field(random_spinor(rng, d.Vh))
+        En, On, W = d.field(), d.field(), d.field()
+        for hints in (1, 0, 1, 0):
+            d.ck(d.lib.tmb_set_tuning(-1, hints, 0))
+            n = 500
+            for _ in range(20):
+                d.lib.tmb_Hopping_Matrix(0, W, E); d.lib.tmb_Hopping_Matrix(1, En, W)
+            d.timer_start()
+            for _ in range(n):
+                d.lib.tmb_Hopping_Matrix(0, W, E); d.lib.tmb_Hopping_Matrix(1, En, W)
+            us = d.timer_stop() * 1e3 / (2 * n)
+            best = 1e9
+            for rep in range(3):
+                d.call("field_zero", On); d.ck(d.lib.tmb_sync())
+                t0 = time.perf_counter()
+                it = d.call("invert_eo", En, On, E, O, 1e-22, 5000, 1)
+                best = min(best, time.perf_counter() - t0)
+            print(f"{dims} hints {hints}: {us:7.2f} us/hop ({1536.0 * d.Vh / us / 1e3:7.1f} GB/s), invert_eo {it} it. {1e6 * best / it:7.2f} us/iteration", flush=True)
+        d.close()
+elif what == "selfnorm":
+    for dims in ((48, 24, 24, 24), (32, 16, 16, 16)):
+        rng = np.random.default_rng(1)
+        d = tm.Device(*dims)
+        d.set_params(KAPPA, GMU)
+        d.gauge_upload(random_gauge(rng, d.V))
+        E, O = d.field(random_spinor(rng, d.Vh)), d.field(random_spinor(rng, d.Vh))
+        En, On = d.field(), d.field()
+        for flags in (16, 0, 16, 0):
+            d.ck(d.lib.tmb_set_overlap(flags))
+            for solver in ("invert_eo", "invert_eo_mixed"):
+                best = 1e9
+                for rep in range(4):
+                    d.call("field_zero", On); d.ck(d.lib.tmb_sync())
+                    t0 = time.perf_counter()
+                    it = d.call(solver, En, On, E, O, 1e-22, 5000, 1)
+                    best = min(best, time.perf_counter() - t0)
+                print(f"{dims} overlap flags {flags:2d} {solver:16s}: {it} iterations, {1e3 * best:8.3f} ms ({1e6 * best / it:7.2f} us/iteration)", flush=True)
+        d.close()
 elif what == "cgpf":
     # CG time-to-solution with / without the L2 prefetch of the epilogue operands (tmb_set_overlap bit 3)
     dims = (48, 24, 24, 24)

@@ -56,6 +56,8 @@ def main():
 
     dk, dp, dl, dx = d.field(k[slh]), d.field(p[slh]), d.field(), d.field()
     res = {}
+    plaq = C.c_double(0.)
+    d.ck(d.lib.tmb_measure_plaquette(C.byref(plaq)))  # all-reduced: the same value on every rank
     for ieo in (0, 1):
         d.call("Hopping_Matrix", ieo, dl, dk); res[f"hop{ieo}"] = gather(dl)
         d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3); res[f"tm_sub{ieo}"] = gather(dl)
@@ -106,6 +108,7 @@ def main():
             print(f"hop{ieo} rel {r1:.2e}  tm_sub{ieo} rel {r2:.2e}"); ok &= r1 <= 1e-13 and r2 <= 1e-13
         o.Qtm_pm_psi(e, k); r = rel_l2(res["Qtm_pm"], e); print(f"Qtm_pm rel {r:.2e}"); ok &= r <= 1e-13
         r = abs(sq / o.square_norm(k, Vh) - 1); print(f"global square_norm rel {r:.2e}"); ok &= r < 1e-14
+        r = abs(plaq.value / o.measure_plaquette() - 1); print(f"measure_plaquette rel {r:.2e}"); ok &= r < 1e-13
         x = o.spinor(); itr = o.cg_her(x, k, 2000, 1e-22, 1); r = rel_l2(res["cg_x"], x)
         print(f"cg_her iters {it} (oracle {itr}) x rel {r:.2e}"); ok &= abs(it - itr) <= 1 and r <= 1e-10
         en, on = o.spinor(), o.spinor(); itr = o.invert_eo_cg(en, on, k, p, 1e-22, 2000, 1)

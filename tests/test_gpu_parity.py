@@ -104,6 +104,34 @@ def test_residency_448_every_epilogue(oracle_lib, hints):
         d.close()
 
 
+@pytest.mark.parametrize("loopback", [0, 1, 2])
+def test_cg_pro_from_second_hop(oracle_lib, loopback):
+    """<p, Q+ Q- p> taken as |Q- p|^2 in the epilogue of the second hop (default) against the operand dot product in the
+    last hop (tmb_set_overlap bit 4): same iteration count, same solution, double and mixed precision"""
+    rng, o, d, g = _setup(oracle_lib, (8, 4, 6, 8), (1., 0.3, 0., 0.7))
+    try:
+        if loopback:
+            d.ck(d.lib.tmb_comm_loopback(loopback)); d.gauge_upload(g)
+        k = random_spinor(rng, o.Vh)
+        dk, dx = d.field(k), d.field()
+        xr = o.spinor()
+        itr = o.cg_her(xr, k, 2000, 1e-22, 1)
+        out = {}
+        for flags in (0, 16):
+            d.ck(d.lib.tmb_set_overlap(flags))
+            d.call("field_zero", dx)
+            it = d.call("cg_her", dx, dk, 2000, 1e-22, 1)
+            out[flags] = (it, d.download(dx))
+            assert abs(it - itr) <= 1 and rel_l2(out[flags][1], xr) <= 1e-10
+            d.call("field_zero", dx)
+            itm = d.call("mixed_cg_her", dx, dk, 2000, 1e-22, 1)
+            assert itm > 0 and rel_l2(d.download(dx), xr) <= 1e-8
+        assert out[0][0] == out[16][0] and rel_l2(out[0][1], out[16][1]) <= 1e-12
+    finally:
+        d.ck(d.lib.tmb_set_overlap(0))
+        d.close()
+
+
 def test_automatic_residency_at_16x16x16x32(oracle_lib):
     """the default (-1) takes the 448-thread kernels at 65536 sites per parity: same numbers"""
     rng, o, d, g = _setup(oracle_lib, (32, 16, 16, 16), (1., 0., 0., 0.))

@@ -75,7 +75,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = -1, hints = 1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 0;
+  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 0, cg_selfnorm = 1;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -210,7 +210,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = -1; C.hints = 1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 0;
+  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 0; C.cg_selfnorm = 1;
   C.init = true;
   return 0;
 }
@@ -395,14 +395,14 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   NEED_INIT();
   if (hop_variant < -1 || hop_variant > 10) return fail(-7, "hop_variant must be -1 (automatic) .. 10");
   if (xblock > 0 && C.g.LX % xblock) return fail(-7, "xblock must divide LX");
-  C.hop_variant = hop_variant; C.hints = cache_hints ? 1 : 0; C.xblock = xblock;
+  C.hop_variant = hop_variant; C.hints = cache_hints < 0 ? -1 : (cache_hints ? 1 : 0); C.xblock = xblock;
   return 0;
 }
 /* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
 /* number of time-slice chunks of the pipelined host-pointer Hopping_Matrix (1..64) */
 extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 1 || n > MAXCHUNK) return fail(-7, "host chunks must be in [1, %d]", MAXCHUNK); C.host_chunks = n; return 0; }
 extern "C" int tmb_set_overlap(int flags) {
-  NEED_INIT(); C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1;
+  NEED_INIT(); C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1; C.cg_selfnorm = (flags & 16) ? 0 : 1;
   C.p2p_diag = (flags >> 3) & 31; /* timing diagnostics only: 1 = boundary reads from the LOCAL field, 2 = no end-of-hop handshake */
   return 0;
 }
@@ -571,6 +571,7 @@ static double2 *scratch(int k) {
 struct HopOpt {
   int mode = 0; double2 cf = {1., 0.}; const void *p = nullptr;
   const void *dotw = nullptr; const tmb_cg_state *st = nullptr;
+  bool selfnorm = false;      /* fused reduction of |out|^2 instead of <dotw, out> */
   int *npartial = nullptr;
   int site0 = 0, nsites = -1; /* sub-range of output sites (single rank only); -1: all */
   int prec = 0;               /* 0: double fields, 1: float fields + float gauge copy */
@@ -582,6 +583,14 @@ static int ensure_gauge12(int prec);
  * or 448 (144 registers, variant 10).  The fuller residency wins when it saves a nearly empty trailing wave on a
  * launch of only a few waves (16^3x32: 1.15 -> 0.99); on long launches the extra spill traffic costs more than the
  * tail (24^3x48: 5.84 vs 5.004 waves - the 448 variant would ADD a wave there). */
+/* L2 cache policies of the hop kernels (gauge links evict-first / no L1 allocation, neighbour spinors evict-last):
+ * right when the links stream through L2 once per hop (24^3x48: 84.6 vs 92.3 us), wrong when gauge field + the six CG
+ * vectors (2304 B per site of one parity) fit in the 126 MB L2 - then evict-first throws away links the next hop
+ * would have hit (16^4: CG 77.8 -> 60.1 us/iteration without the policies).  -1 = decide by the working set. */
+static int eff_hints() {
+  if (C.hints >= 0) return C.hints;
+  return 2304. * C.g.Vh > 100e6 ? 1 : 0;
+}
 static bool hop_residency_448(int nsites) {
   const double w384 = nsites / (148. * 384.), w448 = nsites / (148. * 448.);
   if (w384 > 4.) return false;
@@ -607,7 +616,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   }
   a.partial = C.partial; a.st = o.st; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
-  a.cf = o.cf; a.mode = o.mode; a.dot = o.dotw ? 1 : 0; a.hints = C.hints;
+  a.cf = o.cf; a.mode = o.mode; a.dot = (o.dotw || o.selfnorm) ? 1 : 0; a.hints = eff_hints();
   a.pdl = C.pdl; a.prefetch = C.prefetch;
   a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && C.nranks == 1) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
   int np = 0;
@@ -761,18 +770,22 @@ extern "C" int tmb_tm_sub_H_eo_gamma5(void *l, const void *p, const void *k, int
 }
 
 /* Qtm_pm_psi (tm_operators.c:338-345): 4 hops, each with its diagonal fused in the epilogue.
- * dotw/st: the CG asks for <dotw, l> and the early exit. */
+ * dotw/st: the CG asks for <dotw, l> and the early exit.  For dotw == k (the CG's <p, A p>, cg_her.c:93) the
+ * reduction moves to the SECOND hop as |Q- k|^2: Q+ is the adjoint of Q-, so <k, Q+ Q- k> = |Q- k|^2, and the
+ * squared norm of a hop's own output needs no operand - 192 B/site and the widest epilogue of the CG saved. */
 static int qtm_pm(double2 *l, const double2 *k, const double2 *dotw, const tmb_cg_state *st, int *np,
                   int fin_op = -1, int fin_slot = 0) {
   SCR(w0, 0); SCR(w1, 1);
+  const bool self = dotw != nullptr && dotw == k && C.cg_selfnorm;
   HopOpt a; a.mode = 1; a.cf = z_inv(-1.); a.st = st;
   TRY(hop(0, w1, k, a));
   HopOpt b; b.mode = 2; b.cf = z_fwd(-1.); b.p = k; b.st = st;
+  if (self) { b.selfnorm = true; b.npartial = np; b.fin_op = fin_op; b.fin_slot = fin_slot; }
   TRY(hop(1, w0, w1, b));
   HopOpt c; c.mode = 1; c.cf = z_inv(+1.); c.st = st;
   TRY(hop(0, w1, w0, c));
-  HopOpt d; d.mode = 2; d.cf = z_fwd(+1.); d.p = w0; d.st = st; d.dotw = dotw; d.npartial = np;
-  d.fin_op = fin_op; d.fin_slot = fin_slot;
+  HopOpt d; d.mode = 2; d.cf = z_fwd(+1.); d.p = w0; d.st = st;
+  if (!self) { d.dotw = dotw; d.npartial = np; d.fin_op = fin_op; d.fin_slot = fin_slot; }
   TRY(hop(1, l, w1, d));
   return 0;
 }
@@ -969,7 +982,7 @@ static int hop2(int ieo, double2 *o0, double2 *o1, const double2 *i0, const doub
   memset(&a, 0, sizeof(a));
   a.in0 = i0; a.in1 = i1; a.out0 = o0; a.out1 = o1; a.p0 = p0; a.p1 = p1; a.U = C.U; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
-  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = C.hints; a.variant = C.hop2_variant;
+  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = eff_hints(); a.variant = C.hop2_variant;
   KL(tmb_launch_hop2(a, C.s_main));
   return 0;
 }

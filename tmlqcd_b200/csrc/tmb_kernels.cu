@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
 #pragma unroll
       for (int c = 0; c < 12; c++) {
         if (MODE >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.p + (size_t)c * a.g.Vh + i));
-        if (DOT) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.dotw + (size_t)c * a.g.Vh + i));
+        if (DOT && a.dotw) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.dotw + (size_t)c * a.g.Vh + i));
       }
     }
     V2 r[12];
@@ -287,19 +287,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
      * (Qtm_minus_psi(l, l), invert_eo.c:270), so the compiler must not move a load across a store,
      * and interleaving them serialises 12 DRAM round trips per thread (measured: 138 us instead of
      * 80 us per launch at 24^3x48, profiles/r01_cg_launches_before_epilogue_fix.csv). */
+    /* DOT with dotw == nullptr: the squared norm of the OUTPUT (no extra operand).  The CG uses it on the second
+     * hop of Qtm_pm_psi: <p, Q+ Q- p> = |Q- p|^2 because Q+ is the adjoint of Q- (gamma5-hermiticity). */
+    const bool selfnorm = DOT && dw_ == nullptr;
     V2 pc[12], dw[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) {
       if (MODE >= 2) pc[c] = pp[(size_t)c * a.g.Vh + i];
-      if (DOT) dw[c] = dw_[(size_t)c * a.g.Vh + i];
+      if (DOT && !selfnorm) dw[c] = dw_[(size_t)c * a.g.Vh + i];
     }
     V2 o[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) {
       o[c] = tmb_epilogue<MODE>(c, r[c], MODE >= 2 ? pc[c] : mk2<V2>(0, 0), cf);
       if (DOT) {
-        dsum += (double)dw[c].x * (double)o[c].x;
-        dsum += (double)dw[c].y * (double)o[c].y;
+        const V2 wv = selfnorm ? o[c] : dw[c];
+        dsum += (double)wv.x * (double)o[c].x;
+        dsum += (double)wv.y * (double)o[c].y;
       }
     }
 #pragma unroll
