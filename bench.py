@@ -108,6 +108,25 @@ def make_gauge(dims, seed):
     return g, None, f"numpy QR random SU(3) (seed {seed})"
 
 
+def chunked_fields(dims, rank, chunk_t):
+    """Decomposition-independent synthetic inputs for the strong-scaling series: the GLOBAL lattice is cut into chunks
+    of `chunk_t` time-slices, chunk c of the global lattice is drawn from numpy seeds tied to c, and a rank assembles
+    the chunks of its slab (t is the slowest index of the lexicographic and of the even/odd orderings, so chunks
+    concatenate).  Every N that divides the number of chunks sees the same global gauge field and sources."""
+    T, LX, LY, LZ = dims
+    assert T % chunk_t == 0 and chunk_t % 2 == 0
+    per = T // chunk_t
+    gs, srcs = [], [[], [], []]
+    for c in range(per):
+        gc = rank * per + c
+        g, _, _ = make_gauge((chunk_t, LX, LY, LZ), 7000 + gc)
+        gs.append(g)
+        rng = np.random.default_rng(8000 + gc)
+        for k in range(3):
+            srcs[k].append(rng.normal(scale=np.sqrt(0.5), size=(chunk_t * LX * LY * LZ // 2, 24)))
+    return np.concatenate(gs), [np.concatenate(x) for x in srcs], f"numpy QR random SU(3), global chunks of {chunk_t} time-slices (seed 7000 + chunk)"
+
+
 def pinned(dev, shape):
     n = int(np.prod(shape))
     p = dev.lib.tmb_host_alloc(n * 8)
@@ -196,6 +215,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lattice", default=None, help="local TxLXxLYxLZ, e.g. 48x24x24x24")
+    ap.add_argument("--global-chunk-t", type=int, default=0,
+                    help="strong-scaling series: draw gauge field and sources per chunk of this many GLOBAL time-slices, so every N sees the same global problem")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -251,7 +272,12 @@ def main():
         dev.ck(lib.tmb_comm_init(C.cast(idbuf, C.c_void_p), world, rank))
 
     V, Vh = dev.V, dev.Vh
-    g, ref, gauge_how = make_gauge(dims, 123456 if world == 1 else 1000 + rank)
+    chunk_src = None
+    if args.global_chunk_t:
+        g, chunk_src, gauge_how = chunked_fields(dims, rank, args.global_chunk_t)
+        ref = None
+    else:
+        g, ref, gauge_how = make_gauge(dims, 123456 if world == 1 else 1000 + rank)
     dev.set_params(KAPPA, GMU)
     if args.variant is not None or args.hints is not None or args.xblock is not None:
         dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, -1 if args.hints is None else args.hints, args.xblock or 0))
@@ -260,7 +286,7 @@ def main():
         dev.ck(lib.tmb_comm_loopback(2 if args.loopback2 else 1))
     dev.gauge_upload(g)
     rng = np.random.default_rng(99 + rank)
-    src = rng.normal(scale=np.sqrt(0.5), size=(Vh, 24))
+    src = chunk_src[0] if chunk_src else rng.normal(scale=np.sqrt(0.5), size=(Vh, 24))
     f0, f1, f2 = dev.field(src), dev.field(), dev.field()
 
     def barrier():
@@ -406,6 +432,8 @@ def main():
     # ---- eo-CG time-to-solution (the configs[1] solve): device-resident and through invert_eo with host buffers ----
     if not args.skip_cg:
         E = rng.normal(scale=np.sqrt(0.5), size=(Vh, 24)); O = rng.normal(scale=np.sqrt(0.5), size=(Vh, 24))
+        if chunk_src:
+            E, O = chunk_src[1], chunk_src[2]
         dE, dO, dEn, dOn = dev.field(E), dev.field(O), dev.field(), dev.field()
         dev.call("invert_eo", dEn, dOn, dE, dO, CG_EPS_SQ, CG_MAXITER, 1)  # warm-up solve
         dev.call("field_zero", dOn)
