@@ -72,6 +72,26 @@ elif what == "quant":
                 best = min(best, time.perf_counter() - t0)
             print(f"{dims} variant {v:2d}: {us:7.2f} us/hop ({1536.0 * d.Vh / us / 1e3:7.1f} GB/s), invert_eo {it} it. {1e6 * best / it:7.2f} us/iteration", flush=True)
         d.close()
+elif what == "restart":
+    # fixed cost of a solve that converges at once (HMC derivative calls with a good chronological guess): CUDA-graph
+    # capture + instantiation per solve against plain launches (tmb_set_overlap bit 2)
+    for dims in ((32, 16, 16, 16), (48, 24, 24, 24)):
+        rng = np.random.default_rng(1)
+        d = tm.Device(*dims)
+        d.set_params(KAPPA, GMU)
+        d.gauge_upload(random_gauge(rng, d.V))
+        k, x = d.field(random_spinor(rng, d.Vh)), d.field()
+        it = d.call("cg_her", x, k, 5000, 1e-20, 1)
+        for flags in (0, 4, 0, 4):
+            d.ck(d.lib.tmb_set_overlap(flags))
+            ts = []
+            for rep in range(6):
+                d.ck(d.lib.tmb_sync())
+                t0 = time.perf_counter()
+                it2 = d.call("cg_her", x, k, 5000, 1e-18, 1)  # x already solves to 1e-20
+                ts.append(time.perf_counter() - t0)
+            print(f"{dims} first solve {it} it.; restart from the solution: {it2} it., flags {flags}: min {1e6 * min(ts):8.1f} us  all {[round(1e6 * t) for t in ts]}", flush=True)
+        d.close()
 elif what == "hints":
     # small lattices fit (partly) in the 126 MB L2: is the evict-first policy on the gauge stream still right there?
     for dims in ((8, 8, 8, 8), (16, 8, 8, 8), (16, 16, 16, 16), (32, 16, 16, 16), (24, 24, 24, 24)):
