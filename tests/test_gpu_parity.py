@@ -61,7 +61,7 @@ def test_hopping_and_epilogues(oracle_lib, dims, theta, loopback):
         d.close()
 
 
-@pytest.mark.parametrize("variant", range(0, 10))
+@pytest.mark.parametrize("variant", range(0, 11))
 @pytest.mark.parametrize("hints,xblock", [(1, 0), (0, 0), (1, 2)])
 def test_hopping_kernel_variants(oracle_lib, variant, hints, xblock):
     """every tuning variant of the plain kernel computes the same thing"""
