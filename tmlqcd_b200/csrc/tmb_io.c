@@ -189,6 +189,7 @@ int write_gauge_field(char *filename, int prec, paramsXlfInfo const *xlf) {
   DML_Checksum cs = {0, 0};
   unsigned char buf[4 * sizeof(su3)];
   su3 tmp[4];
+  memset(tmp, 0, sizeof(tmp));
   static const int file_mu[4] = {1, 2, 3, 0}; /* file order x,y,z,t; memory order t,x,y,z */
   for (int t = 0; t < T; t++) for (int z = 0; z < LZ; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
     const uint64_t rank = (uint64_t)(((t * LZ + z) * LY + y) * LX + x);
