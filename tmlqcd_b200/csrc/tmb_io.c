@@ -34,18 +34,20 @@ tmb_gauge_info GaugeInfo = {0., 0, {0, 0}, NULL, NULL};
 static inline uint64_t bswap64(uint64_t x) { return __builtin_bswap64(x); }
 static inline uint32_t bswap32(uint32_t x) { return __builtin_bswap32(x); }
 static int host_is_little(void) { const uint16_t one = 1; return *(const unsigned char *)&one == 1; }
+/* All accesses go through memcpy: the buffers are su3 / double / unsigned char objects, and reading them through
+ * uint64_t / uint32_t lvalues would break the aliasing rules (gcc -O2 then drops the stores that filled them). */
 static void be64_copy(void *dst, const void *src, size_t n) { /* n doubles */
-  const uint64_t *s = (const uint64_t *)src; uint64_t *d = (uint64_t *)dst;
-  if (host_is_little()) for (size_t i = 0; i < n; i++) d[i] = bswap64(s[i]);
-  else memcpy(dst, src, 8 * n);
+  if (!host_is_little()) { memcpy(dst, src, 8 * n); return; }
+  const unsigned char *s = (const unsigned char *)src; unsigned char *d = (unsigned char *)dst;
+  for (size_t i = 0; i < n; i++) { uint64_t u; memcpy(&u, s + 8 * i, 8); u = bswap64(u); memcpy(d + 8 * i, &u, 8); }
 }
 static void be32_from_double(void *dst, const double *src, size_t n) {
-  uint32_t *d = (uint32_t *)dst;
-  for (size_t i = 0; i < n; i++) { float f = (float)src[i]; uint32_t u; memcpy(&u, &f, 4); d[i] = host_is_little() ? bswap32(u) : u; }
+  unsigned char *d = (unsigned char *)dst;
+  for (size_t i = 0; i < n; i++) { float f = (float)src[i]; uint32_t u; memcpy(&u, &f, 4); if (host_is_little()) u = bswap32(u); memcpy(d + 4 * i, &u, 4); }
 }
 static void double_from_be32(double *dst, const void *src, size_t n) {
-  const uint32_t *s = (const uint32_t *)src;
-  for (size_t i = 0; i < n; i++) { uint32_t u = host_is_little() ? bswap32(s[i]) : s[i]; float f; memcpy(&f, &u, 4); dst[i] = (double)f; }
+  const unsigned char *s = (const unsigned char *)src;
+  for (size_t i = 0; i < n; i++) { uint32_t u; memcpy(&u, s + 4 * i, 4); if (host_is_little()) u = bswap32(u); float f; memcpy(&f, &u, 4); dst[i] = (double)f; }
 }
 
 /* ------------------------------------------------------------------ SciDAC checksum: io/dml.c:49-60, io/DML_crc32.c */
