@@ -616,7 +616,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   }
   a.partial = C.partial; a.st = o.st; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
-  a.cf = o.cf; a.mode = o.mode; a.dot = (o.dotw || o.selfnorm) ? 1 : 0; a.hints = eff_hints();
+  a.cf = o.cf; a.mode = o.mode; a.dot = o.selfnorm ? 2 : (o.dotw ? 1 : 0); a.hints = eff_hints();
   a.pdl = C.pdl; a.prefetch = C.prefetch;
   a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && C.nranks == 1) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
   int np = 0;

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
 #pragma unroll
       for (int c = 0; c < 12; c++) {
         if (MODE >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.p + (size_t)c * a.g.Vh + i));
-        if (DOT && a.dotw) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.dotw + (size_t)c * a.g.Vh + i));
+        if (DOT == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.dotw + (size_t)c * a.g.Vh + i));
       }
     }
     V2 r[12];
@@ -287,23 +287,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
      * (Qtm_minus_psi(l, l), invert_eo.c:270), so the compiler must not move a load across a store,
      * and interleaving them serialises 12 DRAM round trips per thread (measured: 138 us instead of
      * 80 us per launch at 24^3x48, profiles/r01_cg_launches_before_epilogue_fix.csv). */
-    /* DOT with dotw == nullptr: the squared norm of the OUTPUT (no extra operand).  The CG uses it on the second
-     * hop of Qtm_pm_psi: <p, Q+ Q- p> = |Q- p|^2 because Q+ is the adjoint of Q- (gamma5-hermiticity). */
-    const bool selfnorm = DOT && dw_ == nullptr;
+    /* DOT == 1: Re <dotw, out>.  DOT == 2: the squared norm of the OUTPUT (no operand; a compile-time choice - as a
+     * run-time branch around the operand loads it cost the whole CG 8 %).  The CG uses it on the second hop of
+     * Qtm_pm_psi: <p, Q+ Q- p> = |Q- p|^2 because Q+ is the adjoint of Q- (gamma5-hermiticity). */
     V2 pc[12], dw[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) {
       if (MODE >= 2) pc[c] = pp[(size_t)c * a.g.Vh + i];
-      if (DOT && !selfnorm) dw[c] = dw_[(size_t)c * a.g.Vh + i];
+      if (DOT == 1) dw[c] = dw_[(size_t)c * a.g.Vh + i];
     }
     V2 o[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) {
       o[c] = tmb_epilogue<MODE>(c, r[c], MODE >= 2 ? pc[c] : mk2<V2>(0, 0), cf);
-      if (DOT) {
-        const V2 wv = selfnorm ? o[c] : dw[c];
-        dsum += (double)wv.x * (double)o[c].x;
-        dsum += (double)wv.y * (double)o[c].y;
+      if (DOT == 1) {
+        dsum += (double)dw[c].x * (double)o[c].x;
+        dsum += (double)dw[c].y * (double)o[c].y;
+      } else if (DOT == 2) {
+        dsum += (double)o[c].x * (double)o[c].x;
+        dsum += (double)o[c].y * (double)o[c].y;
       }
     }
 #pragma unroll
@@ -376,6 +378,7 @@ template <int HINTS>
 static cudaError_t hop_mode_448(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
     if (a.mode != 2) return cudaErrorInvalidValue;
+    if (a.dot == 2) return hop_go<double2, 2, 0, 2, HINTS, 64, 7>(a, s);
     return hop_go<double2, 2, 0, 1, HINTS, 64, 7>(a, s);
   }
   switch (a.mode) {
@@ -390,6 +393,7 @@ template <int DIST, int HINTS>
 static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
     if (a.mode != 2) return cudaErrorInvalidValue;
+    if (a.dot == 2) return hop_go<double2, 2, DIST, 2, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
     return hop_go<double2, 2, DIST, 1, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
   }
   switch (a.mode) {
@@ -405,6 +409,7 @@ template <int DIST, int CFG>
 static cudaError_t hop_mode_f(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
     if (a.mode != 2) return cudaErrorInvalidValue;
+    if (a.dot == 2) return hop_go<float2, 2, DIST, 2, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
     return hop_go<float2, 2, DIST, 1, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
   }
   switch (a.mode) {

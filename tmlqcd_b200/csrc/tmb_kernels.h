@@ -47,7 +47,7 @@ struct tmb_hop_launch {
   int prec;                 /* 0: double, 1: float */
   int mode;                 /* epilogue 0..3, see tmb_site.cuh */
   int dist;                 /* 1: +-t of the boundary slices from halo buffers */
-  int dot;                  /* 1: accumulate Re<dotw, out> into partial[] */
+  int dot;                  /* 1: accumulate Re<dotw, out> into partial[]; 2: accumulate |out|^2 (no operand) */
   int hints;                /* 1: L1/L2 cache-policy loads */
   int variant;              /* 0: production kernel; 1..9: tuning variants of the plain kernel */
   int site0, nsites;        /* contiguous work range ... */
