@@ -213,6 +213,12 @@ void *tmb_monomial_pf(int id);     /* the pseudo-fermion field (device) */
 void *tmb_monomial_wfield(int k);  /* w_fields[k], k < 6 (device) */
 
 /* number of kernels this library launched since tmb_init (bench.py's gpu_launches) */
+/* single-precision BLAS-1 on float fields (the _32.c files of linalg/).  op: 0 R += c1 S1 (assign_add_mul_r_32), 1 R = c1 R + S1
+ * (assign_mul_add_r_32), 2 R = S1 - S2 (diff_32), 3 R = c1 S1 (mul_r_32), 4 R = c1 R + c2 S1 (assign_mul_add_mul_r_32),
+ * 5 R = gamma5 S1 (gamma5_32) */
+int tmb_blas32(int op, void *r, const void *s1, const void *s2, double c1, double c2);
+int tmb_square_norm_32(const void *field32, double *result);
+int tmb_scalar_prod_r_32(const void *a32, const void *b32, double *result);
 /* measure_plaquette (measure_gauge_action.c:46): sum over all sites of all ranks and the 6 planes of Re tr(P)/3;
  * the average plaquette is result / (6 * VOLUME * nranks) */
 int tmb_measure_plaquette(double *result);

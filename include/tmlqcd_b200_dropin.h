@@ -132,6 +132,16 @@ void Hopping_Matrix_32(const int ieo, spinor32 *const l, spinor32 *const k);
 void Qtm_pm_psi_32(spinor32 *const l, spinor32 *const k);
 int mixed_cg_her(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
                  const int rel_prec, const int N, matrix_mult f, matrix_mult32 f32);
+/* linalg/square_norm_32.c:95, scalar_prod_r_32.c:109, assign_add_mul_r_32.c:104, assign_mul_add_r_32.c:81, diff_32.c:39,
+ * mul_r_32.c:69, assign_mul_add_mul_r_32.c:37; operator/tm_operators_32.c:130 */
+float square_norm_32(const spinor32 *const P, const int N, const int parallel);
+float scalar_prod_r_32(const spinor32 *const S, const spinor32 *const R, const int N, const int parallel);
+void assign_add_mul_r_32(spinor32 *const R, spinor32 *const S, const float c, const int N);
+void assign_mul_add_r_32(spinor32 *const R, const float c, const spinor32 *const S, const int N);
+void diff_32(spinor32 *const Q, const spinor32 *const R, const spinor32 *const S, const int N);
+void mul_r_32(spinor32 *const R, const float c, spinor32 *const S, const int N);
+void assign_mul_add_mul_r_32(spinor32 *const R, spinor32 *const S, const float c1, const float c2, const int N);
+void gamma5_32(spinor32 *const l, spinor32 *const k, const int V);
 /* operator/tm_operators_nd.c:68,:130,:195,:639; solver/cg_her_nd.c:57; invert_doublet_eo.c:68 */
 void M_ee_inv_ndpsi(spinor *const l_s, spinor *const l_c, spinor *const k_s, spinor *const k_c, const double mu, const double eps);
 void Qtm_ndpsi(spinor *const l_strange, spinor *const l_charm, spinor *const k_strange, spinor *const k_charm);

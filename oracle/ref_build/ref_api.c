@@ -481,3 +481,21 @@ int ref_read_spinor(double *even, double *odd, const char *filename, int positio
  *      (wrapper/lib_wrapper.c:232-235) ---- */
 #include "measure_gauge_action.h"
 double ref_measure_plaquette(void) { return measure_plaquette((const su3 **)g_gauge_field); }
+
+/* ---- single-precision BLAS-1 of the mixed solvers: linalg/..._32.c, operator/tm_operators_32.c:130 ---- */
+#include "linalg/square_norm_32.h"
+#include "linalg/scalar_prod_r_32.h"
+#include "linalg/assign_add_mul_r_32.h"
+#include "linalg/assign_mul_add_r_32.h"
+#include "linalg/diff_32.h"
+#include "linalg/mul_r_32.h"
+#include "linalg/assign_mul_add_mul_r_32.h"
+#include "operator/tm_operators_32.h"
+float ref_square_norm_32(float *p, int n) { return square_norm_32((spinor32 *)p, n, 0); }
+float ref_scalar_prod_r_32(float *s, float *r, int n) { return scalar_prod_r_32((spinor32 *)s, (spinor32 *)r, n, 0); }
+void ref_assign_add_mul_r_32(float *r, float *s, float c, int n) { assign_add_mul_r_32((spinor32 *)r, (spinor32 *)s, c, n); }
+void ref_assign_mul_add_r_32(float *r, float c, float *s, int n) { assign_mul_add_r_32((spinor32 *)r, c, (spinor32 *)s, n); }
+void ref_diff_32(float *q, float *r, float *s, int n) { diff_32((spinor32 *)q, (spinor32 *)r, (spinor32 *)s, n); }
+void ref_mul_r_32(float *r, float c, float *s, int n) { mul_r_32((spinor32 *)r, c, (spinor32 *)s, n); }
+void ref_assign_mul_add_mul_r_32(float *r, float *s, float c1, float c2, int n) { assign_mul_add_mul_r_32((spinor32 *)r, (spinor32 *)s, c1, c2, n); }
+void ref_gamma5_32(float *l, float *k, int n) { gamma5_32((spinor32 *)l, (spinor32 *)k, n); }

@@ -221,6 +221,11 @@ void emul_deriv(int ieo, const double *l, const double *k, const double *U, doub
       else          { if (last) tmb_deriv_site<0, 1>(f, g, q, i, ka, 2. * factor); else tmb_deriv_site<0, 0>(f, g, q, i, ka, 2. * factor); }
     }
 }
+/* single-precision BLAS-1 functor of the product (tmb_kernels.cu: EwBlas32), n2 = 12 * sites complex numbers */
+void emul_blas32(int op, float *r, const float *s1, const float *s2, float c1, float c2, long n2) {
+  EwBlas32 f = {(float2 *)r, (const float2 *)s1, (const float2 *)s2, c1, c2, op, (size_t)n2 / 2};
+  for (size_t k = 0; k < (size_t)n2; k++) f(k);
+}
 /* plaquette sum by the device site function; dist: the +t links of the last slice come from `up` = [2][3][9][S]
  * (emul_pack_gauge_first_slice of the rank above; of the same field for a periodic single rank) */
 void emul_pack_gauge_first_slice(double *out, const double *U, int T, int LX, int LY, int LZ) {

@@ -35,6 +35,7 @@ def load():
         "emul_pack_deriv": [dp, dp, i, i, i, i], "emul_unpack_deriv": [dp, dp, i, i, i, i],
         "emul_pack_deriv_halo": [dp, dp, dp, i, i, i, i],
         "emul_deriv": [i, dp, dp, dp, dp, dp, i, i, i, i, dp, d, i],
+        "emul_blas32": [i, fp, fp, fp, C.c_float, C.c_float, C.c_long],
         "emul_pack_gauge_first_slice": [dp, dp, i, i, i, i], "emul_plaquette": [dp, dp, i, i, i, i, i],
         "emul_nd_mee_inv": [dp, dp, dp, dp, d, d, i], "emul_nd_moo_sub_g5": [dp, dp, dp, dp, dp, dp, d, d, i],
     }

@@ -86,6 +86,7 @@ DEVICE_API = {
     "tmb_monomial_acc": (_i, [_i, C.POINTER(_d)]),
     "tmb_monomial_info": (_i, [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tmb_monomial_pf": (_vp, [_i]), "tmb_monomial_wfield": (_vp, [_i]),
+    "tmb_blas32": (_i, [_i, _vp, _vp, _vp, _d, _d]), "tmb_square_norm_32": (_i, [_vp, C.POINTER(_d)]), "tmb_scalar_prod_r_32": (_i, [_vp, _vp, C.POINTER(_d)]),
     "tmb_measure_plaquette": (_i, [C.POINTER(_d)]), "tmb_launch_count": (C.c_longlong, []), "tmb_measure_copy_gbs": (_i, [C.c_size_t, _i, C.POINTER(_d)]),
 }
 
@@ -167,6 +168,10 @@ DROPIN_API = {
     "det_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
     "detratio_heatbath": (None, [_i, C.POINTER(HamiltonianField)]), "detratio_acc": (_d, [_i, C.POINTER(HamiltonianField)]),
     "detratio_derivative": (None, [_i, C.POINTER(HamiltonianField)]),
+    "square_norm_32": (C.c_float, [_fp, _i, _i]), "scalar_prod_r_32": (C.c_float, [_fp, _fp, _i, _i]),
+    "assign_add_mul_r_32": (None, [_fp, _fp, C.c_float, _i]), "assign_mul_add_r_32": (None, [_fp, C.c_float, _fp, _i]),
+    "diff_32": (None, [_fp, _fp, _fp, _i]), "mul_r_32": (None, [_fp, C.c_float, _fp, _i]),
+    "assign_mul_add_mul_r_32": (None, [_fp, _fp, C.c_float, C.c_float, _i]), "gamma5_32": (None, [_fp, _fp, _i]),
     "measure_plaquette": (_d, [_vp]),
     "construct_paramsXlfInfo": (_vp, [_d, _i]), "read_gauge_field": (_i, [C.c_char_p, _vp]),
     "write_gauge_field": (_i, [C.c_char_p, _i, _vp]), "read_spinor": (_i, [_sp, _sp, C.c_char_p, _i]),

@@ -346,6 +346,50 @@ void Qtm_pm_psi_32(spinor32 *const l, spinor32 *const k) {
   CHK(tmb_Qtm_pm_psi_32(dev32(1), dev32(0))); CHK(tmb_field32_download((float *)l, dev32(1)));
 }
 
+/* ---------------- single-precision BLAS-1 of the mixed solvers (the _32.c files of linalg/, operator/tm_operators_32.c:130) ----------------
+ * N is VOLUME/2 or VOLUME like the double-precision family; every call moves its operands across PCIe. */
+#define PART32(h, j) ((spinor32 *)(h) + (size_t)(j) * (VOLUME / 2))
+static void up32(int k, const spinor32 *h) { CHK(tmb_field32_upload(dev32(k), (const float *)h)); }
+static void down32(spinor32 *h, int k) { CHK(tmb_field32_download((float *)h, dev32(k))); }
+float square_norm_32(const spinor32 *const P, const int N, const int parallel) {
+  (void)parallel; sync_globals();
+  double acc = 0.;
+  for (int j = 0, n = nparts(N, __func__); j < n; j++) { double r; up32(0, PART32(P, j)); CHK(tmb_square_norm_32(dev32(0), &r)); acc += r; }
+  return (float)acc;
+}
+float scalar_prod_r_32(const spinor32 *const S, const spinor32 *const R, const int N, const int parallel) {
+  (void)parallel; sync_globals();
+  double acc = 0.;
+  for (int j = 0, n = nparts(N, __func__); j < n; j++) {
+    double r; up32(0, PART32(S, j)); up32(1, PART32(R, j)); CHK(tmb_scalar_prod_r_32(dev32(0), dev32(1), &r)); acc += r;
+  }
+  return (float)acc;
+}
+void assign_add_mul_r_32(spinor32 *const R, spinor32 *const S, const float c, const int N) {
+  sync_globals();
+  for (int j = 0, n = nparts(N, __func__); j < n; j++) { up32(0, PART32(R, j)); up32(1, PART32(S, j)); CHK(tmb_blas32(0, dev32(0), dev32(1), NULL, c, 0.)); down32(PART32(R, j), 0); }
+}
+void assign_mul_add_r_32(spinor32 *const R, const float c, const spinor32 *const S, const int N) {
+  sync_globals();
+  for (int j = 0, n = nparts(N, __func__); j < n; j++) { up32(0, PART32(R, j)); up32(1, PART32(S, j)); CHK(tmb_blas32(1, dev32(0), dev32(1), NULL, c, 0.)); down32(PART32(R, j), 0); }
+}
+void diff_32(spinor32 *const Q, const spinor32 *const R, const spinor32 *const S, const int N) {
+  sync_globals();
+  for (int j = 0, n = nparts(N, __func__); j < n; j++) { up32(0, PART32(R, j)); up32(1, PART32(S, j)); CHK(tmb_blas32(2, dev32(2), dev32(0), dev32(1), 0., 0.)); down32(PART32(Q, j), 2); }
+}
+void mul_r_32(spinor32 *const R, const float c, spinor32 *const S, const int N) {
+  sync_globals();
+  for (int j = 0, n = nparts(N, __func__); j < n; j++) { up32(0, PART32(S, j)); CHK(tmb_blas32(3, dev32(1), dev32(0), NULL, c, 0.)); down32(PART32(R, j), 1); }
+}
+void assign_mul_add_mul_r_32(spinor32 *const R, spinor32 *const S, const float c1, const float c2, const int N) {
+  sync_globals();
+  for (int j = 0, n = nparts(N, __func__); j < n; j++) { up32(0, PART32(R, j)); up32(1, PART32(S, j)); CHK(tmb_blas32(4, dev32(0), dev32(1), NULL, c1, c2)); down32(PART32(R, j), 0); }
+}
+void gamma5_32(spinor32 *const l, spinor32 *const k, const int V) {
+  sync_globals();
+  for (int j = 0, n = nparts(V, __func__); j < n; j++) { up32(0, PART32(k, j)); CHK(tmb_blas32(5, dev32(1), dev32(0), NULL, 0., 0.)); down32(PART32(l, j), 1); }
+}
+
 /* invert_eo.c:83-561: the even/odd CG branch (:152-157, :252, :268-270, :306-310) */
 int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
               const double precision, const int max_iter, const int solver_flag, const int rel_prec,

@@ -616,6 +616,23 @@ struct EwToFloat { float2 *d; const double2 *sv;
 struct EwAddFromFloat { double2 *d; const float2 *sv;
   __host__ __device__ void operator()(size_t k) const { double2 v = d[k]; const float2 w = sv[k]; v.x += (double)w.x; v.y += (double)w.y; d[k] = v; } };
 
+/* single-precision BLAS-1 of the mixed solvers (the _32.c files of linalg/): op 0 R += c1 S (assign_add_mul_r_32.c:42), 1 R = c1 R + S
+ * (assign_mul_add_r_32.c:18), 2 R = S - S2 (diff_32.c:39), 3 R = c1 S (mul_r_32.c:69), 4 R = c1 R + c2 S
+ * (assign_mul_add_mul_r_32.c:37), 5 R = gamma5 S (tm_operators_32.c:130); arithmetic in float like the reference */
+struct EwBlas32 { float2 *r; const float2 *sv, *s2; float c1, c2; int op; size_t half;
+  __host__ __device__ void operator()(size_t k) const {
+    float2 v;
+    if (op == 0) { v = r[k]; const float2 w = sv[k]; v.x += c1 * w.x; v.y += c1 * w.y; }
+    else if (op == 1) { v = r[k]; const float2 w = sv[k]; v.x = c1 * v.x + w.x; v.y = c1 * v.y + w.y; }
+    else if (op == 2) { const float2 a = sv[k], b = s2[k]; v = make_float2(a.x - b.x, a.y - b.y); }
+    else if (op == 3) { const float2 w = sv[k]; v = make_float2(c1 * w.x, c1 * w.y); }
+    else if (op == 4) { v = r[k]; const float2 w = sv[k]; v.x = c1 * v.x + c2 * w.x; v.y = c1 * v.y + c2 * w.y; }
+    else { const float2 w = sv[k]; v = (k >= half) ? make_float2(-w.x, -w.y) : w; }
+    r[k] = v;
+  } };
+cudaError_t tmb_launch_blas32(int op, float2 *r, const float2 *sv, const float2 *s2, float c1, float c2, size_t n2, size_t half, cudaStream_t s) {
+  EwBlas32 f = {r, sv, s2, c1, c2, op, half}; EW_LAUNCH(f, n2, nullptr, s);
+}
 cudaError_t tmb_launch_axpy(double2 *p, const double2 *q, double c, size_t n2, cudaStream_t s) { EwAxpy f = {p, q, c}; EW_LAUNCH(f, n2, nullptr, s); }
 cudaError_t tmb_launch_xpay(double2 *r, double c, const double2 *sv, size_t n2, cudaStream_t s) { EwXpay f = {r, sv, c}; EW_LAUNCH(f, n2, nullptr, s); }
 cudaError_t tmb_launch_lincomb(double2 *q, double a, const double2 *r, double b, const double2 *sv, size_t n2, cudaStream_t s) { EwLin f = {q, r, sv, a, b}; EW_LAUNCH(f, n2, nullptr, s); }

@@ -147,6 +147,8 @@ cudaError_t tmb_launch_pack_deriv_halo(double2 *out, const double2 *k, const dou
 cudaError_t tmb_launch_pack_deriv(double *dev, const double *lex, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_unpack_deriv(double *lex, const double *dev, tmb_geom g, int add, cudaStream_t s);
 
+/* single-precision BLAS-1 (the _32.c files of linalg/), op codes in tmb_kernels.cu */
+cudaError_t tmb_launch_blas32(int op, float2 *r, const float2 *sv, const float2 *s2, float c1, float c2, size_t n2, size_t half, cudaStream_t s);
 /* ---- plaquette (tmb_force.cu): measure_gauge_action.c:46-106; partial[] gets one sum per CTA (grid from tmb_plaq_grid) ---- */
 int tmb_plaq_grid(const tmb_geom &g);
 cudaError_t tmb_launch_plaquette(const double2 *U, const double2 *Uup, tmb_geom g, int dist, double *partial, cudaStream_t s);
