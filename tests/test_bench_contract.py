@@ -32,3 +32,25 @@ def test_b200_arm_fails_loudly_without_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--lattice", "4x4x4x4",
                         "--skip-cpu", "--skip-sections"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_strong_scaling_inputs_do_not_depend_on_the_decomposition(oracle_lib):
+    """bench.py --global-chunk-t: N = 1, 2, 4 ranks assemble the same GLOBAL gauge field and sources from per-chunk seeds,
+    and the fields are a valid input of the path (SU(3) links: unit plaquette normalisation through the oracle)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    T, LX, LY, LZ, ct = 8, 4, 4, 4, 2
+    g1, s1, how = bench.chunked_fields((T, LX, LY, LZ), 0, ct)
+    assert "chunks of 2" in how and g1.shape == (T * LX * LY * LZ, 4, 18) and s1[0].shape == (T * LX * LY * LZ // 2, 24)
+    for world in (2, 4):
+        parts = [bench.chunked_fields((T // world, LX, LY, LZ), r, ct) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), g1)
+        for k in range(3):
+            assert np.array_equal(np.concatenate([p[1][k] for p in parts]), s1[k])
+    u = g1.reshape(-1, 9, 2)
+    m = (u[..., 0] + 1j * u[..., 1]).reshape(-1, 3, 3)
+    assert np.allclose(m @ m.conj().transpose(0, 2, 1), np.eye(3), atol=1e-13) and np.allclose(np.linalg.det(m), 1., atol=1e-13)
+    o = oracle_lib.Oracle(T, LX, LY, LZ)
+    o.set_gauge(np.ascontiguousarray(g1))
+    assert abs(o.measure_plaquette()) < 6 * T * LX * LY * LZ  # finite, below the unit-gauge value
