@@ -221,6 +221,38 @@ void emul_deriv(int ieo, const double *l, const double *k, const double *U, doub
       else          { if (last) tmb_deriv_site<0, 1>(f, g, q, i, ka, 2. * factor); else tmb_deriv_site<0, 0>(f, g, q, i, ka, 2. * factor); }
     }
 }
+/* two-flavour hopping term with the epilogues of hop2_kernel (tmb_force.cu), applied site by site on the host:
+ * mode 0 plain, 1 M_ee_inv_ndpsi of the two results, 2 scale * g5( M_oo(p0, p1) - H ) */
+void emul_hop2(int par, double *out0, double *out1, const double *in0, const double *in1, const double *p0, const double *p1,
+               const double *U, int T, int LX, int LY, int LZ, const double *ka8, int mode, double mu, double eps, double scale) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  tmb_policies pol = {0, 0};
+  double2 ka[4];
+  for (int m = 0; m < 4; m++) ka[m] = make_double2(ka8[2 * m], ka8[2 * m + 1]);
+  const size_t Vh = g.Vh;
+  double2 *o0 = (double2 *)out0, *o1 = (double2 *)out1;
+  const double2 *q0 = (const double2 *)p0, *q1 = (const double2 *)p1;
+  for (int i = 0; i < g.Vh; i++) {
+    double2 r0[12], r1[12];
+    tmb_hop_site2<0>(r0, r1, (const double2 *)in0, (const double2 *)in1, (const double2 *)U, g, par, i, ka, pol);
+    for (int c = 0; c < 12; c++) {
+      if (mode == 1) {
+        double2 ls, lc;
+        tmb_nd_mee_inv_regs(ls, lc, r0[c], r1[c], c, mu, eps, 1. / (1. + mu * mu - eps * eps));
+        r0[c] = ls; r1[c] = lc;
+      } else if (mode == 2) { /* the arithmetic of hop2_kernel<2> */
+        const bool up = c < 6;
+        const double2 zs = make_double2(1., up ? -mu : mu), zc = c_conj(zs);
+        const double2 a = q0[c * Vh + i], b = q1[c * Vh + i];
+        double2 x = c_mul(zs, a); x.x += eps * b.x; x.y += eps * b.y;
+        double2 y = c_mul(zc, b); y.x += eps * a.x; y.y += eps * a.y;
+        const double2 d0 = up ? c_sub(x, r0[c]) : c_sub(r0[c], x), d1 = up ? c_sub(y, r1[c]) : c_sub(r1[c], y);
+        r0[c] = make_double2(scale * d0.x, scale * d0.y); r1[c] = make_double2(scale * d1.x, scale * d1.y);
+      }
+      o0[c * Vh + i] = r0[c]; o1[c * Vh + i] = r1[c];
+    }
+  }
+}
 /* single-precision BLAS-1 functor of the product (tmb_kernels.cu: EwBlas32), n2 = 12 * sites complex numbers */
 void emul_blas32(int op, float *r, const float *s1, const float *s2, float c1, float c2, long n2) {
   EwBlas32 f = {(float2 *)r, (const float2 *)s1, (const float2 *)s2, c1, c2, op, (size_t)n2 / 2};

@@ -36,6 +36,7 @@ def load():
         "emul_pack_deriv_halo": [dp, dp, dp, i, i, i, i],
         "emul_deriv": [i, dp, dp, dp, dp, dp, i, i, i, i, dp, d, i],
         "emul_blas32": [i, fp, fp, fp, C.c_float, C.c_float, C.c_long],
+        "emul_hop2": [i, dp, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, i, d, d, d],
         "emul_pack_gauge_first_slice": [dp, dp, i, i, i, i], "emul_plaquette": [dp, dp, i, i, i, i, i],
         "emul_nd_mee_inv": [dp, dp, dp, dp, d, d, i], "emul_nd_moo_sub_g5": [dp, dp, dp, dp, dp, dp, d, d, i],
     }
@@ -79,6 +80,14 @@ class Emul:
                           0 if halo is None else 1)
         out = np.zeros(32 * self.V); self.E.emul_unpack_deriv(out, dev, *self.dims)
         return out.reshape(self.V, 4, 8)
+
+    def hop2(self, par, in0, in1, U, ka, mode=0, p0=None, p1=None, mu=0., eps=0., scale=1.):
+        """two-flavour hop with the epilogues of hop2_kernel; fields in device layout"""
+        o0, o1 = np.zeros(24 * self.Vh), np.zeros(24 * self.Vh)
+        z = np.zeros(2)
+        self.E.emul_hop2(par, o0, o1, in0, in1, p0 if p0 is not None else z, p1 if p1 is not None else z, U, *self.dims,
+                         np.asarray(ka, dtype=np.float64), mode, mu, eps, scale)
+        return o0, o1
 
     def plaquette(self, U, up=None):
         """measure_plaquette on the device-layout gauge field; up = first-slice spatial links of the rank above"""

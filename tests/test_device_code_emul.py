@@ -172,3 +172,37 @@ def test_golden_fermion_force_through_device_code():
     for ieo in (0, 1):
         got = e.deriv(ieo, sl, sk, U, ka, np.zeros((e.V, 4, 8)), 0.7)
         assert rel_l2(got, gold[f"deriv_Sb{ieo}"]) < 1e-14
+
+
+@pytest.mark.parametrize("dims,theta", [((4, 4, 4, 4), (0., 0., 0., 0.)), ((4, 6, 2, 8), (1., 0.3, 0., 0.7))])
+def test_two_flavour_hop_and_fused_flavour_mixing(oracle_lib, dims, theta):
+    """tmb_hop_site2 + the epilogues of hop2_kernel (host emulation), composed exactly as qtm_pm_nd() in tmb_capi.cu
+    composes its four launches, against the oracle's Qtm_pm_ndpsi (tm_operators_nd.c:195-239) and its pieces"""
+    rng = np.random.default_rng(9)
+    e, o = Emul(*dims), oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    mubar, epsbar, invmaxev = 0.139, 0.15, 0.9
+    o.set_gauge(g); o.set_params(KAPPA, GMU, theta); o.set_nd_params(mubar, epsbar, invmaxev)
+    ka = ka_of(KAPPA, theta, dims)
+    U = e.pack_gauge(g)
+    ks, kc = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+    sks, skc = e.pack(ks), e.pack(kc)
+    # mode 0: two plain hops with one gauge stream
+    h0, h1 = e.hop2(1, sks, skc, U, ka)
+    exp = o.spinor()
+    o.Hopping_Matrix(1, exp, ks); assert rel_l2(e.unpack(h0), exp) < 1e-14
+    o.Hopping_Matrix(1, exp, kc); assert rel_l2(e.unpack(h1), exp) < 1e-14
+    # mode 1 against H_eo + M_ee_inv_ndpsi
+    a0, a1 = e.hop2(0, skc, sks, U, ka, mode=1, mu=mubar, eps=epsbar)
+    hc, hs = o.spinor(), o.spinor()
+    o.Hopping_Matrix(0, hc, kc); o.Hopping_Matrix(0, hs, ks)
+    m0, m1 = o.spinor(), o.spinor()
+    o.M_ee_inv_ndpsi(m0, m1, hc, hs, mubar, epsbar)
+    assert rel_l2(e.unpack(a0), m0) < 1e-14 and rel_l2(e.unpack(a1), m1) < 1e-14
+    # the four-launch composition of Qtm_pm_ndpsi
+    b0, b1 = e.hop2(1, a0, a1, U, ka, mode=2, p0=skc, p1=sks, mu=-mubar, eps=-epsbar, scale=1.)
+    a0, a1 = e.hop2(0, b0, b1, U, ka, mode=1, mu=-mubar, eps=epsbar)
+    ls, lc = e.hop2(1, a1, a0, U, ka, mode=2, p0=b1, p1=b0, mu=-mubar, eps=-epsbar, scale=invmaxev * invmaxev)
+    es, ec = o.spinor(), o.spinor()
+    o.Qtm_pm_ndpsi(es, ec, ks, kc)
+    assert rel_l2(e.unpack(ls), es) < 1e-13 and rel_l2(e.unpack(lc), ec) < 1e-13
