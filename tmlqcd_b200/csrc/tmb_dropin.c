@@ -461,7 +461,11 @@ int invert_doublet_eo(spinor *const Even_new_s, spinor *const Odd_new_s, spinor 
                       const double precision, const int max_iter, const int solver_flag, const int rel_prec,
                       solver_params_t solver_params, const ExternalInverter external_inverter,
                       const SloppyPrecision sloppy, const CompressionType compression) {
-  (void)solver_flag; (void)solver_params; (void)external_inverter; (void)sloppy; (void)compression;
+  (void)solver_params; (void)external_inverter; (void)sloppy; (void)compression;
+  /* invert_doublet_eo.c:143-156 knows CG and RGMIXEDCG; both are served by the double-precision CG on the two-flavour
+   * kernels here (same solution to the requested precision; the count returned is the CG's) */
+  if (solver_flag != TMB_SOLVER_CG && g_proc_id == 0 && g_debug_level > 0)
+    printf("# invert_doublet_eo (B200): solver_flag %d is served by the double-precision CG\n", solver_flag);
   sync_globals();
   up(4, Even_s); up(5, Odd_s); up(6, Even_c); up(7, Odd_c);
   up(1, Odd_new_s); up(3, Odd_new_c); /* initial guess of cg_her_nd */
