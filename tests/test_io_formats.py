@@ -171,3 +171,56 @@ print("OK")
 """
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("dims", [(4, 2, 6, 4), (2, 4, 4, 8)])
+def test_non_cubic_round_trips_and_appended_propagators(dims, tmp_path):
+    """lattices with LX != LY != LZ (the reference sizes its records with L^3, gauge_write.c:31, so only this library is
+    on both sides here): gauge round trip at both precisions, three propagators appended to one file and read back by
+    position (spinor_read.c:60-78), a position past the end refused"""
+    import tmlqcd_b200 as tm
+    lib = tm.load()
+    T, LX, LY, LZ = dims
+    V = T * LX * LY * LZ
+    for n, v in (("T", T), ("L", LX), ("LX", LX), ("LY", LY), ("LZ", LZ), ("VOLUME", V), ("VOLUMEPLUSRAND", V), ("RAND", 0),
+                 ("g_debug_level", 0), ("g_disable_IO_checks", 0)):
+        C.c_int.in_dll(lib, n).value = v
+    rng = np.random.default_rng(4)
+    gauge = rng.normal(size=(V, 4, 18))
+    keep = gauge.copy()
+    rows = (C.c_void_p * V)(*[gauge.ctypes.data + ix * 4 * 144 for ix in range(V)])
+    old = C.c_void_p.in_dll(lib, "g_gauge_field").value
+    C.c_void_p.in_dll(lib, "g_gauge_field").value = C.addressof(rows)
+    try:
+        lib.construct_paramsXlfInfo.restype = C.c_void_p
+        xlf = C.c_void_p(lib.construct_paramsXlfInfo(C.c_double(0.6), 1))
+        for prec in (64, 32):
+            fn = str(tmp_path / f"conf.{prec}").encode()
+            gauge[:] = keep
+            assert lib.write_gauge_field(fn, prec, xlf) == 0
+            gauge[:] = 0
+            C.c_int.in_dll(lib, "gauge_precision_read_flag").value = prec
+            assert lib.read_gauge_field(fn, rows) == 0
+            assert np.array_equal(gauge, keep if prec == 64 else keep.astype(np.float32).astype(np.float64))
+        C.c_int.in_dll(lib, "gauge_precision_read_flag").value = 64
+        # a file of another lattice with the SAME volume is refused by the ildg-format record (the reference only prints the
+        # mismatch, gauge_read.c:172-180; this reader is stricter) ...
+        C.c_int.in_dll(lib, "LX").value = LZ; C.c_int.in_dll(lib, "LZ").value = LX  # LX != LZ in both cases
+        assert lib.read_gauge_field(str(tmp_path / "conf.64").encode(), rows) != 0
+        C.c_int.in_dll(lib, "LX").value = LX; C.c_int.in_dll(lib, "LZ").value = LZ
+        # ... and inconsistent globals (VOLUME != T LX LY LZ) before anything is written into the field
+        C.c_int.in_dll(lib, "LY").value = LY + 2
+        gauge[:] = 7.
+        assert lib.read_gauge_field(str(tmp_path / "conf.64").encode(), rows) != 0 and np.all(gauge == 7.)
+        C.c_int.in_dll(lib, "LY").value = LY
+        props = [(rng.normal(size=(V // 2, 24)), rng.normal(size=(V // 2, 24))) for _ in range(3)]
+        fn = str(tmp_path / "props").encode()
+        for k, (e, o) in enumerate(props):
+            assert lib.tmb_write_propagator(fn, e, o, 64, 1e-12, 10 + k, b"CG", 1 if k else 0) == 0
+        a, b = np.zeros((V // 2, 24)), np.zeros((V // 2, 24))
+        for k in (2, 0, 1):
+            assert lib.read_spinor(a, b, fn, k) == 0
+            assert np.array_equal(a, props[k][0]) and np.array_equal(b, props[k][1])
+        assert lib.read_spinor(a, b, fn, 3) == -5
+    finally:
+        C.c_void_p.in_dll(lib, "g_gauge_field").value = old

@@ -163,6 +163,7 @@ paramsXlfInfo *construct_paramsXlfInfo(double const plaq, int const counter) {
 int write_gauge_field(char *filename, int prec, paramsXlfInfo const *xlf) {
   if (prec != 64 && prec != 32) { fprintf(stderr, "write_gauge_field: precision must be 64 or 32\n"); return -1; }
   if (!g_gauge_field) { fprintf(stderr, "write_gauge_field: no gauge field (tmb_dropin_init first)\n"); return -1; }
+  if (VOLUME != T * LX * LY * LZ) { fprintf(stderr, "%s: inconsistent lattice globals (VOLUME = %d, T LX LY LZ = %d %d %d %d).\n", __func__, VOLUME, T, LX, LY, LZ); return -1; }
   FILE *fp = fopen(filename, "w");
   if (!fp) { fprintf(stderr, "Failed to create writer. Aborting...\n"); return -1; }
   crc_init();
@@ -219,6 +220,10 @@ int read_gauge_field(char *filename, su3 **const gf) {
     return -1;
   }
   crc_init();
+  if (VOLUME != T * LX * LY * LZ) { /* the site loop below indexes gf with T, LX, LY, LZ and sizes the record with VOLUME */
+    fprintf(stderr, "read_gauge_field: inconsistent lattice globals (VOLUME = %d, T LX LY LZ = %d %d %d %d).\n", VOLUME, T, LX, LY, LZ);
+    fclose(fp); return -1;
+  }
   lime_rec r, prev;
   int have_prev = 0, status, gauge_read = 0, dml_read = 0, fmt_read = 0;
   DML_Checksum calc = {0, 0}, stored = {0, 0};
@@ -313,6 +318,19 @@ int read_gauge_field(char *filename, su3 **const gf) {
       fprintf(stderr, "For gauge file %s, calculated and stored values for SciDAC checksum B do not match.\n", filename);
       return -1;
     }
+    if (g_proc_id == 0 && g_debug_level > 0) { /* gauge_read.c:172-180 */
+      printf("# Reading ildg-format record:\n#   Precision = %d bits (%s).\n", fmt.prec, fmt.prec == 64 ? "double" : "single");
+      printf("#   Lattice size: LX = %d, LY = %d, LZ = %d, LT = %d.\n", fmt.lx, fmt.ly, fmt.lz, fmt.lt);
+      printf("# Input parameters:\n#   Precision = %d bits (%s).\n", want_prec, want_prec == 64 ? "double" : "single");
+      printf("#   Lattice size: LX = %d, LY = %d, LZ = %d, LT = %d.\n", LX, LY, LZ, T * g_nproc_t);
+    }
+    /* stricter than the reference, which only prints the two (gauge_read.c:172-180): a file whose extents are a
+     * permutation of the requested ones has the right size and the right checksum, and every link in the wrong place */
+    if (fmt.lx != LX || fmt.ly != LY || fmt.lz != LZ || fmt.lt != T * g_nproc_t) {
+      fprintf(stderr, "For gauge file %s, the ildg-format record (LX = %d, LY = %d, LZ = %d, LT = %d) does not match the input "
+                      "parameters (LX = %d, LY = %d, LZ = %d, LT = %d).\n", filename, fmt.lx, fmt.ly, fmt.lz, fmt.lt, LX, LY, LZ, T * g_nproc_t);
+      return -1;
+    }
   } else if (!gauge_read) return -1;
   g_update_gauge_copy = 1; /* io/gauge_read.c:186: the device copy is stale */
   return 0;
@@ -326,6 +344,7 @@ int read_gauge_field(char *filename, su3 **const gf) {
 int tmb_write_propagator(const char *filename, spinor *const s, spinor *const r, int prec, double epssq, int iter,
                          const char *solver_name, int append) {
   if (prec != 64 && prec != 32) { fprintf(stderr, "tmb_write_propagator: precision must be 64 or 32\n"); return -1; }
+  if (VOLUME != T * LX * LY * LZ) { fprintf(stderr, "%s: inconsistent lattice globals (VOLUME = %d, T LX LY LZ = %d %d %d %d).\n", __func__, VOLUME, T, LX, LY, LZ); return -1; }
   FILE *fp = fopen(filename, append ? "a" : "w");
   if (!fp) { fprintf(stderr, "Failed to create writer. Aborting...\n"); return -1; }
   crc_init();
@@ -377,6 +396,7 @@ int tmb_write_propagator(const char *filename, spinor *const s, spinor *const r,
 
 /* io/spinor_read.c:27-150 (r != NULL: even/odd pair), position-th scidac-binary-data record */
 int read_spinor(spinor *const s, spinor *const r, char *filename, const int position_) {
+  if (VOLUME != T * LX * LY * LZ) { fprintf(stderr, "%s: inconsistent lattice globals (VOLUME = %d, T LX LY LZ = %d %d %d %d).\n", __func__, VOLUME, T, LX, LY, LZ); return -1; }
   FILE *fp = fopen(filename, "r");
   if (!fp) {
     fprintf(stderr, "\nUnable to open file for reading.\nPlease verify file existence and access rights.\nUnable to continue.\n");
