@@ -224,3 +224,22 @@ def test_non_cubic_round_trips_and_appended_propagators(dims, tmp_path):
         assert lib.read_spinor(a, b, fn, 3) == -5
     finally:
         C.c_void_p.in_dll(lib, "g_gauge_field").value = old
+
+
+def test_damaged_files_under_address_and_ub_sanitizers(tmp_path):
+    """tests/io_sanitize/io_fuzz.c: tmb_io.c compiled with -fsanitize=address,undefined, 400 truncated / bit-flipped /
+    garbage-overwritten configuration and propagator files; every read must come back without a memory error"""
+    exe = tmp_path / "io_fuzz"
+    cmd = ["gcc", "-std=gnu99", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "io_sanitize", "io_fuzz.c"), os.path.join(ROOT, "tmlqcd_b200", "csrc", "tmb_io.c"), "-o", str(exe), "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("no sanitizer runtime with this gcc")
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    env.pop("LD_PRELOAD", None)
+    r = subprocess.run([str(exe), "400"], capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=600)
+    assert r.returncode == 0 and "IOFUZZ accepted" in r.stderr, r.stderr[-3000:]
+    assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr
+    refused = int(r.stderr.split("refused")[-1].split()[0])
+    assert refused > 100  # most damage is detected (flips in free-text records are legitimately accepted)

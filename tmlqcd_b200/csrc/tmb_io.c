@@ -104,6 +104,11 @@ static int lime_next(FILE *fp, lime_rec *r, const lime_rec *prev) {
   r->bytes = get_be(b + 8, 8);
   memcpy(r->type, b + 16, 128); r->type[128] = 0;
   r->data_pos = ftell(fp);
+  /* a length field that points past the end of the file is a damaged header: refuse it here, before anybody
+   * allocates or seeks by it */
+  if (r->data_pos < 0 || fseek(fp, 0, SEEK_END) != 0) return -1;
+  const long size = ftell(fp);
+  if (fseek(fp, r->data_pos, SEEK_SET) != 0 || size < r->data_pos || r->bytes > (uint64_t)(size - r->data_pos)) return -1;
   return 0;
 }
 static char *lime_read_message(FILE *fp, const lime_rec *r) {
