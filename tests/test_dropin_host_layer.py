@@ -1,0 +1,155 @@
+"""The product's HOST layer on the CPU: tmlqcd_b200/csrc/tmb_dropin.c (the reference-named symbols: argument order,
+scratch use, VOLUME/2 | VOLUME splitting, the globals it pushes down, the tmLQCD.h facade with its lexicographic
+conversion and 2 kappa normalisation, error returns) linked against a host stand-in for the device-level C ABI
+(tests/stubdev/tmb_stub.c, which hands every operator to the CPU oracle).  The test bodies are the GPU tests'
+own - run here on the stand-in, on a B200 on the CUDA library - and the expected values are those of the unmodified
+reference (tests/golden) or of the oracle.  TEST INFRASTRUCTURE: the stand-in is never loaded by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+
+STUB = os.path.join(ROOT, "tests", "stubdev", "libtmb_dropin_stub.so")
+
+
+@pytest.fixture(scope="module")
+def stub_lib():
+    import tmlqcd_b200.capi as capi
+    r = subprocess.run(["bash", os.path.join(ROOT, "tests", "stubdev", "build.sh")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lib = C.CDLL(STUB)
+    for name, (res, args) in capi.DROPIN_API.items():
+        f = getattr(lib, name)  # every reference-named symbol of the product's host layer is in the test library
+        f.restype = res; f.argtypes = args
+    for name in ("tmb_last_error",):
+        getattr(lib, name).restype = C.c_char_p
+    return lib
+
+
+@pytest.fixture()
+def on_stub(stub_lib, monkeypatch):
+    """tm.DropIn / tm.load bound to the stand-in library for the duration of one test"""
+    import tmlqcd_b200 as tm
+    import tmlqcd_b200.capi as capi
+
+    class StubDropIn(capi.DropIn):
+        def __init__(self, T, LX, LY, LZ, device=0):
+            self.lib = stub_lib
+            self.dims = (T, LX, LY, LZ); self.V = T * LX * LY * LZ; self.Vh = self.V // 2
+            assert stub_lib.tmb_dropin_init(T, LX, LY, LZ, device) == 0, stub_lib.tmb_last_error()
+
+    monkeypatch.setattr(tm, "DropIn", StubDropIn)
+    monkeypatch.setattr(tm, "load", lambda: stub_lib)
+    return StubDropIn
+
+
+def _gold(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name))
+
+
+@pytest.fixture()
+def dropin(on_stub):
+    base = _gold("ref_4x4x4x4.npz")
+    D = on_stub(*[int(x) for x in base["dims"]])
+    D.set_params(float(base["kappa"]), float(base["gmu"]), base["theta"])
+    D.set_nd_params(*base["nd"])
+    D.set_gauge(base["gauge"])
+    yield D, base
+    D.close()
+
+
+def test_operator_family_members_vs_reference(dropin):
+    import test_gpu_dropin_ops as g
+    g.test_operator_family_members_vs_reference(dropin)
+
+
+def test_host_memory_helpers_and_precision_conversion(dropin):
+    import test_gpu_dropin_ops as g
+    g.test_host_memory_helpers_and_precision_conversion(dropin)
+
+
+def test_solvers_with_reference_signatures(dropin):
+    import test_gpu_dropin_ops as g
+    g.test_solvers_with_reference_signatures(dropin)
+
+
+def test_reference_symbols_globals_and_dirty_flag(on_stub, oracle_lib):
+    import test_gpu_parity as g
+    g.test_dropin_reference_symbols(oracle_lib)
+
+
+def test_tmLQCD_facade(on_stub, oracle_lib, tmp_path, monkeypatch):
+    import test_gpu_parity as g
+    monkeypatch.chdir(tmp_path)  # tmLQCD_read_gauge(0) looks for ./conf.0000
+    g.test_tmLQCD_facade(oracle_lib)
+
+
+def test_fermion_force_accumulates_into_the_callers_array(on_stub):
+    gold = _gold("ref_hmc_4x4x4x4.npz")
+    D = on_stub(*[int(x) for x in gold["dims"]])
+    try:
+        D.set_params(float(gold["kappa"]), float(gold["gmu"]), gold["theta"])
+        D.set_gauge(gold["gauge"])
+        l, k = np.array(gold["l"]), np.array(gold["k"])
+        for ieo in (0, 1):
+            df = np.zeros((D.V, 4, 8))
+            hf = D.hamiltonian_field(df)
+            D.deriv_Sb(ieo, l, k, C.byref(hf), 0.7)
+            assert rel_l2(df, gold[f"deriv_Sb{ieo}"]) <= 1e-13
+            D.deriv_Sb(ieo, l, k, C.byref(hf), -0.7)
+            assert np.abs(df).max() <= 1e-12
+    finally:
+        D.close()
+
+
+def test_blas32_and_plaquette_symbols(on_stub):
+    g32 = _gold("ref_blas32_4x4x4x4.npz")
+    io = _gold("ref_io_4x4x4x4.npz")
+    import json
+    plaq = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_plaquette_4x4x4x4.json")))["ref_io_4x4x4x4.npz"]
+    D = on_stub(4, 4, 4, 4)
+    try:
+        D.set_params(0.16, 0.0032)
+        D.set_gauge(np.ascontiguousarray(io["gauge"]))
+        val = D.lib.measure_plaquette(C.c_void_p.in_dll(D.lib, "g_gauge_field"))
+        assert val == float.fromhex(plaq["hex"])
+        for nparts in (1, 2):  # VOLUME/2 and VOLUME sites
+            n = 128 * nparts
+            rep = lambda a: np.ascontiguousarray(np.concatenate([a] * nparts))
+            r, s, s2 = rep(g32["r"]), rep(g32["s"]), rep(g32["s2"])
+            c1, c2 = float(g32["c1"]), float(g32["c2"])
+            x = r.copy(); D.assign_add_mul_r_32(x, s, c1, n); assert np.array_equal(x, rep(g32["assign_add_mul_r_32"]))
+            x = r.copy(); D.assign_mul_add_r_32(x, c1, s, n); assert np.array_equal(x, rep(g32["assign_mul_add_r_32"]))
+            x = np.zeros_like(r); D.diff_32(x, s, s2, n); assert np.array_equal(x, rep(g32["diff_32"]))
+            x = np.zeros_like(r); D.mul_r_32(x, c1, s, n); assert np.array_equal(x, rep(g32["mul_r_32"]))
+            x = r.copy(); D.assign_mul_add_mul_r_32(x, s, c1, c2, n); assert np.array_equal(x, rep(g32["assign_mul_add_mul_r_32"]))
+            x = np.zeros_like(r); D.gamma5_32(x, s, n); assert np.array_equal(x, rep(g32["gamma5_32"]))
+            assert abs(D.square_norm_32(r, n, 0) - nparts * float(g32["square_norm_32"])) <= 1e-6 * nparts * float(g32["square_norm_32"])
+    finally:
+        D.close()
+
+
+def test_fatal_conditions_terminate_like_the_reference(stub_lib, tmp_path):
+    """operators are void and exit(1) with a message (D_psi_body.c:267-272 style); checked in a child process"""
+    code = f"""
+import ctypes as C, numpy as np
+lib = C.CDLL({STUB!r})
+a = np.zeros((128, 24))
+lib.Hopping_Matrix(0, a.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p))
+"""
+    r = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert r.returncode == 1 and "tmb_dropin_init has not been called" in r.stderr
+    code = f"""
+import ctypes as C, numpy as np
+lib = C.CDLL({STUB!r})
+assert lib.tmb_dropin_init(4, 4, 4, 4, 0) == 0
+a = np.zeros((128, 24))
+lib.square_norm.restype = C.c_double
+lib.square_norm(a.ctypes.data_as(C.c_void_p), 100, 0)
+"""
+    r = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert r.returncode == 1 and "neither VOLUME/2 nor VOLUME" in r.stderr

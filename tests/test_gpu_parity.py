@@ -428,7 +428,7 @@ def test_tmLQCD_facade(oracle_lib):
         o.convert_eo_to_lexic(exp, En * (2 * KAPPA), On * (2 * KAPPA))
         assert abs(it.value - itr) <= 1 and rel_l2(prop, exp) <= 1e-10
         assert rp.value <= 1e-18 * np.linalg.norm(src) ** 2
-        assert lib.tmLQCD_read_gauge(0) == -1  # LIME I/O is out of scope and says so
+        assert lib.tmLQCD_read_gauge(0) == -1  # no ./conf.0000 here: refused with a message (lib_wrapper.c:218-221)
     finally:
         assert lib.tmLQCD_finalise() == 0
 
