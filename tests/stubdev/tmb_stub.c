@@ -90,6 +90,10 @@ int tmb_host_free(void *p) { free(p); return 0; }
 int tmb_host_register(void *p, size_t b) { (void)p; (void)b; return 0; }
 int tmb_host_unregister(void *p) { (void)p; return 0; }
 int tmb_sync(void) { return 0; }
+#include <time.h>
+static struct timespec t_start;
+int tmb_timer_start(void) { clock_gettime(CLOCK_MONOTONIC, &t_start); return 0; }
+int tmb_timer_stop(float *ms) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); *ms = (float)(1e3 * (t.tv_sec - t_start.tv_sec) + 1e-6 * (t.tv_nsec - t_start.tv_nsec)); return 0; }
 int tmb_field_upload(void *f, const double *h) { NEED(); memcpy(f, h, NF * sizeof(double)); return 0; }
 int tmb_field_download(double *h, const void *f) { NEED(); memcpy(h, f, NF * sizeof(double)); return 0; }
 int tmb_field32_upload(void *f, const float *h) { NEED(); memcpy(f, h, NF * sizeof(float)); return 0; }
