@@ -9,7 +9,7 @@
  * tests/stubdev/libtmb_dropin_stub.so; nothing under tmlqcd_b200/ references it, it is never a fallback of the
  * product (whose tmb_init refuses to run without a CUDA device).
  *
- * Entry points that have no oracle counterpart (chronological guess, monomials) return -99.
+ * Entry points that have no oracle counterpart at this level (the host-pointer chronological guess) return -99.
  */
 #include <complex.h>
 #include <math.h>
@@ -79,7 +79,8 @@ int tmb_set_nd(double a, double b, double c) { NEED(); orc_set_nd_params(a, b, c
 int tmb_set_compression(int n) { NEED(); return (n == 18 || n == 12) ? 0 : -21; }
 int tmb_set_mixcg(double e, int n) { (void)e; (void)n; NEED(); return 0; }
 int tmb_set_mcg_delta(double d) { (void)d; NEED(); return 0; }
-int tmb_set_relative_precision_flag(int f) { (void)f; NEED(); return 0; }
+void orc_set_relative_precision_flag(int);
+int tmb_set_relative_precision_flag(int f) { NEED(); orc_set_relative_precision_flag(f); return 0; }
 
 void *tmb_field_alloc(void) { return S.up ? calloc(NF, sizeof(double)) : NULL; }
 void *tmb_field32_alloc(void) { return S.up ? calloc(NF, sizeof(float)) : NULL; }
@@ -233,9 +234,33 @@ int tmb_measure_plaquette(double *r) { NEEDG(); *r = orc_measure_plaquette(); re
 static int refuse(const char *who) { snprintf(S.err, sizeof(S.err), "%s is not part of the host stand-in", who); return -99; }
 int tmb_chrono_add_solution(const void *t, void *const *v, int *ia, int N, int *n) { (void)t; (void)v; (void)ia; (void)N; (void)n; return refuse(__func__); }
 int tmb_chrono_guess(void *t, const void *p, void *const *v, const int *ia, int N, int n, int op) { (void)t; (void)p; (void)v; (void)ia; (void)N; (void)n; (void)op; return refuse(__func__); }
-int tmb_monomial_add(int a, double b, double c, double d, double e, int f, int g, double h, double i, int j) { (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; (void)g; (void)h; (void)i; (void)j; return refuse(__func__); }
-int tmb_monomial_clear(void) { return 0; }
-int tmb_monomial_heatbath(int id, const void *g, double *e) { (void)id; (void)g; (void)e; return refuse(__func__); }
-int tmb_monomial_derivative(int id) { (void)id; return refuse(__func__); }
-int tmb_monomial_acc(int id, double *dH) { (void)id; (void)dH; return refuse(__func__); }
-int tmb_monomial_info(int id, double *a, double *b, int *c, int *d, int *e) { (void)id; (void)a; (void)b; (void)c; (void)d; (void)e; return refuse(__func__); }
+/* DET / DETRATIO monomials: the oracle's restatement of det_monomial.c / detratio_monomial.c; the oracle sets kappa, mu and
+ * the hopping phases per monomial from its own state (periodic or the theta given to orc_set_params), so the stand-in
+ * re-installs the caller's phases after every call like mnl_backup_restore_globals does */
+int orc_mnl_add(int, double, double, double, double, int, int, double, double, int);
+void orc_mnl_clear(void);
+double orc_mnl_heatbath(int, const double *);
+void orc_mnl_derivative(int, double *);
+double orc_mnl_acc(int);
+void orc_mnl_info(int, double *, double *, int *, int *, int *);
+void orc_set_relative_precision_flag(int);
+void orc_set_theta(double, double, double, double);
+extern double X0, X1, X2, X3; /* tmb_dropin.c: the reference's boundary angles */
+int tmb_monomial_add(int type, double kappa, double mu, double kappa2, double mu2, int solver, int maxiter, double fp, double ap, int csg) {
+  NEED(); return orc_mnl_add(type, kappa, mu, kappa2, mu2, solver, maxiter, fp, ap, csg);
+}
+int tmb_monomial_clear(void) { orc_mnl_clear(); return 0; }
+int tmb_monomial_heatbath(int id, const void *g, double *e) {
+  NEEDG(); orc_set_theta(X0, X1, X2, X3); const double v = orc_mnl_heatbath(id, g); if (e) *e = v; orc_set_hopping_phases(S.ka, S.mu); return 0;
+}
+int tmb_monomial_derivative(int id) {
+  NEEDG(); if (need_df()) return -100; orc_set_theta(X0, X1, X2, X3); orc_mnl_derivative(id, S.df); orc_set_hopping_phases(S.ka, S.mu); return 0;
+}
+int tmb_monomial_acc(int id, double *dH) {
+  NEEDG(); orc_set_theta(X0, X1, X2, X3); const double v = orc_mnl_acc(id); if (dH) *dH = v; orc_set_hopping_phases(S.ka, S.mu); return 0;
+}
+int tmb_monomial_info(int id, double *a, double *b, int *c, int *d, int *e) {
+  NEED(); double e0, e1; int i0, i1, n; orc_mnl_info(id, &e0, &e1, &i0, &i1, &n);
+  if (a) *a = e0; if (b) *b = e1; if (c) *c = i0; if (d) *d = i1; if (e) *e = n;
+  return 0;
+}

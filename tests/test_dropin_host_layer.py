@@ -106,6 +106,11 @@ def test_fermion_force_accumulates_into_the_callers_array(on_stub):
         D.close()
 
 
+def test_monomials_with_reference_signatures(on_stub):
+    import test_gpu_dropin_ops as g
+    g.test_hmc_monomials_with_reference_signatures()
+
+
 def test_blas32_and_plaquette_symbols(on_stub):
     g32 = _gold("ref_blas32_4x4x4x4.npz")
     io = _gold("ref_io_4x4x4x4.npz")

@@ -91,14 +91,19 @@ def test_solvers_with_reference_signatures(dropin):
     assert it > 0 and rel_l2(x, xr) <= 1e-8
 
 
-def test_hmc_symbols_with_reference_signatures():
-    """deriv_Sb / chrono_* / det_* / detratio_* with the reference's own signatures and host buffers"""
+def _hmc_dropin():
     import tmlqcd_b200 as tm
     gold = _gold("ref_hmc_4x4x4x4.npz")
     D = tm.DropIn(*[int(x) for x in gold["dims"]])
+    D.set_params(float(gold["kappa"]), float(gold["gmu"]), gold["theta"])
+    D.set_gauge(gold["gauge"])
+    return D, gold
+
+
+def test_hmc_deriv_Sb_with_reference_signature():
+    """deriv_Sb(ieo, l, k, hf, factor) with host buffers accumulates into the caller's derivative array"""
+    D, gold = _hmc_dropin()
     try:
-        D.set_params(float(gold["kappa"]), float(gold["gmu"]), gold["theta"])
-        D.set_gauge(gold["gauge"])
         l, k = np.array(gold["l"]), np.array(gold["k"])
         for ieo in (0, 1):
             df = np.zeros((D.V, 4, 8))
@@ -107,7 +112,16 @@ def test_hmc_symbols_with_reference_signatures():
             assert rel_l2(df, gold[f"deriv_Sb{ieo}"]) <= TOL
             D.deriv_Sb(ieo, l, k, C.byref(hf), -0.7)  # accumulates into the caller's array
             assert np.abs(df).max() <= 1e-12
-        # chronological guess on host fields: the exact solution in the history reproduces itself
+    finally:
+        D.close()
+
+
+def test_hmc_chrono_guess_with_reference_signatures():
+    """chronological guess on host fields: the exact solution in the history reproduces itself"""
+    import tmlqcd_b200 as tm
+    D, gold = _hmc_dropin()
+    try:
+        k = np.array(gold["k"])
         N = 2
         hist = [D.spinor() for _ in range(N)]
         v = (C.c_void_p * N)(*[h.ctypes.data for h in hist])
@@ -120,7 +134,15 @@ def test_hmc_symbols_with_reference_signatures():
         trial = D.spinor()
         assert D.chrono_guess(trial, k, v, idx, N, n.value, D.Vh, D.fptr("Qtm_pm_psi")) == 0
         assert rel_l2(trial, x) <= 1e-9
-        # monomials through the hbfunction / derivativefunction / accfunction signatures
+    finally:
+        D.close()
+
+
+def test_hmc_monomials_with_reference_signatures():
+    """det_* / detratio_* through the hbfunction / derivativefunction / accfunction signatures (monomial.h:125-127)"""
+    import tmlqcd_b200 as tm
+    D, gold = _hmc_dropin()
+    try:
         etas = {}
 
         def rng(ptr, repro, rn_type):
