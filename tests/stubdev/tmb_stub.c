@@ -9,7 +9,7 @@
  * tests/stubdev/libtmb_dropin_stub.so; nothing under tmlqcd_b200/ references it, it is never a fallback of the
  * product (whose tmb_init refuses to run without a CUDA device).
  *
- * Entry points that have no oracle counterpart at this level (the host-pointer chronological guess) return -99.
+ * The chronological guess is restated here on host fields (a few lines; the oracle keeps its own inside the monomials).
  */
 #include <complex.h>
 #include <math.h>
@@ -230,10 +230,47 @@ int tmb_derivative_download(double *h) { NEED(); if (need_df()) return -100; mem
 int tmb_deriv_Sb(int ieo, const void *l, const void *k, double factor) { NEEDG(); if (need_df()) return -100; orc_deriv_Sb(ieo, l, k, S.df, factor); return 0; }
 int tmb_measure_plaquette(double *r) { NEEDG(); *r = orc_measure_plaquette(); return 0; }
 
-/* no oracle counterpart at this level: refused */
-static int refuse(const char *who) { snprintf(S.err, sizeof(S.err), "%s is not part of the host stand-in", who); return -99; }
-int tmb_chrono_add_solution(const void *t, void *const *v, int *ia, int N, int *n) { (void)t; (void)v; (void)ia; (void)N; (void)n; return refuse(__func__); }
-int tmb_chrono_guess(void *t, const void *p, void *const *v, const int *ia, int N, int n, int op) { (void)t; (void)p; (void)v; (void)ia; (void)N; (void)n; (void)op; return refuse(__func__); }
+/* chronological guess (solver/chrono_guess.c:43-172) on the stand-in's host fields: the ring-buffer bookkeeping,
+ * Gram-Schmidt against the newest vector, G_ij = <v_i, A v_j>, b_i = <v_i, phi>, a plain Gaussian elimination for the
+ * few-by-few system, trial = sum_i x_i v_i */
+static cplx cdot(const double *a, const double *b) { const cplx *A = (const cplx *)a, *B = (const cplx *)b; cplx s = 0; for (int i = 0; i < S.Vh * 12; i++) s += conj(A[i]) * B[i]; return s; }
+int tmb_chrono_add_solution(const void *trial, void *const *v, int *ia, int N, int *n) {
+  NEED();
+  if (N <= 0) return 0;
+  int slot;
+  if (*n < N) { ia[*n] = *n; *n += 1; slot = ia[*n - 1]; }
+  else { for (int i = 1; i < N; i++) ia[i - 1] = ia[i]; ia[N - 1] = (N >= 2 ? (ia[N - 2] + 1) % N : 0); slot = ia[N - 1]; }
+  double nrm; tmb_square_norm(trial, &nrm);
+  return tmb_mul_r(v[slot], 1. / sqrt(nrm), trial);
+}
+int tmb_chrono_guess(void *trial, const void *phi, void *const *v, const int *ia, int N, int n, int op) {
+  NEEDG();
+  if (N <= 0 || n <= 0) { memset(trial, 0, NF * sizeof(double)); return 0; }
+  if (n > 20 || op < 0 || op > 2) return -31;
+  cplx G[20][20], b[20], x[20];
+  for (int i = n - 2; i > -1; i--) { /* orthogonalise the older vectors against the newest (:105-117) */
+    const cplx s = cdot(v[ia[n - 1]], v[ia[i]]);
+    cplx *vi = (cplx *)v[ia[i]]; const cplx *vj = (const cplx *)v[ia[n - 1]];
+    for (int k = 0; k < S.Vh * 12; k++) vi[k] -= s * vj[k];
+  }
+  double *t = malloc(NF * sizeof(double));
+  for (int j = 0; j < n; j++) {
+    if (op == TMB_OP_QTM_PM) orc_Qtm_pm_psi(t, v[ia[j]]); else if (op == TMB_OP_QTM_PLUS) orc_Qtm_plus_psi(t, v[ia[j]]); else orc_Qtm_minus_psi(t, v[ia[j]]);
+    for (int i = 0; i <= j; i++) { G[i][j] = cdot(v[ia[i]], t); if (i != j) G[j][i] = conj(G[i][j]); }
+    b[j] = cdot(v[ia[j]], phi);
+  }
+  free(t);
+  for (int c = 0; c < n; c++) { /* Gaussian elimination with partial pivoting */
+    int p = c; for (int r = c + 1; r < n; r++) if (cabs(G[r][c]) > cabs(G[p][c])) p = r;
+    if (p != c) { for (int k = 0; k < n; k++) { cplx w = G[c][k]; G[c][k] = G[p][k]; G[p][k] = w; } cplx w = b[c]; b[c] = b[p]; b[p] = w; }
+    for (int r = c + 1; r < n; r++) { const cplx f = G[r][c] / G[c][c]; for (int k = c; k < n; k++) G[r][k] -= f * G[c][k]; b[r] -= f * b[c]; }
+  }
+  for (int r = n - 1; r >= 0; r--) { cplx s = b[r]; for (int k = r + 1; k < n; k++) s -= G[r][k] * x[k]; x[r] = s / G[r][r]; }
+  cplx *T = trial;
+  for (int k = 0; k < S.Vh * 12; k++) { cplx s = 0; for (int i = 0; i < n; i++) s += x[i] * ((const cplx *)v[ia[i]])[k]; T[k] = s; }
+  return 0;
+}
+
 /* DET / DETRATIO monomials: the oracle's restatement of det_monomial.c / detratio_monomial.c; the oracle sets kappa, mu and
  * the hopping phases per monomial from its own state (periodic or the theta given to orc_set_params), so the stand-in
  * re-installs the caller's phases after every call like mnl_backup_restore_globals does */

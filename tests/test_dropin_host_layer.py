@@ -111,6 +111,11 @@ def test_monomials_with_reference_signatures(on_stub):
     g.test_hmc_monomials_with_reference_signatures()
 
 
+def test_chrono_guess_with_reference_signatures(on_stub):
+    import test_gpu_dropin_ops as g
+    g.test_hmc_chrono_guess_with_reference_signatures()
+
+
 def test_blas32_and_plaquette_symbols(on_stub):
     g32 = _gold("ref_blas32_4x4x4x4.npz")
     io = _gold("ref_io_4x4x4x4.npz")
