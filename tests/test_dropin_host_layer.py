@@ -181,3 +181,23 @@ def test_c_host_programs_run_on_the_stand_in(stub_lib, tmp_path, name, args):
     assert r.returncode == 0 and "# all checks passed" in r.stdout, r.stdout[-2500:] + r.stderr[-1500:]
     if name == "invert_b200":
         assert "# The computed plaquette value is" in r.stdout and os.path.exists(tmp_path / "prop_b200.0000.00.00.inverted")
+
+
+@pytest.mark.parametrize("name,args", [("invert_b200", []), ("benchmark_b200", ["4", "4", "4", "4"])])
+def test_host_layer_under_address_and_ub_sanitizers(tmp_path, name, args):
+    """the same programs with the whole C host layer (tmb_dropin.c, tmb_io.c) compiled in, under ASan + UBSan"""
+    exe = tmp_path / (name + "_san")
+    src = [os.path.join(ROOT, "examples", name + ".c"), os.path.join(ROOT, "tmlqcd_b200", "csrc", "tmb_dropin.c"),
+           os.path.join(ROOT, "tmlqcd_b200", "csrc", "tmb_io.c"), os.path.join(ROOT, "tests", "stubdev", "tmb_stub.c"),
+           os.path.join(ROOT, "oracle", "tmoracle.c")]
+    cmd = ["gcc", "-std=gnu99", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-strict-aliasing",
+           "-ffp-contract=off", "-I", os.path.join(ROOT, "include")] + src + ["-o", str(exe), "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("no sanitizer runtime with this gcc")
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    env.pop("LD_PRELOAD", None)
+    r = subprocess.run([str(exe)] + args, capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
+    assert r.returncode == 0 and "# all checks passed" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
