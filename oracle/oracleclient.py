@@ -111,6 +111,11 @@ class Oracle:
         self.lib.orc_mnl_info(id, C.byref(e0), C.byref(e1), C.byref(i0), C.byref(i1), C.byref(n))
         return {"energy0": e0.value, "energy1": e1.value, "iter0": i0.value, "iter1": i1.value, "csg_n": n.value}
 
+    def lexic2eosub(self):
+        out = np.zeros(self.V, dtype=np.int32)
+        self.lib.orc_get_lexic2eosub(out)
+        return out
+
     def eo2lexic(self):
         out = np.zeros(self.V, dtype=np.int32)
         self.lib.orc_get_eo2lexic(out)

@@ -19,13 +19,30 @@ def ka_of(kappa, theta, ext):
     return np.stack([kappa * np.cos(x), kappa * np.sin(x)], axis=1).reshape(-1)
 
 
-@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (4, 6, 4, 8), (2, 2, 2, 2), (6, 2, 10, 4)])
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (4, 6, 4, 8), (2, 2, 2, 2), (6, 2, 10, 4), (2, 2, 2, 4), (10, 2, 4, 6),
+                                  (4, 8, 2, 2), (2, 10, 6, 4), (12, 4, 2, 8), (2, 4, 12, 2)])
 def test_closed_form_geometry_matches_reference_tables(oracle_lib, dims):
     e = Emul(*dims)
     o = oracle_lib.Oracle(*dims)
     e2l = np.zeros(e.V, dtype=np.int32)
     e.E.emul_eo2lexic(e2l, *dims)
     assert np.array_equal(e2l, o.eo2lexic())
+    # neighbour arithmetic (incl. the wrap-around of extents of 2) against a table built from the reference's orderings:
+    # lexic ix = ((t LX + x) LY + y) LZ + z (geometry_eo.c:290), eo-sub index from g_lexic2eosub
+    T, LX, LY, LZ = dims
+    l2e = o.lexic2eosub()
+    for par in (0, 1):
+        nb = np.zeros(e.Vh * 8, dtype=np.int32)
+        e.E.emul_neighbours(nb, par, *dims)
+        ix = e2l[par * e.Vh:(par + 1) * e.Vh].astype(np.int64)
+        z = ix % LZ; y = (ix // LZ) % LY; x = (ix // (LZ * LY)) % LX; t = ix // (LZ * LY * LX)
+        exp = np.zeros((e.Vh, 8), dtype=np.int64)
+        for mu, (c, ext) in enumerate(((t, T), (x, LX), (y, LY), (z, LZ))):
+            for d, sh in ((0, +1), (1, -1)):
+                cc = [t, x, y, z]
+                cc[mu] = (c + sh) % ext
+                exp[:, 2 * mu + d] = l2e[((cc[0] * LX + cc[1]) * LY + cc[2]) * LZ + cc[3]]
+        assert np.array_equal(nb.reshape(e.Vh, 8), exp), par
     if dims == (4, 4, 4, 4):  # the reference's own g_hi table (golden fixture, geometry_eo.c:1470-1536)
         hi = np.load(os.path.join(ROOT, "tests", "golden", "ref_4x4x4x4.npz"))["hi"]
         for par in (0, 1):
