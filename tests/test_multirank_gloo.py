@@ -1,7 +1,7 @@
 """world_size-2 CPU test (gloo) of the N>1 path's host-side logic: T-slab decomposition of the global
 fields, half-spinor face packing, the send/recv pattern of exchange_faces() (send_up -> rank+1's
 halo_dn, send_dn -> rank-1's halo_up, tmb_capi.cu), the one-off gauge halo, the interior/boundary
-site ranges, and the global sum of reductions.  Compute on each rank is the PRODUCT's site code
+site ranges, the first-slice link halo of the plaquette, and the global sum of reductions.  Compute on each rank is the PRODUCT's site code
 compiled for the host (tests/emul); the check is the oracle on the global lattice."""
 import os
 import sys
@@ -55,6 +55,13 @@ def _worker(rank, world, port, dims_loc, theta, q):
         hu, hd = exchange(su, sd)
         outs[f"hop{par}"] = e.unpack(e.hop(par, sk, U, ka, 0, halo=(hu, hd, Uhalo.numpy())))
         outs[f"tm_sub{par}"] = e.unpack(e.hop(par, sk, U, ka, 2, (1.0, 0.3), sp, halo=(hu, hd, Uhalo.numpy())))
+    # plaquette: the spatial links of my FIRST slice go to rank-1, I receive rank+1's (tmb_measure_plaquette)
+    psend = e.pack_gauge_first_slice(U)
+    pup = torch.empty(psend.size, dtype=torch.float64)
+    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, torch.from_numpy(psend), dn_r, tag=3), dist.P2POp(dist.irecv, pup, up_r, tag=3)]):
+        w.wait()
+    plaq = torch.tensor([e.plaquette(U, pup.numpy())], dtype=torch.float64)
+    dist.all_reduce(plaq)  # the ncclAllReduce behind finish_reduction
     nrm = torch.tensor([float(np.sum(k[rank * Vhl:(rank + 1) * Vhl] ** 2))], dtype=torch.float64)
     dist.all_reduce(nrm)  # the ncclAllReduce of tmb_square_norm
     gathered = {}
@@ -63,7 +70,7 @@ def _worker(rank, world, port, dims_loc, theta, q):
         dist.all_gather(lst, torch.from_numpy(np.ascontiguousarray(loc)))
         gathered[name] = torch.cat(lst).numpy()
     if rank == 0:
-        q.put((gathered, float(nrm.item()), g, k, p))
+        q.put((gathered, float(nrm.item()), g, k, p, float(plaq.item())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,7 +84,7 @@ def test_two_rank_T_split_matches_global_oracle(oracle_lib, dims_loc, theta):
     procs = [ctx.Process(target=_worker, args=(r, world, port, dims_loc, theta, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    gathered, nrm, g, k, p = q.get(timeout=180)
+    gathered, nrm, g, k, p, plaq = q.get(timeout=180)
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
@@ -91,3 +98,4 @@ def test_two_rank_T_split_matches_global_oracle(oracle_lib, dims_loc, theta):
         o.tm_sub_Hopping_Matrix(par, exp, p, k, 1.0, 0.3)
         assert np.linalg.norm(gathered[f"tm_sub{par}"] - exp) / np.linalg.norm(exp) < 1e-14
     assert abs(nrm / o.square_norm(k, o.Vh) - 1) < 1e-14
+    assert abs(plaq / o.measure_plaquette() - 1) < 1e-13
