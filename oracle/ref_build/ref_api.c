@@ -499,3 +499,17 @@ void ref_diff_32(float *q, float *r, float *s, int n) { diff_32((spinor32 *)q, (
 void ref_mul_r_32(float *r, float c, float *s, int n) { mul_r_32((spinor32 *)r, c, (spinor32 *)s, n); }
 void ref_assign_mul_add_mul_r_32(float *r, float *s, float c1, float c2, int n) { assign_mul_add_mul_r_32((spinor32 *)r, (spinor32 *)s, c1, c2, n); }
 void ref_gamma5_32(float *l, float *k, int n) { gamma5_32((spinor32 *)l, (spinor32 *)k, n); }
+
+/* ---- the RGMIXEDCG branch of invert_doublet_eo (invert_doublet_eo.c:145-150): groundwork for the next round ---- */
+#include "operator/tm_operators_nd_32.h"
+#include "solver/rg_mixed_cg_her_nd.h"
+void ref_Qtm_pm_ndpsi_32(float *ls, float *lc, float *ks, float *kc) {
+  Qtm_pm_ndpsi_32((spinor32 *)ls, (spinor32 *)lc, (spinor32 *)ks, (spinor32 *)kc);
+}
+int ref_rg_mixed_cg_her_nd(double *pu, double *pd, double *qu, double *qd, int max_iter, double eps_sq, int rel_prec, double delta) {
+  solver_params_t sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.mcg_delta = (float)delta;
+  return rg_mixed_cg_her_nd((spinor *)pu, (spinor *)pd, (spinor *)qu, (spinor *)qd, sp, max_iter, eps_sq, rel_prec, VOLUME / 2,
+                            &Qtm_pm_ndpsi, &Qtm_pm_ndpsi_32);
+}

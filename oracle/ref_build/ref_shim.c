@@ -34,6 +34,8 @@ OFF_PATH(assign_mul_one_sw_pm_imu_site_lexic)
 OFF_PATH(assign_mul_one_sw_pm_imu_site_lexic_32)
 OFF_PATH(clover_gamma5_nd)
 OFF_PATH(clover_inv_nd)
+/* referenced by Qsw_pm_ndpsi_32 in operator/tm_operators_nd_32.c (compiled for Qtm_pm_ndpsi_32) */
+OFF_PATH(assign_mul_one_sw_pm_imu_eps_32_orphaned) OFF_PATH(clover_gamma5_nd_32_orphaned) OFF_PATH(clover_inv_nd_32_orphaned)
 OFF_PATH(init_blocks_eo_gaugefield)
 OFF_PATH(init_blocks_eo_gaugefield_32)
 OFF_PATH(init_blocks_gaugefield)
