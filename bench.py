@@ -7,7 +7,17 @@
 A step is one EO+OE pair of Hopping_Matrix calls over the whole local lattice, exactly the loop
 body of the reference's benchmark.c:293-299.  Workload: N=1 -> BASELINE configs[1] lattice
 (24^3 x 48, kappa=0.16, mu=0.01, random SU(3) gauge); N>1 -> configs[2]: 48^3 x (12 N) split
-along T, 48^3 x 12 per GPU (weak scaling), halos over NCCL.  One JSON line on stdout (rank 0).
+along T, 48^3 x 12 per GPU (weak scaling), T-neighbour fields read over NVLink (peer mode; NCCL halos as fallback).
+One JSON line on stdout (rank 0).
+
+Keys beyond the driver's contract: `roofline` (achieved = 1536 B x sites / mean launch time, peak = MEASURED_PEAKS.json,
+`traffic` = DRAM bytes per launch from the committed ncu capture, `copy_gbs_sustained_this_run` = device-to-device copy
+bandwidth sustained in this process), `e2e` (the same pairs through the reference-named Hopping_Matrix() with pinned HOST
+buffers, at every N), `cg` (invert_eo time to solution: device-resident, through the host-pointer drop-in, mixed precision,
+12-real links, true residual by the CPU M_full), `cpu_baseline` (the unmodified reference on all host cores), `compression12`,
+and one section per remaining BASELINE config, each in its own process (scripts/bench_sections.py): `benchmark_8x8x8x8`
+(configs[0]), `nd` (configs[3]), `hmc` (configs[4]).  `--lattice TxLXxLYxLZ --global-chunk-t 12` gives the strong-scaling
+series of configs[2] on one global problem (scripts/gpu_strong.sh).
 """
 import argparse
 import ctypes as C
