@@ -77,6 +77,11 @@ def test_solvers_with_reference_signatures(dropin):
     g.test_solvers_with_reference_signatures(dropin)
 
 
+def test_inversions_with_reference_signatures(dropin):
+    import test_gpu_dropin_ops as g
+    g.test_inversions_with_reference_signatures(dropin)
+
+
 def test_reference_symbols_globals_and_dirty_flag(on_stub, oracle_lib):
     import test_gpu_parity as g
     g.test_dropin_reference_symbols(oracle_lib)

@@ -91,6 +91,24 @@ def test_solvers_with_reference_signatures(dropin):
     assert it > 0 and rel_l2(x, xr) <= 1e-8
 
 
+def test_inversions_with_reference_signatures(dropin):
+    """invert_eo (17 arguments, invert_eo.c:83-89) and invert_doublet_eo (invert_doublet_eo.c:68-76) with host buffers
+    against the solutions of the unmodified reference: argument order of the four outputs and four sources included"""
+    import tmlqcd_b200 as tm
+    D, base = dropin
+    k, p, q, w = (np.array(base[n]) for n in ("k", "p", "q", "w"))
+    sp = tm.capi.SolverParams()
+    en, on = D.spinor(), D.spinor()
+    it = D.invert_eo(en, on, k, p, 1e-20, 1000, CG, 1, 0, 1, 0, None, sp, 0, 0, 0, 18)
+    assert abs(it - int(base["invert_iters"])) <= 1
+    assert rel_l2(en, base["invert_en"]) <= 1e-8 and rel_l2(on, base["invert_on"]) <= 1e-8
+    outs = [D.spinor() for _ in range(4)]
+    it = D.invert_doublet_eo(*outs, k, p, q, w, 1e-18, 1000, CG, 1, sp, 0, 0, 18)
+    assert abs(it - int(base["invert_doublet_iters"])) <= 1
+    for o_, name in zip(outs, ("ens", "ons", "enc", "onc")):
+        assert rel_l2(o_, base["invert_doublet_" + name]) <= 1e-8, name
+
+
 def _hmc_dropin():
     import tmlqcd_b200 as tm
     gold = _gold("ref_hmc_4x4x4x4.npz")
