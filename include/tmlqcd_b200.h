@@ -58,7 +58,8 @@ int tmb_set_hop2_variant(int v); /* two-flavour hop: 0 = both flavours in one th
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);
 int tmb_set_host_chunks(int n); /* chunks of the pipelined host-pointer Hopping_Matrix (default 8, the measured best at 24^3x48) */
-int tmb_set_overlap(int flags); /* bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows, bit2: no CUDA-graph replay in the CG, bit3: L2 prefetch of the epilogue operands (p, dotw), bit4: the CG takes <p, A p> from the last hop (operand load) instead of |Q- p|^2 from the second */
+int tmb_set_p2p_diag(int bits); /* peer-mode timing diagnostics (results INVALID across ranks); refused unless TMB_P2P_DIAG=1 */
+int tmb_set_overlap(int flags); /* unknown bits are refused. bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows, bit2: no CUDA-graph replay in the CG, bit3: L2 prefetch of the epilogue operands (p, dotw), bit4: the CG takes <p, A p> from the last hop (operand load) instead of |Q- p|^2 from the second */
 
 /* ---- memory ---- */
 void *tmb_field_alloc(void);         /* one eo spinor field, VOLUME/2 sites, device SoA layout */
@@ -85,6 +86,9 @@ int tmb_timer_stop(float *ms);
 /* ---- operators on device fields ---- */
 /* Hopping_Matrix(ieo,l,k): operator/Hopping_Matrix.c:131 */
 int tmb_Hopping_Matrix(int ieo, void *l, const void *k);
+/* Hopping_Matrix_nocom (operator/Hopping_Matrix_nocom.c): no halo exchange - the comm-off leg of benchmark.c:337-373;
+ * with a split T the slab wraps onto itself, on one rank it is Hopping_Matrix */
+int tmb_Hopping_Matrix_nocom(int ieo, void *l, const void *k);
 /* the same on caller-owned HOST buffers (reference AoS layout), transfers pipelined with the kernel
  * in chunks of time-slices; mode 0: Hopping_Matrix, mode 1: tm_times_Hopping_Matrix with cfactor */
 int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_host, int mode, double cf_re, double cf_im);
@@ -146,6 +150,12 @@ int tmb_assign_to_32(void *field32, const void *field64);        /* linalg/assig
 int tmb_assign_to_64(void *field64, const void *field32);
 int tmb_Hopping_Matrix_32(int ieo, void *l32, const void *k32);  /* operator/Hopping_Matrix_32.c:119 */
 int tmb_Qtm_pm_psi_32(void *l32, const void *k32);               /* operator/tm_operators_32.c:94 */
+/* D_psi_32 on an (even, odd) pair of float fields (operator/D_psi.h:28); M_full_32 with g5 != 0 gives the Q_full rows
+ * that Q_pm_psi_32 (tm_operators_32.c:141) is built from */
+int tmb_D_psi_eo_32(void *even_new32, void *odd_new32, const void *even32, const void *odd32);
+int tmb_M_full_32(void *even_new32, void *odd_new32, const void *even32, const void *odd32, int g5);
+int tmb_field32_upload_lexic(void *even32, void *odd32, const float *host_lexic32);
+int tmb_field32_download_lexic(float *host_lexic32, const void *even32, const void *odd32);
 int tmb_set_mixcg(double innereps, int maxinnersolverit);        /* mixcg_innereps / mixcg_maxinnersolverit, default_input_values.h:193 */
 /* mixed_cg_her(P,Q,params,max_iter,eps_sq,rel_prec,VOLUME/2,&Qtm_pm_psi,&Qtm_pm_psi_32): solver/mixed_cg_her.c:65 */
 int tmb_mixed_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec);

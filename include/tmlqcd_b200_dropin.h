@@ -130,6 +130,9 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
 /* operator/Hopping_Matrix_32.c:119; operator/tm_operators_32.c:94; solver/mixed_cg_her.c:65 */
 void Hopping_Matrix_32(const int ieo, spinor32 *const l, spinor32 *const k);
 void Qtm_pm_psi_32(spinor32 *const l, spinor32 *const k);
+/* operator/D_psi.h:28; operator/tm_operators_32.c:141: lexicographic spinor32 fields of VOLUME sites */
+void D_psi_32(spinor32 *const P, spinor32 *const Q);
+void Q_pm_psi_32(spinor32 *const l, spinor32 *const k);
 int mixed_cg_her(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
                  const int rel_prec, const int N, matrix_mult f, matrix_mult32 f32);
 /* linalg/square_norm_32.c:95, scalar_prod_r_32.c:109, assign_add_mul_r_32.c:104, assign_mul_add_r_32.c:81, diff_32.c:39,

@@ -328,6 +328,10 @@ void ref_update_gauge32(void) {
 void ref_set_mixcg(double innereps, int maxinner) { mixcg_innereps = innereps; mixcg_maxinnersolverit = maxinner; }
 void ref_Hopping_Matrix_32(int ieo, float *l, float *k) { Hopping_Matrix_32(ieo, (spinor32 *)l, (spinor32 *)k); }
 void ref_Qtm_pm_psi_32(float *l, float *k) { Qtm_pm_psi_32((spinor32 *)l, (spinor32 *)k); }
+/* operator/D_psi.h:28 and its caller operator/tm_operators_32.c:141: lexicographic spinor32 fields of VOLUME sites
+ * (Q_pm_psi_32 uses g_spinor_field32[0] as a VOLUME-site scratch: fields 0 and 1 of the contiguous slab) */
+void ref_D_psi_32(float *p, float *q) { D_psi_32((spinor32 *)p, (spinor32 *)q); }
+void ref_Q_pm_psi_32(float *l, float *k) { Q_pm_psi_32((spinor32 *)l, (spinor32 *)k); }
 int ref_mixed_cg_her(double *p, double *q, int max_iter, double eps_sq, int rel_prec) {
   solver_params_t sp;
   memset(&sp, 0, sizeof(sp));

@@ -111,6 +111,8 @@ int tmb_gauge_upload(const double *g) {
 #define NEEDG() do { NEED(); if (!S.gauge) { snprintf(S.err, sizeof(S.err), "no gauge field on the device"); return -9; } } while (0)
 
 int tmb_Hopping_Matrix(int ieo, void *l, const void *k) { NEEDG(); orc_Hopping_Matrix(ieo, l, k); return 0; }
+int tmb_Hopping_Matrix_nocom(int ieo, void *l, const void *k) { return tmb_Hopping_Matrix(ieo, l, k); }
+int tmb_comm_nranks(void) { return 1; }
 int tmb_Hopping_Matrix_host(int ieo, double *l, const double *k, int mode, double cre, double cim) {
   NEEDG();
   if (mode == 0) orc_Hopping_Matrix(ieo, l, k); else if (mode == 1) orc_tm_times_Hopping_Matrix(ieo, l, k, cre, cim); else return -13;
@@ -189,6 +191,29 @@ int tmb_assign_to_32(void *f32, const void *f64) { NEED(); narrow(f32, f64); ret
 int tmb_assign_to_64(void *f64, const void *f32) { NEED(); double *d = f64; const float *f = f32; for (size_t i = 0; i < NF; i++) d[i] = f[i]; return 0; }
 int tmb_Hopping_Matrix_32(int ieo, void *l, const void *k) { NEEDG(); double *a = widen(k), *b = malloc(NF * sizeof(double)); orc_Hopping_Matrix(ieo, b, a); narrow(l, b); free(a); free(b); return 0; }
 int tmb_Qtm_pm_psi_32(void *l, const void *k) { NEEDG(); double *a = widen(k), *b = malloc(NF * sizeof(double)); orc_Qtm_pm_psi(b, a); narrow(l, b); free(a); free(b); return 0; }
+int tmb_M_full_32(void *en, void *on, const void *e, const void *o, int g5) {
+  NEEDG();
+  double *a = widen(e), *b = widen(o), *c = malloc(NF * sizeof(double)), *d = malloc(NF * sizeof(double));
+  if (g5) orc_Q_full(c, d, a, b); else orc_M_full(c, d, a, b);
+  narrow(en, c); narrow(on, d); free(a); free(b); free(c); free(d);
+  return 0;
+}
+int tmb_D_psi_eo_32(void *en, void *on, const void *e, const void *o) { return tmb_M_full_32(en, on, e, o, 0); }
+int tmb_field32_upload_lexic(void *e, void *o, const float *lex) {
+  NEED();
+  double *l = malloc(2 * NF * sizeof(double)), *a = malloc(NF * sizeof(double)), *b = malloc(NF * sizeof(double));
+  for (size_t i = 0; i < 2 * NF; i++) l[i] = lex[i];
+  orc_convert_lexic_to_eo(a, b, l); narrow(e, a); narrow(o, b); free(l); free(a); free(b);
+  return 0;
+}
+int tmb_field32_download_lexic(float *lex, const void *e, const void *o) {
+  NEED();
+  double *l = malloc(2 * NF * sizeof(double)), *a = widen(e), *b = widen(o);
+  orc_convert_eo_to_lexic(l, a, b);
+  for (size_t i = 0; i < 2 * NF; i++) lex[i] = (float)l[i];
+  free(l); free(a); free(b);
+  return 0;
+}
 int tmb_blas32(int op, void *r, const void *s1, const void *s2, double c1d, double c2d) {
   NEED();
   float *R = r; const float *A = s1, *B = s2; const float c1 = (float)c1d, c2 = (float)c2d;

@@ -58,6 +58,18 @@ def test_operator_family_members_vs_reference(dropin):
     D.M_oo_sub_g5_ndpsi(a, b, k, p, q, w, -0.139, -0.15)
     assert rel_l2(a, ops["M_oo_sub_g5_ndpsi_s"]) <= TOL and rel_l2(b, ops["M_oo_sub_g5_ndpsi_c"]) <= TOL
     D.mul_one_pm_iconst(out, k, 0.21, -1); assert rel_l2(out, ops["mul_one_pm_iconst"]) <= TOL
+    # single-precision lexicographic operators (operator/D_psi.h:28, tm_operators_32.c:141) vs the unmodified reference's
+    # float results: both sides round differently, north_star's single-precision tolerance is 1e-5
+    g32 = _gold("ref_dpsi32_4x4x4x4.npz")
+    lex32 = np.array(g32["lex32"]); o32 = np.zeros_like(lex32)
+    D.D_psi_32(o32, lex32); assert rel_l2(o32.astype(np.float64), g32["D_psi_32"].astype(np.float64)) <= 1e-5
+    assert rel_l2(o32.astype(np.float64), ops_D_psi(D, lex32)) <= 1e-5
+    D.Q_pm_psi_32(o32, lex32); assert rel_l2(o32.astype(np.float64), g32["Q_pm_psi_32"].astype(np.float64)) <= 1e-5
+
+
+def ops_D_psi(D, lex32):
+    """the double-precision D_psi of the same library on the float-rounded input"""
+    out = D.spinor(D.V); D.D_psi(out, np.ascontiguousarray(lex32, dtype=np.float64)); return out
 
 
 def test_host_memory_helpers_and_precision_conversion(dropin):

@@ -38,7 +38,7 @@ DEVICE_API = {
     "tmb_comm_unique_id": (_i, [_vp]), "tmb_comm_init": (_i, [_vp, _i, _i]), "tmb_comm_loopback": (_i, [_i]),
     "tmb_comm_nranks": (_i, []), "tmb_comm_peer_mode": (_i, []),
     "tmb_set_boundary": (_i, [_d, _dp]), "tmb_set_hopping_phases": (_i, [_dp]), "tmb_set_mu": (_i, [_d]),
-    "tmb_set_nd": (_i, [_d] * 3), "tmb_set_tuning": (_i, [_i] * 3), "tmb_set_hop2_variant": (_i, [_i]), "tmb_set_overlap": (_i, [_i]), "tmb_set_host_chunks": (_i, [_i]), "tmb_set_compression": (_i, [_i]),
+    "tmb_set_nd": (_i, [_d] * 3), "tmb_set_tuning": (_i, [_i] * 3), "tmb_set_hop2_variant": (_i, [_i]), "tmb_set_overlap": (_i, [_i]), "tmb_set_p2p_diag": (_i, [_i]), "tmb_set_host_chunks": (_i, [_i]), "tmb_set_compression": (_i, [_i]),
     "tmb_field_alloc": (_vp, []), "tmb_field_free": (_i, [_vp]), "tmb_field_zero": (_i, [_vp]),
     "tmb_host_alloc": (_vp, [C.c_size_t]), "tmb_host_free": (_i, [_vp]),
     "tmb_host_register": (_i, [_vp, C.c_size_t]), "tmb_host_unregister": (_i, [_vp]),
@@ -46,7 +46,7 @@ DEVICE_API = {
     "tmb_field_upload_lexic": (_i, [_vp, _vp, _vp]), "tmb_field_download_lexic": (_i, [_vp, _vp, _vp]),
     "tmb_gauge_upload": (_i, [_vp]), "tmb_sync": (_i, []),
     "tmb_timer_start": (_i, []), "tmb_timer_stop": (_i, [C.POINTER(C.c_float)]),
-    "tmb_Hopping_Matrix": (_i, [_i, _vp, _vp]), "tmb_Hopping_Matrix_host": (_i, [_i, _vp, _vp, _i, _d, _d]),
+    "tmb_Hopping_Matrix": (_i, [_i, _vp, _vp]), "tmb_Hopping_Matrix_nocom": (_i, [_i, _vp, _vp]), "tmb_Hopping_Matrix_host": (_i, [_i, _vp, _vp, _i, _d, _d]),
     "tmb_tm_times_Hopping_Matrix": (_i, [_i, _vp, _vp, _d, _d]),
     "tmb_tm_sub_Hopping_Matrix": (_i, [_i, _vp, _vp, _vp, _d, _d]),
     "tmb_H_eo_tm_inv_psi": (_i, [_vp, _vp, _i, _d]), "tmb_tm_sub_H_eo_gamma5": (_i, [_vp, _vp, _vp, _i, _d]),
@@ -69,6 +69,8 @@ DEVICE_API = {
     "tmb_field32_alloc": (_vp, []), "tmb_field32_upload": (_i, [_vp, _vp]), "tmb_field32_download": (_i, [_vp, _vp]),
     "tmb_assign_to_32": (_i, [_vp, _vp]), "tmb_assign_to_64": (_i, [_vp, _vp]),
     "tmb_Hopping_Matrix_32": (_i, [_i, _vp, _vp]), "tmb_Qtm_pm_psi_32": (_i, [_vp, _vp]),
+    "tmb_D_psi_eo_32": (_i, [_vp] * 4), "tmb_M_full_32": (_i, [_vp] * 4 + [_i]),
+    "tmb_field32_upload_lexic": (_i, [_vp, _vp, _vp]), "tmb_field32_download_lexic": (_i, [_vp, _vp, _vp]),
     "tmb_set_mixcg": (_i, [_d, _i]), "tmb_mixed_cg_her": (_i, [_vp, _vp, _i, _d, _i]),
     "tmb_invert_eo_mixed": (_i, [_vp] * 4 + [_d, _i, _i]),
     "tmb_set_mcg_delta": (_i, [_d]), "tmb_rg_mixed_cg_her": (_i, [_vp, _vp, _i, _d, _i]),
@@ -137,6 +139,7 @@ DROPIN_API = {
     "cg_her": (_i, [_sp, _sp, _i, _d, _i, _i, _vp]),
     "invert_eo": (_i, [_sp] * 4 + [_d, _i, _i, _i, _i, _i, _i, _vp, SolverParams, _i, _i, _i, _i]),
     "Hopping_Matrix_32": (None, [_i, _fp, _fp]), "Qtm_pm_psi_32": (None, [_fp, _fp]),
+    "D_psi_32": (None, [_fp, _fp]), "Q_pm_psi_32": (None, [_fp, _fp]),
     "mixed_cg_her": (_i, [_sp, _sp, SolverParams, _i, _d, _i, _i, _vp, _vp]),
     "M_ee_inv_ndpsi": (None, [_sp] * 4 + [_d, _d]), "Qtm_ndpsi": (None, [_sp] * 4),
     "Qtm_dagger_ndpsi": (None, [_sp] * 4), "Qtm_pm_ndpsi": (None, [_sp] * 4),

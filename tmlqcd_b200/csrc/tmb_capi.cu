@@ -21,7 +21,7 @@
  * (the process usually already has torch's libnccl.so.2 loaded; dlopen gives us that copy) */
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { NCCL_SUM = 0, NCCL_FLOAT64 = 8, NCCL_UINT8 = 1 };
+enum { NCCL_SUM = 0, NCCL_MIN = 3, NCCL_FLOAT64 = 8, NCCL_UINT8 = 1 };
 struct NcclApi {
   void *handle;
   int (*GetUniqueId)(ncclUniqueId *);
@@ -273,6 +273,7 @@ static int p2p_small_buffers() {
   const char *cc = getenv("TMB_P2P_COPY_CTAS");
   C.p2p_copy_ctas = cc ? atoi(cc) : 64;
   if (C.p2p_copy_ctas < 1) C.p2p_copy_ctas = 1;
+  if (C.p2p_copy_ctas > 2 * 148) C.p2p_copy_ctas = 2 * 148; /* each pull CTA owns a partial slot and delays the stencil CTAs behind it */
   if (!C.p2p_err) { CU(cudaMalloc(&C.p2p_err, sizeof(int))); CU(cudaMemset(C.p2p_err, 0, sizeof(int))); }
   return 0;
 }
@@ -287,6 +288,17 @@ static int setup_p2p() {
   if (mb) want = (size_t)atoll(mb) << 20;
   if (want > freeb / 10 * 7) want = freeb / 10 * 7;
   want &= ~(size_t)((2 << 20) - 1);
+  { /* every rank must run out of arena at the same allocation (peer mode or NCCL halos is decided per field, and the
+     * two sides of a hop must decide alike): agree on the smallest size any rank can afford */
+    double *dmin = nullptr; CU(cudaMalloc(&dmin, sizeof(double)));
+    double w = (double)want;
+    CU(cudaMemcpy(dmin, &w, sizeof(double), cudaMemcpyHostToDevice));
+    NC(C.nccl.AllReduce(dmin, dmin, 1, NCCL_FLOAT64, NCCL_MIN, C.comm, C.s_main));
+    CU(cudaStreamSynchronize(C.s_main));
+    CU(cudaMemcpy(&w, dmin, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dmin);
+    want = (size_t)w;
+  }
   if (cudaMalloc(&C.arena, want) != cudaSuccess) { cudaGetLastError(); C.arena = nullptr; fprintf(stderr, "tmlqcd_b200: arena allocation failed; NCCL halos only\n"); return 0; }
   C.arena_bytes = want; C.arena_used = ARENA_RESERVED; C.arena_free.clear();
   CU(cudaMemset(C.arena, 0, ARENA_RESERVED));
@@ -336,6 +348,9 @@ extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) {
   memcpy(&id, id128, 128);
   NC(C.nccl.CommInitRank(&C.comm, nranks, id, rank));
   C.nranks = nranks; C.rank = rank; C.dist = true; C.g.dist_t = 1;
+  /* a gauge field uploaded before this call has no exchanged U_0 halo (nor float / 12-real copies of one): make the
+   * next hop fail with "call tmb_gauge_upload first" instead of reading uninitialised Uhalo */
+  C.gauge_loaded = false; C.gauge32_valid = false; C.c12_valid = false; C.c12f_valid = false;
   TRY(setup_p2p());
   return 0;
 }
@@ -402,8 +417,20 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
 /* number of time-slice chunks of the pipelined host-pointer Hopping_Matrix (1..64) */
 extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 1 || n > MAXCHUNK) return fail(-7, "host chunks must be in [1, %d]", MAXCHUNK); C.host_chunks = n; return 0; }
 extern "C" int tmb_set_overlap(int flags) {
-  NEED_INIT(); C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1; C.cg_selfnorm = (flags & 16) ? 0 : 1;
-  C.p2p_diag = (flags >> 3) & 31; /* timing diagnostics only: 1 = boundary reads from the LOCAL field, 2 = no end-of-hop handshake */
+  NEED_INIT();
+  if (flags & ~31) return fail(-7, "tmb_set_overlap: unknown bits in 0x%x (bits 0..4 are defined)", flags);
+  C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1; C.cg_selfnorm = (flags & 16) ? 0 : 1;
+  return 0;
+}
+/* Peer-mode TIMING diagnostics, kept apart from the tuning options above because every one of them gives WRONG
+ * results across ranks: 1 boundary slices read from the LOCAL field, 2 no end-of-hop handshake, 4 no pull,
+ * 8 no halo path in the boundary CTAs, 16 natural slice order.  Refused unless TMB_P2P_DIAG=1 is set in the environment. */
+extern "C" int tmb_set_p2p_diag(int bits) {
+  NEED_INIT();
+  if (bits & ~31) return fail(-7, "tmb_set_p2p_diag: unknown bits in 0x%x", bits);
+  const char *e = getenv("TMB_P2P_DIAG");
+  if (bits && !(e && atoi(e) == 1)) return fail(-7, "tmb_set_p2p_diag: results become invalid; set TMB_P2P_DIAG=1 to allow it");
+  C.p2p_diag = bits;
   return 0;
 }
 
@@ -576,6 +603,7 @@ struct HopOpt {
   int site0 = 0, nsites = -1; /* sub-range of output sites (single rank only); -1: all */
   int prec = 0;               /* 0: double fields, 1: float fields + float gauge copy */
   int fin_op = -1, fin_slot = 0; /* fused finish of the dot reduction (single rank) */
+  bool nocom = false;         /* Hopping_Matrix_nocom: no halo exchange, the slab wraps onto itself in T */
 };
 static int ensure_gauge32();
 static int ensure_gauge12(int prec);
@@ -620,7 +648,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   a.pdl = C.pdl; a.prefetch = C.prefetch;
   a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && C.nranks == 1) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
   int np = 0;
-  if (!C.dist) {
+  if (!C.dist || o.nocom) {
     a.dist = 0; a.site0 = o.site0; a.nsites = o.nsites < 0 ? C.g.Vh : o.nsites; a.split = a.nsites; a.gap = 0;
     /* tuning variants exist for the plain Hopping_Matrix kernel only */
     a.variant = (o.mode == 0 && !a.dot && !a.recon12 && !o.prec) ? C.hop_variant : 0;
@@ -628,6 +656,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
       a.variant = (!a.recon12 && !o.prec && (C.hop_variant == 10 || hop_residency_448(a.nsites))) ? 10 : 0;
     a.xblock = o.nsites < 0 ? C.xblock : 0;
     np = tmb_hop_grid(a);
+    if (np > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", np, C.npartial);
     a.fin_total = np;
     KL(tmb_launch_hop(a, C.s_main));
   } else if (C.p2p && o.nsites < 0 && (C.nranks == 1 || in_arena(in))) {
@@ -643,6 +672,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     a.halo_up_w = C.halo_up; a.halo_dn_w = C.halo_dn;
     a.p2p_copy_ctas = C.p2p_copy_ctas;
     np = tmb_hop_grid(a);
+    if (np > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", np, C.npartial);
     a.fin_total = np;
     KL(tmb_launch_hop(a, C.s_main));
   } else {
@@ -668,13 +698,13 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     a.dist = 1; a.site0 = 0; a.nsites = 2 * S; a.split = S; a.gap = Vh - 2 * S;
     a.partial = C.partial + nb_int;
     a.fin_total = ai.fin_total = nb_int + tmb_hop_grid(a);
+    if (a.fin_total > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", a.fin_total, C.npartial);
     KL(tmb_launch_hop(a, C.s_comm));
     CU(cudaEventRecord(C.ev_halo, C.s_comm));
     if (nb_int > 0) KL(tmb_launch_hop(ai, C.s_main));
     CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
     np = nb_int + tmb_hop_grid(a);
   }
-  if (np > C.npartial) return fail(-10, "partial buffer too small");
   if (o.npartial) *o.npartial = np;
   return 0;
 }
@@ -747,6 +777,13 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
 /* ------------------------------------------------------------------ operators on device fields */
 extern "C" int tmb_Hopping_Matrix(int ieo, void *l, const void *k) {
   NEED_INIT(); HopOpt o; return hop(ieo, F(l), F(k), o);
+}
+/* Hopping_Matrix_nocom (operator/Hopping_Matrix_nocom.c): the same arithmetic without the exchange, which the reference
+ * times against Hopping_Matrix to isolate the communication (benchmark.c:337-373).  Without xchange_field the reference
+ * reads whatever its halo region holds; here the +-t neighbours of the boundary slices are the slab's own opposite
+ * boundary (plain single-GPU kernel on the local slab).  On one rank it IS Hopping_Matrix. */
+extern "C" int tmb_Hopping_Matrix_nocom(int ieo, void *l, const void *k) {
+  NEED_INIT(); HopOpt o; o.nocom = true; return hop(ieo, F(l), F(k), o);
 }
 extern "C" int tmb_tm_times_Hopping_Matrix(int ieo, void *l, const void *k, double cre, double cim) {
   NEED_INIT(); HopOpt o; o.mode = 1; o.cf = make_double2(cre, cim); return hop(ieo, F(l), F(k), o);

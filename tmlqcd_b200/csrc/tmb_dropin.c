@@ -110,7 +110,11 @@ static void down(spinor *h, int k) { CHK(tmb_field_download((double *)h, dev(k))
 void Hopping_Matrix(const int ieo, spinor *const l, spinor *const k) {
   sync_globals(); CHK(tmb_Hopping_Matrix_host(ieo, (double *)l, (const double *)k, 0, 1., 0.));
 }
-void Hopping_Matrix_nocom(const int ieo, spinor *const l, spinor *const k) { Hopping_Matrix(ieo, l, k); }
+/* operator/Hopping_Matrix_nocom.c: no exchange (benchmark.c:337-373 times it against Hopping_Matrix); one rank: identical */
+void Hopping_Matrix_nocom(const int ieo, spinor *const l, spinor *const k) {
+  if (tmb_comm_nranks() == 1) { Hopping_Matrix(ieo, l, k); return; }
+  sync_globals(); up(0, k); CHK(tmb_Hopping_Matrix_nocom(ieo, dev(1), dev(0))); down(l, 1);
+}
 void tm_times_Hopping_Matrix(const int ieo, spinor *const l, spinor *const k, _Complex double const cf) {
   sync_globals(); CHK(tmb_Hopping_Matrix_host(ieo, (double *)l, (const double *)k, 1, creal(cf), cimag(cf)));
 }
@@ -340,6 +344,29 @@ static void *dev32(int k) {
 void Hopping_Matrix_32(const int ieo, spinor32 *const l, spinor32 *const k) {
   sync_globals(); CHK(tmb_field32_upload(dev32(0), (const float *)k));
   CHK(tmb_Hopping_Matrix_32(ieo, dev32(1), dev32(0))); CHK(tmb_field32_download((float *)l, dev32(1)));
+}
+/* operator/D_psi.h:28 (body: operator/D_psi.c, the float instantiation of D_psi_body.c) and its caller Q_pm_psi_32,
+ * operator/tm_operators_32.c:141-149: lexicographic spinor32 fields of VOLUME sites */
+void D_psi_32(spinor32 *const P, spinor32 *const Q) {
+  if (P == Q) { /* D_psi_body.c:267-272 */
+    printf("Error in D_psi (operator.c):\n");
+    printf("Arguments must be different spinor fields\n");
+    printf("Program aborted\n");
+    exit(1);
+  }
+  sync_globals();
+  CHK(tmb_field32_upload_lexic(dev32(0), dev32(1), (const float *)Q));
+  CHK(tmb_D_psi_eo_32(dev32(2), dev32(3), dev32(0), dev32(1)));
+  CHK(tmb_field32_download_lexic((float *)P, dev32(2), dev32(3)));
+}
+void Q_pm_psi_32(spinor32 *const l, spinor32 *const k) {
+  sync_globals();
+  CHK(tmb_field32_upload_lexic(dev32(0), dev32(1), (const float *)k));
+  CHK(tmb_set_mu(-g_mu));
+  CHK(tmb_M_full_32(dev32(2), dev32(3), dev32(0), dev32(1), 1)); /* g5 D(-mu) */
+  CHK(tmb_set_mu(g_mu));
+  CHK(tmb_M_full_32(dev32(0), dev32(1), dev32(2), dev32(3), 1)); /* g5 D(+mu) */
+  CHK(tmb_field32_download_lexic((float *)l, dev32(0), dev32(1)));
 }
 void Qtm_pm_psi_32(spinor32 *const l, spinor32 *const k) {
   sync_globals(); CHK(tmb_field32_upload(dev32(0), (const float *)k));

@@ -416,6 +416,7 @@ static cudaError_t hop_mode_f(const tmb_hop_launch &a, cudaStream_t s) {
     case 0: return hop_go<float2, 0, DIST, 0, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
     case 1: return hop_go<float2, 1, DIST, 0, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
     case 2: return hop_go<float2, 2, DIST, 0, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
+    case 3: return hop_go<float2, 3, DIST, 0, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s); /* D_psi_32 rows */
   }
   return cudaErrorInvalidValue;
 }
@@ -690,14 +691,14 @@ struct EwPackEoRange { double2 *soa; const double2 *aos; int Vh, i0, n;
 struct EwUnpackEoRange { double2 *aos; const double2 *soa; int Vh, i0, n;
   __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / n), i = i0 + (int)(k - (size_t)c * n); aos[(size_t)i * 12 + c] = soa[(size_t)c * Vh + i]; } };
 /* lexicographic host field of V sites <-> (even, odd) device fields (linalg/convert_eo_to_lexic.c:35-115) */
-struct EwPackLex { double2 *even, *odd; const double2 *lex; tmb_geom g;
+template <class V2> struct EwPackLex { V2 *even, *odd; const V2 *lex; tmb_geom g;
   __host__ __device__ void operator()(size_t k) const {
     const size_t per = (size_t)12 * g.Vh; const int par = (int)(k / per); const size_t kk = k - par * per;
     const int c = (int)(kk / g.Vh), i = (int)(kk - (size_t)c * g.Vh);
     const int ix = tmb_eo_to_lexic(g, par, i);
     (par ? odd : even)[kk] = lex[(size_t)ix * 12 + c];
   } };
-struct EwUnpackLex { double2 *lex; const double2 *even, *odd; tmb_geom g;
+template <class V2> struct EwUnpackLex { V2 *lex; const V2 *even, *odd; tmb_geom g;
   __host__ __device__ void operator()(size_t k) const {
     const size_t per = (size_t)12 * g.Vh; const int par = (int)(k / per); const size_t kk = k - par * per;
     const int c = (int)(kk / g.Vh), i = (int)(kk - (size_t)c * g.Vh);
@@ -732,8 +733,10 @@ cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStr
 cudaError_t tmb_launch_unpack_eo(double2 *aos, const double2 *soa, int Vh, cudaStream_t s) { EwUnpackEo f = {aos, soa, Vh}; EW_LAUNCH(f, (size_t)12 * Vh, nullptr, s); }
 cudaError_t tmb_launch_pack_eo_range(double2 *soa, const double2 *aos, int Vh, int i0, int n, cudaStream_t s) { EwPackEoRange f = {soa, aos, Vh, i0, n}; EW_LAUNCH(f, (size_t)12 * n, nullptr, s); }
 cudaError_t tmb_launch_unpack_eo_range(double2 *aos, const double2 *soa, int Vh, int i0, int n, cudaStream_t s) { EwUnpackEoRange f = {aos, soa, Vh, i0, n}; EW_LAUNCH(f, (size_t)12 * n, nullptr, s); }
-cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackLex f = {even, odd, lex, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
-cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s) { EwUnpackLex f = {lex, even, odd, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
+cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackLex<double2> f = {even, odd, lex, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
+cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s) { EwUnpackLex<double2> f = {lex, even, odd, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
+cudaError_t tmb_launch_pack_lexic_f(float2 *even, float2 *odd, const float2 *lex, tmb_geom g, cudaStream_t s) { EwPackLex<float2> f = {even, odd, lex, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
+cudaError_t tmb_launch_unpack_lexic_f(float2 *lex, const float2 *even, const float2 *odd, tmb_geom g, cudaStream_t s) { EwUnpackLex<float2> f = {lex, even, odd, g}; EW_LAUNCH(f, (size_t)24 * g.Vh, nullptr, s); }
 cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s) { EwPackGauge f = {U, lex, g}; EW_LAUNCH(f, (size_t)72 * g.Vh, nullptr, s); }
 cudaError_t tmb_launch_pack_halo(int prec, void *up, void *dn, const void *in, tmb_geom g, cudaStream_t s) {
   if (prec) { EwPackHalo<float2> f = {(float2 *)up, (float2 *)dn, (const float2 *)in, g}; EW_LAUNCH(f, (size_t)6 * g.S, nullptr, s); }

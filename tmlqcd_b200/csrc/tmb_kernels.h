@@ -121,6 +121,8 @@ cudaError_t tmb_launch_pack_eo_range(double2 *soa, const double2 *aos, int Vh, i
 cudaError_t tmb_launch_unpack_eo_range(double2 *aos, const double2 *soa, int Vh, int i0, int n, cudaStream_t s);
 cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s);
+cudaError_t tmb_launch_pack_lexic_f(float2 *even, float2 *odd, const float2 *lex, tmb_geom g, cudaStream_t s);
+cudaError_t tmb_launch_unpack_lexic_f(float2 *lex, const float2 *even, const float2 *odd, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_pack_gauge(double2 *U, const double2 *lex, tmb_geom g, cudaStream_t s);
 /* T-face half-spinors: send_up = (1-g0) proj of the last slice, send_dn = (1+g0) proj of the first */
 cudaError_t tmb_launch_pack_halo(int prec, void *send_up, void *send_dn, const void *in, tmb_geom g, cudaStream_t s);
