@@ -53,7 +53,9 @@ int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_ope
  * of the plain kernel; 10 forces 448.  cache_hints: 1 = L2 eviction policies on the link / spinor loads, 0 = plain
  * loads, -1 (default) = policies only when links + CG vectors exceed the L2 (see eff_hints() in tmb_capi.cu) */
 int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
-int tmb_set_hop2_variant(int v); /* two-flavour hop: 0 = both flavours in one thread (default, measured best), 1 = lane-paired flavours */
+/* two-flavour hop: 2 (default) = the hopping kernel with two flavour groups of warps per CTA (every precision, compression and
+ * communication mode, fused <p, A p>); 0 = both flavours in one thread, 1 = lane-paired flavours (round-1 kernels: one rank, double) */
+int tmb_set_hop2_variant(int v);
 /* CompressionType of the reference (misc_types.h:33-37): 18 = full links (default), 12 = two rows streamed,
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);
@@ -174,6 +176,14 @@ int tmb_Qtm_pm_ndpsi(void *ls, void *lc, const void *ks, const void *kc);
 int tmb_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq, int rel_prec);
 int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
                           const void *ec, const void *oc, double precision, int max_iter, int rel_prec);
+/* the same with invert_doublet_eo's solver_flag (invert_doublet_eo.c:145-156): 14 = RGMIXEDCG -> rg_mixed_cg_her_nd, else cg_her_nd */
+int tmb_invert_doublet_eo_solver(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
+                                 const void *ec, const void *oc, double precision, int max_iter, int rel_prec, int solver_flag);
+/* Qtm_pm_ndpsi_32 on float fields (operator/tm_operators_nd_32.c:215) and rg_mixed_cg_her_nd (solver/rg_mixed_cg_her_nd.c:182;
+ * delta = tmb_set_mcg_delta); counts of the last reliable-update solve: float inner, double inner, outer iterations */
+int tmb_Qtm_pm_ndpsi_32(void *ls32, void *lc32, const void *ks32, const void *kc32);
+int tmb_rg_mixed_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq, int rel_prec);
+int tmb_solver_stats_rg(int *inner_sp, int *inner_dp, int *outer);
 
 /* rg_mixed_cg_her (solver/rg_mixed_cg_her.c:180), the default mixed solver of solve_degenerate; delta = solver_params.mcg_delta */
 int tmb_set_mcg_delta(double delta);

@@ -50,6 +50,9 @@ extern double X0, X1, X2, X3; /* read_input.h:65, defined in boundary.c:37 */
 #include "solver/cg_her_nd.h"
 #include "solver/solver_params.h"
 #include "solver/mixed_cg_her.h"
+#include "invert_eo.h"
+#include "invert_doublet_eo.h"
+#include "solver/solver_types.h"
 #include "operator/Hopping_Matrix_32.h"
 #include "operator/tm_operators_32.h"
 
@@ -202,23 +205,18 @@ int ref_cg_her(double *p, double *q, int max_iter, double eps_sq, int rel_prec) 
   return cg_her((spinor *)p, (spinor *)q, max_iter, eps_sq, rel_prec, VOLUME / 2, &Qtm_pm_psi);
 }
 
-/* The CG branch of invert_eo restated on top of the compiled reference functions:
- * invert_eo.c:152-157, :252, :268-270, :306-310 (invert_eo.c itself needs c-lime headers
- * and every other solver to link).  Returns the cg_her iteration count. */
+/* invert_eo itself, compiled unmodified (invert_eo.c:83-561; lime.h comes from stubs/, the solvers it can dispatch to
+ * outside the scoped path are abort stubs in ref_shim.c).  even_odd_flag = 1, no extra masses, NO_EXT_INV. */
+int ref_invert_eo(double *even_new, double *odd_new, double *even, double *odd,
+                  double precision, int max_iter, int rel_prec, int solver_flag) {
+  solver_params_t sp;
+  memset(&sp, 0, sizeof(sp));
+  return invert_eo((spinor *)even_new, (spinor *)odd_new, (spinor *)even, (spinor *)odd, precision, max_iter, solver_flag,
+                   rel_prec, 0, 1, 0, NULL, sp, 0, NO_EXT_INV, 0, NO_COMPRESSION);
+}
 int ref_invert_eo_cg(double *even_new, double *odd_new, double *even, double *odd,
                      double precision, int max_iter, int rel_prec) {
-  spinor *En = (spinor *)even_new, *On = (spinor *)odd_new, *E = (spinor *)even, *O = (spinor *)odd;
-  int iter;
-  assign_mul_one_pm_imu_inv(En, E, +1., VOLUME / 2);
-  Hopping_Matrix(OE, g_spinor_field[DUM_DERI], En);
-  assign_mul_add_r(g_spinor_field[DUM_DERI], +1., O, VOLUME / 2);
-  gamma5(g_spinor_field[DUM_DERI], g_spinor_field[DUM_DERI], VOLUME / 2);
-  iter = cg_her(On, g_spinor_field[DUM_DERI], max_iter, precision, rel_prec, VOLUME / 2, &Qtm_pm_psi);
-  Qtm_minus_psi(On, On);
-  Hopping_Matrix(EO, g_spinor_field[DUM_DERI], On);
-  mul_one_pm_imu_inv(g_spinor_field[DUM_DERI], +1., VOLUME / 2);
-  assign_add_mul_r(En, g_spinor_field[DUM_DERI], +1., VOLUME / 2);
-  return iter;
+  return ref_invert_eo(even_new, odd_new, even, odd, precision, max_iter, rel_prec, CG);
 }
 
 /* ---- ND doublet (a29, a30) ---- */
@@ -238,30 +236,21 @@ int ref_cg_her_nd(double *ps, double *pc, double *qs, double *qc, int max_iter, 
   return cg_her_nd((spinor *)ps, (spinor *)pc, (spinor *)qs, (spinor *)qc, max_iter, eps_sq, rel_prec,
                    VOLUME / 2, &Qtm_pm_ndpsi);
 }
-/* invert_doublet_eo.c:102-178 restated on the compiled reference functions (NO_EXT_INV, CG). */
+/* invert_doublet_eo itself, compiled unmodified (invert_doublet_eo.c:68-187): solver_flag CG or RGMIXEDCG (mcg_delta = delta) */
+int ref_invert_doublet_eo(double *ens, double *ons, double *enc, double *onc,
+                          double *es, double *os, double *ec, double *oc,
+                          double precision, int max_iter, int rel_prec, int solver_flag, double delta) {
+  solver_params_t sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.mcg_delta = (float)delta;
+  return invert_doublet_eo((spinor *)ens, (spinor *)ons, (spinor *)enc, (spinor *)onc, (spinor *)es, (spinor *)os,
+                           (spinor *)ec, (spinor *)oc, precision, max_iter, solver_flag, rel_prec, sp, NO_EXT_INV, 0,
+                           NO_COMPRESSION);
+}
 int ref_invert_doublet_eo_cg(double *ens, double *ons, double *enc, double *onc,
                              double *es, double *os, double *ec, double *oc,
                              double precision, int max_iter, int rel_prec) {
-  spinor *Ens = (spinor *)ens, *Ons = (spinor *)ons, *Enc = (spinor *)enc, *Onc = (spinor *)onc;
-  spinor *Es = (spinor *)es, *Os = (spinor *)os, *Ec = (spinor *)ec, *Oc = (spinor *)oc;
-  int iter;
-  M_ee_inv_ndpsi(Ens, Enc, Es, Ec, g_mubar, g_epsbar);
-  Hopping_Matrix(OE, g_spinor_field[DUM_DERI], Ens);
-  Hopping_Matrix(OE, g_spinor_field[DUM_DERI + 1], Enc);
-  assign_mul_add_r(g_spinor_field[DUM_DERI], +1., Os, VOLUME / 2);
-  assign_mul_add_r(g_spinor_field[DUM_DERI + 1], +1., Oc, VOLUME / 2);
-  gamma5(g_spinor_field[DUM_DERI], g_spinor_field[DUM_DERI], VOLUME / 2);
-  gamma5(g_spinor_field[DUM_DERI + 1], g_spinor_field[DUM_DERI + 1], VOLUME / 2);
-  iter = cg_her_nd(Ons, Onc, g_spinor_field[DUM_DERI], g_spinor_field[DUM_DERI + 1], max_iter, precision,
-                   rel_prec, VOLUME / 2, &Qtm_pm_ndpsi);
-  Qtm_dagger_ndpsi(Ons, Onc, Ons, Onc);
-  Hopping_Matrix(EO, g_spinor_field[DUM_DERI], Ons);
-  Hopping_Matrix(EO, g_spinor_field[DUM_DERI + 1], Onc);
-  M_ee_inv_ndpsi(g_spinor_field[DUM_DERI + 2], g_spinor_field[DUM_DERI + 3], g_spinor_field[DUM_DERI],
-                 g_spinor_field[DUM_DERI + 1], g_mubar, g_epsbar);
-  assign_add_mul_r(Ens, g_spinor_field[DUM_DERI + 2], +1., VOLUME / 2);
-  assign_add_mul_r(Enc, g_spinor_field[DUM_DERI + 3], +1., VOLUME / 2);
-  return iter;
+  return ref_invert_doublet_eo(ens, ons, enc, onc, es, os, ec, oc, precision, max_iter, rel_prec, CG, 0.);
 }
 
 /* ---- timing, the benchmark.c:262-327 recipe: nreps x { H(0, sf1, sf0); H(1, sf2, sf1) } ---- */

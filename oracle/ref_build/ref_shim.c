@@ -62,3 +62,8 @@ OFF_PATH(poly_acc) OFF_PATH(poly_derivative) OFF_PATH(poly_heatbath)
 OFF_PATH(rat_acc) OFF_PATH(rat_derivative) OFF_PATH(rat_heatbath) OFF_PATH(ratcor_acc) OFF_PATH(ratcor_heatbath)
 OFF_PATH(bicgstab_complex) OFF_PATH(cg_mms_tm) OFF_PATH(cg_mms_tm_nd) OFF_PATH(mixed_cg_mms_tm_nd)
 OFF_PATH(sw_term) OFF_PATH(sw_invert) OFF_PATH(sw_deriv) OFF_PATH(sw_all)
+/* invert_eo.c (compiled unmodified) can dispatch to every Krylov solver of solver/; only CG, MIXEDCG and RGMIXEDCG are on
+ * the scoped path */
+OFF_PATH(bicg_complex) OFF_PATH(bicgstabell) OFF_PATH(cgs_real) OFF_PATH(cr) OFF_PATH(fgmres) OFF_PATH(gcr) OFF_PATH(gmres)
+OFF_PATH(gmres_dr) OFF_PATH(incr_eigcg) OFF_PATH(mcr) OFF_PATH(mr) OFF_PATH(pcg_her)
+int gmres_m_parameter = 10, gmresdr_nr_ev = 0; /* read_input.h, only passed to the solvers above */

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 SRC=../../tmlqcd_b200/csrc
 fresh=1
-for f in tmb_emul.cu build.sh $SRC/tmb_kernels.cu $SRC/tmb_force.cu $SRC/tmb_site.cuh $SRC/tmb_geom.h $SRC/tmb_kernels.h; do
+for f in tmb_emul.cu build.sh $SRC/tmb_hop.cuh $SRC/tmb_kernels.cu $SRC/tmb_force.cu $SRC/tmb_site.cuh $SRC/tmb_geom.h $SRC/tmb_kernels.h; do
   if [ ! -e libtmb_emul.so ] || [ "$f" -nt libtmb_emul.so ]; then fresh=0; fi
 done
 if [ $fresh = 1 ]; then exit 0; fi

@@ -9,6 +9,8 @@
  */
 #include "../../tmlqcd_b200/csrc/tmb_kernels.cu"
 #include "../../tmlqcd_b200/csrc/tmb_force.cu"
+/* the two-flavour instantiations (tmb_hop2.cu) are not needed by the host emulation: nothing here launches a kernel */
+cudaError_t tmb_launch_hop_nd(const tmb_hop_launch &, cudaStream_t) { return cudaErrorNotSupported; }
 
 template <int MODE, int DIST>
 static void hop_host(double2 *out, const tmb_hop_fields<double2> &f, const double2 *p, const tmb_geom &g, int par,
@@ -38,12 +40,12 @@ void emul_unpack_eo(double *aos, const double *soa, int Vh) {
 }
 void emul_pack_lexic(double *even, double *odd, const double *lex, int T, int LX, int LY, int LZ) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
-  EwPackLex f = {(double2 *)even, (double2 *)odd, (const double2 *)lex, g};
+  EwPackLex<double2> f = {(double2 *)even, (double2 *)odd, (const double2 *)lex, g};
   for (size_t k = 0; k < (size_t)24 * g.Vh; k++) f(k);
 }
 void emul_unpack_lexic(double *lex, const double *even, const double *odd, int T, int LX, int LY, int LZ) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
-  EwUnpackLex f = {(double2 *)lex, (const double2 *)even, (const double2 *)odd, g};
+  EwUnpackLex<double2> f = {(double2 *)lex, (const double2 *)even, (const double2 *)odd, g};
   for (size_t k = 0; k < (size_t)24 * g.Vh; k++) f(k);
 }
 void emul_pack_gauge(double *U, const double *lex, int T, int LX, int LY, int LZ) {

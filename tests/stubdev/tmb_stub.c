@@ -246,6 +246,10 @@ int tmb_cg_her_nd(void *pu, void *pd, const void *qu, const void *qd, int m, dou
 int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os, const void *ec, const void *oc, double p, int m, int r) {
   NEEDG(); return S.last_iters = orc_invert_doublet_eo_cg(ens, ons, enc, onc, es, os, ec, oc, p, m, r);
 }
+/* RGMIXEDCG (rg_mixed_cg_her_nd) reaches the same solution as the CG to the requested precision; the stand-in serves both with the oracle's CG */
+int tmb_invert_doublet_eo_solver(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os, const void *ec, const void *oc, double p, int m, int r, int solver) {
+  (void)solver; return tmb_invert_doublet_eo(ens, ons, enc, onc, es, os, ec, oc, p, m, r);
+}
 
 /* fermion force */
 static int need_df(void) { if (!S.df) S.df = calloc((size_t)S.V * 32, sizeof(double)); return S.df ? 0 : -100; }

@@ -297,10 +297,10 @@ def test_cg_and_invert_eo(oracle_lib, dims, theta, loopback):
         d.close()
 
 
-@pytest.mark.parametrize("dims,variant", [((4, 4, 6, 8), 0), ((4, 4, 6, 8), 1), ((2, 6, 2, 6), 1)])
+@pytest.mark.parametrize("dims,variant", [((4, 4, 6, 8), 0), ((4, 4, 6, 8), 1), ((2, 6, 2, 6), 1), ((4, 4, 6, 8), 2), ((2, 6, 2, 6), 2)])
 def test_nd_doublet(oracle_lib, dims, variant):
-    """variant 0: both flavours in one thread (default), 1: lane-paired two-flavour kernel;
-    2x6x2x6: 2*Vh = 144 threads, the last warp of the paired kernel is half filled"""
+    """variant 2: two flavour groups of warps per CTA (default), 0: both flavours in one thread, 1: lane-paired two-flavour kernel;
+    2x6x2x6: 72 sites per parity - the last warp of the lane-paired kernel is half filled, the last CTA of the warp-grouped one too"""
     rng, o, d, g = _setup(oracle_lib, dims, (1., 0., 0., 0.))
     try:
         d.ck(d.lib.tmb_set_hop2_variant(variant))
@@ -326,6 +326,81 @@ def test_nd_doublet(oracle_lib, dims, variant):
         assert abs(it - it_ref) <= 1
         for f, a in zip(outs, A):
             assert rel_l2(d.download(f), a) <= 1e-9
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("loopback", [0, 1, 2])
+@pytest.mark.parametrize("compression", [18, 12])
+def test_nd_two_flavour_kernel_every_mode(oracle_lib, loopback, compression):
+    """hop_kernel with NFL = 2 (default two-flavour path): plain, halo-buffer and peer-mode T split, 18- and 12-real links;
+    the CG takes <p, A p> from the second launch (invmaxev^2 |Qhat^dagger p|^2): same counts as the oracle's cg_her_nd"""
+    rng, o, d, g = _setup(oracle_lib, (8, 4, 6, 8), (1., 0.3, 0., 0.7))
+    try:
+        if loopback:
+            d.ck(d.lib.tmb_comm_loopback(loopback)); d.gauge_upload(g)
+        d.ck(d.lib.tmb_set_compression(compression))
+        s, c = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        ds, dc, dls, dlc = d.field(s), d.field(c), d.field(), d.field()
+        for name in ("Qtm_ndpsi", "Qtm_dagger_ndpsi", "Qtm_pm_ndpsi"):
+            e1, e2 = o.spinor(), o.spinor()
+            getattr(o, name)(e1, e2, s, c)
+            d.call(name, dls, dlc, ds, dc)
+            assert rel_l2(d.download(dls), e1) <= TOL and rel_l2(d.download(dlc), e2) <= TOL, name
+        d.call("Qtm_pm_ndpsi", ds, dc, ds, dc)  # l may alias k (tm_operators_nd.c:185)
+        assert rel_l2(d.download(ds), e1) <= TOL and rel_l2(d.download(dc), e2) <= TOL
+        d.upload(ds, s); d.upload(dc, c)
+        e1, e2 = o.spinor(), o.spinor()
+        it_ref = o.cg_her_nd(e1, e2, s, c, 2000, 1e-20, 1)
+        it = d.call("cg_her_nd", dls, dlc, ds, dc, 2000, 1e-20, 1)
+        assert abs(it - it_ref) <= 1
+        assert rel_l2(d.download(dls), e1) <= 1e-9 and rel_l2(d.download(dlc), e2) <= 1e-9
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("loopback", [0, 2])
+def test_rg_mixed_cg_her_nd_vs_reference(oracle_lib, loopback):
+    """Qtm_pm_ndpsi_32 and rg_mixed_cg_her_nd (the RGMIXEDCG branch of invert_doublet_eo.c:145-149) against the unmodified
+    reference's results (tests/golden/ref_ndmixed_4x4x4x4.npz): float operator <= 1e-5, count within +-1 outer / a few inner
+    iterations of the reference's (float rounding decides single inner steps), solution to the solve's precision"""
+    import tmlqcd_b200 as tm
+    gold = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_ndmixed_4x4x4x4.npz"))
+    dims = tuple(int(x) for x in gold["dims"])
+    d = tm.Device(*dims)
+    try:
+        d.set_params(float(gold["kappa"]), float(gold["gmu"]), gold["theta"])
+        d.ck(d.lib.tmb_set_nd(*[float(x) for x in gold["nd"]]))
+        if loopback:
+            d.ck(d.lib.tmb_comm_loopback(loopback))
+        d.gauge_upload(gold["gauge"])
+        s, c = np.array(gold["s"]), np.array(gold["c"])
+        a32, b32, l32, m32 = d.field32(s.astype(np.float32)), d.field32(c.astype(np.float32)), d.field32(), d.field32()
+        d.call("Qtm_pm_ndpsi_32", l32, m32, a32, b32)
+        assert rel_l2(d.download32(l32).astype(np.float64), gold["Qtm_pm_ndpsi_32_s"].astype(np.float64)) <= 1e-5
+        assert rel_l2(d.download32(m32).astype(np.float64), gold["Qtm_pm_ndpsi_32_c"].astype(np.float64)) <= 1e-5
+        d.ck(d.lib.tmb_set_mcg_delta(float(gold["delta"])))
+        ds, dc, dx, dy = d.field(s), d.field(c), d.field(), d.field()
+        it = d.call("rg_mixed_cg_her_nd", dx, dy, ds, dc, 2000, float(gold["eps_sq"]), int(gold["rel_prec"]))
+        assert it > 0 and abs(it - int(gold["count"])) <= 3, (it, int(gold["count"]))
+        assert rel_l2(d.download(dx), gold["x_s"]) <= 1e-8 and rel_l2(d.download(dy), gold["x_c"]) <= 1e-8
+        # the true residual of the returned solution, with the double-precision operator
+        d.call("Qtm_pm_ndpsi", dx, dy, dx, dy)
+        rs, rc = d.download(dx) - s, d.download(dy) - c
+        assert np.sum(rs ** 2) + np.sum(rc ** 2) <= float(gold["eps_sq"]) * (np.sum(s ** 2) + np.sum(c ** 2)) * 1.01
+        # invert_doublet_eo with solver_flag RGMIXEDCG against the oracle's CG solution
+        o = oracle_lib.Oracle(*dims)
+        o.set_gauge(gold["gauge"]); o.set_params(float(gold["kappa"]), float(gold["gmu"]), gold["theta"]); o.set_nd_params(*gold["nd"])
+        rng = np.random.default_rng(4)
+        q, w = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        A = [o.spinor() for _ in range(4)]
+        o.invert_doublet_eo_cg(*A, s, c, q, w, 1e-20, 2000, 1)
+        dq, dw = d.field(q), d.field(w)
+        outs = [d.field() for _ in range(4)]
+        it = d.call("invert_doublet_eo_solver", *outs, ds, dc, dq, dw, 1e-20, 2000, 1, 14)
+        assert it > 0
+        for f, a in zip(outs, A):
+            assert rel_l2(d.download(f), a) <= 1e-8
     finally:
         d.close()
 

@@ -66,6 +66,8 @@ DEVICE_API = {
     "tmb_M_ee_inv_ndpsi": (_i, [_vp] * 4 + [_d, _d]), "tmb_Qtm_ndpsi": (_i, [_vp] * 4),
     "tmb_Qtm_dagger_ndpsi": (_i, [_vp] * 4), "tmb_Qtm_pm_ndpsi": (_i, [_vp] * 4),
     "tmb_cg_her_nd": (_i, [_vp] * 4 + [_i, _d, _i]), "tmb_invert_doublet_eo": (_i, [_vp] * 8 + [_d, _i, _i]),
+    "tmb_invert_doublet_eo_solver": (_i, [_vp] * 8 + [_d, _i, _i, _i]), "tmb_Qtm_pm_ndpsi_32": (_i, [_vp] * 4),
+    "tmb_rg_mixed_cg_her_nd": (_i, [_vp] * 4 + [_i, _d, _i]), "tmb_solver_stats_rg": (_i, [C.POINTER(_i)] * 3),
     "tmb_field32_alloc": (_vp, []), "tmb_field32_upload": (_i, [_vp, _vp]), "tmb_field32_download": (_i, [_vp, _vp]),
     "tmb_assign_to_32": (_i, [_vp, _vp]), "tmb_assign_to_64": (_i, [_vp, _vp]),
     "tmb_Hopping_Matrix_32": (_i, [_i, _vp, _vp]), "tmb_Qtm_pm_psi_32": (_i, [_vp, _vp]),
@@ -194,7 +196,7 @@ DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND"
                   "GaugeInfo", "gauge_precision_read_flag", "g_disable_IO_checks", "g_beta", "g_rgi_C1"]
 
 _SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed",
-            "rg_mixed_cg_her", "solve_degenerate"}
+            "rg_mixed_cg_her", "solve_degenerate", "invert_doublet_eo_solver", "rg_mixed_cg_her_nd"}
 _lib = None
 
 

@@ -75,7 +75,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 0, cg_selfnorm = 1;
+  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 2, cg_selfnorm = 1;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -89,14 +89,20 @@ struct Ctx {
   std::vector<std::pair<size_t, size_t>> arena_free; /* (offset, bytes) */
   char *up_base = nullptr, *dn_base = nullptr;
   unsigned int *flags = nullptr, *up_flags = nullptr, *dn_flags = nullptr, *p2p_ticket = nullptr;
-  int host_chunks = 8; int *p2p_err = nullptr; unsigned int hop_seq = 0; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
+  int host_chunks = 8; int *p2p_err = nullptr; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
+  /* sequence numbers of the peer-mode hops are *seq_dev + hop_off: the host counts offsets, the device base only moves
+   * at the end of a replayed CG graph (whose kernels carry fixed offsets); seq_dev[1] is the reduction counter of xred_sum */
+  unsigned int *seq_dev = nullptr; unsigned int hop_off = 0;
+  char *peer_base[TMB_XR_MAXR] = {nullptr};   /* every rank's arena ([rank] = own) when nranks <= TMB_XR_MAXR */
+  tmb_xred_table *xr_tab = nullptr; bool xred = false; /* cross-rank sums inside the reduction finish (no NCCL in the CG) */
   /* HMC side (tmb_capi_hmc.inc) */
   double2 phase[4] = {{1., 0.}, {1., 0.}, {1., 0.}, {1., 0.}}; /* exp(i theta_mu pi / L_mu): ka_mu / kappa */
   double *df = nullptr;                       /* hf->derivative on the device, [2][4][8][Vh] */
   double2 *dhalo_send = nullptr, *dhalo_recv = nullptr;
   Monomial mnl[TMB_MAXMNL]; int nmnl = 0;
   double2 *w[6] = {nullptr};                  /* w_fields (monomial.c:57) */
-  double2 *nd[7] = {nullptr};                 /* two-flavour CG vectors of tmb_cg_her_nd (0..4) and temporaries of tmb_invert_doublet_eo (5, 6), [2][12][Vh] each */
+  double2 *nd[8] = {nullptr};                 /* two-flavour CG vectors of tmb_cg_her_nd (0..4), temporaries of tmb_invert_doublet_eo (5, 6), xhigh of tmb_rg_mixed_cg_her_nd (7), [2][12][Vh] each */
+  float2 *nd32[4] = {nullptr};                /* float two-flavour vectors of tmb_rg_mixed_cg_her_nd's inner loops */
   int rel_prec_flag = 0;                      /* g_relative_precision_flag */
   double mcg_delta = 5.0e-5;                  /* solver_params.mcg_delta = _default_mixcg_innereps (monomial.c:106) */
 };
@@ -127,7 +133,9 @@ static inline const double2 *F(const void *p) { return (const double2 *)p; }
  * With more than one rank every spinor field comes out of ONE arena per rank, allocated in the same order
  * on all ranks (SPMD), so that "the same field on the neighbouring rank" is the neighbour's arena base plus
  * this rank's offset - what the peer-mode hopping kernel dereferences over NVLink. */
-#define ARENA_RESERVED 256 /* flags live at the start of the arena */
+#define ARENA_RESERVED 4096 /* start of the arena: hop flags at 0, landing arrays of the cross-rank sums at 1024 (values) and 2048 (sequence words) */
+#define ARENA_XR_VAL 1024
+#define ARENA_XR_SEQ 2048
 static inline bool in_arena(const void *p) {
   return C.arena && (const char *)p >= C.arena && (const char *)p < C.arena + C.arena_bytes;
 }
@@ -203,14 +211,14 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   CU(cudaMalloc(&C.st, sizeof(tmb_cg_state)));
   CU(cudaMemset(C.st, 0, sizeof(tmb_cg_state)));
   CU(cudaHostAlloc(&C.st_host, 2 * sizeof(tmb_cg_state), cudaHostAllocDefault));
-  const size_t hb = (size_t)6 * C.g.S * sizeof(double2);
+  const size_t hb = (size_t)2 * 6 * C.g.S * sizeof(double2); /* two faces: the two flavours of the doublet share an exchange */
   CU(cudaMalloc(&C.send_up, hb)); CU(cudaMalloc(&C.send_dn, hb));
   CU(cudaMalloc(&C.halo_up, hb)); CU(cudaMalloc(&C.halo_dn, hb));
   CU(cudaMalloc(&C.Uhalo, (size_t)18 * C.g.S * sizeof(double2)));
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 0; C.cg_selfnorm = 1;
+  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 2; C.cg_selfnorm = 1;
   C.init = true;
   return 0;
 }
@@ -218,7 +226,6 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
 extern "C" int tmb_finalize(void) {
   if (!C.init) return 0;
   cudaDeviceSynchronize();
-  if (C.comm && C.nccl.CommDestroy) { C.nccl.CommDestroy(C.comm); C.comm = nullptr; }
   for (void *p : C.fields) sym_free(p);
   C.fields.clear(); C.field_bytes.clear();
   for (int i = 0; i < NSCRATCH; i++) { sym_free(C.scratch[i]); C.scratch[i] = nullptr; }
@@ -228,9 +235,26 @@ extern "C" int tmb_finalize(void) {
   if (C.df) cudaFree(C.df); if (C.dhalo_send) cudaFree(C.dhalo_send); if (C.dhalo_recv) cudaFree(C.dhalo_recv);
   for (int k = 0; k < C.nmnl; k++) { sym_free(C.mnl[k].pf); for (int i = 0; i < TMB_MAXCSG; i++) sym_free(C.mnl[k].csg[i]); }
   for (int i = 0; i < 6; i++) sym_free(C.w[i]);
-  for (int i = 0; i < 7; i++) { sym_free(C.nd[i]); C.nd[i] = nullptr; }
-  if (C.up_base && C.up_base != C.arena) cudaIpcCloseMemHandle(C.up_base);
-  if (C.dn_base && C.dn_base != C.arena && C.dn_base != C.up_base) cudaIpcCloseMemHandle(C.dn_base);
+  for (int i = 0; i < 8; i++) { sym_free(C.nd[i]); C.nd[i] = nullptr; }
+  for (int i = 0; i < 4; i++) { sym_free(C.nd32[i]); C.nd32[i] = nullptr; }
+  {
+    bool closed_up = false, closed_dn = false;
+    for (int r = 0; r < TMB_XR_MAXR; r++)
+      if (C.peer_base[r] && C.peer_base[r] != C.arena) {
+        if (C.peer_base[r] == C.up_base) closed_up = true;
+        if (C.peer_base[r] == C.dn_base) closed_dn = true;
+        cudaIpcCloseMemHandle(C.peer_base[r]);
+      }
+    if (C.up_base && C.up_base != C.arena && !closed_up) cudaIpcCloseMemHandle(C.up_base);
+    if (C.dn_base && C.dn_base != C.arena && C.dn_base != C.up_base && !closed_dn) cudaIpcCloseMemHandle(C.dn_base);
+  }
+  /* nobody may free an arena a peer still has mapped: all ranks pass here after unmapping and before freeing */
+  if (C.comm && C.nranks > 1 && C.st) {
+    C.nccl.AllReduce(&C.st->tmp[0], &C.st->tmp[0], 1, NCCL_FLOAT64, NCCL_SUM, C.comm, C.s_main);
+    cudaStreamSynchronize(C.s_main);
+  }
+  if (C.comm && C.nccl.CommDestroy) { C.nccl.CommDestroy(C.comm); C.comm = nullptr; }
+  if (C.seq_dev) cudaFree(C.seq_dev); if (C.xr_tab) cudaFree(C.xr_tab);
   if (C.arena) cudaFree(C.arena); else if (C.flags) cudaFree(C.flags);
   if (C.p2p_ticket) cudaFree(C.p2p_ticket); if (C.p2p_err) cudaFree(C.p2p_err);
   if (C.gauge_raw) cudaFree(C.gauge_raw);
@@ -275,6 +299,23 @@ static int p2p_small_buffers() {
   if (C.p2p_copy_ctas < 1) C.p2p_copy_ctas = 1;
   if (C.p2p_copy_ctas > 2 * 148) C.p2p_copy_ctas = 2 * 148; /* each pull CTA owns a partial slot and delays the stencil CTAs behind it */
   if (!C.p2p_err) { CU(cudaMalloc(&C.p2p_err, sizeof(int))); CU(cudaMemset(C.p2p_err, 0, sizeof(int))); }
+  if (!C.seq_dev) CU(cudaMalloc(&C.seq_dev, 2 * sizeof(unsigned int)));
+  CU(cudaMemset(C.seq_dev, 0, 2 * sizeof(unsigned int)));
+  C.hop_off = 0;
+  return 0;
+}
+/* the table xred_sum() reads: every rank's landing arrays as seen from this rank */
+static int setup_xred(char *const *bases, int nranks, int rank) {
+  C.xred = false;
+  const char *env = getenv("TMB_XRED");
+  if ((env && atoi(env) == 0) || nranks > TMB_XR_MAXR) return 0;
+  tmb_xred_table h;
+  memset(&h, 0, sizeof(h));
+  h.nranks = nranks; h.rank = rank; h.ctr = C.seq_dev + 1; h.err = C.p2p_err;
+  for (int q = 0; q < nranks; q++) { h.val[q] = (double *)(bases[q] + ARENA_XR_VAL); h.seq[q] = (unsigned int *)(bases[q] + ARENA_XR_SEQ); }
+  if (!C.xr_tab) CU(cudaMalloc(&C.xr_tab, sizeof(h)));
+  CU(cudaMemcpy(C.xr_tab, &h, sizeof(h), cudaMemcpyHostToDevice));
+  C.xred = true;
   return 0;
 }
 static int setup_p2p() {
@@ -319,10 +360,16 @@ static int setup_p2p() {
   for (int r = 0; r < C.nranks; r++) ok = ok && msgs[r].ok;
   const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
   void *pu = nullptr, *pd = nullptr;
-  if (ok && cudaIpcOpenMemHandle(&pu, msgs[up].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
-  if (ok) {
-    if (dn == up) pd = pu;
-    else if (cudaIpcOpenMemHandle(&pd, msgs[dn].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  /* all ranks' arenas when the cross-rank sums can use them (<= TMB_XR_MAXR ranks), the two T-neighbours' otherwise */
+  const bool allp = C.nranks <= TMB_XR_MAXR;
+  for (int r = 0; r < C.nranks && ok; r++) {
+    if (r == C.rank) { if (allp) C.peer_base[r] = C.arena; continue; }
+    if (!allp && r != up && r != dn) continue;
+    void *pp = nullptr;
+    if (cudaIpcOpenMemHandle(&pp, msgs[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    if (allp) C.peer_base[r] = (char *)pp;
+    if (r == up) pu = pp;
+    if (r == dn) pd = pp;
   }
   /* everybody must agree, otherwise one rank would wait for flags nobody writes */
   int *dflag = nullptr; CU(cudaMalloc(&dflag, sizeof(double)));
@@ -336,7 +383,8 @@ static int setup_p2p() {
   C.up_base = (char *)pu; C.dn_base = (char *)pd;
   C.flags = (unsigned int *)C.arena; C.up_flags = (unsigned int *)C.up_base; C.dn_flags = (unsigned int *)C.dn_base;
   TRY(p2p_small_buffers());
-  C.hop_seq = 0; C.p2p = true;
+  C.p2p = true;
+  if (allp) TRY(setup_xred(C.peer_base, C.nranks, C.rank));
   return 0;
 }
 extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) {
@@ -361,16 +409,22 @@ extern "C" int tmb_comm_loopback(int on) {
   if (C.nranks > 1) return fail(-6, "tmb_comm_loopback: only for a single rank");
   C.loopback = on != 0; C.loopback_mode = on; C.dist = C.loopback; C.g.dist_t = C.dist ? 1 : 0;
   C.gauge_loaded = false; /* Uhalo must be rebuilt */
-  C.p2p = false;
+  C.p2p = false; C.xred = false;
   if (on == 2) {
     if (!C.flags) { CU(cudaMalloc(&C.flags, ARENA_RESERVED)); }
     CU(cudaMemset(C.flags, 0, ARENA_RESERVED));
     C.up_flags = C.dn_flags = C.flags;
     TRY(p2p_small_buffers());
-    C.hop_seq = 0; C.p2p = true;
+    C.p2p = true;
+    char *self[1] = {(char *)C.flags}; /* the sums run through the landing arrays too, over one rank */
+    TRY(setup_xred(self, 1, 0));
   }
   return 0;
 }
+/* reductions finish inside the producing kernel (no separate launch, no NCCL) on one rank and, over several ranks, when the
+ * cross-rank sum can go through peer memory */
+static inline bool fuse_fin() { return C.nranks == 1 || C.xred; }
+static inline const tmb_xred_table *xr_tab() { return C.xred ? C.xr_tab : nullptr; }
 static int allreduce_slot(int slot) {
   if (C.nranks > 1) NC(C.nccl.AllReduce(&C.st->tmp[slot], &C.st->tmp[slot], 1, NCCL_FLOAT64, NCCL_SUM, C.comm, C.s_main));
   return 0;
@@ -405,7 +459,7 @@ extern "C" int tmb_set_mu(double g_mu) { NEED_INIT(); C.mu = g_mu; return 0; }
 extern "C" int tmb_set_nd(double mubar, double epsbar, double invmaxev) {
   NEED_INIT(); C.mubar = mubar; C.epsbar = epsbar; C.invmaxev = invmaxev; return 0;
 }
-extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < 0 || v > 1) return fail(-7, "hop2 variant must be 0 or 1"); C.hop2_variant = v; return 0; }
+extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < 0 || v > 2) return fail(-7, "hop2 variant must be 0, 1 or 2"); C.hop2_variant = v; return 0; }
 extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   NEED_INIT();
   if (hop_variant < -1 || hop_variant > 10) return fail(-7, "hop_variant must be -1 (automatic) .. 10");
@@ -604,6 +658,9 @@ struct HopOpt {
   int prec = 0;               /* 0: double fields, 1: float fields + float gauge copy */
   int fin_op = -1, fin_slot = 0; /* fused finish of the dot reduction (single rank) */
   bool nocom = false;         /* Hopping_Matrix_nocom: no halo exchange, the slab wraps onto itself in T */
+  /* two flavours in one launch (hop_kernel NFL = 2): second flavour's fields, flavour mixing of the epilogue */
+  int nfl = 1; const void *in1 = nullptr; void *out1 = nullptr; const void *p1 = nullptr;
+  double nd_mu = 0., nd_eps = 0., nd_scale = 1., dot_scale = 1.;
 };
 static int ensure_gauge32();
 static int ensure_gauge12(int prec);
@@ -632,6 +689,8 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   a.prec = o.prec;
   a.recon12 = C.compression == 12;
   a.in = in; a.out = out; a.p = o.p; a.dotw = o.dotw;
+  a.nfl = o.nfl; a.in1 = o.in1; a.out1 = o.out1; a.p1 = o.p1;
+  a.nd_mu = o.nd_mu; a.nd_eps = o.nd_eps; a.nd_scale = o.nd_scale; a.dot_scale = o.dot_scale;
   a.halo_up = C.halo_up; a.halo_dn = C.halo_dn;
   if (a.recon12) {
     TRY(ensure_gauge12(o.prec));
@@ -646,7 +705,8 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.selfnorm ? 2 : (o.dotw ? 1 : 0); a.hints = eff_hints();
   a.pdl = C.pdl; a.prefetch = C.prefetch;
-  a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && C.nranks == 1) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
+  a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && fuse_fin()) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
+  a.xr = a.fin_op >= 0 ? xr_tab() : nullptr;
   int np = 0;
   if (!C.dist || o.nocom) {
     a.dist = 0; a.site0 = o.site0; a.nsites = o.nsites < 0 ? C.g.Vh : o.nsites; a.split = a.nsites; a.gap = 0;
@@ -654,20 +714,27 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     a.variant = (o.mode == 0 && !a.dot && !a.recon12 && !o.prec) ? C.hop_variant : 0;
     if (C.hop_variant == 10 || C.hop_variant == -1) /* 448-thread residency: every epilogue of the plain double kernel */
       a.variant = (!a.recon12 && !o.prec && (C.hop_variant == 10 || hop_residency_448(a.nsites))) ? 10 : 0;
+    if (o.nfl == 2) a.variant = 0;
     a.xblock = o.nsites < 0 ? C.xblock : 0;
     np = tmb_hop_grid(a);
     if (np > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", np, C.npartial);
     a.fin_total = np;
     KL(tmb_launch_hop(a, C.s_main));
-  } else if (C.p2p && o.nsites < 0 && (C.nranks == 1 || in_arena(in))) {
+  } else if (C.p2p && o.nsites < 0 && (C.nranks == 1 || (in_arena(in) && (o.nfl == 1 || in_arena(o.in1))))) {
     /* peer mode: one launch; boundary slices read the neighbours' copies of `in` over NVLink */
     const size_t off = C.nranks == 1 ? 0 : (size_t)((const char *)in - C.arena);
+    if (o.nfl == 2) {
+      const size_t off1 = C.nranks == 1 ? 0 : (size_t)((const char *)o.in1 - C.arena);
+      const bool loc = C.nranks == 1 || (C.p2p_diag & 1);
+      a.in_up1 = loc ? o.in1 : (const void *)(C.up_base + off1);
+      a.in_dn1 = loc ? o.in1 : (const void *)(C.dn_base + off1);
+    }
     a.dist = 2; a.site0 = 0; a.nsites = C.g.Vh; a.split = a.nsites; a.gap = 0; a.variant = 0; a.xblock = 0;
     const bool local = C.nranks == 1 || (C.p2p_diag & 1);
     a.in_up = local ? in : (const void *)(C.up_base + off);
     a.in_dn = local ? in : (const void *)(C.dn_base + off);
     a.p2p_nohandshake = (C.p2p_diag & 2) ? 1 : 0; a.p2p_diag = C.p2p_diag;
-    a.seq = ++C.hop_seq; a.flags = C.flags; a.up_flags = C.up_flags; a.dn_flags = C.dn_flags;
+    a.seq_base = C.seq_dev; a.seq_off = ++C.hop_off; a.flags = C.flags; a.up_flags = C.up_flags; a.dn_flags = C.dn_flags;
     a.p2p_err = C.p2p_err; a.p2p_copied = C.p2p_ticket;
     a.halo_up_w = C.halo_up; a.halo_dn_w = C.halo_dn;
     a.p2p_copy_ctas = C.p2p_copy_ctas;
@@ -682,8 +749,11 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     const int S = C.g.S, Vh = C.g.Vh;
     CU(cudaEventRecord(C.ev_in, C.s_main));
     CU(cudaStreamWaitEvent(C.s_comm, C.ev_in, 0));
+    const size_t face = (size_t)6 * S * (o.prec ? sizeof(float2) : sizeof(double2));
     KL(tmb_launch_pack_halo(o.prec, C.send_up, C.send_dn, in, C.g, C.s_comm));
-    TRY(exchange_faces(C.send_up, C.send_dn, C.halo_up, C.halo_dn, (size_t)6 * S * (o.prec ? sizeof(float2) : sizeof(double2)), C.s_comm));
+    if (o.nfl == 2) /* the second flavour's faces behind the first's: one exchange for both */
+      KL(tmb_launch_pack_halo(o.prec, (char *)C.send_up + face, (char *)C.send_dn + face, o.in1, C.g, C.s_comm));
+    TRY(exchange_faces(C.send_up, C.send_dn, C.halo_up, C.halo_dn, o.nfl * face, C.s_comm));
     a.variant = 0; a.xblock = 0;
     /* the interior grid size fixes where the boundary launch puts its fused-dot partials */
     int nb_int = 0;
@@ -887,8 +957,8 @@ extern "C" int tmb_gamma5(void *l, const void *k) { NEED_INIT(); KL(tmb_launch_g
 
 /* ------------------------------------------------------------------ BLAS-1 */
 static int finish_reduction(int npart, double *result) {
-  KL(tmb_launch_final(C.partial, npart, C.st, 0, TMB_FIN_STORE, 0, C.s_main));
-  TRY(allreduce_slot(0));
+  KL(tmb_launch_final(C.partial, npart, C.st, 0, TMB_FIN_STORE, 0, xr_tab(), C.s_main));
+  if (!C.xred) TRY(allreduce_slot(0));
   CU(cudaMemcpyAsync(result, &C.st->tmp[0], sizeof(double), cudaMemcpyDeviceToHost, C.s_main));
   CU(cudaStreamSynchronize(C.s_main));
   return 0;
@@ -921,12 +991,12 @@ extern "C" int tmb_mul_r(void *r, double c, const void *s) { NEED_INIT(); KL(tmb
  * enqueues iterations in chunks without a synchronisation per iteration. */
 #define CG_CHUNK 8
 static int reduce_to(int npart, int slot, int op) {
-  if (C.nranks > 1) {
-    KL(tmb_launch_final(C.partial, npart, C.st, slot, op, 0, C.s_main));
+  if (!fuse_fin()) { /* NCCL fallback: partial sum, all-reduce of one double, bookkeeping */
+    KL(tmb_launch_final(C.partial, npart, C.st, slot, op, 0, nullptr, C.s_main));
     TRY(allreduce_slot(slot));
     KL(tmb_launch_apply(C.st, slot, op, C.s_main));
   } else {
-    KL(tmb_launch_final(C.partial, npart, C.st, slot, op, 1, C.s_main));
+    KL(tmb_launch_final(C.partial, npart, C.st, slot, op, 1, xr_tab(), C.s_main));
   }
   return 0;
 }
@@ -1007,12 +1077,29 @@ extern "C" int tmb_M_oo_sub_g5_ndpsi(void *ls, void *lc, const void *ks, const v
 }
 static int hop0(int ieo, double2 *l, const double2 *k) { HopOpt o; return hop(ieo, l, k, o); }
 
-/* Two-flavour fused path (single rank, 18-real links): every Hopping_Matrix pair of tm_operators_nd.c is ONE
+static int hop2_legacy(int ieo, double2 *o0, double2 *o1, const double2 *i0, const double2 *i1, int mode, const double2 *p0,
+                       const double2 *p1, double mu, double eps, double scale);
+/* Two-flavour fused path: every Hopping_Matrix pair of tm_operators_nd.c is ONE
  * launch that streams the links once for both flavours, with M_ee_inv_ndpsi / M_oo_sub_g5_ndpsi and the
  * phmc_invmaxev scaling in its epilogue.  mode 1: out = M_ee_inv_nd(H in0, H in1); mode 2: out = scale g5(M_oo(p) - H in). */
-static bool nd_fused() { return !C.dist && C.compression == 18; }
-static int hop2(int ieo, double2 *o0, double2 *o1, const double2 *i0, const double2 *i1, int mode, const double2 *p0,
-                const double2 *p1, double mu, double eps, double scale) {
+static bool nd_fused() { return C.hop2_variant == 2 || (!C.dist && C.compression == 18); }
+struct NdDot { const tmb_cg_state *st = nullptr; int fin_op = -1, fin_slot = 0; double scale = 1.; int *np = nullptr; bool on = false; };
+static int hop2(int ieo, void *o0, void *o1, const void *i0, const void *i1, int mode, const void *p0,
+                const void *p1, double mu, double eps, double scale, int prec = 0, const tmb_cg_state *st = nullptr,
+                const NdDot *dot = nullptr) {
+  if (C.hop2_variant == 2 || prec) { /* hop_kernel with NFL = 2: every precision, compression and communication mode */
+    HopOpt o; o.nfl = 2; o.mode = mode; o.prec = prec; o.in1 = i1; o.out1 = o1; o.p = p0; o.p1 = p1; o.st = st;
+    o.nd_mu = mu; o.nd_eps = eps; o.nd_scale = scale;
+    if (dot && dot->on) { o.selfnorm = true; o.fin_op = dot->fin_op; o.fin_slot = dot->fin_slot; o.dot_scale = dot->scale; o.npartial = dot->np; }
+    return hop(ieo, o0, i0, o);
+  }
+  if (dot && dot->on) return fail(-7, "the fused two-flavour norm needs tmb_set_hop2_variant(2)");
+  return hop2_legacy(ieo, F(o0), F(o1), F(i0), F(i1), mode, F(p0), F(p1), mu, eps, scale);
+}
+/* the round-1 kernels (tmb_force.cu: one thread carries both flavours, variant 0; lane-paired flavours, variant 1): one
+ * rank, 18-real links, double precision only */
+static int hop2_legacy(int ieo, double2 *o0, double2 *o1, const double2 *i0, const double2 *i1, int mode, const double2 *p0,
+                       const double2 *p1, double mu, double eps, double scale) {
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
   if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
   tmb_hop2_launch a;
@@ -1058,16 +1145,25 @@ extern "C" int tmb_Qtm_dagger_ndpsi(void *ls_, void *lc_, const void *ks_, const
   KL(tmb_launch_scale(ls, C.invmaxev, ls, N2(), C.s_main));
   return 0;
 }
-/* tm_operators_nd.c:195-238 */
+/* tm_operators_nd.c:195-238 (prec 0) and tm_operators_nd_32.c:215-262 (prec 1, float fields) as 4 two-flavour launches,
+ * 8448 B/site in double instead of 8 hops + 5 sweeps, 17.7 kB/site.  Qtm_pm_ndpsi = Qhat Qhat^dagger: its first half B =
+ * Qhat^dagger k is the output of the second launch, so the CG's <k, Qhat Qhat^dagger k> = invmaxev^2 |B|^2 is the squared norm
+ * of that launch's own output (`dot`: fused reduction and finish, no operand load, no separate dot kernel). */
+static float2 *scratch32(int k);
+static int qtm_pm_nd_x(int prec, void *ls, void *lc, const void *ks, const void *kc, const tmb_cg_state *st, NdDot *dot) {
+  void *a0, *a1, *b0, *b1;
+  if (prec) { a0 = scratch32(6); a1 = scratch32(7); b0 = scratch32(8); b1 = scratch32(9); }
+  else { a0 = scratch(6); a1 = scratch(7); b0 = scratch(8); b1 = scratch(9); }
+  if (!a0 || !a1 || !b0 || !b1) return -100;
+  if (dot) dot->scale = C.invmaxev * C.invmaxev;
+  TRY(hop2(0, a0, a1, kc, ks, 1, nullptr, nullptr, C.mubar, C.epsbar, 1., prec, st));            /* A = Mee^-1 H_eo (kc, ks) */
+  TRY(hop2(1, b0, b1, a0, a1, 2, kc, ks, -C.mubar, -C.epsbar, 1., prec, st, dot));              /* B = g5(Moo(kc,ks) - H_oe A): tau1 Qhat tau1 */
+  TRY(hop2(0, a0, a1, b0, b1, 1, nullptr, nullptr, -C.mubar, C.epsbar, 1., prec, st));          /* A = (s5, s4) */
+  return hop2(1, ls, lc, a1, a0, 2, b1, b0, -C.mubar, -C.epsbar, C.invmaxev * C.invmaxev, prec, st);
+}
 static int qtm_pm_nd(double2 *ls, double2 *lc, const double2 *ks, const double2 *kc) {
   SCR(s0, 6); SCR(s1, 7); SCR(s2, 8); SCR(s3, 9); SCR(s4, 10); SCR(s5, 11);
-  if (nd_fused()) { /* 4 launches, 8448 B/site instead of 8 hops + 5 sweeps, 17.7 kB/site */
-    double2 *a0 = s0, *a1 = s1, *b0 = s2, *b1 = s3;
-    TRY(hop2(0, a0, a1, kc, ks, 1, nullptr, nullptr, C.mubar, C.epsbar, 1.));            /* A = Mee^-1 H_eo (kc, ks) */
-    TRY(hop2(1, b0, b1, a0, a1, 2, kc, ks, -C.mubar, -C.epsbar, 1.));                   /* B = g5(Moo(kc,ks) - H_oe A): tau1 Qhat tau1 */
-    TRY(hop2(0, a0, a1, b0, b1, 1, nullptr, nullptr, -C.mubar, C.epsbar, 1.));          /* A = (s5, s4) */
-    return hop2(1, ls, lc, a1, a0, 2, b1, b0, -C.mubar, -C.epsbar, C.invmaxev * C.invmaxev);
-  }
+  if (nd_fused()) return qtm_pm_nd_x(0, ls, lc, ks, kc, nullptr, nullptr);
   TRY(hop0(0, s0, kc)); TRY(hop0(0, s1, ks));
   KL(tmb_launch_nd_mee_inv(s2, s3, s0, s1, C.mubar, C.epsbar, N2(), HALF(), C.s_main));
   TRY(hop0(1, s0, s2)); TRY(hop0(1, s1, s3));
@@ -1090,10 +1186,17 @@ extern "C" int tmb_Qtm_pm_ndpsi(void *ls, void *lc, const void *ks, const void *
 /* tmb_cg_her_nd (solver/cg_her_nd.c:57-170): device-resident, see tmb_capi_mixed.inc */
 extern "C" int tmb_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq, int rel_prec);
 
-/* invert_doublet_eo.c:102-178 (NO_EXT_INV, CG) */
+/* invert_doublet_eo.c:102-178 (NO_EXT_INV): solver_flag RGMIXEDCG (14) -> rg_mixed_cg_her_nd (:145-149), anything else -> cg_her_nd */
 static int nd_pair(int k, double2 **p);
+extern "C" int tmb_rg_mixed_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int max_iter, double eps_sq, int rel_prec);
+extern "C" int tmb_invert_doublet_eo_solver(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
+                                            const void *ec, const void *oc, double precision, int max_iter, int rel_prec, int solver_flag);
 extern "C" int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
                                      const void *ec, const void *oc, double precision, int max_iter, int rel_prec) {
+  return tmb_invert_doublet_eo_solver(ens, ons, enc, onc, es, os, ec, oc, precision, max_iter, rel_prec, TMB_SOLVER_CG);
+}
+extern "C" int tmb_invert_doublet_eo_solver(void *ens, void *ons, void *enc, void *onc, const void *es, const void *os,
+                                            const void *ec, const void *oc, double precision, int max_iter, int rel_prec, int solver_flag) {
   NEED_INIT();
   const size_t n2 = N2();
   /* temporaries live in the context: allocating and freeing four fields per call cost more than the rest of the
@@ -1110,7 +1213,8 @@ extern "C" int tmb_invert_doublet_eo(void *ens, void *ons, void *enc, void *onc,
     if ((rc = tmb_assign_mul_add_r(d[1], 1., oc)) < 0) break;
     if ((rc = tmb_gamma5(d[0], d[0])) < 0) break;
     if ((rc = tmb_gamma5(d[1], d[1])) < 0) break;
-    iter = tmb_cg_her_nd(ons, onc, d[0], d[1], max_iter, precision, rel_prec);
+    if (solver_flag == TMB_SOLVER_RGMIXEDCG) iter = tmb_rg_mixed_cg_her_nd(ons, onc, d[0], d[1], max_iter, precision, rel_prec);
+    else iter = tmb_cg_her_nd(ons, onc, d[0], d[1], max_iter, precision, rel_prec);
     if (iter < -1) { rc = iter; break; }
     if ((rc = tmb_Qtm_dagger_ndpsi(ons, onc, ons, onc)) < 0) break;
     if ((rc = hop0(0, d[0], F(ons))) < 0) break;

@@ -488,15 +488,14 @@ int invert_doublet_eo(spinor *const Even_new_s, spinor *const Odd_new_s, spinor 
                       const double precision, const int max_iter, const int solver_flag, const int rel_prec,
                       solver_params_t solver_params, const ExternalInverter external_inverter,
                       const SloppyPrecision sloppy, const CompressionType compression) {
-  (void)solver_params; (void)external_inverter; (void)sloppy; (void)compression;
-  /* invert_doublet_eo.c:143-156 knows CG and RGMIXEDCG; both are served by the double-precision CG on the two-flavour
-   * kernels here (same solution to the requested precision; the count returned is the CG's) */
-  if (solver_flag != TMB_SOLVER_CG && g_proc_id == 0 && g_debug_level > 0)
-    printf("# invert_doublet_eo (B200): solver_flag %d is served by the double-precision CG\n", solver_flag);
+  (void)external_inverter; (void)sloppy; (void)compression;
+  /* invert_doublet_eo.c:143-156: RGMIXEDCG -> rg_mixed_cg_her_nd (float inner loops on Qtm_pm_ndpsi_32, delta =
+   * solver_params.mcg_delta), every other flag -> cg_her_nd */
   sync_globals();
+  if (solver_flag == TMB_SOLVER_RGMIXEDCG) CHK(tmb_set_mcg_delta((double)solver_params.mcg_delta));
   up(4, Even_s); up(5, Odd_s); up(6, Even_c); up(7, Odd_c);
   up(1, Odd_new_s); up(3, Odd_new_c); /* initial guess of cg_her_nd */
-  int iter = tmb_invert_doublet_eo(dev(0), dev(1), dev(2), dev(3), dev(4), dev(5), dev(6), dev(7), precision, max_iter, rel_prec);
+  int iter = tmb_invert_doublet_eo_solver(dev(0), dev(1), dev(2), dev(3), dev(4), dev(5), dev(6), dev(7), precision, max_iter, rel_prec, solver_flag);
   if (iter < -1) die(__func__);
   down(Even_new_s, 0); down(Odd_new_s, 1); down(Even_new_c, 2); down(Odd_new_c, 3);
   return iter;

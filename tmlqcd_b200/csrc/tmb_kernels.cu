@@ -14,345 +14,11 @@
 #include "tmb_kernels.h"
 #include "tmb_site.cuh"
 
-#define TMB_SMS 148
+#include "tmb_hop.cuh"
 
-/* ------------------------------------------------------------------ block reduction */
-template <int BLOCK>
-__device__ __forceinline__ double block_sum(double v) {
-  __shared__ double sh[32];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) sh[wid] = v;
-  __syncthreads();
-  v = 0.;
-  if (wid == 0) {
-    v = (lane < BLOCK / 32) ? sh[lane] : 0.;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  }
-  return v; /* valid in thread 0 */
-}
-
-__device__ void cg_apply(tmb_cg_state *st, int slot, int op) {
-  const double sum = st->tmp[slot];
-  if (op == TMB_FIN_CG_PRO) {
-    st->pro = sum;
-    st->alpha = st->fprec ? (double)((float)st->normsq / (float)sum) : st->normsq / sum;
-  } else if (op == TMB_FIN_CG_ERR) {
-    st->err = sum;
-    st->iter += 1;
-    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
-    if (sum <= thr) {
-      st->converged = 1;
-    } else {
-      st->beta = sum / st->normsq;
-      st->normsq = sum;
-    }
-  } else if (op == TMB_FIN_CG_INIT) {
-    st->normsq = sum;
-  } else if (op == TMB_FIN_MCG_ERR) {
-    /* solver/mixed_cg_her.c:139-150: j counts the iterations that did NOT break */
-    st->err = sum;
-    const double thr = st->rel_prec ? st->eps_sq * st->sqnorm_q : st->eps_sq;
-    if (sum <= st->inner_eps * st->sqnrm0 || st->iter == st->max_iter || 1.3 * sum <= thr) {
-      st->converged = 1;
-    } else {
-      st->beta = sum / st->normsq;
-      st->normsq = sum;
-      st->iter += 1;
-    }
-  } else if (op == TMB_FIN_RG_ERR) {
-    /* rg_mixed_cg_her.c:118-145 (float) / :75-104 (double): ++j; ...; rho = |r|^2; beta = rho / *rho1; *rho1 = rho;
-     * if (1.3 rho < eps_sq) break; if (rho > rhomax) rhomax = rho; while (rho > delta*rhomax && j+iter <= max_iter) */
-    const double rho = st->fprec ? (double)(float)sum : sum;
-    st->err = rho;
-    st->iter += 1;
-    st->beta = st->fprec ? (double)((float)rho / (float)st->normsq) : rho / st->normsq;
-    st->normsq = rho;
-    const double eps = st->fprec ? (double)(float)st->eps_sq : st->eps_sq;
-    if (1.3 * rho < eps) {
-      st->converged = 1;
-    } else {
-      if (rho > st->sqnrm0) st->sqnrm0 = rho;
-      const double lim = st->fprec ? (double)((float)st->inner_eps * (float)st->sqnrm0) : st->inner_eps * st->sqnrm0;
-      if (!(rho > lim && st->iter <= st->max_iter)) st->converged = 1;
-    }
-  }
-}
-
-/* Fused finish of a two-stage reduction: the CTA that takes the last ticket sums all block partials
- * in index order (same order whichever CTA is last -> deterministic) and does the CG bookkeeping,
- * which saves the separate one-CTA launch per reduction.  Used when no all-reduce sits in between. */
-template <int BLOCK>
-__device__ __forceinline__ void finish_last_block(const double *partial, int total, tmb_cg_state *st, int slot, int op) {
-  __shared__ int is_last;
-  if (threadIdx.x == 0) {
-    __threadfence(); /* this CTA's partial is visible before the ticket is taken */
-    const unsigned t = atomicAdd(&st->ticket[slot], 1u);
-    is_last = (t == (unsigned)(total - 1));
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    double acc = 0.;
-    for (int k = threadIdx.x; k < total; k += BLOCK) acc += __ldcg(partial + k);
-    const double s = block_sum<BLOCK>(acc);
-    if (threadIdx.x == 0) {
-      st->tmp[slot] = s;
-      cg_apply(st, slot, op);
-      st->ticket[slot] = 0;
-    }
-  }
-}
-
-/* ------------------------------------------------------------------ cross-GPU flags (peer mode) */
-__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-/* spin until *p has reached seq (wrap-safe); gives up after ~4 s and raises *err instead of hanging the GPU */
-__device__ __forceinline__ void wait_flag(const unsigned int *p, unsigned int seq, int *err) {
-  const long long t0 = clock64();
-  while ((int)(ld_acquire_sys(p) - seq) < 0) {
-    if (clock64() - t0 > 8000000000LL) { *err = 1; break; }
-    __nanosleep(100);
-  }
-}
-
-/* ------------------------------------------------------------------ K1: hopping */
-template <class V2, int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a) {
-  /* Programmatic dependent launch: let the next kernel of the stream start filling SMs while this
-   * grid drains, and do everything that does not depend on the previous kernel before the wait -
-   * optionally an L2 bulk prefetch of this CTA's gauge rows.  Both instructions are no-ops when
-   * the launch carries no PDL attribute.  (Measured: neither helps this kernel, see DESIGN.md.) */
-  asm volatile("griddepcontrol.launch_dependents;");
-  const int NE = (HINTS & 2) ? 6 : 9; /* stored complex numbers per link (12-real compression: 6) */
-  if ((a.prefetch & 1) && threadIdx.x < 8 * NE) {
-    const int first = blockIdx.x * BLOCK;
-    int n = a.nsites - first; n = n > BLOCK ? BLOCK : n;
-    if (n > 0) {
-      const int i0 = a.site0 + first + (first >= a.split ? a.gap : 0);
-      const int d = threadIdx.x / NE, e = threadIdx.x - NE * d, mu = d >> 1, bwd = d & 1;
-      int j0 = i0;
-      if (bwd) {
-        const int shift = mu == 0 ? a.g.S : (mu == 1 ? a.g.LY * a.g.Lzh : (mu == 2 ? a.g.Lzh : 0));
-        j0 = i0 - shift; if (j0 < 0) j0 += a.g.Vh;
-      }
-      if (j0 > a.g.Vh - n) j0 = a.g.Vh - n;
-      const V2 *src = (const V2 *)a.U + (size_t)(((bwd ? 1 - a.par : a.par) * 4 + mu) * NE + e) * a.g.Vh + j0;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((int)(n * sizeof(V2))));
-    }
-  }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (a.st != nullptr && a.st->converged) return; /* CG already stopped: uniform early exit (same on every rank) */
-  int w = blockIdx.x * BLOCK + threadIdx.x;
-  bool worker = true, bcta = false;
-  if (DIST == 2) {
-    /* Peer mode: ONE launch does the whole hop and its halo exchange.
-     * (1) Block 0 tells both neighbours that this rank's input field is complete (everything before this
-     *     kernel in the stream has finished).
-     * (2) The first p2p_copy_ctas CTAs wait for the neighbours' ready flags and PULL the two boundary
-     *     time-slices of the neighbours' fields over NVLink, projecting them to half-spinors on the way
-     *     (192 B read remotely, 96 B written locally per site), with 12 loads in flight per thread.
-     * (3) Block 0 then acts as the closer: when all pulls have landed it publishes halo_ready = seq for the
-     *     boundary CTAs, tells the neighbours that this rank no longer reads their memory (only the pull CTAs
-     *     ever do) and waits for the same from them.  The kernel cannot complete before that, so whatever
-     *     follows in the stream may overwrite the input field.  No election, no per-CTA atomics.
-     * (4) All other CTAs do the stencil in the ROTATED slice order T/2, .., T-1, 0, .., T/2-1: consecutive slices
-     *     stay adjacent in time (the +-t neighbour slices are L2 hits, exactly one pair is cut), the two
-     *     boundary slices T-1 and 0 sit in the middle of the launch - half a hop after the pull started, and
-     *     not in the tail - and only their CTAs wait for halo_ready. */
-    const int Gc = a.p2p_copy_ctas;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      __threadfence_system();
-      st_release_sys(a.up_flags + 1, a.seq);
-      st_release_sys(a.dn_flags + 0, a.seq);
-    }
-    if ((int)blockIdx.x < Gc) {
-      worker = false;
-      if (threadIdx.x == 0) { wait_flag(a.flags + 0, a.seq, a.p2p_err); wait_flag(a.flags + 1, a.seq, a.p2p_err); }
-      __syncthreads();
-      const size_t n = (size_t)12 * a.g.S, stride = (size_t)Gc * BLOCK;
-      const size_t half = (size_t)6 * a.g.S;
-      const V2 *iu = (const V2 *)a.in_up, *id = (const V2 *)a.in_dn;
-      V2 *hu = (V2 *)a.halo_up_w, *hd = (V2 *)a.halo_dn_w;
-      const unsigned long long keep = tmb_policy_evict_last();
-      for (size_t k0 = (size_t)blockIdx.x * BLOCK + threadIdx.x; k0 < n && !(a.p2p_diag & 4); k0 += 6 * stride) {
-        V2 x[6], y[6]; /* 12 remote loads in flight before the first store */
-#pragma unroll
-        for (int u = 0; u < 6; u++) {
-          const size_t k = k0 + u * stride;
-          if (k < n) {
-            const bool up = k < half; const size_t kk = up ? k : k - half;
-            const int c = (int)(kk / a.g.S), j = (int)(kk - (size_t)c * a.g.S);
-            const V2 *src = up ? iu : id; const size_t site = up ? (size_t)j : (size_t)(a.g.T - 1) * a.g.S + j;
-            x[u] = src[(size_t)c * a.g.Vh + site]; y[u] = src[(size_t)(c + 6) * a.g.Vh + site];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 6; u++) { /* halo buffers: keep them in L2 until the boundary CTAs come */
-          const size_t k = k0 + u * stride;
-          if (k < n) { if (k < half) tmb_st_keep(hu + k, c_add(x[u], y[u]), keep); else tmb_st_keep(hd + (k - half), c_sub(x[u], y[u]), keep); }
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(a.p2p_copied, 1u);
-        if (blockIdx.x == 0) { /* the closer */
-          const long long t0 = clock64();
-          while (*(volatile unsigned int *)a.p2p_copied < (unsigned int)Gc) {
-            if (clock64() - t0 > 8000000000LL) { *a.p2p_err = 1; break; }
-            __nanosleep(200);
-          }
-          *a.p2p_copied = 0;
-          __threadfence();
-          *(volatile unsigned int *)(a.p2p_copied + 1) = a.seq; /* halo_ready */
-          __threadfence_system();
-          st_release_sys(a.up_flags + 3, a.seq);
-          st_release_sys(a.dn_flags + 2, a.seq);
-          if (!a.p2p_nohandshake) { wait_flag(a.flags + 2, a.seq, a.p2p_err); wait_flag(a.flags + 3, a.seq, a.p2p_err); }
-        }
-      }
-    } else {
-      const int wb = (int)blockIdx.x - Gc;
-      w = wb * BLOCK + threadIdx.x;
-      const int S = a.g.S, Vh = a.g.Vh;
-      const int s0 = (a.g.T + 1) / 2;                               /* first slice of the rotated order */
-      const int b0 = (a.g.T - 1 - s0) * S, b1 = b0 + 2 * S;        /* work range of slices T-1 and 0 */
-      (void)Vh;
-      if (wb * BLOCK + BLOCK > b0 && wb * BLOCK < b1) { /* block-uniform: this CTA touches slice T-1 or slice 0 */
-        bcta = !(a.p2p_diag & 8);
-        if (threadIdx.x == 0) {
-          const long long t0 = clock64();
-          while ((int)(*(volatile unsigned int *)(a.p2p_copied + 1) - a.seq) < 0) {
-            if (clock64() - t0 > 8000000000LL) { *a.p2p_err = 1; break; }
-            __nanosleep(100);
-          }
-          __threadfence();
-        }
-        __syncthreads();
-      }
-    }
-  }
-  double dsum = 0.;
-  if (worker && w < a.nsites) {
-    int ww = w;
-    if (DIST == 2 && !(a.p2p_diag & 16)) { /* rotated slice order s0, .., T-1, 0, .., s0-1 */
-      ww = w + ((a.g.T + 1) / 2) * a.g.S;
-      if (ww >= a.g.Vh) ww -= a.g.Vh;
-    }
-    if (a.xblock > 0) { /* x-blocked traversal of the (t,x) planes, memory layout unchanged */
-      const int P = a.g.LY * a.g.Lzh, XB = a.xblock;
-      const int plane = ww / P, off = ww - plane * P;
-      const int per = a.g.T * XB;
-      const int xb = plane / per, rem = plane - xb * per;
-      const int t = rem / XB, xi = rem - t * XB;
-      ww = (t * a.g.LX + xb * XB + xi) * P + off;
-    }
-    const int i = a.site0 + ww + (ww >= a.split ? a.gap : 0);
-    tmb_policies pol;
-    pol.stream = tmb_policy_evict_first();
-    pol.reuse = tmb_policy_evict_last();
-    tmb_hop_fields<V2> f;
-    f.in = (const V2 *)a.in; f.U = (const V2 *)a.U;
-    f.halo_up = (const V2 *)a.halo_up; f.halo_dn = (const V2 *)a.halo_dn; f.Uhalo = (const V2 *)a.Uhalo;
-    V2 ka[4];
-#pragma unroll
-    for (int m = 0; m < 4; m++) ka[m] = cvt2<V2>(a.ka[m]);
-    const V2 cf = cvt2<V2>(a.cf);
-    /* optional (tmb_set_overlap bit 3): ask L2 for the epilogue operands of this site now, so that the batch of
-     * loads after the 8 directions finds them there instead of paying a DRAM round trip with all registers live */
-    if ((MODE >= 2 || DOT) && (a.prefetch & 2) && (threadIdx.x & 7) == 0) {
-#pragma unroll
-      for (int c = 0; c < 12; c++) {
-        if (MODE >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.p + (size_t)c * a.g.Vh + i));
-        if (DOT == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"((const V2 *)a.dotw + (size_t)c * a.g.Vh + i));
-      }
-    }
-    V2 r[12];
-    /* peer mode: interior CTAs run the branch-free site code (all 8 directions' loads can be batched), only
-     * the CTAs of the two boundary slices take the variant with the per-site halo branches */
-    if (DIST == 1 || (DIST == 2 && bcta)) tmb_hop_site<1, HINTS>(r, f, a.g, a.par, i, ka, pol);
-    else tmb_hop_site<0, HINTS>(r, f, a.g, a.par, i, ka, pol);
-    const V2 *pp = (const V2 *)a.p, *dw_ = (const V2 *)a.dotw;
-    V2 *out = (V2 *)a.out;
-    /* All epilogue operands are loaded as one batch BEFORE the first store: `out` may alias `p`
-     * (Qtm_minus_psi(l, l), invert_eo.c:270), so the compiler must not move a load across a store,
-     * and interleaving them serialises 12 DRAM round trips per thread (measured: 138 us instead of
-     * 80 us per launch at 24^3x48, profiles/r01_cg_launches_before_epilogue_fix.csv). */
-    /* DOT == 1: Re <dotw, out>.  DOT == 2: the squared norm of the OUTPUT (no operand; a compile-time choice - as a
-     * run-time branch around the operand loads it cost the whole CG 8 %).  The CG uses it on the second hop of
-     * Qtm_pm_psi: <p, Q+ Q- p> = |Q- p|^2 because Q+ is the adjoint of Q- (gamma5-hermiticity). */
-    V2 pc[12], dw[12];
-#pragma unroll
-    for (int c = 0; c < 12; c++) {
-      if (MODE >= 2) pc[c] = pp[(size_t)c * a.g.Vh + i];
-      if (DOT == 1) dw[c] = dw_[(size_t)c * a.g.Vh + i];
-    }
-    V2 o[12];
-#pragma unroll
-    for (int c = 0; c < 12; c++) {
-      o[c] = tmb_epilogue<MODE>(c, r[c], MODE >= 2 ? pc[c] : mk2<V2>(0, 0), cf);
-      if (DOT == 1) {
-        dsum += (double)dw[c].x * (double)o[c].x;
-        dsum += (double)dw[c].y * (double)o[c].y;
-      } else if (DOT == 2) {
-        dsum += (double)o[c].x * (double)o[c].x;
-        dsum += (double)o[c].y * (double)o[c].y;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 12; c++) tmb_store_out<HINTS & 1>(out + (size_t)c * a.g.Vh + i, o[c], pol);
-  }
-  if (DOT) {
-    const double s = block_sum<BLOCK>(dsum);
-    if (threadIdx.x == 0) a.partial[blockIdx.x] = s;
-    if (a.fin_op >= 0) finish_last_block<BLOCK>(a.partial_base, a.fin_total, a.st_fin, a.fin_slot, a.fin_op);
-  }
-}
-
-/* production configuration: chosen from the sweep in profiles/  */
-#ifndef TMB_HOP_BLOCK
-#define TMB_HOP_BLOCK 128
-#endif
-#ifndef TMB_HOP_MINB
-#define TMB_HOP_MINB 3
-#endif
-/* single precision: half the registers per value -> more CTAs per SM */
-#define TMB_HOP_BLOCK_F 128
-#define TMB_HOP_MINB_F 4
-
-static int hop_variant_block(int variant) {
-  static const int b[11] = {TMB_HOP_BLOCK, 64, 64, 128, 128, 128, 256, 256, 96, 192, 64};
-  return (variant >= 0 && variant < 11) ? b[variant] : TMB_HOP_BLOCK;
-}
 int tmb_hop_grid(const tmb_hop_launch &a) {
-  const int b = a.prec ? TMB_HOP_BLOCK_F : hop_variant_block(a.variant);
+  const int b = (a.prec ? TMB_HOP_BLOCK_F : hop_variant_block(a.variant)) / (a.nfl == 2 ? 2 : 1); /* sites per CTA */
   return (a.nsites + b - 1) / b + (a.dist == 2 ? a.p2p_copy_ctas : 0);
-}
-
-template <class V2, int MODE, int DIST, int DOT, int HINTS, int BLOCK, int MINB>
-static cudaError_t hop_go(const tmb_hop_launch &a, cudaStream_t s) {
-  const int grid = (a.nsites + BLOCK - 1) / BLOCK + (DIST == 2 ? a.p2p_copy_ctas : 0);
-  if (grid <= 0) return cudaSuccess;
-  if (a.pdl) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, hop_kernel<V2, MODE, DIST, DOT, HINTS, BLOCK, MINB>, a);
-  }
-  hop_kernel<V2, MODE, DIST, DOT, HINTS, BLOCK, MINB><<<grid, BLOCK, 0, s>>>(a);
-  return cudaGetLastError();
 }
 
 /* HINTS is a configuration mask: bit 0 cache-policy loads, bit 1 12-real links (see tmb_site.cuh) */
@@ -439,6 +105,7 @@ static cudaError_t hop_tune(const tmb_hop_launch &a, int variant, cudaStream_t s
 }
 
 cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s) {
+  if (a.nfl == 2) return tmb_launch_hop_nd(a, s); /* tmb_hop2.cu */
   if (a.prec) {
     if (a.recon12) return hop_dist_f<3>(a, s);
     return hop_dist_f<1>(a, s);
@@ -495,24 +162,25 @@ template <class V2> struct RedCgXR { /* x += alpha p ; r -= alpha Ap ; |r|^2    
 
 template <class F>
 __global__ void __launch_bounds__(RED_BLOCK) red_kernel(F f, size_t n2, double *partial, const tmb_cg_state *st,
-                                                         tmb_cg_state *st_fin, int fin_slot, int fin_op) {
+                                                         tmb_cg_state *st_fin, int fin_slot, int fin_op, const tmb_xred_table *xr) {
   if (st != nullptr && st->converged) return;
   double acc = 0.;
   for (size_t k = (size_t)blockIdx.x * RED_BLOCK + threadIdx.x; k < n2; k += (size_t)gridDim.x * RED_BLOCK)
     acc += f(k);
   const double s = block_sum<RED_BLOCK>(acc);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
-  if (fin_op >= 0) finish_last_block<RED_BLOCK>(partial, (int)gridDim.x, st_fin, fin_slot, fin_op);
+  if (fin_op >= 0) finish_last_block<RED_BLOCK>(partial, (int)gridDim.x, st_fin, fin_slot, fin_op, xr);
 }
 
 /* one CTA: sums the block partials in a fixed order (deterministic), then the CG bookkeeping */
 __global__ void __launch_bounds__(RED_BLOCK) final_kernel(const double *partial, int n, tmb_cg_state *st, int slot,
-                                                           int op, int apply) {
+                                                           int op, int apply, const tmb_xred_table *xr) {
   if (op != TMB_FIN_STORE && st->converged) return;
   double acc = 0.;
   for (int k = threadIdx.x; k < n; k += RED_BLOCK) acc += partial[k];
-  const double s = block_sum<RED_BLOCK>(acc);
+  double s = block_sum<RED_BLOCK>(acc);
   if (threadIdx.x == 0) {
+    if (xr != nullptr) s = xred_sum(xr, s);
     st->tmp[slot] = s;
     if (apply) cg_apply(st, slot, op);
   }
@@ -523,8 +191,13 @@ __global__ void apply_kernel(tmb_cg_state *st, int slot, int op) {
 }
 
 cudaError_t tmb_launch_final(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
-                             cudaStream_t s) {
-  final_kernel<<<1, RED_BLOCK, 0, s>>>(partial, n, st, slot, op, apply);
+                             const tmb_xred_table *xr, cudaStream_t s) {
+  final_kernel<<<1, RED_BLOCK, 0, s>>>(partial, n, st, slot, op, apply, xr);
+  return cudaGetLastError();
+}
+__global__ void seq_bump_kernel(unsigned int *base, unsigned int n) { *base += n; }
+cudaError_t tmb_launch_seq_bump(unsigned int *base, unsigned int n, cudaStream_t s) {
+  seq_bump_kernel<<<1, 1, 0, s>>>(base, n);
   return cudaGetLastError();
 }
 cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s) {
@@ -532,9 +205,9 @@ cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s)
   return cudaGetLastError();
 }
 #define RED_LAUNCH(f, n2, partial, st, s) \
-  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st, nullptr, 0, -1); return cudaGetLastError(); } while (0)
-#define RED_LAUNCH_FIN(f, n2, partial, st, stf, slot, op, s) \
-  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st, stf, slot, op); return cudaGetLastError(); } while (0)
+  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st, nullptr, 0, -1, nullptr); return cudaGetLastError(); } while (0)
+#define RED_LAUNCH_FIN(f, n2, partial, st, stf, slot, op, xr, s) \
+  do { red_kernel<<<tmb_red_grid(n2), RED_BLOCK, 0, s>>>(f, n2, partial, st, stf, slot, op, xr); return cudaGetLastError(); } while (0)
 
 cudaError_t tmb_launch_norm2(int prec, const void *a, size_t n2, double *partial, cudaStream_t s) {
   if (prec) { RedNorm2<float2> f = {(const float2 *)a}; RED_LAUNCH(f, n2, partial, nullptr, s); }
@@ -545,16 +218,18 @@ cudaError_t tmb_launch_dot(int prec, const void *a, const void *b, size_t n2, do
   RedDot<double2> f = {(const double2 *)a, (const double2 *)b}; RED_LAUNCH(f, n2, partial, nullptr, s);
 }
 /* <a,b> with the fused finish + CG bookkeeping (no all-reduce in between: single rank) */
-cudaError_t tmb_launch_dot_fin(const double2 *a, const double2 *b, size_t n2, double *partial, tmb_cg_state *st, int slot, int op, cudaStream_t s) {
-  RedDot<double2> f = {a, b}; RED_LAUNCH_FIN(f, n2, partial, st, st, slot, op, s);
+cudaError_t tmb_launch_dot_fin(const double2 *a, const double2 *b, size_t n2, double *partial, tmb_cg_state *st, int slot, int op,
+                               const tmb_xred_table *xr, cudaStream_t s) {
+  RedDot<double2> f = {a, b}; RED_LAUNCH_FIN(f, n2, partial, st, st, slot, op, xr, s);
 }
 cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s) {
   RedXpayNorm f = {r, sv, c}; RED_LAUNCH(f, n2, partial, nullptr, s);
 }
 cudaError_t tmb_launch_cg_update_xr(int prec, void *x, void *r, const void *p, const void *ap, size_t n2,
-                                    tmb_cg_state *st, double *partial, int fin_slot, int fin_op, cudaStream_t s) {
-  if (prec) { RedCgXR<float2> f = {(float2 *)x, (float2 *)r, (const float2 *)p, (const float2 *)ap, st}; RED_LAUNCH_FIN(f, n2, partial, st, st, fin_slot, fin_op, s); }
-  RedCgXR<double2> f = {(double2 *)x, (double2 *)r, (const double2 *)p, (const double2 *)ap, st}; RED_LAUNCH_FIN(f, n2, partial, st, st, fin_slot, fin_op, s);
+                                    tmb_cg_state *st, double *partial, int fin_slot, int fin_op, const tmb_xred_table *xr,
+                                    cudaStream_t s) {
+  if (prec) { RedCgXR<float2> f = {(float2 *)x, (float2 *)r, (const float2 *)p, (const float2 *)ap, st}; RED_LAUNCH_FIN(f, n2, partial, st, st, fin_slot, fin_op, xr, s); }
+  RedCgXR<double2> f = {(double2 *)x, (double2 *)r, (const double2 *)p, (const double2 *)ap, st}; RED_LAUNCH_FIN(f, n2, partial, st, st, fin_slot, fin_op, xr, s);
 }
 
 /* ------------------------------------------------------------------ K3: elementwise */

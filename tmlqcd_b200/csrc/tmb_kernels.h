@@ -36,8 +36,29 @@ enum tmb_fin_op {
   TMB_FIN_RG_ERR = 5    /* inner loops of rg_mixed_cg_her.c:75-104 / :107-145: inner_eps = delta, sqnrm0 = rhomax */
 };
 
+/* Cross-rank sum inside the reduction finish (peer mode): the CTA that finishes a rank's two-stage reduction stores its
+ * partial into EVERY rank's landing array over NVLink (st.release.sys of a sequence word behind it), waits for the
+ * nranks words of its own array and adds the values in rank order - the same order on every rank, so all ranks hold
+ * bit-identical sums (and take identical stop decisions).  Replaces final_kernel + ncclAllReduce(1 double) +
+ * apply_kernel: no extra launches and no NCCL in the CG.  Sequence numbers come from a device counter that only
+ * performed reductions advance (kernels that return early after the CG's stop do not), ring of TMB_XR_RING slots. */
+#define TMB_XR_MAXR 8
+#define TMB_XR_RING 4
+struct tmb_xred_table {            /* device memory, written once at tmb_comm_init */
+  int nranks, rank;
+  double *val[TMB_XR_MAXR];        /* rank q's landing array [RING][MAXR] (peer memory; [rank] = own) */
+  unsigned int *seq[TMB_XR_MAXR];  /* rank q's sequence words [RING][MAXR] */
+  unsigned int *ctr;               /* this rank's reduction counter */
+  int *err;                        /* set to 1 when a wait timed out */
+};
+
 struct tmb_hop_launch {
   const void *in; void *out; const void *p; const void *dotw;
+  /* nfl == 2 (non-degenerate doublet): the second flavour's fields and the 2x2 flavour mixing of the epilogue
+   * (tm_operators_nd.c:639-756): mode 1 out_f = nrm[(1 -+ i mu g5) H in_f + eps H in_f'], mode 2 out_f = scale g5[(1 -+ i mu g5) p_f
+   * + eps p_f' - H in_f], flavour 0 with the upper sign; dot == 2 accumulates dot_scale (|out|^2 + |out1|^2) */
+  int nfl; const void *in1; void *out1; const void *p1; double nd_mu, nd_eps, nd_scale, dot_scale;
+  const void *in_up1, *in_dn1; /* peer mode: the neighbours' copies of in1 */
   const void *U; const void *halo_up, *halo_dn, *Uhalo;
   double *partial;          /* fused-dot block partials (DOT) */
   const tmb_cg_state *st;   /* if non-null: kernel exits immediately when st->converged */
@@ -63,7 +84,8 @@ struct tmb_hop_launch {
    * rank+1, [3] done from rank-1; up_flags / dn_flags are the neighbours' arrays seen from here. */
   const void *in_up, *in_dn;
   void *halo_up_w, *halo_dn_w;
-  unsigned int seq;
+  const unsigned int *seq_base; unsigned int seq_off; /* this hop's sequence number is *seq_base + seq_off (a CUDA graph
+                             * of a CG chunk carries fixed offsets; its last node advances the base) */
   int p2p_copy_ctas;
   unsigned int *flags, *up_flags, *dn_flags;
   unsigned int *p2p_copied; /* device-local: [0] pull CTAs finished (counter), [1] halo_ready (= seq) */
@@ -72,23 +94,27 @@ struct tmb_hop_launch {
   int p2p_diag;             /* timing diagnostics (results invalid): 4 no pull, 8 no halo path in boundary CTAs, 16 natural slice order */
   /* fused finish of the DOT reduction (fin_op >= 0): the last of fin_total CTAs sums partial_base[0..fin_total) */
   tmb_cg_state *st_fin; const double *partial_base; int fin_op, fin_slot, fin_total;
+  const tmb_xred_table *xr; /* non-null: the finish sums over ranks through peer memory */
 };
 
 int tmb_hop_grid(const tmb_hop_launch &a);
 cudaError_t tmb_launch_hop(const tmb_hop_launch &a, cudaStream_t s);
+cudaError_t tmb_launch_hop_nd(const tmb_hop_launch &a, cudaStream_t s); /* nfl == 2 instantiations (tmb_hop2.cu) */
 
 /* reductions: block partials -> one scalar in st->tmp[slot] (+ optional CG bookkeeping) */
 cudaError_t tmb_launch_final(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
-                             cudaStream_t s);
+                             const tmb_xred_table *xr, cudaStream_t s);
+cudaError_t tmb_launch_seq_bump(unsigned int *base, unsigned int n, cudaStream_t s); /* *base += n */
 cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s);
 int tmb_red_grid(size_t n2);
 cudaError_t tmb_launch_norm2(int prec, const void *a, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_dot(int prec, const void *a, const void *b, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_dot_fin(const double2 *a, const double2 *b, size_t n2, double *partial, tmb_cg_state *st, int slot,
-                               int op, cudaStream_t s);
+                               int op, const tmb_xred_table *xr, cudaStream_t s);
 cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_cg_update_xr(int prec, void *x, void *r, const void *p, const void *ap, size_t n2,
-                                    tmb_cg_state *st, double *partial, int fin_slot, int fin_op, cudaStream_t s);
+                                    tmb_cg_state *st, double *partial, int fin_slot, int fin_op, const tmb_xred_table *xr,
+                                    cudaStream_t s);
 cudaError_t tmb_launch_cg_update_p(int prec, void *p, const void *r, size_t n2, const tmb_cg_state *st, cudaStream_t s);
 
 /* elementwise, n2 = 12*Vh complex elements; `half` = 6*Vh separates spin 0,1 from spin 2,3 */
