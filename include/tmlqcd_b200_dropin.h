@@ -152,6 +152,10 @@ void Qtm_dagger_ndpsi(spinor *const l_strange, spinor *const l_charm, spinor *co
 void Qtm_pm_ndpsi(spinor *const l_strange, spinor *const l_charm, spinor *const k_strange, spinor *const k_charm);
 int cg_her_nd(spinor *const P_up, spinor *P_dn, spinor *const Q_up, spinor *const Q_dn, const int max_iter,
               double eps_sq, const int rel_prec, const int N, matrix_mult_nd f);
+/* operator/tm_operators_nd_32.c:215; solver/rg_mixed_cg_her_nd.c:182 (the RGMIXEDCG branch of invert_doublet_eo.c:145-149) */
+void Qtm_pm_ndpsi_32(spinor32 *const l_strange, spinor32 *const l_charm, spinor32 *const k_strange, spinor32 *const k_charm);
+int rg_mixed_cg_her_nd(spinor *const P_up, spinor *const P_dn, spinor *const Q_up, spinor *const Q_dn, solver_params_t solver_params,
+                       const int max_iter, const double eps_sq, const int rel_prec, const int N, matrix_mult_nd f, matrix_mult_nd32 f32);
 int invert_doublet_eo(spinor *const Even_new_s, spinor *const Odd_new_s, spinor *const Even_new_c, spinor *const Odd_new_c,
                       spinor *const Even_s, spinor *const Odd_s, spinor *const Even_c, spinor *const Odd_c,
                       const double precision, const int max_iter, const int solver_flag, const int rel_prec,

@@ -58,14 +58,25 @@ def section_nd(dims):
     src = [random_spinor(rng, d.Vh) for _ in range(4)]
     f = [d.field(s) for s in src] + [d.field() for _ in range(4)]
     eps_sq, maxit = 1e-14, 5000
-    # operator alone: Qtm_pm_ndpsi = 8 hops + flavour mixing
-    d.call("Qtm_pm_ndpsi", f[4], f[5], f[0], f[1]); d.ck(d.lib.tmb_sync())
+    # operator alone: Qtm_pm_ndpsi = 8 hops + flavour mixing; variant 2 = the default two-flavour kernel (two flavour
+    # groups of warps per CTA), variant 0 = round 1's kernel (both flavours in one thread)
     n = 20
-    t0 = time.perf_counter()
+    t_var = {}
+    for variant in (0, 2):
+        d.ck(d.lib.tmb_set_hop2_variant(variant))
+        d.call("Qtm_pm_ndpsi", f[4], f[5], f[0], f[1]); d.ck(d.lib.tmb_sync())
+        d.timer_start()
+        for _ in range(n):
+            d.lib.tmb_Qtm_pm_ndpsi(f[4], f[5], f[0], f[1])
+        t_var[variant] = d.timer_stop() * 1e-3 / n
+    t_op = t_var[2]
+    # the same in single precision (Qtm_pm_ndpsi_32, the operator of rg_mixed_cg_her_nd's inner loops)
+    f32 = [d.field32(src[0].astype(np.float32)), d.field32(src[1].astype(np.float32)), d.field32(), d.field32()]
+    d.call("Qtm_pm_ndpsi_32", f32[2], f32[3], f32[0], f32[1]); d.ck(d.lib.tmb_sync())
+    d.timer_start()
     for _ in range(n):
-        d.call("Qtm_pm_ndpsi", f[4], f[5], f[0], f[1])
-    d.ck(d.lib.tmb_sync())
-    t_op = (time.perf_counter() - t0) / n
+        d.lib.tmb_Qtm_pm_ndpsi_32(f32[2], f32[3], f32[0], f32[1])
+    t_op32 = d.timer_stop() * 1e-3 / n
     it = d.call("invert_doublet_eo", f[4], f[5], f[6], f[7], f[0], f[1], f[2], f[3], eps_sq, maxit, 1)  # warm-up
     d.call("field_zero", f[5]); d.call("field_zero", f[7])
     d.ck(d.lib.tmb_sync())
@@ -74,10 +85,28 @@ def section_nd(dims):
     d.ck(d.lib.tmb_sync())
     t_solve = time.perf_counter() - t0
     its, err, t_cg = d.solver_stats()
+    # RGMIXEDCG (invert_doublet_eo.c:145-149): rg_mixed_cg_her_nd, float inner loops, default mcg_delta (operator.c:125)
+    x_cg = d.download(f[5])
+    d.ck(d.lib.tmb_set_mcg_delta(5.0e-5))
+    d.call("invert_doublet_eo_solver", f[4], f[5], f[6], f[7], f[0], f[1], f[2], f[3], eps_sq, maxit, 1, 14)  # warm-up
+    d.call("field_zero", f[5]); d.call("field_zero", f[7])
+    d.ck(d.lib.tmb_sync())
+    t0 = time.perf_counter()
+    it_rg = d.call("invert_doublet_eo_solver", f[4], f[5], f[6], f[7], f[0], f[1], f[2], f[3], eps_sq, maxit, 1, 14)
+    d.ck(d.lib.tmb_sync())
+    t_rg = time.perf_counter() - t0
+    _, err_rg, _ = d.solver_stats()
+    isp, idp, iou = C.c_int(), C.c_int(), C.c_int()
+    d.lib.tmb_solver_stats_rg(C.byref(isp), C.byref(idp), C.byref(iou))
+    x_rg = d.download(f[5])
     out = {"workload": "BASELINE configs[3]: invert_doublet_eo, non-degenerate doublet CG on Qtm_pm_ndpsi, %dx%dx%dx%d (TxLXxLYxLZ)" % dims,
            "gauge": how, "2KappaMubar": mubar, "2KappaEpsbar": epsbar, "eps_sq": eps_sq, "rel_prec": 1,
            "iterations": it, "time_to_solution_s": t_solve, "cg_loop_s": t_cg, "final_rr": err,
-           "Qtm_pm_ndpsi_us": 1e6 * t_op,
+           "Qtm_pm_ndpsi_us": 1e6 * t_op, "Qtm_pm_ndpsi_us_round1_kernel": 1e6 * t_var[0], "Qtm_pm_ndpsi_32_us": 1e6 * t_op32,
+           "Qtm_pm_ndpsi_32_hbm_gbs_effective": 4224.0 * d.Vh / t_op32 / 1e9,
+           "rgmixed": {"count": it_rg, "time_to_solution_s": t_rg, "true_rr": err_rg, "inner_sp": isp.value, "inner_dp": idp.value,
+                       "outer": iou.value, "mcg_delta": 5.0e-5, "speedup_vs_cg": t_solve / t_rg,
+                       "odd_solution_rel_l2_vs_cg": float(np.linalg.norm(x_rg - x_cg) / np.linalg.norm(x_cg))},
            "Qtm_pm_ndpsi_algorithmic_bytes_per_site": 8448,
            "Qtm_pm_ndpsi_bytes_how": "4 two-flavour launches: 2 x (1152 links + 4 x 192 spinors) + 2 x (1152 + 6 x 192); "
                                      "the reference's call sequence (8 hops + 5 sweeps) moves 17664",
@@ -85,6 +114,13 @@ def section_nd(dims):
            "Qtm_pm_ndpsi_hbm_gbs_at_8x1536_B_per_site": 8 * 1536.0 * d.Vh / t_op / 1e9,
            "gflops_1320_per_hop": 8 * 1320.0 * d.Vh / t_op / 1e9}
     d.close()
+    fix = os.path.join(ROOT, "tests", "golden", "ref_nd_count_%dx%dx%dx%d.json" % dims)
+    if os.path.exists(fix):  # counts of the unmodified reference's invert_doublet_eo on these very inputs (tests/golden/make_golden_nd_count.py)
+        j = json.load(open(fix))
+        out["cpu_reference_counts"] = {"CG": j["CG"]["iterations"], "RGMIXEDCG": j["RGMIXEDCG"]["iterations"],
+                                       "CG_seconds": j["CG"]["seconds"], "RGMIXEDCG_seconds": j["RGMIXEDCG"]["seconds"], "threads": j["threads"],
+                                       "how": "unmodified invert_doublet_eo.c (oracle/_ref) on the same gauge field and sources, committed fixture"}
+        out["iterations_match_reference"] = bool(abs(it - j["CG"]["iterations"]) <= 1)
     if ref is not None:
         ref.set_params(KAPPA, GMU); ref.set_nd_params(mubar, epsbar, 1.0)
         a, b = ref.spinor(), ref.spinor()
@@ -114,7 +150,15 @@ def section_hmc(dims):
     d.gauge_upload(g)
     d.ck(d.lib.tmb_set_relative_precision_flag(0))
     rng = np.random.default_rng(11)
-    etas = [random_spinor(rng, d.Vh) for _ in mons]
+    if ref is not None:
+        # both arms see the SAME pseudo-fermion noise: what the reference's heatbath draws after start_ranlux(1, 1000 + id)
+        # (random_spinor_field_eo(w_fields[0], repro, RN_GAUSS), det_monomial.c:177, detratio_monomial.c:224)
+        etas = []
+        for id in range(len(mons)):
+            ref.start_ranlux(1, 1000 + id)
+            etas.append(ref.random_spinor_eo())
+    else:
+        etas = [random_spinor(rng, d.Vh) for _ in mons]
     out = {"workload": "BASELINE configs[4]: det + detratio monomials (heatbath, derivative = CG inversion + deriv_Sb force, acc), "
                        "%dx%dx%dx%d (TxLXxLYxLZ), fields resident in HBM" % dims,
            "gauge": how, "forceprec": forceprec, "accprec": accprec, "csg_N": csgN, "solver": "CG", "monomials": []}
@@ -163,8 +207,7 @@ def section_hmc(dims):
         tot = 0.
         recs = []
         for id in ids:
-            # the reference draws its own noise; the timing does not depend on which Gaussian field it is
-            ref.start_ranlux(1, 1000 + id)
+            ref.start_ranlux(1, 1000 + id)  # the heatbath draws the field the device arm was given
             t0 = time.perf_counter(); ref.mnl_heatbath(id); th = time.perf_counter() - t0
             df = ref.derivative()
             ts = []
@@ -177,6 +220,14 @@ def section_hmc(dims):
                                 "sample": "the same sequence (heatbath, 3 derivatives, acc per monomial) by the unmodified reference "
                                           "(half-spinor OpenMP build: det_monomial.c, detratio_monomial.c, deriv_Sb.c, chrono_guess.c, cg_her.c)"}
         out["speedup_vs_cpu_reference"] = tot / tot_gpu
+        cmp = []
+        for a, b in zip(out["monomials"], recs):
+            cmp.append({"energy0_rel_diff": abs(a["energy0"] - b["energy0"]) / abs(b["energy0"]),
+                        "energy1_rel_diff": abs(a["energy1"] - b["energy1"]) / abs(b["energy1"]),
+                        "iter0": [a["iter0"], b["iter0"]], "iter1": [a["iter1"], b["iter1"]]})
+        out["same_noise_comparison"] = cmp
+        # the force itself: three accumulated derivative calls of the last monomial, device against reference
+        out["derivative_rel_l2_vs_cpu_reference"] = float(np.linalg.norm(df_gpu - df) / np.linalg.norm(df))
     out["derivative_norm"] = float(np.linalg.norm(df_gpu))
     return out
 

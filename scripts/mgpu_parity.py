@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Multi-GPU parity: torchrun --nproc-per-node N scripts/mgpu_parity.py
 The GLOBAL lattice (T = N*T_loc) is generated identically on every rank; rank r takes its T-slab
-(the reference's PARALLELT decomposition, mpi_init.c:321), runs the distributed operators / CG with
-NCCL half-spinor halos, and rank 0 compares the gathered result with the CPU oracle on the global
+(the reference's PARALLELT decomposition, mpi_init.c:321), runs the distributed operators / solvers (peer mode by
+default; TMB_P2P=0: NCCL half-spinor halos and all-reduces; TMB_XRED=0: peer hops with NCCL all-reduces), and rank 0 compares the gathered result with the CPU oracle on the global
 lattice (the decomposition-independence recipe of SURVEY 4: reproducible global fields)."""
 import ctypes as C
 import os
@@ -76,6 +76,8 @@ def main():
     d.call("Qtm_pm_ndpsi", dls, dlc, dk, dp); res["nd_s"], res["nd_c"] = gather(dls), gather(dlc)
     d.call("field_zero", dls); d.call("field_zero", dlc)
     itn = d.call("cg_her_nd", dls, dlc, dk, dp, 2000, 1e-20, 1); res["cgnd_s"], res["cgnd_c"] = gather(dls), gather(dlc)
+    d.ck(d.lib.tmb_set_mcg_delta(0.1))
+    itr_nd = d.call("rg_mixed_cg_her_nd", dls, dlc, dk, dp, 2000, 1e-20, 1); res["rgnd_s"], res["rgnd_c"] = gather(dls), gather(dlc)
     # fermion force and a det monomial with chronological guess (deriv_Sb exchanges the projected first slices)
 
     def gather_df():
@@ -122,6 +124,8 @@ def main():
         es[:] = 0; ec[:] = 0; itr = o.cg_her_nd(es, ec, k, p, 2000, 1e-20, 1)
         r1, r2 = rel_l2(res["cgnd_s"], es), rel_l2(res["cgnd_c"], ec)
         print(f"cg_her_nd iters {itn} (oracle {itr}) rel {r1:.2e} {r2:.2e}"); ok &= abs(itn - itr) <= 1 and max(r1, r2) <= 1e-9
+        r1, r2 = rel_l2(res["rgnd_s"], es), rel_l2(res["rgnd_c"], ec)
+        print(f"rg_mixed_cg_her_nd count {itr_nd}: x rel {r1:.2e} {r2:.2e}"); ok &= itr_nd > 0 and max(r1, r2) <= 1e-8
         df = o.derivative(); o.deriv_Sb(0, k, p, df, 0.7); o.deriv_Sb(1, p, k, df, -0.4)
         r = rel_l2(res["df"], df); print(f"deriv_Sb rel {r:.2e}"); ok &= r <= 1e-13
         o.mnl_clear(); assert o.mnl_add(*margs) == 0

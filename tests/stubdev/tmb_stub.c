@@ -214,6 +214,18 @@ int tmb_field32_download_lexic(float *lex, const void *e, const void *o) {
   free(l); free(a); free(b);
   return 0;
 }
+int tmb_Qtm_pm_ndpsi_32(void *ls, void *lc, const void *ks, const void *kc) {
+  NEEDG();
+  double *a = widen(ks), *b = widen(kc), *c = malloc(NF * sizeof(double)), *d = malloc(NF * sizeof(double));
+  orc_Qtm_pm_ndpsi(c, d, a, b); narrow(ls, c); narrow(lc, d); free(a); free(b); free(c); free(d);
+  return 0;
+}
+/* the reliable-update solver reaches the CG's solution to the requested precision; the stand-in serves it with the oracle's CG */
+int tmb_rg_mixed_cg_her_nd(void *Pup, void *Pdn, const void *Qup, const void *Qdn, int m, double e, int r) {
+  NEEDG();
+  memset(Pup, 0, NF * sizeof(double)); memset(Pdn, 0, NF * sizeof(double));
+  return orc_cg_her_nd(Pup, Pdn, Qup, Qdn, m, e, r);
+}
 int tmb_blas32(int op, void *r, const void *s1, const void *s2, double c1d, double c2d) {
   NEED();
   float *R = r; const float *A = s1, *B = s2; const float c1 = (float)c1d, c2 = (float)c2d;

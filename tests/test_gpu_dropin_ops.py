@@ -119,6 +119,25 @@ def test_inversions_with_reference_signatures(dropin):
     assert abs(it - int(base["invert_doublet_iters"])) <= 1
     for o_, name in zip(outs, ("ens", "ons", "enc", "onc")):
         assert rel_l2(o_, base["invert_doublet_" + name]) <= 1e-8, name
+    # the RGMIXEDCG branch (invert_doublet_eo.c:145-149): same solution, to the solve's precision
+    sp.mcg_delta = 0.1
+    outs = [D.spinor() for _ in range(4)]
+    it = D.invert_doublet_eo(*outs, k, p, q, w, 1e-18, 1000, RGMIXEDCG, 1, sp, 0, 0, 18)
+    assert it > 0
+    for o_, name in zip(outs, ("ens", "ons", "enc", "onc")):
+        assert rel_l2(o_, base["invert_doublet_" + name]) <= 1e-7, name
+    # rg_mixed_cg_her_nd and Qtm_pm_ndpsi_32 with the reference's signatures, against the unmodified reference's results
+    g = _gold("ref_ndmixed_4x4x4x4.npz")
+    D.set_params(float(g["kappa"]), float(g["gmu"]), g["theta"]); D.set_nd_params(*g["nd"]); D.set_gauge(g["gauge"])
+    s_, c_ = np.array(g["s"]), np.array(g["c"])
+    l1, l2 = np.zeros((D.Vh, 24), dtype=np.float32), np.zeros((D.Vh, 24), dtype=np.float32)
+    D.Qtm_pm_ndpsi_32(l1, l2, s_.astype(np.float32), c_.astype(np.float32))
+    assert rel_l2(l1.astype(np.float64), g["Qtm_pm_ndpsi_32_s"].astype(np.float64)) <= 1e-5
+    assert rel_l2(l2.astype(np.float64), g["Qtm_pm_ndpsi_32_c"].astype(np.float64)) <= 1e-5
+    sp.mcg_delta = float(g["delta"])
+    xu, xd = D.spinor(), D.spinor()
+    it = D.rg_mixed_cg_her_nd(xu, xd, s_, c_, sp, 2000, float(g["eps_sq"]), int(g["rel_prec"]), D.Vh, D.fptr("Qtm_pm_ndpsi"), D.fptr("Qtm_pm_ndpsi_32"))
+    assert it > 0 and rel_l2(xu, g["x_s"]) <= 1e-8 and rel_l2(xd, g["x_c"]) <= 1e-8
 
 
 def _hmc_dropin():

@@ -146,6 +146,7 @@ DROPIN_API = {
     "M_ee_inv_ndpsi": (None, [_sp] * 4 + [_d, _d]), "Qtm_ndpsi": (None, [_sp] * 4),
     "Qtm_dagger_ndpsi": (None, [_sp] * 4), "Qtm_pm_ndpsi": (None, [_sp] * 4),
     "cg_her_nd": (_i, [_sp] * 4 + [_i, _d, _i, _i, _vp]),
+    "Qtm_pm_ndpsi_32": (None, [_fp] * 4), "rg_mixed_cg_her_nd": (_i, [_sp] * 4 + [SolverParams, _i, _d, _i, _i, _vp, _vp]),
     "invert_doublet_eo": (_i, [_sp] * 8 + [_d, _i, _i, _i, SolverParams, _i, _i, _i]),
     "Mee_inv_psi": (None, [_sp, _sp, _d]), "Mee_psi": (None, [_sp, _sp, _d]),
     "mul_one_pm_imu_sub_mul": (None, [_sp, _sp, _sp, _d, _i]), "mul_one_sub_mul_gamma5": (None, [_sp, _sp, _sp]),

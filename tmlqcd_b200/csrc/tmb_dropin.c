@@ -483,6 +483,27 @@ int cg_her_nd(spinor *const P_up, spinor *P_dn, spinor *const Q_up, spinor *cons
   down(P_up, 0); down(P_dn, 1);
   return iter;
 }
+/* operator/tm_operators_nd_32.c:215 on host spinor32 buffers; solver/rg_mixed_cg_her_nd.c:182 */
+void Qtm_pm_ndpsi_32(spinor32 *const l_strange, spinor32 *const l_charm, spinor32 *const k_strange, spinor32 *const k_charm) {
+  sync_globals();
+  CHK(tmb_field32_upload(dev32(0), (const float *)k_strange)); CHK(tmb_field32_upload(dev32(1), (const float *)k_charm));
+  CHK(tmb_Qtm_pm_ndpsi_32(dev32(2), dev32(3), dev32(0), dev32(1)));
+  CHK(tmb_field32_download((float *)l_strange, dev32(2))); CHK(tmb_field32_download((float *)l_charm, dev32(3)));
+}
+int rg_mixed_cg_her_nd(spinor *const P_up, spinor *const P_dn, spinor *const Q_up, spinor *const Q_dn, solver_params_t solver_params,
+                       const int max_iter, const double eps_sq, const int rel_prec, const int N, matrix_mult_nd f, matrix_mult_nd32 f32) {
+  if (f != &Qtm_pm_ndpsi || f32 != (matrix_mult_nd32)&Qtm_pm_ndpsi_32 || N != VOLUME / 2) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in rg_mixed_cg_her_nd: only (Qtm_pm_ndpsi, Qtm_pm_ndpsi_32) on VOLUME/2 sites is implemented\n");
+    exit(1);
+  }
+  sync_globals();
+  CHK(tmb_set_mcg_delta((double)solver_params.mcg_delta));
+  up(2, Q_up); up(3, Q_dn);
+  int iter = tmb_rg_mixed_cg_her_nd(dev(0), dev(1), dev(2), dev(3), max_iter, eps_sq, rel_prec);
+  if (iter < -1) die(__func__);
+  down(P_up, 0); down(P_dn, 1);
+  return iter;
+}
 int invert_doublet_eo(spinor *const Even_new_s, spinor *const Odd_new_s, spinor *const Even_new_c, spinor *const Odd_new_c,
                       spinor *const Even_s, spinor *const Odd_s, spinor *const Even_c, spinor *const Odd_c,
                       const double precision, const int max_iter, const int solver_flag, const int rel_prec,
