@@ -377,6 +377,7 @@ def main():
     ap.add_argument("--loopback", action="store_true", help="1 GPU: run the T-split halo/boundary path against itself")
     ap.add_argument("--loopback2", action="store_true", help="1 GPU: run the T-split peer-mode path against itself")
     ap.add_argument("--sweep", action="store_true", help="time every kernel variant (tuning aid, prints to stderr)")
+    ap.add_argument("--sweep-sustained", action="store_true", help="time the residency variants for >= 0.6 s each (power-capped regime; stderr)")
     ap.add_argument("--overlap", type=int, default=0, help="tmb_set_overlap flags: 1 PDL, 2 L2 gauge prefetch")
     ap.add_argument("--p2p-diag", type=int, default=0, help="tmb_set_p2p_diag bits (timing diagnostics, results invalid; needs TMB_P2P_DIAG=1)")
     ap.add_argument("--variant", type=int, default=None)
@@ -442,6 +443,20 @@ def main():
         dev.ck(lib.tmb_comm_loopback(2 if args.loopback2 else 1))
         dev.gauge_upload(g)
     f0, f1, f2 = dev.field(src), dev.field(), dev.field()
+
+    if args.sweep_sustained and rank == 0:
+        # every residency variant of the plain kernel for >= 0.6 s each: the power-capped regime the CG lives in
+        log("sustained sweep (>= 0.6 s per variant, cache policies on):")
+        for variant in list(range(0, 11)):
+            dev.ck(lib.tmb_set_tuning(variant, 1, 0))
+            S.time_pairs(20, f0, f1, f2)
+            ms1, _ = S.time_pairs(100, f0, f1, f2)
+            n = int(max(200, 600.0 / (ms1 / 100)))
+            ms_v, _ = S.time_pairs(n, f0, f1, f2)
+            per = ms_v / (2 * n)
+            log(f"  variant={variant:2d}: burst {1e3 * ms1 / 200:7.2f} us/hop, sustained {1e3 * per:7.2f} us/hop "
+                f"{Vh * BYTES_SITE / per / 1e6:8.1f} GB/s = {Vh * BYTES_SITE / per / 1e6 / measured_peaks()[0]:.3f} of the measured peak")
+        dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, -1 if args.hints is None else args.hints, args.xblock or 0))
 
     if args.sweep and rank == 0:
         results = []
@@ -574,6 +589,42 @@ def main():
                       "gbs_per_direction_per_gpu": 2 * Vh * 192 * ne / dt / 1e9,
                       "api": "Hopping_Matrix(ieo, spinor* l, spinor* k) drop-in, pinned host buffers, upload+kernel+download per call"}
         out["gpu_launches"] += int(lib.tmb_launch_count() - n0)
+        # what the host link of this box gives (pinned memory, copy engines), and the same pairs on PAGEABLE buffers - what the
+        # reference's calloc'ed fields are (init/init_spinor_field.c:38-66): the library page-locks a slab when it first sees it
+        try:
+            la, lb, lc = C.c_double(), C.c_double(), C.c_double()
+            dev.ck(lib.tmb_measure_pcie_gbs(64 << 20, 10, C.byref(la), C.byref(lb), C.byref(lc)))
+            out["e2e"]["link_gbs"] = {"h2d": la.value, "d2h": lb.value, "duplex_per_direction": lc.value,
+                                      "how": "64 MB pinned copies on the library's two copy streams, this process, this box"}
+            out["e2e"]["frac_of_duplex_link"] = out["e2e"]["gbs_per_direction_per_gpu"] / lc.value
+            pk, p1, p2 = np.array(src), np.zeros((Vh, 24)), np.zeros((Vh, 24))
+
+            def pairs_on_pageable(n):
+                S.barrier()
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    D.Hopping_Matrix(0, p1, pk); D.Hopping_Matrix(1, p2, p1)
+                S.barrier()
+                return S.max_over_ranks(time.perf_counter() - t0)
+            pairs_on_pageable(1)
+            npg = max(3, ne // 2)
+            dt_plain = pairs_on_pageable(npg)   # as they are: the driver's bounce buffers
+            t0 = time.perf_counter()
+            for a_ in (pk, p1, p2):             # the INTEGRATION.md recipe: page-lock each slab once
+                dev.ck(lib.tmb_host_register(a_.ctypes.data_as(C.c_void_p), a_.nbytes))
+            t_reg = time.perf_counter() - t0
+            pairs_on_pageable(1)
+            dt_reg = pairs_on_pageable(ne)
+            for a_ in (pk, p1, p2):
+                dev.ck(lib.tmb_host_unregister(a_.ctypes.data_as(C.c_void_p)))
+            out["e2e"]["pageable"] = {
+                "value": V * world * FLOP_SITE * ne / dt_reg / 1e9, "unit": "GFLOP/s", "ms_per_step": 1e3 * dt_reg / ne,
+                "register_once_ms": 1e3 * t_reg, "unregistered_value": V * world * FLOP_SITE * npg / dt_plain / 1e9,
+                "unregistered_ms_per_step": 1e3 * dt_plain / npg,
+                "how": "numpy (malloc) buffers like the reference's calloc slabs: `value` after tmb_host_register(slab) once per slab "
+                       "(register_once_ms for the three 64 MB slabs), `unregistered_value` with the buffers left pageable"}
+        except Exception as e:  # pragma: no cover
+            out["e2e"]["link_gbs"] = {"error": repr(e)[:200]}
 
     # ---- eo-CG time-to-solution (the configs[1] solve): device-resident and through invert_eo with host buffers ----
     if not args.skip_cg:

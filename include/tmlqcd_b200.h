@@ -53,13 +53,14 @@ int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_ope
  * of the plain kernel; 10 forces 448.  cache_hints: 1 = L2 eviction policies on the link / spinor loads, 0 = plain
  * loads, -1 (default) = policies only when links + CG vectors exceed the L2 (see eff_hints() in tmb_capi.cu) */
 int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
-/* two-flavour hop: 2 (default) = the hopping kernel with two flavour groups of warps per CTA (every precision, compression and
- * communication mode, fused <p, A p>); 0 = both flavours in one thread, 1 = lane-paired flavours (round-1 kernels: one rank, double) */
+/* two-flavour hop: 2 = the hopping kernel with two flavour groups of warps per CTA (every precision, compression and
+ * communication mode, fused <p, A p>); 0 = both flavours in one thread, 1 = lane-paired flavours (one rank, 18-real links, double
+ * only); -1 (default) = 0 where it applies (measured faster there), 2 elsewhere */
 int tmb_set_hop2_variant(int v);
 /* CompressionType of the reference (misc_types.h:33-37): 18 = full links (default), 12 = two rows streamed,
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);
-int tmb_set_host_chunks(int n); /* chunks of the pipelined host-pointer Hopping_Matrix (default 8, the measured best at 24^3x48) */
+int tmb_set_host_chunks(int n); /* chunks of the pipelined host-pointer Hopping_Matrix; 0 (default): two time-slices per chunk, at least 1 MB */
 int tmb_set_p2p_diag(int bits); /* peer-mode timing diagnostics (results INVALID across ranks); refused unless TMB_P2P_DIAG=1 */
 int tmb_set_overlap(int flags); /* unknown bits are refused. bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows, bit2: no CUDA-graph replay in the CG, bit3: L2 prefetch of the epilogue operands (p, dotw), bit4: the CG takes <p, A p> from the last hop (operand load) instead of |Q- p|^2 from the second */
 
@@ -245,6 +246,8 @@ int tmb_measure_plaquette(double *result);
 long long tmb_launch_count(void);
 /* measurement aid: sustained device-to-device copy bandwidth (read + write), GB/s, `reps` copies of `bytes` */
 int tmb_measure_copy_gbs(size_t bytes, int reps, double *gbs);
+/* measurement aid: pinned-memory host link, GB/s per direction: upload alone, download alone, both at once */
+int tmb_measure_pcie_gbs(size_t bytes, int reps, double *h2d, double *d2h, double *duplex_each);
 
 #ifdef __cplusplus
 }

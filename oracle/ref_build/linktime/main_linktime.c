@@ -45,6 +45,7 @@ extern const char *tmb_last_error(void);
 double mixcg_innereps = 5.0e-5;
 int mixcg_maxinnersolverit = 5000;
 double phmc_invmaxev = 1.;
+double X0 = 0., X1 = 0., X2 = 0., X3 = 0.; /* read_input.h: the flex parser's theta angles, read by boundary() */
 extern int even_odd_flag;
 
 static void rd(FILE *f, void *p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "linktime: short read\n"); exit(3); } }

@@ -69,14 +69,20 @@ def section_nd(dims):
         for _ in range(n):
             d.lib.tmb_Qtm_pm_ndpsi(f[4], f[5], f[0], f[1])
         t_var[variant] = d.timer_stop() * 1e-3 / n
-    t_op = t_var[2]
+    d.ck(d.lib.tmb_set_hop2_variant(-1))  # automatic: round 1's kernel here (one rank, 18-real links, double)
+    t_op = min(t_var.values())
     # the same in single precision (Qtm_pm_ndpsi_32, the operator of rg_mixed_cg_her_nd's inner loops)
     f32 = [d.field32(src[0].astype(np.float32)), d.field32(src[1].astype(np.float32)), d.field32(), d.field32()]
-    d.call("Qtm_pm_ndpsi_32", f32[2], f32[3], f32[0], f32[1]); d.ck(d.lib.tmb_sync())
-    d.timer_start()
-    for _ in range(n):
-        d.lib.tmb_Qtm_pm_ndpsi_32(f32[2], f32[3], f32[0], f32[1])
-    t_op32 = d.timer_stop() * 1e-3 / n
+    t_var32 = {}
+    for variant in (0, 2):
+        d.ck(d.lib.tmb_set_hop2_variant(variant))
+        d.call("Qtm_pm_ndpsi_32", f32[2], f32[3], f32[0], f32[1]); d.ck(d.lib.tmb_sync())
+        d.timer_start()
+        for _ in range(n):
+            d.lib.tmb_Qtm_pm_ndpsi_32(f32[2], f32[3], f32[0], f32[1])
+        t_var32[variant] = d.timer_stop() * 1e-3 / n
+    d.ck(d.lib.tmb_set_hop2_variant(-1))
+    t_op32 = min(t_var32.values())
     it = d.call("invert_doublet_eo", f[4], f[5], f[6], f[7], f[0], f[1], f[2], f[3], eps_sq, maxit, 1)  # warm-up
     d.call("field_zero", f[5]); d.call("field_zero", f[7])
     d.ck(d.lib.tmb_sync())
@@ -102,7 +108,9 @@ def section_nd(dims):
     out = {"workload": "BASELINE configs[3]: invert_doublet_eo, non-degenerate doublet CG on Qtm_pm_ndpsi, %dx%dx%dx%d (TxLXxLYxLZ)" % dims,
            "gauge": how, "2KappaMubar": mubar, "2KappaEpsbar": epsbar, "eps_sq": eps_sq, "rel_prec": 1,
            "iterations": it, "time_to_solution_s": t_solve, "cg_loop_s": t_cg, "final_rr": err,
-           "Qtm_pm_ndpsi_us": 1e6 * t_op, "Qtm_pm_ndpsi_us_round1_kernel": 1e6 * t_var[0], "Qtm_pm_ndpsi_32_us": 1e6 * t_op32,
+           "Qtm_pm_ndpsi_us": 1e6 * t_op, "Qtm_pm_ndpsi_us_one_thread_two_flavours": 1e6 * t_var[0],
+           "Qtm_pm_ndpsi_us_two_flavour_warp_groups": 1e6 * t_var[2], "Qtm_pm_ndpsi_32_us": 1e6 * t_op32,
+           "Qtm_pm_ndpsi_32_us_one_thread_two_flavours": 1e6 * t_var32[0], "Qtm_pm_ndpsi_32_us_two_flavour_warp_groups": 1e6 * t_var32[2],
            "Qtm_pm_ndpsi_32_hbm_gbs_effective": 4224.0 * d.Vh / t_op32 / 1e9,
            "rgmixed": {"count": it_rg, "time_to_solution_s": t_rg, "true_rr": err_rg, "inner_sp": isp.value, "inner_dp": idp.value,
                        "outer": iou.value, "mcg_delta": 5.0e-5, "speedup_vs_cg": t_solve / t_rg,

@@ -33,6 +33,9 @@ def T(label, fn, reps=5):
     return min(ts)
 
 
+a, b, c = C.c_double(), C.c_double(), C.c_double()
+d.ck(d.lib.tmb_measure_pcie_gbs(64 << 20, 20, C.byref(a), C.byref(b), C.byref(c)))
+print(f"host link (pinned, 64 MB copies): H2D {a.value:.1f} GB/s, D2H {b.value:.1f} GB/s, both at once {c.value:.1f} GB/s per direction", flush=True)
 hk, h1, h2, h3 = (pinned((d.Vh, 24)) for _ in range(4))
 hk[:] = random_spinor(rng, d.Vh); h1[:] = random_spinor(rng, d.Vh)
 f0, f1 = d.field(), d.field()
@@ -44,10 +47,15 @@ pg = np.array(hk)
 t = T("field_upload (pageable)", lambda: d.upload(f0, pg)); print(f"   -> {mb / t / 1e3:.1f} GB/s")
 T("drop-in Hopping_Matrix (first: gauge upload)", lambda: D.Hopping_Matrix(0, h2, hk), reps=1)
 t = T("drop-in Hopping_Matrix (pinned)", lambda: D.Hopping_Matrix(0, h2, hk)); print(f"   -> {mb / t / 1e3:.1f} GB/s each way")
-for nch in (4, 8, 16, 24, 48):
+pgk, pgl = np.array(hk), np.zeros_like(hk)
+t = T("drop-in Hopping_Matrix (pageable numpy buffers, page-locked on first sight)", lambda: D.Hopping_Matrix(0, pgl, pgk)); print(f"   -> {mb / t / 1e3:.1f} GB/s each way")
+def pair():
+    D.Hopping_Matrix(0, h2, hk); D.Hopping_Matrix(1, h3, h2)
+t = T("drop-in EO+OE pair (pinned)", pair, reps=8); print(f"   -> {2 * mb / t / 1e3:.1f} GB/s each way")
+for nch in (4, 8, 16, 24, 48, 0):
     d.ck(d.lib.tmb_set_host_chunks(nch))
     t = T(f"drop-in Hopping_Matrix (pinned), {nch} chunks", lambda: D.Hopping_Matrix(0, h2, hk)); print(f"   -> {mb / t / 1e3:.1f} GB/s each way")
-d.ck(d.lib.tmb_set_host_chunks(16))
+d.ck(d.lib.tmb_set_host_chunks(0))
 t = T("device Hopping_Matrix", lambda: d.lib.tmb_Hopping_Matrix(0, f1, f0))
 hk2 = pinned((d.Vh, 24)); hk2[:] = hk
 sp = tm.capi.SolverParams()

@@ -9,5 +9,5 @@ for f in tmb_stub.c build.sh $SRC/tmb_dropin.c $SRC/tmb_io.c ../../oracle/tmorac
   if [ ! -e libtmb_dropin_stub.so ] || [ "$f" -nt libtmb_dropin_stub.so ]; then fresh=0; fi
 done
 if [ $fresh = 1 ]; then exit 0; fi
-gcc -std=gnu99 -O2 -fno-strict-aliasing -ffp-contract=off -fPIC -shared -Wall -o libtmb_dropin_stub.so \
+gcc -std=gnu99 -O2 -fno-strict-aliasing -ffp-contract=off -fPIC -shared -Wall -Wl,-Bsymbolic-functions -o libtmb_dropin_stub.so \
     $SRC/tmb_dropin.c $SRC/tmb_io.c tmb_stub.c ../../oracle/tmoracle.c -lm

@@ -340,6 +340,7 @@ def test_nd_two_flavour_kernel_every_mode(oracle_lib, loopback, compression):
         if loopback:
             d.ck(d.lib.tmb_comm_loopback(loopback)); d.gauge_upload(g)
         d.ck(d.lib.tmb_set_compression(compression))
+        d.ck(d.lib.tmb_set_hop2_variant(2))  # the automatic choice would take round 1's kernel on one rank with 18-real links
         s, c = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
         ds, dc, dls, dlc = d.field(s), d.field(c), d.field(), d.field()
         for name in ("Qtm_ndpsi", "Qtm_dagger_ndpsi", "Qtm_pm_ndpsi"):
@@ -401,6 +402,67 @@ def test_rg_mixed_cg_her_nd_vs_reference(oracle_lib, loopback):
         assert it > 0
         for f, a in zip(outs, A):
             assert rel_l2(d.download(f), a) <= 1e-8
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("loopback", [0, 1, 2])
+def test_host_pointer_hop_pipeline(oracle_lib, loopback):
+    """Hopping_Matrix / tm_times_Hopping_Matrix with HOST buffers: chunked full-duplex pipeline replayed as a cached CUDA
+    graph (one rank) or with the boundary slices behind a face exchange (split T, here against itself); pageable numpy
+    buffers are page-locked on first sight; a parameter change (g_mu, kappa, theta) must not replay a stale graph"""
+    import tmlqcd_b200 as tm
+    dims = (8, 8, 8, 8)
+    rng = np.random.default_rng(17)
+    o = oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g)
+    D = tm.DropIn(*dims)
+    try:
+        if loopback:
+            assert D.lib.tmb_comm_loopback(loopback) == 0
+        D.set_gauge(g)
+        k = random_spinor(rng, o.Vh); l = np.zeros_like(k); exp = o.spinor()
+        for theta, kappa in (((1., 0.3, 0., 0.7), KAPPA), ((0., 0., 0., 0.), 0.12)):
+            o.set_params(kappa, GMU, theta); D.set_params(kappa, GMU, theta)
+            for rep in range(3):  # first call captures, the others replay
+                for ieo in (0, 1):
+                    o.Hopping_Matrix(ieo, exp, k); l[:] = 0; D.Hopping_Matrix(ieo, l, k)
+                    assert rel_l2(l, exp) <= TOL, (theta, rep, ieo)
+            o.tm_times_Hopping_Matrix(1, exp, k, 0.9, -0.2); D.tm_times_Hopping_Matrix(1, l, k, 0.9, -0.2)
+            assert rel_l2(l, exp) <= TOL
+        k2 = random_spinor(rng, o.Vh)  # another buffer, other contents: its own graph
+        o.Hopping_Matrix(0, exp, k2); D.Hopping_Matrix(0, l, k2); assert rel_l2(l, exp) <= TOL
+        for nch in (1, 3, 8):
+            assert D.lib.tmb_set_host_chunks(nch) == 0
+            o.Hopping_Matrix(1, exp, k); D.Hopping_Matrix(1, l, k); assert rel_l2(l, exp) <= TOL, nch
+        assert D.lib.tmb_set_host_chunks(0) == 0
+    finally:
+        D.close()
+
+
+def test_reductions_at_48x48x48x96_against_compensated_sums():
+    """The reference's square_norm / scalar_prod_r are Kahan sums (linalg/scalar_prod_r.c:159-194, square_norm.c); the device
+    sums in a fixed tree (thread -> warp -> CTA -> one CTA over the partials).  At the largest BASELINE volume (5.3 M sites per
+    parity, 127 M doubles) both must agree with an extended-precision sum far below what changes a CG iteration count."""
+    import tmlqcd_b200 as tm
+    dims = (96, 48, 48, 48)
+    d = tm.Device(*dims)
+    try:
+        rng = np.random.default_rng(96)
+        a = rng.normal(scale=np.sqrt(0.5), size=(d.Vh, 24)); b = rng.normal(scale=np.sqrt(0.5), size=(d.Vh, 24))
+        b += 0.25 * a  # a scalar product that does not average to zero
+        da, db = d.field(a), d.field(b)
+        n2 = d.reduce("square_norm", da); sp = d.reduce("scalar_prod_r", da, db)
+        ld = np.longdouble
+        n2_ref = float(np.sum(np.square(a, dtype=ld), dtype=ld)); sp_ref = float(np.sum(np.multiply(a, b, dtype=ld), dtype=ld))
+        assert abs(n2 / n2_ref - 1) <= 1e-14, abs(n2 / n2_ref - 1)
+        assert abs(sp / sp_ref - 1) <= 1e-13, abs(sp / sp_ref - 1)
+        # the float fields of the mixed solvers accumulate in double on the device
+        a32 = d.field32(a.astype(np.float32))
+        n32 = d.reduce("square_norm_32", a32)
+        n32_ref = float(np.sum(np.square(a.astype(np.float32), dtype=ld), dtype=ld))
+        assert abs(n32 / n32_ref - 1) <= 1e-13
     finally:
         d.close()
 

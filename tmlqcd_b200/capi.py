@@ -92,6 +92,7 @@ DEVICE_API = {
     "tmb_monomial_pf": (_vp, [_i]), "tmb_monomial_wfield": (_vp, [_i]),
     "tmb_blas32": (_i, [_i, _vp, _vp, _vp, _d, _d]), "tmb_square_norm_32": (_i, [_vp, C.POINTER(_d)]), "tmb_scalar_prod_r_32": (_i, [_vp, _vp, C.POINTER(_d)]),
     "tmb_measure_plaquette": (_i, [C.POINTER(_d)]), "tmb_launch_count": (C.c_longlong, []), "tmb_measure_copy_gbs": (_i, [C.c_size_t, _i, C.POINTER(_d)]),
+    "tmb_measure_pcie_gbs": (_i, [C.c_size_t, _i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
 }
 
 _sp = _dp  # host spinor buffers (reference AoS layout) as float64 arrays

@@ -75,7 +75,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = 2, cg_selfnorm = 1;
+  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = -1, cg_selfnorm = 1;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -89,7 +89,9 @@ struct Ctx {
   std::vector<std::pair<size_t, size_t>> arena_free; /* (offset, bytes) */
   char *up_base = nullptr, *dn_base = nullptr;
   unsigned int *flags = nullptr, *up_flags = nullptr, *dn_flags = nullptr, *p2p_ticket = nullptr;
-  int host_chunks = 8; int *p2p_err = nullptr; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
+  int host_chunks = 0; /* chunks of the pipelined host-pointer hop; 0: two time-slices per chunk (>= 1 MB) */
+  unsigned long long param_gen = 1; /* bumped by every setter whose value is baked into a cached host-hop graph */
+  int *p2p_err = nullptr; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
   /* sequence numbers of the peer-mode hops are *seq_dev + hop_off: the host counts offsets, the device base only moves
    * at the end of a replayed CG graph (whose kernels carry fixed offsets); seq_dev[1] is the reduction counter of xred_sum */
   unsigned int *seq_dev = nullptr; unsigned int hop_off = 0;
@@ -107,6 +109,7 @@ struct Ctx {
   double mcg_delta = 5.0e-5;                  /* solver_params.mcg_delta = _default_mixcg_innereps (monomial.c:106) */
 };
 static Ctx C;
+static void hgraphs_clear(); static void pinned_clear();
 static int ensure_gauge12(int prec);
 extern "C" int tmb_rg_mixed_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec);
 static std::string g_err;
@@ -218,7 +221,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = 2; C.cg_selfnorm = 1;
+  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = -1; C.cg_selfnorm = 1;
   C.init = true;
   return 0;
 }
@@ -226,6 +229,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
 extern "C" int tmb_finalize(void) {
   if (!C.init) return 0;
   cudaDeviceSynchronize();
+  hgraphs_clear(); pinned_clear();
   for (void *p : C.fields) sym_free(p);
   C.fields.clear(); C.field_bytes.clear();
   for (int i = 0; i < NSCRATCH; i++) { sym_free(C.scratch[i]); C.scratch[i] = nullptr; }
@@ -407,7 +411,7 @@ extern "C" int tmb_comm_peer_mode(void) { return C.p2p ? 1 : 0; }
 extern "C" int tmb_comm_loopback(int on) {
   NEED_INIT();
   if (C.nranks > 1) return fail(-6, "tmb_comm_loopback: only for a single rank");
-  C.loopback = on != 0; C.loopback_mode = on; C.dist = C.loopback; C.g.dist_t = C.dist ? 1 : 0;
+  C.loopback = on != 0; C.loopback_mode = on; C.dist = C.loopback; C.g.dist_t = C.dist ? 1 : 0; C.param_gen++;
   C.gauge_loaded = false; /* Uhalo must be rebuilt */
   C.p2p = false; C.xred = false;
   if (on == 2) {
@@ -436,7 +440,7 @@ extern "C" int tmb_set_boundary(double kappa, const double theta[4]) {
   /* boundary.c:40-55, incl. its PI_ literal; global extents: only T is distributed */
   const double PI_ = 3.14159265358979;
   const double ext[4] = {(double)C.g.T * C.nranks, (double)C.g.LX, (double)C.g.LY, (double)C.g.LZ};
-  C.kappa = kappa;
+  C.kappa = kappa; C.param_gen++;
   for (int m = 0; m < 4; m++) {
     const double x = (theta ? theta[m] : 0.) * PI_ / ext[m];
     C.ka[m] = make_double2(kappa * cos(x), kappa * sin(x));
@@ -447,6 +451,10 @@ extern "C" int tmb_set_boundary(double kappa, const double theta[4]) {
 /* ka0..ka3 exactly as the caller's boundary() computed them (re,im pairs) */
 extern "C" int tmb_set_hopping_phases(const double ka_re_im[8]) {
   NEED_INIT();
+  bool same = true;
+  for (int m = 0; m < 4; m++) same = same && C.ka[m].x == ka_re_im[2 * m] && C.ka[m].y == ka_re_im[2 * m + 1];
+  if (same) return 0; /* the drop-in layer pushes the globals at every call: nothing changed, cached graphs stay valid */
+  C.param_gen++;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(ka_re_im[2 * m], ka_re_im[2 * m + 1]);
   C.kappa = sqrt(C.ka[0].x * C.ka[0].x + C.ka[0].y * C.ka[0].y);
   for (int m = 0; m < 4; m++) {
@@ -455,25 +463,26 @@ extern "C" int tmb_set_hopping_phases(const double ka_re_im[8]) {
   }
   return 0;
 }
-extern "C" int tmb_set_mu(double g_mu) { NEED_INIT(); C.mu = g_mu; return 0; }
+extern "C" int tmb_set_mu(double g_mu) { NEED_INIT(); if (C.mu != g_mu) { C.mu = g_mu; C.param_gen++; } return 0; }
 extern "C" int tmb_set_nd(double mubar, double epsbar, double invmaxev) {
   NEED_INIT(); C.mubar = mubar; C.epsbar = epsbar; C.invmaxev = invmaxev; return 0;
 }
-extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < 0 || v > 2) return fail(-7, "hop2 variant must be 0, 1 or 2"); C.hop2_variant = v; return 0; }
+extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < -1 || v > 2) return fail(-7, "hop2 variant must be -1 (automatic), 0, 1 or 2"); C.hop2_variant = v; return 0; }
 extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   NEED_INIT();
   if (hop_variant < -1 || hop_variant > 10) return fail(-7, "hop_variant must be -1 (automatic) .. 10");
   if (xblock > 0 && C.g.LX % xblock) return fail(-7, "xblock must divide LX");
-  C.hop_variant = hop_variant; C.hints = cache_hints < 0 ? -1 : (cache_hints ? 1 : 0); C.xblock = xblock;
+  C.hop_variant = hop_variant; C.hints = cache_hints < 0 ? -1 : (cache_hints ? 1 : 0); C.xblock = xblock; C.param_gen++;
   return 0;
 }
 /* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
 /* number of time-slice chunks of the pipelined host-pointer Hopping_Matrix (1..64) */
-extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 1 || n > MAXCHUNK) return fail(-7, "host chunks must be in [1, %d]", MAXCHUNK); C.host_chunks = n; return 0; }
+extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 0 || n > MAXCHUNK) return fail(-7, "host chunks must be in [0, %d] (0: two time-slices per chunk)", MAXCHUNK); C.host_chunks = n; C.param_gen++; return 0; }
 extern "C" int tmb_set_overlap(int flags) {
   NEED_INIT();
   if (flags & ~31) return fail(-7, "tmb_set_overlap: unknown bits in 0x%x (bits 0..4 are defined)", flags);
   C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1; C.cg_selfnorm = (flags & 16) ? 0 : 1;
+  C.param_gen++;
   return 0;
 }
 /* Peer-mode TIMING diagnostics, kept apart from the tuning options above because every one of them gives WRONG
@@ -516,8 +525,8 @@ extern "C" void *tmb_host_alloc(size_t bytes) {
   return p;
 }
 extern "C" int tmb_host_free(void *p) { CU(cudaFreeHost(p)); return 0; }
-extern "C" int tmb_host_register(void *p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return 0; }
-extern "C" int tmb_host_unregister(void *p) { CU(cudaHostUnregister(p)); return 0; }
+extern "C" int tmb_host_register(void *p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); hgraphs_clear(); return 0; }
+extern "C" int tmb_host_unregister(void *p) { hgraphs_clear(); CU(cudaHostUnregister(p)); return 0; }
 extern "C" int tmb_sync(void) {
   NEED_INIT(); CU(cudaStreamSynchronize(C.s_comm)); CU(cudaStreamSynchronize(C.s_main));
   if (C.p2p_err) {
@@ -559,8 +568,56 @@ extern "C" int tmb_measure_copy_gbs(size_t bytes, int reps, double *gbs) {
   return 0;
 }
 
+/* Measurement aid for bench.py's e2e leg: what this box's host link gives with pinned memory - host-to-device alone,
+ * device-to-host alone, and both directions at once (GB/s per direction) - `reps` copies of `bytes` on the two copy streams the
+ * pipelined host-pointer operators use.  The e2e figure is quoted as a fraction of the last one. */
+extern "C" int tmb_measure_pcie_gbs(size_t bytes, int reps, double *h2d, double *d2h, double *duplex_each) {
+  NEED_INIT();
+  if (bytes < 4096 || reps < 1) return fail(-7, "tmb_measure_pcie_gbs: bad arguments");
+  void *ha = nullptr, *hb = nullptr, *da = nullptr, *db = nullptr;
+  cudaEvent_t e0, e1, e2;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
+  if (cudaHostAlloc(&ha, bytes, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc(&hb, bytes, cudaHostAllocDefault) != cudaSuccess ||
+      cudaMalloc(&da, bytes) != cudaSuccess || cudaMalloc(&db, bytes) != cudaSuccess) {
+    cudaFreeHost(ha); cudaFreeHost(hb); cudaFree(da); cudaFree(db);
+    return fail(-100, "tmb_measure_pcie_gbs: out of memory");
+  }
+  memset(ha, 1, bytes); memset(hb, 2, bytes);
+  float ms = 0.f;
+  auto run = [&](bool up, bool down, double *each) -> int {
+    CU(cudaDeviceSynchronize());
+    if (up) CU(cudaMemcpyAsync(da, ha, bytes, cudaMemcpyHostToDevice, C.s_h2d));   /* warm-up */
+    if (down) CU(cudaMemcpyAsync(hb, db, bytes, cudaMemcpyDeviceToHost, C.s_d2h));
+    CU(cudaDeviceSynchronize());
+    CU(cudaEventRecord(e0, C.s_main));
+    CU(cudaStreamWaitEvent(C.s_h2d, e0, 0)); CU(cudaStreamWaitEvent(C.s_d2h, e0, 0));
+    for (int i = 0; i < reps; i++) {
+      if (up) CU(cudaMemcpyAsync(da, ha, bytes, cudaMemcpyHostToDevice, C.s_h2d));
+      if (down) CU(cudaMemcpyAsync(hb, db, bytes, cudaMemcpyDeviceToHost, C.s_d2h));
+    }
+    CU(cudaEventRecord(e1, C.s_h2d)); CU(cudaEventRecord(e2, C.s_d2h));
+    CU(cudaStreamWaitEvent(C.s_main, e1, 0)); CU(cudaStreamWaitEvent(C.s_main, e2, 0));
+    CU(cudaEventRecord(e1, C.s_main));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    *each = (double)bytes * reps / (ms * 1e-3) / 1e9;
+    return 0;
+  };
+  double a = 0., b = 0., c = 0.;
+  int rc = run(true, false, &a);
+  if (rc >= 0) rc = run(false, true, &b);
+  if (rc >= 0) rc = run(true, true, &c);
+  cudaFreeHost(ha); cudaFreeHost(hb); cudaFree(da); cudaFree(db);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  if (rc < 0) return rc;
+  if (h2d) *h2d = a; if (d2h) *d2h = b; if (duplex_each) *duplex_each = c;
+  return 0;
+}
+
+static void ensure_pinned(const void *p, size_t bytes);
 extern "C" int tmb_field_upload(void *field, const double *host) {
   NEED_INIT();
+  ensure_pinned(host, FIELD_BYTES());
   CU(cudaMemcpyAsync(C.stage, host, FIELD_BYTES(), cudaMemcpyHostToDevice, C.s_main));
   KL(tmb_launch_pack_eo(F(field), C.stage, C.g.Vh, C.s_main));
   CU(cudaStreamSynchronize(C.s_main));
@@ -568,6 +625,7 @@ extern "C" int tmb_field_upload(void *field, const double *host) {
 }
 extern "C" int tmb_field_download(double *host, const void *field) {
   NEED_INIT();
+  ensure_pinned(host, FIELD_BYTES());
   KL(tmb_launch_unpack_eo(C.stage, F(field), C.g.Vh, C.s_main));
   CU(cudaMemcpyAsync(host, C.stage, FIELD_BYTES(), cudaMemcpyDeviceToHost, C.s_main));
   CU(cudaStreamSynchronize(C.s_main));
@@ -575,6 +633,7 @@ extern "C" int tmb_field_download(double *host, const void *field) {
 }
 extern "C" int tmb_field_upload_lexic(void *even, void *odd, const double *host) {
   NEED_INIT();
+  ensure_pinned(host, 2 * FIELD_BYTES());
   CU(cudaMemcpyAsync(C.stage, host, 2 * FIELD_BYTES(), cudaMemcpyHostToDevice, C.s_main));
   KL(tmb_launch_pack_lexic(F(even), F(odd), C.stage, C.g, C.s_main));
   CU(cudaStreamSynchronize(C.s_main));
@@ -582,6 +641,7 @@ extern "C" int tmb_field_upload_lexic(void *even, void *odd, const double *host)
 }
 extern "C" int tmb_field_download_lexic(double *host, const void *even, const void *odd) {
   NEED_INIT();
+  ensure_pinned(host, 2 * FIELD_BYTES());
   KL(tmb_launch_unpack_lexic(C.stage, F(even), F(odd), C.g, C.s_main));
   CU(cudaMemcpyAsync(host, C.stage, 2 * FIELD_BYTES(), cudaMemcpyDeviceToHost, C.s_main));
   CU(cudaStreamSynchronize(C.s_main));
@@ -658,6 +718,7 @@ struct HopOpt {
   int prec = 0;               /* 0: double fields, 1: float fields + float gauge copy */
   int fin_op = -1, fin_slot = 0; /* fused finish of the dot reduction (single rank) */
   bool nocom = false;         /* Hopping_Matrix_nocom: no halo exchange, the slab wraps onto itself in T */
+  bool boundary_only = false; /* split T: exchange the faces and compute time-slices 0 and T-1 only (the interior was done in sub-ranges) */
   /* two flavours in one launch (hop_kernel NFL = 2): second flavour's fields, flavour mixing of the epilogue */
   int nfl = 1; const void *in1 = nullptr; void *out1 = nullptr; const void *p1 = nullptr;
   double nd_mu = 0., nd_eps = 0., nd_scale = 1., dot_scale = 1.;
@@ -705,6 +766,11 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.selfnorm ? 2 : (o.dotw ? 1 : 0); a.hints = eff_hints();
   a.pdl = C.pdl; a.prefetch = C.prefetch;
+  if (o.nfl == 2 && a.hints == 1 && !o.prec && !a.recon12) { /* experiment switch: gauge links of the two-flavour kernel through L1 */
+    static int l1 = -1;
+    if (l1 < 0) { const char *e = getenv("TMB_ND_L1"); l1 = (e && atoi(e) == 1) ? 1 : 0; }
+    if (l1) a.hints = 5;
+  }
   a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && fuse_fin()) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
   a.xr = a.fin_op >= 0 ? xr_tab() : nullptr;
   int np = 0;
@@ -720,7 +786,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     if (np > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", np, C.npartial);
     a.fin_total = np;
     KL(tmb_launch_hop(a, C.s_main));
-  } else if (C.p2p && o.nsites < 0 && (C.nranks == 1 || (in_arena(in) && (o.nfl == 1 || in_arena(o.in1))))) {
+  } else if (C.p2p && o.nsites < 0 && !o.boundary_only && (C.nranks == 1 || (in_arena(in) && (o.nfl == 1 || in_arena(o.in1))))) {
     /* peer mode: one launch; boundary slices read the neighbours' copies of `in` over NVLink */
     const size_t off = C.nranks == 1 ? 0 : (size_t)((const char *)in - C.arena);
     if (o.nfl == 2) {
@@ -771,7 +837,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     if (a.fin_total > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", a.fin_total, C.npartial);
     KL(tmb_launch_hop(a, C.s_comm));
     CU(cudaEventRecord(C.ev_halo, C.s_comm));
-    if (nb_int > 0) KL(tmb_launch_hop(ai, C.s_main));
+    if (nb_int > 0 && !o.boundary_only) KL(tmb_launch_hop(ai, C.s_main));
     CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
     np = nb_int + tmb_hop_grid(a);
   }
@@ -784,37 +850,113 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
  * 1536 B/site of HBM traffic).  Instead of upload -> kernel -> download, the field is cut into
  * chunks of time-slices: chunk c is computed as soon as chunks c-1, c, c+1 have arrived, and its
  * result goes back while later chunks are still coming in, so the H2D and D2H copy engines run
- * concurrently (full duplex) and the kernel time disappears behind them. */
-extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_host, int mode, double cre, double cim) {
-  NEED_INIT();
-  if (mode != 0 && mode != 1) return fail(-13, "tmb_Hopping_Matrix_host: mode must be 0 or 1");
-  SCR(din, 12); SCR(dout, 13);
-  const int T = C.g.T, S = C.g.S, Vh = C.g.Vh;
-  if (C.dist) { /* distributed T: plain upload / compute / download */
-    TRY(tmb_field_upload(din, k_host));
-    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim);
-    TRY(hop(ieo, dout, din, o));
-    return tmb_field_download(l_host, dout);
+ * concurrently (full duplex) and the kernel time disappears behind them.
+ *
+ * What is left on top of the two transfers is the fill (three chunks up before the first kernel) and the drain (one
+ * chunk down after the last), so chunks are small: two time-slices, at least ~1 MB.  That many chunks cost more host
+ * time to ENQUEUE (copy, events, pack, hop, unpack, copy: ~9 driver calls each) than they take to run, so the whole
+ * pipeline of one call is captured once as a CUDA graph, keyed on everything baked into it (host pointers, ieo, mode,
+ * coefficient, parameter generation), and replayed: the reference calls its operators with the same few field slabs
+ * over and over (init/init_spinor_field.c:38-66).
+ *
+ * With a split T the same pipeline runs on the interior time-slices 1 .. T-2 (no halo needed); the two boundary slices
+ * follow once the whole input is on the device and the projected faces have been exchanged. */
+struct HostHopGraph {
+  const void *k = nullptr; void *l = nullptr; int ieo = 0, mode = 0; double cre = 0., cim = 0.; unsigned long long gen = 0;
+  cudaGraphExec_t exec = nullptr; long long launches = 0; unsigned long long used = 0;
+};
+static std::vector<HostHopGraph> g_hgraphs;
+static unsigned long long g_hgraph_clock = 0;
+static void hgraphs_clear() {
+  for (auto &h : g_hgraphs) if (h.exec) cudaGraphExecDestroy(h.exec);
+  g_hgraphs.clear();
+}
+
+/* Pageable host memory (the reference's fields are calloc slabs, ALIGN empty unless SSE): cudaMemcpyAsync bounces it through
+ * the driver's staging buffers at a fraction of the link rate and without overlap.  The recipe is to page-lock a slab ONCE:
+ * explicitly with tmb_host_register(slab, bytes) right after the reference allocated it, or - with
+ * TMB_AUTO_PIN=1 in the environment - automatically when a range is seen for the first time (cudaHostRegister, remembered
+ * until tmb_finalize).  The automatic form is opt-in because it is only safe when the caller never frees a field while the
+ * library is initialised (true for tmLQCD's init_spinor_field / init_solver_field slabs, not for a test harness that
+ * allocates and drops buffers: a stale registration of a recycled address range would be used for DMA). */
+struct PinnedRange { char *lo, *hi; };
+static std::vector<PinnedRange> g_pinned;
+static void pinned_clear() {
+  for (auto &r : g_pinned) cudaHostUnregister(r.lo);
+  g_pinned.clear();
+}
+static void ensure_pinned(const void *p, size_t bytes) {
+  static int enabled = -1;
+  if (enabled < 0) { const char *e = getenv("TMB_AUTO_PIN"); enabled = (e && atoi(e) == 1) ? 1 : 0; }
+  if (!enabled || !p) return;
+  char *lo = (char *)p, *hi = lo + bytes;
+  for (auto &r : g_pinned) if (lo >= r.lo && hi <= r.hi) return;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return; /* already pinned / managed */
+  cudaGetLastError();
+  const size_t page = 4096;
+  lo = (char *)((size_t)lo & ~(page - 1)); hi = (char *)(((size_t)hi + page - 1) & ~(page - 1));
+  if (cudaHostRegister(lo, (size_t)(hi - lo), cudaHostRegisterDefault) == cudaSuccess) {
+    g_pinned.push_back({lo, hi});
+    hgraphs_clear(); /* graphs captured on the pageable pointer hold pageable copy nodes */
+  } else {
+    cudaGetLastError(); /* overlapping an existing registration, or not allowed: the copies still work, just slower */
   }
-  /* a chunk should carry at least ~2 MB: below that the per-chunk copies, events and launches cost more than the
-   * overlap saves (8^4: 0.39 MB per field -> one chunk, 350 -> ~40 us per call) */
-  int want = C.host_chunks;
-  const size_t min_chunk = (size_t)2 << 20;
-  if (FIELD_BYTES() / (size_t)want < min_chunk) { want = (int)(FIELD_BYTES() / min_chunk); if (want < 1) want = 1; }
-  int spc = (T + want - 1) / want; if (spc < 1) spc = 1; /* time-slices per chunk */
-  const int nchunk = (T + spc - 1) / spc;
-  if (nchunk > MAXCHUNK) return fail(-13, "too many chunks");
+}
+
+static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int mode, double cre, double cim, double2 *din, double2 *dout) {
+  const int T = C.g.T, S = C.g.S, Vh = C.g.Vh;
+  /* interior slices [t_lo, t_hi): all of them on one rank, 1 .. T-2 with a split T */
+  const int t_lo = C.dist ? 1 : 0, t_hi = C.dist ? T - 1 : T;
+  const int nt = t_hi - t_lo;
+  /* Chunk boundaries cb[0..nchunk] in time-slices.  What the pipeline adds to the two transfers is the fill (the chunks
+   * the first kernel needs: the first two and, periodic lattice, the last) and the drain (the last chunk going back), while
+   * every chunk costs a few microseconds of copy / dependency latency.  So: SMALL chunks where fill and drain are paid
+   * (`small` slices, >= 1 MB) and LARGE chunks (about an eighth of the field) in between.  tmb_set_host_chunks(n > 0)
+   * forces n equal chunks.  (Measured on this box's link, 55 GB/s one way, 47.6 GB/s per direction both ways, 24^3x48:
+   * 8 equal chunks 1.89 ms per call, 24 equal chunks 2.00 ms, 48: 2.33 ms - profiles/r02_e2e_diag.log.) */
+  int cb[MAXCHUNK + 1], nchunk = 0;
+  cb[0] = t_lo;
+  if (C.host_chunks > 0) {
+    const int spc = (nt + C.host_chunks - 1) / C.host_chunks > 0 ? (nt + C.host_chunks - 1) / C.host_chunks : 1;
+    for (int t = t_lo; t < t_hi; t += spc) cb[++nchunk] = t + spc < t_hi ? t + spc : t_hi;
+  } else {
+    /* sizes: head (small, small), body (big ...), tail (2 small, small, small).  The chunks that go up LAST decide the drain:
+     * when the upload ends, the outputs of the last two uploaded chunks and of the wrap-around chunk are still to come
+     * down (each output chunk waits for its upper neighbour's input), so the body tapers off into small chunks. */
+    int small = 1;
+    while ((size_t)small * S * 192 < ((size_t)1 << 20) && small < nt) small++;
+    int big = (nt + 5) / 6; if (big < small) big = small;
+    const int nhead = C.dist ? 1 : 2; /* a split T has no wrap: the first kernel needs the (already sent) boundary slice and two chunks */
+    const int tail[3] = {2 * small, small, small};
+    int t = t_lo, ntail = 0, tail_len = 0;
+    while (ntail < 3 && nt - (nhead * small + tail_len + tail[ntail]) >= big) tail_len += tail[ntail++];
+    for (int h = 0; h < nhead && t_hi - tail_len - t > small; h++) { t += small; cb[++nchunk] = t; }
+    while (t_hi - tail_len - t > big + big / 2) { t += big; cb[++nchunk] = t; }
+    if (t < t_hi - tail_len) { t = t_hi - tail_len; cb[++nchunk] = t; }
+    for (int k = 0; k < ntail; k++) { t += tail[k]; cb[++nchunk] = t; }
+  }
+  if (nchunk > MAXCHUNK - 1) return fail(-13, "too many chunks");
   double2 *in_aos = C.stage, *out_aos = C.stage + (size_t)12 * Vh;
   const double2 *hk = (const double2 *)k_host; double2 *hl = (double2 *)l_host;
-  CU(cudaStreamSynchronize(C.s_main));
-  auto first = [&](int c) { return c * spc * S; };
-  auto count = [&](int c) { int t1 = (c + 1) * spc; if (t1 > T) t1 = T; return (t1 - c * spc) * S; };
-  /* upload order: the three chunks the first output chunk needs, then the rest */
+  auto first = [&](int c) { return cb[c] * S; };
+  auto count = [&](int c) { return (cb[c + 1] - cb[c]) * S; };
+  /* fork: the copy streams join the work of s_main (also what makes them part of a graph capture) */
+  CU(cudaEventRecord(C.ev_in, C.s_main));
+  CU(cudaStreamWaitEvent(C.s_h2d, C.ev_in, 0));
+  CU(cudaStreamWaitEvent(C.s_d2h, C.ev_in, 0));
+  /* upload order: the chunks the first output chunk needs, then the rest; with a split T the two boundary slices come
+   * first of all (their faces have the longest way to go) */
+  if (C.dist) {
+    CU(cudaMemcpyAsync(in_aos, hk, (size_t)S * 192, cudaMemcpyHostToDevice, C.s_h2d));
+    CU(cudaMemcpyAsync(in_aos + (size_t)(T - 1) * S * 12, hk + (size_t)(T - 1) * S * 12, (size_t)S * 192, cudaMemcpyHostToDevice, C.s_h2d));
+    CU(cudaEventRecord(C.ev_halo, C.s_h2d));
+  }
   int order[MAXCHUNK], no = 0;
-  order[no++] = 0;
+  if (nchunk > 0) order[no++] = 0;
   if (nchunk > 1) order[no++] = 1;
-  if (nchunk > 2) order[no++] = nchunk - 1;
-  for (int c = 2; c < nchunk - 1; c++) order[no++] = c;
+  if (nchunk > 2 && !C.dist) order[no++] = nchunk - 1;
+  for (int c = 2; c < nchunk - (C.dist ? 0 : 1); c++) order[no++] = c;
   for (int q = 0; q < no; q++) {
     const int c = order[q];
     CU(cudaMemcpyAsync(in_aos + (size_t)first(c) * 12, hk + (size_t)first(c) * 12, (size_t)count(c) * 192,
@@ -822,16 +964,22 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
     CU(cudaEventRecord(C.ev_up[c], C.s_h2d));
   }
   bool packed[MAXCHUNK] = {false};
+  if (C.dist) { /* the boundary slices are packed first: interior chunks 0 and nchunk-1 read them as neighbours */
+    CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
+    KL(tmb_launch_pack_eo_range(din, in_aos, Vh, 0, S, C.s_main));
+    KL(tmb_launch_pack_eo_range(din, in_aos, Vh, (T - 1) * S, S, C.s_main));
+  }
   for (int c = 0; c < nchunk; c++) {
-    const int need[3] = {(c + nchunk - 1) % nchunk, c, (c + 1) % nchunk};
+    int need[3] = {c - 1, c, c + 1};
+    if (!C.dist) { need[0] = (c + nchunk - 1) % nchunk; need[2] = (c + 1) % nchunk; }
     for (int q = 0; q < 3; q++) {
       const int n = need[q];
-      if (packed[n]) continue;
+      if (n < 0 || n >= nchunk || packed[n]) continue;
       CU(cudaStreamWaitEvent(C.s_main, C.ev_up[n], 0));
       KL(tmb_launch_pack_eo_range(din, in_aos, Vh, first(n), count(n), C.s_main));
       packed[n] = true;
     }
-    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.site0 = first(c); o.nsites = count(c);
+    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.site0 = first(c); o.nsites = count(c); o.nocom = true;
     TRY(hop(ieo, dout, din, o));
     KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, first(c), count(c), C.s_main));
     CU(cudaEventRecord(C.ev_done[c], C.s_main));
@@ -839,7 +987,129 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
     CU(cudaMemcpyAsync(hl + (size_t)first(c) * 12, out_aos + (size_t)first(c) * 12, (size_t)count(c) * 192,
                        cudaMemcpyDeviceToHost, C.s_d2h));
   }
-  CU(cudaStreamSynchronize(C.s_d2h));
+  if (C.dist) {
+    /* boundary slices 0 and T-1: faces projected and exchanged (half-spinors, xchange_halffield's idea), then the halo
+     * kernel on those two slices only */
+    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.boundary_only = true;
+    TRY(hop(ieo, dout, din, o));
+    KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, 0, S, C.s_main));
+    KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, (T - 1) * S, S, C.s_main));
+    CU(cudaEventRecord(C.ev_done[MAXCHUNK - 1], C.s_main));
+    CU(cudaStreamWaitEvent(C.s_d2h, C.ev_done[MAXCHUNK - 1], 0));
+    CU(cudaMemcpyAsync(hl, out_aos, (size_t)S * 192, cudaMemcpyDeviceToHost, C.s_d2h));
+    CU(cudaMemcpyAsync(hl + (size_t)(T - 1) * S * 12, out_aos + (size_t)(T - 1) * S * 12, (size_t)S * 192, cudaMemcpyDeviceToHost, C.s_d2h));
+  }
+  /* join */
+  CU(cudaEventRecord(C.ev_chk[0], C.s_d2h));
+  CU(cudaEventRecord(C.ev_chk[1], C.s_h2d));
+  CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[0], 0));
+  CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[1], 0));
+  return 0;
+}
+
+/* Zero-copy form of the pipeline (one rank, both buffers pinned and mapped): no copy engines and no AoS staging - the
+ * pack kernel of chunk c reads the caller's buffer across PCIe and writes the device layout, the unpack kernel writes the
+ * result straight into the caller's buffer.  Kernels cost a few microseconds each where a copy costs ~17, so the chunks can
+ * be as small as two time-slices and fill and drain shrink with them. */
+static int host_hop_enqueue_zc(int ieo, double2 *l_dev, const double2 *k_dev, int mode, double cre, double cim, double2 *din, double2 *dout) {
+  const int T = C.g.T, S = C.g.S, Vh = C.g.Vh;
+  int spc = 1;
+  while ((size_t)spc * S * 192 < ((size_t)2 << 20) && spc < T) spc++;
+  if (C.host_chunks > 0) spc = (T + C.host_chunks - 1) / C.host_chunks;
+  int nchunk = (T + spc - 1) / spc;
+  if (nchunk > MAXCHUNK) { spc = (T + MAXCHUNK - 1) / MAXCHUNK; nchunk = (T + spc - 1) / spc; }
+  static int ctas = 0;
+  if (!ctas) { const char *e = getenv("TMB_E2E_CTAS"); ctas = e ? atoi(e) : 32; if (ctas < 1) ctas = 1; if (ctas > 592) ctas = 592; }
+  auto first = [&](int c) { return c * spc * S; };
+  auto count = [&](int c) { int t1 = (c + 1) * spc; if (t1 > T) t1 = T; return (t1 - c * spc) * S; };
+  CU(cudaEventRecord(C.ev_in, C.s_main));
+  CU(cudaStreamWaitEvent(C.s_h2d, C.ev_in, 0));
+  CU(cudaStreamWaitEvent(C.s_d2h, C.ev_in, 0));
+  int order[MAXCHUNK], no = 0;
+  order[no++] = 0;
+  if (nchunk > 1) order[no++] = 1;
+  if (nchunk > 2) order[no++] = nchunk - 1;
+  for (int c = 2; c < nchunk - 1; c++) order[no++] = c;
+  for (int q = 0; q < no; q++) {
+    const int c = order[q];
+    KL(tmb_launch_pack_host_range(din, k_dev, Vh, first(c), count(c), ctas, C.s_h2d));
+    CU(cudaEventRecord(C.ev_up[c], C.s_h2d));
+  }
+  bool waited[MAXCHUNK] = {false};
+  for (int c = 0; c < nchunk; c++) {
+    const int need[3] = {(c + nchunk - 1) % nchunk, c, (c + 1) % nchunk};
+    for (int q = 0; q < 3; q++)
+      if (!waited[need[q]]) { CU(cudaStreamWaitEvent(C.s_main, C.ev_up[need[q]], 0)); waited[need[q]] = true; }
+    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.site0 = first(c); o.nsites = count(c); o.nocom = true;
+    TRY(hop(ieo, dout, din, o));
+    CU(cudaEventRecord(C.ev_done[c], C.s_main));
+    CU(cudaStreamWaitEvent(C.s_d2h, C.ev_done[c], 0));
+    KL(tmb_launch_unpack_host_range(l_dev, dout, Vh, first(c), count(c), ctas, C.s_d2h));
+  }
+  CU(cudaEventRecord(C.ev_chk[0], C.s_d2h));
+  CU(cudaEventRecord(C.ev_chk[1], C.s_h2d));
+  CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[0], 0));
+  CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[1], 0));
+  return 0;
+}
+/* the device-side address of a pinned, mapped host buffer; nullptr for pageable memory */
+static void *mapped_host_pointer(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_host, int mode, double cre, double cim) {
+  NEED_INIT();
+  if (mode != 0 && mode != 1) return fail(-13, "tmb_Hopping_Matrix_host: mode must be 0 or 1");
+  if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
+  SCR(din, 12); SCR(dout, 13);
+  if (C.compression == 12) TRY(ensure_gauge12(0)); /* nothing may allocate or synchronise inside a capture */
+  ensure_pinned(k_host, FIELD_BYTES()); ensure_pinned(l_host, FIELD_BYTES());
+  CU(cudaStreamSynchronize(C.s_main));
+  /* a split T exchanges faces through NCCL inside the pipeline: not captured (NCCL calls stay out of graphs here) */
+  const bool use_graph = C.cg_graph && !C.dist;
+  static int zc_env = -1;
+  if (zc_env < 0) { const char *e = getenv("TMB_E2E_ZEROCOPY"); zc_env = e ? atoi(e) : 0; }
+  double2 *l_dev = nullptr; const double2 *k_dev = nullptr;
+  const bool zc = zc_env && !C.dist && (l_dev = (double2 *)mapped_host_pointer(l_host)) != nullptr &&
+                  (k_dev = (const double2 *)mapped_host_pointer(k_host)) != nullptr;
+  auto enqueue = [&]() { return zc ? host_hop_enqueue_zc(ieo, l_dev, k_dev, mode, cre, cim, din, dout)
+                                   : host_hop_enqueue(ieo, l_host, k_host, mode, cre, cim, din, dout); };
+  if (!use_graph) {
+    TRY(enqueue());
+    CU(cudaStreamSynchronize(C.s_main));
+    return 0;
+  }
+  HostHopGraph *hit = nullptr;
+  for (auto &h : g_hgraphs)
+    if (h.k == k_host && h.l == l_host && h.ieo == ieo && h.mode == mode && h.cre == cre && h.cim == cim && h.gen == C.param_gen) { hit = &h; break; }
+  if (!hit) {
+    if (g_hgraphs.size() >= 32) { /* forget the least recently used one */
+      size_t lru = 0;
+      for (size_t i = 1; i < g_hgraphs.size(); i++) if (g_hgraphs[i].used < g_hgraphs[lru].used) lru = i;
+      cudaGraphExecDestroy(g_hgraphs[lru].exec);
+      g_hgraphs.erase(g_hgraphs.begin() + lru);
+    }
+    const long long l0 = C.launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(C.s_main, cudaStreamCaptureModeRelaxed) != cudaSuccess) return fail(-100, "cudaStreamBeginCapture failed");
+    const int rc = enqueue();
+    cudaError_t e = cudaStreamEndCapture(C.s_main, &graph);
+    HostHopGraph h;
+    h.launches = C.launches - l0; C.launches = l0;
+    if (rc < 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(-100, "capture of the host-pointer hop failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(-100, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    h.k = k_host; h.l = l_host; h.ieo = ieo; h.mode = mode; h.cre = cre; h.cim = cim; h.gen = C.param_gen;
+    g_hgraphs.push_back(h);
+    hit = &g_hgraphs.back();
+  }
+  hit->used = ++g_hgraph_clock;
+  if (cudaGraphLaunch(hit->exec, C.s_main) != cudaSuccess) return fail(-101, "cudaGraphLaunch failed");
+  C.launches += hit->launches;
   CU(cudaStreamSynchronize(C.s_main));
   return 0;
 }
@@ -1077,36 +1347,58 @@ extern "C" int tmb_M_oo_sub_g5_ndpsi(void *ls, void *lc, const void *ks, const v
 }
 static int hop0(int ieo, double2 *l, const double2 *k) { HopOpt o; return hop(ieo, l, k, o); }
 
-static int hop2_legacy(int ieo, double2 *o0, double2 *o1, const double2 *i0, const double2 *i1, int mode, const double2 *p0,
-                       const double2 *p1, double mu, double eps, double scale);
+struct NdDot;
+static int hop2_legacy(int ieo, void *o0, void *o1, const void *i0, const void *i1, int mode, const void *p0,
+                       const void *p1, double mu, double eps, double scale, int prec, const tmb_cg_state *st, const NdDot *dot);
 /* Two-flavour fused path: every Hopping_Matrix pair of tm_operators_nd.c is ONE
  * launch that streams the links once for both flavours, with M_ee_inv_ndpsi / M_oo_sub_g5_ndpsi and the
  * phmc_invmaxev scaling in its epilogue.  mode 1: out = M_ee_inv_nd(H in0, H in1); mode 2: out = scale g5(M_oo(p) - H in). */
-static bool nd_fused() { return C.hop2_variant == 2 || (!C.dist && C.compression == 18); }
+/* Which two-flavour kernel: the NFL = 2 instantiation of hop_kernel serves every precision, compression and communication
+ * mode; round 1's one-thread-two-flavours kernel (tmb_force.cu) is 13 % faster where it applies - one rank, 18-real links,
+ * double (32^3x64: 1.60 against 1.84 ms per Qtm_pm_ndpsi, profiles/r02_section_nd_first.json) - and is taken there. */
+static bool nd_legacy_ok() { return !C.dist && C.compression == 18; }
+static bool nd_nfl2(int prec) {
+  if (C.hop2_variant == 2) return true;
+  if (C.hop2_variant == 0) return !nd_legacy_ok() && prec; /* forced: double falls back to single hops where the kernel does not apply */
+  if (C.hop2_variant == 1) return prec != 0;               /* the lane-paired kernel is double only */
+  return !nd_legacy_ok();
+}
+static bool nd_fused() { return nd_nfl2(0) || nd_legacy_ok(); }
 struct NdDot { const tmb_cg_state *st = nullptr; int fin_op = -1, fin_slot = 0; double scale = 1.; int *np = nullptr; bool on = false; };
 static int hop2(int ieo, void *o0, void *o1, const void *i0, const void *i1, int mode, const void *p0,
                 const void *p1, double mu, double eps, double scale, int prec = 0, const tmb_cg_state *st = nullptr,
                 const NdDot *dot = nullptr) {
-  if (C.hop2_variant == 2 || prec) { /* hop_kernel with NFL = 2: every precision, compression and communication mode */
+  if (nd_nfl2(prec)) { /* hop_kernel with NFL = 2: every precision, compression and communication mode */
     HopOpt o; o.nfl = 2; o.mode = mode; o.prec = prec; o.in1 = i1; o.out1 = o1; o.p = p0; o.p1 = p1; o.st = st;
     o.nd_mu = mu; o.nd_eps = eps; o.nd_scale = scale;
     if (dot && dot->on) { o.selfnorm = true; o.fin_op = dot->fin_op; o.fin_slot = dot->fin_slot; o.dot_scale = dot->scale; o.npartial = dot->np; }
     return hop(ieo, o0, i0, o);
   }
-  if (dot && dot->on) return fail(-7, "the fused two-flavour norm needs tmb_set_hop2_variant(2)");
-  return hop2_legacy(ieo, F(o0), F(o1), F(i0), F(i1), mode, F(p0), F(p1), mu, eps, scale);
+  return hop2_legacy(ieo, o0, o1, i0, i1, mode, p0, p1, mu, eps, scale, prec, st, dot);
 }
 /* the round-1 kernels (tmb_force.cu: one thread carries both flavours, variant 0; lane-paired flavours, variant 1): one
  * rank, 18-real links, double precision only */
-static int hop2_legacy(int ieo, double2 *o0, double2 *o1, const double2 *i0, const double2 *i1, int mode, const double2 *p0,
-                       const double2 *p1, double mu, double eps, double scale) {
+static int hop2_legacy(int ieo, void *o0, void *o1, const void *i0, const void *i1, int mode, const void *p0,
+                       const void *p1, double mu, double eps, double scale, int prec, const tmb_cg_state *st, const NdDot *dot) {
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
   if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
+  if (!nd_legacy_ok()) return fail(-7, "this two-flavour kernel runs on one rank with 18-real links only");
+  if (prec) TRY(ensure_gauge32());
   tmb_hop2_launch a;
   memset(&a, 0, sizeof(a));
-  a.in0 = i0; a.in1 = i1; a.out0 = o0; a.out1 = o1; a.p0 = p0; a.p1 = p1; a.U = C.U; a.g = C.g; a.par = ieo ? 1 : 0;
+  a.in0 = i0; a.in1 = i1; a.out0 = o0; a.out1 = o1; a.p0 = p0; a.p1 = p1; a.g = C.g; a.par = ieo ? 1 : 0;
+  a.prec = prec; a.U = prec ? (const void *)C.U32 : (const void *)C.U;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
-  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = eff_hints(); a.variant = C.hop2_variant;
+  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = eff_hints(); a.variant = (C.hop2_variant == 1 && !prec) ? 1 : 0;
+  a.st = st; a.fin_op = -1;
+  if (dot && dot->on) {
+    if (a.variant == 1) return fail(-7, "the lane-paired two-flavour kernel has no fused norm");
+    a.dot = 2; a.dot_scale = dot->scale; a.partial = C.partial; a.st_fin = C.st;
+    a.fin_op = fuse_fin() ? dot->fin_op : -1; a.fin_slot = dot->fin_slot; a.xr = a.fin_op >= 0 ? xr_tab() : nullptr;
+    const int np = tmb_hop2_grid(a);
+    if (np > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", np, C.npartial);
+    if (dot->np) *dot->np = np;
+  }
   KL(tmb_launch_hop2(a, C.s_main));
   return 0;
 }

@@ -800,14 +800,31 @@ void addto_32(spinor *const Q, const spinor32 *const R, const int N) {
   }
 }
 /* solver/solver_field.c:31-71: host scratch for callers that drive their own recurrences */
+/* solver/solver_field.c:31-66: one slab of nr fields.  This library owns the allocation (it replaces solver_field.o), so the
+ * slab is page-locked host memory: solver fields are what a generic-f solver hands to the per-call operators over and over */
+#define MAX_PINNED_SLABS 64
+static void *pinned_slabs[MAX_PINNED_SLABS];
 int init_solver_field(spinor ***const solver_field, const int V, const int nr) {
   if ((*solver_field = (spinor **)malloc((size_t)(nr + 1) * sizeof(spinor *))) == NULL) return 2;
-  if (((*solver_field)[nr] = (spinor *)calloc((size_t)nr * V + 1, sizeof(spinor))) == NULL) return 1;
+  const size_t bytes = ((size_t)nr * V + 1) * sizeof(spinor);
+  spinor *slab = NULL;
+  if (dropin_up) {
+    for (int i = 0; i < MAX_PINNED_SLABS && !slab; i++)
+      if (!pinned_slabs[i] && (slab = (spinor *)tmb_host_alloc(bytes)) != NULL) { pinned_slabs[i] = slab; memset(slab, 0, bytes); break; }
+  }
+  if (!slab && (slab = (spinor *)calloc((size_t)nr * V + 1, sizeof(spinor))) == NULL) return 1;
+  (*solver_field)[nr] = slab;
   (*solver_field)[0] = (*solver_field)[nr];
   for (int i = 1; i < nr; i++) (*solver_field)[i] = (*solver_field)[i - 1] + V;
   return 0;
 }
-void finalize_solver(spinor **solver_field, const int nr) { free(solver_field[nr]); free(solver_field); }
+void finalize_solver(spinor **solver_field, const int nr) {
+  int pinned = 0;
+  for (int i = 0; i < MAX_PINNED_SLABS; i++)
+    if (pinned_slabs[i] && pinned_slabs[i] == (void *)solver_field[nr]) { pinned_slabs[i] = NULL; pinned = 1; }
+  if (pinned) tmb_host_free(solver_field[nr]); else free(solver_field[nr]);
+  free(solver_field);
+}
 /* tm_operators_nd.c:508, :698, :599 */
 void H_eo_tm_ndpsi(spinor *const ls, spinor *const lc, spinor *const ks, spinor *const kc, const int ieo) {
   sync_globals(); up(0, ks); up(1, kc);

@@ -7,13 +7,16 @@
  * contiguous across the warp.  Bandwidth-bound like the hopping kernel (1.25 flop/B): algorithmic
  * bytes per link-owner site 192 (spinor, perfect reuse) + 4*144 (links) + 2*4*64 (df r/w) = 1280.
  */
-#include "tmb_kernels.h"
-#include "tmb_site.cuh"
+#include "tmb_hop.cuh" /* block_sum, finish_last_block for the two-flavour kernel's fused norm */
 
 template <int DIST>
 __global__ void __launch_bounds__(128, 3) deriv_kernel(const tmb_deriv_launch a) {
-  const int q = blockIdx.y;                       /* parity of the link owner */
-  const int w = blockIdx.x * 128 + threadIdx.x;
+  /* The two parities of the same 128-site range are neighbours in the grid (q is the fastest block index): the CTA of parity
+   * ieo reads l locally and k at the +mu neighbours, its sibling k locally and l at the neighbours, so both fields come out of
+   * L2 for one of the two and DRAM sees every spinor once.  With the parities as two halves of the grid (round 1) each field
+   * crossed DRAM twice: 14 % traffic above the algorithmic 1280 B per link-owner site. */
+  const int q = blockIdx.x & 1;                   /* parity of the link owner */
+  const int w = (blockIdx.x >> 1) * 128 + threadIdx.x;
   if (w >= a.nt * a.g.S) return;
   const int i = a.t0 * a.g.S + w;
   tmb_deriv_fields f;
@@ -26,7 +29,7 @@ __global__ void __launch_bounds__(128, 3) deriv_kernel(const tmb_deriv_launch a)
 cudaError_t tmb_launch_deriv(const tmb_deriv_launch &a, cudaStream_t s) {
   const int n = a.nt * a.g.S;
   if (n <= 0) return cudaSuccess;
-  dim3 grid((n + 127) / 128, 2);
+  const int grid = 2 * ((n + 127) / 128);
   if (a.dist) deriv_kernel<1><<<grid, 128, 0, s>>>(a);
   else deriv_kernel<0><<<grid, 128, 0, s>>>(a);
   return cudaGetLastError();
@@ -112,44 +115,70 @@ cudaError_t tmb_launch_pack_gauge_first_slice(double2 *out, const double2 *U, tm
 
 /* ------------------------------------------------------------------ two-flavour hopping kernel
  * (lives in this translation unit to keep tmb_kernels.cu's compile time down) */
-template <int MODE, int HINTS>
-__global__ void __launch_bounds__(128, 2) hop2_kernel(const tmb_hop2_launch a) {
+/* One thread carries BOTH flavours of a site: every link is loaded once into registers and applied to the two projected
+ * spinors.  V2 = double2: 254 registers, 2 CTAs of 128 per SM; V2 = float2 (Qtm_pm_ndpsi_32, the operator of
+ * rg_mixed_cg_her_nd's inner loops): half the registers per value, 4 CTAs per SM.  DOT == 2: the partial sums of
+ * dot_scale (|out0|^2 + |out1|^2) and, for the CTA that takes the last ticket, the reduction finish with the CG
+ * bookkeeping (tmb_hop.cuh) - the <p, A p> of cg_her_nd out of the second launch of Qtm_pm_ndpsi. */
+template <class V2, int MODE, int DOT, int HINTS, int MINB>
+__global__ void __launch_bounds__(128, MINB) hop2_kernel(const tmb_hop2_launch a) {
+  typedef typename tmb_real<V2>::type R;
+  if (a.st != nullptr && a.st->converged) return;
   const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= a.g.Vh) return;
-  tmb_policies pol;
-  pol.stream = tmb_policy_evict_first();
-  pol.reuse = tmb_policy_evict_last();
-  double2 r0[12], r1[12];
-  tmb_hop_site2<HINTS>(r0, r1, (const double2 *)a.in0, (const double2 *)a.in1, (const double2 *)a.U, a.g, a.par, i, a.ka, pol);
-  double2 *o0 = (double2 *)a.out0, *o1 = (double2 *)a.out1;
-  const size_t Vh = a.g.Vh;
-  if (MODE == 1) {
-    const double nrm = 1. / (1. + a.mu * a.mu - a.eps * a.eps);
+  double dsum = 0.;
+  if (i < a.g.Vh) {
+    tmb_policies pol;
+    pol.stream = tmb_policy_evict_first();
+    pol.reuse = tmb_policy_evict_last();
+    V2 ka[4];
 #pragma unroll
-    for (int c = 0; c < 12; c++) {
-      double2 ls, lc;
-      tmb_nd_mee_inv_regs(ls, lc, r0[c], r1[c], c, a.mu, a.eps, nrm);
-      r0[c] = ls; r1[c] = lc;
+    for (int m = 0; m < 4; m++) ka[m] = cvt2<V2>(a.ka[m]);
+    V2 r0[12], r1[12];
+    tmb_hop_site2<HINTS>(r0, r1, (const V2 *)a.in0, (const V2 *)a.in1, (const V2 *)a.U, a.g, a.par, i, ka, pol);
+    V2 *o0 = (V2 *)a.out0, *o1 = (V2 *)a.out1;
+    const size_t Vh = a.g.Vh;
+    const R mu = (R)a.mu, eps = (R)a.eps, scale = (R)a.scale;
+    if (MODE == 1) {
+      const double nrm = 1. / (1. + a.mu * a.mu - a.eps * a.eps);
+#pragma unroll
+      for (int c = 0; c < 12; c++) {
+        V2 ls, lc;
+        tmb_nd_mee_inv_regs(ls, lc, r0[c], r1[c], c, a.mu, a.eps, nrm);
+        r0[c] = ls; r1[c] = lc;
+      }
+    } else if (MODE == 2) {
+      const V2 *p0 = (const V2 *)a.p0, *p1 = (const V2 *)a.p1;
+      V2 q0[12], q1[12]; /* all operand loads before the first store: out may alias p (see hop_kernel) */
+#pragma unroll
+      for (int c = 0; c < 12; c++) { q0[c] = p0[c * Vh + i]; q1[c] = p1[c * Vh + i]; }
+#pragma unroll
+      for (int c = 0; c < 12; c++) {
+        const bool up = c < 6;
+        const V2 zs = mk2<V2>((R)1, up ? -mu : mu), zc = c_conj(zs);
+        V2 x = c_mul(zs, q0[c]); x.x += eps * q1[c].x; x.y += eps * q1[c].y;
+        V2 y = c_mul(zc, q1[c]); y.x += eps * q0[c].x; y.y += eps * q0[c].y;
+        const V2 d0 = up ? c_sub(x, r0[c]) : c_sub(r0[c], x), d1 = up ? c_sub(y, r1[c]) : c_sub(r1[c], y);
+        r0[c] = mk2<V2>(scale * d0.x, scale * d0.y); r1[c] = mk2<V2>(scale * d1.x, scale * d1.y);
+      }
     }
-  } else if (MODE == 2) {
-    const double2 *p0 = (const double2 *)a.p0, *p1 = (const double2 *)a.p1;
-    double2 q0[12], q1[12]; /* all operand loads before the first store: out may alias p (see hop_kernel) */
+    if (DOT == 2) {
 #pragma unroll
-    for (int c = 0; c < 12; c++) { q0[c] = p0[c * Vh + i]; q1[c] = p1[c * Vh + i]; }
+      for (int c = 0; c < 12; c++) {
+        dsum += (double)r0[c].x * (double)r0[c].x; dsum += (double)r0[c].y * (double)r0[c].y;
+        dsum += (double)r1[c].x * (double)r1[c].x; dsum += (double)r1[c].y * (double)r1[c].y;
+      }
+      dsum *= a.dot_scale;
+    }
 #pragma unroll
     for (int c = 0; c < 12; c++) {
-      const bool up = c < 6;
-      const double2 zs = make_double2(1., up ? -a.mu : a.mu), zc = c_conj(zs);
-      double2 x = c_mul(zs, q0[c]); x.x += a.eps * q1[c].x; x.y += a.eps * q1[c].y;
-      double2 y = c_mul(zc, q1[c]); y.x += a.eps * q0[c].x; y.y += a.eps * q0[c].y;
-      const double2 d0 = up ? c_sub(x, r0[c]) : c_sub(r0[c], x), d1 = up ? c_sub(y, r1[c]) : c_sub(r1[c], y);
-      r0[c] = make_double2(a.scale * d0.x, a.scale * d0.y); r1[c] = make_double2(a.scale * d1.x, a.scale * d1.y);
+      tmb_store_out<HINTS & 1>(o0 + c * Vh + i, r0[c], pol);
+      tmb_store_out<HINTS & 1>(o1 + c * Vh + i, r1[c], pol);
     }
   }
-#pragma unroll
-  for (int c = 0; c < 12; c++) {
-    tmb_store_out<HINTS & 1>(o0 + c * Vh + i, r0[c], pol);
-    tmb_store_out<HINTS & 1>(o1 + c * Vh + i, r1[c], pol);
+  if (DOT) {
+    const double sblk = block_sum<128>(dsum);
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = sblk;
+    if (a.fin_op >= 0) finish_last_block<128>(a.partial, (int)gridDim.x, a.st_fin, a.fin_slot, a.fin_op, a.xr);
   }
 }
 /* Lane-paired variant (tmb_set_hop2_variant(1); measured SLOWER than hop2_kernel at 32^3x64: 450 vs 413 us per
@@ -207,9 +236,26 @@ __global__ void __launch_bounds__(128, 3) hop2p_kernel(const tmb_hop2_launch a) 
 #pragma unroll
   for (int c = 0; c < 12; c++) tmb_store_out<HINTS & 1>(out + c * Vh + i, r[c], pol);
 }
+template <class V2, int HINTS, int MINB>
+static cudaError_t hop2_go1(const tmb_hop2_launch &a, cudaStream_t s) {
+  const int grid = (a.g.Vh + 127) / 128;
+  if (a.dot) {
+    if (a.mode != 2 || a.dot != 2) return cudaErrorInvalidValue;
+    hop2_kernel<V2, 2, 2, HINTS, MINB><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+  }
+  switch (a.mode) {
+    case 0: hop2_kernel<V2, 0, 0, HINTS, MINB><<<grid, 128, 0, s>>>(a); break;
+    case 1: hop2_kernel<V2, 1, 0, HINTS, MINB><<<grid, 128, 0, s>>>(a); break;
+    case 2: hop2_kernel<V2, 2, 0, HINTS, MINB><<<grid, 128, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
 template <int HINTS>
 static cudaError_t hop2_go(const tmb_hop2_launch &a, cudaStream_t s) {
   if (a.variant == 1) { /* lane-paired */
+    if (a.prec || a.dot) return cudaErrorInvalidValue;
     const int gridp = (int)(((size_t)2 * a.g.Vh + 127) / 128);
     switch (a.mode) {
       case 0: hop2p_kernel<0, HINTS><<<gridp, 128, 0, s>>>(a); break;
@@ -219,13 +265,10 @@ static cudaError_t hop2_go(const tmb_hop2_launch &a, cudaStream_t s) {
     }
     return cudaGetLastError();
   }
-  const int grid = (a.g.Vh + 127) / 128;
-  switch (a.mode) {
-    case 0: hop2_kernel<0, HINTS><<<grid, 128, 0, s>>>(a); break;
-    case 1: hop2_kernel<1, HINTS><<<grid, 128, 0, s>>>(a); break;
-    case 2: hop2_kernel<2, HINTS><<<grid, 128, 0, s>>>(a); break;
-    default: return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  return hop2_go1<double2, HINTS, 2>(a, s);
 }
-cudaError_t tmb_launch_hop2(const tmb_hop2_launch &a, cudaStream_t s) { return a.hints ? hop2_go<1>(a, s) : hop2_go<0>(a, s); }
+int tmb_hop2_grid(const tmb_hop2_launch &a) { return (a.g.Vh + 127) / 128; }
+cudaError_t tmb_launch_hop2(const tmb_hop2_launch &a, cudaStream_t s) {
+  if (a.prec) return hop2_go1<float2, 1, 4>(a, s); /* single precision: cache-policy loads always on */
+  return a.hints ? hop2_go<1>(a, s) : hop2_go<0>(a, s);
+}

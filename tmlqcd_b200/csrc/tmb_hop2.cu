@@ -28,5 +28,6 @@ cudaError_t tmb_launch_hop_nd(const tmb_hop_launch &a, cudaStream_t s) {
     return nd_dist<float2, 1, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
   }
   if (a.recon12) return nd_dist<double2, 3, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
+  if (a.hints == 5) return nd_dist<double2, 5, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s); /* policies + gauge links through L1 */
   return a.hints ? nd_dist<double2, 1, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s) : nd_dist<double2, 0, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
 }

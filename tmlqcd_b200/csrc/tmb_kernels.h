@@ -145,6 +145,9 @@ cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStr
 cudaError_t tmb_launch_unpack_eo(double2 *aos, const double2 *soa, int Vh, cudaStream_t s);
 cudaError_t tmb_launch_pack_eo_range(double2 *soa, const double2 *aos, int Vh, int i0, int n, cudaStream_t s);
 cudaError_t tmb_launch_unpack_eo_range(double2 *aos, const double2 *soa, int Vh, int i0, int n, cudaStream_t s);
+/* the same with `aos` in pinned host memory, accessed by the kernel itself across PCIe (zero-copy) */
+cudaError_t tmb_launch_pack_host_range(double2 *soa, const double2 *aos_host, int Vh, int i0, int n, int ctas, cudaStream_t s);
+cudaError_t tmb_launch_unpack_host_range(double2 *aos_host, const double2 *soa, int Vh, int i0, int n, int ctas, cudaStream_t s);
 cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_pack_lexic_f(float2 *even, float2 *odd, const float2 *lex, tmb_geom g, cudaStream_t s);
@@ -194,5 +197,9 @@ struct tmb_hop2_launch {
   tmb_geom g; int par; double2 ka[4];
   int mode; double mu, eps, scale; int hints;
   int variant; /* 0: one thread carries both flavours (hop2_kernel, default), 1: lane-paired flavours (hop2p_kernel) */
+  int prec;    /* 1: float fields and float links (hop2_kernel only) */
+  /* hop2_kernel, mode 2 only: dot == 2 accumulates dot_scale (|out0|^2 + |out1|^2) into partial[]; fin_op >= 0: fused finish */
+  int dot; double dot_scale; double *partial; const tmb_cg_state *st; tmb_cg_state *st_fin; int fin_op, fin_slot; const tmb_xred_table *xr;
 };
 cudaError_t tmb_launch_hop2(const tmb_hop2_launch &a, cudaStream_t s);
+int tmb_hop2_grid(const tmb_hop2_launch &a);

@@ -50,6 +50,18 @@ __device__ __forceinline__ float2 tmb_ld_stream(const float2 *p, unsigned long l
       : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+/* gauge links of the two-flavour kernel: read by the two flavour groups of a CTA within a short time -> allocate in L1
+ * (the second group's request should hit there), still evict-first in L2 */
+__device__ __forceinline__ double2 tmb_ld_stream_l1(const double2 *p, unsigned long long pol) {
+  double2 v;
+  asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 tmb_ld_stream_l1(const float2 *p, unsigned long long pol) {
+  float2 v;
+  asm("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
 /* neighbour spinors: reused by 8 output sites -> keep in L1/L2 */
 __device__ __forceinline__ double2 tmb_ld_reuse(const double2 *p, unsigned long long pol) {
   double2 v;
@@ -95,6 +107,7 @@ struct tmb_policies { unsigned long long stream, reuse; };
 template <int HINTS, class V2>
 TMB_HD V2 tmb_load_gauge(const V2 *p, const tmb_policies &pol) {
 #if defined(__CUDA_ARCH__)
+  if (HINTS & 4) return tmb_ld_stream_l1(p, pol.stream);
   if (HINTS) return tmb_ld_stream(p, pol.stream);
   return __ldg(p);
 #else
@@ -234,7 +247,7 @@ TMB_HD void tmb_hop_dir(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_geom &g
   /* forward link lives at the output site (parity par), backward link at the neighbour (parity 1-par) */
   const V2 *ub = f.U + (size_t)(((BWD ? 1 - par : par) * 4 + mu) * NE) * g.Vh + (BWD ? n : i);
 #pragma unroll
-  for (int e = 0; e < NE; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
+  for (int e = 0; e < NE; e++) u[e] = tmb_load_gauge<CFG & 5>(ub + (size_t)e * g.Vh, pol);
   tmb_project<D, HINTS>(a, b, f.in, g.Vh, n, pol);
   if (NE == 6) tmb_reconstruct_row2(u);
   tmb_link_accumulate<D>(r, u, a, b, ka);
@@ -249,7 +262,7 @@ TMB_HD void tmb_hop_dir_halo(V2 r[12], const tmb_hop_fields<V2> &f, const tmb_ge
   if (D == 0) { /* +t at t == T-1: local forward link, half-spinor from rank+1 */
     const V2 *ub = f.U + (size_t)((par * 4 + 0) * NE) * g.Vh + i;
 #pragma unroll
-    for (int e = 0; e < NE; e++) u[e] = tmb_load_gauge<HINTS>(ub + (size_t)e * g.Vh, pol);
+    for (int e = 0; e < NE; e++) u[e] = tmb_load_gauge<CFG & 5>(ub + (size_t)e * g.Vh, pol);
 #pragma unroll
     for (int c = 0; c < 3; c++) { a[c] = f.halo_up[(size_t)c * g.S + j]; b[c] = f.halo_up[(size_t)(3 + c) * g.S + j]; }
   } else {      /* -t at t == 0: link and half-spinor from rank-1 */
