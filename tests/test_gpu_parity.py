@@ -117,7 +117,7 @@ def test_cg_pro_from_second_hop(oracle_lib, loopback):
         xr = o.spinor()
         itr = o.cg_her(xr, k, 2000, 1e-22, 1)
         out = {}
-        for flags in (0, 16):
+        for flags in (0, 16, 32):  # 32: the x / r update as a separate sweep instead of the last hop's epilogue
             d.ck(d.lib.tmb_set_overlap(flags))
             d.call("field_zero", dx)
             it = d.call("cg_her", dx, dk, 2000, 1e-22, 1)
@@ -127,6 +127,7 @@ def test_cg_pro_from_second_hop(oracle_lib, loopback):
             itm = d.call("mixed_cg_her", dx, dk, 2000, 1e-22, 1)
             assert itm > 0 and rel_l2(d.download(dx), xr) <= 1e-8
         assert out[0][0] == out[16][0] and rel_l2(out[0][1], out[16][1]) <= 1e-12
+        assert out[0][0] == out[32][0] and rel_l2(out[0][1], out[32][1]) <= 1e-12
     finally:
         d.ck(d.lib.tmb_set_overlap(0))
         d.close()

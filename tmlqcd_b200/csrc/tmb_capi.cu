@@ -75,7 +75,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = -1, cg_selfnorm = 1;
+  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = -1, cg_selfnorm = 1, cg_tail = 1;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -221,7 +221,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = -1; C.cg_selfnorm = 1;
+  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = -1; C.cg_selfnorm = 1; C.cg_tail = 1;
   C.init = true;
   return 0;
 }
@@ -480,8 +480,9 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
 extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 0 || n > MAXCHUNK) return fail(-7, "host chunks must be in [0, %d] (0: two time-slices per chunk)", MAXCHUNK); C.host_chunks = n; C.param_gen++; return 0; }
 extern "C" int tmb_set_overlap(int flags) {
   NEED_INIT();
-  if (flags & ~31) return fail(-7, "tmb_set_overlap: unknown bits in 0x%x (bits 0..4 are defined)", flags);
+  if (flags & ~63) return fail(-7, "tmb_set_overlap: unknown bits in 0x%x (bits 0..5 are defined)", flags);
   C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1; C.cg_selfnorm = (flags & 16) ? 0 : 1;
+  C.cg_tail = (flags & 32) ? 0 : 1;
   C.param_gen++;
   return 0;
 }
@@ -720,6 +721,7 @@ struct HopOpt {
   bool nocom = false;         /* Hopping_Matrix_nocom: no halo exchange, the slab wraps onto itself in T */
   bool boundary_only = false; /* split T: exchange the faces and compute time-slices 0 and T-1 only (the interior was done in sub-ranges) */
   /* two flavours in one launch (hop_kernel NFL = 2): second flavour's fields, flavour mixing of the epilogue */
+  void *cg_x = nullptr, *cg_r = nullptr; const void *cg_p = nullptr; /* mode 4: the CG's x / r update in the epilogue */
   int nfl = 1; const void *in1 = nullptr; void *out1 = nullptr; const void *p1 = nullptr;
   double nd_mu = 0., nd_eps = 0., nd_scale = 1., dot_scale = 1.;
 };
@@ -750,6 +752,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   a.prec = o.prec;
   a.recon12 = C.compression == 12;
   a.in = in; a.out = out; a.p = o.p; a.dotw = o.dotw;
+  a.cg_x = o.cg_x; a.cg_r = o.cg_r; a.cg_p = o.cg_p;
   a.nfl = o.nfl; a.in1 = o.in1; a.out1 = o.out1; a.p1 = o.p1;
   a.nd_mu = o.nd_mu; a.nd_eps = o.nd_eps; a.nd_scale = o.nd_scale; a.dot_scale = o.dot_scale;
   a.halo_up = C.halo_up; a.halo_dn = C.halo_dn;
@@ -766,11 +769,8 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.selfnorm ? 2 : (o.dotw ? 1 : 0); a.hints = eff_hints();
   a.pdl = C.pdl; a.prefetch = C.prefetch;
-  if (o.nfl == 2 && a.hints == 1 && !o.prec && !a.recon12) { /* experiment switch: gauge links of the two-flavour kernel through L1 */
-    static int l1 = -1;
-    if (l1 < 0) { const char *e = getenv("TMB_ND_L1"); l1 = (e && atoi(e) == 1) ? 1 : 0; }
-    if (l1) a.hints = 5;
-  }
+  /* the two flavour groups of the NFL = 2 kernel read the same links: let them allocate in L1 (32^3x64: 1.86 -> 1.81 ms) */
+  if (o.nfl == 2 && a.hints == 1 && !o.prec && !a.recon12) a.hints = 5;
   a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && fuse_fin()) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
   a.xr = a.fin_op >= 0 ? xr_tab() : nullptr;
   int np = 0;
@@ -906,98 +906,91 @@ static void ensure_pinned(const void *p, size_t bytes) {
 
 static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int mode, double cre, double cim, double2 *din, double2 *dout) {
   const int T = C.g.T, S = C.g.S, Vh = C.g.Vh;
-  /* interior slices [t_lo, t_hi): all of them on one rank, 1 .. T-2 with a split T */
+  /* interior slices [t_lo, t_hi): all of them on one rank, 1 .. T-2 with a split T (slices 0 and T-1 wait for the faces) */
   const int t_lo = C.dist ? 1 : 0, t_hi = C.dist ? T - 1 : T;
   const int nt = t_hi - t_lo;
-  /* Chunk boundaries cb[0..nchunk] in time-slices.  What the pipeline adds to the two transfers is the fill (the chunks
-   * the first kernel needs: the first two and, periodic lattice, the last) and the drain (the last chunk going back), while
-   * every chunk costs a few microseconds of copy / dependency latency.  So: SMALL chunks where fill and drain are paid
-   * (`small` slices, >= 1 MB) and LARGE chunks (about an eighth of the field) in between.  tmb_set_host_chunks(n > 0)
-   * forces n equal chunks.  (Measured on this box's link, 55 GB/s one way, 47.6 GB/s per direction both ways, 24^3x48:
-   * 8 equal chunks 1.89 ms per call, 24 equal chunks 2.00 ms, 48: 2.33 ms - profiles/r02_e2e_diag.log.) */
-  int cb[MAXCHUNK + 1], nchunk = 0;
+  /* INPUT chunks cb[0..n] in time-slices; OUTPUT pieces are the same ranges shifted DOWN by one slice:
+   *   piece p = [cb[p] - 1, cb[p+1] - 1)   (piece 0 starts at t_lo, one more piece [t_hi - 1, t_hi) closes the lattice)
+   * so that piece p needs the inputs of chunks p-1 and p only - its download starts as soon as its own chunk is up, not one
+   * chunk later - plus, on a periodic lattice, the wrap-around slice (last chunk, sent second).  What the pipeline adds to
+   * the two transfers is then one chunk of upload before the first download and what is left to download when the upload
+   * ends; every copy costs ~17 us of latency whatever its size.  Hence few LARGE chunks (a sixth of the field) that halve
+   * towards the end.  tmb_set_host_chunks(n > 0) forces n equal chunks.  Measured (24^3x48, link 55 GB/s one way, 48 GB/s
+   * per direction both ways): profiles/r02_e2e_summary.md. */
+  int cb[MAXCHUNK + 1], n = 0;
   cb[0] = t_lo;
-  if (C.host_chunks > 0) {
-    const int spc = (nt + C.host_chunks - 1) / C.host_chunks > 0 ? (nt + C.host_chunks - 1) / C.host_chunks : 1;
-    for (int t = t_lo; t < t_hi; t += spc) cb[++nchunk] = t + spc < t_hi ? t + spc : t_hi;
-  } else {
-    /* sizes: head (small, small), body (big ...), tail (2 small, small, small).  The chunks that go up LAST decide the drain:
-     * when the upload ends, the outputs of the last two uploaded chunks and of the wrap-around chunk are still to come
-     * down (each output chunk waits for its upper neighbour's input), so the body tapers off into small chunks. */
-    int small = 1;
-    while ((size_t)small * S * 192 < ((size_t)1 << 20) && small < nt) small++;
-    int big = (nt + 5) / 6; if (big < small) big = small;
-    const int nhead = C.dist ? 1 : 2; /* a split T has no wrap: the first kernel needs the (already sent) boundary slice and two chunks */
-    const int tail[3] = {2 * small, small, small};
-    int t = t_lo, ntail = 0, tail_len = 0;
-    while (ntail < 3 && nt - (nhead * small + tail_len + tail[ntail]) >= big) tail_len += tail[ntail++];
-    for (int h = 0; h < nhead && t_hi - tail_len - t > small; h++) { t += small; cb[++nchunk] = t; }
-    while (t_hi - tail_len - t > big + big / 2) { t += big; cb[++nchunk] = t; }
-    if (t < t_hi - tail_len) { t = t_hi - tail_len; cb[++nchunk] = t; }
-    for (int k = 0; k < ntail; k++) { t += tail[k]; cb[++nchunk] = t; }
+  if (nt > 0) {
+    if (C.host_chunks > 0) {
+      const int spc = (nt + C.host_chunks - 1) / C.host_chunks > 0 ? (nt + C.host_chunks - 1) / C.host_chunks : 1;
+      for (int t = t_lo; t < t_hi; t += spc) cb[++n] = t + spc < t_hi ? t + spc : t_hi;
+    } else {
+      int small = 1;
+      while ((size_t)small * S * 192 < ((size_t)1 << 20) && small < nt) small++;
+      int big = (nt + 5) / 6; if (big < small) big = small;
+      int t = t_lo, rem = nt;
+      while (4 * rem > 7 * big) { t += big; rem -= big; cb[++n] = t; }
+      while (rem > 0) {
+        const int sz = rem <= 2 * small ? rem : ((rem + 1) / 2 > small ? (rem + 1) / 2 : small);
+        t += sz; rem -= sz; cb[++n] = t;
+      }
+    }
   }
-  if (nchunk > MAXCHUNK - 1) return fail(-13, "too many chunks");
+  if (n > MAXCHUNK - 2) return fail(-13, "too many chunks");
   double2 *in_aos = C.stage, *out_aos = C.stage + (size_t)12 * Vh;
   const double2 *hk = (const double2 *)k_host; double2 *hl = (double2 *)l_host;
-  auto first = [&](int c) { return cb[c] * S; };
-  auto count = [&](int c) { return (cb[c + 1] - cb[c]) * S; };
+  auto up = [&](int t0, int t1, cudaEvent_t ev) -> int { /* input slices [t0, t1) to the device, event when they are there */
+    CU(cudaMemcpyAsync(in_aos + (size_t)t0 * S * 12, hk + (size_t)t0 * S * 12, (size_t)(t1 - t0) * S * 192, cudaMemcpyHostToDevice, C.s_h2d));
+    CU(cudaEventRecord(ev, C.s_h2d));
+    return 0;
+  };
+  auto pack = [&](int t0, int t1, cudaEvent_t ev) -> int { /* AoS -> device layout on the compute stream, behind the copy */
+    CU(cudaStreamWaitEvent(C.s_main, ev, 0));
+    KL(tmb_launch_pack_eo_range(din, in_aos, Vh, t0 * S, (t1 - t0) * S, C.s_main));
+    return 0;
+  };
+  auto down = [&](int t0, int t1, cudaEvent_t ev) -> int { /* device layout -> AoS, then output slices [t0, t1) to the host */
+    KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, t0 * S, (t1 - t0) * S, C.s_main));
+    CU(cudaEventRecord(ev, C.s_main));
+    CU(cudaStreamWaitEvent(C.s_d2h, ev, 0));
+    CU(cudaMemcpyAsync(hl + (size_t)t0 * S * 12, out_aos + (size_t)t0 * S * 12, (size_t)(t1 - t0) * S * 192, cudaMemcpyDeviceToHost, C.s_d2h));
+    return 0;
+  };
   /* fork: the copy streams join the work of s_main (also what makes them part of a graph capture) */
   CU(cudaEventRecord(C.ev_in, C.s_main));
   CU(cudaStreamWaitEvent(C.s_h2d, C.ev_in, 0));
   CU(cudaStreamWaitEvent(C.s_d2h, C.ev_in, 0));
-  /* upload order: the chunks the first output chunk needs, then the rest; with a split T the two boundary slices come
-   * first of all (their faces have the longest way to go) */
+  /* upload order: with a split T the two boundary slices first of all (their faces have the longest way to go), then chunk 0,
+   * the wrap-around chunk (periodic lattice), then the rest in order */
   if (C.dist) {
-    CU(cudaMemcpyAsync(in_aos, hk, (size_t)S * 192, cudaMemcpyHostToDevice, C.s_h2d));
+    TRY(up(0, 1, C.ev_halo));
     CU(cudaMemcpyAsync(in_aos + (size_t)(T - 1) * S * 12, hk + (size_t)(T - 1) * S * 12, (size_t)S * 192, cudaMemcpyHostToDevice, C.s_h2d));
     CU(cudaEventRecord(C.ev_halo, C.s_h2d));
   }
-  int order[MAXCHUNK], no = 0;
-  if (nchunk > 0) order[no++] = 0;
-  if (nchunk > 1) order[no++] = 1;
-  if (nchunk > 2 && !C.dist) order[no++] = nchunk - 1;
-  for (int c = 2; c < nchunk - (C.dist ? 0 : 1); c++) order[no++] = c;
-  for (int q = 0; q < no; q++) {
-    const int c = order[q];
-    CU(cudaMemcpyAsync(in_aos + (size_t)first(c) * 12, hk + (size_t)first(c) * 12, (size_t)count(c) * 192,
-                       cudaMemcpyHostToDevice, C.s_h2d));
-    CU(cudaEventRecord(C.ev_up[c], C.s_h2d));
-  }
-  bool packed[MAXCHUNK] = {false};
-  if (C.dist) { /* the boundary slices are packed first: interior chunks 0 and nchunk-1 read them as neighbours */
+  if (n > 0) TRY(up(cb[0], cb[1], C.ev_up[0]));
+  if (n > 1 && !C.dist) TRY(up(cb[n - 1], cb[n], C.ev_up[n - 1]));
+  for (int c = 1; c < n - (C.dist ? 0 : 1); c++) TRY(up(cb[c], cb[c + 1], C.ev_up[c]));
+  if (C.dist) {
     CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
     KL(tmb_launch_pack_eo_range(din, in_aos, Vh, 0, S, C.s_main));
     KL(tmb_launch_pack_eo_range(din, in_aos, Vh, (T - 1) * S, S, C.s_main));
   }
-  for (int c = 0; c < nchunk; c++) {
-    int need[3] = {c - 1, c, c + 1};
-    if (!C.dist) { need[0] = (c + nchunk - 1) % nchunk; need[2] = (c + 1) % nchunk; }
-    for (int q = 0; q < 3; q++) {
-      const int n = need[q];
-      if (n < 0 || n >= nchunk || packed[n]) continue;
-      CU(cudaStreamWaitEvent(C.s_main, C.ev_up[n], 0));
-      KL(tmb_launch_pack_eo_range(din, in_aos, Vh, first(n), count(n), C.s_main));
-      packed[n] = true;
-    }
-    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.site0 = first(c); o.nsites = count(c); o.nocom = true;
+  bool packed[MAXCHUNK] = {false};
+  for (int p = 0; p <= n && n > 0; p++) {
+    if (p < n && !packed[p]) { TRY(pack(cb[p], cb[p + 1], C.ev_up[p])); packed[p] = true; }
+    if (p == 0 && n > 1 && !C.dist) { TRY(pack(cb[n - 1], cb[n], C.ev_up[n - 1])); packed[n - 1] = true; } /* the wrap-around slice lives in the last chunk */
+    const int lo = p == 0 ? t_lo : cb[p] - 1, hi = p == n ? t_hi : cb[p + 1] - 1;
+    if (hi <= lo) continue;
+    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.site0 = lo * S; o.nsites = (hi - lo) * S; o.nocom = true;
     TRY(hop(ieo, dout, din, o));
-    KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, first(c), count(c), C.s_main));
-    CU(cudaEventRecord(C.ev_done[c], C.s_main));
-    CU(cudaStreamWaitEvent(C.s_d2h, C.ev_done[c], 0));
-    CU(cudaMemcpyAsync(hl + (size_t)first(c) * 12, out_aos + (size_t)first(c) * 12, (size_t)count(c) * 192,
-                       cudaMemcpyDeviceToHost, C.s_d2h));
+    TRY(down(lo, hi, C.ev_done[p]));
   }
   if (C.dist) {
     /* boundary slices 0 and T-1: faces projected and exchanged (half-spinors, xchange_halffield's idea), then the halo
      * kernel on those two slices only */
     HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.boundary_only = true;
     TRY(hop(ieo, dout, din, o));
-    KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, 0, S, C.s_main));
-    KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, (T - 1) * S, S, C.s_main));
-    CU(cudaEventRecord(C.ev_done[MAXCHUNK - 1], C.s_main));
-    CU(cudaStreamWaitEvent(C.s_d2h, C.ev_done[MAXCHUNK - 1], 0));
-    CU(cudaMemcpyAsync(hl, out_aos, (size_t)S * 192, cudaMemcpyDeviceToHost, C.s_d2h));
-    CU(cudaMemcpyAsync(hl + (size_t)(T - 1) * S * 12, out_aos + (size_t)(T - 1) * S * 12, (size_t)S * 192, cudaMemcpyDeviceToHost, C.s_d2h));
+    TRY(down(0, 1, C.ev_done[MAXCHUNK - 2]));
+    TRY(down(T - 1, T, C.ev_done[MAXCHUNK - 1]));
   }
   /* join */
   CU(cudaEventRecord(C.ev_chk[0], C.s_d2h));
@@ -1005,58 +998,6 @@ static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int m
   CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[0], 0));
   CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[1], 0));
   return 0;
-}
-
-/* Zero-copy form of the pipeline (one rank, both buffers pinned and mapped): no copy engines and no AoS staging - the
- * pack kernel of chunk c reads the caller's buffer across PCIe and writes the device layout, the unpack kernel writes the
- * result straight into the caller's buffer.  Kernels cost a few microseconds each where a copy costs ~17, so the chunks can
- * be as small as two time-slices and fill and drain shrink with them. */
-static int host_hop_enqueue_zc(int ieo, double2 *l_dev, const double2 *k_dev, int mode, double cre, double cim, double2 *din, double2 *dout) {
-  const int T = C.g.T, S = C.g.S, Vh = C.g.Vh;
-  int spc = 1;
-  while ((size_t)spc * S * 192 < ((size_t)2 << 20) && spc < T) spc++;
-  if (C.host_chunks > 0) spc = (T + C.host_chunks - 1) / C.host_chunks;
-  int nchunk = (T + spc - 1) / spc;
-  if (nchunk > MAXCHUNK) { spc = (T + MAXCHUNK - 1) / MAXCHUNK; nchunk = (T + spc - 1) / spc; }
-  static int ctas = 0;
-  if (!ctas) { const char *e = getenv("TMB_E2E_CTAS"); ctas = e ? atoi(e) : 32; if (ctas < 1) ctas = 1; if (ctas > 592) ctas = 592; }
-  auto first = [&](int c) { return c * spc * S; };
-  auto count = [&](int c) { int t1 = (c + 1) * spc; if (t1 > T) t1 = T; return (t1 - c * spc) * S; };
-  CU(cudaEventRecord(C.ev_in, C.s_main));
-  CU(cudaStreamWaitEvent(C.s_h2d, C.ev_in, 0));
-  CU(cudaStreamWaitEvent(C.s_d2h, C.ev_in, 0));
-  int order[MAXCHUNK], no = 0;
-  order[no++] = 0;
-  if (nchunk > 1) order[no++] = 1;
-  if (nchunk > 2) order[no++] = nchunk - 1;
-  for (int c = 2; c < nchunk - 1; c++) order[no++] = c;
-  for (int q = 0; q < no; q++) {
-    const int c = order[q];
-    KL(tmb_launch_pack_host_range(din, k_dev, Vh, first(c), count(c), ctas, C.s_h2d));
-    CU(cudaEventRecord(C.ev_up[c], C.s_h2d));
-  }
-  bool waited[MAXCHUNK] = {false};
-  for (int c = 0; c < nchunk; c++) {
-    const int need[3] = {(c + nchunk - 1) % nchunk, c, (c + 1) % nchunk};
-    for (int q = 0; q < 3; q++)
-      if (!waited[need[q]]) { CU(cudaStreamWaitEvent(C.s_main, C.ev_up[need[q]], 0)); waited[need[q]] = true; }
-    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim); o.site0 = first(c); o.nsites = count(c); o.nocom = true;
-    TRY(hop(ieo, dout, din, o));
-    CU(cudaEventRecord(C.ev_done[c], C.s_main));
-    CU(cudaStreamWaitEvent(C.s_d2h, C.ev_done[c], 0));
-    KL(tmb_launch_unpack_host_range(l_dev, dout, Vh, first(c), count(c), ctas, C.s_d2h));
-  }
-  CU(cudaEventRecord(C.ev_chk[0], C.s_d2h));
-  CU(cudaEventRecord(C.ev_chk[1], C.s_h2d));
-  CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[0], 0));
-  CU(cudaStreamWaitEvent(C.s_main, C.ev_chk[1], 0));
-  return 0;
-}
-/* the device-side address of a pinned, mapped host buffer; nullptr for pageable memory */
-static void *mapped_host_pointer(const void *p) {
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
 extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_host, int mode, double cre, double cim) {
@@ -1069,13 +1010,7 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
   CU(cudaStreamSynchronize(C.s_main));
   /* a split T exchanges faces through NCCL inside the pipeline: not captured (NCCL calls stay out of graphs here) */
   const bool use_graph = C.cg_graph && !C.dist;
-  static int zc_env = -1;
-  if (zc_env < 0) { const char *e = getenv("TMB_E2E_ZEROCOPY"); zc_env = e ? atoi(e) : 0; }
-  double2 *l_dev = nullptr; const double2 *k_dev = nullptr;
-  const bool zc = zc_env && !C.dist && (l_dev = (double2 *)mapped_host_pointer(l_host)) != nullptr &&
-                  (k_dev = (const double2 *)mapped_host_pointer(k_host)) != nullptr;
-  auto enqueue = [&]() { return zc ? host_hop_enqueue_zc(ieo, l_dev, k_dev, mode, cre, cim, din, dout)
-                                   : host_hop_enqueue(ieo, l_host, k_host, mode, cre, cim, din, dout); };
+  auto enqueue = [&]() { return host_hop_enqueue(ieo, l_host, k_host, mode, cre, cim, din, dout); };
   if (!use_graph) {
     TRY(enqueue());
     CU(cudaStreamSynchronize(C.s_main));
@@ -1167,6 +1102,32 @@ static int qtm_pm(double2 *l, const double2 *k, const double2 *dotw, const tmb_c
   return 0;
 }
 extern "C" int tmb_Qtm_pm_psi(void *l, const void *k) { NEED_INIT(); return qtm_pm(F(l), F(k), nullptr, nullptr, nullptr); }
+
+/* One CG iteration's operator part with the vector updates folded in (cg_her.c:92-101), both precisions:
+ *   hop 1, hop 2 (+ |Q- p|^2 = <p, A p>, finish: alpha), hop 3, hop 4 whose epilogue does x += alpha p, r -= alpha A p, |r|^2
+ * A p itself is never written.  4 launches; the fourth leaves the |r|^2 partials (finished in place when fuse_fin()). */
+static float2 *scratch32(int k);
+static int reduce_to(int npart, int slot, int op);
+static int qtm_pm_cg(int prec, void *x, void *r, const void *p, int err_op, int *np_err) {
+  void *w0, *w1;
+  if (prec) { w0 = scratch32(0); w1 = scratch32(1); } else { w0 = scratch(0); w1 = scratch(1); }
+  if (!w0 || !w1) return -100;
+  const bool fuse = fuse_fin();
+  int np = 0;
+  HopOpt a; a.prec = prec; a.mode = 1; a.cf = z_inv(-1.); a.st = C.st;
+  TRY(hop(0, w1, p, a));
+  HopOpt b; b.prec = prec; b.mode = 2; b.cf = z_fwd(-1.); b.p = p; b.st = C.st;
+  b.selfnorm = true; b.npartial = &np; b.fin_op = fuse ? TMB_FIN_CG_PRO : -1; b.fin_slot = 1;
+  TRY(hop(1, w0, w1, b));
+  if (!fuse) TRY(reduce_to(np, 1, TMB_FIN_CG_PRO)); /* alpha must exist before the fourth hop starts */
+  HopOpt c; c.prec = prec; c.mode = 1; c.cf = z_inv(+1.); c.st = C.st;
+  TRY(hop(0, w1, w0, c));
+  HopOpt d; d.prec = prec; d.mode = 4; d.cf = z_fwd(+1.); d.p = w0; d.st = C.st;
+  d.cg_x = x; d.cg_r = r; d.cg_p = p;
+  d.selfnorm = true; d.npartial = np_err; d.fin_op = fuse ? err_op : -1; d.fin_slot = 2;
+  TRY(hop(1, w1 /* unused: mode 4 writes x and r */, w1, d));
+  return 0;
+}
 
 /* Q_+- = g5[(1 +- i mu g5) k - H_oe (1 +- i mu g5)^-1 H_eo k]  (tm_operators.c:172-177, :216-221);
  * l may alias k: k is only read site-locally by the last kernel */

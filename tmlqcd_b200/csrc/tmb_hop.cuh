@@ -142,9 +142,12 @@ __device__ __forceinline__ void finish_last_block(const double *partial, int tot
  * applied to a strange and a charm field with the same links).  A CTA of BLOCK threads works on BLOCK/2 sites: its
  * first half of warps takes flavour 0, the second half flavour 1 of the SAME sites, so every warp-wide load still
  * moves 32 consecutive elements (512 B in double) and each thread carries one 12-component accumulator (the registers
- * and residency of the one-field kernel).  Both flavour groups issue the same gauge addresses at about the same time:
- * the second request is served by L1 / L2, DRAM streams every link once for both flavours (1920 B per site pair instead
- * of 2 x 1536).  The 2x2 flavour mixing of M_ee_inv_ndpsi / M_oo_sub_g5_ndpsi (tm_operators_nd.c:639-756) is the
+ * and residency of the one-field kernel).  Both flavour groups issue the same gauge addresses at about the same time
+ * (links allocate in L1 here, unlike in the one-field kernel): the second request is served by L1 / L2 and DRAM streams every
+ * link once for both flavours (1920 B per site pair instead of 2 x 1536; ncu: 515 + 93 MB per MODE 1 launch at 24^3x48,
+ * the same as the one-thread kernel).  Staging the eight links of a site in shared memory instead (cp.async, four directions
+ * per flavour thread, one barrier) was measured SLOWER (32^3x64 Qtm_pm_ndpsi 1.92 ms against 1.82 ms: the barrier keeps the
+ * spinor loads behind the link latency) and is not kept.  The 2x2 flavour mixing of M_ee_inv_ndpsi / M_oo_sub_g5_ndpsi (tm_operators_nd.c:639-756) is the
  * epilogue; the partner flavour's value comes through shared memory.
  *   NFL = 2, MODE 1: out_f = nrm [ (1 -+ i mu g5) H in_f + eps H in_f' ]                    (mu sign flips with f)
  *   NFL = 2, MODE 2: out_f = scale g5 [ (1 -+ i mu g5) p_f + eps p_f' - H in_f ]
@@ -319,7 +322,38 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
     if (DIST == 1 || (DIST == 2 && bcta)) tmb_hop_site<1, HINTS>(r, f, a.g, a.par, i, ka, pol);
     else tmb_hop_site<0, HINTS>(r, f, a.g, a.par, i, ka, pol);
   }
-  if constexpr (NFL == 1) {
+  if constexpr (NFL == 1 && MODE == 4) {
+    /* CG tail (the last hop of Qtm_pm_psi inside cg_her): A p = g5((cf | conj cf) w0 - H w1) stays in registers and goes
+     * straight into  x += alpha p ; r -= alpha A p ; |r|^2  (cg_her.c:95-101).  alpha = normsq / <p, A p> is known by now
+     * because <p, A p> = |Q- p|^2 came out of the SECOND hop.  Saves writing A p and reading it back (384 B per site) and
+     * the separate sweep's launch: 2496 B per site for this launch + nothing, instead of 1728 + 1152. */
+    if (active) {
+      typedef typename tmb_real<V2>::type R;
+      const V2 cf = cvt2<V2>(a.cf);
+      const R al = (R)a.st_fin->alpha;
+      const V2 *__restrict__ w0 = (const V2 *)a.p, *__restrict__ pv = (const V2 *)a.cg_p;
+      V2 *__restrict__ xv = (V2 *)a.cg_x, *__restrict__ rv = (V2 *)a.cg_r;
+#pragma unroll
+      for (int h = 0; h < 2; h++) { /* two batches of six components: 24 operand loads in flight, then their stores */
+        V2 w[6], pp[6], xx[6], rr[6];
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+          const size_t k = (size_t)(6 * h + u) * a.g.Vh + i;
+          w[u] = w0[k]; pp[u] = pv[k]; xx[u] = xv[k]; rr[u] = rv[k];
+        }
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+          const int c = 6 * h + u;
+          const size_t k = (size_t)c * a.g.Vh + i;
+          const V2 ap = tmb_epilogue<2>(c, r[c], w[u], cf);
+          xx[u].x += al * pp[u].x; xx[u].y += al * pp[u].y;
+          rr[u].x = rr[u].x - al * ap.x; rr[u].y = rr[u].y - al * ap.y;
+          dsum += (double)rr[u].x * (double)rr[u].x; dsum += (double)rr[u].y * (double)rr[u].y;
+          xv[k] = xx[u]; rv[k] = rr[u];
+        }
+      }
+    }
+  } else if constexpr (NFL == 1) {
     if (active) {
       const V2 cf = cvt2<V2>(a.cf);
       const V2 *pp = (const V2 *)a.p, *dw_ = (const V2 *)a.dotw;

@@ -43,6 +43,7 @@ static cudaError_t hop_dist_f(const tmb_hop_launch &a, cudaStream_t s) {
 template <int HINTS>
 static cudaError_t hop_mode_448(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
+    if (a.mode == 4 && a.dot == 2) return hop_go<double2, 4, 0, 2, HINTS, 64, 7>(a, s); /* CG tail */
     if (a.mode != 2) return cudaErrorInvalidValue;
     if (a.dot == 2) return hop_go<double2, 2, 0, 2, HINTS, 64, 7>(a, s);
     return hop_go<double2, 2, 0, 1, HINTS, 64, 7>(a, s);
@@ -58,6 +59,7 @@ static cudaError_t hop_mode_448(const tmb_hop_launch &a, cudaStream_t s) {
 template <int DIST, int HINTS>
 static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
+    if (a.mode == 4 && a.dot == 2) return hop_go<double2, 4, DIST, 2, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s); /* CG tail */
     if (a.mode != 2) return cudaErrorInvalidValue;
     if (a.dot == 2) return hop_go<double2, 2, DIST, 2, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
     return hop_go<double2, 2, DIST, 1, HINTS, TMB_HOP_BLOCK, TMB_HOP_MINB>(a, s);
@@ -74,6 +76,7 @@ static cudaError_t hop_mode(const tmb_hop_launch &a, cudaStream_t s) {
 template <int DIST, int CFG>
 static cudaError_t hop_mode_f(const tmb_hop_launch &a, cudaStream_t s) {
   if (a.dot) {
+    if (a.mode == 4 && a.dot == 2) return hop_go<float2, 4, DIST, 2, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s); /* CG tail */
     if (a.mode != 2) return cudaErrorInvalidValue;
     if (a.dot == 2) return hop_go<float2, 2, DIST, 2, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
     return hop_go<float2, 2, DIST, 1, CFG, TMB_HOP_BLOCK_F, TMB_HOP_MINB_F>(a, s);
@@ -365,45 +368,6 @@ struct EwPackEoRange { double2 *soa; const double2 *aos; int Vh, i0, n;
   __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / n), i = i0 + (int)(k - (size_t)c * n); soa[(size_t)c * Vh + i] = aos[(size_t)i * 12 + c]; } };
 struct EwUnpackEoRange { double2 *aos; const double2 *soa; int Vh, i0, n;
   __host__ __device__ void operator()(size_t k) const { const int c = (int)(k / n), i = i0 + (int)(k - (size_t)c * n); aos[(size_t)i * 12 + c] = soa[(size_t)c * Vh + i]; } };
-/* Zero-copy forms of the two range kernels: `aos` is PINNED HOST memory read / written by the SMs across PCIe.  The host
- * side is touched strictly in address order (thread k moves element k of the range: whole 128-byte lines per warp, the
- * largest requests an SM can put on the link); the strided side is HBM, where a 16-byte access per 32-byte sector costs
- * nothing that matters next to the link.  A few CTAs with eight independent 16-byte accesses per thread keep far more
- * bytes in flight than the link's latency-bandwidth product (~100 KB) asks for. */
-__global__ void __launch_bounds__(256) pack_host_kernel(double2 *soa, const double2 *aos, int Vh, int i0, int n) {
-  const size_t tot = (size_t)12 * n, stride = (size_t)gridDim.x * 256;
-  const double2 *src = aos + (size_t)i0 * 12;
-  for (size_t k0 = (size_t)blockIdx.x * 256 + threadIdx.x; k0 < tot; k0 += 8 * stride) {
-    double2 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) { const size_t k = k0 + u * stride; if (k < tot) v[u] = __ldcs(src + k); }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const size_t k = k0 + u * stride;
-      if (k < tot) { const size_t i = k / 12; const int c = (int)(k - i * 12); soa[(size_t)c * Vh + i0 + i] = v[u]; }
-    }
-  }
-}
-__global__ void __launch_bounds__(256) unpack_host_kernel(double2 *aos, const double2 *soa, int Vh, int i0, int n) {
-  const size_t tot = (size_t)12 * n, stride = (size_t)gridDim.x * 256;
-  double2 *dst = aos + (size_t)i0 * 12;
-  for (size_t k0 = (size_t)blockIdx.x * 256 + threadIdx.x; k0 < tot; k0 += 8 * stride) {
-    double2 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const size_t k = k0 + u * stride;
-      if (k < tot) { const size_t i = k / 12; const int c = (int)(k - i * 12); v[u] = soa[(size_t)c * Vh + i0 + i]; }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) { const size_t k = k0 + u * stride; if (k < tot) __stcs(dst + k, v[u]); }
-  }
-}
-cudaError_t tmb_launch_pack_host_range(double2 *soa, const double2 *aos_host, int Vh, int i0, int n, int ctas, cudaStream_t s) {
-  pack_host_kernel<<<ctas, 256, 0, s>>>(soa, aos_host, Vh, i0, n); return cudaGetLastError();
-}
-cudaError_t tmb_launch_unpack_host_range(double2 *aos_host, const double2 *soa, int Vh, int i0, int n, int ctas, cudaStream_t s) {
-  unpack_host_kernel<<<ctas, 256, 0, s>>>(aos_host, soa, Vh, i0, n); return cudaGetLastError();
-}
 /* lexicographic host field of V sites <-> (even, odd) device fields (linalg/convert_eo_to_lexic.c:35-115) */
 template <class V2> struct EwPackLex { V2 *even, *odd; const V2 *lex; tmb_geom g;
   __host__ __device__ void operator()(size_t k) const {

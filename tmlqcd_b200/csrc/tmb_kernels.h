@@ -57,6 +57,9 @@ struct tmb_hop_launch {
   /* nfl == 2 (non-degenerate doublet): the second flavour's fields and the 2x2 flavour mixing of the epilogue
    * (tm_operators_nd.c:639-756): mode 1 out_f = nrm[(1 -+ i mu g5) H in_f + eps H in_f'], mode 2 out_f = scale g5[(1 -+ i mu g5) p_f
    * + eps p_f' - H in_f], flavour 0 with the upper sign; dot == 2 accumulates dot_scale (|out|^2 + |out1|^2) */
+  /* mode 4 (CG tail, one field, dot == 2): out is not written; A p = g5((cf|conj cf) p - H in) feeds cg_x += alpha cg_p,
+   * cg_r -= alpha A p in registers (alpha = st_fin->alpha) and the reduction is |cg_r|^2 */
+  void *cg_x, *cg_r; const void *cg_p;
   int nfl; const void *in1; void *out1; const void *p1; double nd_mu, nd_eps, nd_scale, dot_scale;
   const void *in_up1, *in_dn1; /* peer mode: the neighbours' copies of in1 */
   const void *U; const void *halo_up, *halo_dn, *Uhalo;
@@ -145,9 +148,6 @@ cudaError_t tmb_launch_pack_eo(double2 *soa, const double2 *aos, int Vh, cudaStr
 cudaError_t tmb_launch_unpack_eo(double2 *aos, const double2 *soa, int Vh, cudaStream_t s);
 cudaError_t tmb_launch_pack_eo_range(double2 *soa, const double2 *aos, int Vh, int i0, int n, cudaStream_t s);
 cudaError_t tmb_launch_unpack_eo_range(double2 *aos, const double2 *soa, int Vh, int i0, int n, cudaStream_t s);
-/* the same with `aos` in pinned host memory, accessed by the kernel itself across PCIe (zero-copy) */
-cudaError_t tmb_launch_pack_host_range(double2 *soa, const double2 *aos_host, int Vh, int i0, int n, int ctas, cudaStream_t s);
-cudaError_t tmb_launch_unpack_host_range(double2 *aos_host, const double2 *soa, int Vh, int i0, int n, int ctas, cudaStream_t s);
 cudaError_t tmb_launch_pack_lexic(double2 *even, double2 *odd, const double2 *lex, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_unpack_lexic(double2 *lex, const double2 *even, const double2 *odd, tmb_geom g, cudaStream_t s);
 cudaError_t tmb_launch_pack_lexic_f(float2 *even, float2 *odd, const float2 *lex, tmb_geom g, cudaStream_t s);
