@@ -121,6 +121,28 @@ void emul_compress12(double *dst, const double *src, long n, int nlinks) {
   EwCompress12 f = {(double2 *)dst, (const double2 *)src, (size_t)n};
   for (size_t k = 0; k < (size_t)nlinks * 6 * n; k++) f(k);
 }
+/* second split direction (Z): face pack, gauge z-halo and the fix-up of the face sites, as the device composes them */
+void emul_pack_zfaces(double *up, double *dn, const double *in, int T, int LX, int LY, int LZ, int pin) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  EwPackZFaces<double2> f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g, pin};
+  for (size_t k = 0; k < (size_t)6 * (T * LX * LY / 2); k++) f(k);
+}
+void emul_pack_gauge_zhalo(double *out, const double *U, int T, int LX, int LY, int LZ) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  EwPackGaugeZHalo<double2> f = {(double2 *)out, (const double2 *)U, g};
+  for (size_t k = 0; k < (size_t)18 * (T * LX * LY / 2); k++) f(k);
+}
+void emul_zfix(int mode, double *out, const double *in, const double *U, const double *hz_up, const double *hz_dn, const double *Uzh,
+               int T, int LX, int LY, int LZ, int par, const double *ka8, double cre, double cim) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  const double2 ka3 = make_double2(ka8[6], ka8[7]), cf = make_double2(cre, cim);
+  for (int j = 0; j < T * LX * LY / 2; j++) {
+    if (mode == 0) tmb_zfix_pair<0>((double2 *)out, (const double2 *)in, (const double2 *)U, (const double2 *)hz_up, (const double2 *)hz_dn, (const double2 *)Uzh, g, par, j, ka3, cf);
+    else if (mode == 1) tmb_zfix_pair<1>((double2 *)out, (const double2 *)in, (const double2 *)U, (const double2 *)hz_up, (const double2 *)hz_dn, (const double2 *)Uzh, g, par, j, ka3, cf);
+    else if (mode == 2) tmb_zfix_pair<2>((double2 *)out, (const double2 *)in, (const double2 *)U, (const double2 *)hz_up, (const double2 *)hz_dn, (const double2 *)Uzh, g, par, j, ka3, cf);
+    else tmb_zfix_pair<3>((double2 *)out, (const double2 *)in, (const double2 *)U, (const double2 *)hz_up, (const double2 *)hz_dn, (const double2 *)Uzh, g, par, j, ka3, cf);
+  }
+}
 /* single precision instantiation of the same site code */
 int emul_hop_f(int par, float *out, const float *in, const float *U, int T, int LX, int LY, int LZ, const double *ka8) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);

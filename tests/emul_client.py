@@ -39,6 +39,8 @@ def load():
         "emul_hop2": [i, dp, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, i, d, d, d],
         "emul_pack_gauge_first_slice": [dp, dp, i, i, i, i], "emul_plaquette": [dp, dp, i, i, i, i, i],
         "emul_nd_mee_inv": [dp, dp, dp, dp, d, d, i], "emul_nd_moo_sub_g5": [dp, dp, dp, dp, dp, dp, d, d, i],
+        "emul_pack_zfaces": [dp, dp, dp, i, i, i, i, i], "emul_pack_gauge_zhalo": [dp, dp, i, i, i, i],
+        "emul_zfix": [i, dp, dp, dp, dp, dp, dp, i, i, i, i, i, dp, d, d],
     }
     for n, a in sig.items():
         getattr(E, n).argtypes = a

@@ -223,3 +223,53 @@ def test_two_flavour_hop_and_fused_flavour_mixing(oracle_lib, dims, theta):
     es, ec = o.spinor(), o.spinor()
     o.Qtm_pm_ndpsi(es, ec, ks, kc)
     assert rel_l2(e.unpack(ls), es) < 1e-13 and rel_l2(e.unpack(lc), ec) < 1e-13
+
+
+@pytest.mark.parametrize("gdims,nz", [((4, 4, 4, 8), 2), ((2, 4, 6, 12), 3), ((4, 2, 4, 4), 2)])
+def test_z_split_face_exchange_and_fixup(oracle_lib, gdims, nz):
+    """Second split direction (Z): every z slab runs the UNCHANGED hopping code as if it were periodic in z, then the fix-up
+    replaces the wrapped term of its face sites by the term built from the neighbour slab's packed faces and z-links
+    (tmb_site.cuh).  All epilogues, against the oracle on the global lattice."""
+    T, LX, LY, LZ = gdims
+    LZl = LZ // nz
+    rng = np.random.default_rng(41)
+    theta = (1., 0., 0.3, 0.7)
+    o = oracle_lib.Oracle(*gdims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, theta)
+    ka = ka_of(KAPPA, theta, gdims)  # global extents in the phases
+    k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+    e = Emul(T, LX, LY, LZl)
+    rows, Sz = T * LX * LY, T * LX * LY // 2
+    gs = g.reshape(T, LX, LY, LZ, 4, 18)
+    slab_f = lambda f, s: np.ascontiguousarray(f.reshape(rows, LZ // 2, 24)[:, s * (LZl // 2):(s + 1) * (LZl // 2), :]).reshape(-1, 24)
+    U = [e.pack_gauge(np.ascontiguousarray(gs[:, :, :, s * LZl:(s + 1) * LZl]).reshape(-1, 4, 18)) for s in range(nz)]
+    Uzh = []
+    for s in range(nz):
+        out = np.zeros(36 * Sz); e.E.emul_pack_gauge_zhalo(out, U[s], T, LX, LY, LZl); Uzh.append(out)
+    for par in (0, 1):
+        sk = [e.pack(slab_f(k, s)) for s in range(nz)]
+        sp = [e.pack(slab_f(p, s)) for s in range(nz)]
+        faces = []
+        for s in range(nz):
+            up, dn = np.zeros(12 * Sz), np.zeros(12 * Sz)
+            e.E.emul_pack_zfaces(up, dn, sk[s], T, LX, LY, LZl, 1 - par)
+            faces.append((up, dn))
+        for mode, cf, ref in ((0, (1., 0.), lambda x: o.Hopping_Matrix(par, x, k)),
+                              (1, (0.9, -0.2), lambda x: o.tm_times_Hopping_Matrix(par, x, k, 0.9, -0.2)),
+                              (2, (1.0, 0.3), lambda x: o.tm_sub_Hopping_Matrix(par, x, p, k, 1.0, 0.3)),
+                              (3, (1.0, GMU), None)):
+            exp = o.spinor()
+            if ref is not None:
+                ref(exp)
+            else:
+                hk = o.spinor(); o.Hopping_Matrix(par, hk, k)
+                zp = o.spinor(); o.assign_mul_one_pm_imu(zp, p, +1., o.Vh)
+                exp = zp - hk
+            for s in range(nz):
+                out = e.hop(par, sk[s], U[s], ka, mode, cf, sp[s] if mode >= 2 else None)
+                wrong = rel_l2(e.unpack(out), slab_f(exp, s))
+                e.E.emul_zfix(mode, out, sk[s], U[s], faces[(s + 1) % nz][1], faces[(s - 1) % nz][0], Uzh[(s - 1) % nz],
+                              T, LX, LY, LZl, par, np.asarray(ka, dtype=np.float64), cf[0], cf[1])
+                assert rel_l2(e.unpack(out), slab_f(exp, s)) < 1e-14, (par, mode, s)
+                assert wrong > 1e-3  # the un-fixed slab result really differs

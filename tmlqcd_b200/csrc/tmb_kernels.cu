@@ -463,4 +463,41 @@ cudaError_t tmb_launch_su3_defect(const double2 *U, size_t n, int nlinks, double
   max_kernel<<<tmb_red_grid((size_t)nlinks * n), RED_BLOCK, 0, s>>>(f, (size_t)nlinks * n, partial);
   return cudaGetLastError();
 }
+/* ---- second split direction (Z): face pack, gauge z-halo, fix-up of the face sites (tmb_site.cuh) ---- */
+cudaError_t tmb_launch_pack_zfaces(int prec, void *up, void *dn, const void *in, tmb_geom g, int pin, cudaStream_t s) {
+  const size_t n = (size_t)6 * (g.T * g.LX * g.LY / 2);
+  if (prec) { EwPackZFaces<float2> f = {(float2 *)up, (float2 *)dn, (const float2 *)in, g, pin}; EW_LAUNCH(f, n, nullptr, s); }
+  EwPackZFaces<double2> f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g, pin}; EW_LAUNCH(f, n, nullptr, s);
+}
+cudaError_t tmb_launch_pack_gauge_zhalo(int prec, void *out, const void *U, tmb_geom g, cudaStream_t s) {
+  const size_t n = (size_t)18 * (g.T * g.LX * g.LY / 2);
+  if (prec) { EwPackGaugeZHalo<float2> f = {(float2 *)out, (const float2 *)U, g}; EW_LAUNCH(f, n, nullptr, s); }
+  EwPackGaugeZHalo<double2> f = {(double2 *)out, (const double2 *)U, g}; EW_LAUNCH(f, n, nullptr, s);
+}
+template <int MODE, class V2>
+__global__ void __launch_bounds__(128) zfix_kernel(V2 *out, const V2 *in, const V2 *U, const V2 *hz_up, const V2 *hz_dn, const V2 *Uzh,
+                                                   tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st) {
+  if (st != nullptr && st->converged) return;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= g.T * g.LX * g.LY / 2) return;
+  tmb_zfix_pair<MODE>(out, in, U, hz_up, hz_dn, Uzh, g, par, j, cvt2<V2>(ka3), cvt2<V2>(cf));
+}
+template <class V2>
+static cudaError_t zfix_go(int mode, V2 *out, const V2 *in, const V2 *U, const V2 *hu, const V2 *hd, const V2 *Uzh, tmb_geom g, int par,
+                           double2 ka3, double2 cf, const tmb_cg_state *st, cudaStream_t s) {
+  const int grid = (g.T * g.LX * g.LY / 2 + 127) / 128;
+  switch (mode) {
+    case 0: zfix_kernel<0, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
+    case 1: zfix_kernel<1, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
+    case 2: zfix_kernel<2, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
+    case 3: zfix_kernel<3, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t tmb_launch_zfix(int prec, int mode, void *out, const void *in, const void *U, const void *hz_up, const void *hz_dn, const void *Uzh,
+                            tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st, cudaStream_t s) {
+  if (prec) return zfix_go<float2>(mode, (float2 *)out, (const float2 *)in, (const float2 *)U, (const float2 *)hz_up, (const float2 *)hz_dn, (const float2 *)Uzh, g, par, ka3, cf, st, s);
+  return zfix_go<double2>(mode, (double2 *)out, (const double2 *)in, (const double2 *)U, (const double2 *)hz_up, (const double2 *)hz_dn, (const double2 *)Uzh, g, par, ka3, cf, st, s);
+}
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s) { EwPackGaugeHalo f = {out, U, g}; EW_LAUNCH(f, (size_t)18 * g.S, nullptr, s); }

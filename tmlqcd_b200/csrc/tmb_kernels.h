@@ -161,6 +161,15 @@ cudaError_t tmb_launch_su3_defect(const double2 *U, size_t n, int nlinks, double
 /* Uhalo[q][e][j] = U[q][0][e][(T-1)S + j] : what rank+1 needs from this rank */
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s);
 
+/* ---- second split direction (Z), see tmb_site.cuh: Sz = T*LX*LY/2 face entries per parity ----
+ * pack_zfaces: send_up[6][Sz] = (1 - g3)-type projection (hop direction -z) of this rank's last-z sites of `in` (parity pin), for
+ * rank z+1; send_dn[6][Sz] = direction +z projection of its first-z sites, for rank z-1.  pack_gauge_zhalo: U_z of the last-z
+ * sites, [2][9][Sz], for rank z+1.  zfix: replaces the wrapped z term of the face sites of `out` by the halo term. */
+cudaError_t tmb_launch_pack_zfaces(int prec, void *send_up, void *send_dn, const void *in, tmb_geom g, int pin, cudaStream_t s);
+cudaError_t tmb_launch_pack_gauge_zhalo(int prec, void *out, const void *U, tmb_geom g, cudaStream_t s);
+cudaError_t tmb_launch_zfix(int prec, int mode, void *out, const void *in, const void *U, const void *hz_up, const void *hz_dn, const void *Uzh,
+                            tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st, cudaStream_t s);
+
 /* ---- fermion force (tmb_force.cu): deriv_Sb.c:402-649 as a gather over link owners ---- */
 struct tmb_deriv_launch {
   const void *l, *k, *U; double *df;

@@ -342,6 +342,108 @@ TMB_HD void tmb_nd_mee_inv_regs(V2 &ls, V2 &lc, V2 ks, V2 kc, int c, double mu, 
   ls = mk2<V2>((R)nrm * a.x, (R)nrm * a.y); lc = mk2<V2>((R)nrm * b.x, (R)nrm * b.y);
 }
 
+/* ====================================================================================
+ * Second split direction (Z).  Ranks form an (nt x nz) grid (the reference's PARALLELXT.. family, mpi_init.c:331-357, here
+ * T then Z); the local z extent is LZ / nz (even, so parities need no offset).  Per row (t, x, y) of the eo layout exactly
+ * ONE site of each parity sits on a z face: with r = (t + x + y + parity) & 1, the site zh = Lzh-1 of a row with r = 1 has its
+ * +z neighbour on rank z+1, the site zh = 0 of a row with r = 0 has its -z neighbour on rank z-1.  Rows come in (y even, y odd)
+ * pairs with opposite r, so face buffers are indexed by j = row >> 1, Sz = T*LX*LY/2 entries.
+ *
+ * The hopping kernels are NOT touched: they run on the slab as if it were periodic in z (the face sites pick up the slab's
+ * own opposite face: the WRONG neighbour), and a fix-up over the face sites replaces that one term by the right one from
+ * the halo:  out += L( ka U (h_halo - h_wrap) )  for +z,  out += L( conj(ka) [Uhalo^+ h_halo - Uwrap^+ h_wrap] )  for -z,
+ * with L the linear map of the epilogue (MODE 0: +, 1: (cf|conj cf), 2: -g5, 3: -).  Faces are 1/Lzh of the sites.
+ *   face buffers  hz[c * Sz + j], c < 6: the projected half-spinor (a0..a2, b0..b2) of direction +z (D = 6, from rank z+1's
+ *                 first z) or -z (D = 7, from rank z-1's last z)
+ *   Uz halo       Uzh[(q * 9 + e) * Sz + j]: U_z of rank z-1's last-z sites of parity q (for the -z hop of parity 1-q) */
+template <class V2>
+TMB_HD void tmb_zface_row(const tmb_geom &g, int par, int j, int want_r, int *row, int *t) {
+  /* the row of pair j whose r = (t + x + y + par) & 1 equals want_r */
+  const int r0 = 2 * j; /* y even */
+  const int y = r0 % g.LY; const int tx = r0 / g.LY; const int x = tx % g.LX; const int tt = tx / g.LX;
+  (void)y;
+  const int re = (tt + x + par) & 1; /* r of the y-even row */
+  *row = re == want_r ? r0 : r0 + 1; *t = tt;
+}
+/* what rank z-1 needs for its +z hops (send_dn: D = 6 projection of this rank's z = 0 sites) and what rank z+1 needs for its
+ * -z hops (send_up: D = 7 projection of this rank's z = LZ-1 sites); `in` has parity pin, k in [0, 6 * Sz) */
+template <class V2> struct EwPackZFaces { V2 *up, *dn; const V2 *in; tmb_geom g; int pin;
+  __host__ __device__ void operator()(size_t k) const {
+    const int Sz = g.T * g.LX * g.LY / 2;
+    const int c = (int)(k / Sz), j = (int)(k - (size_t)c * Sz);
+    int row, t;
+    /* z = 0 site of the input parity: zh = 0 in a row with r_in = 0 */
+    tmb_zface_row<V2>(g, pin, j, 0, &row, &t);
+    {
+      const size_t i = (size_t)row * g.Lzh;
+      const int cc = c % 3, hi = c / 3; /* hi 0: a = s0 + i s2, hi 1: b = s1 - i s3 */
+      const V2 x = in[(size_t)(hi ? 3 + cc : cc) * g.Vh + i], y = in[(size_t)(hi ? 9 + cc : 6 + cc) * g.Vh + i];
+      dn[k] = hi ? c_comb<3>(x, y) : c_comb<2>(x, y);
+    }
+    tmb_zface_row<V2>(g, pin, j, 1, &row, &t);
+    {
+      const size_t i = (size_t)row * g.Lzh + (g.Lzh - 1);
+      const int cc = c % 3, hi = c / 3; /* hi 0: a = s0 - i s2, hi 1: b = s1 + i s3 */
+      const V2 x = in[(size_t)(hi ? 3 + cc : cc) * g.Vh + i], y = in[(size_t)(hi ? 9 + cc : 6 + cc) * g.Vh + i];
+      up[k] = hi ? c_comb<2>(x, y) : c_comb<3>(x, y);
+    }
+  } };
+/* U_z of this rank's last-z sites, both owner parities: out[(q * 9 + e) * Sz + j] (what rank z+1 needs), k in [0, 18 * Sz) */
+template <class V2> struct EwPackGaugeZHalo { V2 *out; const V2 *U; tmb_geom g;
+  __host__ __device__ void operator()(size_t k) const {
+    const int Sz = g.T * g.LX * g.LY / 2;
+    const int j = (int)(k % Sz); const int qe = (int)(k / Sz); const int e = qe % 9, q = qe / 9;
+    int row, t;
+    tmb_zface_row<V2>(g, q, j, 1, &row, &t); /* the site of parity q at zh = Lzh-1 has z = LZ-1 iff its row has r = 1 */
+    out[k] = U[(size_t)((q * 4 + 3) * 9 + e) * g.Vh + (size_t)row * g.Lzh + (g.Lzh - 1)];
+  } };
+/* the fix-up of one face site pair j of the OUTPUT parity par; U is the full 18-real link field */
+template <int MODE, class V2>
+TMB_HD void tmb_zfix_pair(V2 *out, const V2 *in, const V2 *U, const V2 *hz_up, const V2 *hz_dn, const V2 *Uzh, const tmb_geom &g,
+                          int par, int j, V2 ka3, V2 cf) {
+  const int Sz = g.T * g.LX * g.LY / 2;
+  int row, t;
+  for (int side = 0; side < 2; side++) { /* 0: the +z face site (r = 1, zh = Lzh-1), 1: the -z face site (r = 0, zh = 0) */
+    tmb_zface_row<V2>(g, par, j, side ? 0 : 1, &row, &t);
+    const size_t i = (size_t)row * g.Lzh + (side ? 0 : g.Lzh - 1);
+    const size_t iw = (size_t)row * g.Lzh + (side ? g.Lzh - 1 : 0); /* the slab's own opposite face: what the kernel used */
+    V2 d[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) d[c] = mk2<V2>(0, 0);
+    V2 ah[3], bh[3], aw[3], bw[3], u[9];
+    const V2 *hz = side ? hz_dn : hz_up;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ah[c] = hz[(size_t)c * Sz + j]; bh[c] = hz[(size_t)(3 + c) * Sz + j]; }
+    tmb_policies pol = {0, 0};
+    if (!side) { /* +z: same local link for both terms */
+      tmb_project<6, 0>(aw, bw, in, g.Vh, (int)iw, pol);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { ah[c] = c_sub(ah[c], aw[c]); bh[c] = c_sub(bh[c], bw[c]); }
+#pragma unroll
+      for (int e = 0; e < 9; e++) u[e] = U[(size_t)((par * 4 + 3) * 9 + e) * g.Vh + i];
+      tmb_link_accumulate<6>(d, u, ah, bh, ka3);
+    } else {     /* -z: the right link comes with the halo, the wrong one is the local link at the wrapped neighbour */
+#pragma unroll
+      for (int e = 0; e < 9; e++) u[e] = Uzh[(size_t)((1 - par) * 9 + e) * Sz + j];
+      tmb_link_accumulate<7>(d, u, ah, bh, ka3);
+      tmb_project<7, 0>(aw, bw, in, g.Vh, (int)iw, pol);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { aw[c] = mk2<V2>(-aw[c].x, -aw[c].y); bw[c] = mk2<V2>(-bw[c].x, -bw[c].y); }
+#pragma unroll
+      for (int e = 0; e < 9; e++) u[e] = U[(size_t)(((1 - par) * 4 + 3) * 9 + e) * g.Vh + iw];
+      tmb_link_accumulate<7>(d, u, aw, bw, ka3);
+    }
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      V2 o = out[(size_t)c * g.Vh + i], x = d[c];
+      if (MODE == 1) x = c_mul((c < 6) ? cf : c_conj(cf), x);
+      else if (MODE == 2) x = (c < 6) ? mk2<V2>(-x.x, -x.y) : x;
+      else if (MODE == 3) x = mk2<V2>(-x.x, -x.y);
+      out[(size_t)c * g.Vh + i] = c_add(o, x);
+    }
+  }
+}
+
 /* Epilogues (hopping.h:674-694):
  *   MODE 0  l = r                                   _store_res                 Hopping_Matrix
  *   MODE 1  l = (cf on s0,s1 | conj(cf) on s2,s3) r _hop_mul_g5_cmplx_and_store tm_times_Hopping_Matrix
