@@ -243,9 +243,10 @@ def cpu_baseline(ref, dims, target_s=10.0):
 class Session:
     """one library context on this rank's GPU: tmb_init (+ tmb_comm_init over `dist`), parameters, gauge"""
 
-    def __init__(self, dims, world, rank, local_rank, dist, gauge, p2p=True):
+    def __init__(self, dims, world, rank, local_rank, dist, gauge, p2p=True, nz=1):
         import tmlqcd_b200 as tm
         self.tm, self.world, self.rank, self.dist = tm, world, rank, dist
+        self.nz, self.nt, self.dims = nz, world // nz, dims
         os.environ["TMB_P2P"] = "1" if p2p else "0"
         self.dev = dev = tm.Device(*dims, device=local_rank)
         self.lib = lib = dev.lib
@@ -257,10 +258,12 @@ class Session:
             t_id = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
             dist.broadcast(t_id, 0)
             idbuf = (C.c_ubyte * 128)(*t_id.cpu().tolist())
-            dev.ck(lib.tmb_comm_init(C.cast(idbuf, C.c_void_p), world, rank))
+            dev.ck(lib.tmb_comm_init_grid(C.cast(idbuf, C.c_void_p), world // nz, nz, rank))
         dev.set_params(KAPPA, GMU)
         dev.gauge_upload(gauge)
         self.path = "peer" if lib.tmb_comm_peer_mode() else ("nccl" if world > 1 else "single")
+        if nz > 1:
+            self.path += f"+zsplit{nz}"
 
     def barrier(self):
         self.dev.ck(self.lib.tmb_sync())
@@ -299,7 +302,11 @@ class Session:
         t = torch.from_numpy(loc).cuda()
         lst = [torch.empty_like(t) for _ in range(self.world)] if self.rank == 0 else None
         self.dist.gather(t, lst, dst=0)
-        return torch.cat(lst).cpu().numpy() if self.rank == 0 else None
+        if self.rank != 0:
+            return None
+        if self.nz == 1:
+            return torch.cat(lst).cpu().numpy()
+        return unslab([x.cpu().numpy() for x in lst], self.dims, self.nt, self.nz, 2, 24)
 
     def operators_and_solve(self, src, E, O, keep=True):
         """the parity workload: both hops and Qtm_pm_psi on `src`, invert_eo on (E, O); fields gathered on rank 0"""
@@ -322,14 +329,37 @@ class Session:
         self.dev.close()
 
 
-def scatter_rows(dist, world, rank, arr, rows, cols):
-    """rank 0 holds arr[world * rows, cols]; every rank returns its block of `rows` rows (numpy)"""
+def slab(arr, dims, nt, nz, r, zdiv, cols):
+    """the part of a GLOBAL field that rank r = ct * nz + cz of an (nt x nz) grid holds: t is the slowest index of the
+    lexicographic and of the even/odd orderings, z the fastest (z / 2 for eo fields: zdiv = 2).  `dims` are the local extents."""
+    T, LX, LY, LZ = dims
+    ct, cz = r // nz, r % nz
+    a = arr.reshape(T * nt, LX * LY, LZ * nz // zdiv, cols)
+    return np.ascontiguousarray(a[ct * T:(ct + 1) * T, :, cz * (LZ // zdiv):(cz + 1) * (LZ // zdiv)]).reshape(-1, cols)
+
+
+def unslab(parts, dims, nt, nz, zdiv, cols):
+    T, LX, LY, LZ = dims
+    out = np.zeros((T * nt, LX * LY, LZ * nz // zdiv, cols))
+    for r, part in enumerate(parts):
+        ct, cz = r // nz, r % nz
+        out[ct * T:(ct + 1) * T, :, cz * (LZ // zdiv):(cz + 1) * (LZ // zdiv)] = part.reshape(T, LX * LY, LZ // zdiv, cols)
+    return out.reshape(-1, cols)
+
+
+def scatter_rows(dist, world, rank, arr, rows, cols, grid=None):
+    """rank 0 holds the global field; every rank returns its slab of `rows` rows (numpy).  grid = (dims, nt, nz, zdiv) for a
+    T x Z grid of ranks, None for T slabs (contiguous row blocks)"""
     import torch
     out = torch.empty((rows, cols), dtype=torch.float64, device="cuda")
     lst = None
     if rank == 0:
-        src = torch.from_numpy(np.ascontiguousarray(arr).reshape(world * rows, cols)).cuda()
-        lst = list(src.chunk(world))
+        if grid is not None and grid[2] > 1:
+            dims_, nt_, nz_, zdiv_ = grid
+            lst = [torch.from_numpy(slab(np.asarray(arr), dims_, nt_, nz_, r, zdiv_, cols)).cuda() for r in range(world)]
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(arr).reshape(world * rows, cols)).cuda()
+            lst = list(src.chunk(world))
     dist.scatter(out, lst, src=0)
     res = out.cpu().numpy()
     del out, lst
@@ -380,6 +410,7 @@ def main():
     ap.add_argument("--sweep-sustained", action="store_true", help="time the residency variants for >= 0.6 s each (power-capped regime; stderr)")
     ap.add_argument("--overlap", type=int, default=0, help="tmb_set_overlap flags: 1 PDL, 2 L2 gauge prefetch")
     ap.add_argument("--p2p-diag", type=int, default=0, help="tmb_set_p2p_diag bits (timing diagnostics, results invalid; needs TMB_P2P_DIAG=1)")
+    ap.add_argument("--nz", type=int, default=1, help="split Z over this many ranks as well (rank grid (gpus / nz) x nz); default: T only")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--hints", type=int, default=None)
     ap.add_argument("--xblock", type=int, default=None)
@@ -399,7 +430,10 @@ def main():
         dims = tuple(int(x) for x in args.lattice.lower().split("x"))
     else:
         dims = (48, 24, 24, 24) if args.gpus == 1 else ANCHOR_DIMS
-    gdims = (dims[0] * world,) + dims[1:]
+    nz = args.nz if world > 1 else 1
+    assert world % nz == 0
+    nt = world // nz
+    gdims = (dims[0] * nt, dims[1], dims[2], dims[3] * nz)
 
     if args.impl == "reference":
         run_reference(args, dims, real_stdout)
@@ -426,13 +460,13 @@ def main():
     else:
         if rank == 0:
             G["g"], G["srcs"], ref, gauge_how = reference_inputs(gdims)
-        g = scatter_rows(dist, world, rank, G.get("g"), V, 72)
-        srcs = [scatter_rows(dist, world, rank, G["srcs"][k] if rank == 0 else None, Vh, 24) for k in range(3)]
+        g = scatter_rows(dist, world, rank, G.get("g"), V, 72, (dims, nt, nz, 1))
+        srcs = [scatter_rows(dist, world, rank, G["srcs"][k] if rank == 0 else None, Vh, 24, (dims, nt, nz, 2)) for k in range(3)]
         gauge_how = gauge_how if rank == 0 else ""
     src, E, O = srcs
     log(f"rank {rank}: inputs ready in {time.perf_counter() - t_in:.1f} s")
 
-    S = Session(dims, world, rank, local_rank, dist, g, p2p=True)
+    S = Session(dims, world, rank, local_rank, dist, g, p2p=True, nz=nz)
     dev, lib = S.dev, S.lib
     if args.variant is not None or args.hints is not None or args.xblock is not None:
         dev.ck(lib.tmb_set_tuning(-1 if args.variant is None else args.variant, -1 if args.hints is None else args.hints, args.xblock or 0))
@@ -501,7 +535,7 @@ def main():
         "metric": "Hopping_Matrix GFLOP/s (eo, double, 1320 flop/site)", "value": gflops, "unit": "GFLOP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world, dims, gauge_how),
+        "config": dict(workload_config(world, dims, gauge_how), rank_grid_TxZ=[nt, nz], global_lattice_TxLXxLYxLZ=list(gdims)),
         "gflops_1608": sites * FLOP_SITE_REF * args.steps / (ms * 1e-3) / 1e9,
         "hbm_gbs_effective_per_gpu": achieved,
         "peer_mode": bool(lib.tmb_comm_peer_mode()),
@@ -690,7 +724,7 @@ def main():
         S.close()
     if world > 1 and not args.skip_parity:
         # the same global problem once more with NCCL halos and NCCL all-reduces (TMB_P2P=0), a short timing beside it
-        S2 = Session(dims, world, rank, local_rank, dist, g, p2p=False)
+        S2 = Session(dims, world, rank, local_rank, dist, g, p2p=False, nz=nz)
         a0, a1, a2 = S2.dev.field(src), S2.dev.field(), S2.dev.field()
         S2.time_pairs(args.warmup, a0, a1, a2)
         ms_n, _ = S2.time_pairs(max(args.steps, 50), a0, a1, a2)

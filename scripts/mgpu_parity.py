@@ -26,45 +26,63 @@ def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    Tl, LX, LY, LZ = (int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "8x8x8x8").split("x"))
-    T = Tl * world
+    args = [a for a in sys.argv[1:] if not a.startswith("--grid")]
+    grid = [a for a in sys.argv[1:] if a.startswith("--grid")]
+    nt, nz = (int(x) for x in grid[0].split("=")[1].split("x")) if grid else (world, 1)
+    assert nt * nz == world
+    ct, cz = rank // nz, rank % nz
+    Tl, LX, LY, LZl = (int(x) for x in (args[0] if args else "8x8x8x8").split("x"))
+    T, LZ = Tl * nt, LZl * nz
     rng = np.random.default_rng(2024)
     V, Vh = T * LX * LY * LZ, T * LX * LY * LZ // 2
     g = random_gauge(rng, V)
     k, p = random_spinor(rng, Vh), random_spinor(rng, Vh)
-    Vl, Vhl = V // world, Vh // world
-    sl, slh = slice(rank * Vl, (rank + 1) * Vl), slice(rank * Vhl, (rank + 1) * Vhl)
 
-    d = tm.Device(Tl, LX, LY, LZ, device=lr)
+    # the slab of rank (ct, cz): t is the slowest index of both orderings, z the fastest (eo fields: z/2 with LZl even)
+    def slab_eo(f):
+        return np.ascontiguousarray(f.reshape(T, LX * LY, LZ // 2, -1)[ct * Tl:(ct + 1) * Tl, :, cz * (LZl // 2):(cz + 1) * (LZl // 2)]).reshape(-1, f.shape[-1])
+
+    def slab_lex(f):
+        return np.ascontiguousarray(f.reshape(T, LX * LY, LZ, -1)[ct * Tl:(ct + 1) * Tl, :, cz * LZl:(cz + 1) * LZl]).reshape((-1,) + f.shape[1:])
+
+    def unslab(parts, zdiv, tail):
+        """inverse of slab_*: parts[rank] -> global array; zdiv = 2 for eo fields, 1 for lexicographic ones"""
+        out = np.zeros((T, LX * LY, LZ // zdiv) + tail)
+        for r, part in enumerate(parts):
+            a, b = r // nz, r % nz
+            out[a * Tl:(a + 1) * Tl, :, b * (LZl // zdiv):(b + 1) * (LZl // zdiv)] = part.reshape((Tl, LX * LY, LZl // zdiv) + tail)
+        return out
+    d = tm.Device(Tl, LX, LY, LZl, device=lr)
     idbuf = (C.c_ubyte * 128)()
     if rank == 0:
         d.ck(d.lib.tmb_comm_unique_id(C.cast(idbuf, C.c_void_p)))
     t_id = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
     dist.broadcast(t_id, 0)
     idbuf = (C.c_ubyte * 128)(*t_id.cpu().tolist())
-    d.ck(d.lib.tmb_comm_init(C.cast(idbuf, C.c_void_p), world, rank))
+    d.ck(d.lib.tmb_comm_init_grid(C.cast(idbuf, C.c_void_p), nt, nz, rank))
     d.set_params(KAPPA, GMU, THETA)
-    d.gauge_upload(g[sl])
+    d.gauge_upload(slab_lex(g))
     if rank == 0:
-        print("peer mode:", bool(d.lib.tmb_comm_peer_mode()), flush=True)
+        print(f"grid {nt} x {nz} (T x Z), peer mode:", bool(d.lib.tmb_comm_peer_mode()), flush=True)
 
     def gather(field):
         loc = torch.from_numpy(d.download(field)).cuda()
         out = [torch.empty_like(loc) for _ in range(world)]
         dist.all_gather(out, loc)
-        return torch.cat(out).cpu().numpy()
+        return unslab([o_.cpu().numpy() for o_ in out], 2, (24,)).reshape(-1, 24)
 
-    dk, dp, dl, dx = d.field(k[slh]), d.field(p[slh]), d.field(), d.field()
+    dk, dp, dl, dx = d.field(slab_eo(k)), d.field(slab_eo(p)), d.field(), d.field()
     res = {}
     plaq = C.c_double(0.)
-    d.ck(d.lib.tmb_measure_plaquette(C.byref(plaq)))  # all-reduced: the same value on every rank
+    if nz == 1:
+        d.ck(d.lib.tmb_measure_plaquette(C.byref(plaq)))  # all-reduced: the same value on every rank
     for ieo in (0, 1):
         d.call("Hopping_Matrix", ieo, dl, dk); res[f"hop{ieo}"] = gather(dl)
         d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3); res[f"tm_sub{ieo}"] = gather(dl)
     d.call("Qtm_pm_psi", dl, dk); res["Qtm_pm"] = gather(dl)
     sq = d.reduce("square_norm", dk)
     it = d.call("cg_her", dx, dk, 2000, 1e-22, 1); res["cg_x"] = gather(dx)
-    dE, dO, dEn, dOn = d.field(k[slh]), d.field(p[slh]), d.field(), d.field()
+    dE, dO, dEn, dOn = d.field(slab_eo(k)), d.field(slab_eo(p)), d.field(), d.field()
     it2 = d.call("invert_eo", dEn, dOn, dE, dO, 1e-22, 2000, 1)
     res["inv_e"], res["inv_o"] = gather(dEn), gather(dOn)
     # mixed-precision solvers (float hops through the same halo machinery)
@@ -77,14 +95,18 @@ def main():
     d.call("field_zero", dls); d.call("field_zero", dlc)
     itn = d.call("cg_her_nd", dls, dlc, dk, dp, 2000, 1e-20, 1); res["cgnd_s"], res["cgnd_c"] = gather(dls), gather(dlc)
     d.ck(d.lib.tmb_set_mcg_delta(0.1))
-    itr_nd = d.call("rg_mixed_cg_her_nd", dls, dlc, dk, dp, 2000, 1e-20, 1); res["rgnd_s"], res["rgnd_c"] = gather(dls), gather(dlc)
+    hmc = nz == 1  # the float two-flavour solver, the fermion force and the monomials are T-split only
+    if hmc:
+        itr_nd = d.call("rg_mixed_cg_her_nd", dls, dlc, dk, dp, 2000, 1e-20, 1); res["rgnd_s"], res["rgnd_c"] = gather(dls), gather(dlc)
     # fermion force and a det monomial with chronological guess (deriv_Sb exchanges the projected first slices)
 
     def gather_df():
         loc = torch.from_numpy(d.derivative_download()).cuda()
         out = [torch.empty_like(loc) for _ in range(world)]
         dist.all_gather(out, loc)
-        return torch.cat(out).cpu().numpy()
+        return unslab([o_.cpu().numpy() for o_ in out], 1, (4, 8)).reshape(-1, 4, 8)
+    if not hmc:
+        return finish(d, rank, world, T, LX, LY, LZ, g, k, p, Vh, res, sq, plaq, it, it2, itm, itg, itn, None, None, None, None, None, nz)
     d.call("derivative_zero")
     d.call("deriv_Sb", 0, dk, dp, 0.7); d.call("deriv_Sb", 1, dp, dk, -0.4)
     res["df"] = gather_df()
@@ -98,6 +120,11 @@ def main():
     res["mnl_df"] = gather_df()
     dH = C.c_double(); d.ck(d.lib.tmb_monomial_acc(0, C.byref(dH)))
     minfo = d.monomial_info(0)
+    return finish(d, rank, world, T, LX, LY, LZ, g, k, p, Vh, res, sq, plaq, it, it2, itm, itg, itn, itr_nd, e0, dH, minfo, margs, nz)
+
+
+def finish(d, rank, world, T, LX, LY, LZ, g, k, p, Vh, res, sq, plaq, it, it2, itm, itg, itn, itr_nd, e0, dH, minfo, margs, nz):
+    hmc = nz == 1
     d.set_params(KAPPA, GMU, THETA)
     ok = True
     if rank == 0:
@@ -110,7 +137,8 @@ def main():
             print(f"hop{ieo} rel {r1:.2e}  tm_sub{ieo} rel {r2:.2e}"); ok &= r1 <= 1e-13 and r2 <= 1e-13
         o.Qtm_pm_psi(e, k); r = rel_l2(res["Qtm_pm"], e); print(f"Qtm_pm rel {r:.2e}"); ok &= r <= 1e-13
         r = abs(sq / o.square_norm(k, Vh) - 1); print(f"global square_norm rel {r:.2e}"); ok &= r < 1e-14
-        r = abs(plaq.value / o.measure_plaquette() - 1); print(f"measure_plaquette rel {r:.2e}"); ok &= r < 1e-13
+        if hmc:
+            r = abs(plaq.value / o.measure_plaquette() - 1); print(f"measure_plaquette rel {r:.2e}"); ok &= r < 1e-13
         x = o.spinor(); itr = o.cg_her(x, k, 2000, 1e-22, 1); r = rel_l2(res["cg_x"], x)
         print(f"cg_her iters {it} (oracle {itr}) x rel {r:.2e}"); ok &= abs(it - itr) <= 1 and r <= 1e-10
         en, on = o.spinor(), o.spinor(); itr = o.invert_eo_cg(en, on, k, p, 1e-22, 2000, 1)
@@ -124,6 +152,9 @@ def main():
         es[:] = 0; ec[:] = 0; itr = o.cg_her_nd(es, ec, k, p, 2000, 1e-20, 1)
         r1, r2 = rel_l2(res["cgnd_s"], es), rel_l2(res["cgnd_c"], ec)
         print(f"cg_her_nd iters {itn} (oracle {itr}) rel {r1:.2e} {r2:.2e}"); ok &= abs(itn - itr) <= 1 and max(r1, r2) <= 1e-9
+        if not hmc:
+            print("MGPU PARITY", "OK" if ok else "FAILED", f"world={world} global={T}x{LX}x{LY}x{LZ} (Z split: operators and solvers)")
+            return close(d, ok)
         r1, r2 = rel_l2(res["rgnd_s"], es), rel_l2(res["rgnd_c"], ec)
         print(f"rg_mixed_cg_her_nd count {itr_nd}: x rel {r1:.2e} {r2:.2e}"); ok &= itr_nd > 0 and max(r1, r2) <= 1e-8
         df = o.derivative(); o.deriv_Sb(0, k, p, df, 0.7); o.deriv_Sb(1, p, k, df, -0.4)
@@ -138,6 +169,10 @@ def main():
               f"dH {dH.value:.2e} (oracle {dHr:.2e})")
         ok &= abs(e0.value / e0r - 1) <= 1e-13 and r <= 1e-8 and abs(minfo["iter1"] - oinfo["iter1"]) <= 3 and abs(dH.value - dHr) <= 1e-7
         print("MGPU PARITY", "OK" if ok else "FAILED", f"world={world} global={T}x{LX}x{LY}x{LZ}")
+    return close(d, ok)
+
+
+def close(d, ok):
     d.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

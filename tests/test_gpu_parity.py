@@ -468,6 +468,56 @@ def test_reductions_at_48x48x48x96_against_compensated_sums():
         d.close()
 
 
+@pytest.mark.parametrize("tloop", [0, 1, 2])
+def test_z_split_against_itself(oracle_lib, tloop):
+    """Second split direction (Z) with this rank as its own z neighbour (the real two-slab arithmetic is checked on the CPU
+    through the device code, tests/test_device_code_emul.py::test_z_split_face_exchange_and_fixup, and on several GPUs by
+    scripts/mgpu_parity.py --grid): face pack, exchange, fix-up, un-fused solver reductions, alone and on top of the T split"""
+    rng, o, d, g = _setup(oracle_lib, (8, 4, 6, 8), (1., 0.3, 0., 0.7))
+    try:
+        if tloop:
+            d.ck(d.lib.tmb_comm_loopback(tloop))
+        d.ck(d.lib.tmb_comm_loopback_z(1)); d.gauge_upload(g)
+        k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        dk, dp, dl, dx = d.field(k), d.field(p), d.field(), d.field()
+        exp = o.spinor()
+        for ieo in (0, 1):
+            o.Hopping_Matrix(ieo, exp, k); d.call("Hopping_Matrix", ieo, dl, dk); assert rel_l2(d.download(dl), exp) <= TOL
+            o.tm_times_Hopping_Matrix(ieo, exp, k, 0.9, -0.2); d.call("tm_times_Hopping_Matrix", ieo, dl, dk, 0.9, -0.2)
+            assert rel_l2(d.download(dl), exp) <= TOL
+            o.tm_sub_Hopping_Matrix(ieo, exp, p, k, 1.0, 0.3); d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3)
+            assert rel_l2(d.download(dl), exp) <= TOL
+        o.Qtm_pm_psi(exp, k); d.call("Qtm_pm_psi", dl, dk); assert rel_l2(d.download(dl), exp) <= TOL
+        e1, e2 = o.spinor(), o.spinor(); o.M_full(e1, e2, k, p)
+        dm = d.field(); d.call("M_full", dl, dm, dk, dp)
+        assert rel_l2(d.download(dl), e1) <= TOL and rel_l2(d.download(dm), e2) <= TOL
+        k32 = k.astype(np.float32); dk32, dl32 = d.field32(k32), d.field32()
+        o.Hopping_Matrix(1, exp, k); d.call("Hopping_Matrix_32", 1, dl32, dk32)
+        assert rel_l2(d.download32(dl32).astype(np.float64), exp) <= 1e-5
+        xr = o.spinor(); itr = o.cg_her(xr, k, 2000, 1e-22, 1)
+        it = d.call("cg_her", dx, dk, 2000, 1e-22, 1)
+        assert abs(it - itr) <= 1 and rel_l2(d.download(dx), xr) <= 1e-10
+        it = d.call("mixed_cg_her", dx, dk, 2000, 1e-22, 1)
+        assert it > 0 and rel_l2(d.download(dx), xr) <= 1e-9
+        en, on = o.spinor(), o.spinor(); itr = o.invert_eo_cg(en, on, k, p, 1e-22, 2000, 1)
+        dEn, dOn = d.field(), d.field()
+        it = d.call("invert_eo", dEn, dOn, dk, dp, 1e-22, 2000, 1)
+        assert abs(it - itr) <= 1 and rel_l2(d.download(dEn), en) <= 1e-10 and rel_l2(d.download(dOn), on) <= 1e-10
+        o.set_nd_params(*ND); d.ck(d.lib.tmb_set_nd(*ND))
+        es, ec = o.spinor(), o.spinor(); o.Qtm_pm_ndpsi(es, ec, k, p)
+        dls, dlc = d.field(), d.field(); d.call("Qtm_pm_ndpsi", dls, dlc, dk, dp)
+        assert rel_l2(d.download(dls), es) <= TOL and rel_l2(d.download(dlc), ec) <= TOL
+        # host-pointer hop on a split Z: plain upload / compute / download
+        out = np.zeros_like(k); d.call("Hopping_Matrix_host", 0, out, k, 0, 1., 0.)
+        o.Hopping_Matrix(0, exp, k); assert rel_l2(out, exp) <= TOL
+        # T-split-only entry points refuse loudly
+        import tmlqcd_b200 as tm
+        with pytest.raises(tm.capi.TmbError, match="split Z"):
+            d.call("deriv_Sb", 0, dk, dp, 1.0)
+    finally:
+        d.close()
+
+
 def test_dropin_reference_symbols(oracle_lib):
     """the reference-named entry points with host buffers (what a tmLQCD executable links)"""
     import tmlqcd_b200 as tm

@@ -57,6 +57,11 @@ struct Ctx {
   tmb_geom g;
   int nranks = 1, rank = 0;
   bool dist = false, loopback = false;
+  /* rank grid (nt x nz), rank = ct * nz + cz: T is split over nt, Z over nz (the reference's PARALLELT / the z part of
+   * PARALLELXYZT, mpi_init.c:321-357).  `dist` means "T is split (or looped back)"; zsplit "Z is split (or looped back)" */
+  int nt = 1, nz = 1, ct = 0, cz = 0; bool zsplit = false, loop_z = false;
+  double2 *zsend_up = nullptr, *zsend_dn = nullptr, *zhalo_up = nullptr, *zhalo_dn = nullptr, *Uzh = nullptr; float2 *Uzh32 = nullptr;
+  cudaEvent_t ev_z = nullptr;
   cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_up[MAXCHUNK] = {nullptr}, ev_done[MAXCHUNK] = {nullptr};
   cudaEvent_t ev_in = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
@@ -171,6 +176,12 @@ extern "C" int tmb_is_initialized(void) { return C.init ? 1 : 0; }
 extern "C" int tmb_volume_half(void) { return C.init ? C.g.Vh : 0; }
 extern "C" long long tmb_launch_count(void) { return C.launches; }
 extern "C" int tmb_comm_nranks(void) { return C.nranks; }
+extern "C" int tmb_comm_grid(int *nt, int *nz) { if (nt) *nt = C.nt; if (nz) *nz = C.nz; return 0; }
+static inline int t_up() { return ((C.ct + 1) % C.nt) * C.nz + C.cz; }
+static inline int t_dn() { return ((C.ct + C.nt - 1) % C.nt) * C.nz + C.cz; }
+static inline int z_up() { return C.ct * C.nz + (C.cz + 1) % C.nz; }
+static inline int z_dn() { return C.ct * C.nz + (C.cz + C.nz - 1) % C.nz; }
+static inline size_t SZ() { return (size_t)C.g.T * C.g.LX * C.g.LY / 2; } /* sites of one parity on a z face */
 
 extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   if (C.init) {
@@ -203,6 +214,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   }
   CU(cudaEventCreateWithFlags(&C.ev_in, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_halo, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&C.ev_z, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_chk[0], cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_chk[1], cudaEventDisableTiming));
   CU(cudaEventCreate(&C.ev_t0));
@@ -265,6 +277,9 @@ extern "C" int tmb_finalize(void) {
   cudaFree(C.U); cudaFree(C.Uhalo); cudaFree(C.stage); cudaFree(C.partial); cudaFree(C.st);
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
+  if (C.zsend_up) cudaFree(C.zsend_up); if (C.zsend_dn) cudaFree(C.zsend_dn); if (C.zhalo_up) cudaFree(C.zhalo_up);
+  if (C.zhalo_dn) cudaFree(C.zhalo_dn); if (C.Uzh) cudaFree(C.Uzh); if (C.Uzh32) cudaFree(C.Uzh32);
+  cudaEventDestroy(C.ev_z);
   cudaEventDestroy(C.ev_in); cudaEventDestroy(C.ev_halo); cudaEventDestroy(C.ev_t0); cudaEventDestroy(C.ev_t1);
   cudaEventDestroy(C.ev_chk[0]); cudaEventDestroy(C.ev_chk[1]);
   for (int i = 0; i < MAXCHUNK; i++) { cudaEventDestroy(C.ev_up[i]); cudaEventDestroy(C.ev_done[i]); }
@@ -362,7 +377,7 @@ static int setup_p2p() {
   CU(cudaMemcpy(msgs.data(), drecv, sizeof(Msg) * C.nranks, cudaMemcpyDeviceToHost));
   cudaFree(dsend); cudaFree(drecv);
   for (int r = 0; r < C.nranks; r++) ok = ok && msgs[r].ok;
-  const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
+  const int up = t_up(), dn = t_dn(); /* the hops read the T neighbours' fields */
   void *pu = nullptr, *pd = nullptr;
   /* all ranks' arenas when the cross-rank sums can use them (<= TMB_XR_MAXR ranks), the two T-neighbours' otherwise */
   const bool allp = C.nranks <= TMB_XR_MAXR;
@@ -391,15 +406,27 @@ static int setup_p2p() {
   if (allp) TRY(setup_xred(C.peer_base, C.nranks, C.rank));
   return 0;
 }
-extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) {
+static int z_buffers() {
+  const size_t fb = (size_t)6 * SZ() * sizeof(double2);
+  if (!C.zsend_up) { CU(cudaMalloc(&C.zsend_up, fb)); CU(cudaMalloc(&C.zsend_dn, fb)); CU(cudaMalloc(&C.zhalo_up, fb)); CU(cudaMalloc(&C.zhalo_dn, fb)); }
+  if (!C.Uzh) CU(cudaMalloc(&C.Uzh, (size_t)18 * SZ() * sizeof(double2)));
+  return 0;
+}
+extern "C" int tmb_comm_init_grid(const void *id128, int nt, int nz, int rank);
+extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) { return tmb_comm_init_grid(id128, nranks, 1, rank); }
+/* rank grid nt x nz, rank = ct * nz + cz; tmb_init's extents are the LOCAL ones (T / nt, LZ / nz, both even) */
+extern "C" int tmb_comm_init_grid(const void *id128, int nt, int nz, int rank) {
   NEED_INIT();
-  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(-5, "tmb_comm_init: bad rank %d of %d", rank, nranks);
-  if (nranks == 1) { C.nranks = 1; C.rank = 0; C.dist = C.loopback; C.g.dist_t = C.dist; return 0; }
+  const int nranks = nt * nz;
+  if (nt < 1 || nz < 1 || rank < 0 || rank >= nranks) return fail(-5, "tmb_comm_init: bad rank %d of %d x %d", rank, nt, nz);
+  if (nranks == 1) { C.nranks = 1; C.rank = 0; C.nt = C.nz = 1; C.ct = C.cz = 0; C.dist = C.loopback; C.g.dist_t = C.dist; C.zsplit = C.loop_z; return 0; }
   TRY(load_nccl());
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   NC(C.nccl.CommInitRank(&C.comm, nranks, id, rank));
-  C.nranks = nranks; C.rank = rank; C.dist = true; C.g.dist_t = 1;
+  C.nranks = nranks; C.rank = rank; C.nt = nt; C.nz = nz; C.ct = rank / nz; C.cz = rank % nz;
+  C.dist = nt > 1; C.g.dist_t = C.dist ? 1 : 0; C.zsplit = nz > 1; C.param_gen++;
+  if (C.zsplit) TRY(z_buffers());
   /* a gauge field uploaded before this call has no exchanged U_0 halo (nor float / 12-real copies of one): make the
    * next hop fail with "call tmb_gauge_upload first" instead of reading uninitialised Uhalo */
   C.gauge_loaded = false; C.gauge32_valid = false; C.c12_valid = false; C.c12f_valid = false;
@@ -407,6 +434,14 @@ extern "C" int tmb_comm_init(const void *id128, int nranks, int rank) {
   return 0;
 }
 extern "C" int tmb_comm_peer_mode(void) { return C.p2p ? 1 : 0; }
+/* single GPU: exercise the Z-split path (face pack, exchange with itself, fix-up) */
+extern "C" int tmb_comm_loopback_z(int on) {
+  NEED_INIT();
+  if (C.nranks > 1) return fail(-6, "tmb_comm_loopback_z: only for a single rank");
+  C.loop_z = on != 0; C.zsplit = C.loop_z; C.gauge_loaded = false; C.param_gen++;
+  if (C.zsplit) TRY(z_buffers());
+  return 0;
+}
 /* on = 1: halo buffers (pack / copy / boundary launch); on = 2: peer mode against itself (one launch, flags) */
 extern "C" int tmb_comm_loopback(int on) {
   NEED_INIT();
@@ -439,7 +474,7 @@ extern "C" int tmb_set_boundary(double kappa, const double theta[4]) {
   NEED_INIT();
   /* boundary.c:40-55, incl. its PI_ literal; global extents: only T is distributed */
   const double PI_ = 3.14159265358979;
-  const double ext[4] = {(double)C.g.T * C.nranks, (double)C.g.LX, (double)C.g.LY, (double)C.g.LZ};
+  const double ext[4] = {(double)C.g.T * C.nt, (double)C.g.LX, (double)C.g.LY, (double)C.g.LZ * C.nz};
   C.kappa = kappa; C.param_gen++;
   for (int m = 0; m < 4; m++) {
     const double x = (theta ? theta[m] : 0.) * PI_ / ext[m];
@@ -650,13 +685,29 @@ extern "C" int tmb_field_download_lexic(double *host, const void *even, const vo
 }
 
 /* exchange of the two T-face buffers: send_up -> rank+1's halo_dn, send_dn -> rank-1's halo_up */
-static int exchange_faces(const void *sup, const void *sdn, void *hup, void *hdn, size_t bytes, cudaStream_t s) {
-  if (C.nranks == 1) { /* loopback: this rank is its own neighbour in T */
+/* the same for the two Z faces: send_up -> rank z+1's halo_dn, send_dn -> rank z-1's halo_up */
+static int exchange_zfaces(const void *sup, const void *sdn, void *hup, void *hdn, size_t bytes, cudaStream_t s) {
+  if (C.nz == 1) { /* loopback */
     CU(cudaMemcpyAsync(hdn, sup, bytes, cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(hup, sdn, bytes, cudaMemcpyDeviceToDevice, s));
     return 0;
   }
-  const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
+  const int up = z_up(), dn = z_dn();
+  NC(C.nccl.GroupStart());
+  NC(C.nccl.Send(sup, bytes, NCCL_UINT8, up, C.comm, s));
+  NC(C.nccl.Recv(hdn, bytes, NCCL_UINT8, dn, C.comm, s));
+  NC(C.nccl.Send(sdn, bytes, NCCL_UINT8, dn, C.comm, s));
+  NC(C.nccl.Recv(hup, bytes, NCCL_UINT8, up, C.comm, s));
+  NC(C.nccl.GroupEnd());
+  return 0;
+}
+static int exchange_faces(const void *sup, const void *sdn, void *hup, void *hdn, size_t bytes, cudaStream_t s) {
+  if (C.nt == 1) { /* loopback: this rank is its own neighbour in T */
+    CU(cudaMemcpyAsync(hdn, sup, bytes, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(hup, sdn, bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  const int up = t_up(), dn = t_dn();
   NC(C.nccl.GroupStart());
   NC(C.nccl.Send(sup, bytes, NCCL_UINT8, up, C.comm, s));
   NC(C.nccl.Recv(hdn, bytes, NCCL_UINT8, dn, C.comm, s));
@@ -682,13 +733,29 @@ extern "C" int tmb_gauge_upload(const double *host_gauge) {
     const size_t n = (size_t)18 * C.g.S;
     CU(cudaMalloc(&tmp, n * sizeof(double2)));
     KL(tmb_launch_pack_gauge_halo(tmp, C.U, C.g, C.s_main));
-    if (C.nranks == 1) {
+    if (C.nt == 1) {
       CU(cudaMemcpyAsync(C.Uhalo, tmp, n * sizeof(double2), cudaMemcpyDeviceToDevice, C.s_main));
     } else {
-      const int up = (C.rank + 1) % C.nranks, dn = (C.rank + C.nranks - 1) % C.nranks;
+      const int up = t_up(), dn = t_dn();
       NC(C.nccl.GroupStart());
       NC(C.nccl.Send(tmp, 2 * n, NCCL_FLOAT64, up, C.comm, C.s_main));
       NC(C.nccl.Recv(C.Uhalo, 2 * n, NCCL_FLOAT64, dn, C.comm, C.s_main));
+      NC(C.nccl.GroupEnd());
+    }
+    CU(cudaStreamSynchronize(C.s_main));
+    CU(cudaFree(tmp));
+  }
+  if (C.zsplit) { /* U_z of rank z-1's last-z sites, for the -z hops of the z = 0 face */
+    double2 *tmp = nullptr;
+    const size_t n = (size_t)18 * SZ();
+    CU(cudaMalloc(&tmp, n * sizeof(double2)));
+    KL(tmb_launch_pack_gauge_zhalo(0, tmp, C.U, C.g, C.s_main));
+    if (C.nz == 1) {
+      CU(cudaMemcpyAsync(C.Uzh, tmp, n * sizeof(double2), cudaMemcpyDeviceToDevice, C.s_main));
+    } else {
+      NC(C.nccl.GroupStart());
+      NC(C.nccl.Send(tmp, 2 * n, NCCL_FLOAT64, z_up(), C.comm, C.s_main));
+      NC(C.nccl.Recv(C.Uzh, 2 * n, NCCL_FLOAT64, z_dn(), C.comm, C.s_main));
       NC(C.nccl.GroupEnd());
     }
     CU(cudaStreamSynchronize(C.s_main));
@@ -756,6 +823,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   a.nfl = o.nfl; a.in1 = o.in1; a.out1 = o.out1; a.p1 = o.p1;
   a.nd_mu = o.nd_mu; a.nd_eps = o.nd_eps; a.nd_scale = o.nd_scale; a.dot_scale = o.dot_scale;
   a.halo_up = C.halo_up; a.halo_dn = C.halo_dn;
+  if (C.zsplit && o.prec) TRY(ensure_gauge32()); /* the z fix-up reads the full float links */
   if (a.recon12) {
     TRY(ensure_gauge12(o.prec));
     a.U = o.prec ? (const void *)C.U12f : (const void *)C.U12;
@@ -773,6 +841,19 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   if (o.nfl == 2 && a.hints == 1 && !o.prec && !a.recon12) a.hints = 5;
   a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && fuse_fin()) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
   a.xr = a.fin_op >= 0 ? xr_tab() : nullptr;
+  /* Z split: the faces of `in` go to the z neighbours while the kernels below run on the slab as if it were periodic in z;
+   * the fix-up at the end replaces the wrapped z term of the face sites by the halo term (tmb_site.cuh) */
+  const bool zs = C.zsplit && !o.nocom;
+  if (zs) {
+    if (a.dot || o.mode == 4 || o.nfl == 2 || o.nsites >= 0 || o.boundary_only)
+      return fail(-12, "fused reductions, the CG tail, the two-flavour kernel and site sub-ranges are not available with a split Z direction");
+    const size_t fb = (size_t)6 * SZ() * (o.prec ? sizeof(float2) : sizeof(double2));
+    CU(cudaEventRecord(C.ev_in, C.s_main));
+    CU(cudaStreamWaitEvent(C.s_comm, C.ev_in, 0));
+    KL(tmb_launch_pack_zfaces(o.prec, C.zsend_up, C.zsend_dn, in, C.g, 1 - a.par, C.s_comm));
+    TRY(exchange_zfaces(C.zsend_up, C.zsend_dn, C.zhalo_up, C.zhalo_dn, fb, C.s_comm));
+    CU(cudaEventRecord(C.ev_z, C.s_comm));
+  }
   int np = 0;
   if (!C.dist || o.nocom) {
     a.dist = 0; a.site0 = o.site0; a.nsites = o.nsites < 0 ? C.g.Vh : o.nsites; a.split = a.nsites; a.gap = 0;
@@ -840,6 +921,11 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     if (nb_int > 0 && !o.boundary_only) KL(tmb_launch_hop(ai, C.s_main));
     CU(cudaStreamWaitEvent(C.s_main, C.ev_halo, 0));
     np = nb_int + tmb_hop_grid(a);
+  }
+  if (zs) {
+    CU(cudaStreamWaitEvent(C.s_main, C.ev_z, 0));
+    KL(tmb_launch_zfix(o.prec, o.mode, out, in, o.prec ? (const void *)C.U32 : (const void *)C.U, C.zhalo_up, C.zhalo_dn,
+                       o.prec ? (const void *)C.Uzh32 : (const void *)C.Uzh, C.g, a.par, C.ka[3], o.cf, o.st, C.s_main));
   }
   if (o.npartial) *o.npartial = np;
   return 0;
@@ -1005,6 +1091,12 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
   if (mode != 0 && mode != 1) return fail(-13, "tmb_Hopping_Matrix_host: mode must be 0 or 1");
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
   SCR(din, 12); SCR(dout, 13);
+  if (C.zsplit) { /* split Z: plain upload / compute / download */
+    TRY(tmb_field_upload(din, k_host));
+    HopOpt o; o.mode = mode; o.cf = make_double2(cre, cim);
+    TRY(hop(ieo, dout, din, o));
+    return tmb_field_download(l_host, dout);
+  }
   if (C.compression == 12) TRY(ensure_gauge12(0)); /* nothing may allocate or synchronise inside a capture */
   ensure_pinned(k_host, FIELD_BYTES()); ensure_pinned(l_host, FIELD_BYTES());
   CU(cudaStreamSynchronize(C.s_main));
@@ -1088,6 +1180,7 @@ extern "C" int tmb_tm_sub_H_eo_gamma5(void *l, const void *p, const void *k, int
 static int qtm_pm(double2 *l, const double2 *k, const double2 *dotw, const tmb_cg_state *st, int *np,
                   int fin_op = -1, int fin_slot = 0) {
   SCR(w0, 0); SCR(w1, 1);
+  if (C.zsplit && dotw != nullptr) return fail(-12, "no fused reduction with a split Z direction");
   const bool self = dotw != nullptr && dotw == k && C.cg_selfnorm;
   HopOpt a; a.mode = 1; a.cf = z_inv(-1.); a.st = st;
   TRY(hop(0, w1, k, a));
@@ -1317,8 +1410,9 @@ static int hop2_legacy(int ieo, void *o0, void *o1, const void *i0, const void *
 /* Which two-flavour kernel: the NFL = 2 instantiation of hop_kernel serves every precision, compression and communication
  * mode; round 1's one-thread-two-flavours kernel (tmb_force.cu) is 13 % faster where it applies - one rank, 18-real links,
  * double (32^3x64: 1.60 against 1.84 ms per Qtm_pm_ndpsi, profiles/r02_section_nd_first.json) - and is taken there. */
-static bool nd_legacy_ok() { return !C.dist && C.compression == 18; }
+static bool nd_legacy_ok() { return !C.dist && C.compression == 18 && !C.zsplit; }
 static bool nd_nfl2(int prec) {
+  if (C.zsplit) return false; /* split Z: single hops (each with its z fix-up) + sweeps */
   if (C.hop2_variant == 2) return true;
   if (C.hop2_variant == 0) return !nd_legacy_ok() && prec; /* forced: double falls back to single hops where the kernel does not apply */
   if (C.hop2_variant == 1) return prec != 0;               /* the lane-paired kernel is double only */

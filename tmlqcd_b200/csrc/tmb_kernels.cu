@@ -221,9 +221,10 @@ cudaError_t tmb_launch_dot(int prec, const void *a, const void *b, size_t n2, do
   RedDot<double2> f = {(const double2 *)a, (const double2 *)b}; RED_LAUNCH(f, n2, partial, nullptr, s);
 }
 /* <a,b> with the fused finish + CG bookkeeping (no all-reduce in between: single rank) */
-cudaError_t tmb_launch_dot_fin(const double2 *a, const double2 *b, size_t n2, double *partial, tmb_cg_state *st, int slot, int op,
+cudaError_t tmb_launch_dot_fin(int prec, const void *a, const void *b, size_t n2, double *partial, tmb_cg_state *st, int slot, int op,
                                const tmb_xred_table *xr, cudaStream_t s) {
-  RedDot<double2> f = {a, b}; RED_LAUNCH_FIN(f, n2, partial, st, st, slot, op, xr, s);
+  if (prec) { RedDot<float2> f = {(const float2 *)a, (const float2 *)b}; RED_LAUNCH_FIN(f, n2, partial, st, st, slot, op, xr, s); }
+  RedDot<double2> f = {(const double2 *)a, (const double2 *)b}; RED_LAUNCH_FIN(f, n2, partial, st, st, slot, op, xr, s);
 }
 cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s) {
   RedXpayNorm f = {r, sv, c}; RED_LAUNCH(f, n2, partial, nullptr, s);

@@ -112,7 +112,7 @@ cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s)
 int tmb_red_grid(size_t n2);
 cudaError_t tmb_launch_norm2(int prec, const void *a, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_dot(int prec, const void *a, const void *b, size_t n2, double *partial, cudaStream_t s);
-cudaError_t tmb_launch_dot_fin(const double2 *a, const double2 *b, size_t n2, double *partial, tmb_cg_state *st, int slot,
+cudaError_t tmb_launch_dot_fin(int prec, const void *a, const void *b, size_t n2, double *partial, tmb_cg_state *st, int slot,
                                int op, const tmb_xred_table *xr, cudaStream_t s);
 cudaError_t tmb_launch_xpay_norm(double2 *r, double c, const double2 *sv, size_t n2, double *partial, cudaStream_t s);
 cudaError_t tmb_launch_cg_update_xr(int prec, void *x, void *r, const void *p, const void *ap, size_t n2,
