@@ -1002,7 +1002,7 @@ static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int m
    * the two transfers is then one chunk of upload before the first download and what is left to download when the upload
    * ends; every copy costs ~17 us of latency whatever its size.  Hence few LARGE chunks (a sixth of the field) that halve
    * towards the end.  tmb_set_host_chunks(n > 0) forces n equal chunks.  Measured (24^3x48, link 55 GB/s one way, 48 GB/s
-   * per direction both ways): profiles/r02_e2e_summary.md. */
+   * per direction both ways): profiles/r02_summary.md (§ host-pointer calls) and profiles/r02_e2e_diag_final.log. */
   int cb[MAXCHUNK + 1], n = 0;
   cb[0] = t_lo;
   if (nt > 0) {
