@@ -61,6 +61,16 @@ int tmb_set_nd(double g_mubar, double g_epsbar, double phmc_invmaxev); /* tm_ope
  * of the plain kernel; 10 forces 448.  cache_hints: 1 = L2 eviction policies on the link / spinor loads, 0 = plain
  * loads, -1 (default) = policies only when links + CG vectors exceed the L2 (see eff_hints() in tmb_capi.cu) */
 int tmb_set_tuning(int hop_variant, int cache_hints, int xblock);
+/* CTA tile traversal of the hopping kernels (default OFF, TMB_TILE=1 in the environment turns it on): the four warps of a
+ * CTA take the same 32-site run at 2 x 2 neighbouring (t, x) instead of 128 consecutive sites, which turns neighbour-spinor
+ * requests to L2 into L1 hits (24^3x48: L1 hit rate 18.8 -> 24.3 %, L2 -> SM bytes 720 -> 667 MB per hop).  Memory layout and
+ * results are unchanged (bit for bit).  Measured: no gain, 1-5 % slower in every configuration (profiles/r02_tile_ab.jsonl) -
+ * the kernel is not bound by the L2 -> SM path - hence off; kept selectable like the other tuning variants.  Lattices whose
+ * LY*LZ/2 is not a multiple of 32 or whose T is odd always keep the linear traversal. */
+int tmb_set_tile(int on);
+/* tuning experiment: with tmb_set_overlap bit 1, the hopping kernels bulk-prefetch into L2 the gauge rows of the CTA `ctas`
+ * CTAs ahead of them (0: their own rows) */
+int tmb_set_prefetch_distance(int ctas);
 /* two-flavour hop: 2 = the hopping kernel with two flavour groups of warps per CTA (every precision, compression and
  * communication mode, fused <p, A p>); 0 = both flavours in one thread, 1 = lane-paired flavours (one rank, 18-real links, double
  * only); -1 (default) = 0 where it applies (measured faster there), 2 elsewhere */

@@ -173,6 +173,14 @@ void emul_xblock_perm(int *out, int T, int LX, int LY, int LZ, int XB) {
   }
 }
 
+/* CTA tile traversal (tmb_tile_site / tmb_tile_t of tmb_geom.h, used by hop_kernel and hop2_kernel); returns tmb_tile_ok */
+int emul_tile_perm(int *site, int *tslice, int T, int LX, int LY, int LZ, int tshift) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  if (!tmb_tile_ok(g)) return 0;
+  for (int w = 0; w < g.Vh; w++) { site[w] = tmb_tile_site(g, w, tshift); tslice[w] = tmb_tile_t(g, w, tshift); }
+  return 1;
+}
+
 /* peer mode: the halo buffers as the copy CTAs of hop_kernel pull them out of the neighbours' fields */
 void emul_pull_halo(double *halo_up, double *halo_dn, const double *in_up, const double *in_dn, int T, int LX, int LY, int LZ) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 1);

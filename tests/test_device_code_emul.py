@@ -126,6 +126,37 @@ def test_lexic_permutation_and_elementwise_functors(oracle_lib):
     assert rel_l2(e.unpack(o1), e1) < 1e-15 and rel_l2(e.unpack(o2), e2) < 1e-15
 
 
+@pytest.mark.parametrize("dims", [(8, 8, 8, 8), (4, 4, 8, 16), (6, 2, 16, 4), (2, 4, 8, 8), (12, 6, 24, 24), (4, 8, 6, 8), (3, 4, 8, 8)])
+def test_cta_tile_traversal(dims):
+    """The 2 x 2 x 32 CTA tiles of the hopping kernels (tmb_geom.h): a bijection of the sites; every warp keeps 32
+    consecutive sites; a CTA holds one 32-run at 2 time-slices x 2 x-planes; with the odd slice shift of the peer mode the
+    boundary slices T-1 and 0 share their CTAs (the kernel's `touches` rule finds exactly those)."""
+    e = Emul(*dims)
+    T, LX, LY, LZ = dims
+    P = LY * LZ // 2
+    for tshift in (0, (T // 2) | 1):
+        site, ts = np.zeros(e.Vh, dtype=np.int32), np.zeros(e.Vh, dtype=np.int32)
+        ok = e.E.emul_tile_perm(site, ts, *dims, tshift)
+        assert ok == int(P % 32 == 0 and T % 2 == 0 and LX % 2 == 0)
+        if not ok:
+            continue
+        assert e.Vh % 128 == 0
+        assert np.array_equal(np.sort(site), np.arange(e.Vh))
+        assert np.array_equal(ts, site // (LX * P))
+        w = site.reshape(-1, 4, 32)
+        assert np.all(np.diff(w, axis=2) == 1) and np.all(w[:, :, 0] % 32 == 0)      # warps: aligned consecutive runs
+        t, x, off = w[:, :, 0] // (LX * P), (w[:, :, 0] // P) % LX, w[:, :, 0] % P
+        assert np.all(off == off[:, :1])                                              # one run per CTA
+        assert np.all(x[:, 1] == x[:, 0] + 1) and np.all(x[:, 2] == x[:, 0]) and np.all(x[:, 3] == x[:, 1]) and np.all(x[:, 0] % 2 == 0)
+        assert np.all(t[:, 1] == t[:, 0]) and np.all(t[:, 2] == (t[:, 0] + 1) % T) and np.all(t[:, 3] == t[:, 2])
+        tl = ts.reshape(-1, 128)[:, 0]
+        touches = (tl == 0) | (tl >= T - 2)                                           # hop_kernel's boundary-CTA rule
+        has_boundary = np.any((t == 0) | (t == T - 1), axis=1)
+        assert np.array_equal(touches, has_boundary)
+        if tshift & 1 and T > 2:
+            assert np.all(t[touches][:, 0] == T - 1) and np.all(t[touches][:, 2] == 0)   # one tile layer holds both
+
+
 @pytest.mark.parametrize("dims,xb", [((4, 8, 4, 6), 2), ((4, 8, 4, 6), 4), ((6, 6, 2, 4), 3)])
 def test_xblock_traversal_is_a_permutation(dims, xb):
     e = Emul(*dims)

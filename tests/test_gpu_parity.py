@@ -33,7 +33,9 @@ def _setup(oracle_lib, dims, theta, seed=7):
 
 
 CASES = [((4, 4, 4, 4), (0., 0., 0., 0.)), ((8, 4, 6, 8), (1., 0.3, 0., 0.7)), ((6, 10, 2, 6), (1., 0., 0., 0.)),
-         ((8, 8, 8, 8), (0., 0., 0., 0.)), ((2, 6, 4, 4), (1., 0., 0.5, 0.))]  # last: T = 2, every slice is a boundary slice
+         ((8, 8, 8, 8), (0., 0., 0., 0.)), ((2, 6, 4, 4), (1., 0., 0.5, 0.)),  # T = 2, every slice is a boundary slice
+         # lattices whose LY*LZ/2 is a multiple of 32: the hopping kernels traverse them in 2 x 2 x 32 CTA tiles (tmb_geom.h)
+         ((4, 4, 8, 16), (1., 0.2, 0., 0.)), ((6, 2, 16, 4), (1., 0., 0., 0.3)), ((2, 4, 8, 8), (1., 0., 0., 0.))]
 
 
 @pytest.mark.parametrize("dims,theta", CASES)
@@ -57,6 +59,50 @@ def test_hopping_and_epilogues(oracle_lib, dims, theta, loopback):
             o.tm_sub_Hopping_Matrix(ieo, exp, p, k, 1.0, 0.3)
             d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3)
             assert rel_l2(d.download(dl), exp) <= TOL
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("dims", [(8, 8, 8, 8), (4, 4, 8, 16), (6, 2, 16, 4), (2, 4, 8, 8)])
+@pytest.mark.parametrize("loopback", [0, 1, 2])
+def test_cta_tile_traversal_changes_nothing(oracle_lib, dims, loopback):
+    """tmb_set_tile(1) (default) against tmb_set_tile(0): operators bit for bit, solvers with the same iteration counts -
+    one rank, halo buffers and the peer-mode kernel (whose boundary CTAs are found by a different rule when tiled);
+    double, float and 12-real links, the one- and the two-flavour kernels"""
+    rng, o, d, g = _setup(oracle_lib, dims, (1., 0.1, 0., 0.4))
+    try:
+        if loopback:
+            d.ck(d.lib.tmb_comm_loopback(loopback))
+            d.gauge_upload(g)
+        k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+        dk, dp, dl, dm = d.field(k), d.field(p), d.field(), d.field()
+        gk, gl = d.field32(k.astype(np.float32)), d.field32()
+        res = {}
+        for tile in (0, 1):
+            d.ck(d.lib.tmb_set_tile(tile))
+            r = []
+            for comp in (18, 12):
+                d.ck(d.lib.tmb_set_compression(comp))
+                for ieo in (0, 1):
+                    d.call("Hopping_Matrix", ieo, dl, dk); r.append(d.download(dl))
+                    d.call("tm_sub_Hopping_Matrix", ieo, dl, dp, dk, 1.0, 0.3); r.append(d.download(dl))
+                    d.call("Hopping_Matrix_32", ieo, gl, gk); r.append(d.download32(gl))
+                d.call("Qtm_pm_psi", dl, dk); r.append(d.download(dl))
+            d.ck(d.lib.tmb_set_compression(18))
+            d.call("Qtm_pm_ndpsi", dl, dm, dk, dp); r.append(d.download(dl)); r.append(d.download(dm))
+            d.call("field_zero", dl)
+            it = d.call("cg_her", dl, dk, 2000, 1e-20, 1)
+            x = d.download(dl)
+            d.call("field_zero", dl); d.call("field_zero", dm)
+            itnd = d.call("cg_her_nd", dl, dm, dk, dp, 2000, 1e-20, 1)
+            res[tile] = (r, it, x, itnd, d.download(dl))
+        for a, b in zip(res[0][0], res[1][0]):
+            assert np.array_equal(a, b)
+        assert abs(res[0][1] - res[1][1]) <= 1 and abs(res[0][3] - res[1][3]) <= 1
+        assert rel_l2(res[1][2], res[0][2]) <= 1e-12 and rel_l2(res[1][4], res[0][4]) <= 1e-12
+        exp = o.spinor()
+        o.Hopping_Matrix(1, exp, k)
+        assert rel_l2(res[1][0][3], exp) <= TOL      # (18-real, ieo = 1, plain hop) against the oracle
     finally:
         d.close()
 

@@ -80,7 +80,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = -1, hints = -1, xblock = 0, pdl = 0, prefetch = 0, cg_graph = 1, hop2_variant = -1, cg_selfnorm = 1, cg_tail = 1;
+  int hop_variant = -1, hints = -1, xblock = 0, tile = 0, pdl = 0, prefetch = 0, prefetch_dist = 0, cg_graph = 1, hop2_variant = -1, cg_selfnorm = 1, cg_tail = 1;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -233,7 +233,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.pdl = 0; C.prefetch = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = -1; C.cg_selfnorm = 1; C.cg_tail = 1;
+  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.tile = getenv("TMB_TILE") ? atoi(getenv("TMB_TILE")) : 0; C.pdl = 0; C.prefetch = 0; C.prefetch_dist = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = -1; C.cg_selfnorm = 1; C.cg_tail = 1;
   C.init = true;
   return 0;
 }
@@ -502,7 +502,15 @@ extern "C" int tmb_set_mu(double g_mu) { NEED_INIT(); if (C.mu != g_mu) { C.mu =
 extern "C" int tmb_set_nd(double mubar, double epsbar, double invmaxev) {
   NEED_INIT(); C.mubar = mubar; C.epsbar = epsbar; C.invmaxev = invmaxev; return 0;
 }
-extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < -1 || v > 2) return fail(-7, "hop2 variant must be -1 (automatic), 0, 1 or 2"); C.hop2_variant = v; return 0; }
+extern "C" int tmb_set_hop2_variant(int v) { NEED_INIT(); if (v < -1 || v > 3) return fail(-7, "hop2 variant must be -1 (automatic), 0, 1, 2 or 3"); C.hop2_variant = v; return 0; }
+/* with tmb_set_overlap bit 1 (L2 bulk prefetch of gauge rows): prefetch the rows of the CTA `ctas` CTAs ahead (one wave:
+ * 148 x resident CTAs per SM) instead of the CTA's own */
+extern "C" int tmb_set_prefetch_distance(int ctas) { NEED_INIT(); if (ctas < 0) return fail(-7, "prefetch distance must be >= 0"); C.prefetch_dist = ctas; C.param_gen++; return 0; }
+extern "C" int tmb_set_tile(int on) { /* CTA tile traversal of the hopping kernels (default off: measured, no gain; TMB_TILE=1) */
+  if (!C.init) return fail(-1, "not initialised");
+  C.tile = on ? 1 : 0; C.param_gen++;
+  return 0;
+}
 extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
   NEED_INIT();
   if (hop_variant < -1 || hop_variant > 10) return fail(-7, "hop_variant must be -1 (automatic) .. 10");
@@ -811,6 +819,10 @@ static bool hop_residency_448(int nsites) {
   if (w384 > 4.) return false;
   return ceil(w448) < ceil(w384);
 }
+/* CTA tile traversal (tmb_tile_site, tmb_geom.h): whole-lattice launches of the 128-site CTAs of the one-field kernels */
+static int hop_tile_ok(const tmb_hop_launch &a, bool whole) {
+  return C.tile && whole && a.nfl != 2 && a.xblock == 0 && tmb_tile_ok(a.g) && tmb_hop_block(a) == 128;
+}
 static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
   if (C.kappa == 0.) return fail(-9, "hopping parameter not set: call tmb_set_boundary first");
@@ -836,7 +848,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   a.partial = C.partial; a.st = o.st; a.g = C.g; a.par = ieo ? 1 : 0;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
   a.cf = o.cf; a.mode = o.mode; a.dot = o.selfnorm ? 2 : (o.dotw ? 1 : 0); a.hints = eff_hints();
-  a.pdl = C.pdl; a.prefetch = C.prefetch;
+  a.pdl = C.pdl; a.prefetch = C.prefetch; a.prefetch_dist = 0;
   /* the two flavour groups of the NFL = 2 kernel read the same links: let them allocate in L1 (32^3x64: 1.86 -> 1.81 ms) */
   if (o.nfl == 2 && a.hints == 1 && !o.prec && !a.recon12) a.hints = 5;
   a.st_fin = C.st; a.partial_base = C.partial; a.fin_op = (a.dot && fuse_fin()) ? o.fin_op : -1; a.fin_slot = o.fin_slot;
@@ -863,6 +875,8 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
       a.variant = (!a.recon12 && !o.prec && (C.hop_variant == 10 || hop_residency_448(a.nsites))) ? 10 : 0;
     if (o.nfl == 2) a.variant = 0;
     a.xblock = o.nsites < 0 ? C.xblock : 0;
+    a.tile = hop_tile_ok(a, o.nsites < 0);
+    if (!a.tile && !a.xblock) a.prefetch_dist = C.prefetch_dist;
     np = tmb_hop_grid(a);
     if (np > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", np, C.npartial);
     a.fin_total = np;
@@ -885,6 +899,7 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
     a.p2p_err = C.p2p_err; a.p2p_copied = C.p2p_ticket;
     a.halo_up_w = C.halo_up; a.halo_dn_w = C.halo_dn;
     a.p2p_copy_ctas = C.p2p_copy_ctas;
+    a.tile = hop_tile_ok(a, true);
     np = tmb_hop_grid(a);
     if (np > C.npartial) return fail(-10, "partial buffer too small (%d > %d)", np, C.npartial);
     a.fin_total = np;
@@ -1414,7 +1429,7 @@ static bool nd_legacy_ok() { return !C.dist && C.compression == 18 && !C.zsplit;
 static bool nd_nfl2(int prec) {
   if (C.zsplit) return false; /* split Z: single hops (each with its z fix-up) + sweeps */
   if (C.hop2_variant == 2) return true;
-  if (C.hop2_variant == 0) return !nd_legacy_ok() && prec; /* forced: double falls back to single hops where the kernel does not apply */
+  if (C.hop2_variant == 0 || C.hop2_variant == 3) return !nd_legacy_ok() && prec; /* forced: double falls back to single hops where the kernel does not apply */
   if (C.hop2_variant == 1) return prec != 0;               /* the lane-paired kernel is double only */
   return !nd_legacy_ok();
 }
@@ -1444,7 +1459,10 @@ static int hop2_legacy(int ieo, void *o0, void *o1, const void *i0, const void *
   a.in0 = i0; a.in1 = i1; a.out0 = o0; a.out1 = o1; a.p0 = p0; a.p1 = p1; a.g = C.g; a.par = ieo ? 1 : 0;
   a.prec = prec; a.U = prec ? (const void *)C.U32 : (const void *)C.U;
   for (int m = 0; m < 4; m++) a.ka[m] = C.ka[m];
-  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = eff_hints(); a.variant = (C.hop2_variant == 1 && !prec) ? 1 : 0;
+  a.mode = mode; a.mu = mu; a.eps = eps; a.scale = scale; a.hints = eff_hints(); a.variant = (C.hop2_variant == 1 && !prec) ? 1 : ((C.hop2_variant == 3 && !prec) ? 3 : 0);
+  a.prefetch = C.prefetch & 1; a.prefetch_dist = C.prefetch_dist;
+  a.tile = C.tile && a.variant != 1 && tmb_tile_ok(a.g);
+  if (a.tile) a.prefetch = 0;
   a.st = st; a.fin_op = -1;
   if (dot && dot->on) {
     if (a.variant == 1) return fail(-7, "the lane-paired two-flavour kernel has no fused norm");

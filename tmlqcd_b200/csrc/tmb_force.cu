@@ -123,10 +123,26 @@ cudaError_t tmb_launch_pack_gauge_first_slice(double2 *out, const double2 *U, tm
 template <class V2, int MODE, int DOT, int HINTS, int MINB>
 __global__ void __launch_bounds__(128, MINB) hop2_kernel(const tmb_hop2_launch a) {
   typedef typename tmb_real<V2>::type R;
+  if (a.prefetch && threadIdx.x < 72) { /* L2 bulk prefetch of the 8 x 9 gauge rows of the CTA prefetch_dist CTAs ahead (linear traversal) */
+    const int first = (blockIdx.x + a.prefetch_dist) * 128;
+    int n = a.g.Vh - first; n = n > 128 ? 128 : n;
+    if (n > 0) {
+      const int d = threadIdx.x / 9, e = threadIdx.x - 9 * d, mu = d >> 1, bwd = d & 1;
+      int j0 = first;
+      if (bwd) {
+        const int shift = mu == 0 ? a.g.S : (mu == 1 ? a.g.LY * a.g.Lzh : (mu == 2 ? a.g.Lzh : 0));
+        j0 = first - shift; if (j0 < 0) j0 += a.g.Vh;
+      }
+      if (j0 > a.g.Vh - n) j0 = a.g.Vh - n;
+      const V2 *src = (const V2 *)a.U + (size_t)(((bwd ? 1 - a.par : a.par) * 4 + mu) * 9 + e) * a.g.Vh + j0;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((int)(n * sizeof(V2))));
+    }
+  }
   if (a.st != nullptr && a.st->converged) return;
-  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int w = blockIdx.x * 128 + threadIdx.x;
+  const int i = a.tile ? tmb_tile_site(a.g, w, 0) : w; /* tiled: Vh is a multiple of 128 */
   double dsum = 0.;
-  if (i < a.g.Vh) {
+  if (w < a.g.Vh) {
     tmb_policies pol;
     pol.stream = tmb_policy_evict_first();
     pol.reuse = tmb_policy_evict_last();
@@ -265,6 +281,7 @@ static cudaError_t hop2_go(const tmb_hop2_launch &a, cudaStream_t s) {
     }
     return cudaGetLastError();
   }
+  if (a.variant == 3) return hop2_go1<double2, HINTS, 3>(a, s); /* 168 registers, ~1 KB of spills per thread */
   return hop2_go1<double2, HINTS, 2>(a, s);
 }
 int tmb_hop2_grid(const tmb_hop2_launch &a) { return (a.g.Vh + 127) / 128; }

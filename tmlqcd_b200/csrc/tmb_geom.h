@@ -50,6 +50,36 @@ TMB_HD int tmb_eo_to_lexic(const tmb_geom g, int par, int i) {
   return ((t * g.LX + x) * g.LY + y) * g.LZ + z;
 }
 
+/* CTA tile traversal of the hopping kernels (memory layout UNCHANGED): work index w -> eo-sub index such that the four
+ * warps of a 128-thread CTA take the SAME run of 32 consecutive (y,z) sites at (t0,x0), (t0,x0+1), (t0+1,x0), (t0+1,x0+1)
+ * instead of 128 consecutive sites of one (t,x) plane.  Every warp-wide load still covers 32 consecutive elements; what
+ * changes is how many of the 8 neighbour spinors of a site are ALSO neighbours (or the sites themselves) of other threads
+ * of the CTA, i.e. L1 hits instead of L2 requests.  Distinct input spinors a CTA touches, per output site:
+ *   128 consecutive sites (LZ/2 = 12):  1 + 2/10.7 (y) + 2 (x) + 2 (t)       = 5.2   (measured: L1 hit rate 35 % of 8)
+ *   2 x 2 x 32:                         1 + 2/2.7 (y) + 2/2 (x) + 2/2 (t)    = 3.75
+ * MEASURED (B200, scripts/tile_ab.py, profiles/r02_tile_ab.jsonl, profiles/r02_tile_ncu_metrics.csv): the L1 hit rate goes
+ * from 18.8 to 24.3 % and the L2 -> SM traffic from 720 to 667 MB per hop at 24^3x48, but the kernel gets 1-5 % SLOWER in
+ * every configuration (double, float, 12-real links, peer mode, two flavours; burst and power-capped): the L2 -> SM path is
+ * not what bounds it.  Off by default (tmb_set_tile); kept as a selectable variant.  tshift rotates the time-slices (peer
+ * mode: the boundary slices T-1 and 0 form ONE pair in the middle of the launch when tshift is odd). */
+TMB_HD int tmb_tile_ok(const tmb_geom g) {
+  return ((g.LY * g.Lzh) % 32 == 0) && (g.T % 2 == 0) && (g.LX % 2 == 0);
+}
+TMB_HD int tmb_tile_t(const tmb_geom g, int w, int tshift) { /* time-slice of work index w */
+  const int R = (g.LY * g.Lzh) >> 5, q = (w >> 5) & 3, c = (w >> 7) / R;
+  int t = 2 * (c / (g.LX >> 1)) + (q >> 1) + tshift;
+  return t >= g.T ? t - g.T : t;
+}
+TMB_HD int tmb_tile_site(const tmb_geom g, int w, int tshift) {
+  const int P = g.LY * g.Lzh, R = P >> 5;
+  const int lane = w & 31, q = (w >> 5) & 3, b = w >> 7;
+  const int c = b / R, r = b - c * R;
+  const int hx = g.LX >> 1, bt = c / hx, bx = c - bt * hx;
+  int t = 2 * bt + (q >> 1) + tshift;
+  if (t >= g.T) t -= g.T;
+  return (t * g.LX + 2 * bx + (q & 1)) * P + (r << 5) + lane;
+}
+
 /* Neighbour eo-sub indices (in the field of the OPPOSITE parity) of site i of parity `par`,
  * order +t,-t,+x,-x,+y,-y,+z,-z as g_hi[16*icx + 2d+1] (geometry_eo.c:1470-1536).
  * Periodic wrap inside the slab; with dist_t the caller replaces nb[0] for t==T-1 and nb[1]

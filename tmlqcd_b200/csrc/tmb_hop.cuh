@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
   asm volatile("griddepcontrol.launch_dependents;");
   const int NE = (HINTS & 2) ? 6 : 9; /* stored complex numbers per link (12-real compression: 6) */
   if ((a.prefetch & 1) && threadIdx.x < 8 * NE) {
-    const int first = blockIdx.x * SITES;
+    const int first = (blockIdx.x + a.prefetch_dist) * SITES;
     int n = a.nsites - first; n = n > SITES ? SITES : n;
     if (n > 0) {
       const int i0 = a.site0 + first + (first >= a.split ? a.gap : 0);
@@ -265,7 +265,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
       const int s0 = (a.g.T + 1) / 2;                               /* first slice of the rotated order */
       const int b0 = (a.g.T - 1 - s0) * S, b1 = b0 + 2 * S;        /* work range of slices T-1 and 0 */
       (void)Vh;
-      if (wb * SITES + SITES > b0 && wb * SITES < b1) { /* block-uniform: this CTA touches slice T-1 or slice 0 */
+      bool touches;
+      if (a.tile) { /* tiled traversal: the CTA holds the slice pair (tl, tl + 1 mod T) */
+        const int tl = tmb_tile_t(a.g, wb * SITES, (a.p2p_diag & 16) ? 0 : ((a.g.T >> 1) | 1));
+        touches = tl == 0 || tl >= a.g.T - 2;
+      } else touches = wb * SITES + SITES > b0 && wb * SITES < b1;
+      if (touches) { /* block-uniform: this CTA touches slice T-1 or slice 0 */
         bcta = !(a.p2p_diag & 8);
         if (threadIdx.x == 0) {
           const long long t0 = clock64();
@@ -288,7 +293,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) hop_kernel(const tmb_hop_launch a
   V2 r[12];
   if (active) {
     int ww = w;
-    if (DIST == 2 && !(a.p2p_diag & 16)) { /* rotated slice order s0, .., T-1, 0, .., s0-1 */
+    if (a.tile) { /* 2 x 2 x 32 CTA tiles; peer mode: slices rotated by an odd shift, so that T-1 and 0 share a tile layer */
+      ww = tmb_tile_site(a.g, w, (DIST == 2 && !(a.p2p_diag & 16)) ? ((a.g.T >> 1) | 1) : 0);
+    } else if (DIST == 2 && !(a.p2p_diag & 16)) { /* rotated slice order s0, .., T-1, 0, .., s0-1 */
       ww = w + ((a.g.T + 1) / 2) * a.g.S;
       if (ww >= a.g.Vh) ww -= a.g.Vh;
     }

@@ -16,6 +16,9 @@
 
 #include "tmb_hop.cuh"
 
+int tmb_hop_block(const tmb_hop_launch &a) { /* threads per CTA of the kernel tmb_launch_hop will pick */
+  return a.prec ? TMB_HOP_BLOCK_F : hop_variant_block(a.variant);
+}
 int tmb_hop_grid(const tmb_hop_launch &a) {
   const int b = (a.prec ? TMB_HOP_BLOCK_F : hop_variant_block(a.variant)) / (a.nfl == 2 ? 2 : 1); /* sites per CTA */
   return (a.nsites + b - 1) / b + (a.dist == 2 ? a.p2p_copy_ctas : 0);

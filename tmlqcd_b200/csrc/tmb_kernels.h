@@ -77,8 +77,10 @@ struct tmb_hop_launch {
   int site0, nsites;        /* contiguous work range ... */
   int split, gap;           /* ... with a hole: i = site0 + w + (w >= split ? gap : 0) */
   int xblock;               /* >0: traverse (t,x) planes x-blocked for L2 locality */
+  int tile;                 /* 1: CTA tile traversal 2 x 2 x 32 (tmb_tile_site, tmb_geom.h); whole-lattice launches of 128-site CTAs only */
   int pdl;                  /* launch with programmatic stream serialization (PDL) */
   int prefetch;             /* bulk-prefetch the CTA's gauge rows into L2 before the dependency wait */
+  int prefetch_dist;        /* ... the rows of the CTA this many CTAs AHEAD instead (linear traversal only; 0: own rows) */
   int recon12;              /* U / Uhalo hold 12-real compressed links (6 complex per link) */
   /* peer mode (dist == 2): ONE launch per hop.  Its first p2p_copy_ctas CTAs pull the projected boundary
    * time-slices out of the neighbours' copies of `in` (in_up / in_dn: peer memory over NVLink) into halo_up /
@@ -205,10 +207,13 @@ struct tmb_hop2_launch {
   const void *in0, *in1; void *out0, *out1; const void *p0, *p1; const void *U;
   tmb_geom g; int par; double2 ka[4];
   int mode; double mu, eps, scale; int hints;
-  int variant; /* 0: one thread carries both flavours (hop2_kernel, default), 1: lane-paired flavours (hop2p_kernel) */
+  int variant; /* 0: one thread carries both flavours (hop2_kernel, default), 1: lane-paired flavours (hop2p_kernel), 3: as 0 with 3 CTAs per SM (168 registers, spills) */
   int prec;    /* 1: float fields and float links (hop2_kernel only) */
+  int tile;    /* 1: CTA tile traversal (tmb_tile_site); hop2_kernel only */
+  int prefetch, prefetch_dist; /* hop2_kernel: L2 bulk prefetch of the gauge rows of the CTA prefetch_dist CTAs ahead */
   /* hop2_kernel, mode 2 only: dot == 2 accumulates dot_scale (|out0|^2 + |out1|^2) into partial[]; fin_op >= 0: fused finish */
   int dot; double dot_scale; double *partial; const tmb_cg_state *st; tmb_cg_state *st_fin; int fin_op, fin_slot; const tmb_xred_table *xr;
 };
 cudaError_t tmb_launch_hop2(const tmb_hop2_launch &a, cudaStream_t s);
 int tmb_hop2_grid(const tmb_hop2_launch &a);
+int tmb_hop_block(const tmb_hop_launch &a);
