@@ -71,6 +71,11 @@ int tmb_set_tile(int on);
 /* tuning experiment: with tmb_set_overlap bit 1, the hopping kernels bulk-prefetch into L2 the gauge rows of the CTA `ctas`
  * CTAs ahead of them (0: their own rows) */
 int tmb_set_prefetch_distance(int ctas);
+/* host-pointer Hopping_Matrix pipeline: explicit chunk sizes in time-slices (n = 0: automatic schedule), and a diagnostic
+ * run that returns (kind, first slice, microseconds) rows: kind 0 upload done, 1 kernels of a piece done, 2 download done,
+ * 3 end of the call */
+int tmb_set_host_chunk_sizes(const int *sizes, int n);
+int tmb_host_hop_timeline(int ieo, double *l_host, const double *k_host, double *out, int max_rows);
 /* two-flavour hop: 2 = the hopping kernel with two flavour groups of warps per CTA (every precision, compression and
  * communication mode, fused <p, A p>); 0 = both flavours in one thread, 1 = lane-paired flavours (one rank, 18-real links, double
  * only); -1 (default) = 0 where it applies (measured faster there), 2 elsewhere */

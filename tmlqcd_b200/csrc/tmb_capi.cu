@@ -64,6 +64,7 @@ struct Ctx {
   cudaEvent_t ev_z = nullptr;
   cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_up[MAXCHUNK] = {nullptr}, ev_done[MAXCHUNK] = {nullptr};
+  int host_sched[MAXCHUNK] = {0}, host_sched_n = 0; /* explicit chunk sizes of the host-pointer pipeline (tmb_set_host_chunk_sizes) */
   cudaEvent_t ev_in = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
   double2 *U = nullptr, *Uhalo = nullptr;
   double2 *send_up = nullptr, *send_dn = nullptr, *halo_up = nullptr, *halo_dn = nullptr;
@@ -521,6 +522,16 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
 /* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
 /* number of time-slice chunks of the pipelined host-pointer Hopping_Matrix (1..64) */
 extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 0 || n > MAXCHUNK) return fail(-7, "host chunks must be in [0, %d] (0: two time-slices per chunk)", MAXCHUNK); C.host_chunks = n; C.param_gen++; return 0; }
+/* explicit chunk sizes (time-slices, in order) for the pipelined host-pointer Hopping_Matrix; n = 0 returns to the automatic
+ * schedule.  Used when the sizes add up to the number of pipelined slices, ignored otherwise. */
+extern "C" int tmb_set_host_chunk_sizes(const int *sizes, int n) {
+  NEED_INIT();
+  if (n < 0 || n > MAXCHUNK - 2) return fail(-7, "at most %d chunks", MAXCHUNK - 2);
+  for (int i = 0; i < n; i++) if (sizes[i] <= 0) return fail(-7, "chunk sizes must be positive");
+  for (int i = 0; i < n; i++) C.host_sched[i] = sizes[i];
+  C.host_sched_n = n; C.param_gen++;
+  return 0;
+}
 extern "C" int tmb_set_overlap(int flags) {
   NEED_INIT();
   if (flags & ~63) return fail(-7, "tmb_set_overlap: unknown bits in 0x%x (bits 0..5 are defined)", flags);
@@ -1005,6 +1016,16 @@ static void ensure_pinned(const void *p, size_t bytes) {
   }
 }
 
+struct HopTrace { int kind, idx; cudaEvent_t ev; };
+static std::vector<HopTrace> g_trace; /* tmb_host_hop_timeline: timing events of one un-captured pipeline run */
+static bool g_tracing = false;
+static void trace_mark(int kind, int idx, cudaStream_t s) {
+  if (!g_tracing) return;
+  HopTrace t; t.kind = kind; t.idx = idx; t.ev = nullptr;
+  if (cudaEventCreate(&t.ev) != cudaSuccess) return;
+  cudaEventRecord(t.ev, s);
+  g_trace.push_back(t);
+}
 static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int mode, double cre, double cim, double2 *din, double2 *dout) {
   const int T = C.g.T, S = C.g.S, Vh = C.g.Vh;
   /* interior slices [t_lo, t_hi): all of them on one rank, 1 .. T-2 with a split T (slices 0 and T-1 wait for the faces) */
@@ -1015,13 +1036,21 @@ static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int m
    * so that piece p needs the inputs of chunks p-1 and p only - its download starts as soon as its own chunk is up, not one
    * chunk later - plus, on a periodic lattice, the wrap-around slice (last chunk, sent second).  What the pipeline adds to
    * the two transfers is then one chunk of upload before the first download and what is left to download when the upload
-   * ends; every copy costs ~17 us of latency whatever its size.  Hence few LARGE chunks (a sixth of the field) that halve
-   * towards the end.  tmb_set_host_chunks(n > 0) forces n equal chunks.  Measured (24^3x48, link 55 GB/s one way, 48 GB/s
-   * per direction both ways): profiles/r02_summary.md (§ host-pointer calls) and profiles/r02_e2e_diag_final.log. */
+   * ends; copies get slower the smaller they are once both directions are busy (tmb_host_hop_timeline, 24^3x48: a 10.6 MB
+   * upload takes ~255 us = 42 GB/s next to a running download, a 2.6 MB one ~105 us = 25 GB/s, against 55 GB/s alone).
+   * Hence few LARGE chunks (a sixth of the field), the first one split 1/4 + 3/4, halving towards the end.
+   * tmb_set_host_chunks(n > 0) forces n equal chunks, tmb_set_host_chunk_sizes an explicit schedule.  The upload stream is
+   * the critical path: it is busy from the start to ~0.1 ms before the end.  Measured schedules and timelines:
+   * profiles/r02_pipe_diag.log, profiles/r02_summary.md (section host-pointer calls). */
   int cb[MAXCHUNK + 1], n = 0;
   cb[0] = t_lo;
   if (nt > 0) {
-    if (C.host_chunks > 0) {
+    int sched_sum = 0;
+    for (int i = 0; i < C.host_sched_n; i++) sched_sum += C.host_sched[i];
+    if (C.host_sched_n > 0 && sched_sum == nt) {
+      int t = t_lo;
+      for (int i = 0; i < C.host_sched_n; i++) { t += C.host_sched[i]; cb[++n] = t; }
+    } else if (C.host_chunks > 0) {
       const int spc = (nt + C.host_chunks - 1) / C.host_chunks > 0 ? (nt + C.host_chunks - 1) / C.host_chunks : 1;
       for (int t = t_lo; t < t_hi; t += spc) cb[++n] = t + spc < t_hi ? t + spc : t_hi;
     } else {
@@ -1029,9 +1058,16 @@ static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int m
       while ((size_t)small * S * 192 < ((size_t)1 << 20) && small < nt) small++;
       int big = (nt + 5) / 6; if (big < small) big = small;
       int t = t_lo, rem = nt;
+      /* the first big chunk goes up as a quarter and three quarters: the first download starts ~150 us earlier (measured
+       * 24^3x48, profiles/r02_pipe_diag.log: 2,6,8,8,8,8,4,2,1,1 slices 1.66 ms against 8,8,8,8,8,4,2,2 1.70 ms per call) */
+      if (big >= 4 * small && 4 * rem > 7 * big) {
+        const int q = big / 4;
+        t += q; rem -= q; cb[++n] = t;
+        t += big - q; rem -= big - q; cb[++n] = t;
+      }
       while (4 * rem > 7 * big) { t += big; rem -= big; cb[++n] = t; }
       while (rem > 0) {
-        const int sz = rem <= 2 * small ? rem : ((rem + 1) / 2 > small ? (rem + 1) / 2 : small);
+        const int sz = rem <= small ? rem : ((rem + 1) / 2 > small ? (rem + 1) / 2 : small);
         t += sz; rem -= sz; cb[++n] = t;
       }
     }
@@ -1039,9 +1075,11 @@ static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int m
   if (n > MAXCHUNK - 2) return fail(-13, "too many chunks");
   double2 *in_aos = C.stage, *out_aos = C.stage + (size_t)12 * Vh;
   const double2 *hk = (const double2 *)k_host; double2 *hl = (double2 *)l_host;
-  auto up = [&](int t0, int t1, cudaEvent_t ev) -> int { /* input slices [t0, t1) to the device, event when they are there */
+  auto up = [&](int t0, int t1, cudaEvent_t ev) -> int { /* input slices [t0, t1) to the device, event when they are there.
+    * (Splitting a chunk into two concurrent copies on two streams was tried: 1.99 against 1.66 ms per call.) */
     CU(cudaMemcpyAsync(in_aos + (size_t)t0 * S * 12, hk + (size_t)t0 * S * 12, (size_t)(t1 - t0) * S * 192, cudaMemcpyHostToDevice, C.s_h2d));
     CU(cudaEventRecord(ev, C.s_h2d));
+    trace_mark(0, t0, C.s_h2d);
     return 0;
   };
   auto pack = [&](int t0, int t1, cudaEvent_t ev) -> int { /* AoS -> device layout on the compute stream, behind the copy */
@@ -1052,11 +1090,14 @@ static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int m
   auto down = [&](int t0, int t1, cudaEvent_t ev) -> int { /* device layout -> AoS, then output slices [t0, t1) to the host */
     KL(tmb_launch_unpack_eo_range(out_aos, dout, Vh, t0 * S, (t1 - t0) * S, C.s_main));
     CU(cudaEventRecord(ev, C.s_main));
+    trace_mark(1, t0, C.s_main);
     CU(cudaStreamWaitEvent(C.s_d2h, ev, 0));
     CU(cudaMemcpyAsync(hl + (size_t)t0 * S * 12, out_aos + (size_t)t0 * S * 12, (size_t)(t1 - t0) * S * 192, cudaMemcpyDeviceToHost, C.s_d2h));
+    trace_mark(2, t0, C.s_d2h);
     return 0;
   };
   /* fork: the copy streams join the work of s_main (also what makes them part of a graph capture) */
+  trace_mark(-1, 0, C.s_main);
   CU(cudaEventRecord(C.ev_in, C.s_main));
   CU(cudaStreamWaitEvent(C.s_h2d, C.ev_in, 0));
   CU(cudaStreamWaitEvent(C.s_d2h, C.ev_in, 0));
@@ -1154,6 +1195,36 @@ extern "C" int tmb_Hopping_Matrix_host(int ieo, double *l_host, const double *k_
   C.launches += hit->launches;
   CU(cudaStreamSynchronize(C.s_main));
   return 0;
+}
+
+/* Diagnostic: one un-captured run of the pipeline with a timing event behind every upload (kind 0), every piece's kernels
+ * (kind 1) and every download (kind 2).  out[3 i ..] = (kind, first time-slice, microseconds since the start); returns the
+ * number of rows (at most max_rows), the last one (kind 3) being the end of the call. */
+extern "C" int tmb_host_hop_timeline(int ieo, double *l_host, const double *k_host, double *out, int max_rows) {
+  NEED_INIT();
+  if (!C.gauge_loaded) return fail(-9, "no gauge field on the device: call tmb_gauge_upload first");
+  if (C.zsplit || C.dist) return fail(-12, "timeline: one rank only");
+  SCR(din, 12); SCR(dout, 13);
+  ensure_pinned(k_host, FIELD_BYTES()); ensure_pinned(l_host, FIELD_BYTES());
+  CU(cudaStreamSynchronize(C.s_main));
+  g_trace.clear(); g_tracing = true;
+  const int rc = host_hop_enqueue(ieo, l_host, k_host, 0, 0., 0., din, dout);
+  trace_mark(3, 0, C.s_main);
+  g_tracing = false;
+  cudaStreamSynchronize(C.s_main);
+  int rows = 0;
+  cudaEvent_t start = nullptr;
+  for (auto &t : g_trace) if (t.kind == -1) start = t.ev;
+  for (auto &t : g_trace) {
+    if (t.kind >= 0 && start && rows < max_rows) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, start, t.ev);
+      out[3 * rows] = t.kind; out[3 * rows + 1] = t.idx; out[3 * rows + 2] = 1e3 * ms; rows++;
+    }
+  }
+  for (auto &t : g_trace) cudaEventDestroy(t.ev);
+  g_trace.clear();
+  return rc < 0 ? rc : rows;
 }
 
 /* ------------------------------------------------------------------ operators on device fields */
