@@ -163,7 +163,7 @@ def test_cg_pro_from_second_hop(oracle_lib, loopback):
         xr = o.spinor()
         itr = o.cg_her(xr, k, 2000, 1e-22, 1)
         out = {}
-        for flags in (0, 16, 32):  # 32: the x / r update as a separate sweep instead of the last hop's epilogue
+        for flags in (0, 16, 32, 64, 4, 68):  # 32: x / r update as a separate sweep; 64: <p,Ap> finished on the side stream next to the third hop; 4: no CUDA graphs
             d.ck(d.lib.tmb_set_overlap(flags))
             d.call("field_zero", dx)
             it = d.call("cg_her", dx, dk, 2000, 1e-22, 1)
@@ -174,6 +174,8 @@ def test_cg_pro_from_second_hop(oracle_lib, loopback):
             assert itm > 0 and rel_l2(d.download(dx), xr) <= 1e-8
         assert out[0][0] == out[16][0] and rel_l2(out[0][1], out[16][1]) <= 1e-12
         assert out[0][0] == out[32][0] and rel_l2(out[0][1], out[32][1]) <= 1e-12
+        for f in (64, 4, 68):  # the same sums in the same order wherever they are finished: identical solutions
+            assert out[0][0] == out[f][0] and np.array_equal(out[0][1], out[f][1])
     finally:
         d.ck(d.lib.tmb_set_overlap(0))
         d.close()

@@ -64,6 +64,7 @@ struct Ctx {
   cudaEvent_t ev_z = nullptr;
   cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_up[MAXCHUNK] = {nullptr}, ev_done[MAXCHUNK] = {nullptr};
+  cudaEvent_t ev_side[2] = {nullptr, nullptr}; /* fork / join of the CG's <p,Ap> finish on the side stream */
   int host_sched[MAXCHUNK] = {0}, host_sched_n = 0; /* explicit chunk sizes of the host-pointer pipeline (tmb_set_host_chunk_sizes) */
   cudaEvent_t ev_in = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
   double2 *U = nullptr, *Uhalo = nullptr;
@@ -81,7 +82,7 @@ struct Ctx {
   int compression = 18; /* 18: full links; 12: two rows stored, third reconstructed (CompressionType, misc_types.h:33) */
   double2 *U12 = nullptr, *Uhalo12 = nullptr; float2 *U12f = nullptr, *Uhalo12f = nullptr; bool c12_valid = false, c12f_valid = false;
   double mixcg_innereps = 5.0e-5; int mixcg_maxinnersolverit = 5000; /* default_input_values.h:193-194 */
-  int hop_variant = -1, hints = -1, xblock = 0, tile = 0, pdl = 0, prefetch = 0, prefetch_dist = 0, cg_graph = 1, hop2_variant = -1, cg_selfnorm = 1, cg_tail = 1;
+  int hop_variant = -1, hints = -1, xblock = 0, tile = 0, pdl = 0, prefetch = 0, prefetch_dist = 0, cg_graph = 1, hop2_variant = -1, cg_selfnorm = 1, cg_tail = 1, cg_side = 0;
   NcclApi nccl = {};
   ncclComm_t comm = nullptr;
   std::vector<void *> fields; std::vector<size_t> field_bytes;
@@ -216,6 +217,8 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   CU(cudaEventCreateWithFlags(&C.ev_in, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_halo, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_z, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&C.ev_side[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&C.ev_side[1], cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_chk[0], cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&C.ev_chk[1], cudaEventDisableTiming));
   CU(cudaEventCreate(&C.ev_t0));
@@ -234,7 +237,7 @@ extern "C" int tmb_init(int T, int LX, int LY, int LZ, int device) {
   C.kappa = 0.; C.mu = 0.;
   for (int m = 0; m < 4; m++) C.ka[m] = make_double2(0., 0.);
   C.nranks = 1; C.rank = 0; C.dist = false; C.loopback = false; C.gauge_loaded = false;
-  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.tile = getenv("TMB_TILE") ? atoi(getenv("TMB_TILE")) : 0; C.pdl = 0; C.prefetch = 0; C.prefetch_dist = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = -1; C.cg_selfnorm = 1; C.cg_tail = 1;
+  C.launches = 0; C.hop_variant = -1; C.hints = -1; C.xblock = 0; C.tile = getenv("TMB_TILE") ? atoi(getenv("TMB_TILE")) : 0; C.pdl = 0; C.prefetch = 0; C.prefetch_dist = 0; C.compression = 18; C.cg_graph = 1; C.hop2_variant = -1; C.cg_selfnorm = 1; C.cg_tail = 1; C.cg_side = 0;
   C.init = true;
   return 0;
 }
@@ -534,9 +537,10 @@ extern "C" int tmb_set_host_chunk_sizes(const int *sizes, int n) {
 }
 extern "C" int tmb_set_overlap(int flags) {
   NEED_INIT();
-  if (flags & ~63) return fail(-7, "tmb_set_overlap: unknown bits in 0x%x (bits 0..5 are defined)", flags);
+  if (flags & ~127) return fail(-7, "tmb_set_overlap: unknown bits in 0x%x (bits 0..6 are defined)", flags);
   C.pdl = flags & 1; C.prefetch = ((flags >> 1) & 1) | ((flags & 8) ? 2 : 0); C.cg_graph = (flags & 4) ? 0 : 1; C.cg_selfnorm = (flags & 16) ? 0 : 1;
   C.cg_tail = (flags & 32) ? 0 : 1;
+  C.cg_side = (flags & 64) ? 1 : 0;
   C.param_gen++;
   return 0;
 }
@@ -1296,11 +1300,24 @@ static int qtm_pm_cg(int prec, void *x, void *r, const void *p, int err_op, int 
   HopOpt a; a.prec = prec; a.mode = 1; a.cf = z_inv(-1.); a.st = C.st;
   TRY(hop(0, w1, p, a));
   HopOpt b; b.prec = prec; b.mode = 2; b.cf = z_fwd(-1.); b.p = p; b.st = C.st;
-  b.selfnorm = true; b.npartial = &np; b.fin_op = fuse ? TMB_FIN_CG_PRO : -1; b.fin_slot = 1;
+  /* <p, A p> = |Q- p|^2 comes out of the second hop as per-CTA partials; alpha is needed by the FOURTH hop only.  Default:
+   * finished by the last CTA of the second hop (fence + ticket per CTA; ncu: 103.3 against 89.4 us for that launch at
+   * 24^3x48).  Experiment (tmb_set_overlap bit 6): the finish as a one-CTA kernel on the side stream WHILE the third hop
+   * runs.  Same sums, bit-identical solutions, but the two cross-stream dependencies cost more than the tail they remove:
+   * 0.475 against 0.459 ms per iteration at 24^3x48, 0.134 against 0.118 at 16^3x32 (profiles/r02_cg_side_ab.log). */
+  const bool side = fuse && C.cg_side;
+  b.selfnorm = true; b.npartial = &np; b.fin_op = (fuse && !side) ? TMB_FIN_CG_PRO : -1; b.fin_slot = 1;
   TRY(hop(1, w0, w1, b));
   if (!fuse) TRY(reduce_to(np, 1, TMB_FIN_CG_PRO)); /* alpha must exist before the fourth hop starts */
+  if (side) {
+    CU(cudaEventRecord(C.ev_side[0], C.s_main));
+    CU(cudaStreamWaitEvent(C.s_comm, C.ev_side[0], 0));
+    KL(tmb_launch_final_hop(C.partial, np, C.st, 1, TMB_FIN_CG_PRO, 1, xr_tab(), C.s_comm));
+    CU(cudaEventRecord(C.ev_side[1], C.s_comm));
+  }
   HopOpt c; c.prec = prec; c.mode = 1; c.cf = z_inv(+1.); c.st = C.st;
   TRY(hop(0, w1, w0, c));
+  if (side) CU(cudaStreamWaitEvent(C.s_main, C.ev_side[1], 0));
   HopOpt d; d.prec = prec; d.mode = 4; d.cf = z_fwd(+1.); d.p = w0; d.st = C.st;
   d.cg_x = x; d.cg_r = r; d.cg_p = p;
   d.selfnorm = true; d.npartial = np_err; d.fin_op = fuse ? err_op : -1; d.fin_slot = 2;

@@ -179,12 +179,13 @@ __global__ void __launch_bounds__(RED_BLOCK) red_kernel(F f, size_t n2, double *
 }
 
 /* one CTA: sums the block partials in a fixed order (deterministic), then the CG bookkeeping */
-__global__ void __launch_bounds__(RED_BLOCK) final_kernel(const double *partial, int n, tmb_cg_state *st, int slot,
-                                                           int op, int apply, const tmb_xred_table *xr) {
+template <int B>
+__global__ void __launch_bounds__(B) final_kernel(const double *partial, int n, tmb_cg_state *st, int slot,
+                                                  int op, int apply, const tmb_xred_table *xr) {
   if (op != TMB_FIN_STORE && st->converged) return;
   double acc = 0.;
-  for (int k = threadIdx.x; k < n; k += RED_BLOCK) acc += partial[k];
-  double s = block_sum<RED_BLOCK>(acc);
+  for (int k = threadIdx.x; k < n; k += B) acc += partial[k];
+  double s = block_sum<B>(acc);
   if (threadIdx.x == 0) {
     if (xr != nullptr) s = xred_sum(xr, s);
     st->tmp[slot] = s;
@@ -198,7 +199,14 @@ __global__ void apply_kernel(tmb_cg_state *st, int slot, int op) {
 
 cudaError_t tmb_launch_final(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
                              const tmb_xred_table *xr, cudaStream_t s) {
-  final_kernel<<<1, RED_BLOCK, 0, s>>>(partial, n, st, slot, op, apply, xr);
+  final_kernel<RED_BLOCK><<<1, RED_BLOCK, 0, s>>>(partial, n, st, slot, op, apply, xr);
+  return cudaGetLastError();
+}
+/* the same with the summation tree of the hopping kernels' own finish (finish_last_block<128>): bit-identical sums
+ * whether a hop's partials are finished inside the kernel or next to the following one */
+cudaError_t tmb_launch_final_hop(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
+                                 const tmb_xred_table *xr, cudaStream_t s) {
+  final_kernel<TMB_HOP_BLOCK><<<1, TMB_HOP_BLOCK, 0, s>>>(partial, n, st, slot, op, apply, xr);
   return cudaGetLastError();
 }
 __global__ void seq_bump_kernel(unsigned int *base, unsigned int n) { *base += n; }

@@ -109,6 +109,8 @@ cudaError_t tmb_launch_hop_nd(const tmb_hop_launch &a, cudaStream_t s); /* nfl =
 /* reductions: block partials -> one scalar in st->tmp[slot] (+ optional CG bookkeeping) */
 cudaError_t tmb_launch_final(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
                              const tmb_xred_table *xr, cudaStream_t s);
+cudaError_t tmb_launch_final_hop(const double *partial, int n, tmb_cg_state *st, int slot, int op, int apply,
+                             const tmb_xred_table *xr, cudaStream_t s);
 cudaError_t tmb_launch_seq_bump(unsigned int *base, unsigned int n, cudaStream_t s); /* *base += n */
 cudaError_t tmb_launch_apply(tmb_cg_state *st, int slot, int op, cudaStream_t s);
 int tmb_red_grid(size_t n2);
