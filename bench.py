@@ -263,7 +263,7 @@ class Session:
         dev.gauge_upload(gauge)
         self.path = "peer" if lib.tmb_comm_peer_mode() else ("nccl" if world > 1 else "single")
         if nz > 1:
-            self.path += f"+zsplit{nz}"
+            self.path += f"+zsplit{nz}" + ("(peer)" if lib.tmb_comm_zpeer_mode() else "(nccl)")
 
     def barrier(self):
         self.dev.ck(self.lib.tmb_sync())

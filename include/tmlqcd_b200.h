@@ -47,6 +47,7 @@ int tmb_comm_grid(int *nt, int *nz);
 int tmb_comm_loopback(int on); /* single GPU: exercise the T-split path against itself; 1: halo buffers, 2: peer mode */
 int tmb_comm_loopback_z(int on); /* single GPU: exercise the Z-split path (face pack, exchange, fix-up) against itself */
 int tmb_comm_peer_mode(void);  /* 1 if the hops read the neighbours' fields directly over NVLink (CUDA IPC), 0: NCCL halos */
+int tmb_comm_zpeer_mode(void); /* 1 if the z faces of a Z-split grid are pushed into the z neighbours' memory (CUDA IPC), 0: NCCL send/recv */
 int tmb_comm_nranks(void);
 
 /* ---- parameters: the globals the reference operators read at call time ---- */

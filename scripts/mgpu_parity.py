@@ -63,7 +63,7 @@ def main():
     d.set_params(KAPPA, GMU, THETA)
     d.gauge_upload(slab_lex(g))
     if rank == 0:
-        print(f"grid {nt} x {nz} (T x Z), peer mode:", bool(d.lib.tmb_comm_peer_mode()), flush=True)
+        print(f"grid {nt} x {nz} (T x Z), peer mode:", bool(d.lib.tmb_comm_peer_mode()), "z faces through peer memory:", bool(d.lib.tmb_comm_zpeer_mode()), flush=True)
 
     def gather(field):
         loc = torch.from_numpy(d.download(field)).cuda()

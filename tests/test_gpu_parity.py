@@ -516,8 +516,9 @@ def test_reductions_at_48x48x48x96_against_compensated_sums():
         d.close()
 
 
+@pytest.mark.parametrize("zmode", [1, 2])  # 1: packed faces + copy (the NCCL path's stand-in), 2: faces pushed through peer memory + flags
 @pytest.mark.parametrize("tloop", [0, 1, 2])
-def test_z_split_against_itself(oracle_lib, tloop):
+def test_z_split_against_itself(oracle_lib, tloop, zmode):
     """Second split direction (Z) with this rank as its own z neighbour (the real two-slab arithmetic is checked on the CPU
     through the device code, tests/test_device_code_emul.py::test_z_split_face_exchange_and_fixup, and on several GPUs by
     scripts/mgpu_parity.py --grid): face pack, exchange, fix-up, un-fused solver reductions, alone and on top of the T split"""
@@ -525,7 +526,7 @@ def test_z_split_against_itself(oracle_lib, tloop):
     try:
         if tloop:
             d.ck(d.lib.tmb_comm_loopback(tloop))
-        d.ck(d.lib.tmb_comm_loopback_z(1)); d.gauge_upload(g)
+        d.ck(d.lib.tmb_comm_loopback_z(zmode)); d.gauge_upload(g)
         k, p = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
         dk, dp, dl, dx = d.field(k), d.field(p), d.field(), d.field()
         exp = o.spinor()

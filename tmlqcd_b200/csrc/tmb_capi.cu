@@ -60,8 +60,13 @@ struct Ctx {
   /* rank grid (nt x nz), rank = ct * nz + cz: T is split over nt, Z over nz (the reference's PARALLELT / the z part of
    * PARALLELXYZT, mpi_init.c:321-357).  `dist` means "T is split (or looped back)"; zsplit "Z is split (or looped back)" */
   int nt = 1, nz = 1, ct = 0, cz = 0; bool zsplit = false, loop_z = false;
-  double2 *zsend_up = nullptr, *zsend_dn = nullptr, *zhalo_up = nullptr, *zhalo_dn = nullptr, *Uzh = nullptr; float2 *Uzh32 = nullptr;
+  double2 *zsend_up = nullptr, *zsend_dn = nullptr, *zhalo_up = nullptr, *zhalo_dn = nullptr, *Uzh = nullptr, *Uzl = nullptr; float2 *Uzh32 = nullptr, *Uzl32 = nullptr;
   cudaEvent_t ev_z = nullptr;
+  /* Z faces through peer memory (push): this rank's double-buffered halo buffers, where its own faces go on the z
+   * neighbours, this rank's two flags and the neighbours' (ARENA_ZFLAGS) */
+  bool zpeer = false; char *zloop_buf = nullptr;
+  void *zloc_up[2] = {nullptr, nullptr}, *zloc_dn[2] = {nullptr, nullptr}, *zdst_up[2] = {nullptr, nullptr}, *zdst_dn[2] = {nullptr, nullptr};
+  unsigned int *zflags = nullptr, *zflag_at_up = nullptr, *zflag_at_dn = nullptr;
   cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_up[MAXCHUNK] = {nullptr}, ev_done[MAXCHUNK] = {nullptr};
   cudaEvent_t ev_side[2] = {nullptr, nullptr}; /* fork / join of the CG's <p,Ap> finish on the side stream */
@@ -102,6 +107,7 @@ struct Ctx {
   /* sequence numbers of the peer-mode hops are *seq_dev + hop_off: the host counts offsets, the device base only moves
    * at the end of a replayed CG graph (whose kernels carry fixed offsets); seq_dev[1] is the reduction counter of xred_sum */
   unsigned int *seq_dev = nullptr; unsigned int hop_off = 0;
+  unsigned int zhop_off = 0; /* the same for the z-face pushes (base seq_dev[2]): their own count, its parity picks the halo buffer */
   char *peer_base[TMB_XR_MAXR] = {nullptr};   /* every rank's arena ([rank] = own) when nranks <= TMB_XR_MAXR */
   tmb_xred_table *xr_tab = nullptr; bool xred = false; /* cross-rank sums inside the reduction finish (no NCCL in the CG) */
   /* HMC side (tmb_capi_hmc.inc) */
@@ -144,6 +150,7 @@ static inline const double2 *F(const void *p) { return (const double2 *)p; }
  * on all ranks (SPMD), so that "the same field on the neighbouring rank" is the neighbour's arena base plus
  * this rank's offset - what the peer-mode hopping kernel dereferences over NVLink. */
 #define ARENA_RESERVED 4096 /* start of the arena: hop flags at 0, landing arrays of the cross-rank sums at 1024 (values) and 2048 (sequence words) */
+#define ARENA_ZFLAGS 512 /* two words: [0] this rank's halo_dn has been filled (by rank z-1), [1] its halo_up (by rank z+1) */
 #define ARENA_XR_VAL 1024
 #define ARENA_XR_SEQ 2048
 static inline bool in_arena(const void *p) {
@@ -282,8 +289,9 @@ extern "C" int tmb_finalize(void) {
   cudaFree(C.send_up); cudaFree(C.send_dn); cudaFree(C.halo_up); cudaFree(C.halo_dn);
   cudaFreeHost(C.st_host);
   if (C.zsend_up) cudaFree(C.zsend_up); if (C.zsend_dn) cudaFree(C.zsend_dn); if (C.zhalo_up) cudaFree(C.zhalo_up);
-  if (C.zhalo_dn) cudaFree(C.zhalo_dn); if (C.Uzh) cudaFree(C.Uzh); if (C.Uzh32) cudaFree(C.Uzh32);
+  if (C.zhalo_dn) cudaFree(C.zhalo_dn); if (C.Uzh) cudaFree(C.Uzh); if (C.Uzh32) cudaFree(C.Uzh32); if (C.Uzl) cudaFree(C.Uzl); if (C.Uzl32) cudaFree(C.Uzl32);
   cudaEventDestroy(C.ev_z);
+  if (C.zloop_buf) cudaFree(C.zloop_buf);
   cudaEventDestroy(C.ev_in); cudaEventDestroy(C.ev_halo); cudaEventDestroy(C.ev_t0); cudaEventDestroy(C.ev_t1);
   cudaEventDestroy(C.ev_chk[0]); cudaEventDestroy(C.ev_chk[1]);
   for (int i = 0; i < MAXCHUNK; i++) { cudaEventDestroy(C.ev_up[i]); cudaEventDestroy(C.ev_done[i]); }
@@ -322,9 +330,9 @@ static int p2p_small_buffers() {
   if (C.p2p_copy_ctas < 1) C.p2p_copy_ctas = 1;
   if (C.p2p_copy_ctas > 2 * 148) C.p2p_copy_ctas = 2 * 148; /* each pull CTA owns a partial slot and delays the stencil CTAs behind it */
   if (!C.p2p_err) { CU(cudaMalloc(&C.p2p_err, sizeof(int))); CU(cudaMemset(C.p2p_err, 0, sizeof(int))); }
-  if (!C.seq_dev) CU(cudaMalloc(&C.seq_dev, 2 * sizeof(unsigned int)));
-  CU(cudaMemset(C.seq_dev, 0, 2 * sizeof(unsigned int)));
-  C.hop_off = 0;
+  if (!C.seq_dev) CU(cudaMalloc(&C.seq_dev, 4 * sizeof(unsigned int)));
+  CU(cudaMemset(C.seq_dev, 0, 4 * sizeof(unsigned int)));
+  C.hop_off = 0; C.zhop_off = 0;
   return 0;
 }
 /* the table xred_sum() reads: every rank's landing arrays as seen from this rank */
@@ -408,12 +416,34 @@ static int setup_p2p() {
   TRY(p2p_small_buffers());
   C.p2p = true;
   if (allp) TRY(setup_xred(C.peer_base, C.nranks, C.rank));
+  /* Z split: the z faces go through peer memory too when every arena is mapped.  The four halo buffers (2 sides x 2
+   * sequence parities) sit at the same offset of every rank's arena, in front of the fields. */
+  C.zpeer = false;
+  const char *ez = getenv("TMB_ZPEER");
+  if (C.zsplit && allp && !(ez && atoi(ez) == 0)) {
+    const size_t fb = ((size_t)6 * SZ() * sizeof(double2) + 255) & ~(size_t)255;
+    if (C.arena_used + 4 * fb <= C.arena_bytes / 2) { /* the same decision on every rank: the arena size is an agreed one */
+      const size_t off = C.arena_used;
+      C.arena_used += 4 * fb;
+      char *mine_b = C.arena + off, *up_b = C.peer_base[z_up()] + off, *dn_b = C.peer_base[z_dn()] + off;
+      for (int b = 0; b < 2; b++) {
+        C.zloc_dn[b] = mine_b + (size_t)b * fb; C.zloc_up[b] = mine_b + (size_t)(2 + b) * fb;
+        C.zdst_up[b] = up_b + (size_t)b * fb;        /* my last-z face -> rank z+1's halo_dn */
+        C.zdst_dn[b] = dn_b + (size_t)(2 + b) * fb;  /* my first-z face -> rank z-1's halo_up */
+      }
+      C.zflags = (unsigned int *)(C.arena + ARENA_ZFLAGS);
+      C.zflag_at_up = (unsigned int *)(C.peer_base[z_up()] + ARENA_ZFLAGS) + 0;
+      C.zflag_at_dn = (unsigned int *)(C.peer_base[z_dn()] + ARENA_ZFLAGS) + 1;
+      C.zpeer = true;
+    }
+  }
   return 0;
 }
 static int z_buffers() {
   const size_t fb = (size_t)6 * SZ() * sizeof(double2);
   if (!C.zsend_up) { CU(cudaMalloc(&C.zsend_up, fb)); CU(cudaMalloc(&C.zsend_dn, fb)); CU(cudaMalloc(&C.zhalo_up, fb)); CU(cudaMalloc(&C.zhalo_dn, fb)); }
   if (!C.Uzh) CU(cudaMalloc(&C.Uzh, (size_t)18 * SZ() * sizeof(double2)));
+  if (!C.Uzl) CU(cudaMalloc(&C.Uzl, (size_t)18 * SZ() * sizeof(double2)));
   return 0;
 }
 extern "C" int tmb_comm_init_grid(const void *id128, int nt, int nz, int rank);
@@ -438,12 +468,28 @@ extern "C" int tmb_comm_init_grid(const void *id128, int nt, int nz, int rank) {
   return 0;
 }
 extern "C" int tmb_comm_peer_mode(void) { return C.p2p ? 1 : 0; }
+extern "C" int tmb_comm_zpeer_mode(void) { return C.zsplit && C.zpeer ? 1 : 0; }
 /* single GPU: exercise the Z-split path (face pack, exchange with itself, fix-up) */
 extern "C" int tmb_comm_loopback_z(int on) {
   NEED_INIT();
   if (C.nranks > 1) return fail(-6, "tmb_comm_loopback_z: only for a single rank");
   C.loop_z = on != 0; C.zsplit = C.loop_z; C.gauge_loaded = false; C.param_gen++;
   if (C.zsplit) TRY(z_buffers());
+  C.zpeer = false;
+  if (on == 2) { /* the peer-memory push of the z faces against itself: local buffers and flags stand in for the neighbours' */
+    const size_t fb = ((size_t)6 * SZ() * sizeof(double2) + 255) & ~(size_t)255;
+    if (!C.zloop_buf) CU(cudaMalloc(&C.zloop_buf, 4 * fb));
+    if (!C.flags) { CU(cudaMalloc(&C.flags, ARENA_RESERVED)); CU(cudaMemset(C.flags, 0, ARENA_RESERVED)); }
+    TRY(p2p_small_buffers());
+    CU(cudaMemset((char *)C.flags + ARENA_ZFLAGS, 0, 8));
+    for (int b = 0; b < 2; b++) {
+      C.zloc_dn[b] = C.zloop_buf + (size_t)b * fb; C.zloc_up[b] = C.zloop_buf + (size_t)(2 + b) * fb;
+      C.zdst_up[b] = C.zloc_dn[b]; C.zdst_dn[b] = C.zloc_up[b];
+    }
+    C.zflags = (unsigned int *)((char *)C.flags + ARENA_ZFLAGS);
+    C.zflag_at_up = C.zflags + 0; C.zflag_at_dn = C.zflags + 1;
+    C.zpeer = true;
+  }
   return 0;
 }
 /* on = 1: halo buffers (pack / copy / boundary launch); on = 2: peer mode against itself (one launch, flags) */
@@ -769,9 +815,8 @@ extern "C" int tmb_gauge_upload(const double *host_gauge) {
     CU(cudaFree(tmp));
   }
   if (C.zsplit) { /* U_z of rank z-1's last-z sites, for the -z hops of the z = 0 face */
-    double2 *tmp = nullptr;
+    double2 *tmp = C.Uzl; /* kept: the fix-up reads this rank's own last-z links from it (contiguous) */
     const size_t n = (size_t)18 * SZ();
-    CU(cudaMalloc(&tmp, n * sizeof(double2)));
     KL(tmb_launch_pack_gauge_zhalo(0, tmp, C.U, C.g, C.s_main));
     if (C.nz == 1) {
       CU(cudaMemcpyAsync(C.Uzh, tmp, n * sizeof(double2), cudaMemcpyDeviceToDevice, C.s_main));
@@ -782,7 +827,6 @@ extern "C" int tmb_gauge_upload(const double *host_gauge) {
       NC(C.nccl.GroupEnd());
     }
     CU(cudaStreamSynchronize(C.s_main));
-    CU(cudaFree(tmp));
   }
   C.gauge_loaded = true;
   C.gauge32_valid = false; C.c12_valid = false; C.c12f_valid = false;
@@ -871,14 +915,22 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   /* Z split: the faces of `in` go to the z neighbours while the kernels below run on the slab as if it were periodic in z;
    * the fix-up at the end replaces the wrapped z term of the face sites by the halo term (tmb_site.cuh) */
   const bool zs = C.zsplit && !o.nocom;
+  unsigned int zseq = 0;
   if (zs) {
     if (a.dot || o.mode == 4 || o.nfl == 2 || o.nsites >= 0 || o.boundary_only)
       return fail(-12, "fused reductions, the CG tail, the two-flavour kernel and site sub-ranges are not available with a split Z direction");
     const size_t fb = (size_t)6 * SZ() * (o.prec ? sizeof(float2) : sizeof(double2));
     CU(cudaEventRecord(C.ev_in, C.s_main));
     CU(cudaStreamWaitEvent(C.s_comm, C.ev_in, 0));
-    KL(tmb_launch_pack_zfaces(o.prec, C.zsend_up, C.zsend_dn, in, C.g, 1 - a.par, C.s_comm));
-    TRY(exchange_zfaces(C.zsend_up, C.zsend_dn, C.zhalo_up, C.zhalo_dn, fb, C.s_comm));
+    if (C.zpeer) { /* faces straight into the z neighbours' halo buffers of parity seq & 1, then their flags */
+      zseq = ++C.zhop_off;
+      KL(tmb_launch_pack_zfaces_push(o.prec, C.zdst_up[0], C.zdst_up[1], C.zdst_dn[0], C.zdst_dn[1], C.zsend_up, C.zsend_dn, in, C.g, 1 - a.par, C.seq_dev + 2, zseq,
+                                     C.zflag_at_up, C.zflag_at_dn, C.s_comm));
+      C.launches++; /* the flag kernel */
+    } else {
+      KL(tmb_launch_pack_zfaces(o.prec, C.zsend_up, C.zsend_dn, in, C.g, 1 - a.par, C.s_comm));
+      TRY(exchange_zfaces(C.zsend_up, C.zsend_dn, C.zhalo_up, C.zhalo_dn, fb, C.s_comm));
+    }
     CU(cudaEventRecord(C.ev_z, C.s_comm));
   }
   int np = 0;
@@ -954,8 +1006,12 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
   }
   if (zs) {
     CU(cudaStreamWaitEvent(C.s_main, C.ev_z, 0));
-    KL(tmb_launch_zfix(o.prec, o.mode, out, in, o.prec ? (const void *)C.U32 : (const void *)C.U, C.zhalo_up, C.zhalo_dn,
-                       o.prec ? (const void *)C.Uzh32 : (const void *)C.Uzh, C.g, a.par, C.ka[3], o.cf, o.st, C.s_main));
+    tmb_zpeer zw; memset(&zw, 0, sizeof(zw));
+    zw.own_up = C.zsend_up; zw.own_dn = C.zsend_dn; zw.Uzl = o.prec ? (const void *)C.Uzl32 : (const void *)C.Uzl;
+    if (C.zpeer) { zw.hz_up1 = C.zloc_up[1]; zw.hz_dn1 = C.zloc_dn[1]; zw.flags = C.zflags; zw.seq_base = C.seq_dev + 2; zw.seq_off = zseq; zw.err = C.p2p_err; }
+    KL(tmb_launch_zfix(o.prec, o.mode, out, in, o.prec ? (const void *)C.U32 : (const void *)C.U,
+                       C.zpeer ? (const void *)C.zloc_up[0] : (const void *)C.zhalo_up, C.zpeer ? (const void *)C.zloc_dn[0] : (const void *)C.zhalo_dn,
+                       o.prec ? (const void *)C.Uzh32 : (const void *)C.Uzh, C.g, a.par, C.ka[3], o.cf, o.st, &zw, C.s_main));
   }
   if (o.npartial) *o.npartial = np;
   return 0;

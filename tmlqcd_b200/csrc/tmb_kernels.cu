@@ -481,35 +481,80 @@ cudaError_t tmb_launch_pack_zfaces(int prec, void *up, void *dn, const void *in,
   if (prec) { EwPackZFaces<float2> f = {(float2 *)up, (float2 *)dn, (const float2 *)in, g, pin}; EW_LAUNCH(f, n, nullptr, s); }
   EwPackZFaces<double2> f = {(double2 *)up, (double2 *)dn, (const double2 *)in, g, pin}; EW_LAUNCH(f, n, nullptr, s);
 }
+/* Z faces through PEER MEMORY: the projected faces are written straight into the z neighbours' halo buffers (remote stores
+ * over NVLink), double-buffered on the parity of the hop's sequence number; a one-thread kernel behind the pack kernel (a
+ * kernel boundary: the stores have been performed) raises the neighbours' flags, and the neighbours' fix-up kernels wait
+ * for theirs.  No NCCL call, so solver chunks on a Z-split grid can be captured as CUDA graphs like the T-split ones. */
+template <class V2>
+__global__ void __launch_bounds__(256) pack_zfaces_push_kernel(V2 *up0, V2 *up1, V2 *dn0, V2 *dn1, V2 *own_up, V2 *own_dn, const V2 *in,
+                                                               tmb_geom g, int pin, const unsigned int *seq_base, unsigned int seq_off) {
+  const unsigned int seq = *seq_base + seq_off;
+  EwPackZFaces<V2> f = {(seq & 1u) ? up1 : up0, (seq & 1u) ? dn1 : dn0, in, g, pin, own_up, own_dn}; /* remote + local copy */
+  const size_t n = (size_t)6 * (g.T * g.LX * g.LY / 2);
+  for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (size_t)gridDim.x * 256) f(k);
+}
+__global__ void zflag_kernel(unsigned int *fa, unsigned int *fb, const unsigned int *seq_base, unsigned int seq_off) {
+  const unsigned int seq = *seq_base + seq_off;
+  __threadfence_system();
+  st_release_sys(fa, seq);
+  st_release_sys(fb, seq);
+}
+cudaError_t tmb_launch_pack_zfaces_push(int prec, void *up0, void *up1, void *dn0, void *dn1, void *own_up, void *own_dn, const void *in,
+                                        tmb_geom g, int pin, const unsigned int *seq_base, unsigned int seq_off, unsigned int *flag_up,
+                                        unsigned int *flag_dn, cudaStream_t s) {
+  const size_t n = (size_t)6 * (g.T * g.LX * g.LY / 2);
+  const size_t need = (n + 255) / 256; const int grid = (int)(need < (size_t)148 * 16 ? (need ? need : 1) : (size_t)148 * 16);
+  if (prec) pack_zfaces_push_kernel<float2><<<grid, 256, 0, s>>>((float2 *)up0, (float2 *)up1, (float2 *)dn0, (float2 *)dn1, (float2 *)own_up, (float2 *)own_dn, (const float2 *)in, g, pin, seq_base, seq_off);
+  else pack_zfaces_push_kernel<double2><<<grid, 256, 0, s>>>((double2 *)up0, (double2 *)up1, (double2 *)dn0, (double2 *)dn1, (double2 *)own_up, (double2 *)own_dn, (const double2 *)in, g, pin, seq_base, seq_off);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  zflag_kernel<<<1, 1, 0, s>>>(flag_up, flag_dn, seq_base, seq_off);
+  return cudaGetLastError();
+}
 cudaError_t tmb_launch_pack_gauge_zhalo(int prec, void *out, const void *U, tmb_geom g, cudaStream_t s) {
   const size_t n = (size_t)18 * (g.T * g.LX * g.LY / 2);
   if (prec) { EwPackGaugeZHalo<float2> f = {(float2 *)out, (const float2 *)U, g}; EW_LAUNCH(f, n, nullptr, s); }
   EwPackGaugeZHalo<double2> f = {(double2 *)out, (const double2 *)U, g}; EW_LAUNCH(f, n, nullptr, s);
 }
+/* peer mode (w.flags != nullptr): the halo buffers are the ones of parity seq & 1, filled by the z neighbours' pack kernels;
+ * thread 0 of every CTA waits for the two flags to reach seq */
 template <int MODE, class V2>
-__global__ void __launch_bounds__(128) zfix_kernel(V2 *out, const V2 *in, const V2 *U, const V2 *hz_up, const V2 *hz_dn, const V2 *Uzh,
-                                                   tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st) {
+__global__ void __launch_bounds__(64) zfix_kernel(V2 *out, const V2 *in, const V2 *U, const V2 *hz_up, const V2 *hz_dn, const V2 *Uzh,
+                                                   tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st, const tmb_zpeer w) {
   if (st != nullptr && st->converged) return;
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= g.T * g.LX * g.LY / 2) return;
-  tmb_zfix_pair<MODE>(out, in, U, hz_up, hz_dn, Uzh, g, par, j, cvt2<V2>(ka3), cvt2<V2>(cf));
+  if (w.flags != nullptr) {
+    const unsigned int seq = *w.seq_base + w.seq_off;
+    if (threadIdx.x == 0) { wait_flag(w.flags + 0, seq, w.err); wait_flag(w.flags + 1, seq, w.err); }
+    __syncthreads();
+    if (seq & 1u) { hz_up = (const V2 *)w.hz_up1; hz_dn = (const V2 *)w.hz_dn1; }
+  }
+  /* one thread per (face site, side): 2 Sz threads in CTAs of 64 - the face accesses are strided (one element per row of
+   * Lzh), latency-bound, so the fix-up wants as many independent threads as it can get (one thread per site PAIR in CTAs
+   * of 128: 52 us at 24x48x48x24, a third of the hop) */
+  const int Sz = g.T * g.LX * g.LY / 2;
+  const int q = blockIdx.x * 64 + threadIdx.x;
+  if (q >= 2 * Sz) return;
+  const int side = q >= Sz ? 1 : 0, j = q - side * Sz;
+  tmb_zfix_side<MODE>(out, in, U, hz_up, hz_dn, Uzh, g, par, j, side, cvt2<V2>(ka3), cvt2<V2>(cf), (const V2 *)w.own_up, (const V2 *)w.own_dn, (const V2 *)w.Uzl);
 }
 template <class V2>
 static cudaError_t zfix_go(int mode, V2 *out, const V2 *in, const V2 *U, const V2 *hu, const V2 *hd, const V2 *Uzh, tmb_geom g, int par,
-                           double2 ka3, double2 cf, const tmb_cg_state *st, cudaStream_t s) {
-  const int grid = (g.T * g.LX * g.LY / 2 + 127) / 128;
+                           double2 ka3, double2 cf, const tmb_cg_state *st, const tmb_zpeer &w, cudaStream_t s) {
+  const int grid = (2 * (g.T * g.LX * g.LY / 2) + 63) / 64;
   switch (mode) {
-    case 0: zfix_kernel<0, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
-    case 1: zfix_kernel<1, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
-    case 2: zfix_kernel<2, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
-    case 3: zfix_kernel<3, V2><<<grid, 128, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st); break;
+    case 0: zfix_kernel<0, V2><<<grid, 64, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st, w); break;
+    case 1: zfix_kernel<1, V2><<<grid, 64, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st, w); break;
+    case 2: zfix_kernel<2, V2><<<grid, 64, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st, w); break;
+    case 3: zfix_kernel<3, V2><<<grid, 64, 0, s>>>(out, in, U, hu, hd, Uzh, g, par, ka3, cf, st, w); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 cudaError_t tmb_launch_zfix(int prec, int mode, void *out, const void *in, const void *U, const void *hz_up, const void *hz_dn, const void *Uzh,
-                            tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st, cudaStream_t s) {
-  if (prec) return zfix_go<float2>(mode, (float2 *)out, (const float2 *)in, (const float2 *)U, (const float2 *)hz_up, (const float2 *)hz_dn, (const float2 *)Uzh, g, par, ka3, cf, st, s);
-  return zfix_go<double2>(mode, (double2 *)out, (const double2 *)in, (const double2 *)U, (const double2 *)hz_up, (const double2 *)hz_dn, (const double2 *)Uzh, g, par, ka3, cf, st, s);
+                            tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st, const tmb_zpeer *w, cudaStream_t s) {
+  tmb_zpeer none; memset(&none, 0, sizeof(none));
+  const tmb_zpeer &ww = w ? *w : none;
+  if (prec) return zfix_go<float2>(mode, (float2 *)out, (const float2 *)in, (const float2 *)U, (const float2 *)hz_up, (const float2 *)hz_dn, (const float2 *)Uzh, g, par, ka3, cf, st, ww, s);
+  return zfix_go<double2>(mode, (double2 *)out, (const double2 *)in, (const double2 *)U, (const double2 *)hz_up, (const double2 *)hz_dn, (const double2 *)Uzh, g, par, ka3, cf, st, ww, s);
 }
 cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom g, cudaStream_t s) { EwPackGaugeHalo f = {out, U, g}; EW_LAUNCH(f, (size_t)18 * g.S, nullptr, s); }

@@ -171,8 +171,15 @@ cudaError_t tmb_launch_pack_gauge_halo(double2 *out, const double2 *U, tmb_geom 
  * sites, [2][9][Sz], for rank z+1.  zfix: replaces the wrapped z term of the face sites of `out` by the halo term. */
 cudaError_t tmb_launch_pack_zfaces(int prec, void *send_up, void *send_dn, const void *in, tmb_geom g, int pin, cudaStream_t s);
 cudaError_t tmb_launch_pack_gauge_zhalo(int prec, void *out, const void *U, tmb_geom g, cudaStream_t s);
+/* peer-mode Z exchange: second halo buffers, the two flags of this rank and the hop's sequence number (see tmb_kernels.cu) */
+struct tmb_zpeer { const void *hz_up1, *hz_dn1; const unsigned int *flags; const unsigned int *seq_base; unsigned int seq_off; int *err;
+  /* every mode: this rank's own projected faces and own last-z links as contiguous arrays (tmb_zfix_side, tmb_site.cuh); may be null */
+  const void *own_up, *own_dn, *Uzl; };
+cudaError_t tmb_launch_pack_zfaces_push(int prec, void *up0, void *up1, void *dn0, void *dn1, void *own_up, void *own_dn, const void *in,
+                                        tmb_geom g, int pin, const unsigned int *seq_base, unsigned int seq_off, unsigned int *flag_up,
+                                        unsigned int *flag_dn, cudaStream_t s);
 cudaError_t tmb_launch_zfix(int prec, int mode, void *out, const void *in, const void *U, const void *hz_up, const void *hz_dn, const void *Uzh,
-                            tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st, cudaStream_t s);
+                            tmb_geom g, int par, double2 ka3, double2 cf, const tmb_cg_state *st, const tmb_zpeer *w, cudaStream_t s);
 
 /* ---- fermion force (tmb_force.cu): deriv_Sb.c:402-649 as a gather over link owners ---- */
 struct tmb_deriv_launch {

@@ -367,7 +367,7 @@ TMB_HD void tmb_zface_row(const tmb_geom &g, int par, int j, int want_r, int *ro
 }
 /* what rank z-1 needs for its +z hops (send_dn: D = 6 projection of this rank's z = 0 sites) and what rank z+1 needs for its
  * -z hops (send_up: D = 7 projection of this rank's z = LZ-1 sites); `in` has parity pin, k in [0, 6 * Sz) */
-template <class V2> struct EwPackZFaces { V2 *up, *dn; const V2 *in; tmb_geom g; int pin;
+template <class V2> struct EwPackZFaces { V2 *up, *dn; const V2 *in; tmb_geom g; int pin; V2 *up2 = nullptr, *dn2 = nullptr; /* second copies (peer push: remote + local) */
   __host__ __device__ void operator()(size_t k) const {
     const int Sz = g.T * g.LX * g.LY / 2;
     const int c = (int)(k / Sz), j = (int)(k - (size_t)c * Sz);
@@ -378,14 +378,16 @@ template <class V2> struct EwPackZFaces { V2 *up, *dn; const V2 *in; tmb_geom g;
       const size_t i = (size_t)row * g.Lzh;
       const int cc = c % 3, hi = c / 3; /* hi 0: a = s0 + i s2, hi 1: b = s1 - i s3 */
       const V2 x = in[(size_t)(hi ? 3 + cc : cc) * g.Vh + i], y = in[(size_t)(hi ? 9 + cc : 6 + cc) * g.Vh + i];
-      dn[k] = hi ? c_comb<3>(x, y) : c_comb<2>(x, y);
+      const V2 v = hi ? c_comb<3>(x, y) : c_comb<2>(x, y);
+      dn[k] = v; if (dn2 != nullptr) dn2[k] = v;
     }
     tmb_zface_row<V2>(g, pin, j, 1, &row, &t);
     {
       const size_t i = (size_t)row * g.Lzh + (g.Lzh - 1);
       const int cc = c % 3, hi = c / 3; /* hi 0: a = s0 - i s2, hi 1: b = s1 + i s3 */
       const V2 x = in[(size_t)(hi ? 3 + cc : cc) * g.Vh + i], y = in[(size_t)(hi ? 9 + cc : 6 + cc) * g.Vh + i];
-      up[k] = hi ? c_comb<2>(x, y) : c_comb<3>(x, y);
+      const V2 v = hi ? c_comb<2>(x, y) : c_comb<3>(x, y);
+      up[k] = v; if (up2 != nullptr) up2[k] = v;
     }
   } };
 /* U_z of this rank's last-z sites, both owner parities: out[(q * 9 + e) * Sz + j] (what rank z+1 needs), k in [0, 18 * Sz) */
@@ -398,50 +400,64 @@ template <class V2> struct EwPackGaugeZHalo { V2 *out; const V2 *U; tmb_geom g;
     out[k] = U[(size_t)((q * 4 + 3) * 9 + e) * g.Vh + (size_t)row * g.Lzh + (g.Lzh - 1)];
   } };
 /* the fix-up of one face site pair j of the OUTPUT parity par; U is the full 18-real link field */
+/* own_up / own_dn: this rank's OWN projected faces, as packed for the neighbours ([6][Sz], the same row enumeration): the
+ * wrapped term the kernel used for the +z hop of the last-z sites is the D = 6 projection of the slab's first-z sites =
+ * own_dn, for the -z hop of the first-z sites it is own_up.  Uzl: this rank's own U_z of the last-z sites ([2][9][Sz], what
+ * it sent to rank z+1).  With these every operand of the fix-up except `out` itself is read contiguously; nullptr (the CPU
+ * emulation, older callers) = gather them from `in` and `U` with the stride of a z row. */
+template <int MODE, class V2>
+TMB_HD void tmb_zfix_side(V2 *out, const V2 *in, const V2 *U, const V2 *hz_up, const V2 *hz_dn, const V2 *Uzh, const tmb_geom &g,
+                          int par, int j, int side, V2 ka3, V2 cf, const V2 *own_up = nullptr, const V2 *own_dn = nullptr,
+                          const V2 *Uzl = nullptr) {
+  const int Sz = g.T * g.LX * g.LY / 2;
+  int row, t;
+  tmb_zface_row<V2>(g, par, j, side ? 0 : 1, &row, &t); /* side 0: the +z face site (r = 1, zh = Lzh-1), 1: the -z face site (r = 0, zh = 0) */
+  const size_t i = (size_t)row * g.Lzh + (side ? 0 : g.Lzh - 1);
+  const size_t iw = (size_t)row * g.Lzh + (side ? g.Lzh - 1 : 0); /* the slab's own opposite face: what the kernel used */
+  V2 d[12];
+#pragma unroll
+  for (int c = 0; c < 12; c++) d[c] = mk2<V2>(0, 0);
+  V2 ah[3], bh[3], aw[3], bw[3], u[9];
+  const V2 *hz = side ? hz_dn : hz_up;
+#pragma unroll
+  for (int c = 0; c < 3; c++) { ah[c] = hz[(size_t)c * Sz + j]; bh[c] = hz[(size_t)(3 + c) * Sz + j]; }
+  tmb_policies pol = {0, 0};
+  const V2 *own = side ? own_up : own_dn;
+  if (own != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { aw[c] = own[(size_t)c * Sz + j]; bw[c] = own[(size_t)(3 + c) * Sz + j]; }
+  } else if (!side) tmb_project<6, 0>(aw, bw, in, g.Vh, (int)iw, pol);
+  else tmb_project<7, 0>(aw, bw, in, g.Vh, (int)iw, pol);
+  if (!side) { /* +z: same local link for both terms */
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ah[c] = c_sub(ah[c], aw[c]); bh[c] = c_sub(bh[c], bw[c]); }
+#pragma unroll
+    for (int e = 0; e < 9; e++) u[e] = Uzl != nullptr ? Uzl[(size_t)(par * 9 + e) * Sz + j] : U[(size_t)((par * 4 + 3) * 9 + e) * g.Vh + i];
+    tmb_link_accumulate<6>(d, u, ah, bh, ka3);
+  } else {     /* -z: the right link comes with the halo, the wrong one is the local link at the wrapped neighbour */
+#pragma unroll
+    for (int e = 0; e < 9; e++) u[e] = Uzh[(size_t)((1 - par) * 9 + e) * Sz + j];
+    tmb_link_accumulate<7>(d, u, ah, bh, ka3);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { aw[c] = mk2<V2>(-aw[c].x, -aw[c].y); bw[c] = mk2<V2>(-bw[c].x, -bw[c].y); }
+#pragma unroll
+    for (int e = 0; e < 9; e++) u[e] = Uzl != nullptr ? Uzl[(size_t)((1 - par) * 9 + e) * Sz + j] : U[(size_t)(((1 - par) * 4 + 3) * 9 + e) * g.Vh + iw];
+    tmb_link_accumulate<7>(d, u, aw, bw, ka3);
+  }
+#pragma unroll
+  for (int c = 0; c < 12; c++) {
+    V2 o = out[(size_t)c * g.Vh + i], x = d[c];
+    if (MODE == 1) x = c_mul((c < 6) ? cf : c_conj(cf), x);
+    else if (MODE == 2) x = (c < 6) ? mk2<V2>(-x.x, -x.y) : x;
+    else if (MODE == 3) x = mk2<V2>(-x.x, -x.y);
+    out[(size_t)c * g.Vh + i] = c_add(o, x);
+  }
+}
 template <int MODE, class V2>
 TMB_HD void tmb_zfix_pair(V2 *out, const V2 *in, const V2 *U, const V2 *hz_up, const V2 *hz_dn, const V2 *Uzh, const tmb_geom &g,
                           int par, int j, V2 ka3, V2 cf) {
-  const int Sz = g.T * g.LX * g.LY / 2;
-  int row, t;
-  for (int side = 0; side < 2; side++) { /* 0: the +z face site (r = 1, zh = Lzh-1), 1: the -z face site (r = 0, zh = 0) */
-    tmb_zface_row<V2>(g, par, j, side ? 0 : 1, &row, &t);
-    const size_t i = (size_t)row * g.Lzh + (side ? 0 : g.Lzh - 1);
-    const size_t iw = (size_t)row * g.Lzh + (side ? g.Lzh - 1 : 0); /* the slab's own opposite face: what the kernel used */
-    V2 d[12];
-#pragma unroll
-    for (int c = 0; c < 12; c++) d[c] = mk2<V2>(0, 0);
-    V2 ah[3], bh[3], aw[3], bw[3], u[9];
-    const V2 *hz = side ? hz_dn : hz_up;
-#pragma unroll
-    for (int c = 0; c < 3; c++) { ah[c] = hz[(size_t)c * Sz + j]; bh[c] = hz[(size_t)(3 + c) * Sz + j]; }
-    tmb_policies pol = {0, 0};
-    if (!side) { /* +z: same local link for both terms */
-      tmb_project<6, 0>(aw, bw, in, g.Vh, (int)iw, pol);
-#pragma unroll
-      for (int c = 0; c < 3; c++) { ah[c] = c_sub(ah[c], aw[c]); bh[c] = c_sub(bh[c], bw[c]); }
-#pragma unroll
-      for (int e = 0; e < 9; e++) u[e] = U[(size_t)((par * 4 + 3) * 9 + e) * g.Vh + i];
-      tmb_link_accumulate<6>(d, u, ah, bh, ka3);
-    } else {     /* -z: the right link comes with the halo, the wrong one is the local link at the wrapped neighbour */
-#pragma unroll
-      for (int e = 0; e < 9; e++) u[e] = Uzh[(size_t)((1 - par) * 9 + e) * Sz + j];
-      tmb_link_accumulate<7>(d, u, ah, bh, ka3);
-      tmb_project<7, 0>(aw, bw, in, g.Vh, (int)iw, pol);
-#pragma unroll
-      for (int c = 0; c < 3; c++) { aw[c] = mk2<V2>(-aw[c].x, -aw[c].y); bw[c] = mk2<V2>(-bw[c].x, -bw[c].y); }
-#pragma unroll
-      for (int e = 0; e < 9; e++) u[e] = U[(size_t)(((1 - par) * 4 + 3) * 9 + e) * g.Vh + iw];
-      tmb_link_accumulate<7>(d, u, aw, bw, ka3);
-    }
-#pragma unroll
-    for (int c = 0; c < 12; c++) {
-      V2 o = out[(size_t)c * g.Vh + i], x = d[c];
-      if (MODE == 1) x = c_mul((c < 6) ? cf : c_conj(cf), x);
-      else if (MODE == 2) x = (c < 6) ? mk2<V2>(-x.x, -x.y) : x;
-      else if (MODE == 3) x = mk2<V2>(-x.x, -x.y);
-      out[(size_t)c * g.Vh + i] = c_add(o, x);
-    }
-  }
+  tmb_zfix_side<MODE>(out, in, U, hz_up, hz_dn, Uzh, g, par, j, 0, ka3, cf);
+  tmb_zfix_side<MODE>(out, in, U, hz_up, hz_dn, Uzh, g, par, j, 1, ka3, cf);
 }
 
 /* Epilogues (hopping.h:674-694):
