@@ -173,6 +173,9 @@ void emul_xblock_perm(int *out, int T, int LX, int LY, int LZ, int XB) {
   }
 }
 
+/* chunk schedule of the host-pointer pipeline (tmb_geom.h) */
+int emul_host_chunk_schedule(int nt, int small, int *sizes) { return tmb_host_chunk_schedule(nt, small, sizes); }
+
 /* CTA tile traversal (tmb_tile_site / tmb_tile_t of tmb_geom.h, used by hop_kernel and hop2_kernel); returns tmb_tile_ok */
 int emul_tile_perm(int *site, int *tslice, int T, int LX, int LY, int LZ, int tshift) {
   tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);

@@ -27,7 +27,7 @@ def load():
         "emul_pack_lexic": [dp, dp, dp, i, i, i, i], "emul_unpack_lexic": [dp, dp, dp, i, i, i, i],
         "emul_pack_gauge": [dp, dp, i, i, i, i], "emul_pack_halo": [dp, dp, dp, i, i, i, i],
         "emul_pack_gauge_halo": [dp, dp, i, i, i, i], "emul_neighbours": [ip, i, i, i, i, i],
-        "emul_eo2lexic": [ip, i, i, i, i], "emul_pull_halo": [dp, dp, dp, dp, i, i, i, i], "emul_xblock_perm": [ip, i, i, i, i, i], "emul_tile_perm": [ip, ip, i, i, i, i, i],
+        "emul_eo2lexic": [ip, i, i, i, i], "emul_pull_halo": [dp, dp, dp, dp, i, i, i, i], "emul_xblock_perm": [ip, i, i, i, i, i], "emul_tile_perm": [ip, ip, i, i, i, i, i], "emul_host_chunk_schedule": [i, i, ip],
         "emul_hop": [i, dp, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, d, d, i, i],
         "emul_hop12": [i, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, i], "emul_compress12": [dp, dp, C.c_long, i],
         "emul_hop_f": [i, fp, fp, fp, i, i, i, i, dp],
@@ -44,7 +44,7 @@ def load():
     }
     for n, a in sig.items():
         getattr(E, n).argtypes = a
-        getattr(E, n).restype = i if n in ("emul_hop", "emul_hop12", "emul_hop_f", "emul_tile_perm") else (d if n == "emul_plaquette" else None)
+        getattr(E, n).restype = i if n in ("emul_hop", "emul_hop12", "emul_hop_f", "emul_tile_perm", "emul_host_chunk_schedule") else (d if n == "emul_plaquette" else None)
     return E
 
 

@@ -157,6 +157,23 @@ def test_cta_tile_traversal(dims):
             assert np.all(t[touches][:, 0] == T - 1) and np.all(t[touches][:, 2] == 0)   # one tile layer holds both
 
 
+def test_host_pipeline_chunk_schedule():
+    """the chunk sizes of the pipelined host-pointer Hopping_Matrix (tmb_host_chunk_schedule, tmb_geom.h): they cover the
+    slices exactly, respect the minimum size except for the remainder, stay few, start with a small chunk and end with the
+    smallest; the measured schedule of 24^3x48 is pinned"""
+    e = Emul(4, 4, 4, 4)
+    buf = np.zeros(64, dtype=np.int32)
+    assert [int(x) for x in buf[:e.E.emul_host_chunk_schedule(48, 1, buf)]] == [2, 6, 8, 8, 8, 8, 4, 2, 1, 1]
+    for nt in list(range(1, 130)) + [256, 510, 1024]:
+        for small in (1, 2, 3, 5, 16):
+            n = e.E.emul_host_chunk_schedule(nt, small, buf)
+            sz = [int(x) for x in buf[:n]]
+            assert 1 <= n <= 8 + int(np.log2(nt)) + 1 and sum(sz) == nt and min(sz) >= 1
+            assert all(x >= min(small, nt) for x in sz[:-1])     # only the last chunk may be a remainder below `small`
+            if nt >= 24 * small:
+                assert sz[0] <= sz[1] <= sz[2] and sz[-1] <= sz[-2] <= sz[-3] and max(sz) == (nt + 5) // 6
+
+
 @pytest.mark.parametrize("dims,xb", [((4, 8, 4, 6), 2), ((4, 8, 4, 6), 4), ((6, 6, 2, 4), 3)])
 def test_xblock_traversal_is_a_permutation(dims, xb):
     e = Emul(*dims)

@@ -1116,20 +1116,10 @@ static int host_hop_enqueue(int ieo, double *l_host, const double *k_host, int m
     } else {
       int small = 1;
       while ((size_t)small * S * 192 < ((size_t)1 << 20) && small < nt) small++;
-      int big = (nt + 5) / 6; if (big < small) big = small;
-      int t = t_lo, rem = nt;
-      /* the first big chunk goes up as a quarter and three quarters: the first download starts ~150 us earlier (measured
-       * 24^3x48, profiles/r02_pipe_diag.log: 2,6,8,8,8,8,4,2,1,1 slices 1.66 ms against 8,8,8,8,8,4,2,2 1.70 ms per call) */
-      if (big >= 4 * small && 4 * rem > 7 * big) {
-        const int q = big / 4;
-        t += q; rem -= q; cb[++n] = t;
-        t += big - q; rem -= big - q; cb[++n] = t;
-      }
-      while (4 * rem > 7 * big) { t += big; rem -= big; cb[++n] = t; }
-      while (rem > 0) {
-        const int sz = rem <= small ? rem : ((rem + 1) / 2 > small ? (rem + 1) / 2 : small);
-        t += sz; rem -= sz; cb[++n] = t;
-      }
+      int sizes[MAXCHUNK];
+      const int nc = tmb_host_chunk_schedule(nt, small, sizes); /* tmb_geom.h */
+      int t = t_lo;
+      for (int c = 0; c < nc && n < MAXCHUNK; c++) { t += sizes[c]; cb[++n] = t; }
     }
   }
   if (n > MAXCHUNK - 2) return fail(-13, "too many chunks");

@@ -102,4 +102,28 @@ TMB_HD int tmb_neighbours(const tmb_geom g, int par, int i, int nb[8]) {
   return (int)t;
 }
 
+/* Chunk schedule of the pipelined host-pointer Hopping_Matrix (tmb_capi.cu, host_hop_enqueue): `nt` time-slices to move, chunks
+ * never smaller than `small` slices (about 1 MB).  Few LARGE chunks (a sixth of the field): once both directions are busy a
+ * copy gets slower the smaller it is (a 10.6 MB upload takes ~255 us next to a running download, a 2.6 MB one ~105 us).  The
+ * first big chunk goes up as a quarter and three quarters, so that the first download starts early, and the tail halves,
+ * so that little is left to come down when the upload ends (24^3x48: 2,6,8,8,8,8,4,2,1,1 slices, 1.66 ms per call against
+ * 1.70 for 8,8,8,8,8,4,2,2 and 1.80 for 12 equal chunks; profiles/r02_pipe_diag.log).  Returns the number of chunks
+ * (<= 8 + log2(nt)); sizes[] gets the sizes in upload order of the slices. */
+TMB_HD int tmb_host_chunk_schedule(int nt, int small, int *sizes) {
+  int n = 0, rem = nt;
+  if (small < 1) small = 1;
+  int big = (nt + 5) / 6;
+  if (big < small) big = small;
+  if (big >= 4 * small && 4 * rem > 7 * big) {
+    const int q = big / 4;
+    sizes[n++] = q; sizes[n++] = big - q; rem -= big;
+  }
+  while (4 * rem > 7 * big) { sizes[n++] = big; rem -= big; }
+  while (rem > 0) {
+    const int sz = rem <= small ? rem : ((rem + 1) / 2 > small ? (rem + 1) / 2 : small);
+    sizes[n++] = sz; rem -= sz;
+  }
+  return n;
+}
+
 #endif /* TMB_GEOM_H */
