@@ -85,7 +85,7 @@ int tmb_set_hop2_variant(int v);
 /* CompressionType of the reference (misc_types.h:33-37): 18 = full links (default), 12 = two rows streamed,
  * third reconstructed in registers (1152 instead of 1536 B/site); refused unless the field is SU(3) to 1e-13 */
 int tmb_set_compression(int nreal);
-int tmb_set_host_chunks(int n); /* chunks of the pipelined host-pointer Hopping_Matrix; 0 (default): two time-slices per chunk, at least 1 MB */
+int tmb_set_host_chunks(int n); /* n equal chunks for the pipelined host-pointer Hopping_Matrix; 0 (default): the automatic schedule (a sixth of the field per chunk, first chunk split 1/4 + 3/4, halving tail) */
 int tmb_set_p2p_diag(int bits); /* peer-mode timing diagnostics (results INVALID across ranks); refused unless TMB_P2P_DIAG=1 */
 int tmb_set_overlap(int flags); /* unknown bits are refused. bit0: programmatic dependent launch, bit1: L2 bulk prefetch of gauge rows, bit2: no CUDA-graph replay in the CG, bit3: L2 prefetch of the epilogue operands (p, dotw), bit4: the CG takes <p, A p> from the last hop (operand load) instead of |Q- p|^2 from the second, bit5: the CG's x / r update as a separate sweep instead of the last hop's epilogue, bit6 (experiment, measured slower): the CG finishes <p, A p> in a one-CTA kernel on the side stream next to the third hop instead of in the last CTA of the second hop */
 

@@ -101,7 +101,7 @@ struct Ctx {
   std::vector<std::pair<size_t, size_t>> arena_free; /* (offset, bytes) */
   char *up_base = nullptr, *dn_base = nullptr;
   unsigned int *flags = nullptr, *up_flags = nullptr, *dn_flags = nullptr, *p2p_ticket = nullptr;
-  int host_chunks = 0; /* chunks of the pipelined host-pointer hop; 0: two time-slices per chunk (>= 1 MB) */
+  int host_chunks = 0; /* equal chunks of the pipelined host-pointer hop; 0: the automatic schedule (tmb_host_chunk_schedule) */
   unsigned long long param_gen = 1; /* bumped by every setter whose value is baked into a cached host-hop graph */
   int *p2p_err = nullptr; bool arena_warned = false; int p2p_diag = 0, p2p_copy_ctas = 64;
   /* sequence numbers of the peer-mode hops are *seq_dev + hop_off: the host counts offsets, the device base only moves
@@ -570,7 +570,7 @@ extern "C" int tmb_set_tuning(int hop_variant, int cache_hints, int xblock) {
 }
 /* bit 0: programmatic dependent launch of the hopping kernels, bit 1: L2 bulk prefetch of gauge rows */
 /* number of time-slice chunks of the pipelined host-pointer Hopping_Matrix (1..64) */
-extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 0 || n > MAXCHUNK) return fail(-7, "host chunks must be in [0, %d] (0: two time-slices per chunk)", MAXCHUNK); C.host_chunks = n; C.param_gen++; return 0; }
+extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 0 || n > MAXCHUNK) return fail(-7, "host chunks must be in [0, %d] (0: automatic schedule)", MAXCHUNK); C.host_chunks = n; C.param_gen++; return 0; }
 /* explicit chunk sizes (time-slices, in order) for the pipelined host-pointer Hopping_Matrix; n = 0 returns to the automatic
  * schedule.  Used when the sizes add up to the number of pipelined slices, ignored otherwise. */
 extern "C" int tmb_set_host_chunk_sizes(const int *sizes, int n) {
@@ -1024,10 +1024,10 @@ static int hop(int ieo, void *out, const void *in, const HopOpt &o) {
  * result goes back while later chunks are still coming in, so the H2D and D2H copy engines run
  * concurrently (full duplex) and the kernel time disappears behind them.
  *
- * What is left on top of the two transfers is the fill (three chunks up before the first kernel) and the drain (one
- * chunk down after the last), so chunks are small: two time-slices, at least ~1 MB.  That many chunks cost more host
- * time to ENQUEUE (copy, events, pack, hop, unpack, copy: ~9 driver calls each) than they take to run, so the whole
- * pipeline of one call is captured once as a CUDA graph, keyed on everything baked into it (host pointers, ieo, mode,
+ * What is left on top of the two transfers is the fill (the first chunk up before the first kernel) and the drain (what is
+ * still to come down when the upload ends); the chunk schedule (tmb_host_chunk_schedule, tmb_geom.h) trades them against the
+ * per-copy cost.  A dozen chunks cost more host time to ENQUEUE (copy, events, pack, hop, unpack, copy: ~9 driver calls each)
+ * than some of them take to run, so the whole pipeline of one call is captured once as a CUDA graph, keyed on everything baked into it (host pointers, ieo, mode,
  * coefficient, parameter generation), and replayed: the reference calls its operators with the same few field slabs
  * over and over (init/init_spinor_field.c:38-66).
  *
