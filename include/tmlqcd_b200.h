@@ -49,6 +49,7 @@ int tmb_comm_loopback(int on); /* single GPU: exercise the T-split path against 
 int tmb_comm_loopback_z(int on); /* single GPU: exercise the Z-split path (face pack, exchange, fix-up) against itself */
 int tmb_comm_peer_mode(void);  /* 1 if the hops read the neighbours' fields directly over NVLink (CUDA IPC), 0: NCCL halos */
 int tmb_comm_zpeer_mode(void); /* 1 if the z faces of a Z-split grid are pushed into the z neighbours' memory (CUDA IPC), 0: NCCL send/recv */
+int tmb_comm_sequence_counts(unsigned int *t_hops, unsigned int *z_pushes); /* test hook: sequence numbers taken by the peer-mode T hops / the z-face pushes */
 int tmb_comm_nranks(void);
 
 /* ---- parameters: the globals the reference operators read at call time ---- */

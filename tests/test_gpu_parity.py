@@ -556,6 +556,12 @@ def test_z_split_against_itself(oracle_lib, tloop, zmode):
         es, ec = o.spinor(), o.spinor(); o.Qtm_pm_ndpsi(es, ec, k, p)
         dls, dlc = d.field(), d.field(); d.call("Qtm_pm_ndpsi", dls, dlc, dk, dp)
         assert rel_l2(d.download(dls), es) <= TOL and rel_l2(d.download(dlc), ec) <= TOL
+        if zmode == 2:  # the pushes count on their own: consecutive pushes alternate the halo buffers whatever the T path takes
+            c0, z0, c1, z1 = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
+            d.ck(d.lib.tmb_comm_sequence_counts(C.byref(c0), C.byref(z0)))
+            d.call("Qtm_pm_psi", dl, dk)
+            d.ck(d.lib.tmb_comm_sequence_counts(C.byref(c1), C.byref(z1)))
+            assert z1.value - z0.value == 4 and c1.value - c0.value == (4 if tloop == 2 else 0)
         # host-pointer hop on a split Z: plain upload / compute / download
         out = np.zeros_like(k); d.call("Hopping_Matrix_host", 0, out, k, 0, 1., 0.)
         o.Hopping_Matrix(0, exp, k); assert rel_l2(out, exp) <= TOL

@@ -37,7 +37,7 @@ DEVICE_API = {
     "tmb_last_error": (C.c_char_p, []), "tmb_volume_half": (_i, []),
     "tmb_comm_unique_id": (_i, [_vp]), "tmb_comm_init": (_i, [_vp, _i, _i]), "tmb_comm_loopback": (_i, [_i]), "tmb_comm_loopback_z": (_i, [_i]),
     "tmb_comm_init_grid": (_i, [_vp, _i, _i, _i]), "tmb_comm_grid": (_i, [C.POINTER(_i), C.POINTER(_i)]),
-    "tmb_comm_nranks": (_i, []), "tmb_comm_peer_mode": (_i, []), "tmb_comm_zpeer_mode": (_i, []),
+    "tmb_comm_nranks": (_i, []), "tmb_comm_peer_mode": (_i, []), "tmb_comm_zpeer_mode": (_i, []), "tmb_comm_sequence_counts": (_i, [_vp, _vp]),
     "tmb_set_boundary": (_i, [_d, _dp]), "tmb_set_hopping_phases": (_i, [_dp]), "tmb_set_mu": (_i, [_d]),
     "tmb_set_nd": (_i, [_d] * 3), "tmb_set_tuning": (_i, [_i] * 3), "tmb_set_hop2_variant": (_i, [_i]), "tmb_set_tile": (_i, [_i]), "tmb_set_prefetch_distance": (_i, [_i]), "tmb_set_host_chunk_sizes": (_i, [_vp, _i]), "tmb_host_hop_timeline": (_i, [_i, _vp, _vp, _vp, _i]), "tmb_set_overlap": (_i, [_i]), "tmb_set_p2p_diag": (_i, [_i]), "tmb_set_host_chunks": (_i, [_i]), "tmb_set_compression": (_i, [_i]),
     "tmb_field_alloc": (_vp, []), "tmb_field_free": (_i, [_vp]), "tmb_field_zero": (_i, [_vp]),

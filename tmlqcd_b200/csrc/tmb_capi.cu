@@ -469,6 +469,15 @@ extern "C" int tmb_comm_init_grid(const void *id128, int nt, int nz, int rank) {
 }
 extern "C" int tmb_comm_peer_mode(void) { return C.p2p ? 1 : 0; }
 extern "C" int tmb_comm_zpeer_mode(void) { return C.zsplit && C.zpeer ? 1 : 0; }
+/* test hook: how many sequence numbers the peer-mode T hops and the z-face pushes have taken so far (they count separately:
+ * the parity of the push count picks the z halo buffer, and a shared counter would give every push of a T x Z grid the same
+ * parity) */
+extern "C" int tmb_comm_sequence_counts(unsigned int *t_hops, unsigned int *z_pushes) {
+  NEED_INIT();
+  if (t_hops) *t_hops = C.hop_off;
+  if (z_pushes) *z_pushes = C.zhop_off;
+  return 0;
+}
 /* single GPU: exercise the Z-split path (face pack, exchange with itself, fix-up) */
 extern "C" int tmb_comm_loopback_z(int on) {
   NEED_INIT();
