@@ -135,8 +135,7 @@ def reference_inputs(gdims, nsrc=3):
             ref = refclient.Reference(*gdims, nthreads=os.cpu_count() or 1, halfspinor=hs)
             g = ref.random_gauge(123456)
             srcs = [ref.random_spinor_eo() for _ in range(nsrc)]
-            return g, srcs, ref, ("unmodified reference on the global lattice: start_ranlux(1,123456); random_gauge_field; "
-                                  "random_spinor_field_eo(RN_GAUSS) (benchmark.c:247-259)")
+            return g, srcs, ref, REFERENCE_INPUTS_HOW
     except Exception as e:  # pragma: no cover
         log("reference generator unavailable:", e)
     rng = np.random.default_rng(99)
@@ -196,7 +195,7 @@ def run_reference(args, dims, real_stdout=sys.stdout):
         "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, dims, "unmodified reference: start_ranlux(1,123456); random_gauge_field"),
+        "config": workload_config(args.gpus, dims, REFERENCE_INPUTS_HOW, nz=(args.nz if args.gpus > 1 else 1)),
         "gflops_1608": V * FLOP_SITE_REF * args.steps / t / 1e9,
         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": ref.nthreads,
                          "kind": "reference", "sample": f"{args.steps} EO+OE Hopping_Matrix pairs on {dims} "
@@ -214,11 +213,18 @@ def workload_name(ngpus, dims):
             "T-neighbour fields read in place over NVLink (peer mode; NCCL half-spinor halos as fallback)")
 
 
-def workload_config(ngpus, dims, gauge_how):
+REFERENCE_INPUTS_HOW = ("unmodified reference on the global lattice: start_ranlux(1,123456); random_gauge_field; "
+                        "random_spinor_field_eo(RN_GAUSS) (benchmark.c:247-259)")
+
+
+def workload_config(ngpus, dims, gauge_how, nt=None, nz=1):
+    """the `config` object of the JSON line - the same for both arms (`--impl reference` times the per-GPU volume on the host)"""
     V = int(np.prod(dims))
+    nt = ngpus // nz if nt is None else nt
     return {"workload": workload_name(ngpus, dims), "lattice_TxLXxLYxLZ": list(dims), "kappa": KAPPA, "mu": MU,
             "gauge": gauge_how, "l2": "inputs larger than L2: gauge field %.0f MB + spinors per call" % (V * 4 * 144 / 1e6),
-            "step": "one EO+OE Hopping_Matrix pair (benchmark.c:293-299)"}
+            "step": "one EO+OE Hopping_Matrix pair (benchmark.c:293-299)",
+            "rank_grid_TxZ": [nt, nz], "global_lattice_TxLXxLYxLZ": [dims[0] * nt, dims[1], dims[2], dims[3] * nz]}
 
 
 def cpu_baseline(ref, dims, target_s=10.0):
@@ -535,7 +541,7 @@ def main():
         "metric": "Hopping_Matrix GFLOP/s (eo, double, 1320 flop/site)", "value": gflops, "unit": "GFLOP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(world, dims, gauge_how), rank_grid_TxZ=[nt, nz], global_lattice_TxLXxLYxLZ=list(gdims)),
+        "config": workload_config(world, dims, gauge_how, nt=nt, nz=nz),
         "gflops_1608": sites * FLOP_SITE_REF * args.steps / (ms * 1e-3) / 1e9,
         "hbm_gbs_effective_per_gpu": achieved,
         "peer_mode": bool(lib.tmb_comm_peer_mode()),

@@ -23,6 +23,11 @@ def test_reference_arm_json_line(ref_available):
         assert key in d, key
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # both arms build `config` with the same function and the same description of the inputs: the driver compares them
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(1, (8, 8, 8, 8), bench.REFERENCE_INPUTS_HOW, nt=1, nz=1)
+    assert d["config"]["rank_grid_TxZ"] == [1, 1] and d["config"]["global_lattice_TxLXxLYxLZ"] == [8, 8, 8, 8]
 
 
 def test_b200_arm_fails_loudly_without_gpu():
