@@ -41,8 +41,8 @@ int tmb_comm_init(const void *id128, int nranks, int rank);
  * the reference's PARALLELXYZT, mpi_init.c:331-357, xchange/xchange_field.c:583-672).  tmb_init takes the local extents T / nt and
  * LZ / nz (even).  With nz > 1 the hopping kernels run unchanged on the slab and a fix-up over the z-face sites swaps the wrapped
  * z term for the neighbour's (the faces are pushed through peer memory when the arenas are mapped, NCCL
- * otherwise); solvers then use un-fused reductions; the fermion force, the plaquette and the
- * two-flavour float solver are T-split only. */
+ * otherwise); solvers then use un-fused reductions; the fermion force gets a fix-up of the z links of
+ * the last-z sites; the plaquette and the two-flavour float solver are T-split only. */
 int tmb_comm_init_grid(const void *id128, int nt, int nz, int rank);
 int tmb_comm_grid(int *nt, int *nz);
 int tmb_comm_loopback(int on); /* single GPU: exercise the T-split path against itself; 1: halo buffers, 2: peer mode */

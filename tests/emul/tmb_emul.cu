@@ -256,6 +256,18 @@ void emul_deriv(int ieo, const double *l, const double *k, const double *U, doub
       else          { if (last) tmb_deriv_site<0, 1>(f, g, q, i, ka, 2. * factor); else tmb_deriv_site<0, 0>(f, g, q, i, ka, 2. * factor); }
     }
 }
+/* Z split of the fermion force: the fix-up of the z links owned by the last-z sites (tmb_deriv_zfix); halo = [k dn-face | l dn-face]
+ * of the slab above, each [6][Sz] as emul_pack_zfaces writes its `dn` output */
+void emul_deriv_zfix(int ieo, const double *l, const double *k, const double *U, double *df, const double *halo_k, const double *halo_l,
+                     int T, int LX, int LY, int LZ, const double *ka8, double factor) {
+  tmb_geom g = tmb_make_geom(T, LX, LY, LZ, 0);
+  tmb_deriv_fields f;
+  f.l = (const double2 *)l; f.k = (const double2 *)k; f.U = (const double2 *)U; f.df = df; f.halo_k = nullptr; f.halo_l = nullptr;
+  const int Sz = T * LX * LY / 2;
+  for (int q = 0; q < 2; q++)
+    for (int j = 0; j < Sz; j++)
+      tmb_deriv_zfix(f, g, ieo, q, j, (const double2 *)halo_k, (const double2 *)halo_l, make_double2(ka8[6], ka8[7]), 2. * factor);
+}
 /* two-flavour hopping term with the epilogues of hop2_kernel (tmb_force.cu), applied site by site on the host:
  * mode 0 plain, 1 M_ee_inv_ndpsi of the two results, 2 scale * g5( M_oo(p0, p1) - H ) */
 void emul_hop2(int par, double *out0, double *out1, const double *in0, const double *in1, const double *p0, const double *p1,

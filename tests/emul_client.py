@@ -35,6 +35,7 @@ def load():
         "emul_pack_deriv": [dp, dp, i, i, i, i], "emul_unpack_deriv": [dp, dp, i, i, i, i],
         "emul_pack_deriv_halo": [dp, dp, dp, i, i, i, i],
         "emul_deriv": [i, dp, dp, dp, dp, dp, i, i, i, i, dp, d, i],
+        "emul_deriv_zfix": [i, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, d],
         "emul_blas32": [i, fp, fp, fp, C.c_float, C.c_float, C.c_long],
         "emul_hop2": [i, dp, dp, dp, dp, dp, dp, dp, i, i, i, i, dp, i, d, d, d],
         "emul_pack_gauge_first_slice": [dp, dp, i, i, i, i], "emul_plaquette": [dp, dp, i, i, i, i, i],

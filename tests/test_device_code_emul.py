@@ -321,3 +321,48 @@ def test_z_split_face_exchange_and_fixup(oracle_lib, gdims, nz):
                               T, LX, LY, LZl, par, np.asarray(ka, dtype=np.float64), cf[0], cf[1])
                 assert rel_l2(e.unpack(out), slab_f(exp, s)) < 1e-14, (par, mode, s)
                 assert wrong > 1e-3  # the un-fixed slab result really differs
+
+
+@pytest.mark.parametrize("gdims,nz", [((4, 4, 4, 8), 2), ((2, 4, 6, 12), 3), ((4, 2, 4, 4), 2)])
+def test_z_split_fermion_force_fixup(oracle_lib, gdims, nz):
+    """deriv_Sb on z slabs: every slab runs the unchanged force code as if it were periodic in z, then the fix-up of the z links
+    owned by its last-z sites takes the half-spinors of the slab above (the `dn` faces of the z-face pack of k and of l).
+    Against the oracle's deriv_Sb on the global lattice, both parities."""
+    T, LX, LY, LZ = gdims
+    LZl = LZ // nz
+    rng = np.random.default_rng(43)
+    theta = (1., 0., 0.3, 0.7)
+    o = oracle_lib.Oracle(*gdims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, theta)
+    ka = ka_of(KAPPA, theta, gdims)
+    l, k = random_spinor(rng, o.Vh), random_spinor(rng, o.Vh)
+    df0 = rng.normal(size=(o.V, 4, 8))
+    e = Emul(T, LX, LY, LZl)
+    rows, Sz = T * LX * LY, T * LX * LY // 2
+    gs = g.reshape(T, LX, LY, LZ, 4, 18)
+    slab_f = lambda f, s: np.ascontiguousarray(f.reshape(rows, LZ // 2, 24)[:, s * (LZl // 2):(s + 1) * (LZl // 2), :]).reshape(-1, 24)
+    slab_d = lambda d, s: np.ascontiguousarray(d.reshape(rows, LZ, 4, 8)[:, s * LZl:(s + 1) * LZl]).reshape(-1, 4, 8)
+    U = [e.pack_gauge(np.ascontiguousarray(gs[:, :, :, s * LZl:(s + 1) * LZl]).reshape(-1, 4, 18)) for s in range(nz)]
+    for ieo in (0, 1):
+        exp = df0.copy(); o.deriv_Sb(ieo, l, k, exp, 0.7)
+        sl = [e.pack(slab_f(l, s)) for s in range(nz)]
+        sk = [e.pack(slab_f(k, s)) for s in range(nz)]
+        faces = []
+        for s in range(nz):  # what slab s sends DOWN: the D = 6 projection of its first-z sites, of k (parity 1 - ieo) and of l (parity ieo)
+            junk, fk, fl = np.zeros(12 * Sz), np.zeros(12 * Sz), np.zeros(12 * Sz)
+            e.E.emul_pack_zfaces(junk, fk, sk[s], T, LX, LY, LZl, 1 - ieo)
+            e.E.emul_pack_zfaces(junk, fl, sl[s], T, LX, LY, LZl, ieo)
+            faces.append((fk, fl))
+        for s in range(nz):
+            d0 = slab_d(df0, s)
+            dev = np.zeros(64 * e.Vh); e.E.emul_pack_deriv(dev, np.ascontiguousarray(d0).reshape(-1), T, LX, LY, LZl)
+            e.E.emul_deriv(ieo, sl[s], sk[s], U[s], dev, np.zeros(2), T, LX, LY, LZl, np.asarray(ka, dtype=np.float64), 0.7, 0)
+            out = np.zeros(32 * e.V); e.E.emul_unpack_deriv(out, dev, T, LX, LY, LZl)
+            wrong = rel_l2(out.reshape(-1, 4, 8) - d0, slab_d(exp, s) - d0)
+            fk, fl = faces[(s + 1) % nz]
+            e.E.emul_deriv_zfix(ieo, sl[s], sk[s], U[s], dev, fk, fl, T, LX, LY, LZl, np.asarray(ka, dtype=np.float64), 0.7)
+            e.E.emul_unpack_deriv(out, dev, T, LX, LY, LZl)
+            assert wrong > 1e-3  # the slab alone is NOT right: the fix-up is what makes it so
+            assert rel_l2(out.reshape(-1, 4, 8) - d0, slab_d(exp, s) - d0) < 1e-14, (ieo, s)
+

@@ -178,12 +178,17 @@ def test_monomials_golden_reference(solver):
         d.close()
 
 
-def test_monomials_vs_oracle_loopback(oracle_lib):
-    """a larger lattice, theta != 0, through the T-split (loopback) halo path of hop and deriv_Sb"""
+@pytest.mark.parametrize("tloop,zloop", [(1, 0), (0, 2), (2, 2), (1, 1)])
+def test_monomials_vs_oracle_loopback(oracle_lib, tloop, zloop):
+    """a larger lattice, theta != 0, through the T-split (loopback) halo path of hop and deriv_Sb, through the Z-split path
+    (faces pushed / copied, fix-up of the hops and of the force) and through both at once"""
     dims, theta = (8, 4, 6, 8), (1., 0.3, 0., 0.7)
     rng, o, d, g = _setup(oracle_lib, dims, theta)
     try:
-        d.ck(d.lib.tmb_comm_loopback(1))
+        if tloop:
+            d.ck(d.lib.tmb_comm_loopback(tloop))
+        if zloop:
+            d.ck(d.lib.tmb_comm_loopback_z(zloop))
         d.gauge_upload(g)
         o.mnl_clear(); d.ck(d.lib.tmb_monomial_clear())
         for id, (typ, csg_N) in enumerate(((0, 2), (1, 1))):

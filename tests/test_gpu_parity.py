@@ -565,10 +565,14 @@ def test_z_split_against_itself(oracle_lib, tloop, zmode):
         # host-pointer hop on a split Z: plain upload / compute / download
         out = np.zeros_like(k); d.call("Hopping_Matrix_host", 0, out, k, 0, 1., 0.)
         o.Hopping_Matrix(0, exp, k); assert rel_l2(out, exp) <= TOL
+        # the fermion force: slab kernels + fix-up of the z links of the last-z sites (deriv_Sb.c:402-649, xchange_2fields)
+        df = o.derivative(); o.deriv_Sb(0, k, p, df, 0.7); o.deriv_Sb(1, p, k, df, -0.4)
+        d.call("derivative_zero"); d.call("deriv_Sb", 0, dk, dp, 0.7); d.call("deriv_Sb", 1, dp, dk, -0.4)
+        assert rel_l2(d.derivative_download(), df) <= TOL
         # T-split-only entry points refuse loudly
         import tmlqcd_b200 as tm
-        with pytest.raises(tm.capi.TmbError, match="split Z"):
-            d.call("deriv_Sb", 0, dk, dp, 1.0)
+        plaq = C.c_double(0.)
+        assert d.lib.tmb_measure_plaquette(C.byref(plaq)) < 0 and "split Z" in d.lib.tmb_last_error().decode()
     finally:
         d.close()
 

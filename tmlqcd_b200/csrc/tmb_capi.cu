@@ -65,6 +65,7 @@ struct Ctx {
   /* Z faces through peer memory (push): this rank's double-buffered halo buffers, where its own faces go on the z
    * neighbours, this rank's two flags and the neighbours' (ARENA_ZFLAGS) */
   bool zpeer = false; char *zloop_buf = nullptr;
+  double2 *zd_send = nullptr, *zd_recv = nullptr; /* fermion force on a split Z: first-z faces of k and l (send: + scratch) */
   void *zloc_up[2] = {nullptr, nullptr}, *zloc_dn[2] = {nullptr, nullptr}, *zdst_up[2] = {nullptr, nullptr}, *zdst_dn[2] = {nullptr, nullptr};
   unsigned int *zflags = nullptr, *zflag_at_up = nullptr, *zflag_at_dn = nullptr;
   cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -292,6 +293,7 @@ extern "C" int tmb_finalize(void) {
   if (C.zhalo_dn) cudaFree(C.zhalo_dn); if (C.Uzh) cudaFree(C.Uzh); if (C.Uzh32) cudaFree(C.Uzh32); if (C.Uzl) cudaFree(C.Uzl); if (C.Uzl32) cudaFree(C.Uzl32);
   cudaEventDestroy(C.ev_z);
   if (C.zloop_buf) cudaFree(C.zloop_buf);
+  if (C.zd_send) cudaFree(C.zd_send); if (C.zd_recv) cudaFree(C.zd_recv);
   cudaEventDestroy(C.ev_in); cudaEventDestroy(C.ev_halo); cudaEventDestroy(C.ev_t0); cudaEventDestroy(C.ev_t1);
   cudaEventDestroy(C.ev_chk[0]); cudaEventDestroy(C.ev_chk[1]);
   for (int i = 0; i < MAXCHUNK; i++) { cudaEventDestroy(C.ev_up[i]); cudaEventDestroy(C.ev_done[i]); }

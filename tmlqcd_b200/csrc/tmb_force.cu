@@ -26,6 +26,24 @@ __global__ void __launch_bounds__(128, 3) deriv_kernel(const tmb_deriv_launch a)
   else            tmb_deriv_site<0, DIST>(f, a.g, q, i, a.ka, a.c);
 }
 
+/* Z split: fix-up of the z links owned by the last-z sites of both parities (tmb_deriv_zfix, tmb_site.cuh); one thread per
+ * (parity, face site).  halo_k / halo_l: the `dn` faces of the z-face pack of k and of l, from rank z+1. */
+__global__ void __launch_bounds__(64) deriv_zfix_kernel(const tmb_deriv_launch a, const double2 *halo_k, const double2 *halo_l) {
+  const int Sz = a.g.T * a.g.LX * a.g.LY / 2;
+  const int w = blockIdx.x * 64 + threadIdx.x;
+  if (w >= 2 * Sz) return;
+  const int q = w >= Sz ? 1 : 0, j = w - q * Sz;
+  tmb_deriv_fields f;
+  f.l = (const double2 *)a.l; f.k = (const double2 *)a.k; f.U = (const double2 *)a.U; f.df = a.df;
+  f.halo_k = nullptr; f.halo_l = nullptr;
+  tmb_deriv_zfix(f, a.g, a.ieo, q, j, halo_k, halo_l, a.ka[3], a.c);
+}
+cudaError_t tmb_launch_deriv_zfix(const tmb_deriv_launch &a, const double2 *halo_k, const double2 *halo_l, cudaStream_t s) {
+  const int n = 2 * (a.g.T * a.g.LX * a.g.LY / 2);
+  deriv_zfix_kernel<<<(n + 63) / 64, 64, 0, s>>>(a, halo_k, halo_l);
+  return cudaGetLastError();
+}
+
 cudaError_t tmb_launch_deriv(const tmb_deriv_launch &a, cudaStream_t s) {
   const int n = a.nt * a.g.S;
   if (n <= 0) return cudaSuccess;

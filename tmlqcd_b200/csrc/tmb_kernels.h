@@ -192,6 +192,7 @@ struct tmb_deriv_launch {
   double2 ka[4]; double c; /* c = 2*factor */
 };
 cudaError_t tmb_launch_deriv(const tmb_deriv_launch &a, cudaStream_t s);
+cudaError_t tmb_launch_deriv_zfix(const tmb_deriv_launch &a, const double2 *halo_k, const double2 *halo_l, cudaStream_t s); /* Z split */
 /* first time-slice of k and of l, (1+g0)-projected: out[0][6][S] from k, out[1][6][S] from l */
 cudaError_t tmb_launch_pack_deriv_halo(double2 *out, const double2 *k, const double2 *l, tmb_geom g, cudaStream_t s);
 /* hf->derivative host layout [ix][mu][8] (init/init_moment_field.c:62-80) <-> device [2][4][8][Vh]; mode 0: set, 1: add */

@@ -602,6 +602,47 @@ TMB_HD void tmb_deriv_site(const tmb_deriv_fields &f, const tmb_geom &g, int q, 
   tmb_deriv_dir<3, FWD, DIST>(f, g, q, i, nb[6], t, loc, ka[3], c);
 }
 
+/* Z split: deriv_kernel runs on the slab as if it were periodic in z, so the z links owned by the LAST-z sites took their
+ * remote half-spinor from the slab's own first-z sites.  The term is linear in the remote half-spinor, hence
+ *   df[x][3] += link( P(local(x)), h_halo - h_wrapped )
+ * with h_halo from rank z+1's first-z sites.  Forward type (x of parity ieo) needs P_6(k(x+z)), backward type P_7(g5 l(x+z)) -
+ * and P_7 after g5 is the P_6 formula on l itself (s0 + i s2, s1 - i s3), so both halos are the `dn` faces of
+ * EwPackZFaces (D = 6 projection of the first-z sites) of k and of l.  halo_k / halo_l: [6][Sz], row enumeration of the
+ * receiving side (tmb_zface_row(g, q, j, 1)).  j in [0, Sz), q = parity of the link owner. */
+TMB_HD void tmb_deriv_zfix(const tmb_deriv_fields &f, const tmb_geom &g, int ieo, int q, int j, const double2 *halo_k,
+                           const double2 *halo_l, double2 ka3, double c) {
+  const int Sz = g.T * g.LX * g.LY / 2;
+  const bool fwd = q == ieo;
+  int row, t;
+  tmb_zface_row<double2>(g, q, j, 1, &row, &t);
+  const size_t i = (size_t)row * g.Lzh + (g.Lzh - 1), iw = (size_t)row * g.Lzh;
+  const double2 *lf = fwd ? f.l : f.k, *rf = fwd ? f.k : f.l, *h = fwd ? halo_k : halo_l;
+  double2 loc[12], rem[12], la[3], lb[3], ra[3], rb[3], u[9];
+#pragma unroll
+  for (int cidx = 0; cidx < 12; cidx++) {
+    double2 s = lf[(size_t)cidx * g.Vh + i], w = rf[(size_t)cidx * g.Vh + iw];
+    if (cidx >= 6) { if (fwd) s = make_double2(-s.x, -s.y); else w = make_double2(-w.x, -w.y); } /* g5 on the l-derived spinor */
+    loc[cidx] = s; rem[cidx] = w;
+  }
+  if (fwd) { tmb_project_regs<6>(la, lb, loc); tmb_project_regs<6>(ra, rb, rem); }
+  else     { tmb_project_regs<7>(la, lb, loc); tmb_project_regs<7>(ra, rb, rem); }
+#pragma unroll
+  for (int cidx = 0; cidx < 3; cidx++) {
+    ra[cidx] = c_sub(h[(size_t)cidx * Sz + j], ra[cidx]);
+    rb[cidx] = c_sub(h[(size_t)(3 + cidx) * Sz + j], rb[cidx]);
+  }
+  const double2 *ub = f.U + (size_t)((q * 4 + 3) * 9) * g.Vh + i;
+#pragma unroll
+  for (int e = 0; e < 9; e++) u[e] = ub[(size_t)e * g.Vh];
+  double *d = f.df + (size_t)((q * 4 + 3) * 8) * g.Vh + i;
+  double r[8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) r[a] = d[(size_t)a * g.Vh];
+  tmb_deriv_link(r, la, lb, ra, rb, u, ka3, c);
+#pragma unroll
+  for (int a = 0; a < 8; a++) d[(size_t)a * g.Vh] = r[a];
+}
+
 /* ====================================================================================
  * Plaquette: measure_plaquette, measure_gauge_action.c:46-106 - what tmLQCD_read_gauge prints after reading a
  * configuration (wrapper/lib_wrapper.c:232-235) and every main stores as plaquette_energy.
