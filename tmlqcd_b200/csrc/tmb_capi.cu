@@ -587,6 +587,7 @@ extern "C" int tmb_set_host_chunks(int n) { NEED_INIT(); if (n < 0 || n > MAXCHU
 extern "C" int tmb_set_host_chunk_sizes(const int *sizes, int n) {
   NEED_INIT();
   if (n < 0 || n > MAXCHUNK - 2) return fail(-7, "at most %d chunks", MAXCHUNK - 2);
+  if (n > 0 && sizes == nullptr) return fail(-7, "tmb_set_host_chunk_sizes: null size array");
   for (int i = 0; i < n; i++) if (sizes[i] <= 0) return fail(-7, "chunk sizes must be positive");
   for (int i = 0; i < n; i++) C.host_sched[i] = sizes[i];
   C.host_sched_n = n; C.param_gen++;
