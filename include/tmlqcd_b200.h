@@ -191,6 +191,9 @@ int tmb_mixed_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int re
 /* invert_eo with solver_flag == MIXEDCG: invert_eo.c:225-232 */
 int tmb_invert_eo_mixed(void *even_new, void *odd_new, const void *even, const void *odd, double precision,
                         int max_iter, int rel_prec);
+/* invert_eo with solver_flag == RGMIXEDCG: invert_eo.c:233-240 (delta of the reliable updates: tmb_set_mcg_delta) */
+int tmb_invert_eo_rgmixed(void *even_new, void *odd_new, const void *even, const void *odd, double precision,
+                          int max_iter, int rel_prec);
 
 /* ---- non-degenerate doublet: operator/tm_operators_nd.c:68,:130,:195,:639; cg_her_nd.c:57;
  *      invert_doublet_eo.c:68 ---- */

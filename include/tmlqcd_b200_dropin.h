@@ -119,7 +119,10 @@ void assign(spinor *const R, spinor *const S, const int N);
 void mul_r(spinor *const R, const double c, spinor *const S, const int N);
 void convert_eo_to_lexic(spinor *const P, spinor *const s, spinor *const r);
 void convert_lexic_to_eo(spinor *const s, spinor *const r, spinor *const P);
-/* solver/cg_her.c:62; invert_eo.c:83 */
+/* solver/cg_her.c:62: f == Qtm_pm_psi on VOLUME/2 sites and f == Q_pm_psi on VOLUME sites run on device-resident fields;
+ * any other f runs the same recurrence with f applied through its host-pointer entry point.
+ * invert_eo.c:83: with even/odd preconditioning solver_flag CG (:252-272), MIXEDCG (:225-232), RGMIXEDCG (:233-240; delta =
+ * solver_params.mcg_delta); without it (even_odd_flag == 0) CG (:527-541).  Other flags terminate with a message. */
 int cg_her(spinor *const P, spinor *const Q, const int max_iter, double eps_sq, const int rel_prec, const int N, matrix_mult f);
 int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
               const double precision, const int max_iter, const int solver_flag, const int rel_prec,

@@ -214,6 +214,16 @@ int ref_invert_eo(double *even_new, double *odd_new, double *even, double *odd,
   return invert_eo((spinor *)even_new, (spinor *)odd_new, (spinor *)even, (spinor *)odd, precision, max_iter, solver_flag,
                    rel_prec, 0, 1, 0, NULL, sp, 0, NO_EXT_INV, 0, NO_COMPRESSION);
 }
+/* the same with every flag of the scoped branches open: solver_flag CG / MIXEDCG / RGMIXEDCG (delta = solver_params.mcg_delta
+ * of the reliable updates), even_odd_flag 0 = the full-lattice branch (invert_eo.c:426-556: cg_her on Q_pm_psi, VOLUME sites) */
+int ref_invert_eo_flags(double *even_new, double *odd_new, double *even, double *odd, double precision, int max_iter,
+                        int rel_prec, int solver_flag, int even_odd_flag, double delta) {
+  solver_params_t sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.mcg_delta = (float)delta;
+  return invert_eo((spinor *)even_new, (spinor *)odd_new, (spinor *)even, (spinor *)odd, precision, max_iter, solver_flag,
+                   rel_prec, 0, even_odd_flag, 0, NULL, sp, 0, NO_EXT_INV, 0, NO_COMPRESSION);
+}
 int ref_invert_eo_cg(double *even_new, double *odd_new, double *even, double *odd,
                      double precision, int max_iter, int rel_prec) {
   return ref_invert_eo(even_new, odd_new, even, odd, precision, max_iter, rel_prec, CG);

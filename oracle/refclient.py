@@ -86,6 +86,7 @@ class Reference:
             "ref_mul_r": (None, [_dp, d, _dp, i]),
             "ref_cg_her": (i, [_dp, _dp, i, d, i]),
             "ref_invert_eo_cg": (i, [_dp, _dp, _dp, _dp, d, i, i]),
+            "ref_invert_eo_flags": (i, [_dp, _dp, _dp, _dp, d, i, i, i, i, d]),
             "ref_Qtm_pm_ndpsi": (None, [_dp] * 4),
             "ref_Qtm_ndpsi": (None, [_dp] * 4),
             "ref_Qtm_dagger_ndpsi": (None, [_dp] * 4),

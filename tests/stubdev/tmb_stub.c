@@ -179,6 +179,7 @@ int tmb_solver_stats(int *it, double *err, double *sec) { if (it) *it = S.last_i
 int tmb_mixed_cg_her(void *P, const void *Q, int m, double e, int r) { NEEDG(); memset(P, 0, NF * sizeof(double)); return tmb_cg_her(P, Q, m, e, r); }
 int tmb_rg_mixed_cg_her(void *P, const void *Q, int m, double e, int r) { return tmb_cg_her(P, Q, m, e, r); }
 int tmb_invert_eo_mixed(void *en, void *on, const void *e, const void *o, double p, int m, int r) { memset(on, 0, NF * sizeof(double)); return tmb_invert_eo(en, on, e, o, p, m, r); }
+int tmb_invert_eo_rgmixed(void *en, void *on, const void *e, const void *o, double p, int m, int r) { return tmb_invert_eo_mixed(en, on, e, o, p, m, r); }
 int tmb_solve_degenerate(void *P, const void *Q, int m, double e, int r, int solver) {
   if (solver != TMB_SOLVER_CG && solver != TMB_SOLVER_MIXEDCG && solver != TMB_SOLVER_RGMIXEDCG) { snprintf(S.err, sizeof(S.err), "solver %d not allowed", solver); return -32; }
   return tmb_cg_her(P, Q, m, e, r);

@@ -82,6 +82,37 @@ def test_inversions_with_reference_signatures(dropin):
     g.test_inversions_with_reference_signatures(dropin)
 
 
+def test_invert_eo_remaining_branches(dropin):
+    import test_gpu_dropin_ops as g
+    g.test_invert_eo_remaining_branches(dropin)
+
+
+def test_invert_eo_branches_against_the_live_reference(dropin, ref_available):
+    """the unmodified invert_eo.c (oracle/_ref, half-spinor build for the float operator) run here with the same flags:
+    RGMIXEDCG with even/odd preconditioning, CG without it - solutions, and the iteration count of the branch whose
+    arithmetic the stand-in shares (the full-lattice CG)"""
+    from oracle import refclient
+    import tmlqcd_b200 as tm
+    if not ref_available or not refclient.available(halfspinor=True):
+        pytest.skip("oracle/_ref not built")
+    D, base = dropin
+    k, p = np.array(base["k"]), np.array(base["p"])
+    ref = refclient.Reference(*[int(x) for x in base["dims"]], nthreads=2, halfspinor=True)
+    ref.set_gauge(base["gauge"]); ref.set_params(float(base["kappa"]), float(base["gmu"]), base["theta"])
+    assert ref.init32() == 0
+    ref.update_gauge32()
+    sp = tm.capi.SolverParams(); sp.mcg_delta = 5e-5
+    for solver, eo, prec in ((14, 1, 1e-20), (1, 0, 1e-24)):
+        enr, onr = ref.spinor(), ref.spinor()
+        itr = ref.invert_eo_flags(enr, onr, k.copy(), p.copy(), prec, 3000, 1, solver, eo, 5e-5)
+        en, on = D.spinor(), D.spinor()
+        it = D.invert_eo(en, on, k, p, prec, 3000, solver, 1, 0, eo, 0, None, sp, 0, 0, 0, 18)
+        assert itr > 0 and it > 0
+        assert rel_l2(en, enr) <= 1e-7 and rel_l2(on, onr) <= 1e-7, (solver, eo)
+        if not eo:
+            assert abs(it - itr) <= 1, (it, itr)
+
+
 def test_reference_symbols_globals_and_dirty_flag(on_stub, oracle_lib):
     import test_gpu_parity as g
     g.test_dropin_reference_symbols(oracle_lib)

@@ -140,6 +140,35 @@ def test_inversions_with_reference_signatures(dropin):
     assert it > 0 and rel_l2(xu, g["x_s"]) <= 1e-8 and rel_l2(xd, g["x_c"]) <= 1e-8
 
 
+def test_invert_eo_remaining_branches(dropin):
+    """invert_eo's MIXEDCG and RGMIXEDCG branches (invert_eo.c:225-240) and its branch WITHOUT even/odd preconditioning
+    (:426-556: cg_her on Q_pm_psi over VOLUME sites, the source as initial guess, then Q_minus_psi): all of them solve the
+    system of the CG branch, whose solution by the unmodified reference is in the fixture.  Then cg_her(N = VOLUME,
+    f = Q_pm_psi) - the recurrence on (even, odd) pairs of device fields - against the generic path (same recurrence, f
+    through its host-pointer entry point) and against the defining equation."""
+    import tmlqcd_b200 as tm
+    D, base = dropin
+    k, p, lex = (np.array(base[n]) for n in ("k", "p", "lex"))
+    sp = tm.capi.SolverParams(); sp.mcg_delta = 5e-5
+    for solver, eo, prec in ((MIXEDCG, 1, 1e-20), (RGMIXEDCG, 1, 1e-20), (CG, 0, 1e-24)):
+        en, on = D.spinor(), D.spinor()
+        it = D.invert_eo(en, on, k, p, prec, 3000, solver, 1, 0, eo, 0, None, sp, 0, 0, 0, 18)
+        assert it > 0, (solver, eo)
+        assert rel_l2(en, base["invert_en"]) <= 1e-7 and rel_l2(on, base["invert_on"]) <= 1e-7, (solver, eo)
+    x1, x2, out = D.spinor(D.V), D.spinor(D.V), D.spinor(D.V)
+    it1 = D.cg_her(x1, lex, 3000, 1e-20, 1, D.V, D.fptr("Q_pm_psi"))
+    raw = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(("Q_pm_psi", D.lib))
+    cb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(lambda l_, k_: raw(l_, k_))
+    it2 = D.cg_her(x2, lex, 3000, 1e-20, 1, D.V, C.cast(cb, C.c_void_p))
+    assert it1 > 0 and abs(it1 - it2) <= 1 and rel_l2(x1, x2) <= 1e-9
+    D.Q_pm_psi(out, x1)
+    assert rel_l2(out, lex) <= 1e-9
+    # solve_degenerate hands f == Q_pm_psi on VOLUME sites to the same CG (monomial_solve.c:149)
+    x3 = D.spinor(D.V)
+    it3 = D.solve_degenerate(x3, lex, sp, 3000, 1e-20, 1, D.V, D.fptr("Q_pm_psi"), CG)
+    assert it3 == it1 and rel_l2(x3, x1) <= 1e-12
+
+
 def _hmc_dropin():
     import tmlqcd_b200 as tm
     gold = _gold("ref_hmc_4x4x4x4.npz")

@@ -75,7 +75,7 @@ DEVICE_API = {
     "tmb_D_psi_eo_32": (_i, [_vp] * 4), "tmb_M_full_32": (_i, [_vp] * 4 + [_i]),
     "tmb_field32_upload_lexic": (_i, [_vp, _vp, _vp]), "tmb_field32_download_lexic": (_i, [_vp, _vp, _vp]),
     "tmb_set_mixcg": (_i, [_d, _i]), "tmb_mixed_cg_her": (_i, [_vp, _vp, _i, _d, _i]),
-    "tmb_invert_eo_mixed": (_i, [_vp] * 4 + [_d, _i, _i]),
+    "tmb_invert_eo_mixed": (_i, [_vp] * 4 + [_d, _i, _i]), "tmb_invert_eo_rgmixed": (_i, [_vp] * 4 + [_d, _i, _i]),
     "tmb_set_mcg_delta": (_i, [_d]), "tmb_rg_mixed_cg_her": (_i, [_vp, _vp, _i, _d, _i]),
     "tmb_derivative_zero": (_i, []), "tmb_derivative_upload": (_i, [_vp]), "tmb_derivative_download": (_i, [_vp]),
     "tmb_deriv_Sb": (_i, [_i, _vp, _vp, _d]),
@@ -198,7 +198,7 @@ DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND"
                   "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit", "g_relative_precision_flag",
                   "GaugeInfo", "gauge_precision_read_flag", "g_disable_IO_checks", "g_beta", "g_rgi_C1"]
 
-_SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed",
+_SOLVERS = {"cg_her", "invert_eo", "cg_her_nd", "invert_doublet_eo", "mixed_cg_her", "invert_eo_mixed", "invert_eo_rgmixed",
             "rg_mixed_cg_her", "solve_degenerate", "invert_doublet_eo_solver", "rg_mixed_cg_her_nd"}
 _lib = None
 

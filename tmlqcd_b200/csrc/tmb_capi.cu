@@ -533,7 +533,7 @@ static int allreduce_slot(int slot) {
 /* ------------------------------------------------------------------ parameters */
 extern "C" int tmb_set_boundary(double kappa, const double theta[4]) {
   NEED_INIT();
-  /* boundary.c:40-55, incl. its PI_ literal; global extents: only T is distributed */
+  /* boundary.c:40-55, incl. its PI_ literal; global extents: T is distributed over nt ranks, Z over nz */
   const double PI_ = 3.14159265358979;
   const double ext[4] = {(double)C.g.T * C.nt, (double)C.g.LX, (double)C.g.LY, (double)C.g.LZ * C.nz};
   C.kappa = kappa; C.param_gen++;

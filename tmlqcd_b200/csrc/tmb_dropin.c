@@ -34,7 +34,7 @@ int mixcg_maxinnersolverit = 5000; /* default_input_values.h:194 */
 
 static su3 *gauge_slab = NULL;
 static int dropin_up = 0;
-#define NDEV 12
+#define NDEV 14
 static void *D[NDEV];
 static void *D32[4];
 
@@ -277,7 +277,57 @@ double measure_plaquette(const su3 **const gf) {
  * way) runs entirely on the device.  Any other f is applied through its own host-pointer
  * entry point with the same recurrence driven from here - correct, but every step crosses
  * PCIe; it exists so that the symbol is a complete replacement. */
+/* cg_her on the full lattice with f == Q_pm_psi (the non-even/odd inversions: invert_eo.c:527-541, the det monomial without
+ * even/odd preconditioning): the recurrence of cg_her.c:80-127 on (even, odd) PAIRS of device fields.  A lexicographic field
+ * is exactly such a pair on the device (the permutation is part of the transfer), Q_pm_psi = Q_+ Q_- is two M_full-type
+ * launches per parity with g_mu flipped in between (tm_operators.c:380-388); only the scalars cross PCIe.
+ * Slots: x = (6,7) initial guess and result, b = (4,5) source; work fields r (8,9), p (10,11), A p (2,3), temporaries (0,1). */
+static void pair_Q_pm(int o0, int o1, int i0, int i1) {
+  CHK(tmb_set_mu(-g_mu));
+  CHK(tmb_Q_full(dev(0), dev(1), dev(i0), dev(i1)));
+  CHK(tmb_set_mu(g_mu));
+  CHK(tmb_Q_full(dev(o0), dev(o1), dev(0), dev(1)));
+}
+static double pair_norm(int a0, int a1) {
+  double r0, r1; CHK(tmb_square_norm(dev(a0), &r0)); CHK(tmb_square_norm(dev(a1), &r1)); return r0 + r1;
+}
+static int cg_pair_Q_pm(const int max_iter, const double eps_sq, const int rel_prec) {
+  int r0 = 8, r1 = 9, q0 = 2, q1 = 3, it; /* cg_her.c's solver_field[1] and [0], swapped every iteration */
+  const int p0 = 10, p1 = 11;
+  double normsq, pro, pr0, pr1, err, e0, e1, alpha, beta;
+  const double t0 = wall(), squarenorm = pair_norm(4, 5);
+  pair_Q_pm(q0, q1, 6, 7);
+  CHK(tmb_diff(dev(r0), dev(4), dev(q0))); CHK(tmb_diff(dev(r1), dev(5), dev(q1)));
+  CHK(tmb_assign(dev(p0), dev(r0))); CHK(tmb_assign(dev(p1), dev(r1)));
+  normsq = pair_norm(r0, r1);
+  for (it = 1; it <= max_iter; it++) {
+    pair_Q_pm(q0, q1, p0, p1);
+    CHK(tmb_scalar_prod_r(dev(p0), dev(q0), &pr0)); CHK(tmb_scalar_prod_r(dev(p1), dev(q1), &pr1));
+    pro = pr0 + pr1;
+    alpha = normsq / pro;
+    CHK(tmb_assign_add_mul_r(dev(6), dev(p0), alpha)); CHK(tmb_assign_add_mul_r(dev(7), dev(p1), alpha));
+    CHK(tmb_assign_mul_add_r_and_square(dev(q0), -alpha, dev(r0), &e0));
+    CHK(tmb_assign_mul_add_r_and_square(dev(q1), -alpha, dev(r1), &e1));
+    err = e0 + e1;
+    if ((err <= eps_sq && rel_prec == 0) || (err <= eps_sq * squarenorm && rel_prec == 1)) break;
+    beta = err / normsq;
+    CHK(tmb_assign_mul_add_r(dev(p0), beta, dev(q0))); CHK(tmb_assign_mul_add_r(dev(p1), beta, dev(q1)));
+    { int t = q0; q0 = r0; r0 = t; t = q1; q1 = r1; r1 = t; }
+    normsq = err;
+  }
+  if (g_debug_level > 0 && g_proc_id == 0) printf("# CG: iter: %d eps_sq: %1.4e t/s: %1.4e\n", it, eps_sq, wall() - t0); /* cg_her.c:134 */
+  return it > max_iter ? -1 : it;
+}
+
 int cg_her(spinor *const P, spinor *const Q, const int max_iter, double eps_sq, const int rel_prec, const int N, matrix_mult f) {
+  if (f == &Q_pm_psi && N == VOLUME) {
+    sync_globals();
+    CHK(tmb_field_upload_lexic(dev(4), dev(5), (const double *)Q));
+    CHK(tmb_field_upload_lexic(dev(6), dev(7), (const double *)P));
+    const int iter = cg_pair_Q_pm(max_iter, eps_sq, rel_prec);
+    CHK(tmb_field_download_lexic((double *)P, dev(6), dev(7)));
+    return iter;
+  }
   if (f == &Qtm_pm_psi && N == VOLUME / 2) {
     sync_globals();
     up(6, Q); up(7, P);
@@ -417,22 +467,44 @@ void gamma5_32(spinor32 *const l, spinor32 *const k, const int V) {
   for (int j = 0, n = nparts(V, __func__); j < n; j++) { up32(0, PART32(k, j)); CHK(tmb_blas32(5, dev32(1), dev32(0), NULL, 0., 0.)); down32(PART32(l, j), 1); }
 }
 
-/* invert_eo.c:83-561: the even/odd CG branch (:152-157, :252, :268-270, :306-310) */
+/* invert_eo.c:83-561.  With even/odd preconditioning (:126-318) the CG, MIXEDCG and RGMIXEDCG branches (:252-272, :225-232,
+ * :233-240); without it (:426-556) the CG branch (:527-541).  Every other solver_flag terminates with a message. */
+static int invert_no_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
+                        const double precision, const int max_iter, const int rel_prec) {
+  /* invert_eo.c:428, :527-541, :555: convert_eo_to_lexic(DUM_DERI, Even, Odd); gamma5(DUM_DERI+1, DUM_DERI);
+   * cg_her(DUM_DERI, DUM_DERI+1, .., VOLUME, &Q_pm_psi) - the source is its own initial guess -;
+   * Q_minus_psi(DUM_DERI+1, DUM_DERI); convert_lexic_to_eo(Even_new, Odd_new, DUM_DERI+1).  On the device the lexicographic
+   * field IS the (even, odd) pair, so the two permutations fall away. */
+  if (g_proc_id == 0 && g_debug_level > 0) { printf("# Not using even/odd preconditioning!\n# Using CG!\n"); fflush(stdout); }
+  sync_globals();
+  up(6, Even); up(7, Odd);
+  CHK(tmb_gamma5(dev(4), dev(6))); CHK(tmb_gamma5(dev(5), dev(7)));
+  const int iter = cg_pair_Q_pm(max_iter, precision, rel_prec);
+  CHK(tmb_set_mu(-g_mu));
+  CHK(tmb_Q_full(dev(2), dev(3), dev(6), dev(7)));
+  CHK(tmb_set_mu(g_mu));
+  down(Even_new, 2); down(Odd_new, 3);
+  return iter;
+}
 int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
               const double precision, const int max_iter, const int solver_flag, const int rel_prec,
               const int sub_evs_flag, const int even_odd_flag, const int no_extra_masses,
               double *const extra_masses, solver_params_t solver_params, const int id,
               const ExternalInverter external_inverter, const SloppyPrecision sloppy,
               const CompressionType compression) {
-  (void)sub_evs_flag; (void)no_extra_masses; (void)extra_masses; (void)solver_params; (void)id;
+  (void)sub_evs_flag; (void)no_extra_masses; (void)extra_masses; (void)id;
   (void)external_inverter; (void)sloppy;
-  if (!even_odd_flag || (solver_flag != TMB_SOLVER_CG && solver_flag != TMB_SOLVER_MIXEDCG)) {
-    fprintf(stderr, "tmLQCD-B200 FATAL in invert_eo: only the even/odd CG and MIXEDCG branches (even_odd_flag != 0) "
-                    "are implemented on the GPU; got solver_flag=%d even_odd_flag=%d\n", solver_flag, even_odd_flag);
+  const int eo_ok = solver_flag == TMB_SOLVER_CG || solver_flag == TMB_SOLVER_MIXEDCG || solver_flag == TMB_SOLVER_RGMIXEDCG;
+  if ((even_odd_flag && !eo_ok) || (!even_odd_flag && solver_flag != TMB_SOLVER_CG)) {
+    fprintf(stderr, "tmLQCD-B200 FATAL in invert_eo: implemented on the GPU are CG, MIXEDCG and RGMIXEDCG with even/odd "
+                    "preconditioning and CG without; got solver_flag=%d even_odd_flag=%d\n", solver_flag, even_odd_flag);
     exit(1);
   }
+  if (!even_odd_flag) return invert_no_eo(Even_new, Odd_new, Even, Odd, precision, max_iter, rel_prec);
   if (g_proc_id == 0 && g_debug_level > 0) {
-    printf("# Using even/odd preconditioning!\n# Using CG!\n# mu = %.12f, kappa = %.12f\n", g_mu / 2. / g_kappa, g_kappa);
+    printf("# Using even/odd preconditioning!\n");
+    if (solver_flag == TMB_SOLVER_CG) printf("# Using CG!\n# mu = %.12f, kappa = %.12f\n", g_mu / 2. / g_kappa, g_kappa);
+    else printf("# Using Mixed Precision CG!\n"); /* invert_eo.c:228, :236 */
     fflush(stdout);
   }
   const double t0 = wall();
@@ -447,6 +519,9 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
   if (solver_flag == TMB_SOLVER_MIXEDCG) { /* invert_eo.c:225-232; mixed_cg_her zeroes the guess (:108) */
     CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
     iter = tmb_invert_eo_mixed(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
+  } else if (solver_flag == TMB_SOLVER_RGMIXEDCG) { /* invert_eo.c:233-240; rg_mixed_cg_her starts from zero (:226) */
+    CHK(tmb_set_mcg_delta((double)solver_params.mcg_delta));
+    iter = tmb_invert_eo_rgmixed(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
   } else
     iter = tmb_invert_eo(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
   if (iter < -1) die(__func__);
@@ -917,8 +992,11 @@ int chrono_guess(spinor *const trial, spinor *const phi, spinor **const v, int i
 /* solver/monomial_solve.c:86 */
 int solve_degenerate(spinor *const P, spinor *const Q, solver_params_t solver_params, const int max_iter, double eps_sq,
                      const int rel_prec, const int N, matrix_mult f, int solver_type) {
+  if (f == &Q_pm_psi && N == VOLUME && solver_type == TMB_SOLVER_CG) /* monomials without even/odd preconditioning: monomial_solve.c:149 */
+    return cg_her(P, Q, max_iter, eps_sq, rel_prec, N, f);
   if (f != &Qtm_pm_psi || N != VOLUME / 2) {
-    fprintf(stderr, "tmLQCD-B200 FATAL in solve_degenerate: only f == Qtm_pm_psi on VOLUME/2 sites is implemented\n");
+    fprintf(stderr, "tmLQCD-B200 FATAL in solve_degenerate: implemented are f == Qtm_pm_psi on VOLUME/2 sites (CG, MIXEDCG, RGMIXEDCG) "
+                    "and f == Q_pm_psi on VOLUME sites (CG)\n");
     exit(1);
   }
   if (solver_type != TMB_SOLVER_CG && solver_type != TMB_SOLVER_MIXEDCG && solver_type != TMB_SOLVER_RGMIXEDCG) {
