@@ -293,6 +293,10 @@ int tmLQCD_b200_set_lattice(int t, int lx, int ly, int lz);
 int tmLQCD_b200_add_operator(double kappa, double two_kappa_mu, double eps_sq, int max_iter, int rel_prec);
 int tmLQCD_b200_set_theta(double x0, double x1, double x2, double x3);
 int tmLQCD_b200_get_solver_info(int op_id, int *iterations, double *reached_prec);
+/* the operator's Solver / UseEvenOdd / mcgdelta keys (read_input.l:1094-1133, :967-974, :835-838; defaults operator.c:102-125:
+ * CG, even/odd preconditioning, 5e-5): TMB_SOLVER_CG / _MIXEDCG / _RGMIXEDCG with even_odd_flag != 0, TMB_SOLVER_CG with 0;
+ * mcg_delta <= 0 keeps the current value.  -1 for a combination invert_eo does not implement here. */
+int tmLQCD_b200_set_operator_solver(int op_id, int solver_flag, int even_odd_flag, double mcg_delta);
 /* GaugeConfigInputFile (default "conf", default_input_values.h:91) and the propagator output of
  * tmLQCD_invert(..., write_prop != 0): basename (default "source", :93) and precision (default 32, :126) */
 int tmLQCD_b200_set_io(const char *gauge_input_filename, const char *prop_basename, int prop_precision);

@@ -124,6 +124,11 @@ def test_tmLQCD_facade(on_stub, oracle_lib, tmp_path, monkeypatch):
     g.test_tmLQCD_facade(oracle_lib)
 
 
+def test_tmLQCD_facade_solver_keys(on_stub, oracle_lib, tmp_path, monkeypatch):
+    import test_gpu_parity as g
+    g.test_tmLQCD_facade_solver_keys(oracle_lib, tmp_path, monkeypatch)
+
+
 def test_fermion_force_accumulates_into_the_callers_array(on_stub):
     gold = _gold("ref_hmc_4x4x4x4.npz")
     D = on_stub(*[int(x) for x in gold["dims"]])

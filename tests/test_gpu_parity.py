@@ -680,6 +680,57 @@ def test_tmLQCD_facade(oracle_lib):
         assert lib.tmLQCD_finalise() == 0
 
 
+def test_tmLQCD_facade_solver_keys(oracle_lib, tmp_path, monkeypatch):
+    """the operator block's Solver / UseEvenOdd / mcgdelta / SolverRelativePrecision keys of invert.input (read_input.l:1094-1133,
+    :967-974, :835-838, :824-833; defaults operator.c:102-125) reach invert_eo's branches through tmLQCD_invert (op_invert,
+    operator.c:349-355): every implemented combination gives the propagator of the CG branch; an unimplemented solver is
+    refused at tmLQCD_invert_init instead of silently running CG"""
+    import tmlqcd_b200 as tm
+    lib = tm.load()
+    dims = (4, 4, 4, 6)
+    rng = np.random.default_rng(12)
+    o = oracle_lib.Oracle(*dims)
+    g = random_gauge(rng, o.V)
+    o.set_gauge(g); o.set_params(KAPPA, GMU, (1., 0., 0., 0.))
+    monkeypatch.chdir(tmp_path)
+    blocks = [("cg", "yes", ""), ("mixedcg", "yes", ""), ("rgmixedcg", "yes", "  mcgdelta = 1.e-3\n"), ("cg", "no", "")]
+    text = f"T = {dims[0]}\nLX = {dims[1]}\nLY = {dims[2]}\nLZ = {dims[3]}\nThetaT = 1.\n"
+    for solver, eo, extra in blocks:
+        text += (f"BeginOperator TMWILSON\n  2KappaMu = {GMU}\n  kappa = {KAPPA}\n  Solver = {solver}\n  UseEvenOdd = {eo}\n{extra}"
+                 "  SolverPrecision = 1.e-20\n  MaxSolverIterations = 3000\n  SolverRelativePrecision = yes\nEndOperator\n")
+    (tmp_path / "invert.input").write_text(text)
+    assert lib.tmLQCD_invert_init(0, None, 0, 0) == 0
+    try:
+        lp = (C.c_uint * 7)()  # tmLQCD_lat_params: LX, LY, LZ, T, nstore, nsave, no_operators (include/tmLQCD.h:37-44)
+        assert lib.tmLQCD_get_lat_params(C.cast(lp, C.c_void_p)) == 0 and lp[6] == len(blocks) and lp[3] == dims[0]
+        gf = C.POINTER(C.c_double)()
+        assert lib.tmLQCD_get_gauge_field_pointer(C.byref(gf)) == 0
+        C.memmove(gf, g.ctypes.data, g.nbytes)
+        src = random_spinor(rng, o.V)
+        E, O, En, On = o.spinor(), o.spinor(), o.spinor(), o.spinor()
+        o.convert_lexic_to_eo(E, O, src)
+        itr = o.invert_eo_cg(En, On, E, O, 1e-20, 3000, 1)
+        exp = o.spinor(o.V)
+        o.convert_eo_to_lexic(exp, En * (2 * KAPPA), On * (2 * KAPPA))
+        for op, (solver, eo, _) in enumerate(blocks):
+            prop = np.zeros_like(src)
+            assert lib.tmLQCD_invert(prop, src, op, 0) == 0
+            it, rp = C.c_int(0), C.c_double(0.)
+            lib.tmLQCD_b200_get_solver_info(op, C.byref(it), C.byref(rp))
+            assert it.value > 0 and rel_l2(prop, exp) <= 1e-7, (solver, eo, it.value)
+            assert rp.value <= 1e-14 * np.linalg.norm(src) ** 2, (solver, eo, rp.value)
+            if op == 0:
+                assert abs(it.value - itr) <= 1
+        # the programmatic form of the same keys; combinations invert_eo does not implement are refused
+        assert lib.tmLQCD_b200_set_operator_solver(0, 13, 1, 0.) == 0
+        assert lib.tmLQCD_b200_set_operator_solver(0, 13, 0, 0.) == -1 and lib.tmLQCD_b200_set_operator_solver(0, 2, 1, 0.) == -1
+        assert lib.tmLQCD_b200_set_operator_solver(99, 1, 1, 0.) == -1
+    finally:
+        assert lib.tmLQCD_finalise() == 0
+    (tmp_path / "invert.input").write_text(text.replace("Solver = mixedcg", "Solver = bicgstab"))
+    assert lib.tmLQCD_invert_init(0, None, 0, 0) == -1
+
+
 def test_full_size_properties(oracle_lib):
     """BASELINE config 2 size (24^3 x 48): size-independent properties + a sampled oracle check."""
     import tmlqcd_b200 as tm

@@ -191,6 +191,7 @@ DROPIN_API = {
     "tmLQCD_get_mpi_params": (_i, [_vp]), "tmLQCD_get_lat_params": (_i, [_vp]),
     "tmLQCD_b200_set_lattice": (_i, [_i] * 4), "tmLQCD_b200_add_operator": (_i, [_d, _d, _d, _i, _i]),
     "tmLQCD_b200_set_theta": (_i, [_d] * 4), "tmLQCD_b200_get_solver_info": (_i, [_i, C.POINTER(_i), C.POINTER(_d)]),
+    "tmLQCD_b200_set_operator_solver": (_i, [_i, _i, _i, _d]),
 }
 DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND", "g_update_gauge_copy", "g_proc_id",
                   "g_debug_level", "g_nproc", "g_nproc_t", "g_kappa", "g_mu", "g_mubar", "g_epsbar", "phmc_invmaxev",

@@ -467,25 +467,30 @@ void gamma5_32(spinor32 *const l, spinor32 *const k, const int V) {
   for (int j = 0, n = nparts(V, __func__); j < n; j++) { up32(0, PART32(k, j)); CHK(tmb_blas32(5, dev32(1), dev32(0), NULL, 0., 0.)); down32(PART32(l, j), 1); }
 }
 
-/* invert_eo.c:83-561.  With even/odd preconditioning (:126-318) the CG, MIXEDCG and RGMIXEDCG branches (:252-272, :225-232,
- * :233-240); without it (:426-556) the CG branch (:527-541).  Every other solver_flag terminates with a message. */
+/* invert_eo without even/odd preconditioning, the device part: source pair in slots (6, 7) (overwritten: it is the CG's initial guess and iterate), solution in (2, 3) */
+static int invert_no_eo_dev(const double precision, const int max_iter, const int rel_prec) {
+  if (g_proc_id == 0 && g_debug_level > 0) { printf("# Not using even/odd preconditioning!\n# Using CG!\n"); fflush(stdout); }
+  CHK(tmb_gamma5(dev(4), dev(6))); CHK(tmb_gamma5(dev(5), dev(7)));
+  const int iter = cg_pair_Q_pm(max_iter, precision, rel_prec);
+  CHK(tmb_set_mu(-g_mu));
+  CHK(tmb_Q_full(dev(2), dev(3), dev(6), dev(7)));
+  CHK(tmb_set_mu(g_mu));
+  return iter;
+}
 static int invert_no_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
                         const double precision, const int max_iter, const int rel_prec) {
   /* invert_eo.c:428, :527-541, :555: convert_eo_to_lexic(DUM_DERI, Even, Odd); gamma5(DUM_DERI+1, DUM_DERI);
    * cg_her(DUM_DERI, DUM_DERI+1, .., VOLUME, &Q_pm_psi) - the source is its own initial guess -;
    * Q_minus_psi(DUM_DERI+1, DUM_DERI); convert_lexic_to_eo(Even_new, Odd_new, DUM_DERI+1).  On the device the lexicographic
    * field IS the (even, odd) pair, so the two permutations fall away. */
-  if (g_proc_id == 0 && g_debug_level > 0) { printf("# Not using even/odd preconditioning!\n# Using CG!\n"); fflush(stdout); }
   sync_globals();
   up(6, Even); up(7, Odd);
-  CHK(tmb_gamma5(dev(4), dev(6))); CHK(tmb_gamma5(dev(5), dev(7)));
-  const int iter = cg_pair_Q_pm(max_iter, precision, rel_prec);
-  CHK(tmb_set_mu(-g_mu));
-  CHK(tmb_Q_full(dev(2), dev(3), dev(6), dev(7)));
-  CHK(tmb_set_mu(g_mu));
+  const int iter = invert_no_eo_dev(precision, max_iter, rel_prec);
   down(Even_new, 2); down(Odd_new, 3);
   return iter;
 }
+/* invert_eo.c:83-561.  With even/odd preconditioning (:126-318) the CG, MIXEDCG and RGMIXEDCG branches (:252-272, :225-232,
+ * :233-240); without it (:426-556) the CG branch (:527-541).  Every other solver_flag terminates with a message. */
 int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
               const double precision, const int max_iter, const int solver_flag, const int rel_prec,
               const int sub_evs_flag, const int even_odd_flag, const int no_extra_masses,
@@ -599,7 +604,7 @@ int invert_doublet_eo(spinor *const Even_new_s, spinor *const Odd_new_s, spinor 
 
 /* ---------------- include/tmLQCD.h facade (wrapper/lib_wrapper.c:77-370) ---------------- */
 #define MAX_OPS 16
-static struct { double kappa, mu, eps_sq, reached_prec; int max_iter, rel_prec, iterations; } ops[MAX_OPS];
+static struct { double kappa, mu, eps_sq, reached_prec, mcg_delta; int max_iter, rel_prec, iterations, solver, even_odd_flag; } ops[MAX_OPS];
 static int no_operators = 0, facade_up = 0, lat[4] = {0, 0, 0, 0};
 
 int tmLQCD_b200_set_lattice(int t, int lx, int ly, int lz) { lat[0] = t; lat[1] = lx; lat[2] = ly; lat[3] = lz; return 0; }
@@ -609,7 +614,23 @@ int tmLQCD_b200_add_operator(double kappa, double two_kappa_mu, double eps_sq, i
   ops[no_operators].kappa = kappa; ops[no_operators].mu = two_kappa_mu; ops[no_operators].eps_sq = eps_sq;
   ops[no_operators].max_iter = max_iter; ops[no_operators].rel_prec = rel_prec;
   ops[no_operators].iterations = 0; ops[no_operators].reached_prec = -1.;
+  /* init_operators' defaults (operator.c:102-103, :125): CG with even/odd preconditioning, mcg_delta = _default_mixcg_innereps */
+  ops[no_operators].solver = TMB_SOLVER_CG; ops[no_operators].even_odd_flag = 1; ops[no_operators].mcg_delta = 5.0e-5;
   return no_operators++;
+}
+/* the operator's Solver / UseEvenOdd / mcgdelta keys (read_input.l:1094-1133, :967-974, :835-838): what invert_eo implements
+ * here - CG, MIXEDCG, RGMIXEDCG with even/odd preconditioning, CG without */
+int tmLQCD_b200_set_operator_solver(int op_id, int solver_flag, int even_odd_flag, double mcg_delta) {
+  if (op_id < 0 || op_id >= no_operators) return -1;
+  const int eo_ok = solver_flag == TMB_SOLVER_CG || solver_flag == TMB_SOLVER_MIXEDCG || solver_flag == TMB_SOLVER_RGMIXEDCG;
+  if ((even_odd_flag && !eo_ok) || (!even_odd_flag && solver_flag != TMB_SOLVER_CG)) {
+    fprintf(stderr, "tmLQCD_b200_set_operator_solver: solver_flag=%d with even_odd_flag=%d is not implemented "
+                    "(CG, MIXEDCG, RGMIXEDCG with even/odd preconditioning; CG without)\n", solver_flag, even_odd_flag);
+    return -1;
+  }
+  ops[op_id].solver = solver_flag; ops[op_id].even_odd_flag = even_odd_flag ? 1 : 0;
+  if (mcg_delta > 0.) ops[op_id].mcg_delta = mcg_delta;
+  return 0;
 }
 int tmLQCD_b200_get_solver_info(int op_id, int *iterations, double *reached_prec) {
   if (op_id < 0 || op_id >= no_operators) return -1;
@@ -628,13 +649,19 @@ static int read_invert_input(const char *fn) {
   if (!f) return -1;
   char line[512], orig[512], key[128], val[128];
   int in_op = 0;
-  double kappa = 0., mu = 0., prec = 1e-14; int maxit = 1000, rel = 0;
+  double kappa = 0., mu = 0., prec = 1e-14, delta = 0.; int maxit = 1000, rel = 0, solver = TMB_SOLVER_CG, eo = 1, bad = 0;
   while (fgets(line, sizeof(line), f)) {
     char *h = strchr(line, '#'); if (h) *h = 0;
     strcpy(orig, line); /* file names keep their case */
     for (char *c = line; *c; c++) *c = (char)tolower((unsigned char)*c);
-    if (strstr(line, "beginoperator")) { in_op = 1; kappa = g_kappa; mu = 0.; prec = 1e-14; maxit = 1000; rel = 0; continue; }
-    if (strstr(line, "endoperator")) { if (in_op) tmLQCD_b200_add_operator(kappa, mu, prec, maxit, rel); in_op = 0; continue; }
+    if (strstr(line, "beginoperator")) { in_op = 1; kappa = g_kappa; mu = 0.; prec = 1e-14; maxit = 1000; rel = 0; solver = TMB_SOLVER_CG; eo = 1; delta = 0.; continue; }
+    if (strstr(line, "endoperator")) {
+      if (in_op) {
+        const int id = tmLQCD_b200_add_operator(kappa, mu, prec, maxit, rel);
+        if (id < 0 || tmLQCD_b200_set_operator_solver(id, solver, eo, delta) != 0) bad = 1;
+      }
+      in_op = 0; continue;
+    }
     if (sscanf(line, " %127[a-z0-9] = %127s", key, val) != 2) continue;
     if (!strcmp(key, "t")) lat[0] = atoi(val);
     else if (!strcmp(key, "l")) lat[1] = lat[2] = lat[3] = atoi(val);
@@ -649,7 +676,15 @@ static int read_invert_input(const char *fn) {
     else if (!strcmp(key, "2kappamu")) { if (in_op) mu = atof(val); else g_mu = atof(val); }
     else if (!strcmp(key, "solverprecision")) prec = atof(val);
     else if (!strcmp(key, "maxsolveriterations")) maxit = atoi(val);
-    else if (!strcmp(key, "userelativeprecision")) rel = !strcmp(val, "yes");
+    else if (!strcmp(key, "userelativeprecision") || !strcmp(key, "solverrelativeprecision")) rel = !strcmp(val, "yes"); /* read_input.l:824-833 */
+    else if (!strcmp(key, "useevenodd")) eo = !strcmp(val, "yes");
+    else if (!strcmp(key, "mcgdelta")) delta = atof(val);
+    else if (!strcmp(key, "solver")) { /* read_input.l:1094-1133 */
+      if (!strcmp(val, "cg")) solver = TMB_SOLVER_CG;
+      else if (!strcmp(val, "mixedcg")) solver = TMB_SOLVER_MIXEDCG;
+      else if (!strcmp(val, "rgmixedcg")) solver = TMB_SOLVER_RGMIXEDCG;
+      else { fprintf(stderr, "invert.input: Solver = %s is not implemented (cg, mixedcg, rgmixedcg)\n", val); bad = 1; }
+    }
     else if (!strcmp(key, "gaugeconfiginputfile") || !strcmp(key, "sourcefilename") || !strcmp(key, "propagatorprecision")) {
       char raw[128] = ""; /* read_input.l:399 (GaugeConfigInputFile), :372 (SourceFilename), :808-816 (PropagatorPrecision) */
       const char *eq = strchr(orig, '=');
@@ -661,13 +696,13 @@ static int read_invert_input(const char *fn) {
     }
   }
   fclose(f);
-  return 0;
+  return bad ? -2 : 0;
 }
 
 int tmLQCD_invert_init(int argc, char *argv[], const int verbose, const int external_id) {
   (void)argc; (void)argv; (void)external_id;
   g_debug_level = verbose;
-  if (lat[0] == 0) read_invert_input("invert.input"); /* lib_wrapper.c:96 reads the same file name */
+  if (lat[0] == 0 && read_invert_input("invert.input") == -2) return -1; /* lib_wrapper.c:96 reads the same file name */
   if (lat[0] == 0) { fprintf(stderr, "tmLQCD_invert_init: lattice size unknown (no invert.input, no tmLQCD_b200_set_lattice)\n"); return -1; }
   if (tmb_dropin_init(lat[0], lat[1], lat[2], lat[3], -1) != 0) { fprintf(stderr, "tmLQCD_invert_init: %s\n", tmb_last_error()); return -1; }
   facade_up = 1;
@@ -729,26 +764,45 @@ int tmLQCD_invert(double *const propagator, double *const source, const int op_i
   g_mu = ops[op_id].mu; g_kappa = ops[op_id].kappa; /* op_set_globals, operator.c:320 */
   boundary(g_kappa);
   sync_globals();
-  CHK(tmb_field_upload_lexic(dev(6), dev(7), source));
-  CHK(tmb_field_zero(dev(8))); CHK(tmb_field_zero(dev(9)));
-  int iter = tmb_invert_eo(dev(8), dev(9), dev(6), dev(7), ops[op_id].eps_sq, ops[op_id].max_iter, ops[op_id].rel_prec);
+  /* source pair in (be, bo), solution in (se, so) */
+  int be = 6, bo = 7, se = 8, so = 9, iter;
+  const double eps_sq = ops[op_id].eps_sq; const int max_iter = ops[op_id].max_iter, rel_prec = ops[op_id].rel_prec;
+  if (!ops[op_id].even_odd_flag) { /* invert_eo.c:426-556: the source is the CG's initial guess and gets overwritten: keep a copy */
+    be = 12; bo = 13; se = 2; so = 3;
+    CHK(tmb_field_upload_lexic(dev(be), dev(bo), source));
+    CHK(tmb_assign(dev(6), dev(be))); CHK(tmb_assign(dev(7), dev(bo)));
+    iter = invert_no_eo_dev(eps_sq, max_iter, rel_prec);
+  } else {
+    CHK(tmb_field_upload_lexic(dev(be), dev(bo), source));
+    CHK(tmb_field_zero(dev(se))); CHK(tmb_field_zero(dev(so)));
+    if (ops[op_id].solver == TMB_SOLVER_MIXEDCG) {
+      CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
+      iter = tmb_invert_eo_mixed(dev(se), dev(so), dev(be), dev(bo), eps_sq, max_iter, rel_prec);
+    } else if (ops[op_id].solver == TMB_SOLVER_RGMIXEDCG) {
+      CHK(tmb_set_mcg_delta(ops[op_id].mcg_delta));
+      iter = tmb_invert_eo_rgmixed(dev(se), dev(so), dev(be), dev(bo), eps_sq, max_iter, rel_prec);
+    } else
+      iter = tmb_invert_eo(dev(se), dev(so), dev(be), dev(bo), eps_sq, max_iter, rel_prec);
+  }
   if (iter < -1) die(__func__);
   ops[op_id].iterations = iter;
   /* reached_prec = |M x - b|^2 (operator.c:358, :379-384) */
   double n1 = 0., n2 = 0.;
-  CHK(tmb_M_full(dev(10), dev(11), dev(8), dev(9)));
-  CHK(tmb_diff(dev(10), dev(10), dev(6))); CHK(tmb_diff(dev(11), dev(11), dev(7)));
+  CHK(tmb_M_full(dev(10), dev(11), dev(se), dev(so)));
+  CHK(tmb_diff(dev(10), dev(10), dev(be))); CHK(tmb_diff(dev(11), dev(11), dev(bo)));
   CHK(tmb_square_norm(dev(10), &n1)); CHK(tmb_square_norm(dev(11), &n2));
   ops[op_id].reached_prec = n1 + n2;
-  if (g_kappa != 0.) { CHK(tmb_mul_r(dev(8), 2. * g_kappa, dev(8))); CHK(tmb_mul_r(dev(9), 2. * g_kappa, dev(9))); }
-  CHK(tmb_field_download_lexic(propagator, dev(8), dev(9)));
+  if (g_kappa != 0.) { CHK(tmb_mul_r(dev(se), 2. * g_kappa, dev(se))); CHK(tmb_mul_r(dev(so), 2. * g_kappa, dev(so))); }
+  CHK(tmb_field_download_lexic(propagator, dev(se), dev(so)));
   if (write_prop) { /* op_write_prop (operator.c:532-605): point-source naming, splitted files */
     char fn[600];
     spinor *pe = (spinor *)malloc((size_t)VOLUME / 2 * sizeof(spinor)), *po = (spinor *)malloc((size_t)VOLUME / 2 * sizeof(spinor));
     if (!pe || !po) { fprintf(stderr, "tmLQCD_invert: out of memory\n"); return -1; }
-    down(pe, 8); down(po, 9);
+    down(pe, se); down(po, so);
     sprintf(fn, "%s.%.4d.%.2d.%.2d.inverted", prop_basename, nstore, 0, 0);
-    const int st = tmb_write_propagator(fn, pe, po, prop_precision, ops[op_id].reached_prec, iter, "CG", 0);
+    /* the solver's name in inverter-info: io/params_construct_InverterInfo.c:57-79 knows "CG", the mixed solvers are "other" */
+    const int st = tmb_write_propagator(fn, pe, po, prop_precision, ops[op_id].reached_prec, iter,
+                                        ops[op_id].solver == TMB_SOLVER_CG ? "CG" : "other", 0);
     free(pe); free(po);
     if (st != 0) { fprintf(stderr, "tmLQCD_invert: writing %s failed\n", fn); return -1; }
   }
