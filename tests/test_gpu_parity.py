@@ -729,6 +729,7 @@ def test_tmLQCD_facade_solver_keys(oracle_lib, tmp_path, monkeypatch):
         assert lib.tmLQCD_finalise() == 0
     (tmp_path / "invert.input").write_text(text.replace("Solver = mixedcg", "Solver = bicgstab"))
     assert lib.tmLQCD_invert_init(0, None, 0, 0) == -1
+    assert lib.tmLQCD_b200_set_operator_solver(0, 1, 1, 0.) == -1  # nothing of the refused file stays behind
 
 
 def test_full_size_properties(oracle_lib):

@@ -702,7 +702,10 @@ static int read_invert_input(const char *fn) {
 int tmLQCD_invert_init(int argc, char *argv[], const int verbose, const int external_id) {
   (void)argc; (void)argv; (void)external_id;
   g_debug_level = verbose;
-  if (lat[0] == 0 && read_invert_input("invert.input") == -2) return -1; /* lib_wrapper.c:96 reads the same file name */
+  if (lat[0] == 0 && read_invert_input("invert.input") == -2) { /* lib_wrapper.c:96 reads the same file name */
+    no_operators = 0; lat[0] = 0; /* nothing of a refused input file stays behind */
+    return -1;
+  }
   if (lat[0] == 0) { fprintf(stderr, "tmLQCD_invert_init: lattice size unknown (no invert.input, no tmLQCD_b200_set_lattice)\n"); return -1; }
   if (tmb_dropin_init(lat[0], lat[1], lat[2], lat[3], -1) != 0) { fprintf(stderr, "tmLQCD_invert_init: %s\n", tmb_last_error()); return -1; }
   facade_up = 1;
