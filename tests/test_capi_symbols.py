@@ -67,3 +67,63 @@ def test_sass_is_sm100a_with_128bit_policy_loads():
     so = os.path.join(ROOT, "tmlqcd_b200", "lib", "libtmlqcd_b200.so")
     elf = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's OWN headers for this path, function by function: everything they declare is either exported by the
+# library under the same name or listed here with the reason it is outside SURVEY section 8.  Needs /root/reference
+# (this container); on the GPU box the test skips.
+REFERENCE_HEADERS = [
+    "operator/tm_operators.h", "operator/tm_operators_nd.h", "operator/tm_operators_nd_32.h", "operator/tm_operators_32.h",
+    "operator/Hopping_Matrix.h", "operator/Hopping_Matrix_32.h", "operator/Hopping_Matrix_nocom.h",
+    "operator/tm_times_Hopping_Matrix.h", "operator/tm_sub_Hopping_Matrix.h", "operator/D_psi.h", "gamma.h", "boundary.h",
+    "solver/cg_her.h", "solver/cg_her_nd.h", "solver/mixed_cg_her.h", "solver/rg_mixed_cg_her.h", "solver/rg_mixed_cg_her_nd.h",
+    "solver/monomial_solve.h", "solver/chrono_guess.h", "solver/solver_field.h", "invert_eo.h", "invert_doublet_eo.h",
+    "deriv_Sb.h", "measure_gauge_action.h", "include/tmLQCD.h", "monomial/det_monomial.h", "monomial/detratio_monomial.h",
+]
+NOT_ON_THE_PATH = {
+    "clover (c_sw > 0) operators, SURVEY 2 row 21": {
+        "H_eo_sw_ndpsi", "Msw_ee_inv_ndpsi", "Qsw_dagger_ndpsi", "Qsw_ndpsi", "Qsw_pm_ndbipsi", "Qsw_pm_ndpsi", "Qsw_tau1_sub_const_ndpsi",
+        "Qsw_pm_ndpsi_32", "invert_cloverdoublet_eo", "Block_Dsw_psi", "Block_Dsw_psi_32"},
+    "polynomial (PHMC / ndpoly monomial) and eigensolver forms of the doublet operator, SURVEY 2 rows 19, 20": {
+        "Q_tau1_sub_const_ndpsi", "Qtau1_P_ndpsi", "Qtm_pm_Ptm_pm_psi", "Qtm_pm_sub_const_nrm_psi", "Q_test_epsilon", "red_noise_nd",
+        "mul_one_pm_itau2", "Qtm_pm_ndbipsi", "Q_pm_ndpsi_32"},
+    "variants for the legacy GPU/ code and the spinorPrecWS preconditioner": {"Q_minus_psi_gpu", "Q_pm_psi_gpu", "Q_pm_psi_prec", "D_psi_prec"},
+    "declared or defined but called nowhere in the reference": {"Q_psi", "Q_pm_psi2"},
+    "float diagonal used only by solver/Msap.c (deflation, out of scope)": {
+        "assign_mul_one_pm_imu_inv_32", "mul_one_pm_imu_inv_32", "mul_one_pm_imu_sub_mul_32"},
+    "`_orphaned` helpers: called only from inside the OpenMP regions of operator/tm_operators_32.c, an object the library replaces": {
+        "gamma5_32_orphaned", "mul_one_pm_imu_inv_32_orphaned", "mul_one_pm_imu_sub_mul_gamma5_32_orphaned", "Hopping_Matrix_32_orphaned"},
+    "block (domain-decomposition / deflation) operators and their boundary helpers, SURVEY 2 row 21": {
+        "Block_D_psi", "Block_D_psi_32", "Block_Dtm_psi", "Block_Dtm_psi_32", "Block_H_psi", "Block_H_psi_32",
+        *{f"boundary_D_{i}" for i in range(8)}},
+    "other members of gamma.h (observables, overlap projectors)": {
+        "P_minus", "P_plus", "Proj", "gamma0", "gamma1", "gamma2", "gamma3", "gamma50", "gamma51", "gamma52", "gamma53"},
+    "multi-shift solves (cg_mms_tm*, SURVEY 2 row 20)": {"solve_mms_nd", "solve_mshift_oneflavour"},
+    "scratch allocators of the replaced solvers' other field types": {
+        "finalize_bisolver", "finalize_lsolver", "finalize_lsolver_32", "finalize_solver_32", "init_bisolver_field", "init_lsolver_field",
+        "init_lsolver_field_32", "init_solver_field_32"},
+    "gauge monomial (SURVEY 2 row 23)": {"measure_gauge_action"},
+}
+
+
+def test_every_function_of_the_reference_headers_is_exported_or_accounted_for(lib):
+    import re
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("needs the reference headers")
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "tmlqcd_b200", "lib", "libtmlqcd_b200.so")],
+                         capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if len(l.split()) == 3 and l.split()[1] in "TB"}
+    excluded = set().union(*NOT_ON_THE_PATH.values())
+    declared = set()
+    for h in REFERENCE_HEADERS:
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ref, h)).read(), flags=re.S)
+        for m in re.finditer(r"^[A-Za-z_][A-Za-z0-9_ \*]*?[ \*]([A-Za-z_][A-Za-z0-9_]*)\s*\(", text, flags=re.M):
+            if not m.group(0).lstrip().startswith(("typedef", "return", "#")):
+                declared.add(m.group(1))
+    assert len(declared) > 100, len(declared)   # the scan really sees the headers
+    missing = sorted(declared - exported - excluded)
+    assert not missing, f"declared by the reference's headers for this path, neither exported nor accounted for: {missing}"
+    stale = sorted(excluded & exported)
+    assert not stale, f"listed as out of scope but exported: {stale}"
