@@ -61,7 +61,7 @@ typedef struct {
 
 /* ---- globals of global.h / boundary.c / phmc.h that the path reads at call time ---- */
 extern int T, L, LX, LY, LZ, VOLUME, RAND, VOLUMEPLUSRAND;
-extern int g_update_gauge_copy, g_proc_id, g_debug_level, g_nproc, g_nproc_t;
+extern int g_update_gauge_copy, g_proc_id, g_debug_level, g_nproc, g_nproc_t, g_nproc_x, g_nproc_y, g_nproc_z; /* global.h:206 */
 extern double g_kappa, g_mu, g_mubar, g_epsbar, phmc_invmaxev;
 extern double X0, X1, X2, X3;
 extern _Complex double ka0, ka1, ka2, ka3, phase_0, phase_1, phase_2, phase_3;

@@ -194,7 +194,7 @@ DROPIN_API = {
     "tmLQCD_b200_set_operator_solver": (_i, [_i, _i, _i, _d]),
 }
 DROPIN_GLOBALS = ["T", "L", "LX", "LY", "LZ", "VOLUME", "RAND", "VOLUMEPLUSRAND", "g_update_gauge_copy", "g_proc_id",
-                  "g_debug_level", "g_nproc", "g_nproc_t", "g_kappa", "g_mu", "g_mubar", "g_epsbar", "phmc_invmaxev",
+                  "g_debug_level", "g_nproc", "g_nproc_t", "g_nproc_x", "g_nproc_y", "g_nproc_z", "g_kappa", "g_mu", "g_mubar", "g_epsbar", "phmc_invmaxev",
                   "X0", "X1", "X2", "X3", "ka0", "ka1", "ka2", "ka3", "phase_0", "phase_1", "phase_2", "phase_3",
                   "g_gauge_field", "mixcg_innereps", "mixcg_maxinnersolverit", "g_relative_precision_flag",
                   "GaugeInfo", "gauge_precision_read_flag", "g_disable_IO_checks", "g_beta", "g_rgi_C1"]

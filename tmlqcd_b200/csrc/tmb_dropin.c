@@ -24,7 +24,7 @@ int tmb_set_hopping_phases(const double ka_re_im[8]);
 
 /* ---- the reference's globals (global.h, boundary.c:34-38, phmc.h) ---- */
 int T, L, LX, LY, LZ, VOLUME, RAND, VOLUMEPLUSRAND;
-int g_update_gauge_copy = 1, g_proc_id = 0, g_debug_level = 0, g_nproc = 1, g_nproc_t = 1;
+int g_update_gauge_copy = 1, g_proc_id = 0, g_debug_level = 0, g_nproc = 1, g_nproc_t = 1, g_nproc_x = 1, g_nproc_y = 1, g_nproc_z = 1;
 double g_kappa = 0., g_mu = 0., g_mubar = 0., g_epsbar = 0., phmc_invmaxev = 1.;
 double X0 = 0., X1 = 0., X2 = 0., X3 = 0.;
 _Complex double ka0, ka1, ka2, ka3, phase_0, phase_1, phase_2, phase_3;
@@ -84,7 +84,7 @@ int tmb_dropin_finalize(void) {
 /* boundary.c:40-55 */
 void boundary(const double kappa) {
   const double PI_ = 3.14159265358979;
-  double x0 = X0 * PI_ / ((T)*g_nproc_t), x1 = X1 * PI_ / (LX), x2 = X2 * PI_ / (LY), x3 = X3 * PI_ / (LZ);
+  double x0 = X0 * PI_ / ((T)*g_nproc_t), x1 = X1 * PI_ / ((LX)*g_nproc_x), x2 = X2 * PI_ / ((LY)*g_nproc_y), x3 = X3 * PI_ / ((LZ)*g_nproc_z);
   ka0 = kappa * cexp(x0 * I); ka1 = kappa * cexp(x1 * I);
   ka2 = kappa * cexp(x2 * I); ka3 = kappa * cexp(x3 * I);
   phase_0 = -ka0; phase_1 = -ka1; phase_2 = -ka2; phase_3 = -ka3;
@@ -753,7 +753,7 @@ int tmLQCD_get_lat_params(tmLQCD_lat_params *p) {
 int tmLQCD_get_mpi_params(tmLQCD_mpi_params *p) {
   if (!facade_up) return -1;
   memset(p, 0, sizeof(*p));
-  p->nproc = g_nproc; p->nproc_t = g_nproc_t; p->nproc_x = p->nproc_y = p->nproc_z = 1;
+  p->nproc = g_nproc; p->nproc_t = g_nproc_t; p->nproc_x = g_nproc_x; p->nproc_y = g_nproc_y; p->nproc_z = g_nproc_z;
   p->proc_id = g_proc_id; p->cart_id = g_proc_id; p->time_rank = g_proc_id; p->omp_num_threads = 1;
   p->proc_coords[0] = g_proc_id;
   return 0;
