@@ -691,6 +691,20 @@ def main():
         cg["mixed_time_to_solution_s"] = time.perf_counter() - t0
         cg["mixed_count"] = itm
         cg["mixed_true_rr"] = dev.solver_stats()[1]
+        if world == 1:
+            # invert_eo's RGMIXEDCG branch (invert_eo.c:233-240): reliable-update CG, float inner loops, delta = operator.c:125's default
+            try:
+                dev.ck(lib.tmb_set_mcg_delta(5.0e-5))
+                dev.call("invert_eo_rgmixed", dEn, dOn, dE, dO, CG_EPS_SQ, CG_MAXITER, 1)
+                S.barrier()
+                t0 = time.perf_counter()
+                itg = dev.call("invert_eo_rgmixed", dEn, dOn, dE, dO, CG_EPS_SQ, CG_MAXITER, 1)
+                S.barrier()
+                cg["rgmixed_time_to_solution_s"] = time.perf_counter() - t0
+                cg["rgmixed_count"] = itg
+                cg["rgmixed_true_rr"] = dev.solver_stats()[1]
+            except Exception as e:  # pragma: no cover
+                cg["rgmixed_error"] = repr(e)[:200]
         # the same two solves with 12-real gauge compression (CompressionType COMPRESSION_12 of invert_eo)
         dev.ck(lib.tmb_set_compression(12))
         for name, fn in (("c12", "invert_eo"), ("c12_mixed", "invert_eo_mixed")):
