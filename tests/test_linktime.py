@@ -63,6 +63,8 @@ def _run(exe, tmp_path, tag, dims, par, gauge, srcs):
         a = np.frombuffer(buf, dtype=np.float64, count=n, offset=pos).copy(); pos += 8 * n
         return a
     res = {"invert_eo": (take_int(), take_f64(Vh * 24).reshape(Vh, 24), take_f64(Vh * 24).reshape(Vh, 24))}
+    for name in ("invert_eo_rg", "invert_eo_no_eo"):
+        res[name] = (take_int(), take_f64(Vh * 24).reshape(Vh, 24), take_f64(Vh * 24).reshape(Vh, 24))
     for name in ("doublet_cg", "doublet_rg"):
         res[name] = (take_int(), [take_f64(Vh * 24).reshape(Vh, 24) for _ in range(4)])
     for name in ("sd_cg", "sd_mixed", "sd_rg"):
@@ -87,6 +89,11 @@ def _check(exe, tmp_path, tol_solve, tol_force):
     it, en, on = r["invert_eo"]
     assert abs(it - int(base["invert_iters"])) <= 1
     assert rel_l2(en, base["invert_en"]) <= tol_solve and rel_l2(on, base["invert_on"]) <= tol_solve
+    # (1b) its RGMIXEDCG branch and its branch without even/odd preconditioning (cg_her on Q_pm_psi over VOLUME sites): the same system
+    for name in ("invert_eo_rg", "invert_eo_no_eo"):
+        it, en, on = r[name]
+        assert it > 0, name
+        assert rel_l2(en, base["invert_en"]) <= 1e-7 and rel_l2(on, base["invert_on"]) <= 1e-7, name
     # (2) invert_doublet_eo.c unmodified: CG -> cg_her_nd, RGMIXEDCG -> rg_mixed_cg_her_nd of the library
     it, sol = r["doublet_cg"]
     assert abs(it - int(base["invert_doublet_iters"])) <= 1
