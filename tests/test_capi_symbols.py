@@ -127,3 +127,15 @@ def test_every_function_of_the_reference_headers_is_exported_or_accounted_for(li
     assert not missing, f"declared by the reference's headers for this path, neither exported nor accounted for: {missing}"
     stale = sorted(excluded & exported)
     assert not stale, f"listed as out of scope but exported: {stale}"
+
+
+def test_public_headers_compile_as_c99_and_cpp(tmp_path):
+    """include/*.h alone, strict: the device-level header as C99 and as C++, the drop-in header as C99"""
+    inc = os.path.join(ROOT, "include")
+    cases = [("tmlqcd_b200.h", ["gcc", "-std=c99", "-pedantic-errors", "-Wall", "-Werror"], "a.c"),
+             ("tmlqcd_b200.h", ["g++", "-std=c++17", "-pedantic-errors", "-Wall", "-Werror"], "b.cpp"),
+             ("tmlqcd_b200_dropin.h", ["gcc", "-std=c99", "-pedantic-errors", "-Wall", "-Werror"], "c.c")]
+    for header, cmd, src in cases:
+        (tmp_path / src).write_text(f'#include "{header}"\nint main(void) {{ return 0; }}\n')
+        r = subprocess.run(cmd + ["-I", inc, "-c", str(tmp_path / src), "-o", str(tmp_path / (src + ".o"))], capture_output=True, text=True)
+        assert r.returncode == 0, (header, cmd[0], r.stderr[-1500:])
