@@ -43,7 +43,12 @@ int main(void) {
   fprintf(f, "# written by invert_b200.c\nT = 8\nL = 4\nkappa = 0.16\n2KappaMu = 0.0032\nThetaT = 1.0\n"
              "GaugeConfigInputFile = conf\nSourceFilename = prop_b200\n"
              "BeginOperator TMWILSON\n  kappa = 0.16\n  2KappaMu = 0.0032\n  SolverPrecision = 1e-18\n"
-             "  MaxSolverIterations = 2000\n  UseRelativePrecision = yes\n  PropagatorPrecision = 32\nEndOperator\n");
+             "  MaxSolverIterations = 2000\n  UseRelativePrecision = yes\n  PropagatorPrecision = 32\nEndOperator\n"
+             /* the keys that pick invert_eo's branch (read_input.l:1094-1133, :967-974; default: cg with even/odd preconditioning) */
+             "BeginOperator TMWILSON\n  kappa = 0.16\n  2KappaMu = 0.0032\n  Solver = rgmixedcg\n  mcgdelta = 1.e-4\n"
+             "  SolverPrecision = 1e-18\n  MaxSolverIterations = 2000\n  SolverRelativePrecision = yes\nEndOperator\n"
+             "BeginOperator TMWILSON\n  kappa = 0.16\n  2KappaMu = 0.0032\n  Solver = cg\n  UseEvenOdd = no\n"
+             "  SolverPrecision = 1e-18\n  MaxSolverIterations = 4000\n  SolverRelativePrecision = yes\nEndOperator\n");
   fclose(f);
   if (tmLQCD_invert_init(0, NULL, 1, 0) != 0) return 2;
   tmLQCD_lat_params lp;
@@ -81,6 +86,19 @@ int main(void) {
   for (size_t i = 0; i < (size_t)24 * VOLUME; i++) { const double x = ((double *)chk)[i] / (2. * g_kappa) - src[i]; d2 += x * x; }
   printf("# |D_psi(prop)/(2 kappa) - source|^2 = %e\n", d2);
   if (!(d2 <= 1e-16)) fails++;
+
+  /* the other two operators of invert.input - reliable-update mixed CG, and CG without even/odd preconditioning - give the same propagator */
+  double *prop2 = (double *)calloc((size_t)24 * VOLUME, sizeof(double));
+  for (int op = 1; op < (int)lp.no_operators; op++) {
+    if (tmLQCD_invert(prop2, src, op, 0) != 0) return 2;
+    tmLQCD_b200_get_solver_info(op, &iters, &reached);
+    double dd = 0., nn = 0.;
+    for (size_t i = 0; i < (size_t)24 * VOLUME; i++) { const double x = prop2[i] - prop[i]; dd += x * x; nn += prop[i] * prop[i]; }
+    printf("# operator %d (%s): %d iterations, squared residue %e, relative squared difference to operator 0: %e\n", op,
+           op == 1 ? "Solver = rgmixedcg" : "UseEvenOdd = no", iters, reached, dd / nn);
+    if (!(iters > 0 && dd / nn <= 1e-13)) fails++;
+  }
+  free(prop2);
 
   /* the propagator file (source.<nstore>.<ix>.<is>.inverted, operator.c:566) against the returned propagator */
   spinor *e = (spinor *)calloc((size_t)VOLUME / 2, sizeof(spinor)), *o = (spinor *)calloc((size_t)VOLUME / 2, sizeof(spinor));
