@@ -340,6 +340,10 @@ int tmb_monomial_acc(int id, double *dH) {
 }
 int tmb_monomial_info(int id, double *a, double *b, int *c, int *d, int *e) {
   NEED(); double e0, e1; int i0, i1, n; orc_mnl_info(id, &e0, &e1, &i0, &i1, &n);
-  if (a) *a = e0; if (b) *b = e1; if (c) *c = i0; if (d) *d = i1; if (e) *e = n;
+  if (a) *a = e0;
+  if (b) *b = e1;
+  if (c) *c = i0;
+  if (d) *d = i1;
+  if (e) *e = n;
   return 0;
 }
