@@ -524,7 +524,7 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
   if (solver_flag == TMB_SOLVER_MIXEDCG) { /* invert_eo.c:225-232; mixed_cg_her zeroes the guess (:108) */
     CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
     iter = tmb_invert_eo_mixed(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
-  } else if (solver_flag == TMB_SOLVER_RGMIXEDCG) { /* invert_eo.c:233-240; rg_mixed_cg_her starts from zero (:226) */
+  } else if (solver_flag == TMB_SOLVER_RGMIXEDCG) { /* invert_eo.c:233-240; rg_mixed_cg_her.c:243-245 always starts from a zero guess */
     CHK(tmb_set_mcg_delta((double)solver_params.mcg_delta));
     iter = tmb_invert_eo_rgmixed(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
   } else
