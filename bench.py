@@ -692,7 +692,7 @@ def main():
         cg["mixed_count"] = itm
         cg["mixed_true_rr"] = dev.solver_stats()[1]
         if world == 1:
-            # invert_eo's RGMIXEDCG branch (invert_eo.c:233-240): reliable-update CG, float inner loops, delta = operator.c:125's default
+            # invert_eo's RGMIXEDCG branch (invert_eo.c:242-249): reliable-update CG, float inner loops, delta = operator.c:125's default
             try:
                 dev.ck(lib.tmb_set_mcg_delta(5.0e-5))
                 dev.call("invert_eo_rgmixed", dEn, dOn, dE, dO, CG_EPS_SQ, CG_MAXITER, 1)

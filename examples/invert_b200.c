@@ -44,7 +44,7 @@ int main(void) {
              "GaugeConfigInputFile = conf\nSourceFilename = prop_b200\n"
              "BeginOperator TMWILSON\n  kappa = 0.16\n  2KappaMu = 0.0032\n  SolverPrecision = 1e-18\n"
              "  MaxSolverIterations = 2000\n  UseRelativePrecision = yes\n  PropagatorPrecision = 32\nEndOperator\n"
-             /* the keys that pick invert_eo's branch (read_input.l:1094-1133, :967-974; default: cg with even/odd preconditioning) */
+             /* the keys that pick invert_eo's branch (read_input.l:1108-1139, :967-974; default: cg with even/odd preconditioning) */
              "BeginOperator TMWILSON\n  kappa = 0.16\n  2KappaMu = 0.0032\n  Solver = rgmixedcg\n  mcgdelta = 1.e-4\n"
              "  SolverPrecision = 1e-18\n  MaxSolverIterations = 2000\n  SolverRelativePrecision = yes\nEndOperator\n"
              "BeginOperator TMWILSON\n  kappa = 0.16\n  2KappaMu = 0.0032\n  Solver = cg\n  UseEvenOdd = no\n"

@@ -188,10 +188,10 @@ int tmb_field32_download_lexic(float *host_lexic32, const void *even32, const vo
 int tmb_set_mixcg(double innereps, int maxinnersolverit);        /* mixcg_innereps / mixcg_maxinnersolverit, default_input_values.h:193 */
 /* mixed_cg_her(P,Q,params,max_iter,eps_sq,rel_prec,VOLUME/2,&Qtm_pm_psi,&Qtm_pm_psi_32): solver/mixed_cg_her.c:65 */
 int tmb_mixed_cg_her(void *P, const void *Q, int max_iter, double eps_sq, int rel_prec);
-/* invert_eo with solver_flag == MIXEDCG: invert_eo.c:225-232 */
+/* invert_eo with solver_flag == MIXEDCG: invert_eo.c:234-241 */
 int tmb_invert_eo_mixed(void *even_new, void *odd_new, const void *even, const void *odd, double precision,
                         int max_iter, int rel_prec);
-/* invert_eo with solver_flag == RGMIXEDCG: invert_eo.c:233-240 (delta of the reliable updates: tmb_set_mcg_delta) */
+/* invert_eo with solver_flag == RGMIXEDCG: invert_eo.c:242-249 (delta of the reliable updates: tmb_set_mcg_delta) */
 int tmb_invert_eo_rgmixed(void *even_new, void *odd_new, const void *even, const void *odd, double precision,
                           int max_iter, int rel_prec);
 

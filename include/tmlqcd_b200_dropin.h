@@ -121,8 +121,8 @@ void convert_eo_to_lexic(spinor *const P, spinor *const s, spinor *const r);
 void convert_lexic_to_eo(spinor *const s, spinor *const r, spinor *const P);
 /* solver/cg_her.c:62: f == Qtm_pm_psi on VOLUME/2 sites and f == Q_pm_psi on VOLUME sites run on device-resident fields;
  * any other f runs the same recurrence with f applied through its host-pointer entry point.
- * invert_eo.c:83: with even/odd preconditioning solver_flag CG (:252-272), MIXEDCG (:225-232), RGMIXEDCG (:233-240; delta =
- * solver_params.mcg_delta); without it (even_odd_flag == 0) CG (:527-541).  Other flags terminate with a message. */
+ * invert_eo.c:83: with even/odd preconditioning solver_flag CG (:250-276), MIXEDCG (:234-241), RGMIXEDCG (:242-249; delta =
+ * solver_params.mcg_delta); without it (even_odd_flag == 0) CG (:505-545).  Other flags terminate with a message. */
 int cg_her(spinor *const P, spinor *const Q, const int max_iter, double eps_sq, const int rel_prec, const int N, matrix_mult f);
 int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
               const double precision, const int max_iter, const int solver_flag, const int rel_prec,
@@ -293,7 +293,7 @@ int tmLQCD_b200_set_lattice(int t, int lx, int ly, int lz);
 int tmLQCD_b200_add_operator(double kappa, double two_kappa_mu, double eps_sq, int max_iter, int rel_prec);
 int tmLQCD_b200_set_theta(double x0, double x1, double x2, double x3);
 int tmLQCD_b200_get_solver_info(int op_id, int *iterations, double *reached_prec);
-/* the operator's Solver / UseEvenOdd / mcgdelta keys (read_input.l:1094-1133, :967-974, :835-838; defaults operator.c:102-125:
+/* the operator's Solver / UseEvenOdd / mcgdelta keys (read_input.l:1108-1139, :967-974, :835-838; defaults operator.c:102-125:
  * CG, even/odd preconditioning, 5e-5): TMB_SOLVER_CG / _MIXEDCG / _RGMIXEDCG with even_odd_flag != 0, TMB_SOLVER_CG with 0;
  * mcg_delta <= 0 keeps the current value.  -1 for a combination invert_eo does not implement here. */
 int tmLQCD_b200_set_operator_solver(int op_id, int solver_flag, int even_odd_flag, double mcg_delta);

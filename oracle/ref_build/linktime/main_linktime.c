@@ -96,8 +96,8 @@ int main(int argc, char **argv) {
   /* (1) unmodified invert_eo.c, CG branch: per-call operators + cg_her(&Qtm_pm_psi) of the library */
   it = invert_eo(sol[0], sol[1], src[0], src[1], 1e-20, 1000, CG, 1, 0, 1, 0, NULL, sp, 0, NO_EXT_INV, 0, NO_COMPRESSION);
   wr(out, &it, sizeof(int)); wr(out, sol[0], fb); wr(out, sol[1], fb);
-  /* (1b) the same file's RGMIXEDCG branch (:233-240: the library's rg_mixed_cg_her must recognise the executable's
-   *      &Qtm_pm_psi / &Qtm_pm_psi_32) and its branch WITHOUT even/odd preconditioning (:426-556: convert_eo_to_lexic, gamma5,
+  /* (1b) the same file's RGMIXEDCG branch (:242-249: the library's rg_mixed_cg_her must recognise the executable's
+   *      &Qtm_pm_psi / &Qtm_pm_psi_32) and its branch WITHOUT even/odd preconditioning (:364-558: convert_eo_to_lexic, gamma5,
    *      cg_her(.., VOLUME, &Q_pm_psi) - the library's CG on (even, odd) pairs, found by f == Q_pm_psi -, Q_minus_psi) */
   for (int pass = 0; pass < 2; pass++) {
     memset(sol[0], 0, fb); memset(sol[1], 0, fb);

@@ -215,7 +215,7 @@ int ref_invert_eo(double *even_new, double *odd_new, double *even, double *odd,
                    rel_prec, 0, 1, 0, NULL, sp, 0, NO_EXT_INV, 0, NO_COMPRESSION);
 }
 /* the same with every flag of the scoped branches open: solver_flag CG / MIXEDCG / RGMIXEDCG (delta = solver_params.mcg_delta
- * of the reliable updates), even_odd_flag 0 = the full-lattice branch (invert_eo.c:426-556: cg_her on Q_pm_psi, VOLUME sites) */
+ * of the reliable updates), even_odd_flag 0 = the full-lattice branch (invert_eo.c:364-558: cg_her on Q_pm_psi, VOLUME sites) */
 int ref_invert_eo_flags(double *even_new, double *odd_new, double *even, double *odd, double precision, int max_iter,
                         int rel_prec, int solver_flag, int even_odd_flag, double delta) {
   solver_params_t sp;

@@ -141,8 +141,8 @@ def test_inversions_with_reference_signatures(dropin):
 
 
 def test_invert_eo_remaining_branches(dropin):
-    """invert_eo's MIXEDCG and RGMIXEDCG branches (invert_eo.c:225-240) and its branch WITHOUT even/odd preconditioning
-    (:426-556: cg_her on Q_pm_psi over VOLUME sites, the source as initial guess, then Q_minus_psi): all of them solve the
+    """invert_eo's MIXEDCG and RGMIXEDCG branches (invert_eo.c:234-249) and its branch WITHOUT even/odd preconditioning
+    (:364-558: cg_her on Q_pm_psi over VOLUME sites, the source as initial guess, then Q_minus_psi): all of them solve the
     system of the CG branch, whose solution by the unmodified reference is in the fixture.  Then cg_her(N = VOLUME,
     f = Q_pm_psi) - the recurrence on (even, odd) pairs of device fields - against the generic path (same recurrence, f
     through its host-pointer entry point) and against the defining equation."""

@@ -681,7 +681,7 @@ def test_tmLQCD_facade(oracle_lib):
 
 
 def test_tmLQCD_facade_solver_keys(oracle_lib, tmp_path, monkeypatch):
-    """the operator block's Solver / UseEvenOdd / mcgdelta / SolverRelativePrecision keys of invert.input (read_input.l:1094-1133,
+    """the operator block's Solver / UseEvenOdd / mcgdelta / SolverRelativePrecision keys of invert.input (read_input.l:1108-1139,
     :967-974, :835-838, :824-833; defaults operator.c:102-125) reach invert_eo's branches through tmLQCD_invert (op_invert,
     operator.c:349-355): every implemented combination gives the propagator of the CG branch; an unimplemented solver is
     refused at tmLQCD_invert_init instead of silently running CG"""

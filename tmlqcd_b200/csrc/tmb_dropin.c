@@ -277,7 +277,7 @@ double measure_plaquette(const su3 **const gf) {
  * way) runs entirely on the device.  Any other f is applied through its own host-pointer
  * entry point with the same recurrence driven from here - correct, but every step crosses
  * PCIe; it exists so that the symbol is a complete replacement. */
-/* cg_her on the full lattice with f == Q_pm_psi (the non-even/odd inversions: invert_eo.c:527-541, the det monomial without
+/* cg_her on the full lattice with f == Q_pm_psi (the non-even/odd inversions: invert_eo.c:505-545, the det monomial without
  * even/odd preconditioning): the recurrence of cg_her.c:80-127 on (even, odd) PAIRS of device fields.  A lexicographic field
  * is exactly such a pair on the device (the permutation is part of the transfer), Q_pm_psi = Q_+ Q_- is two M_full-type
  * launches per parity with g_mu flipped in between (tm_operators.c:380-388); only the scalars cross PCIe.
@@ -479,7 +479,7 @@ static int invert_no_eo_dev(const double precision, const int max_iter, const in
 }
 static int invert_no_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
                         const double precision, const int max_iter, const int rel_prec) {
-  /* invert_eo.c:428, :527-541, :555: convert_eo_to_lexic(DUM_DERI, Even, Odd); gamma5(DUM_DERI+1, DUM_DERI);
+  /* invert_eo.c:367, :505-545, :558: convert_eo_to_lexic(DUM_DERI, Even, Odd); gamma5(DUM_DERI+1, DUM_DERI);
    * cg_her(DUM_DERI, DUM_DERI+1, .., VOLUME, &Q_pm_psi) - the source is its own initial guess -;
    * Q_minus_psi(DUM_DERI+1, DUM_DERI); convert_lexic_to_eo(Even_new, Odd_new, DUM_DERI+1).  On the device the lexicographic
    * field IS the (even, odd) pair, so the two permutations fall away. */
@@ -489,8 +489,8 @@ static int invert_no_eo(spinor *const Even_new, spinor *const Odd_new, spinor *c
   down(Even_new, 2); down(Odd_new, 3);
   return iter;
 }
-/* invert_eo.c:83-561.  With even/odd preconditioning (:126-318) the CG, MIXEDCG and RGMIXEDCG branches (:252-272, :225-232,
- * :233-240); without it (:426-556) the CG branch (:527-541).  Every other solver_flag terminates with a message. */
+/* invert_eo.c:83-561.  With even/odd preconditioning (:126-318) the CG, MIXEDCG and RGMIXEDCG branches (:250-276, :234-241,
+ * :242-249); without it (:364-558) the CG branch (:505-545).  Every other solver_flag terminates with a message. */
 int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even, spinor *const Odd,
               const double precision, const int max_iter, const int solver_flag, const int rel_prec,
               const int sub_evs_flag, const int even_odd_flag, const int no_extra_masses,
@@ -521,10 +521,10 @@ int invert_eo(spinor *const Even_new, spinor *const Odd_new, spinor *const Even,
   up(6, Even); up(7, Odd); up(9, Odd_new); /* Odd_new is the CG's initial guess (cg_her.c:84) */
   const double t2 = wall();
   int iter;
-  if (solver_flag == TMB_SOLVER_MIXEDCG) { /* invert_eo.c:225-232; mixed_cg_her zeroes the guess (:108) */
+  if (solver_flag == TMB_SOLVER_MIXEDCG) { /* invert_eo.c:234-241; mixed_cg_her zeroes the guess (:108) */
     CHK(tmb_set_mixcg(mixcg_innereps, mixcg_maxinnersolverit));
     iter = tmb_invert_eo_mixed(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
-  } else if (solver_flag == TMB_SOLVER_RGMIXEDCG) { /* invert_eo.c:233-240; rg_mixed_cg_her.c:243-245 always starts from a zero guess */
+  } else if (solver_flag == TMB_SOLVER_RGMIXEDCG) { /* invert_eo.c:242-249; rg_mixed_cg_her.c:243-245 always starts from a zero guess */
     CHK(tmb_set_mcg_delta((double)solver_params.mcg_delta));
     iter = tmb_invert_eo_rgmixed(dev(8), dev(9), dev(6), dev(7), precision, max_iter, rel_prec);
   } else
@@ -618,7 +618,7 @@ int tmLQCD_b200_add_operator(double kappa, double two_kappa_mu, double eps_sq, i
   ops[no_operators].solver = TMB_SOLVER_CG; ops[no_operators].even_odd_flag = 1; ops[no_operators].mcg_delta = 5.0e-5;
   return no_operators++;
 }
-/* the operator's Solver / UseEvenOdd / mcgdelta keys (read_input.l:1094-1133, :967-974, :835-838): what invert_eo implements
+/* the operator's Solver / UseEvenOdd / mcgdelta keys (read_input.l:1108-1139, :967-974, :835-838): what invert_eo implements
  * here - CG, MIXEDCG, RGMIXEDCG with even/odd preconditioning, CG without */
 int tmLQCD_b200_set_operator_solver(int op_id, int solver_flag, int even_odd_flag, double mcg_delta) {
   if (op_id < 0 || op_id >= no_operators) return -1;
@@ -679,7 +679,7 @@ static int read_invert_input(const char *fn) {
     else if (!strcmp(key, "userelativeprecision") || !strcmp(key, "solverrelativeprecision")) rel = !strcmp(val, "yes"); /* read_input.l:824-833 */
     else if (!strcmp(key, "useevenodd")) eo = !strcmp(val, "yes");
     else if (!strcmp(key, "mcgdelta")) delta = atof(val);
-    else if (!strcmp(key, "solver")) { /* read_input.l:1094-1133 */
+    else if (!strcmp(key, "solver")) { /* read_input.l:1108-1139 */
       if (!strcmp(val, "cg")) solver = TMB_SOLVER_CG;
       else if (!strcmp(val, "mixedcg")) solver = TMB_SOLVER_MIXEDCG;
       else if (!strcmp(val, "rgmixedcg")) solver = TMB_SOLVER_RGMIXEDCG;
@@ -770,7 +770,7 @@ int tmLQCD_invert(double *const propagator, double *const source, const int op_i
   /* source pair in (be, bo), solution in (se, so) */
   int be = 6, bo = 7, se = 8, so = 9, iter;
   const double eps_sq = ops[op_id].eps_sq; const int max_iter = ops[op_id].max_iter, rel_prec = ops[op_id].rel_prec;
-  if (!ops[op_id].even_odd_flag) { /* invert_eo.c:426-556: the source is the CG's initial guess and gets overwritten: keep a copy */
+  if (!ops[op_id].even_odd_flag) { /* invert_eo.c:364-558: the source is the CG's initial guess and gets overwritten: keep a copy */
     be = 12; bo = 13; se = 2; so = 3;
     CHK(tmb_field_upload_lexic(dev(be), dev(bo), source));
     CHK(tmb_assign(dev(6), dev(be))); CHK(tmb_assign(dev(7), dev(bo)));
