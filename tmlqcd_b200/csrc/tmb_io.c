@@ -9,10 +9,10 @@
  *   u32 BE magic 0x456789AB | u16 BE version 1 | u16 BE flags (bit 15 MB, bit 14 ME) | u64 BE data length |
  *   128-byte NUL-padded type string
  * followed by the data, zero-padded to a multiple of 8 bytes.  Everything inside the records restates the
- * reference: record sequence and XML of io/gauge_write.c:22-60, io/utils_write_{xlf,ildg_format,checksum}.c,
+ * reference: record sequence and XML of io/gauge_write.c:22-58, io/utils_write_{xlf,ildg_format,checksum}.c,
  * payload order and endianness of io/gauge_{read,write}_binary.c (sites t,z,y,x slowest to fastest, links
  * x,y,z,t, big-endian IEEE), io/spinor_{read,write}_binary.c, the SciDAC checksum of io/dml.c:49-60 with the
- * zlib CRC-32 of io/DML_crc32.c, and the checks and return codes of io/gauge_read.c:30-206, io/spinor_read.c.
+ * zlib CRC-32 of io/DML_crc32.c, and the checks and return codes of io/gauge_read.c:29-194, io/spinor_read.c.
  * No arithmetic on fields happens here; nothing in this file touches the GPU.
  */
 #include <complex.h>
@@ -141,7 +141,7 @@ static int parse_ildgformat_xml(char *message, ildg_format *f) { /* io/utils_par
   }
   return n >= 5;
 }
-static int write_checksum_record(FILE *fp, const DML_Checksum *cs, const char *name) { /* io/utils_write_checksum.c:22-50 */
+static int write_checksum_record(FILE *fp, const DML_Checksum *cs, const char *name) { /* io/utils_write_checksum.c:22-49 */
   char m[512];
   snprintf(m, sizeof(m), "<?xml version=\"1.0\" encoding=\"UTF-8\"?>\n<scidacChecksum>\n  <version>1.0</version>\n"
                          "  <suma>%08x</suma>\n  <sumb>%08x</sumb>\n</scidacChecksum>", cs->suma, cs->sumb);
@@ -164,7 +164,7 @@ paramsXlfInfo *construct_paramsXlfInfo(double const plaq, int const counter) {
   return info;
 }
 
-/* io/gauge_write.c:22-60 with io/gauge_write_binary.c:125-215 (single process) */
+/* io/gauge_write.c:22-58 with io/gauge_write_binary.c:125-215 (single process) */
 int write_gauge_field(char *filename, int prec, paramsXlfInfo const *xlf) {
   if (prec != 64 && prec != 32) { fprintf(stderr, "write_gauge_field: precision must be 64 or 32\n"); return -1; }
   if (!g_gauge_field) { fprintf(stderr, "write_gauge_field: no gauge field (tmb_dropin_init first)\n"); return -1; }
@@ -174,7 +174,7 @@ int write_gauge_field(char *filename, int prec, paramsXlfInfo const *xlf) {
   crc_init();
   char m[1024];
   int st = 0;
-  if (xlf) { /* io/utils_write_xlf.c:22-70 */
+  if (xlf) { /* io/utils_write_xlf.c:22-64 */
     if (xlf->kappa != 0.0)
       snprintf(m, sizeof(m), "plaquette = %14.12f\n trajectory nr = %d\n beta = %.12f, kappa = %.12f, mu = %.12f, c2_rec = %f\n"
                              " time = %ld\n hmcversion = %s\n mubar = %.12f\n epsilonbar = %.12f\n date = %s",
@@ -217,7 +217,7 @@ int write_gauge_field(char *filename, int prec, paramsXlfInfo const *xlf) {
   return st ? -2 : 0;
 }
 
-/* io/gauge_read.c:30-206 with io/gauge_read_binary.c:125-215 */
+/* io/gauge_read.c:29-194 with io/gauge_read_binary.c:125-215 */
 int read_gauge_field(char *filename, su3 **const gf) {
   FILE *fp = fopen(filename, "r");
   if (!fp) {
